@@ -1,0 +1,167 @@
+/*
+ * citadels_b200.h -- C ABI of the B200-native Citadels rollout engine.
+ *
+ * This is the drop-in boundary for the reference's hot path: legal-option
+ * enumeration + state transition + random playout.  Every entry point names the reference
+ * interface it replaces (paths relative to the reference repository root).  All functions return
+ * a ctd_status (0 = OK).  Pointer arguments are HOST pointers unless the name ends in `_dev`
+ * (device pointers on the handle's device).  No callbacks, no torch types.
+ *
+ * A handle owns `capacity` game slots in HBM.  A slot holds one 256-byte packed game record
+ * (`ctd_state`, layout below) -- the equivalent of one reference `Game` object
+ * (game/game.py:16-24, :522-540) without the CFR knowledge block.
+ */
+#ifndef CITADELS_B200_H
+#define CITADELS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ctd_engine ctd_engine;
+
+typedef enum {
+  CTD_OK = 0,
+  CTD_EARG = 1,   /* bad argument (null pointer, n > capacity, ...) */
+  CTD_ECUDA = 2,  /* CUDA runtime error; see ctd_last_error() */
+  CTD_ECAP = 3,   /* a fixed-size buffer was too small (options stride, tape) */
+  CTD_ENOMEM = 4
+} ctd_status;
+
+/* rulesets: which variant of each of the 8 ranks is in play (game/config.py:83-91) */
+#define CTD_RULESET_PRESET 0  /* Witch Spy Wizard King Abbot Alchemist Navigator Warlord, game/game.py:479-486 */
+#define CTD_RULESET_CLASSIC 1 /* Assassin Thief Magician King Bishop Merchant Architect Warlord */
+
+/* Packed game record.  Bytes [0,228) are reference-visible state (tests compare them bit for bit with a
+ * dump of the reference Game); bytes [228,256) are engine-private. */
+#define CTD_STATE_BYTES 256
+#define CTD_STATE_VISIBLE_BYTES 228
+typedef struct ctd_state {
+  uint8_t arena[128];    /* card codes, 26 ordered containers back to back: per seat hand, buildings,
+                            museum_cards, just_drawn_cards (game/agent.py:12-20); then deck, discard_deck.
+                            code 0..39 = type_ID; 40..43 = Magic School with suit trade/war/religion/lord */
+  uint8_t off[28];       /* off[c] = start of container c in arena; off[26] = total cards */
+  int8_t gold[6];        /* Agent.gold (may go negative) */
+  uint8_t role[6];       /* 0..7 rank; 8 = None; 9 = "Bewitched" */
+  int8_t replicas[6];    /* Agent.replicas (False == 0) */
+  uint8_t pflags[6];     /* bit0 can_use_lighthouse, bit1 first_to_7, bit2 witch */
+  uint8_t rprops[8];     /* RolePropery per rank: bit0 dead, bits1-2 warrant, bit3 possessed, bit4 robbed,
+                            bits5-6 blackmail (0 None, 1 Real, 2 Fake) */
+  uint8_t variant[8];    /* which of the 3 names of rank r is in game.roles */
+  uint8_t order[6];      /* turn_orders_for_roles */
+  uint8_t used_roles[6]; /* used_roles, value+1 (0 = -1 "Bewitched") */
+  uint8_t used_len;
+  uint8_t rtc_mask;      /* roles_to_choose_from */
+  uint8_t state;         /* GameState.state 0..10 */
+  uint8_t player;        /* GameState.player_id */
+  uint8_t done;          /* already_done_moves flags: smithy, lab, magic_school, museum, character_ability,
+                            begged, take_gold */
+  uint8_t done_builds;   /* low nibble #trade_building, high nibble #non_trade_building */
+  uint8_t next_player;   /* next_gamestate.player_id (only inside an interrupt state) */
+  uint8_t next_mode;     /* 0 none, 1 same done-moves list, 2 reset to [character_ability], 3 empty */
+  uint8_t crown;         /* seat holding the crown */
+  uint8_t gflags;        /* bit0 ending, bit1 terminal */
+  int8_t winner;         /* -1 until terminal */
+  uint8_t wiz_target;    /* seat whose hand the acting Wizard looked at this round, 0xFF none */
+  int8_t points[6];      /* Game.points at terminal */
+  uint8_t warrant_building;
+  uint8_t ruleset;
+  /* ---- engine-private ---- */
+  uint8_t err;           /* CTD_ERR_* flags */
+  uint8_t pad0[3];
+  uint32_t rng_draws;    /* Philox draws consumed by this game so far */
+  uint32_t tape_pos;     /* chance-tape cursor (replay mode) */
+  uint32_t steps;        /* env steps applied to this slot */
+  uint8_t pad1[12];
+} ctd_state;
+
+#define CTD_ERR_OVERFLOW 1   /* a container exceeded its on-chip capacity */
+#define CTD_ERR_REF_RAISE 2  /* the reference would raise here (KeyError/IndexError/...) */
+#define CTD_ERR_UNIMPL 4     /* option kind outside the built tiers */
+#define CTD_ERR_TAPE 8       /* chance tape exhausted or malformed */
+#define CTD_ERR_MAXSTEPS 16  /* playout hit max_steps before terminal */
+
+/* 64-bit option descriptor == one reference `option(name, **attrs)` (game/option.py:8-18).
+ * kind is the index into the reference's action list, game/option.py:34-45. */
+typedef uint64_t ctd_option;
+#define CTD_OPT_KIND(d) ((int)((d) & 0x3F))
+#define CTD_OPT_PERP(d) ((int)(((d) >> 6) & 7))
+#define CTD_OPT_TARGET(d) ((int)(((d) >> 9) & 7) - 1)
+#define CTD_OPT_CARD_A(d) ((int)(((d) >> 12) & 0x3F) - 1)
+#define CTD_OPT_CARD_B(d) ((int)(((d) >> 18) & 0x3F) - 1)
+#define CTD_OPT_RANK(d) ((int)(((d) >> 24) & 0xF) - 1)
+#define CTD_OPT_NAMED(d) ((int)(((d) >> 28) & 0xF) - 1) /* index into game/option.py:69-83 */
+#define CTD_OPT_REPLICA(d) ((int)((((d) >> 32) & 0xF) ^ 8) - 8)
+#define CTD_OPT_BUILD(d) ((int)(((d) >> 36) & 1))
+#define CTD_OPT_NEXT_WITCH(d) ((int)(((d) >> 37) & 1))
+#define CTD_OPT_CROWN(d) ((int)(((d) >> 38) & 1))
+#define CTD_OPT_COUNT(d) ((int)(((d) >> 39) & 0x3F))
+#define CTD_OPT_R(d) ((int)(((d) >> 45) & 0x3F))
+#define CTD_OPT_J(d) ((int)(((d) >> 51) & 0x3FF))
+
+/* aggregate outcome statistics of a batch of playouts (what the reference's drivers tabulate from
+ * compare_to_random.py:24-37 style loops) */
+typedef struct ctd_playout_stats {
+  uint64_t games;
+  uint64_t steps;         /* sum of env steps */
+  uint64_t steps_sq;
+  uint64_t wins[6];
+  int64_t points_sum[6];
+  uint64_t points_sq[6];
+  uint64_t errors;        /* games that ended with err != 0 */
+  uint64_t max_steps;     /* longest game */
+} ctd_playout_stats;
+
+/* ---- lifetime ---- */
+ctd_status ctd_create(int device, uint32_t capacity, ctd_engine** out);
+void ctd_destroy(ctd_engine* e);
+const char* ctd_last_error(const ctd_engine* e);
+ctd_status ctd_sync(ctd_engine* e);
+/* use an existing CUDA stream (cudaStream_t as void*); default is a stream the engine owns */
+ctd_status ctd_set_stream(ctd_engine* e, void* cuda_stream);
+
+/* ---- state in / out ---- */
+/* run_utils.create_game (run_utils.py:20-27): Game(preset=True) + setup_round() for slots [0,n);
+ * game i is keyed by (seed, first_gid + i). */
+ctd_status ctd_reset(ctd_engine* e, uint32_t n, uint64_t seed, uint64_t first_gid, int ruleset);
+/* copy.deepcopy(game) in / out of the engine (run_utils.py:36,40): n records of CTD_STATE_BYTES */
+ctd_status ctd_load_states(ctd_engine* e, uint32_t first_slot, uint32_t n, const ctd_state* states);
+ctd_status ctd_store_states(ctd_engine* e, uint32_t first_slot, uint32_t n, ctd_state* states);
+/* device pointer to slot 0 (for zero-copy interop, e.g. torch.from_blob) */
+ctd_status ctd_states_dev(ctd_engine* e, void** dev_ptr);
+
+/* replay mode: per-slot chance tapes (recorded shuffles, new[k] = old[tape[k]]); tape_off has n+1 entries.
+ * Slots with a tape draw chance from it instead of Philox.  n == 0 clears all tapes. */
+ctd_status ctd_set_tapes(ctd_engine* e, uint32_t n, const uint8_t* tape, const uint32_t* tape_off);
+
+/* ---- the hot path ---- */
+/* Game.get_options_from_state / Agent.get_options (game/game.py:415-418, game/agent.py:50-83) for slots
+ * [0,n): opts[i*stride .. i*stride+counts[i]) in the reference's list order.  Terminal slots report 0.
+ * counts[i] > stride => only the first `stride` were written (status CTD_ECAP). */
+ctd_status ctd_enumerate(ctd_engine* e, uint32_t n, ctd_option* opts, uint32_t* counts, uint32_t stride);
+/* option.carry_out(game) (game/option.py:118-122) for slots [0,n): chosen[i] == 0 skips slot i.
+ * winner[i] = winning seat when that step ended the game, else -1 (the reference returns the winner
+ * Agent or a falsy value). */
+ctd_status ctd_step(ctd_engine* e, uint32_t n, const ctd_option* chosen, int8_t* winner);
+/* the reference's random-playout loop (run_utils.py:37-41; compare_to_random.py:24-32 for seats on
+ * random.choice): new preset games keyed (seed, first_gid+i), uniform-random option each step, to
+ * terminal or max_steps.  Outputs may be NULL.  Runs fused on the device; slots are not touched. */
+ctd_status ctd_playout(ctd_engine* e, uint64_t n_games, uint64_t seed, uint64_t first_gid, int ruleset,
+                       uint32_t max_steps, int8_t* winner, int8_t* points6, uint16_t* steps,
+                       ctd_playout_stats* stats);
+/* same loop continued from the states in slots [0,n) (create_a_close_to_finished_game's tail,
+ * run_utils.py:37-41); the slots receive the terminal states. */
+ctd_status ctd_playout_slots(ctd_engine* e, uint32_t n, uint32_t max_steps, int8_t* winner, uint16_t* steps);
+/* device-resident variant used by bench.py: results stay in HBM, only stats come back.
+ * elapsed_ms (may be NULL) receives the CUDA-event time of the playout kernel alone. */
+ctd_status ctd_playout_dev(ctd_engine* e, uint64_t n_games, uint64_t seed, uint64_t first_gid, int ruleset,
+                           uint32_t max_steps, ctd_playout_stats* stats, float* elapsed_ms);
+/* number of kernels this engine has launched so far */
+uint64_t ctd_launch_count(const ctd_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CITADELS_B200_H */
