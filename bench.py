@@ -1,0 +1,263 @@
+#!/usr/bin/env python
+"""bench.py -- env steps/sec of batched 6-player random playouts (BASELINE.json metric, config[1]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--games G] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch: G independent preset games per GPU, dealt on the
+device from (seed, global game id) and played uniformly at random to terminal by the fused playout kernel.
+Weak scaling: every rank plays G games (rank r owns global ids [r*G*K', ...)), no collective on the step path;
+one all-reduce of the outcome histogram after the timed region.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BYTES_PER_STEP = 512          # read + write of the 256 B packed playout record per env step
+SEED = 0xC17ADE15
+METRIC = "env steps/sec (batched 6p random playouts)"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def _cpu_worker(args):
+    seed, gid0, n = args
+    from oracle import citadels_oracle as O
+    steps = 0
+    t0 = time.perf_counter()
+    for i in range(n):
+        steps += O.playout(seed, gid0 + i)[2]
+    return steps, time.perf_counter() - t0
+
+
+def cpu_playouts(games_per_core, cores, gid0=0):
+    """The reference's random-playout loop (run_utils.py:37-41) as restated in oracle/ (a Python port of a
+    Python reference), on `cores` processes.  Returns (env_steps, wall_seconds)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(SEED, gid0 + c * games_per_core, games_per_core) for c in range(cores)])
+    wall = time.perf_counter() - t0
+    return sum(r[0] for r in res), wall
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_core = max(1, args.ref_games_per_core)
+    for _ in range(args.warmup):
+        cpu_playouts(1, cores)
+    tot_steps, tot_wall = 0, 0.0
+    for k in range(args.steps):
+        s, w = cpu_playouts(per_core, cores, gid0=1000 + k * cores * per_core)
+        tot_steps += s
+        tot_wall += w
+    v = tot_steps / tot_wall
+    sample = "%d games per step (%d per core x %d cores) of the preset random playout, oracle port" % (
+        per_core * cores, per_core, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "env steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_wall / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "preset 6p random playouts to terminal (BASELINE configs[1]), bounded CPU sample",
+                       "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "env steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "env steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--games", type=int, default=1 << 20, help="games per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-games-per-core", type=int, default=24)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ruleset", type=int, default=0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from citadels_self_play_b200 import Engine
+    eng = Engine(capacity=1024, device=local)
+    G = args.games
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def gid0(step):  # disjoint global ids per (step, rank)
+        return (step * world + rank) * G
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up (untimed)
+    for w in range(args.warmup):
+        flush.zero_()
+        torch.cuda.synchronize()
+        eng.playout(G, seed=SEED, first_gid=gid0(1000 + w), ruleset=args.ruleset, outputs=False)
+
+    # ---- device-resident timing: K steps ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launches
+    kernel_ms, env_steps, errors, wins = 0.0, 0, 0, [0] * 6
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        st = eng.playout(G, seed=SEED, first_gid=gid0(k), ruleset=args.ruleset, outputs=False)["stats"]
+        kernel_ms += st["kernel_ms"]
+        env_steps += st["steps"]
+        errors += st["errors"]
+        wins = [a + b for a, b in zip(wins, st["wins"])]
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = eng.launches - launches0
+
+    # ---- end-to-end through the public API with host buffers (D2H of every game's result inside) ----
+    barrier()
+    t1 = time.perf_counter()
+    e2e_steps = 0
+    for k in range(args.steps):
+        out = eng.playout(G, seed=SEED, first_gid=gid0(k), ruleset=args.ruleset, outputs=True)
+        e2e_steps += int(out["steps"].astype("int64").sum())
+    barrier()
+    e2e_wall = time.perf_counter() - t1
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- the only collective: outcome statistics, after the timed region ----
+    t = torch.tensor([wall, e2e_wall, kernel_ms], dtype=torch.float64, device="cuda")
+    s = torch.tensor([env_steps, e2e_steps, errors, launches] + wins, dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    wall, e2e_wall, kernel_ms = [float(x) for x in t.tolist()]
+    env_steps, e2e_steps, errors, launches = [int(x) for x in s.tolist()[:4]]
+    wins = [int(x) for x in s.tolist()[4:]]
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        value = env_steps / wall
+        per_gpu_kernel = (env_steps / world) / (kernel_ms / 1e3)
+        achieved = per_gpu_kernel * BYTES_PER_STEP / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "env steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "%d preset 6-player games per GPU per step, dealt on device from Philox(seed, gid), "
+                                   "uniform-random option to terminal (BASELINE configs[1])" % G,
+                       "ruleset": "preset" if args.ruleset == 0 else "classic", "games_per_gpu_per_step": G,
+                       "l2": "no HBM-resident inputs (games are generated on device); 256 MiB flush between iterations",
+                       "parallelism": "games sharded by global id, %d rank(s), no step-path collective" % world},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "algorithmic 512 B/env step (SURVEY 8(d)); the fused kernel keeps the game in shared "
+                                 "memory for its ~420 steps, so the real limiter is instruction issue (see profiles/)",
+                         "kernel_env_steps_per_s_per_gpu": per_gpu_kernel},
+            "e2e": {"value": e2e_steps / e2e_wall, "unit": "env steps/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 9 * G + 184},
+            "gpu_launches": launches, "clocks": clocks,
+            "outcomes": {"games": G * args.steps * world, "errors": errors, "wins": wins},
+        }
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            per_core = 12
+            cs, cw = cpu_playouts(per_core, cores)
+            line["cpu_baseline"] = {"value": cs / cw, "unit": "env steps/s", "cores": cores, "kind": "port",
+                                    "sample": "%d preset games (%d per core), oracle port of run_utils.py:37-41"
+                                              % (per_core * cores, per_core)}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

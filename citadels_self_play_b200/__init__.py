@@ -1,0 +1,6 @@
+"""B200-native Citadels rollout engine behind the reference's Game / Agent.get_options /
+option.carry_out surface.  The compute path is hand-written sm_100a CUDA reached through the C ABI in
+include/citadels_b200.h; importing this package does not need a GPU, using it does."""
+from .engine import Engine, EngineError, RULESET_PRESET, RULESET_CLASSIC, DEFAULT_SEED  # noqa: F401
+
+__all__ = ["Engine", "EngineError", "RULESET_PRESET", "RULESET_CLASSIC", "DEFAULT_SEED"]

@@ -1,0 +1,1113 @@
+// ctd_engine.cuh -- the Citadels rules engine: on-chip working state, legal-option enumeration and
+// state transition.  Written from the behaviour of the reference (paths below are relative to the
+// reference repository root), not from its code structure: the reference walks Python object graphs
+// (Card/Deck/Agent/option); this engine works on a flat working record that lives in shared memory for
+// the whole life of a game and is only packed to the 256-byte HBM record (ctd_state) at the API boundary.
+//
+// Execution model on the device: one warp owns one game.  The working record sits in that warp's slice
+// of shared memory.  The transition (`ctd_apply`) is a scalar, order-sensitive list manipulation and runs
+// on lane 0; enumeration is read-only and has both a scalar form (`ctd_enumerate`, used for materialised
+// option lists and as the definition of option order) and a warp-cooperative count/select form in
+// ctd_warp.cuh used by the fused playout kernel.
+//
+// The same source compiles for the host (tests/hostsim) so the rules can be replayed against the golden
+// traces without a GPU; that build is a test vehicle, never a fallback of the product.
+#pragma once
+#include <stdint.h>
+#include "../../include/citadels_b200.h"
+
+#if defined(__CUDACC__)
+#define CTD_HD __host__ __device__
+#else
+#define CTD_HD
+#endif
+
+// ------------------------------------------------------------------------------------------ constants
+#define CTD_HAND_CAP 48
+#define CTD_BLD_CAP 16
+#define CTD_MUS_CAP 32
+#define CTD_JD_CAP 32
+#define CTD_DECK_CAP 128 /* ring buffer, power of two */
+#define CTD_DISC_CAP 128
+
+enum { CTD_SUIT_TRADE = 0, CTD_SUIT_WAR, CTD_SUIT_RELIGION, CTD_SUIT_LORD, CTD_SUIT_UNIQUE };
+enum { CTD_ROLE_NONE = 8, CTD_ROLE_BEWITCHED = 9 };
+// role name id = rank*3 + variant (game/config.py:83-91)
+enum {
+  CTD_ASSASSIN = 0, CTD_WITCH, CTD_MAGISTRATE, CTD_THIEF, CTD_SPY, CTD_BLACKMAILER, CTD_MAGICIAN, CTD_WIZARD,
+  CTD_SEER, CTD_KING, CTD_EMPEROR, CTD_PATRICIAN, CTD_BISHOP, CTD_ABBOT, CTD_CARDINAL, CTD_MERCHANT,
+  CTD_ALCHEMIST, CTD_TRADER, CTD_ARCHITECT, CTD_NAVIGATOR, CTD_SCHOLAR, CTD_WARLORD, CTD_DIPLOMAT, CTD_MARSHAL,
+  CTD_NAME_NONE, CTD_NAME_BEWITCHED
+};
+// option kinds = index in game/option.py:34-45
+enum {
+  CTD_K_ROLE_PICK = 0, CTD_K_GOLD_OR_CARD, CTD_K_KEEP, CTD_K_BLACKMAIL_RESPONSE, CTD_K_REVEAL_BLACKMAIL,
+  CTD_K_REVEAL_WARRANT, CTD_K_BUILD, CTD_K_EMPTY, CTD_K_FINISH, CTD_K_GHOST_TOWN, CTD_K_SMITHY, CTD_K_LAB,
+  CTD_K_MAGIC_SCHOOL, CTD_K_WEAPON_STORAGE, CTD_K_LIGHTHOUSE, CTD_K_MUSEUM, CTD_K_GRAVEYARD, CTD_K_TAKE_GOLD_WAR,
+  CTD_K_ASSASSINATION, CTD_K_MAGISTRATE_WARRANT, CTD_K_BEWITCHING, CTD_K_STEAL, CTD_K_BLACKMAIL, CTD_K_SPY,
+  CTD_K_MAGIC_HAND_CHANGE, CTD_K_DISCARD_AND_DRAW, CTD_K_LOOK_AT_HAND, CTD_K_TAKE_FROM_HAND, CTD_K_SEER,
+  CTD_K_GIVE_BACK_CARD, CTD_K_TAKE_CROWN_KING, CTD_K_GIVE_CROWN, CTD_K_TAKE_CROWN_PAT, CTD_K_BISHOP,
+  CTD_K_CARDINAL, CTD_K_ABBOT, CTD_K_ABBOT_BEG, CTD_K_MERCHANT, CTD_K_ALCHEMIST, CTD_K_TRADER, CTD_K_ARCHITECT,
+  CTD_K_NAVIGATOR, CTD_K_SCHOLAR, CTD_K_SCHOLAR_PICK, CTD_K_WARLORD, CTD_K_MARSHAL, CTD_K_DIPLOMAT
+};
+// named choices, game/option.py:69-83
+enum { CTD_N_GOLD = 0, CTD_N_CARD, CTD_N_PAY, CTD_N_NOT_PAY, CTD_N_REVEAL, CTD_N_NOT_REVEAL, CTD_N_4GOLD, CTD_N_4CARD,
+       CTD_N_TRADE };
+// already_done_moves flags
+enum { CTD_DM_SMITHY = 1, CTD_DM_LAB = 2, CTD_DM_MAGIC_SCHOOL = 4, CTD_DM_MUSEUM = 8, CTD_DM_CHARACTER = 16,
+       CTD_DM_BEGGED = 32, CTD_DM_TAKE_GOLD = 64 };
+enum { CTD_NEXT_NONE = 0, CTD_NEXT_ALIAS, CTD_NEXT_RESET_CA, CTD_NEXT_EMPTY };
+enum { CTD_PF_LIGHTHOUSE = 1, CTD_PF_FIRST7 = 2, CTD_PF_WITCH = 4 };
+enum { CTD_RP_DEAD = 1, CTD_RP_WARRANT = 6, CTD_RP_POSSESSED = 8, CTD_RP_ROBBED = 16, CTD_RP_BLACKMAIL = 96 };
+
+// ------------------------------------------------------------------------------------------ card tables
+// game/config.py:2-80.  Tables are folded into immediates so neither host nor device needs memory for them.
+CTD_HD inline int ctd_ctype(int c) { return c >= 40 ? 25 : c; }
+CTD_HD inline int ctd_suit_of_type(int t) { return (t >= 6) + (t >= 10) + (t >= 13) + (t >= 16); }
+CTD_HD inline int ctd_csuit(int c) { return c >= 40 ? c - 40 : ctd_suit_of_type(c); }
+CTD_HD inline int ctd_cost_of_type(int t) {
+  // 3 bits per type: 1,2,4,2,5,3,2,3,5,1,2,3,1,4,3,5,5,3,6,2,6 | 5,5,6,5,6,6,3,6,3,5,5,6,5,4,6,5,4,0,5
+  const uint64_t lo = 1ull | 2ull << 3 | 4ull << 6 | 2ull << 9 | 5ull << 12 | 3ull << 15 | 2ull << 18 | 3ull << 21 |
+                      5ull << 24 | 1ull << 27 | 2ull << 30 | 3ull << 33 | 1ull << 36 | 4ull << 39 | 3ull << 42 |
+                      5ull << 45 | 5ull << 48 | 3ull << 51 | 6ull << 54 | 2ull << 57 | 6ull << 60;
+  const uint64_t hi = 5ull | 5ull << 3 | 6ull << 6 | 5ull << 9 | 6ull << 12 | 6ull << 15 | 3ull << 18 | 6ull << 21 |
+                      3ull << 24 | 5ull << 27 | 5ull << 30 | 6ull << 33 | 5ull << 36 | 4ull << 39 | 6ull << 42 |
+                      5ull << 45 | 4ull << 48 | 0ull << 51 | 5ull << 54;
+  return (int)((t < 21 ? lo >> (3 * t) : hi >> (3 * (t - 21))) & 7);
+}
+CTD_HD inline int ctd_ccost(int c) { return ctd_cost_of_type(ctd_ctype(c)); }
+// i-th card of building_cards + unique_building_cards in list order (game/config.py:2-80)
+CTD_HD inline int ctd_base_deck(int i) {
+  // copies of types 0..15: 5,3,3,4,2,3,3,3,2,3,3,3,3,4,5,3  -> cumulative ends
+  const uint8_t ends[16] = {5, 8, 11, 15, 17, 20, 23, 26, 28, 31, 34, 37, 40, 44, 49, 52};
+  if (i < 52) {
+    int t = 0;
+    while (i >= ends[t]) ++t;
+    return t;
+  }
+  i -= 52;  // uniques: 16,17,17,18,...,37,39
+  if (i == 0) return 16;
+  if (i <= 2) return 17;
+  if (i == 23) return 39;
+  return 15 + i;
+}
+
+// ------------------------------------------------------------------------------------------ descriptors
+CTD_HD inline uint64_t ctd_opt(int kind, int perp) { return (uint64_t)kind | ((uint64_t)perp << 6); }
+CTD_HD inline uint64_t ctd_f_target(int q) { return (uint64_t)(q + 1) << 9; }
+CTD_HD inline uint64_t ctd_f_a(int t) { return (uint64_t)(t + 1) << 12; }
+CTD_HD inline uint64_t ctd_f_b(int t) { return (uint64_t)(t + 1) << 18; }
+CTD_HD inline uint64_t ctd_f_rank(int r) { return (uint64_t)(r + 1) << 24; }
+CTD_HD inline uint64_t ctd_f_named(int n) { return (uint64_t)(n + 1) << 28; }
+CTD_HD inline uint64_t ctd_f_replica(int r) { return (uint64_t)(r & 0xF) << 32; }
+CTD_HD inline uint64_t ctd_f_build(int b) { return (uint64_t)(b & 1) << 36; }
+CTD_HD inline uint64_t ctd_f_next_witch(int b) { return (uint64_t)(b & 1) << 37; }
+CTD_HD inline uint64_t ctd_f_crown(int b) { return (uint64_t)(b & 1) << 38; }
+CTD_HD inline uint64_t ctd_f_count(int c) { return (uint64_t)(c & 0x3F) << 39; }
+CTD_HD inline uint64_t ctd_f_r(int r) { return (uint64_t)(r & 0x3F) << 45; }
+CTD_HD inline uint64_t ctd_f_j(uint32_t j) { return (uint64_t)(j & 0x3FF) << 51; }
+
+// ------------------------------------------------------------------------------------------ working record
+struct CtdWork {
+  uint8_t hand[6][CTD_HAND_CAP];
+  uint8_t bld[6][CTD_BLD_CAP];
+  uint8_t mus[6][CTD_MUS_CAP];
+  uint8_t jd[6][CTD_JD_CAP];
+  uint8_t deck[CTD_DECK_CAP];  // ring: element i is deck[(deck_head + i) & 127]
+  uint8_t disc[CTD_DISC_CAP];
+  uint8_t scratch[128];
+  uint8_t n_hand[6], n_bld[6], n_mus[6], n_jd[6];
+  uint8_t deck_head, n_deck, n_disc;
+  int8_t gold[6];
+  uint8_t role[6];
+  int8_t replicas[6];
+  uint8_t pflags[6];
+  uint8_t rprops[8];
+  uint8_t variant[8];
+  uint8_t order[6];
+  uint8_t used_roles[6];
+  uint8_t used_len, rtc_mask, state, player, done, n_trade, n_nontrade, next_player, next_mode, crown, gflags;
+  int8_t winner;
+  uint8_t wiz_target;
+  int8_t points[6];
+  uint8_t warrant_building, ruleset, err;
+  // chance: Philox4x32-10 keyed (seed, gid) or a recorded tape
+  uint32_t k0, k1, g0, g1;
+  uint32_t draws;
+  uint32_t buf[4];
+  uint32_t buf_blk;
+  const uint8_t* tape;
+  uint32_t tape_pos, tape_len;
+  uint32_t steps;
+};
+
+// ------------------------------------------------------------------------------------------ chance
+CTD_HD inline void ctd_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                              uint32_t out[4]) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+CTD_HD inline void ctd_chance_init(CtdWork& w, uint64_t seed, uint64_t gid, uint32_t draws) {
+  w.k0 = (uint32_t)seed; w.k1 = (uint32_t)(seed >> 32);
+  w.g0 = (uint32_t)gid; w.g1 = (uint32_t)(gid >> 32);
+  w.draws = draws;
+  w.buf_blk = 0xFFFFFFFFu;
+  w.tape = nullptr; w.tape_pos = 0; w.tape_len = 0;
+}
+
+CTD_HD inline uint32_t ctd_u32(CtdWork& w) {
+  uint32_t blk = w.draws >> 2;
+  if (blk != w.buf_blk) {
+    ctd_philox(blk, 0u, w.g0, w.g1, w.k0, w.k1, w.buf);
+    w.buf_blk = blk;
+  }
+  return w.buf[w.draws++ & 3];
+}
+CTD_HD inline uint32_t ctd_randbelow(CtdWork& w, uint32_t n) { return (uint32_t)(((uint64_t)ctd_u32(w) * n) >> 32); }
+
+// Shuffle n elements addressed through `at(i)`.  Philox: Fisher-Yates from the top (the loop shape of
+// CPython's random.shuffle); tape: new[k] = old[tape[k]].  n <= 1 consumes nothing.
+template <class At>
+CTD_HD inline void ctd_shuffle(CtdWork& w, int n, At at) {
+  if (n <= 1) return;
+  if (w.tape != nullptr) {
+    if (w.tape_pos + (uint32_t)n > w.tape_len) { w.err |= CTD_ERR_TAPE; return; }
+    for (int i = 0; i < n; ++i) w.scratch[i] = at(i);
+    for (int i = 0; i < n; ++i) {
+      int src = w.tape[w.tape_pos + i];
+      if (src >= n) { w.err |= CTD_ERR_TAPE; src = 0; }
+      at(i) = w.scratch[src];
+    }
+    w.tape_pos += n;
+    return;
+  }
+  for (int i = n - 1; i > 0; --i) {
+    int j = (int)ctd_randbelow(w, (uint32_t)(i + 1));
+    uint8_t a = at(i), b = at(j);
+    at(i) = b; at(j) = a;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ list helpers
+CTD_HD inline bool ctd_has(const uint8_t* a, int n, int t) {
+  for (int i = 0; i < n; ++i) if (ctd_ctype(a[i]) == t) return true;
+  return false;
+}
+CTD_HD inline int ctd_count_type(const uint8_t* a, int n, int t) {
+  int k = 0;
+  for (int i = 0; i < n; ++i) k += ctd_ctype(a[i]) == t;
+  return k;
+}
+CTD_HD inline int ctd_count_suit(const uint8_t* a, int n, int s) {
+  int k = 0;
+  for (int i = 0; i < n; ++i) k += ctd_csuit(a[i]) == s;
+  return k;
+}
+CTD_HD inline int ctd_remove_at(uint8_t* a, uint8_t& n, int i) {
+  int c = a[i];
+  for (int k = i; k + 1 < n; ++k) a[k] = a[k + 1];
+  --n;
+  return c;
+}
+// Deck.get_a_card_like_it (game/deck.py:49-55): first card of that type; the requested card is fabricated
+// when none matches.
+CTD_HD inline int ctd_take_like(uint8_t* a, uint8_t& n, int t) {
+  for (int i = 0; i < n; ++i)
+    if (ctd_ctype(a[i]) == t) return ctd_remove_at(a, n, i);
+  return t;
+}
+CTD_HD inline void ctd_append(CtdWork& w, uint8_t* a, uint8_t& n, int cap, int c) {
+  if (n >= cap) { w.err |= CTD_ERR_OVERFLOW; return; }
+  a[n++] = (uint8_t)c;
+}
+CTD_HD inline uint8_t& ctd_dk(CtdWork& w, int i) { return w.deck[(w.deck_head + i) & (CTD_DECK_CAP - 1)]; }
+CTD_HD inline void ctd_deck_push(CtdWork& w, int c) {
+  if (w.n_deck >= CTD_DECK_CAP - 1) { w.err |= CTD_ERR_OVERFLOW; return; }
+  ctd_dk(w, w.n_deck) = (uint8_t)c;
+  ++w.n_deck;
+}
+CTD_HD inline void ctd_disc_push(CtdWork& w, int c) { ctd_append(w, w.disc, w.n_disc, CTD_DISC_CAP, c); }
+
+// reshuffle_deck_if_empty (game/option_functions.py:564-570)
+CTD_HD inline void ctd_reshuffle_if_empty(CtdWork& w) {
+  if (w.n_deck == 0 && w.n_disc != 0) {
+    uint8_t* d = w.disc;
+    ctd_shuffle(w, w.n_disc, [d](int i) -> uint8_t& { return d[i]; });
+    w.deck_head = 0;
+    for (int i = 0; i < w.n_disc; ++i) w.deck[i] = w.disc[i];
+    w.n_deck = w.n_disc;
+    w.n_disc = 0;
+  }
+}
+// reshuffle + draw_card; returns -1 for "Deck Empty" (game/deck.py:57-60), which add_card drops (:62-70)
+CTD_HD inline int ctd_draw(CtdWork& w) {
+  ctd_reshuffle_if_empty(w);
+  if (w.n_deck == 0) return -1;
+  int c = w.deck[w.deck_head];
+  w.deck_head = (w.deck_head + 1) & (CTD_DECK_CAP - 1);
+  --w.n_deck;
+  return c;
+}
+CTD_HD inline void ctd_draw_to_hand(CtdWork& w, int p) {
+  int c = ctd_draw(w);
+  if (c >= 0) ctd_append(w, w.hand[p], w.n_hand[p], CTD_HAND_CAP, c);
+}
+CTD_HD inline void ctd_draw_to_jd(CtdWork& w, int p) {
+  int c = ctd_draw(w);
+  if (c >= 0) ctd_append(w, w.jd[p], w.n_jd[p], CTD_JD_CAP, c);
+}
+
+CTD_HD inline int ctd_name(const CtdWork& w, int p) {
+  int r = w.role[p];
+  if (r < 8) return r * 3 + w.variant[r];
+  return r == CTD_ROLE_NONE ? CTD_NAME_NONE : CTD_NAME_BEWITCHED;
+}
+// Game.get_player_from_role_id (game/game.py:403-412); -1 when nobody holds it
+CTD_HD inline int ctd_player_from_rank(const CtdWork& w, int rank) {
+  int want = rank < 0 ? CTD_ROLE_BEWITCHED : rank;
+  for (int p = 0; p < 6; ++p) if (w.role[p] == want) return p;
+  return -1;
+}
+CTD_HD inline bool ctd_owns(const CtdWork& w, int p, int t) { return ctd_has(w.bld[p], w.n_bld[p], t); }
+CTD_HD inline void ctd_clear_done(CtdWork& w) { w.done = 0; w.n_trade = 0; w.n_nontrade = 0; }
+
+// ------------------------------------------------------------------------------------------ round machine
+// Game.setup_round (game/game.py:144-171)
+CTD_HD inline void ctd_setup_round(CtdWork& w) {
+  for (int r = 0; r < 8; ++r) w.rprops[r] = 0;
+  w.used_len = 0;
+  for (int i = 0; i < 6; ++i) w.used_roles[i] = 0;
+  // random.shuffle(list(roles.items())); with 6 players exactly one role is popped face down
+  uint8_t* s = w.scratch + 64;
+  for (int i = 0; i < 8; ++i) s[i] = (uint8_t)i;
+  ctd_shuffle(w, 8, [s](int i) -> uint8_t& { return s[i]; });
+  w.rtc_mask = (uint8_t)(0xFF & ~(1u << s[7]));
+  // turn order rotates by the crowned seat's id, applied to the already rotated list
+  int c = w.crown;
+  uint8_t o[6];
+  for (int i = 0; i < 6; ++i) o[i] = w.order[(i + c) % 6];
+  for (int i = 0; i < 6; ++i) w.order[i] = o[i];
+  w.state = 0;
+  w.player = w.order[0];
+  ctd_clear_done(w);
+  w.next_mode = CTD_NEXT_NONE;
+  w.next_player = 0;
+  w.wiz_target = 0xFF;  // Agent.substract_from_known_hand_confidences_and_clear_wizard (game/agent.py:100-109)
+}
+
+// Game.refresh_used_roles (game/game.py:349-357); value+1 encoding keeps Bewitched (-1) sortable as 0
+CTD_HD inline bool ctd_refresh_used_roles(CtdWork& w) {
+  uint8_t v[6];
+  for (int p = 0; p < 6; ++p) {
+    int r = w.role[p];
+    if (r == CTD_ROLE_NONE) { w.err |= CTD_ERR_REF_RAISE; return false; }
+    v[p] = (uint8_t)(r == CTD_ROLE_BEWITCHED ? 0 : r + 1);
+  }
+  for (int i = 1; i < 6; ++i) {  // insertion sort
+    uint8_t x = v[i];
+    int j = i - 1;
+    while (j >= 0 && v[j] > x) { v[j + 1] = v[j]; --j; }
+    v[j + 1] = x;
+  }
+  for (int i = 0; i < 6; ++i) w.used_roles[i] = v[i];
+  w.used_len = 6;
+  return true;
+}
+
+// Game.setup_next_player (game/game.py:391-401); current < 0 == None
+CTD_HD inline void ctd_setup_next_player(CtdWork& w, int current) {
+  int nxt;
+  if (w.state == 0) {
+    if (!ctd_refresh_used_roles(w)) return;
+    w.state = 1;
+    nxt = ctd_player_from_rank(w, (int)w.used_roles[0] - 1);
+  } else if (current >= 0) {
+    w.state = 1;
+    int r = w.role[current];
+    if (r == CTD_ROLE_NONE) { w.err |= CTD_ERR_REF_RAISE; return; }
+    uint8_t key = (uint8_t)(r == CTD_ROLE_BEWITCHED ? 0 : r + 1);
+    int i = 0;
+    while (i < w.used_len && w.used_roles[i] != key) ++i;
+    if (i + 1 >= w.used_len) { w.err |= CTD_ERR_REF_RAISE; return; }
+    nxt = ctd_player_from_rank(w, (int)w.used_roles[i + 1] - 1);
+    ctd_clear_done(w);
+  } else {
+    w.err |= CTD_ERR_REF_RAISE;
+    return;
+  }
+  if (nxt < 0) { w.err |= CTD_ERR_REF_RAISE; return; }
+  w.player = (uint8_t)nxt;
+}
+
+// Agent.count_points (game/agent.py:116-143)
+CTD_HD inline int ctd_count_points(const CtdWork& w, int p) {
+  int pts = 0;
+  const uint8_t* b = w.bld[p];
+  int n = w.n_bld[p];
+  bool well = ctd_has(b, n, 31);
+  for (int i = 0; i < n; ++i) {
+    int t = ctd_ctype(b[i]);
+    pts += ctd_cost_of_type(t);
+    if (t == 18 || t == 23) pts += 2;
+    if (well && ctd_csuit(b[i]) == CTD_SUIT_UNIQUE) pts += 1;
+  }
+  if (n >= 7) pts += 2;
+  if (w.pflags[p] & CTD_PF_FIRST7) pts += 4;
+  pts += w.n_mus[p];
+  if (ctd_has(b, n, 37)) pts += w.gold[p];
+  if (ctd_has(b, n, 39)) pts += w.n_hand[p];
+  return pts;
+}
+
+// Game.check_game_ending (game/game.py:359-368): first arg-max wins
+CTD_HD inline bool ctd_check_game_ending(CtdWork& w) {
+  if (!(w.gflags & 1)) return false;
+  int best = -1000, bi = 0;
+  for (int p = 0; p < 6; ++p) {
+    int pts = ctd_count_points(w, p);
+    w.points[p] = (int8_t)pts;
+    if (pts > best) { best = pts; bi = p; }
+  }
+  w.gflags |= 2;
+  w.winner = (int8_t)bi;
+  return true;
+}
+
+// move_crown + troneroom_owner_gold (game/option_functions.py:625-631, :588-595)
+CTD_HD inline void ctd_move_crown(CtdWork& w, int target) {
+  w.crown = (uint8_t)target;
+  for (int p = 0; p < 6; ++p)
+    if (ctd_owns(w, p, 32)) { w.gold[p] += 1; break; }
+}
+
+// Game.is_last_round (game/game.py:173-181)
+CTD_HD inline void ctd_is_last_round(CtdWork& w) {
+  if (!(w.gflags & 1))
+    for (int p = 0; p < 6; ++p)
+      if (w.n_bld[p] == 7) { w.gflags |= 1; w.pflags[p] |= CTD_PF_FIRST7; }
+}
+
+// Game.set_preset (game/game.py:420-489): Deck() shuffles the 76 cards, fixed hands are pulled by type
+CTD_HD inline void ctd_deal_preset(CtdWork& w, int ruleset) {
+  for (int p = 0; p < 6; ++p) {
+    w.n_hand[p] = w.n_bld[p] = w.n_mus[p] = w.n_jd[p] = 0;
+    w.gold[p] = 2; w.role[p] = CTD_ROLE_NONE; w.replicas[p] = 0; w.pflags[p] = 0;
+    w.order[p] = (uint8_t)p; w.points[p] = 0; w.used_roles[p] = 0;
+  }
+  for (int r = 0; r < 8; ++r) w.rprops[r] = 0;
+  const uint8_t preset_variant[8] = {1, 1, 1, 0, 1, 1, 1, 0};
+  for (int r = 0; r < 8; ++r) w.variant[r] = ruleset == CTD_RULESET_PRESET ? preset_variant[r] : 0;
+  w.used_len = 0; w.rtc_mask = 0; w.state = 0; w.player = 0xFF;
+  ctd_clear_done(w);
+  w.next_player = 0; w.next_mode = CTD_NEXT_NONE; w.crown = 3; w.gflags = 0; w.winner = -1;
+  w.wiz_target = 0xFF; w.warrant_building = 0xFF; w.ruleset = (uint8_t)ruleset; w.err = 0; w.steps = 0;
+  w.n_disc = 0; w.deck_head = 0;
+  for (int i = 0; i < 76; ++i) w.deck[i] = (uint8_t)ctd_base_deck(i);
+  w.n_deck = 76;
+  uint8_t* d = w.deck;
+  ctd_shuffle(w, 76, [d](int i) -> uint8_t& { return d[i]; });
+  const uint8_t hands[6][6] = {{0, 0, 16, 17, 18, 19}, {1, 1, 20, 21, 22, 23}, {2, 3, 24, 25, 26, 27},
+                               {3, 4, 28, 29, 30, 31}, {4, 0, 32, 33, 34, 35}, {0, 1, 36, 37, 39, 0}};
+  for (int p = 0; p < 6; ++p)
+    for (int k = 0; k < 6; ++k) {
+      int c = ctd_take_like(w.deck, w.n_deck, hands[p][k]);  // head == 0 here, the ring is linear
+      w.hand[p][w.n_hand[p]++] = (uint8_t)c;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ enumeration
+// Visitor that materialises options into a buffer and/or selects the `want`-th one.
+struct CtdEmit {
+  uint64_t* buf;
+  uint32_t cap;
+  uint32_t n;
+  uint32_t want;
+  uint64_t got;
+  CTD_HD void one(uint64_t d) {
+    if (n < cap) buf[n] = d;
+    if (n == want) got = d;
+    ++n;
+  }
+  // cnt options that differ only in the ordinal field j
+  CTD_HD void range(uint64_t base, uint32_t cnt) {
+    if (want >= n && want - n < cnt) got = base | ctd_f_j(want - n);
+    for (uint32_t j = 0; j < cnt && n + j < cap; ++j) buf[n + j] = base | ctd_f_j(j);
+    n += cnt;
+  }
+};
+
+CTD_HD inline int ctd_build_limit(int name) {  // Agent.get_build_limit (game/agent.py:87-98)
+  if (name == CTD_ARCHITECT) return 3;
+  if (name == CTD_SCHOLAR) return 2;
+  if (name == CTD_BISHOP || name == CTD_NAVIGATOR) return 0;
+  return 1;
+}
+// cost as the enumerators see it: Factory (35) makes uniques dearer (game/agent_functions.py:113-114)
+CTD_HD inline int ctd_build_cost(int c, bool factory) {
+  return ctd_ccost(c) + ((factory && ctd_csuit(c) == CTD_SUIT_UNIQUE) ? 1 : 0);
+}
+CTD_HD inline uint64_t ctd_binom(int n, int r) {
+  if (r > n - r) r = n - r;
+  uint64_t v = 1;
+  for (int i = 1; i <= r; ++i) v = v * (uint64_t)(n - r + i) / (uint64_t)i;
+  return v;
+}
+// number of discard_and_draw options of subset size r for a hand of n (game/agent_functions.py:290-294):
+// range(0, C, max(round(C/1e2), 1)) with CPython's round-half-even
+CTD_HD inline uint32_t ctd_magician_count(int n, int r) {
+  uint64_t c = ctd_binom(n, r);
+  uint64_t q = c / 100, rem = c % 100;
+  uint64_t step = rem > 50 ? q + 1 : (rem < 50 ? q : q + (q & 1));
+  if (step < 1) step = 1;
+  return (uint32_t)((c + step - 1) / step);
+}
+
+// character_options (game/agent_functions.py:156-209) and the per-role enumerators it dispatches to
+template <class E>
+CTD_HD inline void ctd_character_options(const CtdWork& w, int p, int nm, E& e) {
+  if (!(w.done & CTD_DM_CHARACTER)) {
+    switch (nm) {
+      case CTD_ASSASSIN:  // :213-218
+        for (int r = 1; r < 8; ++r) e.one(ctd_opt(CTD_K_ASSASSINATION, p) | ctd_f_rank(r));
+        break;
+      case CTD_THIEF:  // :246-253
+        for (int r = 2; r < 8; ++r) e.one(ctd_opt(CTD_K_STEAL, p) | ctd_f_rank(r));
+        break;
+      case CTD_SPY:  // :274-281
+        for (int q = 0; q < 6; ++q)
+          if (q != p)
+            for (int s = 0; s < 5; ++s) e.one(ctd_opt(CTD_K_SPY, p) | ctd_f_target(q) | ctd_f_named(CTD_N_TRADE + s));
+        break;
+      case CTD_MAGICIAN: {  // :284-296
+        for (int q = 0; q < 6; ++q)
+          if (q != p) e.one(ctd_opt(CTD_K_MAGIC_HAND_CHANGE, p) | ctd_f_target(q));
+        int n = w.n_hand[p];
+        for (int r = 1; r <= n; ++r) e.range(ctd_opt(CTD_K_DISCARD_AND_DRAW, p) | ctd_f_r(r), ctd_magician_count(n, r));
+        break;
+      }
+      case CTD_WIZARD:  // :298-308
+        for (int q = 0; q < 6; ++q)
+          if (q != p && w.n_hand[q] > 0) e.one(ctd_opt(CTD_K_LOOK_AT_HAND, p) | ctd_f_target(q));
+        break;
+      case CTD_KING: e.one(ctd_opt(CTD_K_TAKE_CROWN_KING, p)); break;  // :364-366
+      case CTD_BISHOP: e.one(ctd_opt(CTD_K_BISHOP, p)); break;         // :389-391
+      case CTD_ABBOT: {                                                // :422-430
+        int n = ctd_count_suit(w.hand[p], w.n_hand[p], CTD_SUIT_RELIGION);
+        if (n > 0)
+          for (int k = 0; k <= n; ++k) e.one(ctd_opt(CTD_K_ABBOT, p) | ctd_f_count(k));
+        break;
+      }
+      case CTD_MERCHANT: e.one(ctd_opt(CTD_K_MERCHANT, p)); break;    // :438-440
+      case CTD_ALCHEMIST: break;                                       // :442-444
+      case CTD_ARCHITECT: e.one(ctd_opt(CTD_K_ARCHITECT, p)); break;  // :451-452
+      case CTD_NAVIGATOR:                                              // :454-455
+        e.one(ctd_opt(CTD_K_NAVIGATOR, p) | ctd_f_named(CTD_N_4GOLD));
+        e.one(ctd_opt(CTD_K_NAVIGATOR, p) | ctd_f_named(CTD_N_4CARD));
+        break;
+      case CTD_WARLORD:  // :473-482
+        for (int q = 0; q < 6; ++q) {
+          if (w.n_bld[q] >= 7 || ctd_name(w, q) == CTD_BISHOP) continue;
+          uint64_t seen = 0;
+          for (int i = 0; i < w.n_bld[q]; ++i) {
+            int c = w.bld[q][i], t = ctd_ctype(c);
+            if (ctd_ccost(c) - 1 <= w.gold[p] && t != 17 && !((seen >> t) & 1)) {
+              seen |= 1ull << t;
+              e.one(ctd_opt(CTD_K_WARLORD, p) | ctd_f_target(q) | ctd_f_a(t));
+            }
+          }
+        }
+        break;
+      default: break;  // tier C roles are outside the built tiers (caller flags CTD_ERR_UNIMPL)
+    }
+  }
+  if (nm == CTD_ABBOT && !(w.done & CTD_DM_BEGGED)) e.one(ctd_opt(CTD_K_ABBOT_BEG, p));  // :199-202
+  if ((nm == CTD_WARLORD || nm == CTD_MARSHAL || nm == CTD_DIPLOMAT) && !(w.done & CTD_DM_TAKE_GOLD))
+    e.one(ctd_opt(CTD_K_TAKE_GOLD_WAR, p));  // :204-207
+}
+
+// main_round_options (game/agent_functions.py:133-147); concatenation order is observable
+template <class E>
+CTD_HD inline void ctd_main_round_options(const CtdWork& w, int p, int nm, E& e) {
+  const uint8_t* bld = w.bld[p];
+  const int nb = w.n_bld[p];
+  const uint8_t* hand = w.hand[p];
+  const int nh = w.n_hand[p];
+  // which effect buildings do I own
+  uint64_t own = 0;
+  for (int i = 0; i < nb; ++i) own |= 1ull << ctd_ctype(bld[i]);
+  // build_options / get_builds (:108-130)
+  {
+    int built = nm == CTD_TRADER ? w.n_nontrade : w.n_trade + w.n_nontrade;
+    if (built < ctd_build_limit(nm)) {
+      bool factory = (own >> 35) & 1;
+      uint64_t seen = 0;
+      for (int i = 0; i < nh; ++i) {
+        int c = hand[i], t = ctd_ctype(c);
+        int replica = (((own >> t) & 1) && !w.replicas[p]) ? w.replicas[p] + 1 : 0;
+        if (ctd_build_cost(c, factory) <= w.gold[p] && !((seen >> t) & 1)) {
+          seen |= 1ull << t;
+          e.one(ctd_opt(CTD_K_BUILD, p) | ctd_f_a(t) | ctd_f_replica(replica));
+        }
+      }
+    }
+  }
+  ctd_character_options(w, p, nm, e);
+  if (((own >> 21) & 1) && w.gold[p] >= 2 && !(w.done & CTD_DM_SMITHY)) e.one(ctd_opt(CTD_K_SMITHY, p));  // :54-57
+  if (((own >> 22) & 1) && !(w.done & CTD_DM_LAB))                                                      // :59-65
+    for (int i = 0; i < nh; ++i) e.one(ctd_opt(CTD_K_LAB, p) | ctd_f_a(ctd_ctype(hand[i])));
+  if (!(w.done & CTD_DM_MAGIC_SCHOOL) && ((own >> 25) & 1))                                             // :67-74
+    for (int s = 0; s < 5; ++s) e.one(ctd_opt(CTD_K_MAGIC_SCHOOL, p) | ctd_f_named(CTD_N_TRADE + s));
+  if ((own >> 27) & 1)                                                                                  // :76-83
+    for (int q = 0; q < 6; ++q)
+      if (q != p)
+        for (int i = 0; i < w.n_bld[q]; ++i)
+          e.one(ctd_opt(CTD_K_WEAPON_STORAGE, p) | ctd_f_target(q) | ctd_f_a(ctd_ctype(w.bld[q][i])));
+  if (((own >> 29) & 1) && (w.pflags[p] & CTD_PF_LIGHTHOUSE)) {                                          // :85-94
+    uint64_t seen = 0;
+    for (int i = 0; i < w.n_deck; ++i) {
+      int t = ctd_ctype(w.deck[(w.deck_head + i) & (CTD_DECK_CAP - 1)]);
+      if (!((seen >> t) & 1)) { seen |= 1ull << t; e.one(ctd_opt(CTD_K_LIGHTHOUSE, p) | ctd_f_a(t)); }
+    }
+  }
+  if (((own >> 34) & 1) && !(w.done & CTD_DM_MUSEUM)) {                                                  // :96-105
+    uint64_t seen = 0;
+    for (int i = 0; i < nh; ++i) {
+      int t = ctd_ctype(hand[i]);
+      if (!((seen >> t) & 1)) { seen |= 1ull << t; e.one(ctd_opt(CTD_K_MUSEUM, p) | ctd_f_a(t)); }
+    }
+  }
+  e.one(ctd_opt(CTD_K_FINISH, p));
+}
+
+// wizard_take_from_hand_options (game/agent_functions.py:310-326).  `cards` is the looked-at hand copy
+// (HandKnowledge.hand); in a playout it equals the target's current hand.  `replica` leaks across iterations.
+template <class E>
+CTD_HD inline void ctd_wizard_take_options(const CtdWork& w, int p, const uint8_t* cards, int n, E& e) {
+  int q = w.wiz_target;
+  uint64_t own = 0;
+  for (int i = 0; i < w.n_bld[p]; ++i) own |= 1ull << ctd_ctype(w.bld[p][i]);
+  bool factory = (own >> 35) & 1;
+  uint64_t seen_take = 0, seen_b0 = 0, seen_b1 = 0;
+  int replica = 0;
+  uint32_t before = e.n;
+  for (int i = 0; i < n; ++i) {
+    int c = cards[i], t = ctd_ctype(c);
+    if (!((seen_take >> t) & 1)) {
+      seen_take |= 1ull << t;
+      e.one(ctd_opt(CTD_K_TAKE_FROM_HAND, p) | ctd_f_target(q) | ctd_f_a(t));
+    }
+    if ((own >> t) & 1) replica = w.replicas[p] + 1;
+    uint64_t& seen = replica == 0 ? seen_b0 : seen_b1;
+    if (ctd_build_cost(c, factory) <= w.gold[p] && !((seen >> t) & 1)) {
+      seen |= 1ull << t;
+      e.one(ctd_opt(CTD_K_TAKE_FROM_HAND, p) | ctd_f_target(q) | ctd_f_a(t) | ctd_f_build(1) | ctd_f_replica(replica));
+    }
+  }
+  if (e.n == before) e.one(ctd_opt(CTD_K_EMPTY, p));
+}
+
+// Agent.get_options (game/agent.py:50-83).  An empty result with err set means the reference would raise.
+template <class E>
+CTD_HD inline void ctd_enumerate(CtdWork& w, E& e) {
+  if (w.gflags & 2) return;  // terminal: the reference's loops stop here
+  const int p = w.player;
+  const int st = w.state;
+  if (p >= 6) { w.err |= CTD_ERR_REF_RAISE; return; }
+  if (st == 0) {  // pick_role_options (game/agent_functions.py:13-14)
+    for (int r = 0; r < 8; ++r)
+      if ((w.rtc_mask >> r) & 1) e.one(ctd_opt(CTD_K_ROLE_PICK, p) | ctd_f_rank(r));
+    return;
+  }
+  const int role = w.role[p];
+  if (role == CTD_ROLE_NONE) { w.err |= CTD_ERR_REF_RAISE; return; }
+  const int nm = ctd_name(w, p);
+  const bool king = nm == CTD_KING || nm == CTD_PATRICIAN;
+  if (role == CTD_ROLE_BEWITCHED || !(w.rprops[role] & CTD_RP_DEAD)) {
+    switch (st) {
+      case 1:  // gold_or_card_options (:16-17)
+        e.one(ctd_opt(CTD_K_GOLD_OR_CARD, p) | ctd_f_named(CTD_N_GOLD));
+        if (w.n_deck > 1) e.one(ctd_opt(CTD_K_GOLD_OR_CARD, p) | ctd_f_named(CTD_N_CARD));
+        return;
+      case 2: {  // which_card_to_keep_options (:19-33)
+        const uint8_t* jd = w.jd[p];
+        int n = w.n_jd[p];
+        if (ctd_owns(w, p, 20)) {
+          for (int i = 0; i < n; ++i)
+            for (int j = i + 1; j < n; ++j)
+              e.one(ctd_opt(CTD_K_KEEP, p) | ctd_f_a(ctd_ctype(jd[i])) | ctd_f_b(ctd_ctype(jd[j])));
+        } else {
+          uint64_t seen = 0;
+          for (int i = 0; i < n; ++i) {
+            int t = ctd_ctype(jd[i]);
+            if (!((seen >> t) & 1)) { seen |= 1ull << t; e.one(ctd_opt(CTD_K_KEEP, p) | ctd_f_a(t)); }
+          }
+        }
+        return;
+      }
+      case 3:  // blackmail_response_options (:35-38)
+        if (role == CTD_ROLE_BEWITCHED) { w.err |= CTD_ERR_REF_RAISE; return; }
+        if (w.rprops[role] & CTD_RP_BLACKMAIL) {
+          e.one(ctd_opt(CTD_K_BLACKMAIL_RESPONSE, p) | ctd_f_named(CTD_N_PAY));
+          e.one(ctd_opt(CTD_K_BLACKMAIL_RESPONSE, p) | ctd_f_named(CTD_N_NOT_PAY));
+        } else {
+          e.one(ctd_opt(CTD_K_EMPTY, p));
+        }
+        return;
+      case 6:  // graveyard_options (:150-153)
+        e.one(ctd_opt(w.gold[p] > 0 ? CTD_K_GRAVEYARD : CTD_K_EMPTY, p));
+        return;
+      case 4: case 7:
+        w.err |= CTD_ERR_UNIMPL;
+        return;
+      default: break;
+    }
+    if (nm == CTD_WITCH) {  // witch_options (:236-242)
+      for (int r = 1; r < 8; ++r) e.one(ctd_opt(CTD_K_BEWITCHING, p) | ctd_f_rank(r));
+      return;
+    }
+    if (role == CTD_ROLE_BEWITCHED) { w.err |= CTD_ERR_REF_RAISE; return; }
+    if (!(w.rprops[role] & CTD_RP_POSSESSED)) {
+      if (st == 5) {
+        if (w.variant[role] == 2 || nm == CTD_BLACKMAILER || nm == CTD_SEER || nm == CTD_EMPEROR || nm == CTD_CARDINAL ||
+            nm == CTD_TRADER || nm == CTD_SCHOLAR || nm == CTD_DIPLOMAT || nm == CTD_MARSHAL || nm == CTD_MAGISTRATE ||
+            nm == CTD_PATRICIAN) {
+          w.err |= CTD_ERR_UNIMPL;
+          return;
+        }
+        ctd_main_round_options(w, p, nm, e);
+        return;
+      }
+      if (st == 10) {
+        int q = w.wiz_target;
+        if (q >= 6) { w.err |= CTD_ERR_REF_RAISE; return; }
+        ctd_wizard_take_options(w, p, w.hand[q], w.n_hand[q], e);
+        return;
+      }
+      w.err |= CTD_ERR_UNIMPL;
+      return;
+    }
+    e.one(ctd_opt(CTD_K_FINISH, p) | ctd_f_next_witch(1) | ctd_f_crown(king));
+    return;
+  }
+  if (nm == CTD_EMPEROR && !(w.done & CTD_DM_CHARACTER)) { w.err |= CTD_ERR_UNIMPL; return; }
+  e.one(ctd_opt(CTD_K_FINISH, p) | ctd_f_crown(king));
+}
+
+// ------------------------------------------------------------------------------------------ transition
+CTD_HD inline void ctd_to5(CtdWork& w, int p) { w.state = 5; w.player = (uint8_t)p; }
+
+// game.gamestate = game.gamestate.next_gamestate
+CTD_HD inline void ctd_restore_next(CtdWork& w) {
+  if (w.next_mode == CTD_NEXT_NONE) { w.err |= CTD_ERR_REF_RAISE; return; }
+  w.state = 5;
+  w.player = w.next_player;
+  if (w.next_mode == CTD_NEXT_RESET_CA) { ctd_clear_done(w); w.done = CTD_DM_CHARACTER; }
+  else if (w.next_mode == CTD_NEXT_EMPTY) ctd_clear_done(w);
+  w.next_mode = CTD_NEXT_NONE;
+  w.next_player = 0;
+}
+
+// carry_out_building (game/option_functions.py:102-127)
+CTD_HD inline void ctd_apply_build(CtdWork& w, int p, int t, int replica) {
+  int c = ctd_take_like(w.hand[p], w.n_hand[p], t);
+  ctd_append(w, w.bld[p], w.n_bld[p], CTD_BLD_CAP, c);
+  if (ctd_name(w, p) != CTD_ALCHEMIST) w.gold[p] -= (int8_t)ctd_ccost(c);
+  if (replica) w.replicas[p] = (int8_t)replica;
+  if (ctd_csuit(c) == CTD_SUIT_TRADE) { if (w.n_trade < 15) ++w.n_trade; }
+  else { if (w.n_nontrade < 15) ++w.n_nontrade; }
+  if (t == 29) w.pflags[p] |= CTD_PF_LIGHTHOUSE;
+  int r = w.role[p];
+  if (r >= 8) { w.err |= CTD_ERR_REF_RAISE; return; }
+  if (!(w.rprops[r] & CTD_RP_WARRANT)) ctd_to5(w, p);
+  else w.err |= CTD_ERR_UNIMPL;  // tier C: magistrate interrupt
+}
+
+// finish_main_sequnce_actions (game/option_functions.py:189-243).  Returns true when the game ended.
+CTD_HD inline bool ctd_apply_finish(CtdWork& w, uint64_t d) {
+  const int p = CTD_OPT_PERP(d);
+  const int pr = w.role[p];
+  if (pr >= 8) { w.err |= CTD_ERR_REF_RAISE; return false; }
+  const bool dead = w.rprops[pr] & CTD_RP_DEAD;
+  if (!dead) {
+    if (ctd_owns(w, p, 28) && w.n_hand[p] == 0) { ctd_draw_to_jd(w, p); ctd_draw_to_jd(w, p); }  // Park
+    if (ctd_owns(w, p, 30) && w.n_hand[p] == 0) w.gold[p] += 1;                                  // Poorhouse
+  }
+  if (CTD_OPT_CROWN(d)) ctd_move_crown(w, p);
+  if (CTD_OPT_NEXT_WITCH(d)) {  // :211-230 the witch takes over the possessed role
+    int wi = ctd_player_from_rank(w, 0);
+    if (wi < 0) { w.err |= CTD_ERR_REF_RAISE; return false; }
+    w.state = 5;
+    w.player = (uint8_t)wi;
+    w.role[wi] = (uint8_t)pr;
+    w.rprops[pr] &= (uint8_t)~CTD_RP_POSSESSED;
+    w.role[p] = CTD_ROLE_BEWITCHED;
+    ctd_clear_done(w);
+    return false;
+  }
+  if (w.used_len == 0) { w.err |= CTD_ERR_REF_RAISE; return false; }
+  if ((int)w.used_roles[w.used_len - 1] - 1 == pr) {  // last player of the round
+    if (ctd_check_game_ending(w)) return true;
+    ctd_setup_round(w);
+  } else {
+    ctd_setup_next_player(w, p);
+  }
+  return false;
+}
+
+// option.carry_out (game/option.py:118-122).  Returns true when this step ended the game.
+CTD_HD inline bool ctd_apply(CtdWork& w, uint64_t d) {
+  const int k = CTD_OPT_KIND(d);
+  const int p = CTD_OPT_PERP(d);
+  bool won = false;
+  switch (k) {
+    case CTD_K_ROLE_PICK: {  // carry_out_role_pick (:6-30)
+      int r = CTD_OPT_RANK(d);
+      w.role[p] = (uint8_t)r;
+      w.rtc_mask &= (uint8_t)~(1u << r);
+      if (p != w.order[5]) {
+        int i = 0;
+        while (i < 5 && w.order[i] != p) ++i;
+        w.state = 0;
+        w.player = w.order[i + 1];
+      } else {
+        ctd_setup_next_player(w, -1);
+      }
+      break;
+    }
+    case CTD_K_GOLD_OR_CARD: {  // carry_out_gold_or_card (:33-55)
+      int r = w.role[p];
+      if (r >= 8) { w.err |= CTD_ERR_REF_RAISE; break; }
+      if (w.rprops[r] & CTD_RP_ROBBED) {
+        int th = ctd_player_from_rank(w, 1);
+        if (th < 0) { w.err |= CTD_ERR_REF_RAISE; break; }
+        int g = w.gold[p];
+        w.gold[th] += (int8_t)g;  // thief may be p itself only if p holds rank 1, which is never robbed by itself
+        w.gold[p] = (int8_t)(th == p ? g : 0);
+        if (th == p) w.gold[p] = 0;
+      }
+      if (CTD_OPT_NAMED(d) == CTD_N_GOLD) {
+        w.gold[p] += 2;
+        w.state = 3;
+      } else {
+        int n = ctd_owns(w, p, 16) ? 3 : 2;  // Observatory
+        for (int i = 0; i < n; ++i) ctd_draw_to_jd(w, p);
+        w.state = 2;
+      }
+      w.player = (uint8_t)p;
+      break;
+    }
+    case CTD_K_KEEP: {  // carry_out_put_back_card (:58-66)
+      int c = ctd_take_like(w.jd[p], w.n_jd[p], CTD_OPT_CARD_A(d));
+      ctd_append(w, w.hand[p], w.n_hand[p], CTD_HAND_CAP, c);
+      if (CTD_OPT_CARD_B(d) >= 0) {
+        c = ctd_take_like(w.jd[p], w.n_jd[p], CTD_OPT_CARD_B(d));
+        ctd_append(w, w.hand[p], w.n_hand[p], CTD_HAND_CAP, c);
+      }
+      for (int i = 0; i < w.n_jd[p]; ++i) ctd_deck_push(w, w.jd[p][i]);
+      w.n_jd[p] = 0;
+      w.state = 3;
+      w.player = (uint8_t)p;
+      break;
+    }
+    case CTD_K_EMPTY:  // carry_out_empty (:68-69); producers: agent_functions.py:38, :153, :325
+      if (w.state == 3) {
+        ctd_to5(w, p);
+        ctd_clear_done(w);
+        w.next_mode = CTD_NEXT_NONE;
+        w.next_player = 0;
+      } else {
+        ctd_restore_next(w);
+      }
+      break;
+    case CTD_K_BUILD: ctd_apply_build(w, p, CTD_OPT_CARD_A(d), CTD_OPT_REPLICA(d)); break;
+    case CTD_K_FINISH: won = ctd_apply_finish(w, d); break;
+    case CTD_K_SMITHY:  // carry_out_smithy (:131-138): the cards go to just_drawn_cards
+      w.gold[p] -= 2;
+      for (int i = 0; i < 3; ++i) ctd_draw_to_jd(w, p);
+      ctd_to5(w, p);
+      w.done |= CTD_DM_SMITHY;
+      break;
+    case CTD_K_LAB:  // carry_out_laboratory (:140-145)
+      ctd_disc_push(w, ctd_take_like(w.hand[p], w.n_hand[p], CTD_OPT_CARD_A(d)));
+      w.gold[p] += 1;
+      ctd_to5(w, p);
+      w.done |= CTD_DM_LAB;
+      break;
+    case CTD_K_MAGIC_SCHOOL: {  // carry_out_magic_school (:147-153): removed and re-appended with the new suit
+      ctd_take_like(w.bld[p], w.n_bld[p], 25);
+      int s = CTD_OPT_NAMED(d) - CTD_N_TRADE;
+      ctd_append(w, w.bld[p], w.n_bld[p], CTD_BLD_CAP, s == CTD_SUIT_UNIQUE ? 25 : 40 + s);
+      ctd_to5(w, p);
+      w.done |= CTD_DM_MAGIC_SCHOOL;
+      break;
+    }
+    case CTD_K_MUSEUM:  // carry_out_museum (:161-165)
+      ctd_append(w, w.mus[p], w.n_mus[p], CTD_MUS_CAP, ctd_take_like(w.hand[p], w.n_hand[p], CTD_OPT_CARD_A(d)));
+      ctd_to5(w, p);
+      w.done |= CTD_DM_MUSEUM;
+      break;
+    case CTD_K_WEAPON_STORAGE: {  // carry_out_weapon_storage (:167-171)
+      int q = CTD_OPT_TARGET(d);
+      ctd_disc_push(w, ctd_take_like(w.bld[p], w.n_bld[p], 27));
+      ctd_disc_push(w, ctd_take_like(w.bld[q], w.n_bld[q], CTD_OPT_CARD_A(d)));
+      ctd_to5(w, p);
+      break;
+    }
+    case CTD_K_LIGHTHOUSE: {  // carry_out_lighthouse (:173-180)
+      int t = CTD_OPT_CARD_A(d), c = t, n = w.n_deck;
+      for (int i = 0; i < n; ++i)
+        if (ctd_ctype(ctd_dk(w, i)) == t) {
+          c = ctd_dk(w, i);
+          for (int k = i; k + 1 < n; ++k) ctd_dk(w, k) = ctd_dk(w, k + 1);
+          --w.n_deck;
+          break;
+        }
+      ctd_append(w, w.hand[p], w.n_hand[p], CTD_HAND_CAP, c);
+      w.pflags[p] &= (uint8_t)~CTD_PF_LIGHTHOUSE;
+      CtdWork* wp = &w;
+      ctd_shuffle(w, w.n_deck, [wp](int i) -> uint8_t& { return ctd_dk(*wp, i); });
+      ctd_to5(w, p);
+      break;
+    }
+    case CTD_K_GRAVEYARD:  // carry_out_graveyard (:183-187): pops the LAST discard
+      if (w.n_disc == 0) { w.err |= CTD_ERR_REF_RAISE; break; }
+      ctd_append(w, w.bld[p], w.n_bld[p], CTD_BLD_CAP, w.disc[--w.n_disc]);
+      w.gold[p] -= 1;
+      ctd_restore_next(w);
+      break;
+    case CTD_K_TAKE_GOLD_WAR:  // carry_out_take_gold_for_war (:553-559)
+      w.gold[p] += (int8_t)ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_WAR);
+      ctd_to5(w, p);
+      w.done |= CTD_DM_TAKE_GOLD;
+      break;
+    case CTD_K_ASSASSINATION:  // carry_out_assasination (:245-249)
+      w.rprops[CTD_OPT_RANK(d)] |= CTD_RP_DEAD;
+      ctd_to5(w, p);
+      w.done |= CTD_DM_CHARACTER;
+      break;
+    case CTD_K_STEAL:  // carry_out_stealing (:265-269)
+      w.rprops[CTD_OPT_RANK(d)] |= CTD_RP_ROBBED;
+      ctd_to5(w, p);
+      w.done |= CTD_DM_CHARACTER;
+      break;
+    case CTD_K_BEWITCHING:  // carry_out_bewitching (:259-262)
+      w.rprops[CTD_OPT_RANK(d)] |= CTD_RP_POSSESSED;
+      w.pflags[p] |= CTD_PF_WITCH;
+      ctd_setup_next_player(w, p);
+      break;
+    case CTD_K_SPY: {  // carry_out_spying (:278-288)
+      int q = CTD_OPT_TARGET(d), s = CTD_OPT_NAMED(d) - CTD_N_TRADE;
+      int n = ctd_count_suit(w.hand[q], w.n_hand[q], s);
+      int steal = n < w.gold[q] ? n : w.gold[q];
+      w.gold[p] += (int8_t)steal;
+      w.gold[q] -= (int8_t)steal;
+      ctd_draw_to_hand(w, p);
+      ctd_to5(w, p);
+      w.done |= CTD_DM_CHARACTER;
+      break;
+    }
+    case CTD_K_MAGIC_HAND_CHANGE: {  // carry_out_magicking (:291-293)
+      int q = CTD_OPT_TARGET(d);
+      int n = w.n_hand[p] > w.n_hand[q] ? w.n_hand[p] : w.n_hand[q];
+      for (int i = 0; i < n; ++i) { uint8_t a = w.hand[p][i]; w.hand[p][i] = w.hand[q][i]; w.hand[q][i] = a; }
+      uint8_t a = w.n_hand[p]; w.n_hand[p] = w.n_hand[q]; w.n_hand[q] = a;
+      ctd_to5(w, p);
+      w.done |= CTD_DM_CHARACTER;
+      break;
+    }
+    case CTD_K_DISCARD_AND_DRAW: {  // carry_out_magicking (:295-300): ignores the option's cards and removes
+                                    // while iterating; draws as many cards as are left in hand
+      int i = 0;
+      while (i < w.n_hand[p]) {
+        int t = ctd_ctype(w.hand[p][i]);
+        ctd_deck_push(w, ctd_take_like(w.hand[p], w.n_hand[p], t));
+        ++i;
+      }
+      int n = w.n_hand[p];
+      for (int k = 0; k < n; ++k) ctd_draw_to_hand(w, p);
+      ctd_to5(w, p);
+      w.done |= CTD_DM_CHARACTER;
+      break;
+    }
+    case CTD_K_LOOK_AT_HAND:  // carry_out_wizard_hand_looking (:305-310)
+      w.wiz_target = (uint8_t)CTD_OPT_TARGET(d);
+      w.state = 10;
+      w.player = (uint8_t)p;
+      w.done |= CTD_DM_CHARACTER;
+      w.next_player = (uint8_t)p;
+      w.next_mode = CTD_NEXT_ALIAS;
+      break;
+    case CTD_K_TAKE_FROM_HAND: {  // carry_out_wizard_take_from_hand (:312-328)
+      int q = CTD_OPT_TARGET(d), t = CTD_OPT_CARD_A(d);
+      ctd_append(w, w.hand[p], w.n_hand[p], CTD_HAND_CAP, ctd_take_like(w.hand[q], w.n_hand[q], t));
+      if (CTD_OPT_BUILD(d)) ctd_apply_build(w, p, t, ctd_count_type(w.bld[p], w.n_bld[p], t));
+      ctd_restore_next(w);
+      break;
+    }
+    case CTD_K_TAKE_CROWN_KING:  // carry_out_take_crown_king (:354-363)
+      w.gold[p] += (int8_t)ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_LORD);
+      if (!(w.pflags[p] & CTD_PF_WITCH)) ctd_move_crown(w, p);
+      ctd_to5(w, p);
+      w.done |= CTD_DM_CHARACTER;
+      break;
+    case CTD_K_BISHOP:  // carry_out_bishop (:397-403)
+      w.gold[p] += (int8_t)ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_RELIGION);
+      ctd_to5(w, p);
+      w.done |= CTD_DM_CHARACTER;
+      break;
+    case CTD_K_MERCHANT:  // carry_out_merchant (:442-449)
+      w.gold[p] += (int8_t)(ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_TRADE) + 1);
+      ctd_to5(w, p);
+      w.done |= CTD_DM_CHARACTER;
+      break;
+    case CTD_K_ABBOT: {  // carry_out_abbot (:405-412)
+      int n = ctd_count_suit(w.hand[p], w.n_hand[p], CTD_SUIT_RELIGION), kc = CTD_OPT_COUNT(d);
+      w.gold[p] += (int8_t)(n - kc);
+      for (int i = 0; i < kc; ++i) ctd_draw_to_hand(w, p);
+      ctd_to5(w, p);
+      w.done |= CTD_DM_CHARACTER;
+      break;
+    }
+    case CTD_K_ABBOT_BEG: {  // carry_out_abbot_beg (:414-420): first richest seat pays, may be the abbot
+      int rich = 0;
+      for (int q = 1; q < 6; ++q) if (w.gold[q] > w.gold[rich]) rich = q;
+      w.gold[rich] -= 1;
+      int a = ctd_player_from_rank(w, 4);
+      if (a < 0) { w.err |= CTD_ERR_REF_RAISE; break; }
+      w.gold[a] += 1;
+      ctd_to5(w, p);
+      w.done |= CTD_DM_BEGGED;
+      break;
+    }
+    case CTD_K_ARCHITECT:  // carry_out_architect (:464-471)
+      ctd_draw_to_hand(w, p);
+      ctd_draw_to_hand(w, p);
+      ctd_to5(w, p);
+      w.done |= CTD_DM_CHARACTER;
+      break;
+    case CTD_K_NAVIGATOR:  // carry_out_navigator (:473-483)
+      if (CTD_OPT_NAMED(d) == CTD_N_4CARD) for (int i = 0; i < 4; ++i) ctd_draw_to_hand(w, p);
+      else w.gold[p] += 4;
+      ctd_to5(w, p);
+      w.done |= CTD_DM_CHARACTER;
+      break;
+    case CTD_K_WARLORD: {  // carry_out_warlord (:517-535) with settle_museum / settle_lighthouse (:573-586)
+      int q = CTD_OPT_TARGET(d), t = CTD_OPT_CARD_A(d);
+      int c = ctd_take_like(w.bld[q], w.n_bld[q], t);
+      w.gold[p] -= (int8_t)(ctd_ccost(c) - 1);
+      ctd_disc_push(w, c);
+      if (ctd_count_type(w.bld[q], w.n_bld[q], t) > 1) w.replicas[q] -= 1;
+      if (t == 34) {
+        for (int i = 0; i < w.n_mus[q]; ++i) ctd_disc_push(w, w.mus[q][i]);
+        w.n_mus[q] = 0;
+      }
+      if (t == 29 && (w.pflags[q] & CTD_PF_LIGHTHOUSE)) {
+        w.pflags[q] &= (uint8_t)~CTD_PF_LIGHTHOUSE;
+        w.pflags[p] |= CTD_PF_LIGHTHOUSE;
+      }
+      ctd_to5(w, p);
+      w.done |= CTD_DM_CHARACTER;
+      int owner = -1;  // get_graveyard_owner (:597-601)
+      for (int x = 0; x < 6; ++x) if (ctd_owns(w, x, 24)) { owner = x; break; }
+      if (owner >= 0 && owner != p) {
+        w.state = 6;
+        w.player = (uint8_t)owner;
+        w.next_player = (uint8_t)p;
+        w.next_mode = CTD_NEXT_RESET_CA;  // GameState(..., already_done_moves=["character_ability"]) (:535)
+      }
+      break;
+    }
+    default: w.err |= CTD_ERR_UNIMPL; break;
+  }
+  ctd_is_last_round(w);
+  ++w.steps;
+  return won;
+}
+
+// run_utils.create_game (run_utils.py:20-27)
+CTD_HD inline void ctd_new_game(CtdWork& w, uint64_t seed, uint64_t gid, int ruleset) {
+  ctd_chance_init(w, seed, gid, 0);
+  ctd_deal_preset(w, ruleset);
+  ctd_setup_round(w);
+}
+
+// ------------------------------------------------------------------------------------------ pack / unpack
+// Scalar forms (definition of the layout); ctd_warp.cuh has the lane-parallel device forms.
+CTD_HD inline void ctd_pack(const CtdWork& w, ctd_state* s) {
+  uint8_t* raw = (uint8_t*)s;
+  for (int i = 0; i < CTD_STATE_BYTES; ++i) raw[i] = 0;
+  int pos = 0, c = 0;
+  bool ovf = false;
+  auto put = [&](const uint8_t* a, int n) {
+    s->off[c++] = (uint8_t)pos;
+    for (int i = 0; i < n; ++i) { if (pos < 128) s->arena[pos++] = a[i]; else ovf = true; }
+  };
+  for (int p = 0; p < 6; ++p) {
+    put(w.hand[p], w.n_hand[p]); put(w.bld[p], w.n_bld[p]); put(w.mus[p], w.n_mus[p]); put(w.jd[p], w.n_jd[p]);
+  }
+  s->off[c++] = (uint8_t)pos;
+  for (int i = 0; i < w.n_deck; ++i) { if (pos < 128) s->arena[pos++] = w.deck[(w.deck_head + i) & (CTD_DECK_CAP - 1)]; else ovf = true; }
+  put(w.disc, w.n_disc);
+  s->off[c] = (uint8_t)pos;
+  for (int p = 0; p < 6; ++p) {
+    s->gold[p] = w.gold[p]; s->role[p] = w.role[p]; s->replicas[p] = w.replicas[p]; s->pflags[p] = w.pflags[p];
+    s->order[p] = w.order[p]; s->used_roles[p] = w.used_roles[p]; s->points[p] = w.points[p];
+  }
+  for (int r = 0; r < 8; ++r) { s->rprops[r] = w.rprops[r]; s->variant[r] = w.variant[r]; }
+  s->used_len = w.used_len; s->rtc_mask = w.rtc_mask; s->state = w.state; s->player = w.player; s->done = w.done;
+  s->done_builds = (uint8_t)(w.n_trade | (w.n_nontrade << 4));
+  const bool interrupt = w.state == 4 || (w.state >= 6 && w.state <= 10);
+  s->next_player = interrupt ? w.next_player : 0;
+  s->next_mode = interrupt ? w.next_mode : 0;
+  s->crown = w.crown; s->gflags = w.gflags; s->winner = w.winner; s->wiz_target = w.wiz_target;
+  s->warrant_building = w.warrant_building; s->ruleset = w.ruleset;
+  s->err = (uint8_t)(w.err | (ovf ? CTD_ERR_OVERFLOW : 0));
+  s->rng_draws = w.draws; s->tape_pos = w.tape_pos; s->steps = w.steps;
+  s->gid = (uint64_t)w.g0 | ((uint64_t)w.g1 << 32);
+}
+
+CTD_HD inline void ctd_unpack(const ctd_state* s, CtdWork& w) {
+  int c = 0;
+  auto get = [&](uint8_t* a, uint8_t& n, int cap) {
+    int b = s->off[c], e = s->off[c + 1];
+    ++c;
+    int len = e - b;
+    if (len < 0) len = 0;
+    if (len > cap) { len = cap; w.err |= CTD_ERR_OVERFLOW; }
+    for (int i = 0; i < len; ++i) a[i] = s->arena[(b + i) & 127];
+    n = (uint8_t)len;
+  };
+  w.err = s->err;
+  for (int p = 0; p < 6; ++p) {
+    get(w.hand[p], w.n_hand[p], CTD_HAND_CAP); get(w.bld[p], w.n_bld[p], CTD_BLD_CAP);
+    get(w.mus[p], w.n_mus[p], CTD_MUS_CAP); get(w.jd[p], w.n_jd[p], CTD_JD_CAP);
+  }
+  w.deck_head = 0;
+  get(w.deck, w.n_deck, CTD_DECK_CAP - 1);
+  get(w.disc, w.n_disc, CTD_DISC_CAP);
+  for (int p = 0; p < 6; ++p) {
+    w.gold[p] = s->gold[p]; w.role[p] = s->role[p]; w.replicas[p] = s->replicas[p]; w.pflags[p] = s->pflags[p];
+    w.order[p] = s->order[p]; w.used_roles[p] = s->used_roles[p]; w.points[p] = s->points[p];
+  }
+  for (int r = 0; r < 8; ++r) { w.rprops[r] = s->rprops[r]; w.variant[r] = s->variant[r]; }
+  w.used_len = s->used_len; w.rtc_mask = s->rtc_mask; w.state = s->state; w.player = s->player; w.done = s->done;
+  w.n_trade = s->done_builds & 15; w.n_nontrade = s->done_builds >> 4;
+  w.next_player = s->next_player; w.next_mode = s->next_mode; w.crown = s->crown; w.gflags = s->gflags;
+  w.winner = s->winner; w.wiz_target = s->wiz_target; w.warrant_building = s->warrant_building;
+  w.ruleset = s->ruleset;
+  w.draws = s->rng_draws; w.buf_blk = 0xFFFFFFFFu; w.tape_pos = s->tape_pos; w.steps = s->steps;
+  w.g0 = (uint32_t)s->gid; w.g1 = (uint32_t)(s->gid >> 32);
+}

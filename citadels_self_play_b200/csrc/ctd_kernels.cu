@@ -1,0 +1,492 @@
+// ctd_kernels.cu -- sm_100a kernels and the C ABI (include/citadels_b200.h) of the Citadels rollout engine.
+//
+// Layout of the data path:
+//   HBM     ctd_state slots[capacity]          256 B records, 2 x 128 B lines each, one warp moves one
+//                                              record as 32 x 8 B (coalesced)
+//   smem    CtdWork per warp (1.3 KB)          the game lives here for its whole fused playout (~420 steps)
+//   regs    option count / selection           warp-cooperative enumeration (ctd_warp.cuh)
+// One warp owns one game.  The playout kernel is persistent: warps pull game ids from a global counter so
+// that the 244..632-step spread of game lengths does not leave SMs idle at the tail.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+
+#include "ctd_engine.cuh"
+#include "ctd_warp.cuh"
+
+#define CTD_WARPS_PER_BLOCK 8
+#define CTD_BLOCK (CTD_WARPS_PER_BLOCK * 32)
+#define CTD_FULL 0xFFFFFFFFu
+
+// ------------------------------------------------------------------------------------------ device helpers
+// move one 256 B record between HBM and the warp's shared staging buffer: 32 lanes x 8 B
+__device__ __forceinline__ void ctd_record_load(const ctd_state* g, ctd_state* s, int lane) {
+  reinterpret_cast<uint64_t*>(s)[lane] = reinterpret_cast<const uint64_t*>(g)[lane];
+  __syncwarp();
+}
+__device__ __forceinline__ void ctd_record_store(ctd_state* g, const ctd_state* s, int lane) {
+  __syncwarp();
+  reinterpret_cast<uint64_t*>(g)[lane] = reinterpret_cast<const uint64_t*>(s)[lane];
+}
+
+struct CtdTapes {
+  const uint8_t* tape;
+  const uint32_t* off;
+  uint32_t n;
+};
+__device__ __forceinline__ void ctd_attach_tape(CtdWork& w, const CtdTapes& t, uint32_t slot) {
+  if (t.tape != nullptr && slot < t.n) {
+    w.tape = t.tape + t.off[slot];
+    w.tape_len = t.off[slot + 1] - t.off[slot];
+  } else {
+    w.tape = nullptr;
+    w.tape_len = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(CTD_BLOCK) ctd_k_reset(ctd_state* slots, uint32_t n, uint64_t seed, uint64_t first_gid,
+                                                         int ruleset, CtdTapes tapes) {
+  __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
+  __shared__ ctd_state stage[CTD_WARPS_PER_BLOCK];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t slot = blockIdx.x * CTD_WARPS_PER_BLOCK + wib;
+  if (slot >= n) return;
+  CtdWork& w = works[wib];
+  if (lane == 0) {
+    ctd_chance_init(w, seed, first_gid + slot, 0);
+    ctd_attach_tape(w, tapes, slot);
+    ctd_deal_preset(w, ruleset);
+    ctd_setup_round(w);
+    ctd_pack(w, &stage[wib]);
+  }
+  ctd_record_store(&slots[slot], &stage[wib], lane);
+}
+
+__global__ void __launch_bounds__(CTD_BLOCK) ctd_k_enumerate(const ctd_state* slots, uint32_t n, ctd_option* opts,
+                                                             uint32_t* counts, uint32_t stride, uint8_t* errs) {
+  __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
+  __shared__ ctd_state stage[CTD_WARPS_PER_BLOCK];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t slot = blockIdx.x * CTD_WARPS_PER_BLOCK + wib;
+  if (slot >= n) return;
+  CtdWork& w = works[wib];
+  ctd_record_load(&slots[slot], &stage[wib], lane);
+  if (lane == 0) {
+    ctd_unpack(&stage[wib], w);
+    CtdEmit e{opts + (size_t)slot * stride, stride, 0, 0xFFFFFFFFu, 0};
+    ctd_enumerate(w, e);
+    counts[slot] = e.n;
+    errs[slot] = w.err;
+  }
+}
+
+__global__ void __launch_bounds__(CTD_BLOCK) ctd_k_step(ctd_state* slots, uint32_t n, const ctd_option* chosen,
+                                                        int8_t* winner, uint64_t seed, CtdTapes tapes) {
+  __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
+  __shared__ ctd_state stage[CTD_WARPS_PER_BLOCK];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t slot = blockIdx.x * CTD_WARPS_PER_BLOCK + wib;
+  if (slot >= n) return;
+  const ctd_option d = chosen[slot];
+  if (d == 0) {  // role_pick by seat 0 always carries a rank field, so 0 is never a real option
+    if (lane == 0) winner[slot] = -1;
+    return;
+  }
+  CtdWork& w = works[wib];
+  ctd_record_load(&slots[slot], &stage[wib], lane);
+  if (lane == 0) {
+    ctd_unpack(&stage[wib], w);
+    w.k0 = (uint32_t)seed; w.k1 = (uint32_t)(seed >> 32);
+    ctd_attach_tape(w, tapes, slot);
+    bool won = ctd_apply(w, d);
+    winner[slot] = won ? w.winner : (int8_t)-1;
+    ctd_pack(w, &stage[wib]);
+  }
+  ctd_record_store(&slots[slot], &stage[wib], lane);
+}
+
+struct CtdPlayoutArgs {
+  uint64_t n_games, seed, first_gid;
+  int ruleset;
+  uint32_t max_steps;
+  int8_t* winner;    // [n] or null
+  int8_t* points6;   // [n][6] or null
+  uint16_t* steps;   // [n] or null
+  ctd_playout_stats* stats;
+  unsigned long long* counter;
+  ctd_state* slots;  // non-null: continue from slots[0..n) instead of dealing new games
+};
+
+// per-warp partial statistics, kept in lane 0's registers and flushed once
+struct CtdWarpStats {
+  unsigned long long games, steps, steps_sq, errors, max_steps;
+  unsigned long long wins[6];
+  long long psum[6];
+  unsigned long long psq[6];
+};
+
+__global__ void __launch_bounds__(CTD_BLOCK) ctd_k_playout(CtdPlayoutArgs a) {
+  __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
+  __shared__ ctd_state stage[CTD_WARPS_PER_BLOCK];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  CtdWork& w = works[wib];
+  CtdWarpStats st;
+  memset(&st, 0, sizeof(st));
+  for (;;) {
+    unsigned long long g = 0;
+    if (lane == 0) g = atomicAdd(a.counter, 1ull);
+    g = __shfl_sync(CTD_FULL, g, 0);
+    if (g >= a.n_games) break;
+    if (a.slots != nullptr) {
+      ctd_record_load(&a.slots[g], &stage[wib], lane);
+      if (lane == 0) {
+        ctd_unpack(&stage[wib], w);
+        w.k0 = (uint32_t)a.seed; w.k1 = (uint32_t)(a.seed >> 32);
+        w.tape = nullptr; w.tape_len = 0;
+      }
+    } else if (lane == 0) {
+      ctd_new_game(w, a.seed, a.first_gid + g, a.ruleset);
+    }
+    __syncwarp();
+    const uint32_t steps0 = w.steps;
+    // ---- the hot loop: run_utils.py:37-41 ----
+    for (;;) {
+      bool stop = (w.gflags & 2) || w.err || (w.steps - steps0) >= a.max_steps;
+      if (stop) break;
+      // warp-cooperative: count the legal options, draw k, select the k-th (ctd_warp.cuh)
+      uint64_t d = ctd_warp_choose(w, lane);
+      if (lane == 0) {
+        if (d == 0) w.err |= CTD_ERR_REF_RAISE;
+        else ctd_apply(w, d);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) {
+      if (!(w.gflags & 2) && !w.err) w.err |= CTD_ERR_MAXSTEPS;
+      const uint32_t ns = w.steps - steps0;
+      if (a.winner) a.winner[g] = w.winner;
+      if (a.steps) a.steps[g] = (uint16_t)ns;
+      if (a.points6)
+        for (int p = 0; p < 6; ++p) a.points6[g * 6 + p] = w.points[p];
+      st.games += 1;
+      st.steps += ns;
+      st.steps_sq += (unsigned long long)ns * ns;
+      if (ns > st.max_steps) st.max_steps = ns;
+      if (w.err) st.errors += 1;
+      if (w.winner >= 0) st.wins[w.winner] += 1;
+      for (int p = 0; p < 6; ++p) {
+        st.psum[p] += w.points[p];
+        st.psq[p] += (unsigned long long)((int)w.points[p] * (int)w.points[p]);
+      }
+      if (a.slots != nullptr) ctd_pack(w, &stage[wib]);
+    }
+    if (a.slots != nullptr) ctd_record_store(&a.slots[g], &stage[wib], lane);
+    __syncwarp();
+  }
+  if (lane == 0 && st.games != 0 && a.stats != nullptr) {
+    ctd_playout_stats* s = a.stats;
+    atomicAdd((unsigned long long*)&s->games, st.games);
+    atomicAdd((unsigned long long*)&s->steps, st.steps);
+    atomicAdd((unsigned long long*)&s->steps_sq, st.steps_sq);
+    atomicAdd((unsigned long long*)&s->errors, st.errors);
+    atomicMax((unsigned long long*)&s->max_steps, st.max_steps);
+    for (int p = 0; p < 6; ++p) {
+      atomicAdd((unsigned long long*)&s->wins[p], st.wins[p]);
+      atomicAdd((unsigned long long*)&s->points_sum[p], (unsigned long long)st.psum[p]);
+      atomicAdd((unsigned long long*)&s->points_sq[p], st.psq[p]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side / C ABI
+struct ctd_engine {
+  int device;
+  uint32_t capacity;
+  ctd_state* d_slots;
+  cudaStream_t stream;
+  bool own_stream;
+  uint64_t seed;
+  uint64_t launches;
+  // replay tapes
+  uint8_t* d_tape;
+  uint32_t* d_tape_off;
+  uint32_t n_tapes;
+  // scratch
+  void* d_scratch;
+  size_t scratch_bytes;
+  unsigned long long* d_counter;
+  ctd_playout_stats* d_stats;
+  cudaEvent_t ev0, ev1;
+  int sm_count;
+  char err[256];
+};
+
+static ctd_status ctd_fail(ctd_engine* e, cudaError_t c, const char* where) {
+  snprintf(e->err, sizeof(e->err), "%s: %s", where, cudaGetErrorString(c));
+  return CTD_ECUDA;
+}
+#define CTD_CUDA(e, call)                                   \
+  do {                                                      \
+    cudaError_t _c = (call);                                \
+    if (_c != cudaSuccess) return ctd_fail(e, _c, #call);   \
+  } while (0)
+
+static ctd_status ctd_scratch(ctd_engine* e, size_t bytes) {
+  if (bytes <= e->scratch_bytes) return CTD_OK;
+  if (e->d_scratch) CTD_CUDA(e, cudaFree(e->d_scratch));
+  e->d_scratch = nullptr;
+  e->scratch_bytes = 0;
+  CTD_CUDA(e, cudaMalloc(&e->d_scratch, bytes));
+  e->scratch_bytes = bytes;
+  return CTD_OK;
+}
+static CtdTapes ctd_tapes(const ctd_engine* e) { return CtdTapes{e->d_tape, e->d_tape_off, e->n_tapes}; }
+static inline uint32_t ctd_blocks(uint32_t n) { return (n + CTD_WARPS_PER_BLOCK - 1) / CTD_WARPS_PER_BLOCK; }
+
+extern "C" {
+
+ctd_status ctd_create(int device, uint32_t capacity, ctd_engine** out) {
+  if (!out || capacity == 0) return CTD_EARG;
+  ctd_engine* e = new (std::nothrow) ctd_engine();
+  if (!e) return CTD_ENOMEM;
+  memset(e, 0, sizeof(*e));
+  e->device = device;
+  e->capacity = capacity;
+  *out = e;
+  CTD_CUDA(e, cudaSetDevice(device));
+  CTD_CUDA(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  e->own_stream = true;
+  CTD_CUDA(e, cudaMalloc((void**)&e->d_slots, (size_t)capacity * sizeof(ctd_state)));
+  CTD_CUDA(e, cudaMemsetAsync(e->d_slots, 0, (size_t)capacity * sizeof(ctd_state), e->stream));
+  CTD_CUDA(e, cudaMalloc((void**)&e->d_counter, sizeof(unsigned long long)));
+  CTD_CUDA(e, cudaMalloc((void**)&e->d_stats, sizeof(ctd_playout_stats)));
+  CTD_CUDA(e, cudaEventCreate(&e->ev0));
+  CTD_CUDA(e, cudaEventCreate(&e->ev1));
+  CTD_CUDA(e, cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device));
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  return CTD_OK;
+}
+
+void ctd_destroy(ctd_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->d_slots) cudaFree(e->d_slots);
+  if (e->d_tape) cudaFree(e->d_tape);
+  if (e->d_tape_off) cudaFree(e->d_tape_off);
+  if (e->d_scratch) cudaFree(e->d_scratch);
+  if (e->d_counter) cudaFree(e->d_counter);
+  if (e->d_stats) cudaFree(e->d_stats);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+const char* ctd_last_error(const ctd_engine* e) { return e ? e->err : "null engine"; }
+uint64_t ctd_launch_count(const ctd_engine* e) { return e ? e->launches : 0; }
+
+ctd_status ctd_sync(ctd_engine* e) {
+  if (!e) return CTD_EARG;
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  return CTD_OK;
+}
+
+ctd_status ctd_set_stream(ctd_engine* e, void* cuda_stream) {
+  if (!e) return CTD_EARG;
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (e->own_stream) CTD_CUDA(e, cudaStreamDestroy(e->stream));
+  e->stream = (cudaStream_t)cuda_stream;
+  e->own_stream = false;
+  return CTD_OK;
+}
+
+ctd_status ctd_set_seed(ctd_engine* e, uint64_t seed) {
+  if (!e) return CTD_EARG;
+  e->seed = seed;
+  return CTD_OK;
+}
+
+ctd_status ctd_reset(ctd_engine* e, uint32_t n, uint64_t seed, uint64_t first_gid, int ruleset) {
+  if (!e || n > e->capacity || (ruleset != CTD_RULESET_PRESET && ruleset != CTD_RULESET_CLASSIC)) return CTD_EARG;
+  if (n == 0) return CTD_OK;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  e->seed = seed;
+  ctd_k_reset<<<ctd_blocks(n), CTD_BLOCK, 0, e->stream>>>(e->d_slots, n, seed, first_gid, ruleset, ctd_tapes(e));
+  e->launches++;
+  CTD_CUDA(e, cudaGetLastError());
+  return CTD_OK;
+}
+
+ctd_status ctd_load_states(ctd_engine* e, uint32_t first_slot, uint32_t n, const ctd_state* states) {
+  if (!e || !states || (uint64_t)first_slot + n > e->capacity) return CTD_EARG;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  CTD_CUDA(e, cudaMemcpyAsync(e->d_slots + first_slot, states, (size_t)n * sizeof(ctd_state), cudaMemcpyHostToDevice,
+                              e->stream));
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  return CTD_OK;
+}
+
+ctd_status ctd_store_states(ctd_engine* e, uint32_t first_slot, uint32_t n, ctd_state* states) {
+  if (!e || !states || (uint64_t)first_slot + n > e->capacity) return CTD_EARG;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  CTD_CUDA(e, cudaMemcpyAsync(states, e->d_slots + first_slot, (size_t)n * sizeof(ctd_state), cudaMemcpyDeviceToHost,
+                              e->stream));
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  return CTD_OK;
+}
+
+ctd_status ctd_states_dev(ctd_engine* e, void** dev_ptr) {
+  if (!e || !dev_ptr) return CTD_EARG;
+  *dev_ptr = e->d_slots;
+  return CTD_OK;
+}
+
+ctd_status ctd_set_tapes(ctd_engine* e, uint32_t n, const uint8_t* tape, const uint32_t* tape_off) {
+  if (!e || n > e->capacity) return CTD_EARG;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (e->d_tape) { CTD_CUDA(e, cudaFree(e->d_tape)); e->d_tape = nullptr; }
+  if (e->d_tape_off) { CTD_CUDA(e, cudaFree(e->d_tape_off)); e->d_tape_off = nullptr; }
+  e->n_tapes = 0;
+  if (n == 0) return CTD_OK;
+  if (!tape || !tape_off) return CTD_EARG;
+  size_t bytes = tape_off[n];
+  CTD_CUDA(e, cudaMalloc((void**)&e->d_tape, bytes ? bytes : 1));
+  CTD_CUDA(e, cudaMalloc((void**)&e->d_tape_off, (size_t)(n + 1) * sizeof(uint32_t)));
+  CTD_CUDA(e, cudaMemcpy(e->d_tape, tape, bytes, cudaMemcpyHostToDevice));
+  CTD_CUDA(e, cudaMemcpy(e->d_tape_off, tape_off, (size_t)(n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  e->n_tapes = n;
+  return CTD_OK;
+}
+
+ctd_status ctd_enumerate(ctd_engine* e, uint32_t n, ctd_option* opts, uint32_t* counts, uint32_t stride) {
+  if (!e || !opts || !counts || n > e->capacity || stride == 0) return CTD_EARG;
+  if (n == 0) return CTD_OK;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  size_t ob = (size_t)n * stride * sizeof(ctd_option), cb = (size_t)n * sizeof(uint32_t);
+  size_t cb_al = (cb + 255) & ~(size_t)255;
+  ctd_status s = ctd_scratch(e, ob + cb_al + n);
+  if (s != CTD_OK) return s;
+  ctd_option* d_opts = (ctd_option*)e->d_scratch;
+  uint32_t* d_counts = (uint32_t*)((char*)e->d_scratch + ob);
+  uint8_t* d_errs = (uint8_t*)e->d_scratch + ob + cb_al;
+  ctd_k_enumerate<<<ctd_blocks(n), CTD_BLOCK, 0, e->stream>>>(e->d_slots, n, d_opts, d_counts, stride, d_errs);
+  e->launches++;
+  CTD_CUDA(e, cudaGetLastError());
+  CTD_CUDA(e, cudaMemcpyAsync(counts, d_counts, cb, cudaMemcpyDeviceToHost, e->stream));
+  CTD_CUDA(e, cudaMemcpyAsync(opts, d_opts, ob, cudaMemcpyDeviceToHost, e->stream));
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  for (uint32_t i = 0; i < n; ++i)
+    if (counts[i] > stride) return CTD_ECAP;
+  return CTD_OK;
+}
+
+ctd_status ctd_step(ctd_engine* e, uint32_t n, const ctd_option* chosen, int8_t* winner) {
+  if (!e || !chosen || n > e->capacity) return CTD_EARG;
+  if (n == 0) return CTD_OK;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  size_t ob = (size_t)n * sizeof(ctd_option);
+  ctd_status s = ctd_scratch(e, ob + n);
+  if (s != CTD_OK) return s;
+  ctd_option* d_chosen = (ctd_option*)e->d_scratch;
+  int8_t* d_winner = (int8_t*)e->d_scratch + ob;
+  CTD_CUDA(e, cudaMemcpyAsync(d_chosen, chosen, ob, cudaMemcpyHostToDevice, e->stream));
+  ctd_k_step<<<ctd_blocks(n), CTD_BLOCK, 0, e->stream>>>(e->d_slots, n, d_chosen, d_winner, e->seed, ctd_tapes(e));
+  e->launches++;
+  CTD_CUDA(e, cudaGetLastError());
+  if (winner) CTD_CUDA(e, cudaMemcpyAsync(winner, d_winner, n, cudaMemcpyDeviceToHost, e->stream));
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  return CTD_OK;
+}
+
+// persistent grid: enough CTAs to fill every SM at the kernel's occupancy
+static ctd_status ctd_playout_grid(ctd_engine* e, uint64_t n_games, int* grid) {
+  int per_sm = 0;
+  CTD_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctd_k_playout, CTD_BLOCK, 0));
+  if (per_sm < 1) per_sm = 1;
+  uint64_t want = (uint64_t)e->sm_count * per_sm;
+  uint64_t need = (n_games + CTD_WARPS_PER_BLOCK - 1) / CTD_WARPS_PER_BLOCK;
+  *grid = (int)(need < want ? need : want);
+  if (*grid < 1) *grid = 1;
+  return CTD_OK;
+}
+
+static ctd_status ctd_playout_launch(ctd_engine* e, CtdPlayoutArgs& a, ctd_playout_stats* stats, float* elapsed_ms) {
+  int grid = 1;
+  ctd_status s = ctd_playout_grid(e, a.n_games, &grid);
+  if (s != CTD_OK) return s;
+  CTD_CUDA(e, cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream));
+  CTD_CUDA(e, cudaMemsetAsync(e->d_stats, 0, sizeof(ctd_playout_stats), e->stream));
+  a.counter = e->d_counter;
+  a.stats = e->d_stats;
+  CTD_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+  ctd_k_playout<<<grid, CTD_BLOCK, 0, e->stream>>>(a);
+  e->launches++;
+  CTD_CUDA(e, cudaGetLastError());
+  CTD_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+  if (stats) CTD_CUDA(e, cudaMemcpyAsync(stats, e->d_stats, sizeof(ctd_playout_stats), cudaMemcpyDeviceToHost, e->stream));
+  (void)elapsed_ms;
+  return CTD_OK;
+}
+
+ctd_status ctd_playout_dev(ctd_engine* e, uint64_t n_games, uint64_t seed, uint64_t first_gid, int ruleset,
+                           uint32_t max_steps, ctd_playout_stats* stats, float* elapsed_ms) {
+  if (!e || (ruleset != CTD_RULESET_PRESET && ruleset != CTD_RULESET_CLASSIC)) return CTD_EARG;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  CtdPlayoutArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_games = n_games; a.seed = seed; a.first_gid = first_gid; a.ruleset = ruleset; a.max_steps = max_steps;
+  ctd_status s = ctd_playout_launch(e, a, stats, elapsed_ms);
+  if (s != CTD_OK) return s;
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (elapsed_ms) CTD_CUDA(e, cudaEventElapsedTime(elapsed_ms, e->ev0, e->ev1));
+  return CTD_OK;
+}
+
+ctd_status ctd_playout(ctd_engine* e, uint64_t n_games, uint64_t seed, uint64_t first_gid, int ruleset,
+                       uint32_t max_steps, int8_t* winner, int8_t* points6, uint16_t* steps, ctd_playout_stats* stats) {
+  if (!e || (ruleset != CTD_RULESET_PRESET && ruleset != CTD_RULESET_CLASSIC)) return CTD_EARG;
+  if (n_games == 0) { if (stats) memset(stats, 0, sizeof(*stats)); return CTD_OK; }
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  size_t wb = (n_games + 255) & ~(size_t)255, pb = (n_games * 6 + 255) & ~(size_t)255, sb = n_games * 2;
+  ctd_status s = ctd_scratch(e, wb + pb + sb);
+  if (s != CTD_OK) return s;
+  CtdPlayoutArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_games = n_games; a.seed = seed; a.first_gid = first_gid; a.ruleset = ruleset; a.max_steps = max_steps;
+  a.winner = (int8_t*)e->d_scratch;
+  a.points6 = (int8_t*)e->d_scratch + wb;
+  a.steps = (uint16_t*)((char*)e->d_scratch + wb + pb);
+  s = ctd_playout_launch(e, a, stats, nullptr);
+  if (s != CTD_OK) return s;
+  if (winner) CTD_CUDA(e, cudaMemcpyAsync(winner, a.winner, n_games, cudaMemcpyDeviceToHost, e->stream));
+  if (points6) CTD_CUDA(e, cudaMemcpyAsync(points6, a.points6, n_games * 6, cudaMemcpyDeviceToHost, e->stream));
+  if (steps) CTD_CUDA(e, cudaMemcpyAsync(steps, a.steps, sb, cudaMemcpyDeviceToHost, e->stream));
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  return CTD_OK;
+}
+
+ctd_status ctd_playout_slots(ctd_engine* e, uint32_t n, uint32_t max_steps, int8_t* winner, uint16_t* steps) {
+  if (!e || n > e->capacity) return CTD_EARG;
+  if (n == 0) return CTD_OK;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  size_t wb = ((size_t)n + 255) & ~(size_t)255, sb = (size_t)n * 2;
+  ctd_status s = ctd_scratch(e, wb + sb);
+  if (s != CTD_OK) return s;
+  CtdPlayoutArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_games = n; a.seed = e->seed; a.max_steps = max_steps; a.slots = e->d_slots;
+  a.winner = (int8_t*)e->d_scratch;
+  a.steps = (uint16_t*)((char*)e->d_scratch + wb);
+  s = ctd_playout_launch(e, a, nullptr, nullptr);
+  if (s != CTD_OK) return s;
+  if (winner) CTD_CUDA(e, cudaMemcpyAsync(winner, a.winner, n, cudaMemcpyDeviceToHost, e->stream));
+  if (steps) CTD_CUDA(e, cudaMemcpyAsync(steps, a.steps, sb, cudaMemcpyDeviceToHost, e->stream));
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  return CTD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+"""Batch engine: a thin numpy-facing wrapper over the C ABI.  One Engine == one ctd_engine handle ==
+`capacity` game slots in HBM on one device."""
+import ctypes
+import numpy as np
+
+from . import _lib
+from .layout import STATE_BYTES
+
+RULESET_PRESET, RULESET_CLASSIC = 0, 1
+DEFAULT_SEED = 0xC17ADE15
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class Engine:
+    def __init__(self, capacity=1024, device=0):
+        self._lib = _lib.load()
+        h = ctypes.c_void_p()
+        st = self._lib.ctd_create(int(device), int(capacity), ctypes.byref(h))
+        self._h = h
+        if st != 0:
+            msg = self._lib.ctd_last_error(h).decode() if h else "ctd_create failed"
+            raise EngineError("ctd_create: status %d (%s)" % (st, msg))
+        self.capacity = int(capacity)
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ctd_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st, what, allow=()):
+        if st != 0 and st not in allow:
+            raise EngineError("%s: status %d (%s)" % (what, st, self._lib.ctd_last_error(self._h).decode()))
+        return st
+
+    # ---- state ----
+    def reset(self, n, seed=DEFAULT_SEED, first_gid=0, ruleset=RULESET_PRESET):
+        self._check(self._lib.ctd_reset(self._h, n, seed, first_gid, ruleset), "ctd_reset")
+
+    def set_seed(self, seed):
+        self._check(self._lib.ctd_set_seed(self._h, seed), "ctd_set_seed")
+
+    def load_states(self, states, first_slot=0):
+        a = np.ascontiguousarray(states, dtype=np.uint8).reshape(-1, STATE_BYTES)
+        self._check(self._lib.ctd_load_states(self._h, first_slot, len(a), a.ctypes.data), "ctd_load_states")
+
+    def store_states(self, n, first_slot=0):
+        a = np.empty((n, STATE_BYTES), dtype=np.uint8)
+        self._check(self._lib.ctd_store_states(self._h, first_slot, n, a.ctypes.data), "ctd_store_states")
+        return a
+
+    def states_dev_ptr(self):
+        p = ctypes.c_void_p()
+        self._check(self._lib.ctd_states_dev(self._h, ctypes.byref(p)), "ctd_states_dev")
+        return p.value
+
+    def set_tapes(self, tapes):
+        """tapes: list of uint8 arrays (one per slot) or None to clear."""
+        if not tapes:
+            self._check(self._lib.ctd_set_tapes(self._h, 0, None, None), "ctd_set_tapes")
+            return
+        off = np.zeros(len(tapes) + 1, dtype=np.uint32)
+        off[1:] = np.cumsum([len(t) for t in tapes])
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=np.uint8) for t in tapes]))
+        if len(flat) == 0:
+            flat = np.zeros(1, dtype=np.uint8)
+        self._check(self._lib.ctd_set_tapes(self._h, len(tapes), flat.ctypes.data, off.ctypes.data), "ctd_set_tapes")
+
+    # ---- hot path ----
+    def enumerate(self, n, stride=128):
+        """-> (opts[n, stride] uint64, counts[n] uint32); grows stride until every list fits."""
+        while True:
+            opts = np.zeros((n, stride), dtype=np.uint64)
+            counts = np.zeros(n, dtype=np.uint32)
+            st = self._check(self._lib.ctd_enumerate(self._h, n, opts.ctypes.data, counts.ctypes.data, stride),
+                             "ctd_enumerate", allow=(3,))
+            if st == 0:
+                return opts, counts
+            stride = int(max(counts.max(), stride * 2))
+
+    def step(self, chosen):
+        c = np.ascontiguousarray(chosen, dtype=np.uint64)
+        winner = np.empty(len(c), dtype=np.int8)
+        self._check(self._lib.ctd_step(self._h, len(c), c.ctypes.data, winner.ctypes.data), "ctd_step")
+        return winner
+
+    def playout(self, n_games, seed=DEFAULT_SEED, first_gid=0, ruleset=RULESET_PRESET, max_steps=4096,
+                outputs=True):
+        """Fused random playouts of new games.  -> dict(winner, points, steps, stats)."""
+        stats = _lib.PlayoutStats()
+        if outputs:
+            winner = np.empty(n_games, dtype=np.int8)
+            points = np.empty((n_games, 6), dtype=np.int8)
+            steps = np.empty(n_games, dtype=np.uint16)
+            self._check(self._lib.ctd_playout(self._h, n_games, seed, first_gid, ruleset, max_steps, winner.ctypes.data,
+                                              points.ctypes.data, steps.ctypes.data, ctypes.byref(stats)), "ctd_playout")
+            return dict(winner=winner, points=points, steps=steps, stats=stats_dict(stats))
+        ms = ctypes.c_float()
+        self._check(self._lib.ctd_playout_dev(self._h, n_games, seed, first_gid, ruleset, max_steps, ctypes.byref(stats),
+                                              ctypes.byref(ms)), "ctd_playout_dev")
+        d = stats_dict(stats)
+        d["kernel_ms"] = ms.value
+        return dict(stats=d)
+
+    def playout_slots(self, n, max_steps=4096):
+        winner = np.empty(n, dtype=np.int8)
+        steps = np.empty(n, dtype=np.uint16)
+        self._check(self._lib.ctd_playout_slots(self._h, n, max_steps, winner.ctypes.data, steps.ctypes.data),
+                    "ctd_playout_slots")
+        return winner, steps
+
+    def sync(self):
+        self._check(self._lib.ctd_sync(self._h), "ctd_sync")
+
+    @property
+    def launches(self):
+        return int(self._lib.ctd_launch_count(self._h))
+
+
+def stats_dict(s):
+    return dict(games=int(s.games), steps=int(s.steps), steps_sq=int(s.steps_sq), wins=[int(x) for x in s.wins],
+                points_sum=[int(x) for x in s.points_sum], points_sq=[int(x) for x in s.points_sq],
+                errors=int(s.errors), max_steps=int(s.max_steps))

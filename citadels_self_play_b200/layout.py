@@ -1,0 +1,51 @@
+"""Byte layout of the packed game record and bit layout of option descriptors
+(mirror of include/citadels_b200.h; kept in Python so the facade can decode without the oracle)."""
+import numpy as np
+
+STATE_BYTES = 256
+STATE_VISIBLE_BYTES = 228
+
+STATE_DTYPE = np.dtype([
+    ("arena", np.uint8, 128), ("off", np.uint8, 28), ("gold", np.int8, 6), ("role", np.uint8, 6),
+    ("replicas", np.int8, 6), ("pflags", np.uint8, 6), ("rprops", np.uint8, 8), ("variant", np.uint8, 8),
+    ("order", np.uint8, 6), ("used_roles", np.uint8, 6), ("used_len", np.uint8), ("rtc_mask", np.uint8),
+    ("state", np.uint8), ("player", np.uint8), ("done", np.uint8), ("done_builds", np.uint8),
+    ("next_player", np.uint8), ("next_mode", np.uint8), ("crown", np.uint8), ("gflags", np.uint8),
+    ("winner", np.int8), ("wiz_target", np.uint8), ("points", np.int8, 6), ("warrant_building", np.uint8),
+    ("ruleset", np.uint8), ("err", np.uint8), ("pad0", np.uint8, 3), ("rng_draws", np.uint32),
+    ("tape_pos", np.uint32), ("steps", np.uint32), ("pad1", np.uint32), ("gid", np.uint64)])
+assert STATE_DTYPE.itemsize == STATE_BYTES
+
+# option kinds: index in the reference's action list (game/option.py:34-45)
+KIND_NAMES = [
+    "role_pick", "gold_or_card", "which_card_to_keep", "blackmail_response",
+    "reveal_blackmail_as_blackmailer", "reveal_warrant_as_magistrate", "build", "empty_option",
+    "finish_round", "ghost_town_color_choice", "smithy_choice", "laboratory_choice",
+    "magic_school_choice", "weapon_storage_choice", "lighthouse_choice", "museum_choice",
+    "graveyard", "take_gold_for_war", "assassination", "magistrate_warrant", "bewitching",
+    "steal", "blackmail", "spy", "magic_hand_change", "discard_and_draw", "look_at_hand",
+    "take_from_hand", "seer", "give_back_card", "take_crown_king", "give_crown",
+    "take_crown_pat", "bishop", "cardinal_exchange", "abbot_gold_or_card", "abbot_beg",
+    "merchant", "alchemist", "trader", "architect", "navigator_gold_card", "scholar",
+    "scholar_card_pick", "warlord_desctruction", "marshal_steal", "diplomat_exchange"]
+KIND = {n: i for i, n in enumerate(KIND_NAMES)}
+# named choices (game/option.py:69-83)
+NAMED_NAMES = ["gold", "card", "pay", "not_pay", "reveal", "not_reveal", "4gold", "4card", "trade", "war",
+               "religion", "lord", "unique"]
+SUIT_NAMES = ["trade", "war", "religion", "lord", "unique"]
+# role names by rank and variant (game/config.py:83-91)
+ROLES = [["Assassin", "Witch", "Magistrate"], ["Thief", "Spy", "Blackmailer"], ["Magician", "Wizard", "Seer"],
+         ["King", "Emperor", "Patrician"], ["Bishop", "Abbot", "Cardinal"], ["Merchant", "Alchemist", "Trader"],
+         ["Architect", "Navigator", "Scholar"], ["Warlord", "Diplomat", "Marshal"]]
+COST_OF_TYPE = [1, 2, 4, 2, 5, 3, 2, 3, 5, 1, 2, 3, 1, 4, 3, 5,
+                5, 3, 6, 2, 6, 5, 5, 6, 5, 6, 6, 3, 6, 3, 5, 5, 6, 5, 4, 6, 5, 4, 0, 5]
+SUIT_OF_TYPE = [0] * 6 + [1] * 4 + [2] * 3 + [3] * 3 + [4] * 24
+
+
+def opt_fields(d):
+    d = int(d)
+    rep = (d >> 32) & 0xF
+    return dict(kind=d & 0x3F, perp=(d >> 6) & 7, target=((d >> 9) & 7) - 1, a=((d >> 12) & 0x3F) - 1,
+                b=((d >> 18) & 0x3F) - 1, rank=((d >> 24) & 0xF) - 1, named=((d >> 28) & 0xF) - 1,
+                replica=rep - 16 if rep >= 8 else rep, build=(d >> 36) & 1, next_witch=(d >> 37) & 1,
+                crown=(d >> 38) & 1, count=(d >> 39) & 0x3F, r=(d >> 45) & 0x3F, j=(d >> 51) & 0x3FF)

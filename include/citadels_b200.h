@@ -74,7 +74,8 @@ typedef struct ctd_state {
   uint32_t rng_draws;    /* Philox draws consumed by this game so far */
   uint32_t tape_pos;     /* chance-tape cursor (replay mode) */
   uint32_t steps;        /* env steps applied to this slot */
-  uint8_t pad1[12];
+  uint32_t pad1;
+  uint64_t gid;          /* Philox game id of this slot (counter words 2,3) */
 } ctd_state;
 
 #define CTD_ERR_OVERFLOW 1   /* a container exceeded its on-chip capacity */
@@ -121,6 +122,9 @@ const char* ctd_last_error(const ctd_engine* e);
 ctd_status ctd_sync(ctd_engine* e);
 /* use an existing CUDA stream (cudaStream_t as void*); default is a stream the engine owns */
 ctd_status ctd_set_stream(ctd_engine* e, void* cuda_stream);
+
+/* Philox key used by ctd_step / ctd_playout_slots for slots that were loaded rather than reset */
+ctd_status ctd_set_seed(ctd_engine* e, uint64_t seed);
 
 /* ---- state in / out ---- */
 /* run_utils.create_game (run_utils.py:20-27): Game(preset=True) + setup_round() for slots [0,n);

@@ -1,0 +1,68 @@
+// Host build of the engine's rules code (ctd_engine.cuh) -- a TEST VEHICLE so the kernel logic can be
+// replayed against the golden traces without a GPU.  It is not part of the product and the package never
+// loads it (the product path fails loudly when the CUDA library is missing).
+#include "../../citadels_self_play_b200/csrc/ctd_engine.cuh"
+#include <string.h>
+
+static CtdWork g_w;
+
+static void chance_for(CtdWork& w, uint64_t seed, uint64_t gid, const uint8_t* tape, uint32_t tape_len) {
+  uint32_t draws = w.draws, tpos = w.tape_pos;
+  ctd_chance_init(w, seed, gid, draws);
+  w.tape = tape_len ? tape : nullptr;
+  w.tape_len = tape_len;
+  w.tape_pos = tpos;
+}
+
+extern "C" {
+void hs_new_game(uint64_t seed, uint64_t gid, int ruleset, const uint8_t* tape, uint32_t tape_len, ctd_state* out) {
+  CtdWork& w = g_w;
+  memset(&w, 0, sizeof(w));
+  chance_for(w, seed, gid, tape, tape_len);
+  ctd_deal_preset(w, ruleset);
+  ctd_setup_round(w);
+  ctd_pack(w, out);
+}
+int hs_enumerate(const ctd_state* s, uint64_t* opts, uint32_t cap, uint8_t* err) {
+  CtdWork& w = g_w;
+  memset(&w, 0, sizeof(w));
+  ctd_unpack(s, w);
+  CtdEmit e{opts, cap, 0, 0xFFFFFFFFu, 0};
+  ctd_enumerate(w, e);
+  if (err) *err = w.err;
+  return (int)e.n;
+}
+int hs_step(ctd_state* s, uint64_t d, uint64_t seed, uint64_t gid, const uint8_t* tape, uint32_t tape_len) {
+  CtdWork& w = g_w;
+  memset(&w, 0, sizeof(w));
+  ctd_unpack(s, w);
+  chance_for(w, seed, gid, tape, tape_len);
+  bool won = ctd_apply(w, d);
+  ctd_pack(w, s);
+  return won ? w.winner : -1;
+}
+// fused playout, same loop as the device kernel: returns winner, fills points/steps, err
+int hs_playout(uint64_t seed, uint64_t gid, int ruleset, uint32_t max_steps, int8_t* points6, uint32_t* steps,
+               uint8_t* err, ctd_state* final_state) {
+  CtdWork& w = g_w;
+  memset(&w, 0, sizeof(w));
+  ctd_new_game(w, seed, gid, ruleset);
+  uint64_t buf[8];
+  while (!(w.gflags & 2) && !w.err && w.steps < max_steps) {
+    CtdEmit e{buf, 0, 0, 0xFFFFFFFFu, 0};
+    ctd_enumerate(w, e);
+    if (e.n == 0) { w.err |= CTD_ERR_REF_RAISE; break; }
+    uint32_t k = ctd_randbelow(w, e.n);
+    CtdEmit e2{buf, 0, 0, k, 0};
+    ctd_enumerate(w, e2);
+    ctd_apply(w, e2.got);
+  }
+  if (!(w.gflags & 2) && !w.err) w.err |= CTD_ERR_MAXSTEPS;
+  for (int p = 0; p < 6; ++p) points6[p] = w.points[p];
+  *steps = w.steps;
+  *err = w.err;
+  if (final_state) ctd_pack(w, final_state);
+  return w.winner;
+}
+int hs_sizeof_work() { return (int)sizeof(CtdWork); }
+}
