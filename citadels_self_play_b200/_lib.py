@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcitadels_b200.so")
+LIB_PATH = os.environ.get("CTD_LIB", os.path.join(_HERE, "libcitadels_b200.so"))
 
 c_u8p = ctypes.POINTER(ctypes.c_uint8)
 c_void = ctypes.c_void_p

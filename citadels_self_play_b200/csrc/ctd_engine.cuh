@@ -18,8 +18,14 @@
 
 #if defined(__CUDACC__)
 #define CTD_HD __host__ __device__
+// out-of-line on the device: the playout kernel's warps sit at unrelated points of the rules code, so the
+// instruction footprint (not the arithmetic) is what the SM front end sees; one copy of each helper.
+#define CTD_NI __noinline__
+#define CTD_LOOP _Pragma("unroll 1")
 #else
 #define CTD_HD
+#define CTD_NI
+#define CTD_LOOP
 #endif
 
 // ------------------------------------------------------------------------------------------ constants
@@ -82,7 +88,7 @@ CTD_HD inline int ctd_base_deck(int i) {
   const uint8_t ends[16] = {5, 8, 11, 15, 17, 20, 23, 26, 28, 31, 34, 37, 40, 44, 49, 52};
   if (i < 52) {
     int t = 0;
-    while (i >= ends[t]) ++t;
+    CTD_LOOP while (i >= ends[t]) ++t;
     return t;
   }
   i -= 52;  // uniques: 16,17,17,18,...,37,39
@@ -142,10 +148,9 @@ struct CtdWork {
 };
 
 // ------------------------------------------------------------------------------------------ chance
-CTD_HD inline void ctd_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+CTD_HD CTD_NI inline void ctd_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
                               uint32_t out[4]) {
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
+  CTD_LOOP for (int i = 0; i < 10; ++i) {
     uint64_t p0 = (uint64_t)0xD2511F53u * c0;
     uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
     uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -185,8 +190,8 @@ CTD_HD inline void ctd_shuffle(CtdWork& w, int n, At at) {
   if (n <= 1) return;
   if (w.tape != nullptr) {
     if (w.tape_pos + (uint32_t)n > w.tape_len) { w.err |= CTD_ERR_TAPE; return; }
-    for (int i = 0; i < n; ++i) w.scratch[i] = at(i);
-    for (int i = 0; i < n; ++i) {
+    CTD_LOOP for (int i = 0; i < n; ++i) w.scratch[i] = at(i);
+    CTD_LOOP for (int i = 0; i < n; ++i) {
       int src = w.tape[w.tape_pos + i];
       if (src >= n) { w.err |= CTD_ERR_TAPE; src = 0; }
       at(i) = w.scratch[src];
@@ -194,7 +199,7 @@ CTD_HD inline void ctd_shuffle(CtdWork& w, int n, At at) {
     w.tape_pos += n;
     return;
   }
-  for (int i = n - 1; i > 0; --i) {
+  CTD_LOOP for (int i = n - 1; i > 0; --i) {
     int j = (int)ctd_randbelow(w, (uint32_t)(i + 1));
     uint8_t a = at(i), b = at(j);
     at(i) = b; at(j) = a;
@@ -202,30 +207,30 @@ CTD_HD inline void ctd_shuffle(CtdWork& w, int n, At at) {
 }
 
 // ------------------------------------------------------------------------------------------ list helpers
-CTD_HD inline bool ctd_has(const uint8_t* a, int n, int t) {
-  for (int i = 0; i < n; ++i) if (ctd_ctype(a[i]) == t) return true;
+CTD_HD CTD_NI inline bool ctd_has(const uint8_t* a, int n, int t) {
+  CTD_LOOP for (int i = 0; i < n; ++i) if (ctd_ctype(a[i]) == t) return true;
   return false;
 }
-CTD_HD inline int ctd_count_type(const uint8_t* a, int n, int t) {
+CTD_HD CTD_NI inline int ctd_count_type(const uint8_t* a, int n, int t) {
   int k = 0;
-  for (int i = 0; i < n; ++i) k += ctd_ctype(a[i]) == t;
+  CTD_LOOP for (int i = 0; i < n; ++i) k += ctd_ctype(a[i]) == t;
   return k;
 }
-CTD_HD inline int ctd_count_suit(const uint8_t* a, int n, int s) {
+CTD_HD CTD_NI inline int ctd_count_suit(const uint8_t* a, int n, int s) {
   int k = 0;
-  for (int i = 0; i < n; ++i) k += ctd_csuit(a[i]) == s;
+  CTD_LOOP for (int i = 0; i < n; ++i) k += ctd_csuit(a[i]) == s;
   return k;
 }
 CTD_HD inline int ctd_remove_at(uint8_t* a, uint8_t& n, int i) {
   int c = a[i];
-  for (int k = i; k + 1 < n; ++k) a[k] = a[k + 1];
+  CTD_LOOP for (int k = i; k + 1 < n; ++k) a[k] = a[k + 1];
   --n;
   return c;
 }
 // Deck.get_a_card_like_it (game/deck.py:49-55): first card of that type; the requested card is fabricated
 // when none matches.
-CTD_HD inline int ctd_take_like(uint8_t* a, uint8_t& n, int t) {
-  for (int i = 0; i < n; ++i)
+CTD_HD CTD_NI inline int ctd_take_like(uint8_t* a, uint8_t& n, int t) {
+  CTD_LOOP for (int i = 0; i < n; ++i)
     if (ctd_ctype(a[i]) == t) return ctd_remove_at(a, n, i);
   return t;
 }
@@ -242,18 +247,18 @@ CTD_HD inline void ctd_deck_push(CtdWork& w, int c) {
 CTD_HD inline void ctd_disc_push(CtdWork& w, int c) { ctd_append(w, w.disc, w.n_disc, CTD_DISC_CAP, c); }
 
 // reshuffle_deck_if_empty (game/option_functions.py:564-570)
-CTD_HD inline void ctd_reshuffle_if_empty(CtdWork& w) {
+CTD_HD CTD_NI inline void ctd_reshuffle_if_empty(CtdWork& w) {
   if (w.n_deck == 0 && w.n_disc != 0) {
     uint8_t* d = w.disc;
     ctd_shuffle(w, w.n_disc, [d](int i) -> uint8_t& { return d[i]; });
     w.deck_head = 0;
-    for (int i = 0; i < w.n_disc; ++i) w.deck[i] = w.disc[i];
+    CTD_LOOP for (int i = 0; i < w.n_disc; ++i) w.deck[i] = w.disc[i];
     w.n_deck = w.n_disc;
     w.n_disc = 0;
   }
 }
 // reshuffle + draw_card; returns -1 for "Deck Empty" (game/deck.py:57-60), which add_card drops (:62-70)
-CTD_HD inline int ctd_draw(CtdWork& w) {
+CTD_HD CTD_NI inline int ctd_draw(CtdWork& w) {
   ctd_reshuffle_if_empty(w);
   if (w.n_deck == 0) return -1;
   int c = w.deck[w.deck_head];
@@ -276,9 +281,9 @@ CTD_HD inline int ctd_name(const CtdWork& w, int p) {
   return r == CTD_ROLE_NONE ? CTD_NAME_NONE : CTD_NAME_BEWITCHED;
 }
 // Game.get_player_from_role_id (game/game.py:403-412); -1 when nobody holds it
-CTD_HD inline int ctd_player_from_rank(const CtdWork& w, int rank) {
+CTD_HD CTD_NI inline int ctd_player_from_rank(const CtdWork& w, int rank) {
   int want = rank < 0 ? CTD_ROLE_BEWITCHED : rank;
-  for (int p = 0; p < 6; ++p) if (w.role[p] == want) return p;
+  CTD_LOOP for (int p = 0; p < 6; ++p) if (w.role[p] == want) return p;
   return -1;
 }
 CTD_HD inline bool ctd_owns(const CtdWork& w, int p, int t) { return ctd_has(w.bld[p], w.n_bld[p], t); }
@@ -286,20 +291,20 @@ CTD_HD inline void ctd_clear_done(CtdWork& w) { w.done = 0; w.n_trade = 0; w.n_n
 
 // ------------------------------------------------------------------------------------------ round machine
 // Game.setup_round (game/game.py:144-171)
-CTD_HD inline void ctd_setup_round(CtdWork& w) {
-  for (int r = 0; r < 8; ++r) w.rprops[r] = 0;
+CTD_HD CTD_NI inline void ctd_setup_round(CtdWork& w) {
+  CTD_LOOP for (int r = 0; r < 8; ++r) w.rprops[r] = 0;
   w.used_len = 0;
-  for (int i = 0; i < 6; ++i) w.used_roles[i] = 0;
+  CTD_LOOP for (int i = 0; i < 6; ++i) w.used_roles[i] = 0;
   // random.shuffle(list(roles.items())); with 6 players exactly one role is popped face down
   uint8_t* s = w.scratch + 64;
-  for (int i = 0; i < 8; ++i) s[i] = (uint8_t)i;
+  CTD_LOOP for (int i = 0; i < 8; ++i) s[i] = (uint8_t)i;
   ctd_shuffle(w, 8, [s](int i) -> uint8_t& { return s[i]; });
   w.rtc_mask = (uint8_t)(0xFF & ~(1u << s[7]));
   // turn order rotates by the crowned seat's id, applied to the already rotated list
   int c = w.crown;
   uint8_t o[6];
-  for (int i = 0; i < 6; ++i) o[i] = w.order[(i + c) % 6];
-  for (int i = 0; i < 6; ++i) w.order[i] = o[i];
+  CTD_LOOP for (int i = 0; i < 6; ++i) o[i] = w.order[(i + c) % 6];
+  CTD_LOOP for (int i = 0; i < 6; ++i) w.order[i] = o[i];
   w.state = 0;
   w.player = w.order[0];
   ctd_clear_done(w);
@@ -309,26 +314,26 @@ CTD_HD inline void ctd_setup_round(CtdWork& w) {
 }
 
 // Game.refresh_used_roles (game/game.py:349-357); value+1 encoding keeps Bewitched (-1) sortable as 0
-CTD_HD inline bool ctd_refresh_used_roles(CtdWork& w) {
+CTD_HD CTD_NI inline bool ctd_refresh_used_roles(CtdWork& w) {
   uint8_t v[6];
-  for (int p = 0; p < 6; ++p) {
+  CTD_LOOP for (int p = 0; p < 6; ++p) {
     int r = w.role[p];
     if (r == CTD_ROLE_NONE) { w.err |= CTD_ERR_REF_RAISE; return false; }
     v[p] = (uint8_t)(r == CTD_ROLE_BEWITCHED ? 0 : r + 1);
   }
-  for (int i = 1; i < 6; ++i) {  // insertion sort
+  CTD_LOOP for (int i = 1; i < 6; ++i) {  // insertion sort
     uint8_t x = v[i];
     int j = i - 1;
-    while (j >= 0 && v[j] > x) { v[j + 1] = v[j]; --j; }
+    CTD_LOOP while (j >= 0 && v[j] > x) { v[j + 1] = v[j]; --j; }
     v[j + 1] = x;
   }
-  for (int i = 0; i < 6; ++i) w.used_roles[i] = v[i];
+  CTD_LOOP for (int i = 0; i < 6; ++i) w.used_roles[i] = v[i];
   w.used_len = 6;
   return true;
 }
 
 // Game.setup_next_player (game/game.py:391-401); current < 0 == None
-CTD_HD inline void ctd_setup_next_player(CtdWork& w, int current) {
+CTD_HD CTD_NI inline void ctd_setup_next_player(CtdWork& w, int current) {
   int nxt;
   if (w.state == 0) {
     if (!ctd_refresh_used_roles(w)) return;
@@ -340,7 +345,7 @@ CTD_HD inline void ctd_setup_next_player(CtdWork& w, int current) {
     if (r == CTD_ROLE_NONE) { w.err |= CTD_ERR_REF_RAISE; return; }
     uint8_t key = (uint8_t)(r == CTD_ROLE_BEWITCHED ? 0 : r + 1);
     int i = 0;
-    while (i < w.used_len && w.used_roles[i] != key) ++i;
+    CTD_LOOP while (i < w.used_len && w.used_roles[i] != key) ++i;
     if (i + 1 >= w.used_len) { w.err |= CTD_ERR_REF_RAISE; return; }
     nxt = ctd_player_from_rank(w, (int)w.used_roles[i + 1] - 1);
     ctd_clear_done(w);
@@ -353,12 +358,12 @@ CTD_HD inline void ctd_setup_next_player(CtdWork& w, int current) {
 }
 
 // Agent.count_points (game/agent.py:116-143)
-CTD_HD inline int ctd_count_points(const CtdWork& w, int p) {
+CTD_HD CTD_NI inline int ctd_count_points(const CtdWork& w, int p) {
   int pts = 0;
   const uint8_t* b = w.bld[p];
   int n = w.n_bld[p];
   bool well = ctd_has(b, n, 31);
-  for (int i = 0; i < n; ++i) {
+  CTD_LOOP for (int i = 0; i < n; ++i) {
     int t = ctd_ctype(b[i]);
     pts += ctd_cost_of_type(t);
     if (t == 18 || t == 23) pts += 2;
@@ -373,10 +378,10 @@ CTD_HD inline int ctd_count_points(const CtdWork& w, int p) {
 }
 
 // Game.check_game_ending (game/game.py:359-368): first arg-max wins
-CTD_HD inline bool ctd_check_game_ending(CtdWork& w) {
+CTD_HD CTD_NI inline bool ctd_check_game_ending(CtdWork& w) {
   if (!(w.gflags & 1)) return false;
   int best = -1000, bi = 0;
-  for (int p = 0; p < 6; ++p) {
+  CTD_LOOP for (int p = 0; p < 6; ++p) {
     int pts = ctd_count_points(w, p);
     w.points[p] = (int8_t)pts;
     if (pts > best) { best = pts; bi = p; }
@@ -387,42 +392,42 @@ CTD_HD inline bool ctd_check_game_ending(CtdWork& w) {
 }
 
 // move_crown + troneroom_owner_gold (game/option_functions.py:625-631, :588-595)
-CTD_HD inline void ctd_move_crown(CtdWork& w, int target) {
+CTD_HD CTD_NI inline void ctd_move_crown(CtdWork& w, int target) {
   w.crown = (uint8_t)target;
-  for (int p = 0; p < 6; ++p)
+  CTD_LOOP for (int p = 0; p < 6; ++p)
     if (ctd_owns(w, p, 32)) { w.gold[p] += 1; break; }
 }
 
 // Game.is_last_round (game/game.py:173-181)
 CTD_HD inline void ctd_is_last_round(CtdWork& w) {
   if (!(w.gflags & 1))
-    for (int p = 0; p < 6; ++p)
+    CTD_LOOP for (int p = 0; p < 6; ++p)
       if (w.n_bld[p] == 7) { w.gflags |= 1; w.pflags[p] |= CTD_PF_FIRST7; }
 }
 
 // Game.set_preset (game/game.py:420-489): Deck() shuffles the 76 cards, fixed hands are pulled by type
-CTD_HD inline void ctd_deal_preset(CtdWork& w, int ruleset) {
-  for (int p = 0; p < 6; ++p) {
+CTD_HD CTD_NI inline void ctd_deal_preset(CtdWork& w, int ruleset) {
+  CTD_LOOP for (int p = 0; p < 6; ++p) {
     w.n_hand[p] = w.n_bld[p] = w.n_mus[p] = w.n_jd[p] = 0;
     w.gold[p] = 2; w.role[p] = CTD_ROLE_NONE; w.replicas[p] = 0; w.pflags[p] = 0;
     w.order[p] = (uint8_t)p; w.points[p] = 0; w.used_roles[p] = 0;
   }
-  for (int r = 0; r < 8; ++r) w.rprops[r] = 0;
+  CTD_LOOP for (int r = 0; r < 8; ++r) w.rprops[r] = 0;
   const uint8_t preset_variant[8] = {1, 1, 1, 0, 1, 1, 1, 0};
-  for (int r = 0; r < 8; ++r) w.variant[r] = ruleset == CTD_RULESET_PRESET ? preset_variant[r] : 0;
+  CTD_LOOP for (int r = 0; r < 8; ++r) w.variant[r] = ruleset == CTD_RULESET_PRESET ? preset_variant[r] : 0;
   w.used_len = 0; w.rtc_mask = 0; w.state = 0; w.player = 0xFF;
   ctd_clear_done(w);
   w.next_player = 0; w.next_mode = CTD_NEXT_NONE; w.crown = 3; w.gflags = 0; w.winner = -1;
   w.wiz_target = 0xFF; w.warrant_building = 0xFF; w.ruleset = (uint8_t)ruleset; w.err = 0; w.steps = 0;
   w.n_disc = 0; w.deck_head = 0;
-  for (int i = 0; i < 76; ++i) w.deck[i] = (uint8_t)ctd_base_deck(i);
+  CTD_LOOP for (int i = 0; i < 76; ++i) w.deck[i] = (uint8_t)ctd_base_deck(i);
   w.n_deck = 76;
   uint8_t* d = w.deck;
   ctd_shuffle(w, 76, [d](int i) -> uint8_t& { return d[i]; });
   const uint8_t hands[6][6] = {{0, 0, 16, 17, 18, 19}, {1, 1, 20, 21, 22, 23}, {2, 3, 24, 25, 26, 27},
                                {3, 4, 28, 29, 30, 31}, {4, 0, 32, 33, 34, 35}, {0, 1, 36, 37, 39, 0}};
-  for (int p = 0; p < 6; ++p)
-    for (int k = 0; k < 6; ++k) {
+  CTD_LOOP for (int p = 0; p < 6; ++p)
+    CTD_LOOP for (int k = 0; k < 6; ++k) {
       int c = ctd_take_like(w.deck, w.n_deck, hands[p][k]);  // head == 0 here, the ring is linear
       w.hand[p][w.n_hand[p]++] = (uint8_t)c;
     }
@@ -444,7 +449,7 @@ struct CtdEmit {
   // cnt options that differ only in the ordinal field j
   CTD_HD void range(uint64_t base, uint32_t cnt) {
     if (want >= n && want - n < cnt) got = base | ctd_f_j(want - n);
-    for (uint32_t j = 0; j < cnt && n + j < cap; ++j) buf[n + j] = base | ctd_f_j(j);
+    CTD_LOOP for (uint32_t j = 0; j < cnt && n + j < cap; ++j) buf[n + j] = base | ctd_f_j(j);
     n += cnt;
   }
 };
@@ -462,12 +467,12 @@ CTD_HD inline int ctd_build_cost(int c, bool factory) {
 CTD_HD inline uint64_t ctd_binom(int n, int r) {
   if (r > n - r) r = n - r;
   uint64_t v = 1;
-  for (int i = 1; i <= r; ++i) v = v * (uint64_t)(n - r + i) / (uint64_t)i;
+  CTD_LOOP for (int i = 1; i <= r; ++i) v = v * (uint64_t)(n - r + i) / (uint64_t)i;
   return v;
 }
 // number of discard_and_draw options of subset size r for a hand of n (game/agent_functions.py:290-294):
 // range(0, C, max(round(C/1e2), 1)) with CPython's round-half-even
-CTD_HD inline uint32_t ctd_magician_count(int n, int r) {
+CTD_HD CTD_NI inline uint32_t ctd_magician_count(int n, int r) {
   uint64_t c = ctd_binom(n, r);
   uint64_t q = c / 100, rem = c % 100;
   uint64_t step = rem > 50 ? q + 1 : (rem < 50 ? q : q + (q & 1));
@@ -477,29 +482,29 @@ CTD_HD inline uint32_t ctd_magician_count(int n, int r) {
 
 // character_options (game/agent_functions.py:156-209) and the per-role enumerators it dispatches to
 template <class E>
-CTD_HD inline void ctd_character_options(const CtdWork& w, int p, int nm, E& e) {
+CTD_HD CTD_NI inline void ctd_character_options(const CtdWork& w, int p, int nm, E& e) {
   if (!(w.done & CTD_DM_CHARACTER)) {
     switch (nm) {
       case CTD_ASSASSIN:  // :213-218
-        for (int r = 1; r < 8; ++r) e.one(ctd_opt(CTD_K_ASSASSINATION, p) | ctd_f_rank(r));
+        CTD_LOOP for (int r = 1; r < 8; ++r) e.one(ctd_opt(CTD_K_ASSASSINATION, p) | ctd_f_rank(r));
         break;
       case CTD_THIEF:  // :246-253
-        for (int r = 2; r < 8; ++r) e.one(ctd_opt(CTD_K_STEAL, p) | ctd_f_rank(r));
+        CTD_LOOP for (int r = 2; r < 8; ++r) e.one(ctd_opt(CTD_K_STEAL, p) | ctd_f_rank(r));
         break;
       case CTD_SPY:  // :274-281
-        for (int q = 0; q < 6; ++q)
+        CTD_LOOP for (int q = 0; q < 6; ++q)
           if (q != p)
-            for (int s = 0; s < 5; ++s) e.one(ctd_opt(CTD_K_SPY, p) | ctd_f_target(q) | ctd_f_named(CTD_N_TRADE + s));
+            CTD_LOOP for (int s = 0; s < 5; ++s) e.one(ctd_opt(CTD_K_SPY, p) | ctd_f_target(q) | ctd_f_named(CTD_N_TRADE + s));
         break;
       case CTD_MAGICIAN: {  // :284-296
-        for (int q = 0; q < 6; ++q)
+        CTD_LOOP for (int q = 0; q < 6; ++q)
           if (q != p) e.one(ctd_opt(CTD_K_MAGIC_HAND_CHANGE, p) | ctd_f_target(q));
         int n = w.n_hand[p];
-        for (int r = 1; r <= n; ++r) e.range(ctd_opt(CTD_K_DISCARD_AND_DRAW, p) | ctd_f_r(r), ctd_magician_count(n, r));
+        CTD_LOOP for (int r = 1; r <= n; ++r) e.range(ctd_opt(CTD_K_DISCARD_AND_DRAW, p) | ctd_f_r(r), ctd_magician_count(n, r));
         break;
       }
       case CTD_WIZARD:  // :298-308
-        for (int q = 0; q < 6; ++q)
+        CTD_LOOP for (int q = 0; q < 6; ++q)
           if (q != p && w.n_hand[q] > 0) e.one(ctd_opt(CTD_K_LOOK_AT_HAND, p) | ctd_f_target(q));
         break;
       case CTD_KING: e.one(ctd_opt(CTD_K_TAKE_CROWN_KING, p)); break;  // :364-366
@@ -507,7 +512,7 @@ CTD_HD inline void ctd_character_options(const CtdWork& w, int p, int nm, E& e) 
       case CTD_ABBOT: {                                                // :422-430
         int n = ctd_count_suit(w.hand[p], w.n_hand[p], CTD_SUIT_RELIGION);
         if (n > 0)
-          for (int k = 0; k <= n; ++k) e.one(ctd_opt(CTD_K_ABBOT, p) | ctd_f_count(k));
+          CTD_LOOP for (int k = 0; k <= n; ++k) e.one(ctd_opt(CTD_K_ABBOT, p) | ctd_f_count(k));
         break;
       }
       case CTD_MERCHANT: e.one(ctd_opt(CTD_K_MERCHANT, p)); break;    // :438-440
@@ -518,10 +523,10 @@ CTD_HD inline void ctd_character_options(const CtdWork& w, int p, int nm, E& e) 
         e.one(ctd_opt(CTD_K_NAVIGATOR, p) | ctd_f_named(CTD_N_4CARD));
         break;
       case CTD_WARLORD:  // :473-482
-        for (int q = 0; q < 6; ++q) {
+        CTD_LOOP for (int q = 0; q < 6; ++q) {
           if (w.n_bld[q] >= 7 || ctd_name(w, q) == CTD_BISHOP) continue;
           uint64_t seen = 0;
-          for (int i = 0; i < w.n_bld[q]; ++i) {
+          CTD_LOOP for (int i = 0; i < w.n_bld[q]; ++i) {
             int c = w.bld[q][i], t = ctd_ctype(c);
             if (ctd_ccost(c) - 1 <= w.gold[p] && t != 17 && !((seen >> t) & 1)) {
               seen |= 1ull << t;
@@ -540,21 +545,21 @@ CTD_HD inline void ctd_character_options(const CtdWork& w, int p, int nm, E& e) 
 
 // main_round_options (game/agent_functions.py:133-147); concatenation order is observable
 template <class E>
-CTD_HD inline void ctd_main_round_options(const CtdWork& w, int p, int nm, E& e) {
+CTD_HD CTD_NI inline void ctd_main_round_options(const CtdWork& w, int p, int nm, E& e) {
   const uint8_t* bld = w.bld[p];
   const int nb = w.n_bld[p];
   const uint8_t* hand = w.hand[p];
   const int nh = w.n_hand[p];
   // which effect buildings do I own
   uint64_t own = 0;
-  for (int i = 0; i < nb; ++i) own |= 1ull << ctd_ctype(bld[i]);
+  CTD_LOOP for (int i = 0; i < nb; ++i) own |= 1ull << ctd_ctype(bld[i]);
   // build_options / get_builds (:108-130)
   {
     int built = nm == CTD_TRADER ? w.n_nontrade : w.n_trade + w.n_nontrade;
     if (built < ctd_build_limit(nm)) {
       bool factory = (own >> 35) & 1;
       uint64_t seen = 0;
-      for (int i = 0; i < nh; ++i) {
+      CTD_LOOP for (int i = 0; i < nh; ++i) {
         int c = hand[i], t = ctd_ctype(c);
         int replica = (((own >> t) & 1) && !w.replicas[p]) ? w.replicas[p] + 1 : 0;
         if (ctd_build_cost(c, factory) <= w.gold[p] && !((seen >> t) & 1)) {
@@ -567,24 +572,24 @@ CTD_HD inline void ctd_main_round_options(const CtdWork& w, int p, int nm, E& e)
   ctd_character_options(w, p, nm, e);
   if (((own >> 21) & 1) && w.gold[p] >= 2 && !(w.done & CTD_DM_SMITHY)) e.one(ctd_opt(CTD_K_SMITHY, p));  // :54-57
   if (((own >> 22) & 1) && !(w.done & CTD_DM_LAB))                                                      // :59-65
-    for (int i = 0; i < nh; ++i) e.one(ctd_opt(CTD_K_LAB, p) | ctd_f_a(ctd_ctype(hand[i])));
+    CTD_LOOP for (int i = 0; i < nh; ++i) e.one(ctd_opt(CTD_K_LAB, p) | ctd_f_a(ctd_ctype(hand[i])));
   if (!(w.done & CTD_DM_MAGIC_SCHOOL) && ((own >> 25) & 1))                                             // :67-74
-    for (int s = 0; s < 5; ++s) e.one(ctd_opt(CTD_K_MAGIC_SCHOOL, p) | ctd_f_named(CTD_N_TRADE + s));
+    CTD_LOOP for (int s = 0; s < 5; ++s) e.one(ctd_opt(CTD_K_MAGIC_SCHOOL, p) | ctd_f_named(CTD_N_TRADE + s));
   if ((own >> 27) & 1)                                                                                  // :76-83
-    for (int q = 0; q < 6; ++q)
+    CTD_LOOP for (int q = 0; q < 6; ++q)
       if (q != p)
-        for (int i = 0; i < w.n_bld[q]; ++i)
+        CTD_LOOP for (int i = 0; i < w.n_bld[q]; ++i)
           e.one(ctd_opt(CTD_K_WEAPON_STORAGE, p) | ctd_f_target(q) | ctd_f_a(ctd_ctype(w.bld[q][i])));
   if (((own >> 29) & 1) && (w.pflags[p] & CTD_PF_LIGHTHOUSE)) {                                          // :85-94
     uint64_t seen = 0;
-    for (int i = 0; i < w.n_deck; ++i) {
+    CTD_LOOP for (int i = 0; i < w.n_deck; ++i) {
       int t = ctd_ctype(w.deck[(w.deck_head + i) & (CTD_DECK_CAP - 1)]);
       if (!((seen >> t) & 1)) { seen |= 1ull << t; e.one(ctd_opt(CTD_K_LIGHTHOUSE, p) | ctd_f_a(t)); }
     }
   }
   if (((own >> 34) & 1) && !(w.done & CTD_DM_MUSEUM)) {                                                  // :96-105
     uint64_t seen = 0;
-    for (int i = 0; i < nh; ++i) {
+    CTD_LOOP for (int i = 0; i < nh; ++i) {
       int t = ctd_ctype(hand[i]);
       if (!((seen >> t) & 1)) { seen |= 1ull << t; e.one(ctd_opt(CTD_K_MUSEUM, p) | ctd_f_a(t)); }
     }
@@ -595,15 +600,15 @@ CTD_HD inline void ctd_main_round_options(const CtdWork& w, int p, int nm, E& e)
 // wizard_take_from_hand_options (game/agent_functions.py:310-326).  `cards` is the looked-at hand copy
 // (HandKnowledge.hand); in a playout it equals the target's current hand.  `replica` leaks across iterations.
 template <class E>
-CTD_HD inline void ctd_wizard_take_options(const CtdWork& w, int p, const uint8_t* cards, int n, E& e) {
+CTD_HD CTD_NI inline void ctd_wizard_take_options(const CtdWork& w, int p, const uint8_t* cards, int n, E& e) {
   int q = w.wiz_target;
   uint64_t own = 0;
-  for (int i = 0; i < w.n_bld[p]; ++i) own |= 1ull << ctd_ctype(w.bld[p][i]);
+  CTD_LOOP for (int i = 0; i < w.n_bld[p]; ++i) own |= 1ull << ctd_ctype(w.bld[p][i]);
   bool factory = (own >> 35) & 1;
   uint64_t seen_take = 0, seen_b0 = 0, seen_b1 = 0;
   int replica = 0;
   uint32_t before = e.n;
-  for (int i = 0; i < n; ++i) {
+  CTD_LOOP for (int i = 0; i < n; ++i) {
     int c = cards[i], t = ctd_ctype(c);
     if (!((seen_take >> t) & 1)) {
       seen_take |= 1ull << t;
@@ -621,13 +626,13 @@ CTD_HD inline void ctd_wizard_take_options(const CtdWork& w, int p, const uint8_
 
 // Agent.get_options (game/agent.py:50-83).  An empty result with err set means the reference would raise.
 template <class E>
-CTD_HD inline void ctd_enumerate(CtdWork& w, E& e) {
+CTD_HD CTD_NI inline void ctd_enumerate(CtdWork& w, E& e) {
   if (w.gflags & 2) return;  // terminal: the reference's loops stop here
   const int p = w.player;
   const int st = w.state;
   if (p >= 6) { w.err |= CTD_ERR_REF_RAISE; return; }
   if (st == 0) {  // pick_role_options (game/agent_functions.py:13-14)
-    for (int r = 0; r < 8; ++r)
+    CTD_LOOP for (int r = 0; r < 8; ++r)
       if ((w.rtc_mask >> r) & 1) e.one(ctd_opt(CTD_K_ROLE_PICK, p) | ctd_f_rank(r));
     return;
   }
@@ -645,12 +650,12 @@ CTD_HD inline void ctd_enumerate(CtdWork& w, E& e) {
         const uint8_t* jd = w.jd[p];
         int n = w.n_jd[p];
         if (ctd_owns(w, p, 20)) {
-          for (int i = 0; i < n; ++i)
-            for (int j = i + 1; j < n; ++j)
+          CTD_LOOP for (int i = 0; i < n; ++i)
+            CTD_LOOP for (int j = i + 1; j < n; ++j)
               e.one(ctd_opt(CTD_K_KEEP, p) | ctd_f_a(ctd_ctype(jd[i])) | ctd_f_b(ctd_ctype(jd[j])));
         } else {
           uint64_t seen = 0;
-          for (int i = 0; i < n; ++i) {
+          CTD_LOOP for (int i = 0; i < n; ++i) {
             int t = ctd_ctype(jd[i]);
             if (!((seen >> t) & 1)) { seen |= 1ull << t; e.one(ctd_opt(CTD_K_KEEP, p) | ctd_f_a(t)); }
           }
@@ -675,7 +680,7 @@ CTD_HD inline void ctd_enumerate(CtdWork& w, E& e) {
       default: break;
     }
     if (nm == CTD_WITCH) {  // witch_options (:236-242)
-      for (int r = 1; r < 8; ++r) e.one(ctd_opt(CTD_K_BEWITCHING, p) | ctd_f_rank(r));
+      CTD_LOOP for (int r = 1; r < 8; ++r) e.one(ctd_opt(CTD_K_BEWITCHING, p) | ctd_f_rank(r));
       return;
     }
     if (role == CTD_ROLE_BEWITCHED) { w.err |= CTD_ERR_REF_RAISE; return; }
@@ -721,7 +726,7 @@ CTD_HD inline void ctd_restore_next(CtdWork& w) {
 }
 
 // carry_out_building (game/option_functions.py:102-127)
-CTD_HD inline void ctd_apply_build(CtdWork& w, int p, int t, int replica) {
+CTD_HD CTD_NI inline void ctd_apply_build(CtdWork& w, int p, int t, int replica) {
   int c = ctd_take_like(w.hand[p], w.n_hand[p], t);
   ctd_append(w, w.bld[p], w.n_bld[p], CTD_BLD_CAP, c);
   if (ctd_name(w, p) != CTD_ALCHEMIST) w.gold[p] -= (int8_t)ctd_ccost(c);
@@ -736,7 +741,7 @@ CTD_HD inline void ctd_apply_build(CtdWork& w, int p, int t, int replica) {
 }
 
 // finish_main_sequnce_actions (game/option_functions.py:189-243).  Returns true when the game ended.
-CTD_HD inline bool ctd_apply_finish(CtdWork& w, uint64_t d) {
+CTD_HD CTD_NI inline bool ctd_apply_finish(CtdWork& w, uint64_t d) {
   const int p = CTD_OPT_PERP(d);
   const int pr = w.role[p];
   if (pr >= 8) { w.err |= CTD_ERR_REF_RAISE; return false; }
@@ -768,7 +773,7 @@ CTD_HD inline bool ctd_apply_finish(CtdWork& w, uint64_t d) {
 }
 
 // option.carry_out (game/option.py:118-122).  Returns true when this step ended the game.
-CTD_HD inline bool ctd_apply(CtdWork& w, uint64_t d) {
+CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d) {
   const int k = CTD_OPT_KIND(d);
   const int p = CTD_OPT_PERP(d);
   bool won = false;
@@ -779,7 +784,7 @@ CTD_HD inline bool ctd_apply(CtdWork& w, uint64_t d) {
       w.rtc_mask &= (uint8_t)~(1u << r);
       if (p != w.order[5]) {
         int i = 0;
-        while (i < 5 && w.order[i] != p) ++i;
+        CTD_LOOP while (i < 5 && w.order[i] != p) ++i;
         w.state = 0;
         w.player = w.order[i + 1];
       } else {
@@ -803,7 +808,7 @@ CTD_HD inline bool ctd_apply(CtdWork& w, uint64_t d) {
         w.state = 3;
       } else {
         int n = ctd_owns(w, p, 16) ? 3 : 2;  // Observatory
-        for (int i = 0; i < n; ++i) ctd_draw_to_jd(w, p);
+        CTD_LOOP for (int i = 0; i < n; ++i) ctd_draw_to_jd(w, p);
         w.state = 2;
       }
       w.player = (uint8_t)p;
@@ -816,7 +821,7 @@ CTD_HD inline bool ctd_apply(CtdWork& w, uint64_t d) {
         c = ctd_take_like(w.jd[p], w.n_jd[p], CTD_OPT_CARD_B(d));
         ctd_append(w, w.hand[p], w.n_hand[p], CTD_HAND_CAP, c);
       }
-      for (int i = 0; i < w.n_jd[p]; ++i) ctd_deck_push(w, w.jd[p][i]);
+      CTD_LOOP for (int i = 0; i < w.n_jd[p]; ++i) ctd_deck_push(w, w.jd[p][i]);
       w.n_jd[p] = 0;
       w.state = 3;
       w.player = (uint8_t)p;
@@ -836,7 +841,7 @@ CTD_HD inline bool ctd_apply(CtdWork& w, uint64_t d) {
     case CTD_K_FINISH: won = ctd_apply_finish(w, d); break;
     case CTD_K_SMITHY:  // carry_out_smithy (:131-138): the cards go to just_drawn_cards
       w.gold[p] -= 2;
-      for (int i = 0; i < 3; ++i) ctd_draw_to_jd(w, p);
+      CTD_LOOP for (int i = 0; i < 3; ++i) ctd_draw_to_jd(w, p);
       ctd_to5(w, p);
       w.done |= CTD_DM_SMITHY;
       break;
@@ -868,10 +873,10 @@ CTD_HD inline bool ctd_apply(CtdWork& w, uint64_t d) {
     }
     case CTD_K_LIGHTHOUSE: {  // carry_out_lighthouse (:173-180)
       int t = CTD_OPT_CARD_A(d), c = t, n = w.n_deck;
-      for (int i = 0; i < n; ++i)
+      CTD_LOOP for (int i = 0; i < n; ++i)
         if (ctd_ctype(ctd_dk(w, i)) == t) {
           c = ctd_dk(w, i);
-          for (int k = i; k + 1 < n; ++k) ctd_dk(w, k) = ctd_dk(w, k + 1);
+          CTD_LOOP for (int k = i; k + 1 < n; ++k) ctd_dk(w, k) = ctd_dk(w, k + 1);
           --w.n_deck;
           break;
         }
@@ -922,7 +927,7 @@ CTD_HD inline bool ctd_apply(CtdWork& w, uint64_t d) {
     case CTD_K_MAGIC_HAND_CHANGE: {  // carry_out_magicking (:291-293)
       int q = CTD_OPT_TARGET(d);
       int n = w.n_hand[p] > w.n_hand[q] ? w.n_hand[p] : w.n_hand[q];
-      for (int i = 0; i < n; ++i) { uint8_t a = w.hand[p][i]; w.hand[p][i] = w.hand[q][i]; w.hand[q][i] = a; }
+      CTD_LOOP for (int i = 0; i < n; ++i) { uint8_t a = w.hand[p][i]; w.hand[p][i] = w.hand[q][i]; w.hand[q][i] = a; }
       uint8_t a = w.n_hand[p]; w.n_hand[p] = w.n_hand[q]; w.n_hand[q] = a;
       ctd_to5(w, p);
       w.done |= CTD_DM_CHARACTER;
@@ -931,13 +936,13 @@ CTD_HD inline bool ctd_apply(CtdWork& w, uint64_t d) {
     case CTD_K_DISCARD_AND_DRAW: {  // carry_out_magicking (:295-300): ignores the option's cards and removes
                                     // while iterating; draws as many cards as are left in hand
       int i = 0;
-      while (i < w.n_hand[p]) {
+      CTD_LOOP while (i < w.n_hand[p]) {
         int t = ctd_ctype(w.hand[p][i]);
         ctd_deck_push(w, ctd_take_like(w.hand[p], w.n_hand[p], t));
         ++i;
       }
       int n = w.n_hand[p];
-      for (int k = 0; k < n; ++k) ctd_draw_to_hand(w, p);
+      CTD_LOOP for (int k = 0; k < n; ++k) ctd_draw_to_hand(w, p);
       ctd_to5(w, p);
       w.done |= CTD_DM_CHARACTER;
       break;
@@ -976,14 +981,14 @@ CTD_HD inline bool ctd_apply(CtdWork& w, uint64_t d) {
     case CTD_K_ABBOT: {  // carry_out_abbot (:405-412)
       int n = ctd_count_suit(w.hand[p], w.n_hand[p], CTD_SUIT_RELIGION), kc = CTD_OPT_COUNT(d);
       w.gold[p] += (int8_t)(n - kc);
-      for (int i = 0; i < kc; ++i) ctd_draw_to_hand(w, p);
+      CTD_LOOP for (int i = 0; i < kc; ++i) ctd_draw_to_hand(w, p);
       ctd_to5(w, p);
       w.done |= CTD_DM_CHARACTER;
       break;
     }
     case CTD_K_ABBOT_BEG: {  // carry_out_abbot_beg (:414-420): first richest seat pays, may be the abbot
       int rich = 0;
-      for (int q = 1; q < 6; ++q) if (w.gold[q] > w.gold[rich]) rich = q;
+      CTD_LOOP for (int q = 1; q < 6; ++q) if (w.gold[q] > w.gold[rich]) rich = q;
       w.gold[rich] -= 1;
       int a = ctd_player_from_rank(w, 4);
       if (a < 0) { w.err |= CTD_ERR_REF_RAISE; break; }
@@ -999,7 +1004,7 @@ CTD_HD inline bool ctd_apply(CtdWork& w, uint64_t d) {
       w.done |= CTD_DM_CHARACTER;
       break;
     case CTD_K_NAVIGATOR:  // carry_out_navigator (:473-483)
-      if (CTD_OPT_NAMED(d) == CTD_N_4CARD) for (int i = 0; i < 4; ++i) ctd_draw_to_hand(w, p);
+      if (CTD_OPT_NAMED(d) == CTD_N_4CARD) CTD_LOOP for (int i = 0; i < 4; ++i) ctd_draw_to_hand(w, p);
       else w.gold[p] += 4;
       ctd_to5(w, p);
       w.done |= CTD_DM_CHARACTER;
@@ -1011,7 +1016,7 @@ CTD_HD inline bool ctd_apply(CtdWork& w, uint64_t d) {
       ctd_disc_push(w, c);
       if (ctd_count_type(w.bld[q], w.n_bld[q], t) > 1) w.replicas[q] -= 1;
       if (t == 34) {
-        for (int i = 0; i < w.n_mus[q]; ++i) ctd_disc_push(w, w.mus[q][i]);
+        CTD_LOOP for (int i = 0; i < w.n_mus[q]; ++i) ctd_disc_push(w, w.mus[q][i]);
         w.n_mus[q] = 0;
       }
       if (t == 29 && (w.pflags[q] & CTD_PF_LIGHTHOUSE)) {
@@ -1021,7 +1026,7 @@ CTD_HD inline bool ctd_apply(CtdWork& w, uint64_t d) {
       ctd_to5(w, p);
       w.done |= CTD_DM_CHARACTER;
       int owner = -1;  // get_graveyard_owner (:597-601)
-      for (int x = 0; x < 6; ++x) if (ctd_owns(w, x, 24)) { owner = x; break; }
+      CTD_LOOP for (int x = 0; x < 6; ++x) if (ctd_owns(w, x, 24)) { owner = x; break; }
       if (owner >= 0 && owner != p) {
         w.state = 6;
         w.player = (uint8_t)owner;
@@ -1038,7 +1043,7 @@ CTD_HD inline bool ctd_apply(CtdWork& w, uint64_t d) {
 }
 
 // run_utils.create_game (run_utils.py:20-27)
-CTD_HD inline void ctd_new_game(CtdWork& w, uint64_t seed, uint64_t gid, int ruleset) {
+CTD_HD CTD_NI inline void ctd_new_game(CtdWork& w, uint64_t seed, uint64_t gid, int ruleset) {
   ctd_chance_init(w, seed, gid, 0);
   ctd_deal_preset(w, ruleset);
   ctd_setup_round(w);
@@ -1046,27 +1051,27 @@ CTD_HD inline void ctd_new_game(CtdWork& w, uint64_t seed, uint64_t gid, int rul
 
 // ------------------------------------------------------------------------------------------ pack / unpack
 // Scalar forms (definition of the layout); ctd_warp.cuh has the lane-parallel device forms.
-CTD_HD inline void ctd_pack(const CtdWork& w, ctd_state* s) {
+CTD_HD CTD_NI inline void ctd_pack(const CtdWork& w, ctd_state* s) {
   uint8_t* raw = (uint8_t*)s;
-  for (int i = 0; i < CTD_STATE_BYTES; ++i) raw[i] = 0;
+  CTD_LOOP for (int i = 0; i < CTD_STATE_BYTES; ++i) raw[i] = 0;
   int pos = 0, c = 0;
   bool ovf = false;
   auto put = [&](const uint8_t* a, int n) {
     s->off[c++] = (uint8_t)pos;
-    for (int i = 0; i < n; ++i) { if (pos < 128) s->arena[pos++] = a[i]; else ovf = true; }
+    CTD_LOOP for (int i = 0; i < n; ++i) { if (pos < 128) s->arena[pos++] = a[i]; else ovf = true; }
   };
-  for (int p = 0; p < 6; ++p) {
+  CTD_LOOP for (int p = 0; p < 6; ++p) {
     put(w.hand[p], w.n_hand[p]); put(w.bld[p], w.n_bld[p]); put(w.mus[p], w.n_mus[p]); put(w.jd[p], w.n_jd[p]);
   }
   s->off[c++] = (uint8_t)pos;
-  for (int i = 0; i < w.n_deck; ++i) { if (pos < 128) s->arena[pos++] = w.deck[(w.deck_head + i) & (CTD_DECK_CAP - 1)]; else ovf = true; }
+  CTD_LOOP for (int i = 0; i < w.n_deck; ++i) { if (pos < 128) s->arena[pos++] = w.deck[(w.deck_head + i) & (CTD_DECK_CAP - 1)]; else ovf = true; }
   put(w.disc, w.n_disc);
   s->off[c] = (uint8_t)pos;
-  for (int p = 0; p < 6; ++p) {
+  CTD_LOOP for (int p = 0; p < 6; ++p) {
     s->gold[p] = w.gold[p]; s->role[p] = w.role[p]; s->replicas[p] = w.replicas[p]; s->pflags[p] = w.pflags[p];
     s->order[p] = w.order[p]; s->used_roles[p] = w.used_roles[p]; s->points[p] = w.points[p];
   }
-  for (int r = 0; r < 8; ++r) { s->rprops[r] = w.rprops[r]; s->variant[r] = w.variant[r]; }
+  CTD_LOOP for (int r = 0; r < 8; ++r) { s->rprops[r] = w.rprops[r]; s->variant[r] = w.variant[r]; }
   s->used_len = w.used_len; s->rtc_mask = w.rtc_mask; s->state = w.state; s->player = w.player; s->done = w.done;
   s->done_builds = (uint8_t)(w.n_trade | (w.n_nontrade << 4));
   const bool interrupt = w.state == 4 || (w.state >= 6 && w.state <= 10);
@@ -1079,7 +1084,7 @@ CTD_HD inline void ctd_pack(const CtdWork& w, ctd_state* s) {
   s->gid = (uint64_t)w.g0 | ((uint64_t)w.g1 << 32);
 }
 
-CTD_HD inline void ctd_unpack(const ctd_state* s, CtdWork& w) {
+CTD_HD CTD_NI inline void ctd_unpack(const ctd_state* s, CtdWork& w) {
   int c = 0;
   auto get = [&](uint8_t* a, uint8_t& n, int cap) {
     int b = s->off[c], e = s->off[c + 1];
@@ -1087,22 +1092,22 @@ CTD_HD inline void ctd_unpack(const ctd_state* s, CtdWork& w) {
     int len = e - b;
     if (len < 0) len = 0;
     if (len > cap) { len = cap; w.err |= CTD_ERR_OVERFLOW; }
-    for (int i = 0; i < len; ++i) a[i] = s->arena[(b + i) & 127];
+    CTD_LOOP for (int i = 0; i < len; ++i) a[i] = s->arena[(b + i) & 127];
     n = (uint8_t)len;
   };
   w.err = s->err;
-  for (int p = 0; p < 6; ++p) {
+  CTD_LOOP for (int p = 0; p < 6; ++p) {
     get(w.hand[p], w.n_hand[p], CTD_HAND_CAP); get(w.bld[p], w.n_bld[p], CTD_BLD_CAP);
     get(w.mus[p], w.n_mus[p], CTD_MUS_CAP); get(w.jd[p], w.n_jd[p], CTD_JD_CAP);
   }
   w.deck_head = 0;
   get(w.deck, w.n_deck, CTD_DECK_CAP - 1);
   get(w.disc, w.n_disc, CTD_DISC_CAP);
-  for (int p = 0; p < 6; ++p) {
+  CTD_LOOP for (int p = 0; p < 6; ++p) {
     w.gold[p] = s->gold[p]; w.role[p] = s->role[p]; w.replicas[p] = s->replicas[p]; w.pflags[p] = s->pflags[p];
     w.order[p] = s->order[p]; w.used_roles[p] = s->used_roles[p]; w.points[p] = s->points[p];
   }
-  for (int r = 0; r < 8; ++r) { w.rprops[r] = s->rprops[r]; w.variant[r] = s->variant[r]; }
+  CTD_LOOP for (int r = 0; r < 8; ++r) { w.rprops[r] = s->rprops[r]; w.variant[r] = s->variant[r]; }
   w.used_len = s->used_len; w.rtc_mask = s->rtc_mask; w.state = s->state; w.player = s->player; w.done = s->done;
   w.n_trade = s->done_builds & 15; w.n_nontrade = s->done_builds >> 4;
   w.next_player = s->next_player; w.next_mode = s->next_mode; w.crown = s->crown; w.gflags = s->gflags;

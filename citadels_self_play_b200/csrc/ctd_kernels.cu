@@ -18,6 +18,9 @@
 
 #define CTD_WARPS_PER_BLOCK 8
 #define CTD_BLOCK (CTD_WARPS_PER_BLOCK * 32)
+#ifndef CTD_PLAYOUT_MIN_BLOCKS
+#define CTD_PLAYOUT_MIN_BLOCKS 8
+#endif
 #define CTD_FULL 0xFFFFFFFFu
 
 // ------------------------------------------------------------------------------------------ device helpers
@@ -128,7 +131,7 @@ struct CtdWarpStats {
   unsigned long long psq[6];
 };
 
-__global__ void __launch_bounds__(CTD_BLOCK) ctd_k_playout(CtdPlayoutArgs a) {
+__global__ void __launch_bounds__(CTD_BLOCK, CTD_PLAYOUT_MIN_BLOCKS) ctd_k_playout(CtdPlayoutArgs a) {
   __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
   __shared__ ctd_state stage[CTD_WARPS_PER_BLOCK];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
