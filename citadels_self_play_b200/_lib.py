@@ -38,6 +38,12 @@ SIGNATURES = {
     "ctd_playout_dev": (_i, [c_void, _u64, _u64, _u64, _i, _u32, ctypes.POINTER(PlayoutStats),
                              ctypes.POINTER(ctypes.c_float)]),
     "ctd_launch_count": (_u64, [c_void]),
+    "ctd_make_roots": (_i, [c_void, _u32, _u64, _u64, _i, _u32, _u32, c_void]),
+    "ctd_load_roots": (_i, [c_void, _u32, c_void, c_void, c_void, c_void]),
+    "ctd_store_roots": (_i, [c_void, _u32, c_void, c_void, c_void, c_void]),
+    "ctd_mccfr_tree_shape": (None, [_u32, _i, ctypes.POINTER(_u32), ctypes.POINTER(_u32), ctypes.POINTER(_u32),
+                                    ctypes.POINTER(_u64)]),
+    "ctd_mccfr": (_i, [c_void, _u32, _u64, _u32, _i, c_void, c_void, ctypes.POINTER(ctypes.c_float)]),
 }
 
 _lib = None

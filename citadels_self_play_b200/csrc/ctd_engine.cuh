@@ -139,6 +139,7 @@ struct CtdWork {
   uint8_t warrant_building, ruleset, err;
   // chance: Philox4x32-10 keyed (seed, gid) or a recorded tape
   uint32_t k0, k1, g0, g1;
+  uint32_t stream;  // Philox counter word 1: 0 = game chance, 1 = CFR tree
   uint32_t draws;
   uint32_t buf[4];
   uint32_t buf_blk;
@@ -169,6 +170,7 @@ CTD_HD inline void ctd_chance_init(CtdWork& w, uint64_t seed, uint64_t gid, uint
   w.k0 = (uint32_t)seed; w.k1 = (uint32_t)(seed >> 32);
   w.g0 = (uint32_t)gid; w.g1 = (uint32_t)(gid >> 32);
   w.draws = draws;
+  w.stream = 0;
   w.buf_blk = 0xFFFFFFFFu;
   w.tape = nullptr; w.tape_pos = 0; w.tape_len = 0;
 }
@@ -176,7 +178,7 @@ CTD_HD inline void ctd_chance_init(CtdWork& w, uint64_t seed, uint64_t gid, uint
 CTD_HD inline uint32_t ctd_u32(CtdWork& w) {
   uint32_t blk = w.draws >> 2;
   if (blk != w.buf_blk) {
-    ctd_philox(blk, 0u, w.g0, w.g1, w.k0, w.k1, w.buf);
+    ctd_philox(blk, w.stream, w.g0, w.g1, w.k0, w.k1, w.buf);
     w.buf_blk = blk;
   }
   return w.buf[w.draws++ & 3];
@@ -203,6 +205,101 @@ CTD_HD inline void ctd_shuffle(CtdWork& w, int n, At at) {
     int j = (int)ctd_randbelow(w, (uint32_t)(i + 1));
     uint8_t a = at(i), b = at(j);
     at(i) = b; at(j) = a;
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------ knowledge (CFR path)
+// What one observer ("viewer") believes: Agent.known_roles / Agent.known_hands (game/agent.py:25-26,
+// game/helper_classes.py:37-71), plus the looked-at hand of whoever used the Wizard this round
+// (the HandKnowledge the state-10 enumerator reads, game/agent_functions.py:311).  Playouts do not carry it.
+#define CTD_KN_HK_MAX 8
+#define CTD_KN_POOL 256
+#define CTD_KN_WIZ_CAP 48
+enum { CTD_HK_WIZARD = 1, CTD_HK_USED = 2 };
+struct CtdHK {
+  int8_t pid;      // -1 = the deck (Lighthouse)
+  uint8_t conf;    // 5..1, dropped at 0 (game/agent.py:100-109)
+  uint8_t flags;
+  uint8_t n;
+  uint16_t off;    // into pool
+  uint16_t pad;
+};
+struct CtdKnow {
+  uint8_t viewer;
+  uint8_t conf_mask;  // bit q: known_roles[*][q].confirmed (the same for every observer)
+  uint8_t n_hk;
+  uint8_t wiz_n;
+  uint16_t kr[6];     // viewer's possible_roles per seat: bit r = rank r, bit 8 = "Bewitched"
+  CtdHK hk[CTD_KN_HK_MAX];
+  uint8_t wiz_cards[CTD_KN_WIZ_CAP];
+  uint8_t pool[CTD_KN_POOL];
+  uint16_t pool_used;
+  uint8_t err;
+  uint8_t pad[13];
+};
+static_assert(sizeof(CtdKnow) == 400, "CtdKnow layout");
+struct CtdKnowSet {  // the observers being tracked: 1 (CFR viewer) or 6 (root generation); n == 0 in playouts
+  CtdKnow* k;
+  int n;
+};
+
+CTD_HD inline void ctd_kn_init(CtdKnow& k, int viewer) {
+  uint8_t* raw = (uint8_t*)&k;
+  CTD_LOOP for (int i = 0; i < (int)sizeof(CtdKnow); ++i) raw[i] = 0;
+  k.viewer = (uint8_t)viewer;
+}
+// Agent.substract_from_known_hand_confidences_and_clear_wizard + reset_known_roles (game/agent.py:100-114)
+CTD_HD CTD_NI inline void ctd_kn_setup_round(CtdKnow& k) {
+  int keep = 0;
+  uint16_t pos = 0;
+  CTD_LOOP for (int i = 0; i < k.n_hk; ++i) {
+    CtdHK h = k.hk[i];
+    h.conf -= 1;
+    h.flags = 0;
+    if (h.conf != 0) {
+      CTD_LOOP for (int j = 0; j < h.n; ++j) k.pool[pos + j] = k.pool[h.off + j];  // entries only move down
+      h.off = pos;
+      pos += h.n;
+      k.hk[keep++] = h;
+    }
+  }
+  CTD_LOOP for (int i = keep; i < k.n_hk; ++i) { CtdHK z = {0, 0, 0, 0, 0, 0}; k.hk[i] = z; }
+  CTD_LOOP for (int j = pos; j < k.pool_used; ++j) k.pool[j] = 0;  // unused bytes stay zero (records compare bytewise)
+  k.n_hk = (uint8_t)keep;
+  k.pool_used = pos;
+  CTD_LOOP for (int q = 0; q < 6; ++q) k.kr[q] = 0;
+  k.conf_mask = 0;
+  CTD_LOOP for (int j = 0; j < k.wiz_n; ++j) k.wiz_cards[j] = 0;
+  k.wiz_n = 0;
+}
+CTD_HD CTD_NI inline void ctd_kn_add_hk(CtdKnow& k, int pid, const uint8_t* cards, int n, int ring_head, int ring_mask,
+                                        bool wizard) {
+  if (k.n_hk >= CTD_KN_HK_MAX || k.pool_used + n > CTD_KN_POOL) { k.err |= CTD_ERR_OVERFLOW; return; }
+  CtdHK& h = k.hk[k.n_hk++];
+  h.pid = (int8_t)pid; h.conf = 5; h.flags = wizard ? CTD_HK_WIZARD : 0; h.n = (uint8_t)n; h.off = k.pool_used; h.pad = 0;
+  CTD_LOOP for (int i = 0; i < n; ++i) k.pool[k.pool_used + i] = cards[(ring_head + i) & ring_mask];
+  k.pool_used += (uint16_t)n;
+}
+// remove the first card of type t from entry i (Deck.get_a_card_like_it on the HandKnowledge copy)
+CTD_HD CTD_NI inline void ctd_kn_hk_remove(CtdKnow& k, int i, int t) {
+  CtdHK& h = k.hk[i];
+  CTD_LOOP for (int j = 0; j < h.n; ++j)
+    if (ctd_ctype(k.pool[h.off + j]) == t) {
+      CTD_LOOP for (int x = h.off + j; x + 1 < k.pool_used; ++x) k.pool[x] = k.pool[x + 1];
+      --h.n;
+      --k.pool_used;
+      k.pool[k.pool_used] = 0;
+      CTD_LOOP for (int e = i + 1; e < k.n_hk; ++e) k.hk[e].off -= 1;
+      return;
+    }
+}
+// confirm_role_knowledges (game/option_functions.py:608-622): every observer learns `seat`'s role;
+// the filter on the other entries is a no-op
+CTD_HD inline void ctd_kn_confirm(CtdKnowSet ks, int seat, int role) {
+  CTD_LOOP for (int i = 0; i < ks.n; ++i) {
+    ks.k[i].kr[seat] = (uint16_t)(1u << (role == CTD_ROLE_BEWITCHED ? 8 : role));
+    ks.k[i].conf_mask |= (uint8_t)(1u << seat);
   }
 }
 
@@ -291,7 +388,7 @@ CTD_HD inline void ctd_clear_done(CtdWork& w) { w.done = 0; w.n_trade = 0; w.n_n
 
 // ------------------------------------------------------------------------------------------ round machine
 // Game.setup_round (game/game.py:144-171)
-CTD_HD CTD_NI inline void ctd_setup_round(CtdWork& w) {
+CTD_HD CTD_NI inline void ctd_setup_round(CtdWork& w, CtdKnowSet ks = CtdKnowSet{nullptr, 0}) {
   CTD_LOOP for (int r = 0; r < 8; ++r) w.rprops[r] = 0;
   w.used_len = 0;
   CTD_LOOP for (int i = 0; i < 6; ++i) w.used_roles[i] = 0;
@@ -311,6 +408,7 @@ CTD_HD CTD_NI inline void ctd_setup_round(CtdWork& w) {
   w.next_mode = CTD_NEXT_NONE;
   w.next_player = 0;
   w.wiz_target = 0xFF;  // Agent.substract_from_known_hand_confidences_and_clear_wizard (game/agent.py:100-109)
+  CTD_LOOP for (int i = 0; i < ks.n; ++i) ctd_kn_setup_round(ks.k[i]);
 }
 
 // Game.refresh_used_roles (game/game.py:349-357); value+1 encoding keeps Bewitched (-1) sortable as 0
@@ -406,7 +504,7 @@ CTD_HD inline void ctd_is_last_round(CtdWork& w) {
 }
 
 // Game.set_preset (game/game.py:420-489): Deck() shuffles the 76 cards, fixed hands are pulled by type
-CTD_HD CTD_NI inline void ctd_deal_preset(CtdWork& w, int ruleset) {
+CTD_HD CTD_NI inline void ctd_deal_preset(CtdWork& w, int ruleset, uint8_t* used_cards_out = nullptr) {
   CTD_LOOP for (int p = 0; p < 6; ++p) {
     w.n_hand[p] = w.n_bld[p] = w.n_mus[p] = w.n_jd[p] = 0;
     w.gold[p] = 2; w.role[p] = CTD_ROLE_NONE; w.replicas[p] = 0; w.pflags[p] = 0;
@@ -424,6 +522,8 @@ CTD_HD CTD_NI inline void ctd_deal_preset(CtdWork& w, int ruleset) {
   w.n_deck = 76;
   uint8_t* d = w.deck;
   ctd_shuffle(w, 76, [d](int i) -> uint8_t& { return d[i]; });
+  if (used_cards_out != nullptr)  // self.used_cards = deepcopy(self.deck) (game/game.py:424)
+    CTD_LOOP for (int i = 0; i < 76; ++i) used_cards_out[i] = w.deck[i];
   const uint8_t hands[6][6] = {{0, 0, 16, 17, 18, 19}, {1, 1, 20, 21, 22, 23}, {2, 3, 24, 25, 26, 27},
                                {3, 4, 28, 29, 30, 31}, {4, 0, 32, 33, 34, 35}, {0, 1, 36, 37, 39, 0}};
   CTD_LOOP for (int p = 0; p < 6; ++p)
@@ -512,7 +612,7 @@ CTD_HD CTD_NI inline void ctd_character_options(const CtdWork& w, int p, int nm,
       case CTD_ABBOT: {                                                // :422-430
         int n = ctd_count_suit(w.hand[p], w.n_hand[p], CTD_SUIT_RELIGION);
         if (n > 0)
-          CTD_LOOP for (int k = 0; k <= n; ++k) e.one(ctd_opt(CTD_K_ABBOT, p) | ctd_f_count(k));
+          CTD_LOOP for (int k = 0; k <= n; ++k) e.one(ctd_opt(CTD_K_ABBOT, p) | ctd_f_count(k) | ctd_f_r(n));
         break;
       }
       case CTD_MERCHANT: e.one(ctd_opt(CTD_K_MERCHANT, p)); break;    // :438-440
@@ -626,7 +726,7 @@ CTD_HD CTD_NI inline void ctd_wizard_take_options(const CtdWork& w, int p, const
 
 // Agent.get_options (game/agent.py:50-83).  An empty result with err set means the reference would raise.
 template <class E>
-CTD_HD CTD_NI inline void ctd_enumerate(CtdWork& w, E& e) {
+CTD_HD CTD_NI inline void ctd_enumerate(CtdWork& w, E& e, const CtdKnow* kn = nullptr) {
   if (w.gflags & 2) return;  // terminal: the reference's loops stop here
   const int p = w.player;
   const int st = w.state;
@@ -698,7 +798,8 @@ CTD_HD CTD_NI inline void ctd_enumerate(CtdWork& w, E& e) {
       if (st == 10) {
         int q = w.wiz_target;
         if (q >= 6) { w.err |= CTD_ERR_REF_RAISE; return; }
-        ctd_wizard_take_options(w, p, w.hand[q], w.n_hand[q], e);
+        if (kn != nullptr) ctd_wizard_take_options(w, p, kn->wiz_cards, kn->wiz_n, e);
+        else ctd_wizard_take_options(w, p, w.hand[q], w.n_hand[q], e);
         return;
       }
       w.err |= CTD_ERR_UNIMPL;
@@ -741,7 +842,7 @@ CTD_HD CTD_NI inline void ctd_apply_build(CtdWork& w, int p, int t, int replica)
 }
 
 // finish_main_sequnce_actions (game/option_functions.py:189-243).  Returns true when the game ended.
-CTD_HD CTD_NI inline bool ctd_apply_finish(CtdWork& w, uint64_t d) {
+CTD_HD CTD_NI inline bool ctd_apply_finish(CtdWork& w, uint64_t d, CtdKnowSet ks) {
   const int p = CTD_OPT_PERP(d);
   const int pr = w.role[p];
   if (pr >= 8) { w.err |= CTD_ERR_REF_RAISE; return false; }
@@ -750,7 +851,8 @@ CTD_HD CTD_NI inline bool ctd_apply_finish(CtdWork& w, uint64_t d) {
     if (ctd_owns(w, p, 28) && w.n_hand[p] == 0) { ctd_draw_to_jd(w, p); ctd_draw_to_jd(w, p); }  // Park
     if (ctd_owns(w, p, 30) && w.n_hand[p] == 0) w.gold[p] += 1;                                  // Poorhouse
   }
-  if (CTD_OPT_CROWN(d)) ctd_move_crown(w, p);
+  if (CTD_OPT_CROWN(d)) { ctd_kn_confirm(ks, p, pr); ctd_move_crown(w, p); }
+  else if (dead) ctd_kn_confirm(ks, p, pr);
   if (CTD_OPT_NEXT_WITCH(d)) {  // :211-230 the witch takes over the possessed role
     int wi = ctd_player_from_rank(w, 0);
     if (wi < 0) { w.err |= CTD_ERR_REF_RAISE; return false; }
@@ -759,13 +861,18 @@ CTD_HD CTD_NI inline bool ctd_apply_finish(CtdWork& w, uint64_t d) {
     w.role[wi] = (uint8_t)pr;
     w.rprops[pr] &= (uint8_t)~CTD_RP_POSSESSED;
     w.role[p] = CTD_ROLE_BEWITCHED;
+    CTD_LOOP for (int i = 0; i < ks.n; ++i) {  // :222-226
+      CtdKnow& k = ks.k[i];
+      if (k.viewer != wi) k.kr[wi] = (uint16_t)(1u << pr);
+      if (k.viewer != p) k.kr[p] = (uint16_t)(1u << 8);
+    }
     ctd_clear_done(w);
     return false;
   }
   if (w.used_len == 0) { w.err |= CTD_ERR_REF_RAISE; return false; }
   if ((int)w.used_roles[w.used_len - 1] - 1 == pr) {  // last player of the round
     if (ctd_check_game_ending(w)) return true;
-    ctd_setup_round(w);
+    ctd_setup_round(w, ks);
   } else {
     ctd_setup_next_player(w, p);
   }
@@ -773,7 +880,7 @@ CTD_HD CTD_NI inline bool ctd_apply_finish(CtdWork& w, uint64_t d) {
 }
 
 // option.carry_out (game/option.py:118-122).  Returns true when this step ended the game.
-CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d) {
+CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdKnowSet{nullptr, 0}) {
   const int k = CTD_OPT_KIND(d);
   const int p = CTD_OPT_PERP(d);
   bool won = false;
@@ -782,6 +889,17 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d) {
       int r = CTD_OPT_RANK(d);
       w.role[p] = (uint8_t)r;
       w.rtc_mask &= (uint8_t)~(1u << r);
+      CTD_LOOP for (int i = 0; i < ks.n; ++i) {  // only the picker's beliefs are written (:11-25)
+        CtdKnow& k = ks.k[i];
+        if (k.viewer != p) continue;
+        int me = 0;
+        while (me < 5 && w.order[me] != p) ++me;
+        CTD_LOOP for (int oi = 0; oi < 6; ++oi) {
+          int q = w.order[oi];
+          if (q == p) continue;
+          k.kr[q] = oi < me ? (uint16_t)(0xFF & ~w.rtc_mask & ~(1u << r)) : (uint16_t)w.rtc_mask;
+        }
+      }
       if (p != w.order[5]) {
         int i = 0;
         CTD_LOOP while (i < 5 && w.order[i] != p) ++i;
@@ -794,6 +912,8 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d) {
     }
     case CTD_K_GOLD_OR_CARD: {  // carry_out_gold_or_card (:33-55)
       int r = w.role[p];
+      if (r == CTD_ROLE_NONE) { w.err |= CTD_ERR_REF_RAISE; break; }
+      ctd_kn_confirm(ks, p, r);  // confirm_role_knowledges (:35)
       if (r >= 8) { w.err |= CTD_ERR_REF_RAISE; break; }
       if (w.rprops[r] & CTD_RP_ROBBED) {
         int th = ctd_player_from_rank(w, 1);
@@ -838,7 +958,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d) {
       }
       break;
     case CTD_K_BUILD: ctd_apply_build(w, p, CTD_OPT_CARD_A(d), CTD_OPT_REPLICA(d)); break;
-    case CTD_K_FINISH: won = ctd_apply_finish(w, d); break;
+    case CTD_K_FINISH: won = ctd_apply_finish(w, d, ks); break;
     case CTD_K_SMITHY:  // carry_out_smithy (:131-138): the cards go to just_drawn_cards
       w.gold[p] -= 2;
       CTD_LOOP for (int i = 0; i < 3; ++i) ctd_draw_to_jd(w, p);
@@ -873,6 +993,8 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d) {
     }
     case CTD_K_LIGHTHOUSE: {  // carry_out_lighthouse (:173-180)
       int t = CTD_OPT_CARD_A(d), c = t, n = w.n_deck;
+      CTD_LOOP for (int i = 0; i < ks.n; ++i)  // HandKnowledge(player_id=-1, hand=deepcopy(deck)) (:174)
+        if (ks.k[i].viewer == p) ctd_kn_add_hk(ks.k[i], -1, w.deck, n, w.deck_head, CTD_DECK_CAP - 1, false);
       CTD_LOOP for (int i = 0; i < n; ++i)
         if (ctd_ctype(ctd_dk(w, i)) == t) {
           c = ctd_dk(w, i);
@@ -948,6 +1070,14 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d) {
       break;
     }
     case CTD_K_LOOK_AT_HAND:  // carry_out_wizard_hand_looking (:305-310)
+      CTD_LOOP for (int i = 0; i < ks.n; ++i) {
+        CtdKnow& k = ks.k[i];
+        int q = CTD_OPT_TARGET(d), n = w.n_hand[q];
+        if (n > CTD_KN_WIZ_CAP) { k.err |= CTD_ERR_OVERFLOW; n = CTD_KN_WIZ_CAP; }
+        CTD_LOOP for (int j = 0; j < CTD_KN_WIZ_CAP; ++j) k.wiz_cards[j] = j < n ? w.hand[q][j] : 0;
+        k.wiz_n = (uint8_t)n;
+        if (k.viewer == p) ctd_kn_add_hk(k, q, w.hand[q], w.n_hand[q], 0, 0xFFFF, true);
+      }
       w.wiz_target = (uint8_t)CTD_OPT_TARGET(d);
       w.state = 10;
       w.player = (uint8_t)p;
@@ -959,6 +1089,19 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d) {
       int q = CTD_OPT_TARGET(d), t = CTD_OPT_CARD_A(d);
       ctd_append(w, w.hand[p], w.n_hand[p], CTD_HAND_CAP, ctd_take_like(w.hand[q], w.n_hand[q], t));
       if (CTD_OPT_BUILD(d)) ctd_apply_build(w, p, t, ctd_count_type(w.bld[p], w.n_bld[p], t));
+      CTD_LOOP for (int i = 0; i < ks.n; ++i) {  // the looked-at copy loses the card too (:320, :326)
+        CtdKnow& k = ks.k[i];
+        CTD_LOOP for (int j = 0; j < k.wiz_n; ++j)
+          if (ctd_ctype(k.wiz_cards[j]) == t) {
+            CTD_LOOP for (int x = j; x + 1 < k.wiz_n; ++x) k.wiz_cards[x] = k.wiz_cards[x + 1];
+            --k.wiz_n;
+            k.wiz_cards[k.wiz_n] = 0;
+            break;
+          }
+        if (k.viewer == p)
+          CTD_LOOP for (int h = 0; h < k.n_hk; ++h)
+            if (k.hk[h].flags & CTD_HK_WIZARD) { ctd_kn_hk_remove(k, h, t); break; }
+      }
       ctd_restore_next(w);
       break;
     }
@@ -979,7 +1122,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d) {
       w.done |= CTD_DM_CHARACTER;
       break;
     case CTD_K_ABBOT: {  // carry_out_abbot (:405-412)
-      int n = ctd_count_suit(w.hand[p], w.n_hand[p], CTD_SUIT_RELIGION), kc = CTD_OPT_COUNT(d);
+      int n = CTD_OPT_R(d), kc = CTD_OPT_COUNT(d);  // the option carries its own gold/card list
       w.gold[p] += (int8_t)(n - kc);
       CTD_LOOP for (int i = 0; i < kc; ++i) ctd_draw_to_hand(w, p);
       ctd_to5(w, p);

@@ -15,6 +15,7 @@
 
 #include "ctd_engine.cuh"
 #include "ctd_warp.cuh"
+#include "ctd_mccfr.cuh"
 
 #define CTD_WARPS_PER_BLOCK 8
 #define CTD_BLOCK (CTD_WARPS_PER_BLOCK * 32)
@@ -204,6 +205,156 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_PLAYOUT_MIN_BLOCKS) ctd_k_playo
   }
 }
 
+// ------------------------------------------------------------------------------------------ CFR roots + MCCFR
+// run_utils.create_a_close_to_finished_game / create_a_random_game (run_utils.py:29-72): play a preset game to
+// terminal, step back `u` decisions (u uniform in [back_lo, back_hi], drawn from Philox stream word 2), then move
+// forward until the player to move has a real choice.  The game is replayed from its (seed, gid) with the
+// knowledge of all six observers tracked, so the root carries what its player to move has learnt so far.
+struct CtdRootArgs {
+  uint32_t n;
+  uint64_t seed, first_gid;
+  int ruleset;
+  uint32_t back_lo, back_hi;
+  ctd_state* roots;
+  CtdKnow* knows;
+  uint8_t* used_cards;  // [n][76]
+  uint64_t* gids;
+  uint32_t* root_step;  // [n] index of the root in the game's step sequence
+};
+
+__device__ __forceinline__ uint64_t ctd_lane0_choose(CtdWork& w, const CtdKnow* kn) {
+  CtdEmit e{nullptr, 0, 0, 0xFFFFFFFFu, 0};
+  ctd_enumerate(w, e, kn);
+  if (e.n == 0) return 0;
+  uint32_t k = ctd_randbelow(w, e.n);
+  CtdEmit e2{nullptr, 0, 0, k, 0};
+  ctd_enumerate(w, e2, kn);
+  return e2.got;
+}
+
+__global__ void __launch_bounds__(CTD_BLOCK) ctd_k_make_roots(CtdRootArgs a) {
+  __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
+  __shared__ CtdKnow knows[CTD_WARPS_PER_BLOCK][6];
+  __shared__ ctd_state stage[CTD_WARPS_PER_BLOCK];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t slot = blockIdx.x * CTD_WARPS_PER_BLOCK + wib;
+  if (slot >= a.n) return;
+  CtdWork& w = works[wib];
+  CtdKnow* kn = knows[wib];
+  if (lane == 0) {
+    const uint64_t gid = a.first_gid + slot;
+    // pass 1: length of the game
+    ctd_new_game(w, a.seed, gid, a.ruleset);
+    while (!(w.gflags & 2) && !w.err && w.steps < 4096) {
+      uint64_t d = ctd_lane0_choose(w, nullptr);
+      if (d == 0) { w.err |= CTD_ERR_REF_RAISE; break; }
+      ctd_apply(w, d);
+    }
+    const uint32_t T = w.steps;
+    uint32_t r[4];
+    ctd_philox(0u, 2u, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)a.seed, (uint32_t)(a.seed >> 32), r);
+    const uint32_t u = a.back_lo + (uint32_t)(((uint64_t)r[0] * (a.back_hi - a.back_lo + 1)) >> 32);
+    const uint32_t k = T > u ? T - u : 0;
+    // pass 2: replay with knowledge
+    ctd_chance_init(w, a.seed, gid, 0);
+    ctd_deal_preset(w, a.ruleset, a.used_cards + (size_t)slot * 76);
+    for (int o = 0; o < 6; ++o) ctd_kn_init(kn[o], o);
+    CtdKnowSet ks{kn, 6};
+    ctd_setup_round(w, ks);
+    int limit = 0;
+    for (;;) {
+      if ((w.gflags & 2) || w.err) break;
+      CtdEmit e{nullptr, 0, 0, 0xFFFFFFFFu, 0};
+      ctd_enumerate(w, e, &kn[0]);
+      if (e.n == 0) { w.err |= CTD_ERR_REF_RAISE; break; }
+      if (w.steps >= k) {  // `while len(options) < 2 and limit < 100` (run_utils.py:46-50)
+        if (e.n >= 2 || limit >= 100) break;
+        ++limit;
+      }
+      uint32_t pick = ctd_randbelow(w, e.n);
+      CtdEmit e2{nullptr, 0, 0, pick, 0};
+      ctd_enumerate(w, e2, &kn[0]);
+      ctd_apply(w, e2.got, ks);
+    }
+    a.root_step[slot] = w.steps;
+    a.gids[slot] = gid;
+    int viewer = w.player < 6 ? w.player : 0;
+    for (int o = 0; o < 6; ++o) w.err |= kn[o].err;
+    a.knows[slot] = kn[viewer];
+    ctd_pack(w, &stage[wib]);
+  }
+  ctd_record_store(&a.roots[slot], &stage[wib], lane);
+}
+
+struct CtdMccfrArgs {
+  uint32_t n_roots;
+  const ctd_state* roots;
+  const CtdKnow* knows;
+  const uint8_t* used_cards;
+  const uint64_t* gids;
+  uint64_t seed;
+  uint32_t iterations;
+  uint32_t max_nodes, child_cap, arr_cap;
+  uint8_t* trees;
+  size_t tree_stride;
+  ctd_mccfr_result* results;
+  unsigned long long* counter;
+  uint64_t* opts_scratch;  // [gridDim.x * CTD_WARPS_PER_BLOCK][CTD_MCCFR_OPT_CAP]
+};
+
+__device__ __forceinline__ CtdTree ctd_tree_at(uint8_t* base, uint32_t max_nodes, uint32_t child_cap) {
+  CtdTree T;
+  T.hdr = (CtdTreeHdr*)base;
+  T.nodes = (CtdNode*)(base + sizeof(CtdTreeHdr));
+  T.children = (CtdChild*)((uint8_t*)T.nodes + (size_t)max_nodes * sizeof(CtdNode));
+  T.arr = (double*)((uint8_t*)T.children + (size_t)child_cap * sizeof(CtdChild));
+  return T;
+}
+
+__device__ void ctd_write_result(CtdTree& T, ctd_mccfr_result* r) {
+  const CtdTreeHdr& h = *T.hdr;
+  const CtdNode& n = T.nodes[0];
+  r->status = h.status; r->n_nodes = h.n_nodes; r->iterations = h.iterations; r->rng_draws = h.rng_draws;
+  r->n_children = n.n_children; r->role_pick = (n.flags & CTD_NF_ROLE_PICK) ? 1 : 0;
+  r->viewer = h.viewer; r->player = n.player;
+  for (int i = 0; i < 6; ++i) { r->node_value[i] = n.V[i]; r->winning_probabilities[i] = n.P[i]; }
+  const uint32_t K = n.n_children < CTD_MCCFR_MAX_RESULT ? n.n_children : CTD_MCCFR_MAX_RESULT;
+  const bool rp = n.flags & CTD_NF_ROLE_PICK;
+  const uint32_t na = n.n_children == 0 ? 0 : (rp ? 60 : K);
+  for (uint32_t i = 0; i < K; ++i) r->options[i] = T.children[n.child_off + i].desc;
+  const double *R = ctd_R(T, n), *S = ctd_S(T, n), *C = ctd_C(T, n);
+  for (uint32_t i = 0; i < na; ++i) { r->cumulative_regrets[i] = R[i]; r->strategy[i] = S[i]; r->cumulative_strategy[i] = C[i]; }
+}
+
+__global__ void __launch_bounds__(CTD_BLOCK) ctd_k_mccfr(CtdMccfrArgs a) {
+  __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
+  __shared__ CtdKnow knows[CTD_WARPS_PER_BLOCK];
+  __shared__ uint8_t scratch[CTD_WARPS_PER_BLOCK][256];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint64_t* opts = a.opts_scratch + ((size_t)blockIdx.x * CTD_WARPS_PER_BLOCK + wib) * CTD_MCCFR_OPT_CAP;
+  for (;;) {
+    unsigned long long t = 0;
+    if (lane == 0) t = atomicAdd(a.counter, 1ull);
+    t = __shfl_sync(CTD_FULL, t, 0);
+    if (t >= a.n_roots) break;
+    if (lane == 0) {
+      CtdTree T = ctd_tree_at(a.trees + t * a.tree_stride, a.max_nodes, a.child_cap);
+      T.w = &works[wib]; T.kn = &knows[wib]; T.opts = opts; T.scratch = scratch[wib];
+      CtdWork& w = *T.w;
+      for (int i = 0; i < 76; ++i) T.hdr->used_cards[i] = a.used_cards[t * 76 + i];
+      ctd_unpack(&a.roots[t], w);
+      ctd_chance_init(w, a.seed, a.gids[t], 0);
+      w.stream = 1;
+      w.err = 0;
+      *T.kn = a.knows[t];
+      ctd_tree_init(T, a.max_nodes, a.child_cap, a.arr_cap, T.kn->viewer, a.gids[t], false, false);
+      ctd_cfr_train(T, a.iterations);
+      if (a.results) ctd_write_result(T, &a.results[t]);
+    }
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side / C ABI
 struct ctd_engine {
   int device;
@@ -224,6 +375,15 @@ struct ctd_engine {
   ctd_playout_stats* d_stats;
   cudaEvent_t ev0, ev1;
   int sm_count;
+  // CFR roots (device): parallel to slots
+  CtdKnow* d_knows;
+  uint8_t* d_used_cards;
+  uint64_t* d_gids;
+  uint32_t* d_root_step;
+  uint8_t* d_trees;
+  size_t trees_bytes;
+  uint64_t* d_opts_scratch;
+  size_t opts_scratch_bytes;
   char err[256];
 };
 
@@ -282,6 +442,12 @@ void ctd_destroy(ctd_engine* e) {
   if (e->d_scratch) cudaFree(e->d_scratch);
   if (e->d_counter) cudaFree(e->d_counter);
   if (e->d_stats) cudaFree(e->d_stats);
+  if (e->d_knows) cudaFree(e->d_knows);
+  if (e->d_used_cards) cudaFree(e->d_used_cards);
+  if (e->d_gids) cudaFree(e->d_gids);
+  if (e->d_root_step) cudaFree(e->d_root_step);
+  if (e->d_trees) cudaFree(e->d_trees);
+  if (e->d_opts_scratch) cudaFree(e->d_opts_scratch);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
@@ -489,6 +655,123 @@ ctd_status ctd_playout_slots(ctd_engine* e, uint32_t n, uint32_t max_steps, int8
   if (winner) CTD_CUDA(e, cudaMemcpyAsync(winner, a.winner, n, cudaMemcpyDeviceToHost, e->stream));
   if (steps) CTD_CUDA(e, cudaMemcpyAsync(steps, a.steps, sb, cudaMemcpyDeviceToHost, e->stream));
   CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  return CTD_OK;
+}
+
+static ctd_status ctd_root_buffers(ctd_engine* e) {
+  if (e->d_knows) return CTD_OK;
+  CTD_CUDA(e, cudaMalloc((void**)&e->d_knows, (size_t)e->capacity * sizeof(CtdKnow)));
+  CTD_CUDA(e, cudaMalloc((void**)&e->d_used_cards, (size_t)e->capacity * 76));
+  CTD_CUDA(e, cudaMalloc((void**)&e->d_gids, (size_t)e->capacity * sizeof(uint64_t)));
+  CTD_CUDA(e, cudaMalloc((void**)&e->d_root_step, (size_t)e->capacity * sizeof(uint32_t)));
+  CTD_CUDA(e, cudaMemsetAsync(e->d_knows, 0, (size_t)e->capacity * sizeof(CtdKnow), e->stream));
+  CTD_CUDA(e, cudaMemsetAsync(e->d_used_cards, 0, (size_t)e->capacity * 76, e->stream));
+  CTD_CUDA(e, cudaMemsetAsync(e->d_gids, 0, (size_t)e->capacity * sizeof(uint64_t), e->stream));
+  return CTD_OK;
+}
+
+ctd_status ctd_make_roots(ctd_engine* e, uint32_t n, uint64_t seed, uint64_t first_gid, int ruleset, uint32_t back_lo,
+                          uint32_t back_hi, uint32_t* root_step) {
+  if (!e || n > e->capacity || back_hi < back_lo || (ruleset != CTD_RULESET_PRESET && ruleset != CTD_RULESET_CLASSIC))
+    return CTD_EARG;
+  if (n == 0) return CTD_OK;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  ctd_status s = ctd_root_buffers(e);
+  if (s != CTD_OK) return s;
+  e->seed = seed;
+  CtdRootArgs a{n, seed, first_gid, ruleset, back_lo, back_hi, e->d_slots, e->d_knows, e->d_used_cards, e->d_gids,
+                e->d_root_step};
+  ctd_k_make_roots<<<ctd_blocks(n), CTD_BLOCK, 0, e->stream>>>(a);
+  e->launches++;
+  CTD_CUDA(e, cudaGetLastError());
+  if (root_step)
+    CTD_CUDA(e, cudaMemcpyAsync(root_step, e->d_root_step, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  return CTD_OK;
+}
+
+ctd_status ctd_load_roots(ctd_engine* e, uint32_t n, const ctd_state* roots, const void* knows, const uint8_t* used_cards,
+                          const uint64_t* gids) {
+  if (!e || n > e->capacity || !roots || !knows || !used_cards || !gids) return CTD_EARG;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  ctd_status s = ctd_root_buffers(e);
+  if (s != CTD_OK) return s;
+  CTD_CUDA(e, cudaMemcpyAsync(e->d_slots, roots, (size_t)n * sizeof(ctd_state), cudaMemcpyHostToDevice, e->stream));
+  CTD_CUDA(e, cudaMemcpyAsync(e->d_knows, knows, (size_t)n * sizeof(CtdKnow), cudaMemcpyHostToDevice, e->stream));
+  CTD_CUDA(e, cudaMemcpyAsync(e->d_used_cards, used_cards, (size_t)n * 76, cudaMemcpyHostToDevice, e->stream));
+  CTD_CUDA(e, cudaMemcpyAsync(e->d_gids, gids, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream));
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  return CTD_OK;
+}
+
+ctd_status ctd_store_roots(ctd_engine* e, uint32_t n, ctd_state* roots, void* knows, uint8_t* used_cards, uint64_t* gids) {
+  if (!e || n > e->capacity || !e->d_knows) return CTD_EARG;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  if (roots) CTD_CUDA(e, cudaMemcpyAsync(roots, e->d_slots, (size_t)n * sizeof(ctd_state), cudaMemcpyDeviceToHost, e->stream));
+  if (knows) CTD_CUDA(e, cudaMemcpyAsync(knows, e->d_knows, (size_t)n * sizeof(CtdKnow), cudaMemcpyDeviceToHost, e->stream));
+  if (used_cards) CTD_CUDA(e, cudaMemcpyAsync(used_cards, e->d_used_cards, (size_t)n * 76, cudaMemcpyDeviceToHost, e->stream));
+  if (gids) CTD_CUDA(e, cudaMemcpyAsync(gids, e->d_gids, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  return CTD_OK;
+}
+
+void ctd_mccfr_tree_shape(uint32_t iterations, int ruleset, uint32_t* max_nodes, uint32_t* child_cap, uint32_t* arr_cap,
+                          uint64_t* bytes) {
+  // measured on the reference: <= 3.6 nodes per iteration (preset); a classic Magician expands ~1600 options at once
+  uint32_t extra = ruleset == CTD_RULESET_CLASSIC ? 8192 : 0;
+  uint32_t mn = 6 * iterations + 256 + extra, cc = mn + 10 * (iterations + 2), ac = 3 * cc + 180 * 64;
+  if (max_nodes) *max_nodes = mn;
+  if (child_cap) *child_cap = cc;
+  if (arr_cap) *arr_cap = ac;
+  if (bytes) *bytes = (uint64_t)((ctd_tree_bytes(mn, cc, ac) + 255) & ~(size_t)255);
+}
+
+ctd_status ctd_mccfr(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32_t iterations, int ruleset,
+                     ctd_mccfr_result* results, void* trees_out, float* elapsed_ms) {
+  if (!e || n_roots > e->capacity || !e->d_knows) return CTD_EARG;
+  if (n_roots == 0) return CTD_OK;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  uint32_t mn, cc, ac;
+  uint64_t stride;
+  ctd_mccfr_tree_shape(iterations, ruleset, &mn, &cc, &ac, &stride);
+  size_t need = (size_t)stride * n_roots;
+  if (need > e->trees_bytes) {
+    if (e->d_trees) CTD_CUDA(e, cudaFree(e->d_trees));
+    e->d_trees = nullptr; e->trees_bytes = 0;
+    CTD_CUDA(e, cudaMalloc((void**)&e->d_trees, need));
+    e->trees_bytes = need;
+  }
+  size_t rb = (size_t)n_roots * sizeof(ctd_mccfr_result);
+  ctd_status s = ctd_scratch(e, rb);
+  if (s != CTD_OK) return s;
+  CTD_CUDA(e, cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream));
+  CtdMccfrArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_roots = n_roots; a.roots = e->d_slots; a.knows = e->d_knows; a.used_cards = e->d_used_cards; a.gids = e->d_gids;
+  a.seed = seed; a.iterations = iterations; a.max_nodes = mn; a.child_cap = cc; a.arr_cap = ac;
+  a.trees = e->d_trees; a.tree_stride = stride; a.results = (ctd_mccfr_result*)e->d_scratch; a.counter = e->d_counter;
+  int per_sm = 0;
+  CTD_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctd_k_mccfr, CTD_BLOCK, 0));
+  if (per_sm < 1) per_sm = 1;
+  uint64_t want = (uint64_t)e->sm_count * per_sm, needb = (n_roots + CTD_WARPS_PER_BLOCK - 1) / CTD_WARPS_PER_BLOCK;
+  int grid = (int)(needb < want ? needb : want);
+  size_t ob = (size_t)grid * CTD_WARPS_PER_BLOCK * CTD_MCCFR_OPT_CAP * sizeof(uint64_t);
+  if (ob > e->opts_scratch_bytes) {
+    if (e->d_opts_scratch) CTD_CUDA(e, cudaFree(e->d_opts_scratch));
+    e->d_opts_scratch = nullptr; e->opts_scratch_bytes = 0;
+    CTD_CUDA(e, cudaMalloc((void**)&e->d_opts_scratch, ob));
+    e->opts_scratch_bytes = ob;
+  }
+  a.opts_scratch = e->d_opts_scratch;
+  CTD_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+  ctd_k_mccfr<<<grid, CTD_BLOCK, 0, e->stream>>>(a);
+  e->launches++;
+  CTD_CUDA(e, cudaGetLastError());
+  CTD_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+  if (results) CTD_CUDA(e, cudaMemcpyAsync(results, e->d_scratch, rb, cudaMemcpyDeviceToHost, e->stream));
+  if (trees_out) CTD_CUDA(e, cudaMemcpyAsync(trees_out, e->d_trees, need, cudaMemcpyDeviceToHost, e->stream));
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (elapsed_ms) CTD_CUDA(e, cudaEventElapsedTime(elapsed_ms, e->ev0, e->ev1));
   return CTD_OK;
 }
 

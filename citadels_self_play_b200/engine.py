@@ -4,7 +4,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from .layout import STATE_BYTES
+from .layout import STATE_BYTES, KNOW_BYTES, MCCFR_RESULT_DTYPE, TreeView
 
 RULESET_PRESET, RULESET_CLASSIC = 0, 1
 DEFAULT_SEED = 0xC17ADE15
@@ -117,6 +117,53 @@ class Engine:
         self._check(self._lib.ctd_playout_slots(self._h, n, max_steps, winner.ctypes.data, steps.ctypes.data),
                     "ctd_playout_slots")
         return winner, steps
+
+    # ---- MCCFR ----
+    def make_roots(self, n, seed=DEFAULT_SEED, first_gid=0, ruleset=RULESET_PRESET, back_lo=0, back_hi=20):
+        """CFR roots on the device (run_utils.create_a_close_to_finished_game).  -> root_step[n]"""
+        steps = np.empty(n, dtype=np.uint32)
+        self._check(self._lib.ctd_make_roots(self._h, n, seed, first_gid, ruleset, back_lo, back_hi, steps.ctypes.data),
+                    "ctd_make_roots")
+        return steps
+
+    def load_roots(self, roots, knows, used_cards, gids):
+        r = np.ascontiguousarray(roots, dtype=np.uint8).reshape(-1, STATE_BYTES)
+        k = np.ascontiguousarray(knows, dtype=np.uint8).reshape(-1, KNOW_BYTES)
+        u = np.ascontiguousarray(used_cards, dtype=np.uint8).reshape(-1, 76)
+        g = np.ascontiguousarray(gids, dtype=np.uint64)
+        assert len(r) == len(k) == len(u) == len(g)
+        self._check(self._lib.ctd_load_roots(self._h, len(r), r.ctypes.data, k.ctypes.data, u.ctypes.data, g.ctypes.data),
+                    "ctd_load_roots")
+
+    def store_roots(self, n):
+        r = np.empty((n, STATE_BYTES), dtype=np.uint8)
+        k = np.empty((n, KNOW_BYTES), dtype=np.uint8)
+        u = np.empty((n, 76), dtype=np.uint8)
+        g = np.empty(n, dtype=np.uint64)
+        self._check(self._lib.ctd_store_roots(self._h, n, r.ctypes.data, k.ctypes.data, u.ctypes.data, g.ctypes.data),
+                    "ctd_store_roots")
+        return r, k, u, g
+
+    def tree_shape(self, iterations, ruleset=RULESET_PRESET):
+        mn, cc, ac, by = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint64()
+        self._lib.ctd_mccfr_tree_shape(iterations, ruleset, ctypes.byref(mn), ctypes.byref(cc), ctypes.byref(ac),
+                                       ctypes.byref(by))
+        return mn.value, cc.value, ac.value, by.value
+
+    def mccfr(self, n_roots, iterations=200, seed=DEFAULT_SEED, ruleset=RULESET_PRESET, trees=False):
+        """CFRNode(...).cfr_train(iterations) on the loaded/made roots.  -> dict(results, trees, kernel_ms)"""
+        res = np.zeros(n_roots, dtype=MCCFR_RESULT_DTYPE)
+        ms = ctypes.c_float()
+        views = None
+        buf = None
+        if trees:
+            mn, cc, ac, by = self.tree_shape(iterations, ruleset)
+            buf = np.zeros((n_roots, by), dtype=np.uint8)
+        self._check(self._lib.ctd_mccfr(self._h, n_roots, seed, iterations, ruleset, res.ctypes.data,
+                                        buf.ctypes.data if trees else None, ctypes.byref(ms)), "ctd_mccfr")
+        if trees:
+            views = [TreeView(buf[i], mn, cc, ac) for i in range(n_roots)]
+        return dict(results=res, trees=views, kernel_ms=ms.value)
 
     def sync(self):
         self._check(self._lib.ctd_sync(self._h), "ctd_sync")

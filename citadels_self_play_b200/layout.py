@@ -49,3 +49,68 @@ def opt_fields(d):
                 b=((d >> 18) & 0x3F) - 1, rank=((d >> 24) & 0xF) - 1, named=((d >> 28) & 0xF) - 1,
                 replica=rep - 16 if rep >= 8 else rep, build=(d >> 36) & 1, next_witch=(d >> 37) & 1,
                 crown=(d >> 38) & 1, count=(d >> 39) & 0x3F, r=(d >> 45) & 0x3F, j=(d >> 51) & 0x3FF)
+
+
+# ---- MCCFR tree block (csrc/ctd_mccfr.cuh) ----
+KNOW_BYTES = 400
+HK_DTYPE = np.dtype([("pid", np.int8), ("conf", np.uint8), ("flags", np.uint8), ("n", np.uint8), ("off", np.uint16),
+                     ("pad", np.uint16)])
+KNOW_DTYPE = np.dtype([("viewer", np.uint8), ("conf_mask", np.uint8), ("n_hk", np.uint8), ("wiz_n", np.uint8),
+                       ("kr", np.uint16, 6), ("hk", HK_DTYPE, 8), ("wiz_cards", np.uint8, 48), ("pool", np.uint8, 256),
+                       ("pool_used", np.uint16), ("err", np.uint8), ("pad", np.uint8, 13)])
+assert KNOW_DTYPE.itemsize == KNOW_BYTES
+NODE_DTYPE = np.dtype([("parent", np.int32), ("depth", np.uint16), ("player", np.uint8), ("flags", np.uint8),
+                       ("n_children", np.uint32), ("child_cap", np.uint32), ("child_off", np.uint32),
+                       ("arr_off", np.uint32), ("visits", np.uint32), ("pad0", np.uint32), ("V", np.float64, 6),
+                       ("P", np.float64, 6), ("pred", np.float32, 6), ("pad1", np.uint8, 8), ("game", STATE_DTYPE),
+                       ("know", KNOW_DTYPE)])
+assert NODE_DTYPE.itemsize == 816
+CHILD_DTYPE = np.dtype([("desc", np.uint64), ("node", np.uint32), ("pad", np.uint32)])
+TREE_HDR_DTYPE = np.dtype([("n_nodes", np.uint32), ("max_nodes", np.uint32), ("child_used", np.uint32),
+                           ("child_cap", np.uint32), ("arr_used", np.uint32), ("arr_cap", np.uint32),
+                           ("status", np.uint32), ("iterations", np.uint32), ("rng_draws", np.uint32),
+                           ("viewer", np.uint8), ("training", np.uint8), ("has_model", np.uint8), ("pad0", np.uint8),
+                           ("gid", np.uint64), ("used_cards", np.uint8, 76), ("pad1", np.uint8, 4)])
+assert TREE_HDR_DTYPE.itemsize == 128
+NF_ROLE_PICK, NF_TERMINAL = 1, 2
+
+
+def tree_bytes(max_nodes, child_cap, arr_cap):
+    return 128 + max_nodes * 816 + child_cap * 16 + arr_cap * 8
+
+
+class TreeView:
+    """numpy views over one tree block as laid out by the kernels."""
+
+    def __init__(self, buf, max_nodes, child_cap, arr_cap):
+        buf = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf
+        self.hdr = buf[:128].view(TREE_HDR_DTYPE)[0]
+        o = 128
+        self.nodes = buf[o:o + max_nodes * 816].view(NODE_DTYPE)
+        o += max_nodes * 816
+        self.children = buf[o:o + child_cap * 16].view(CHILD_DTYPE)
+        o += child_cap * 16
+        self.arr = buf[o:o + arr_cap * 8].view(np.float64)
+
+    def arrays(self, i):
+        """(R, s, C) of node i shaped like the reference's numpy arrays."""
+        n = self.nodes[i]
+        k = int(n["n_children"])
+        a = self.arr[int(n["arr_off"]):]
+        if n["flags"] & NF_ROLE_PICK and k:
+            return a[0:60].reshape(6, 10), a[60:120].reshape(6, 10), a[120:180].reshape(6, 10)
+        cap = int(n["child_cap"])
+        return a[0:k], a[cap:cap + k], a[2 * cap:2 * cap + k]
+
+    def child_list(self, i):
+        n = self.nodes[i]
+        c = self.children[int(n["child_off"]):int(n["child_off"]) + int(n["n_children"])]
+        return [(int(x["desc"]), int(x["node"])) for x in c]
+
+
+MCCFR_RESULT_DTYPE = np.dtype([("status", np.uint32), ("n_nodes", np.uint32), ("iterations", np.uint32),
+                               ("rng_draws", np.uint32), ("n_children", np.uint32), ("role_pick", np.uint8),
+                               ("viewer", np.uint8), ("player", np.uint8), ("pad", np.uint8),
+                               ("node_value", np.float64, 6), ("winning_probabilities", np.float64, 6),
+                               ("options", np.uint64, 128), ("cumulative_regrets", np.float64, 180),
+                               ("strategy", np.float64, 180), ("cumulative_strategy", np.float64, 180)])

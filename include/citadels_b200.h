@@ -99,7 +99,7 @@ typedef uint64_t ctd_option;
 #define CTD_OPT_NEXT_WITCH(d) ((int)(((d) >> 37) & 1))
 #define CTD_OPT_CROWN(d) ((int)(((d) >> 38) & 1))
 #define CTD_OPT_COUNT(d) ((int)(((d) >> 39) & 0x3F))
-#define CTD_OPT_R(d) ((int)(((d) >> 45) & 0x3F))
+#define CTD_OPT_R(d) ((int)(((d) >> 45) & 0x3F)) /* Magician: subset size; Abbot: length of the gold/card list */
 #define CTD_OPT_J(d) ((int)(((d) >> 51) & 0x3FF))
 
 /* aggregate outcome statistics of a batch of playouts (what the reference's drivers tabulate from
@@ -162,6 +162,50 @@ ctd_status ctd_playout_slots(ctd_engine* e, uint32_t n, uint32_t max_steps, int8
  * elapsed_ms (may be NULL) receives the CUDA-event time of the playout kernel alone. */
 ctd_status ctd_playout_dev(ctd_engine* e, uint64_t n_games, uint64_t seed, uint64_t first_gid, int ruleset,
                            uint32_t max_steps, ctd_playout_stats* stats, float* elapsed_ms);
+/* ---- MCCFR (algorithms/deep_mccfr.py CFRNode) ----
+ * A CFR root is a game slot plus what its player to move has learnt (Agent.known_hands / known_roles,
+ * game/agent.py:25-26) -- 400 bytes, layout `CtdKnow` in csrc/ctd_engine.cuh -- plus Game.used_cards in deal
+ * order (76 bytes, game/game.py:424) and the id that keys the tree's Philox stream. */
+#define CTD_KNOW_BYTES 400
+#define CTD_MCCFR_MAX_RESULT 128
+typedef struct ctd_mccfr_result {
+  uint32_t status;       /* 0 ok; 1 terminal root (the reference's run_mccfr raises ValueError); 2 node pool
+                            exhausted; 4 engine error; 8 more than 2048 options at an expanded node */
+  uint32_t n_nodes;
+  uint32_t iterations;
+  uint32_t rng_draws;
+  uint32_t n_children;   /* len(root.children) */
+  uint8_t role_pick;     /* root.role_pick_node: the arrays below are [6][10] (player-major) */
+  uint8_t viewer;        /* original_player_id */
+  uint8_t player;        /* root.current_player_id */
+  uint8_t pad;
+  double node_value[6];             /* root.node_value */
+  double winning_probabilities[6];  /* root.winning_probabilities */
+  ctd_option options[CTD_MCCFR_MAX_RESULT];  /* option of child i */
+  double cumulative_regrets[180];
+  double strategy[180];
+  double cumulative_strategy[180];
+} ctd_mccfr_result;
+
+/* run_utils.create_a_close_to_finished_game / create_a_random_game (run_utils.py:29-72) for slots [0,n): play game
+ * (seed, first_gid+i) to terminal, step back u decisions (u uniform in [back_lo, back_hi]), move forward until the
+ * player to move has >= 2 options.  Fills the slot, its knowledge block, used_cards and tree id on the device.
+ * root_step (may be NULL) receives the index of the root in the game's step sequence. */
+ctd_status ctd_make_roots(ctd_engine* e, uint32_t n, uint64_t seed, uint64_t first_gid, int ruleset, uint32_t back_lo,
+                          uint32_t back_hi, uint32_t* root_step);
+/* roots supplied by the caller (the facade's CFRNode(game, ...)) and read back */
+ctd_status ctd_load_roots(ctd_engine* e, uint32_t n, const ctd_state* roots, const void* knows, const uint8_t* used_cards,
+                          const uint64_t* gids);
+ctd_status ctd_store_roots(ctd_engine* e, uint32_t n, ctd_state* roots, void* knows, uint8_t* used_cards, uint64_t* gids);
+/* size of one tree block for a given iteration budget */
+void ctd_mccfr_tree_shape(uint32_t iterations, int ruleset, uint32_t* max_nodes, uint32_t* child_cap, uint32_t* arr_cap,
+                          uint64_t* bytes);
+/* CFRNode(game, original_player_id=game.gamestate.player_id).cfr_train(iterations) (run_utils.py:83-85,
+ * algorithms/deep_mccfr.py:187-205) on roots [0,n_roots), one tree per warp.  results[n_roots] (may be NULL) gets
+ * the root's arrays; trees_out (may be NULL) gets every tree block (n_roots * bytes of ctd_mccfr_tree_shape). */
+ctd_status ctd_mccfr(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32_t iterations, int ruleset,
+                     ctd_mccfr_result* results, void* trees_out, float* elapsed_ms);
+
 /* number of kernels this engine has launched so far */
 uint64_t ctd_launch_count(const ctd_engine* e);
 

@@ -92,7 +92,7 @@ def D(kind, perp, target=None, a=None, b=None, rank=None, named=None, replica=0,
 
     [0:6) kind  [6:9) perpetrator  [9:12) target+1  [12:18) card A type+1  [18:24) card B type+1
     [24:28) rank+1  [28:32) named+1  [32:36) replica (4-bit two's complement)  [36] build
-    [37] next_witch  [38] crown  [39:45) count  [45:51) subset size r  [51:61) ordinal j
+    [37] next_witch  [38] crown  [39:45) count  [45:51) subset size r (Magician) / list length (Abbot)  [51:61) ordinal j
     """
     d = kind | (perp << 6)
     if target is not None:
@@ -218,6 +218,110 @@ class Game:
         for p in range(6):
             for t in PRESET_HANDS[p]:
                 self.hand[p].append(self._take_like(self.deck, t))
+
+    def clone(self):
+        """copy.deepcopy(game) as CFRNode uses it (algorithms/deep_mccfr.py:105,137,155); the chance source is shared."""
+        g = Game.__new__(Game)
+        d = self.__dict__
+        for k, v in d.items():
+            if k == "chance":
+                g.chance = v
+            elif k == "kh":
+                g.kh = [[h.copy() for h in lst] for lst in v]
+            elif isinstance(v, list):
+                g.__dict__[k] = [list(x) if isinstance(x, list) else x for x in v]
+            else:
+                g.__dict__[k] = v
+        return g
+
+    def knowledge(self):
+        """Canonical dump of every observer's beliefs (for comparison with the reference's Agent.known_*)."""
+        return [(tuple(self.kr_mask[o]), tuple(self.kr_conf[o]),
+                 tuple((h.pid, h.conf, h.wizard, tuple(h.cards)) for h in self.kh[o])) for o in range(6)]
+
+    # ------------------------------------------------------------------ determinisation (CFR only)
+    def sample_private_information(self, viewer, role_sample=True):
+        """Game.sample_private_information (game/game.py:215-242) with get_unknown_cards (:183-213), sample_deck
+        (:245-262), sample_cards_for_opponent (:264-280), sample_roles_for_opponent (:283-295),
+        remove_role_* (:298-310), refresh_roles_after_sampling_roles (:339-357).  Tier A/B: no warrants/blackmails."""
+        ch = self.chance
+        for hk in self.kh[viewer]:
+            hk.used = (hk.conf - 1) * 0.2 > ch.uniform()
+        # get_unknown_cards
+        unknown = list(self.used_cards)
+        for p in range(6):
+            for c in self.bld[p]:
+                self._remove_like(unknown, ctype(c))
+        for p in range(6):
+            for c in self.mus[p]:
+                self._remove_like(unknown, ctype(c))
+        for c in self.hand[viewer]:
+            self._remove_like(unknown, ctype(c))
+        for hk in self.kh[viewer]:
+            if hk.used:
+                for c in hk.cards:
+                    self._remove_like(unknown, ctype(c))
+        # sample_deck
+        n = len(self.deck)
+        lk = next((h for h in self.kh[viewer] if h.pid == -1 and h.used), None)
+        self.deck = []
+        if lk is not None:
+            k = min(len(lk.cards), n)
+            self.deck += lk.cards[:k]
+            n -= k
+        perm = ch.perm(len(unknown))
+        unknown = [unknown[i] for i in perm]
+        for _ in range(n):
+            if unknown:
+                self.deck.append(unknown.pop(0))
+        if any(self.blackmail) or any(self.warrant):
+            raise NotImplementedError("tier C: sample_warrants_and_blackmails")
+        # roles
+        kr = list(self.kr_mask[viewer])
+        conf = list(self.kr_conf[viewer])
+
+        def remove_role(bit):
+            for q in range(6):
+                if not conf[q]:
+                    kr[q] &= ~(1 << bit)
+        if role_sample:
+            r = self.role[self.player]
+            if r == ROLE_BEWITCHED:
+                remove_role(8)
+            elif r != ROLE_NONE:
+                for x in range(r + 1):
+                    remove_role(x)
+        for p in range(6):
+            if p != viewer:
+                # sample_cards_for_opponent
+                hk = next((h for h in self.kh[viewer] if h.pid == p and h.used), None)
+                n = len(self.hand[p])
+                self.hand[p] = []
+                if hk is not None:
+                    k = min(len(hk.cards), n)
+                    self.hand[p] += hk.cards[:k]
+                    n -= k
+                for _ in range(n):
+                    if unknown:
+                        self.hand[p].append(unknown.pop(0))
+            if role_sample and p != viewer and p != self.player and self.state != 0:
+                cand = [x for x in range(9) if kr[p] >> x & 1]
+                # dict order: possible_roles is built rank-ascending; {-1: "Bewitched"} is always a singleton
+                if cand:
+                    x = cand[ch.randbelow(len(cand))]
+                    self.role[p] = ROLE_BEWITCHED if x == 8 else x
+                    remove_role(x)
+                else:
+                    self.role[p] = next(x for x in range(8) if x not in self.used_roles)
+        if role_sample and self.state != 0:
+            self._refresh_used_roles()
+
+    @staticmethod
+    def _remove_like(cards, t):
+        for i, c in enumerate(cards):
+            if ctype(c) == t:
+                del cards[i]
+                return
 
     # ------------------------------------------------------------------ list helpers (game/deck.py)
     @staticmethod
@@ -525,7 +629,7 @@ class Game:
             elif nm == ABBOT:       # :422-430
                 n = sum(1 for c in self.hand[p] if csuit(c) == SUIT_RELIGION)
                 if n > 0:
-                    o = [D(K["abbot_gold_or_card"], p, count=k) for k in range(n + 1)]
+                    o = [D(K["abbot_gold_or_card"], p, count=k, r=n) for k in range(n + 1)]
             elif nm == MERCHANT:    # :438-440
                 o = [D(K["merchant"], p)]
             elif nm == ALCHEMIST:   # :442-444
@@ -931,9 +1035,9 @@ class Game:
         self.done |= DM_TAKE_GOLD
 
     def _a_abbot(self, d):
-        """game/option_functions.py:405-412 (n = religion cards in hand at enumeration time)."""
+        """game/option_functions.py:405-412 (the option carries its own gold/card list: r entries, count cards)."""
         p = d_perp(d)
-        n = sum(1 for c in self.hand[p] if csuit(c) == SUIT_RELIGION)
+        n = d_r(d)
         k = d_count(d)
         self.gold[p] += n - k
         for _ in range(k):
@@ -1054,6 +1158,47 @@ class Game:
         b[226] = self.warrant_building
         b[227] = self.ruleset
         return bytes(b)
+
+    def pack_know(self, viewer):
+        """The engine's 400-byte knowledge block of one observer (csrc/ctd_engine.cuh `CtdKnow`)."""
+        b = bytearray(400)
+        b[0] = viewer
+        b[1] = sum(1 << q for q in range(6) if self.kr_conf[viewer][q])
+        hks = self.kh[viewer]
+        b[2] = len(hks)
+        wiz = self.wiz_cards if self.wiz_target != 0xFF else []
+        b[3] = len(wiz)
+        for q in range(6):
+            struct.pack_into("<H", b, 4 + 2 * q, self.kr_mask[viewer][q])
+        pos = 0
+        for i, h in enumerate(hks):
+            struct.pack_into("<bBBBHH", b, 16 + 8 * i, h.pid, h.conf, (1 if h.wizard else 0) | (2 if h.used else 0),
+                             len(h.cards), pos, 0)
+            b[128 + pos:128 + pos + len(h.cards)] = bytes(h.cards)
+            pos += len(h.cards)
+        b[80:80 + len(wiz)] = bytes(wiz)
+        struct.pack_into("<H", b, 384, pos)
+        return bytes(b)
+
+    def unpack_know(self, blob, used_cards):
+        """Restore one observer's knowledge block (and Game.used_cards) into this game: enough to run CFR from it."""
+        blob = bytes(blob)
+        v = blob[0]
+        n_hk, wiz_n = blob[2], blob[3]
+        for q in range(6):
+            self.kr_mask[v][q] = struct.unpack_from("<H", blob, 4 + 2 * q)[0]
+            conf = bool(blob[1] >> q & 1)
+            for o in range(6):
+                self.kr_conf[o][q] = conf
+        self.kh[v] = []
+        for i in range(n_hk):
+            pid, conf, flags, n, off, _ = struct.unpack_from("<bBBBHH", blob, 16 + 8 * i)
+            h = HandKnowledge(pid, list(blob[128 + off:128 + off + n]), conf, bool(flags & 1))
+            h.used = bool(flags & 2)
+            self.kh[v].append(h)
+        self.wiz_cards = list(blob[80:80 + wiz_n])
+        self.used_cards = [int(c) for c in used_cards]
+        return v
 
     @classmethod
     def unpack(cls, rec, chance=None):

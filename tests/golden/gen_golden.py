@@ -110,6 +110,91 @@ def gen_outcomes(name, n, procs=8):
     print(name, "games", n, "mean steps", a[:, 7].mean(), "bytes", os.path.getsize(path))
 
 
+def _mccfr_one(args):
+    """One CFR root + tree from the REAL reference (CFRNode.cfr_train) under Philox streams 0 (game) / 1 (tree)."""
+    gid, ruleset, back_hi, iters = args
+    import zlib
+    from copy import deepcopy
+    from oracle.philox import PhiloxChance
+    from oracle import citadels_oracle as O
+    from tests.golden import ref_harness as H
+    H.patch_cfr_chance()
+    from algorithms.deep_mccfr import CFRNode
+    # root as ctd_make_roots defines it (see oracle/mccfr_oracle.make_root), played on the reference
+    ch = PhiloxChance(SEED, gid)
+    g = H.new_ref_game(ch, ruleset)
+    T = 0
+    while True:
+        H.set_chance(ch)
+        o = g.get_options_from_state()
+        T += 1
+        if o[ch.randbelow(len(o))].carry_out(g):
+            break
+    u = PhiloxChance(SEED, gid, stream=2).randbelow(back_hi + 1)
+    k = max(0, T - u)
+    ch = PhiloxChance(SEED, gid)
+    g = H.new_ref_game(ch, ruleset)
+    steps = limit = 0
+    while not g.terminal:
+        H.set_chance(ch)
+        o = g.get_options_from_state()
+        if steps >= k:
+            if len(o) >= 2 or limit >= 100:
+                break
+            limit += 1
+        o[ch.randbelow(len(o))].carry_out(g)
+        steps += 1
+    viewer = g.gamestate.player_id
+    root = H.ref_pack(g, ruleset)
+    know = H.ref_pack_know(g, viewer)
+    used = bytes(H.card_code(c) for c in g.used_cards.cards)
+    out = dict(gid=gid, root=root, know=know, used=used, root_step=steps, terminal=bool(g.terminal))
+    nodes = []
+    if not g.terminal:
+        H.set_chance(PhiloxChance(SEED, gid, stream=1))
+        rn = CFRNode(g, original_player_id=viewer)
+        rn.cfr_train(max_iterations=iters)
+
+        def walk(n):
+            nodes.append(n)
+            for _, c in n.children:
+                walk(c)
+        walk(rn)
+    out["nchild"] = [len(n.children) for n in nodes]
+    out["desc"] = [H.ref_descriptors([c[0]])[0] if c[0].name != "discard_and_draw" else 0 for n in nodes for c in n.children]
+    out["V"] = [list(n.node_value) for n in nodes]
+    out["P"] = [list(n.winning_probabilities) for n in nodes]
+    out["R"] = [float(x) for n in nodes for x in np.asarray(n.cumulative_regrets, dtype=float).ravel()]
+    out["S"] = [float(x) for n in nodes for x in np.asarray(n.strategy, dtype=float).ravel()]
+    out["C"] = [float(x) for n in nodes for x in np.asarray(n.cumulative_strategy, dtype=float).ravel()]
+    out["narr"] = [int(np.asarray(n.cumulative_regrets).size) for n in nodes]
+    out["game_crc"] = [zlib.crc32(H.ref_pack(n.game, ruleset)[:228]) for n in nodes]
+    out["know_crc"] = [zlib.crc32(H.ref_pack_know(n.game, viewer)) for n in nodes]
+    return out
+
+
+def gen_mccfr(name, ruleset, gids, back_hi, iters, procs=8):
+    with Pool(procs) as pool:
+        res = pool.map(_mccfr_one, [(g, ruleset, back_hi, iters) for g in gids], chunksize=1)
+    node_off = np.zeros(len(res) + 1, dtype=np.int64)
+    node_off[1:] = np.cumsum([len(r["nchild"]) for r in res])
+    cat = lambda k, dt: np.concatenate([np.asarray(r[k], dtype=dt).reshape(-1) for r in res])
+    out = dict(seed=np.uint64(SEED), ruleset=np.int32(ruleset), iterations=np.int32(iters), back_hi=np.int32(back_hi),
+               gids=np.asarray(gids, dtype=np.uint64),
+               roots=np.frombuffer(b"".join(r["root"] for r in res), dtype=np.uint8).reshape(-1, 256),
+               knows=np.frombuffer(b"".join(r["know"] for r in res), dtype=np.uint8).reshape(-1, 400),
+               used=np.frombuffer(b"".join(r["used"] for r in res), dtype=np.uint8).reshape(-1, 76),
+               root_step=np.asarray([r["root_step"] for r in res], dtype=np.int32),
+               terminal=np.asarray([r["terminal"] for r in res], dtype=bool),
+               node_off=node_off, nchild=cat("nchild", np.int32), desc=cat("desc", np.uint64),
+               V=cat("V", np.float64).reshape(-1, 6), P=cat("P", np.float64).reshape(-1, 6), narr=cat("narr", np.int32),
+               R=cat("R", np.float64), S=cat("S", np.float64), C=cat("C", np.float64),
+               game_crc=cat("game_crc", np.uint32), know_crc=cat("know_crc", np.uint32))
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **out)
+    print(name, "roots", len(gids), "nodes", int(node_off[-1]), "bytes", os.path.getsize(path))
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("all", "traces"):
@@ -117,5 +202,9 @@ if __name__ == "__main__":
         gen_traces("classic_traces.npz", 1, list(range(100000, 100300)))
         gen_traces("preset_full.npz", 0, list(range(2000, 2006)), full=True)
         gen_traces("classic_full.npz", 1, list(range(102000, 102004)), full=True)
+    if what in ("all", "mccfr"):
+        gen_mccfr("mccfr_preset.npz", 0, list(range(3000, 3024)), 20, 200)
+        gen_mccfr("mccfr_preset_deep_back.npz", 0, list(range(3100, 3112)), 300, 200)
+        gen_mccfr("mccfr_classic.npz", 1, list(range(103000, 103008)), 60, 200)
     if what in ("all", "outcomes"):
         gen_outcomes("ref_outcomes_preset.npz", 20000)

@@ -192,7 +192,7 @@ def ref_descriptors(options):
             else:
                 d = O.D(k, p, target=a["target"], a=a["card"].type_ID, build=0)
         elif n == "abbot_gold_or_card":
-            d = O.D(k, p, count=a["gold_or_card_combination"].count("card"))
+            d = O.D(k, p, count=a["gold_or_card_combination"].count("card"), r=len(a["gold_or_card_combination"]))
         elif n == "discard_and_draw":
             r = len(a["cards"])
             j = r_counts.get(r, 0)
@@ -205,3 +205,76 @@ def ref_descriptors(options):
             raise NotImplementedError(n)
         out.append(d)
     return out
+
+
+# --------------------------------------------------------------------------- CFR chance + knowledge dumps
+def patch_cfr_chance():
+    """Route the reference's CFR-path randomness through `_state['chance']` (mapping: oracle/mccfr_oracle.py)."""
+    import numpy as np
+    load_reference()
+
+    def np_choice(a, size=None, replace=True, p=None):
+        ch = _state["chance"]
+        n = len(a)
+        caller = sys._getframe(1).f_code.co_name
+        if caller == "action_choice":
+            cdf = np.cumsum(p)
+            cdf = cdf / cdf[-1]
+            i = min(int(np.searchsorted(cdf, ch.uniform(), side="right")), n - 1)
+        else:
+            assert caller in ("expand_role_pick", "expand_for_opponents"), caller
+            i = ch.randbelow(n)
+        return a[i]
+
+    def rnd_choice(seq):
+        if not len(seq):
+            raise IndexError("Cannot choose from an empty sequence")
+        return seq[_state["chance"].randbelow(len(seq))]
+
+    np.random.choice = np_choice
+    _random.random = lambda: _state["chance"].uniform()
+    _random.choice = rnd_choice
+
+
+def ref_knowledge(g):
+    out = []
+    for pl in g.players:
+        masks, confs = [], []
+        for rk in pl.known_roles:
+            m = 0
+            for rid in rk.possible_roles.keys():
+                m |= 1 << (8 if rid == -1 else rid)
+            masks.append(m)
+            confs.append(bool(rk.confirmed))
+        hks = tuple((hk.player_id, hk.confidence, bool(hk.wizard), tuple(card_code(c) for c in hk.hand.cards))
+                    for hk in pl.known_hands)
+        out.append((tuple(masks), tuple(confs), hks))
+    return out
+
+
+def ref_pack_know(g, viewer):
+    """Reference Agent.known_roles / known_hands of `viewer` -> the engine's 400-byte knowledge block."""
+    import struct
+    pl = g.players[viewer]
+    b = bytearray(400)
+    b[0] = viewer
+    b[1] = sum(1 << q for q in range(6) if pl.known_roles[q].confirmed)
+    b[2] = len(pl.known_hands)
+    wiz = [hk for p in g.players for hk in p.known_hands if hk.wizard]
+    wcards = [card_code(c) for c in wiz[0].hand.cards] if wiz else []
+    b[3] = len(wcards)
+    for q in range(6):
+        m = 0
+        for rid in pl.known_roles[q].possible_roles.keys():
+            m |= 1 << (8 if rid == -1 else rid)
+        struct.pack_into("<H", b, 4 + 2 * q, m)
+    pos = 0
+    for i, hk in enumerate(pl.known_hands):
+        cards = [card_code(c) for c in hk.hand.cards]
+        struct.pack_into("<bBBBHH", b, 16 + 8 * i, hk.player_id, hk.confidence,
+                         (1 if hk.wizard else 0) | (2 if hk.used else 0), len(cards), pos, 0)
+        b[128 + pos:128 + pos + len(cards)] = bytes(cards)
+        pos += len(cards)
+    b[80:80 + len(wcards)] = bytes(wcards)
+    struct.pack_into("<H", b, 384, pos)
+    return bytes(b)

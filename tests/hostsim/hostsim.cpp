@@ -2,6 +2,7 @@
 // replayed against the golden traces without a GPU.  It is not part of the product and the package never
 // loads it (the product path fails loudly when the CUDA library is missing).
 #include "../../citadels_self_play_b200/csrc/ctd_engine.cuh"
+#include "../../citadels_self_play_b200/csrc/ctd_mccfr.cuh"
 #include <string.h>
 
 static CtdWork g_w;
@@ -65,4 +66,30 @@ int hs_playout(uint64_t seed, uint64_t gid, int ruleset, uint32_t max_steps, int
   return w.winner;
 }
 int hs_sizeof_work() { return (int)sizeof(CtdWork); }
+
+// pure MCCFR on one root, tree built in `tree_buf` (ctd_tree_bytes(max_nodes, child_cap, arr_cap) bytes)
+int hs_mccfr(const ctd_state* root, const CtdKnow* know, const uint8_t* used_cards, uint64_t seed, uint64_t gid,
+             uint32_t iters, uint32_t max_nodes, uint32_t child_cap, uint32_t arr_cap, uint8_t* tree_buf) {
+  static CtdKnow kn;
+  static uint64_t opts[CTD_MCCFR_OPT_CAP];
+  static uint8_t scratch[256];
+  CtdWork& w = g_w;
+  memset(&w, 0, sizeof(w));
+  CtdTree T;
+  T.hdr = (CtdTreeHdr*)tree_buf;
+  T.nodes = (CtdNode*)(tree_buf + sizeof(CtdTreeHdr));
+  T.children = (CtdChild*)((uint8_t*)T.nodes + (size_t)max_nodes * sizeof(CtdNode));
+  T.arr = (double*)((uint8_t*)T.children + (size_t)child_cap * sizeof(CtdChild));
+  T.w = &w; T.kn = &kn; T.opts = opts; T.scratch = scratch;
+  memset(tree_buf, 0, ctd_tree_bytes(max_nodes, child_cap, arr_cap));
+  memcpy(T.hdr->used_cards, used_cards, 76);
+  ctd_unpack(root, w);
+  ctd_chance_init(w, seed, gid, 0);
+  w.stream = 1;
+  kn = *know;
+  ctd_tree_init(T, max_nodes, child_cap, arr_cap, know->viewer, gid, false, false);
+  ctd_cfr_train(T, iters);
+  return (int)T.hdr->status;
+}
+int hs_sizeof_node() { return (int)sizeof(CtdNode); }
 }

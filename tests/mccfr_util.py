@@ -1,0 +1,68 @@
+"""Shared helpers for the MCCFR parity tests: the golden tree fixtures (real reference) and tree comparison."""
+import os
+import zlib
+import numpy as np
+
+from tests.golden_util import GOLDEN
+
+
+class MccfrGolden:
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN, name))
+        self.z = z
+        self.seed = int(z["seed"])
+        self.ruleset = int(z["ruleset"])
+        self.iterations = int(z["iterations"])
+        self.back_hi = int(z["back_hi"])
+        self.gids = z["gids"]
+        self.n = len(self.gids)
+        self.child_off = np.concatenate([[0], np.cumsum(z["nchild"])])
+        self.arr_off = np.concatenate([[0], np.cumsum(z["narr"])])
+
+    def nodes(self, r):
+        """Yield per-node dicts of root r in the reference's DFS pre-order."""
+        z = self.z
+        for i in range(int(z["node_off"][r]), int(z["node_off"][r + 1])):
+            a0, a1 = int(self.arr_off[i]), int(self.arr_off[i + 1])
+            yield dict(nchild=int(z["nchild"][i]), desc=z["desc"][int(self.child_off[i]):int(self.child_off[i + 1])],
+                       V=z["V"][i], P=z["P"][i], R=z["R"][a0:a1], S=z["S"][a0:a1], C=z["C"][a0:a1],
+                       game_crc=int(z["game_crc"][i]), know_crc=int(z["know_crc"][i]))
+
+
+def oracle_preorder(node):
+    """Oracle tree -> the same per-node dicts."""
+    for n in node.walk():
+        yield dict(nchild=len(n.children), desc=np.asarray([c[0] for c in n.children], dtype=np.uint64), V=n.V, P=n.P,
+                   R=np.asarray(n.R, dtype=float).ravel(), S=np.asarray(n.s, dtype=float).ravel(),
+                   C=np.asarray(n.C, dtype=float).ravel(), game_crc=zlib.crc32(n.game.pack()[:228]),
+                   know_crc=zlib.crc32(n.game.pack_know(n.orig)))
+
+
+def tree_preorder(tv):
+    """Engine tree block (layout.TreeView) -> the same per-node dicts."""
+    stack = [0]
+    while stack:
+        i = stack.pop()
+        n = tv.nodes[i]
+        kids = tv.child_list(i)
+        R, S, C = tv.arrays(i)
+        yield dict(nchild=len(kids), desc=np.asarray([k[0] for k in kids], dtype=np.uint64), V=n["V"], P=n["P"],
+                   R=np.asarray(R).ravel(), S=np.asarray(S).ravel(), C=np.asarray(C).ravel(),
+                   game_crc=zlib.crc32(n["game"].tobytes()[:228]), know_crc=zlib.crc32(n["know"].tobytes()))
+        stack.extend(k[1] for k in reversed(kids))
+
+
+def assert_same_tree(a, b, what, rtol=1e-9, atol=1e-12):
+    """Integers exact; regrets / strategies / values to rtol (north_star: 1e-5 relative; we hold 1e-9)."""
+    a, b = list(a), list(b)
+    assert len(a) == len(b), (what, "node count", len(a), len(b))
+    for i, (x, y) in enumerate(zip(a, b)):
+        assert x["nchild"] == y["nchild"], (what, i, "children")
+        m = (np.asarray(x["desc"]) != 0) & (np.asarray(y["desc"]) != 0)   # 0 = descriptor not recorded in the fixture
+        assert np.array_equal(np.asarray(x["desc"])[m], np.asarray(y["desc"])[m]), (what, i, "options")
+        assert x["game_crc"] == y["game_crc"], (what, i, "game record")
+        assert x["know_crc"] == y["know_crc"], (what, i, "knowledge block")
+        for k in ("V", "P", "R", "S", "C"):
+            u, v = np.asarray(x[k], dtype=float), np.asarray(y[k], dtype=float)
+            assert u.shape == v.shape, (what, i, k, u.shape, v.shape)
+            assert np.allclose(u, v, rtol=rtol, atol=atol, equal_nan=True), (what, i, k, u, v)

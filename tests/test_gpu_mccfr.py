@@ -1,0 +1,73 @@
+"""GPU parity tests for the MCCFR path (ctd_make_roots / ctd_mccfr through the C ABI)."""
+import numpy as np
+import pytest
+
+from tests.mccfr_util import MccfrGolden, oracle_preorder, tree_preorder, assert_same_tree
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from citadels_self_play_b200 import Engine
+    e = Engine(capacity=512)
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("name", ["mccfr_preset.npz", "mccfr_preset_deep_back.npz", "mccfr_classic.npz"])
+def test_trees_match_reference(engine, name):
+    """SURVEY 8(d) parity gate 3: every node of trees grown by the real reference's CFRNode.cfr_train(200) --
+    options, regrets, strategies, values (1e-9 relative; the gate asks 1e-5), game record and knowledge block."""
+    G = MccfrGolden(name)
+    z = G.z
+    engine.load_roots(z["roots"], z["knows"], z["used"], G.gids)
+    out = engine.mccfr(G.n, iterations=G.iterations, seed=G.seed, ruleset=G.ruleset, trees=True)
+    for r in range(G.n):
+        res = out["results"][r]
+        if z["terminal"][r]:
+            assert res["status"] == 1
+            continue
+        assert res["status"] == 0, (name, r, int(res["status"]))
+        assert_same_tree(G.nodes(r), tree_preorder(out["trees"][r]), (name, r))
+        root = next(G.nodes(r))
+        k = root["nchild"]
+        assert res["n_children"] == k
+        n = len(root["R"])
+        assert np.allclose(res["cumulative_regrets"][:n], root["R"], rtol=1e-9, atol=1e-12)
+        assert np.allclose(res["cumulative_strategy"][:n], root["C"], rtol=1e-9, atol=1e-12)
+        assert np.allclose(res["node_value"], root["V"], rtol=1e-9, atol=1e-12)
+
+
+def test_make_roots_matches_oracle(engine):
+    """Device root construction (two-pass replay with knowledge of all six observers) vs the oracle."""
+    from oracle import mccfr_oracle as M
+    seed, gid0, n = 777, 50_000, 48
+    for ruleset, lo, hi in ((0, 0, 20), (0, 1, 100), (1, 0, 60)):
+        steps = engine.make_roots(n, seed=seed, first_gid=gid0, ruleset=ruleset, back_lo=lo, back_hi=hi)
+        roots, knows, used, gids = engine.store_roots(n)
+        for i in range(0, n, 3):
+            g, st = M.make_root(seed, gid0 + i, ruleset, lo, hi)
+            assert st == int(steps[i]) and int(gids[i]) == gid0 + i
+            assert roots[i, :228].tobytes() == g.pack()[:228]
+            assert roots[i, 228] == 0
+            if not g.terminal:
+                assert knows[i].tobytes() == g.pack_know(g.player)
+            assert used[i].tobytes() == bytes(g.used_cards)
+
+
+def test_mccfr_fresh_roots_vs_oracle(engine):
+    from oracle import mccfr_oracle as M
+    seed, gid0, n, iters = 4242, 90_000, 12, 200
+    engine.make_roots(n, seed=seed, first_gid=gid0, ruleset=0, back_lo=0, back_hi=20)
+    roots, knows, used, gids = engine.store_roots(n)
+    out = engine.mccfr(n, iterations=iters, seed=seed, trees=True)
+    for i in range(n):
+        res = out["results"][i]
+        if roots[i, 217] & 2:
+            assert res["status"] == 1
+            continue
+        node = M.run_from_root(roots[i], knows[i], used[i], seed, int(gids[i]), iters)
+        assert res["status"] == 0
+        assert_same_tree(oracle_preorder(node), tree_preorder(out["trees"][i]), ("fresh", i))
+        assert int(res["rng_draws"]) == node.game.chance.i
