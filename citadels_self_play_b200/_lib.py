@@ -43,6 +43,11 @@ SIGNATURES = {
     "ctd_store_roots": (_i, [c_void, _u32, c_void, c_void, c_void, c_void]),
     "ctd_mccfr_tree_shape": (None, [_u32, _i, ctypes.POINTER(_u32), ctypes.POINTER(_u32), ctypes.POINTER(_u32),
                                     ctypes.POINTER(_u64)]),
+    "ctd_set_value_model": (_i, [c_void] + [c_void] * 8),
+    "ctd_value_eval": (_i, [c_void, _u32, c_void, ctypes.c_float, c_void]),
+    "ctd_encode": (_i, [c_void, _u32, c_void]),
+    "ctd_mccfr_pred": (_i, [c_void, _u32, _u64, _u32, _u32, _i, ctypes.c_float, c_void, c_void,
+                            ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_u32)]),
     "ctd_mccfr": (_i, [c_void, _u32, _u64, _u32, _i, c_void, c_void, ctypes.POINTER(ctypes.c_float)]),
 }
 

@@ -355,6 +355,180 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_mccfr(CtdMccfrArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------ deep MCCFR
+struct CtdPredArgs {
+  CtdMccfrArgs m;
+  uint32_t max_depth;
+  int first;          // 1: build the trees' roots in this launch
+  float* feat;        // [n_roots][CTD_FEATURES_PAD]
+  float* pred;        // [n_roots][8]
+  uint8_t* pending;   // [n_roots]
+  uint32_t* n_pending;
+};
+
+// one wave of CFRNode.cfr_pred for every tree: walk until a leaf value is needed (or the budget is spent)
+__global__ void __launch_bounds__(CTD_BLOCK) ctd_k_mccfr_pred(CtdPredArgs p) {
+  __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
+  __shared__ CtdKnow knows[CTD_WARPS_PER_BLOCK];
+  __shared__ uint8_t scratch[CTD_WARPS_PER_BLOCK][256];
+  const CtdMccfrArgs& a = p.m;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint64_t* opts = a.opts_scratch + ((size_t)blockIdx.x * CTD_WARPS_PER_BLOCK + wib) * CTD_MCCFR_OPT_CAP;
+  for (;;) {
+    unsigned long long t = 0;
+    if (lane == 0) t = atomicAdd(a.counter, 1ull);
+    t = __shfl_sync(CTD_FULL, t, 0);
+    if (t >= a.n_roots) break;
+    if (lane == 0) {
+      CtdTree T = ctd_tree_at(a.trees + t * a.tree_stride, a.max_nodes, a.child_cap);
+      T.w = &works[wib]; T.kn = &knows[wib]; T.opts = opts; T.scratch = scratch[wib];
+      CtdWork& w = *T.w;
+      if (p.first) {
+        for (int i = 0; i < 76; ++i) T.hdr->used_cards[i] = a.used_cards[t * 76 + i];
+        ctd_unpack(&a.roots[t], w);
+        ctd_chance_init(w, a.seed, a.gids[t], 0);
+        w.stream = 1;
+        w.err = 0;
+        *T.kn = a.knows[t];
+        ctd_tree_init(T, a.max_nodes, a.child_cap, a.arr_cap, T.kn->viewer, a.gids[t], false, true);
+      } else {
+        ctd_chance_init(w, a.seed, a.gids[t], 0);
+        w.stream = 1;
+        w.err = 0;
+      }
+      const bool was_waiting = T.hdr->phase == 2;
+      bool wait = false;
+      if (T.hdr->phase != 3) wait = ctd_cfr_pred_advance(T, a.iterations, p.max_depth, p.feat + t * CTD_FEATURES_PAD, p.pred + t * 8);
+      (void)was_waiting;
+      p.pending[t] = wait ? 1 : 0;
+      if (wait) atomicAdd(p.n_pending, 1u);
+      if (!wait && a.results) ctd_write_result(T, &a.results[t]);
+    }
+    __syncwarp();
+  }
+}
+
+// ValueOnlyNN.forward in eval mode (algorithms/models.py:17-23) with BatchNorm folded into fc1/fc2, then
+// model_reward_weights * square_and_normalize (train_utils.py:143-145).  fp32 CUDA-core version: a tile of 16 rows per
+// CTA, activations k-major in shared memory, weights transposed [in][out] so every warp reads a contiguous row.
+struct CtdValueModel {
+  const float *w1t, *b1, *w2t, *b2, *w3t, *b3, *w4t, *b4;  // w1t [448][512], w2t [512][256], w3t [256][128], w4t [128][6]
+};
+#define CTD_MLP_ROWS 16
+__global__ void __launch_bounds__(256) ctd_k_value_mlp(const float* __restrict__ feat, const uint8_t* __restrict__ pending,
+                                                       uint32_t n, CtdValueModel m, float* __restrict__ pred, float weight) {
+  extern __shared__ float sm[];
+  float* X = sm;                                   // [448][16]
+  float* H1 = X + CTD_FEATURES_PAD * CTD_MLP_ROWS;  // [512][16]
+  float* H2 = H1 + 512 * CTD_MLP_ROWS;             // [256][16]
+  float* H3 = H2 + 256 * CTD_MLP_ROWS;             // [128][16]
+  __shared__ int any;
+  const int t = threadIdx.x;
+  const uint32_t row0 = blockIdx.x * CTD_MLP_ROWS;
+  if (t == 0) any = 0;
+  __syncthreads();
+  if (t < CTD_MLP_ROWS && row0 + t < n && (pending == nullptr || pending[row0 + t])) any = 1;
+  __syncthreads();
+  if (!any) return;
+  for (int i = t; i < CTD_FEATURES_PAD * CTD_MLP_ROWS; i += 256) {
+    int r = i / CTD_FEATURES_PAD, k = i % CTD_FEATURES_PAD;
+    X[k * CTD_MLP_ROWS + r] = row0 + r < n ? feat[(size_t)(row0 + r) * CTD_FEATURES_PAD + k] : 0.f;
+  }
+  __syncthreads();
+  {  // fc1 + bn1 + relu: 512 outputs, thread t -> outputs t and t+256
+    float a0[CTD_MLP_ROWS], a1[CTD_MLP_ROWS];
+#pragma unroll
+    for (int r = 0; r < CTD_MLP_ROWS; ++r) { a0[r] = 0.f; a1[r] = 0.f; }
+    for (int k = 0; k < CTD_FEATURES_PAD; ++k) {
+      const float w0 = m.w1t[k * 512 + t], w1 = m.w1t[k * 512 + t + 256];
+      const float4* x4 = reinterpret_cast<const float4*>(X + k * CTD_MLP_ROWS);
+#pragma unroll
+      for (int q = 0; q < CTD_MLP_ROWS / 4; ++q) {
+        float4 x = x4[q];
+        a0[4 * q + 0] = fmaf(w0, x.x, a0[4 * q + 0]); a0[4 * q + 1] = fmaf(w0, x.y, a0[4 * q + 1]);
+        a0[4 * q + 2] = fmaf(w0, x.z, a0[4 * q + 2]); a0[4 * q + 3] = fmaf(w0, x.w, a0[4 * q + 3]);
+        a1[4 * q + 0] = fmaf(w1, x.x, a1[4 * q + 0]); a1[4 * q + 1] = fmaf(w1, x.y, a1[4 * q + 1]);
+        a1[4 * q + 2] = fmaf(w1, x.z, a1[4 * q + 2]); a1[4 * q + 3] = fmaf(w1, x.w, a1[4 * q + 3]);
+      }
+    }
+    const float c0 = m.b1[t], c1 = m.b1[t + 256];
+#pragma unroll
+    for (int r = 0; r < CTD_MLP_ROWS; ++r) {
+      H1[t * CTD_MLP_ROWS + r] = fmaxf(a0[r] + c0, 0.f);
+      H1[(t + 256) * CTD_MLP_ROWS + r] = fmaxf(a1[r] + c1, 0.f);
+    }
+  }
+  __syncthreads();
+  {  // fc2 + bn2 + relu: 256 outputs
+    float a0[CTD_MLP_ROWS];
+#pragma unroll
+    for (int r = 0; r < CTD_MLP_ROWS; ++r) a0[r] = 0.f;
+    for (int k = 0; k < 512; ++k) {
+      const float w0 = m.w2t[k * 256 + t];
+      const float4* x4 = reinterpret_cast<const float4*>(H1 + k * CTD_MLP_ROWS);
+#pragma unroll
+      for (int q = 0; q < CTD_MLP_ROWS / 4; ++q) {
+        float4 x = x4[q];
+        a0[4 * q + 0] = fmaf(w0, x.x, a0[4 * q + 0]); a0[4 * q + 1] = fmaf(w0, x.y, a0[4 * q + 1]);
+        a0[4 * q + 2] = fmaf(w0, x.z, a0[4 * q + 2]); a0[4 * q + 3] = fmaf(w0, x.w, a0[4 * q + 3]);
+      }
+    }
+    const float c0 = m.b2[t];
+#pragma unroll
+    for (int r = 0; r < CTD_MLP_ROWS; ++r) H2[t * CTD_MLP_ROWS + r] = fmaxf(a0[r] + c0, 0.f);
+  }
+  __syncthreads();
+  {  // fc3 + relu: 128 outputs x 16 rows, thread t -> output t & 127, rows (t >> 7) * 8 ..
+    const int o = t & 127, rb = (t >> 7) * 8;
+    float a0[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) a0[r] = 0.f;
+    for (int k = 0; k < 256; ++k) {
+      const float w0 = m.w3t[k * 128 + o];
+      const float4* x4 = reinterpret_cast<const float4*>(H2 + k * CTD_MLP_ROWS + rb);
+      float4 x = x4[0], y = x4[1];
+      a0[0] = fmaf(w0, x.x, a0[0]); a0[1] = fmaf(w0, x.y, a0[1]); a0[2] = fmaf(w0, x.z, a0[2]); a0[3] = fmaf(w0, x.w, a0[3]);
+      a0[4] = fmaf(w0, y.x, a0[4]); a0[5] = fmaf(w0, y.y, a0[5]); a0[6] = fmaf(w0, y.z, a0[6]); a0[7] = fmaf(w0, y.w, a0[7]);
+    }
+    const float c0 = m.b3[o];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) H3[o * CTD_MLP_ROWS + rb + r] = fmaxf(a0[r] + c0, 0.f);
+  }
+  __syncthreads();
+  // fc4: 6 outputs x 16 rows; then weight * y^2 / sum(y^2)
+  float* Y = X;  // reuse: [16][8]
+  if (t < 6 * CTD_MLP_ROWS) {
+    const int o = t % 6, r = t / 6;
+    float acc = 0.f;
+    for (int k = 0; k < 128; ++k) acc = fmaf(m.w4t[k * 6 + o], H3[k * CTD_MLP_ROWS + r], acc);
+    Y[r * 8 + o] = acc + m.b4[o];
+  }
+  __syncthreads();
+  if (t < CTD_MLP_ROWS && row0 + t < n && (pending == nullptr || pending[row0 + t])) {
+    float s = 0.f, y[6];
+#pragma unroll
+    for (int o = 0; o < 6; ++o) { y[o] = Y[t * 8 + o]; y[o] *= y[o]; s += y[o]; }
+#pragma unroll
+    for (int o = 0; o < 6; ++o) pred[(size_t)(row0 + t) * 8 + o] = weight * (y[o] / s);
+  }
+}
+#define CTD_MLP_SMEM ((CTD_FEATURES_PAD + 512 + 256 + 128) * CTD_MLP_ROWS * sizeof(float))
+
+// features of the games in slots [0,n) as their player to move sees them (role-pick states: player 5)
+__global__ void __launch_bounds__(CTD_BLOCK) ctd_k_encode(const ctd_state* slots, const CtdKnow* knows, uint32_t n, float* feat) {
+  __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
+  __shared__ ctd_state stage[CTD_WARPS_PER_BLOCK];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t slot = blockIdx.x * CTD_WARPS_PER_BLOCK + wib;
+  if (slot >= n) return;
+  ctd_record_load(&slots[slot], &stage[wib], lane);
+  if (lane == 0) {
+    CtdWork& w = works[wib];
+    ctd_unpack(&stage[wib], w);
+    ctd_encode_game(w, knows[slot], w.state == 0 ? 5 : w.player, feat + (size_t)slot * CTD_FEATURES_PAD);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side / C ABI
 struct ctd_engine {
   int device;
@@ -384,6 +558,13 @@ struct ctd_engine {
   size_t trees_bytes;
   uint64_t* d_opts_scratch;
   size_t opts_scratch_bytes;
+  // value model (BN folded, transposed) and deep-MCCFR batch buffers
+  float* d_model;
+  CtdValueModel model;
+  float* d_feat;
+  float* d_pred;
+  uint8_t* d_pending;
+  uint32_t* d_n_pending;
   char err[256];
 };
 
@@ -448,6 +629,11 @@ void ctd_destroy(ctd_engine* e) {
   if (e->d_root_step) cudaFree(e->d_root_step);
   if (e->d_trees) cudaFree(e->d_trees);
   if (e->d_opts_scratch) cudaFree(e->d_opts_scratch);
+  if (e->d_model) cudaFree(e->d_model);
+  if (e->d_feat) cudaFree(e->d_feat);
+  if (e->d_pred) cudaFree(e->d_pred);
+  if (e->d_pending) cudaFree(e->d_pending);
+  if (e->d_n_pending) cudaFree(e->d_n_pending);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
@@ -719,7 +905,7 @@ void ctd_mccfr_tree_shape(uint32_t iterations, int ruleset, uint32_t* max_nodes,
                           uint64_t* bytes) {
   // measured on the reference: <= 3.6 nodes per iteration (preset); a classic Magician expands ~1600 options at once
   uint32_t extra = ruleset == CTD_RULESET_CLASSIC ? 8192 : 0;
-  uint32_t mn = 6 * iterations + 256 + extra, cc = mn + 10 * (iterations + 2), ac = 3 * cc + 180 * 64;
+  uint32_t mn = 8 * iterations + 512 + extra, cc = mn + 10 * (iterations + 2), ac = 3 * cc + 180 * 64;
   if (max_nodes) *max_nodes = mn;
   if (child_cap) *child_cap = cc;
   if (arr_cap) *arr_cap = ac;
@@ -772,6 +958,138 @@ ctd_status ctd_mccfr(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32_t it
   if (trees_out) CTD_CUDA(e, cudaMemcpyAsync(trees_out, e->d_trees, need, cudaMemcpyDeviceToHost, e->stream));
   CTD_CUDA(e, cudaStreamSynchronize(e->stream));
   if (elapsed_ms) CTD_CUDA(e, cudaEventElapsedTime(elapsed_ms, e->ev0, e->ev1));
+  return CTD_OK;
+}
+
+static ctd_status ctd_pred_buffers(ctd_engine* e) {
+  if (e->d_feat) return CTD_OK;
+  CTD_CUDA(e, cudaMalloc((void**)&e->d_feat, (size_t)e->capacity * CTD_FEATURES_PAD * sizeof(float)));
+  CTD_CUDA(e, cudaMalloc((void**)&e->d_pred, (size_t)e->capacity * 8 * sizeof(float)));
+  CTD_CUDA(e, cudaMalloc((void**)&e->d_pending, (size_t)e->capacity));
+  CTD_CUDA(e, cudaMalloc((void**)&e->d_n_pending, sizeof(uint32_t)));
+  CTD_CUDA(e, cudaMemsetAsync(e->d_feat, 0, (size_t)e->capacity * CTD_FEATURES_PAD * sizeof(float), e->stream));
+  CTD_CUDA(e, cudaMemsetAsync(e->d_pred, 0, (size_t)e->capacity * 8 * sizeof(float), e->stream));
+  CTD_CUDA(e, cudaMemsetAsync(e->d_pending, 0, (size_t)e->capacity, e->stream));
+  CTD_CUDA(e, cudaFuncSetAttribute(ctd_k_value_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CTD_MLP_SMEM));
+  return CTD_OK;
+}
+
+ctd_status ctd_set_value_model(ctd_engine* e, const float* w1t, const float* b1, const float* w2t, const float* b2,
+                               const float* w3t, const float* b3, const float* w4t, const float* b4) {
+  if (!e || !w1t || !b1 || !w2t || !b2 || !w3t || !b3 || !w4t || !b4) return CTD_EARG;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  const size_t n1 = (size_t)CTD_FEATURES_PAD * 512, n2 = 512 * 256, n3 = 256 * 128, n4 = 128 * 6 + 2;
+  const size_t total = n1 + 512 + n2 + 256 + n3 + 128 + n4 + 8;
+  if (!e->d_model) CTD_CUDA(e, cudaMalloc((void**)&e->d_model, total * sizeof(float)));
+  float* p = e->d_model;
+  CtdValueModel& m = e->model;
+  const float* src[8] = {w1t, b1, w2t, b2, w3t, b3, w4t, b4};
+  const size_t cnt[8] = {n1, 512, n2, 256, n3, 128, 128 * 6, 6};
+  const size_t pad[8] = {n1, 512, n2, 256, n3, 128, n4, 8};
+  const float** dst[8] = {&m.w1t, &m.b1, &m.w2t, &m.b2, &m.w3t, &m.b3, &m.w4t, &m.b4};
+  for (int i = 0; i < 8; ++i) {
+    CTD_CUDA(e, cudaMemcpyAsync(p, src[i], cnt[i] * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    *dst[i] = p;
+    p += pad[i];
+  }
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  return CTD_OK;
+}
+
+ctd_status ctd_value_eval(ctd_engine* e, uint32_t n, const float* features, float weight, float* out6) {
+  if (!e || !features || !out6 || n > e->capacity || !e->d_model) return CTD_EARG;
+  if (n == 0) return CTD_OK;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  ctd_status s = ctd_pred_buffers(e);
+  if (s != CTD_OK) return s;
+  CTD_CUDA(e, cudaMemcpyAsync(e->d_feat, features, (size_t)n * CTD_FEATURES_PAD * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  ctd_k_value_mlp<<<(n + CTD_MLP_ROWS - 1) / CTD_MLP_ROWS, 256, CTD_MLP_SMEM, e->stream>>>(e->d_feat, nullptr, n, e->model, e->d_pred, weight);
+  e->launches++;
+  CTD_CUDA(e, cudaGetLastError());
+  CTD_CUDA(e, cudaMemcpy2DAsync(out6, 6 * sizeof(float), e->d_pred, 8 * sizeof(float), 6 * sizeof(float), n, cudaMemcpyDeviceToHost, e->stream));
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  return CTD_OK;
+}
+
+ctd_status ctd_encode(ctd_engine* e, uint32_t n, float* features) {
+  if (!e || !features || n > e->capacity || !e->d_knows) return CTD_EARG;
+  if (n == 0) return CTD_OK;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  ctd_status s = ctd_pred_buffers(e);
+  if (s != CTD_OK) return s;
+  ctd_k_encode<<<ctd_blocks(n), CTD_BLOCK, 0, e->stream>>>(e->d_slots, e->d_knows, n, e->d_feat);
+  e->launches++;
+  CTD_CUDA(e, cudaGetLastError());
+  CTD_CUDA(e, cudaMemcpyAsync(features, e->d_feat, (size_t)n * CTD_FEATURES_PAD * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  return CTD_OK;
+}
+
+ctd_status ctd_mccfr_pred(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32_t iterations, uint32_t max_depth, int ruleset,
+                          float reward_weight, ctd_mccfr_result* results, void* trees_out, float* elapsed_ms, uint32_t* waves_out) {
+  if (!e || n_roots > e->capacity || !e->d_knows || !e->d_model) return CTD_EARG;
+  if (n_roots == 0) return CTD_OK;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  ctd_status s = ctd_pred_buffers(e);
+  if (s != CTD_OK) return s;
+  uint32_t mn, cc, ac;
+  uint64_t stride;
+  ctd_mccfr_tree_shape(iterations, ruleset, &mn, &cc, &ac, &stride);
+  size_t need = (size_t)stride * n_roots;
+  if (need > e->trees_bytes) {
+    if (e->d_trees) CTD_CUDA(e, cudaFree(e->d_trees));
+    e->d_trees = nullptr; e->trees_bytes = 0;
+    CTD_CUDA(e, cudaMalloc((void**)&e->d_trees, need));
+    e->trees_bytes = need;
+  }
+  size_t rb = (size_t)n_roots * sizeof(ctd_mccfr_result);
+  s = ctd_scratch(e, rb);
+  if (s != CTD_OK) return s;
+  CtdPredArgs p;
+  memset(&p, 0, sizeof(p));
+  CtdMccfrArgs& a = p.m;
+  a.n_roots = n_roots; a.roots = e->d_slots; a.knows = e->d_knows; a.used_cards = e->d_used_cards; a.gids = e->d_gids;
+  a.seed = seed; a.iterations = iterations; a.max_nodes = mn; a.child_cap = cc; a.arr_cap = ac;
+  a.trees = e->d_trees; a.tree_stride = stride; a.results = (ctd_mccfr_result*)e->d_scratch; a.counter = e->d_counter;
+  p.max_depth = max_depth; p.feat = e->d_feat; p.pred = e->d_pred; p.pending = e->d_pending; p.n_pending = e->d_n_pending;
+  int per_sm = 0;
+  CTD_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctd_k_mccfr_pred, CTD_BLOCK, 0));
+  if (per_sm < 1) per_sm = 1;
+  uint64_t want = (uint64_t)e->sm_count * per_sm, needb = (n_roots + CTD_WARPS_PER_BLOCK - 1) / CTD_WARPS_PER_BLOCK;
+  int grid = (int)(needb < want ? needb : want);
+  size_t ob = (size_t)grid * CTD_WARPS_PER_BLOCK * CTD_MCCFR_OPT_CAP * sizeof(uint64_t);
+  if (ob > e->opts_scratch_bytes) {
+    if (e->d_opts_scratch) CTD_CUDA(e, cudaFree(e->d_opts_scratch));
+    e->d_opts_scratch = nullptr; e->opts_scratch_bytes = 0;
+    CTD_CUDA(e, cudaMalloc((void**)&e->d_opts_scratch, ob));
+    e->opts_scratch_bytes = ob;
+  }
+  a.opts_scratch = e->d_opts_scratch;
+  CTD_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+  uint32_t waves = 0;
+  for (;; ++waves) {
+    if (waves > iterations + 2) { snprintf(e->err, sizeof(e->err), "ctd_mccfr_pred: wave limit"); return CTD_ECAP; }
+    CTD_CUDA(e, cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream));
+    CTD_CUDA(e, cudaMemsetAsync(e->d_n_pending, 0, sizeof(uint32_t), e->stream));
+    p.first = waves == 0;
+    ctd_k_mccfr_pred<<<grid, CTD_BLOCK, 0, e->stream>>>(p);
+    e->launches++;
+    CTD_CUDA(e, cudaGetLastError());
+    uint32_t np = 0;
+    CTD_CUDA(e, cudaMemcpyAsync(&np, e->d_n_pending, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+    if (np == 0) break;
+    ctd_k_value_mlp<<<(n_roots + CTD_MLP_ROWS - 1) / CTD_MLP_ROWS, 256, CTD_MLP_SMEM, e->stream>>>(e->d_feat, e->d_pending, n_roots,
+                                                                                             e->model, e->d_pred, reward_weight);
+    e->launches++;
+    CTD_CUDA(e, cudaGetLastError());
+  }
+  CTD_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+  if (results) CTD_CUDA(e, cudaMemcpyAsync(results, e->d_scratch, rb, cudaMemcpyDeviceToHost, e->stream));
+  if (trees_out) CTD_CUDA(e, cudaMemcpyAsync(trees_out, e->d_trees, need, cudaMemcpyDeviceToHost, e->stream));
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (elapsed_ms) CTD_CUDA(e, cudaEventElapsedTime(elapsed_ms, e->ev0, e->ev1));
+  if (waves_out) *waves_out = waves + 1;
   return CTD_OK;
 }
 

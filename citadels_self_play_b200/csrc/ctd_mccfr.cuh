@@ -59,10 +59,10 @@ struct CtdTreeHdr {
   uint8_t viewer;        // original_player_id
   uint8_t training;
   uint8_t has_model;
-  uint8_t pad0;
+  uint8_t phase;         // deep MCCFR walk: 0 not started, 1 walking, 2 waiting for a leaf value, 3 finished
   uint64_t gid;
   uint8_t used_cards[76];  // Game.used_cards in deal order (game/game.py:424); constant over the tree
-  uint8_t pad1[4];
+  uint32_t cur_node;     // node the walk stands on (deep MCCFR is resumed across kernel launches)
 };
 static_assert(sizeof(CtdTreeHdr) == 128, "CtdTreeHdr layout");
 
@@ -450,9 +450,10 @@ CTD_HD CTD_NI inline void ctd_tree_init(CtdTree& T, uint32_t max_nodes, uint32_t
   CtdTreeHdr& h = *T.hdr;
   h.n_nodes = 0; h.max_nodes = max_nodes; h.child_used = 0; h.child_cap = child_cap; h.arr_used = 0; h.arr_cap = arr_cap;
   h.status = 0; h.iterations = 0; h.rng_draws = 0; h.viewer = (uint8_t)viewer; h.training = training; h.has_model = has_model;
-  h.pad0 = 0; h.gid = gid;
+  h.phase = 0; h.cur_node = 0; h.gid = gid;
   ctd_new_node(T, -1, 0);  // the root constructor runs skip_false_choice on the caller's game (:19-20)
   if (T.nodes[0].flags & CTD_NF_TERMINAL) h.status |= CTD_TREE_TERMINAL_ROOT;
+  h.rng_draws = T.w->draws;
 }
 
 // run `iters` iterations of the pure-MCCFR loop; returns the node the walk is standing on
@@ -477,4 +478,102 @@ CTD_HD CTD_NI inline void ctd_cfr_train(CtdTree& T, uint32_t iters) {
   }
   ctd_update_strategy(T, 0);
   h.rng_draws = T.w->draws;
+}
+
+// ------------------------------------------------------------------------------------------ deep MCCFR
+#define CTD_FEATURES 418
+#define CTD_FEATURES_PAD 448 /* row stride of the feature matrix: multiple of 64 for the tensor-core tiles */
+
+// Game.encode_game (game/game.py:34-128, game/deck.py:75-89) from the working record.  The confirmed-role block
+// reads known_roles[current player][seat].confirmed, which is the same for every observer (conf_mask).
+// Role-pick nodes are encoded with player_id forced to 5 (algorithms/deep_mccfr.py:120-123).
+CTD_HD CTD_NI inline void ctd_encode_game(const CtdWork& w, const CtdKnow& k, int player, float* f) {
+  CTD_LOOP for (int i = 0; i < CTD_FEATURES_PAD; ++i) f[i] = 0.f;
+  CTD_LOOP for (int r = 0; r < 8; ++r) f[r * 3 + w.variant[r]] = 1.f;
+  CTD_LOOP for (int p = 0; p < 6; ++p) {
+    if (w.role[p] < 8 && ((k.conf_mask >> p) & 1)) f[24 + p * 8 + w.role[p]] = 1.f;
+    f[72 + p] = (float)ctd_count_points(w, p);
+    f[78 + p] = (float)w.gold[p];
+    f[84 + p] = (float)w.n_hand[p];
+    CTD_LOOP for (int i = 0; i < w.n_bld[p]; ++i) {
+      int c = w.bld[p][i];
+      f[90 + p * 40 + ctd_ctype(c)] += 1.f;
+      f[330 + p * 5 + ctd_csuit(c)] += 1.f;
+    }
+  }
+  f[360 + player] = 1.f;
+  f[366 + w.state] = 1.f;
+  f[377] = (w.gflags & 1) ? 1.f : 0.f;
+  CTD_LOOP for (int r = 0; r < 8; ++r) {
+    int rp = w.rprops[r];
+    if (rp & CTD_RP_DEAD) f[378 + r * 5 + 0] = 1.f;
+    if (rp & CTD_RP_WARRANT) f[378 + r * 5 + 1] = 1.f;
+    if (rp & CTD_RP_POSSESSED) f[378 + r * 5 + 2] = 1.f;
+    if (rp & CTD_RP_ROBBED) f[378 + r * 5 + 3] = 1.f;
+    if (rp & CTD_RP_BLACKMAIL) f[378 + r * 5 + 4] = 1.f;
+  }
+}
+
+// CFRNode.cfr_pred (algorithms/deep_mccfr.py:207-229) as a resumable walk.  When the walk reaches a node deeper than
+// max_depth whose value is not cached it writes the node's features to `feat` (CTD_FEATURES_PAD floats), expands
+// the node, and returns true: the caller evaluates the value model on the batch of all waiting trees and calls again
+// with `pred` = model_reward_weights * square_and_normalize(model(features)) (:126,:147,:178; train_utils.py:143-145).
+// Returns false when all iterations are done.
+CTD_HD CTD_NI inline bool ctd_cfr_pred_advance(CtdTree& T, uint32_t iters, uint32_t max_depth, float* feat, const float* pred) {
+  CtdTreeHdr& h = *T.hdr;
+  if (h.phase == 3 || (h.status & CTD_TREE_TERMINAL_ROOT)) { h.phase = 3; return false; }
+  T.w->draws = h.rng_draws;
+  T.w->buf_blk = 0xFFFFFFFFu;
+  if (h.phase == 0) {
+    ctd_expand(T, 0);
+    h.cur_node = 0;
+    h.phase = 1;
+  } else if (h.phase == 2) {
+    CtdNode& n = T.nodes[h.cur_node];
+    double reward[6];
+    CTD_LOOP for (int i = 0; i < 6; ++i) { n.pred[i] = pred[i]; reward[i] = (double)pred[i]; }
+    n.flags |= CTD_NF_HAS_PRED;
+    ctd_backpropagate(T, (int)h.cur_node, reward);
+    ctd_update_strategy(T, (int)h.cur_node);
+    h.cur_node = 0;
+    h.phase = 1;
+    ++h.iterations;
+  }
+  int node = (int)h.cur_node;
+  while (h.iterations < iters && !(h.status & ~CTD_TREE_TERMINAL_ROOT)) {
+    ctd_update_strategy(T, node);
+    node = ctd_action_choice(T, node);
+    CtdNode& n = T.nodes[node];
+    if (n.depth > max_depth && !(n.flags & CTD_NF_TERMINAL)) {
+      if (!(n.flags & CTD_NF_HAS_PRED)) {
+        ctd_node_load(T, n);
+        ctd_encode_game(*T.w, *T.kn, n.game.state == 0 ? 5 : n.game.player, feat);
+        ctd_expand(T, node);
+        h.cur_node = (uint32_t)node;
+        h.phase = 2;
+        h.rng_draws = T.w->draws;
+        return true;
+      }
+      ctd_expand(T, node);
+      double reward[6];
+      CTD_LOOP for (int i = 0; i < 6; ++i) reward[i] = (double)n.pred[i];
+      ctd_backpropagate(T, node, reward);
+      ctd_update_strategy(T, node);
+      node = 0;
+    } else if (n.flags & CTD_NF_TERMINAL) {
+      double reward[6] = {0, 0, 0, 0, 0, 0};
+      reward[n.game.winner] = 1.0;
+      ctd_backpropagate(T, node, reward);
+      ctd_update_strategy(T, node);
+      node = 0;
+    } else {
+      ctd_expand(T, node);
+    }
+    ++h.iterations;
+  }
+  ctd_update_strategy(T, 0);
+  h.cur_node = 0;
+  h.phase = 3;
+  h.rng_draws = T.w->draws;
+  return false;
 }

@@ -165,6 +165,41 @@ class Engine:
             views = [TreeView(buf[i], mn, cc, ac) for i in range(n_roots)]
         return dict(results=res, trees=views, kernel_ms=ms.value)
 
+    def set_value_model(self, model):
+        """model: a ValueOnlyNN(418, 512) in eval mode (reference state_dict layout)."""
+        from .value_model import fold
+        arrs = fold(model)
+        self._model_arrays = arrs   # keep alive during the copy
+        self._check(self._lib.ctd_set_value_model(self._h, *[a.ctypes.data for a in arrs]), "ctd_set_value_model")
+
+    def value_eval(self, features, weight=5.0):
+        f = np.zeros((len(features), 448), dtype=np.float32)
+        f[:, :np.shape(features)[1]] = features
+        out = np.empty((len(f), 6), dtype=np.float32)
+        self._check(self._lib.ctd_value_eval(self._h, len(f), f.ctypes.data, weight, out.ctypes.data), "ctd_value_eval")
+        return out
+
+    def encode(self, n):
+        f = np.empty((n, 448), dtype=np.float32)
+        self._check(self._lib.ctd_encode(self._h, n, f.ctypes.data), "ctd_encode")
+        return f[:, :418]
+
+    def mccfr_pred(self, n_roots, iterations=200, max_depth=10, seed=DEFAULT_SEED, ruleset=RULESET_PRESET, weight=5.0,
+                   trees=False):
+        """CFRNode(..., model).cfr_pred(iterations, max_depth) on the loaded/made roots."""
+        res = np.zeros(n_roots, dtype=MCCFR_RESULT_DTYPE)
+        ms, waves = ctypes.c_float(), ctypes.c_uint32()
+        views = buf = None
+        if trees:
+            mn, cc, ac, by = self.tree_shape(iterations, ruleset)
+            buf = np.zeros((n_roots, by), dtype=np.uint8)
+        self._check(self._lib.ctd_mccfr_pred(self._h, n_roots, seed, iterations, max_depth, ruleset, weight, res.ctypes.data,
+                                             buf.ctypes.data if trees else None, ctypes.byref(ms), ctypes.byref(waves)),
+                    "ctd_mccfr_pred")
+        if trees:
+            views = [TreeView(buf[i], mn, cc, ac) for i in range(n_roots)]
+        return dict(results=res, trees=views, kernel_ms=ms.value, waves=waves.value)
+
     def sync(self):
         self._check(self._lib.ctd_sync(self._h), "ctd_sync")
 

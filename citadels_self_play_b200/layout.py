@@ -69,8 +69,8 @@ CHILD_DTYPE = np.dtype([("desc", np.uint64), ("node", np.uint32), ("pad", np.uin
 TREE_HDR_DTYPE = np.dtype([("n_nodes", np.uint32), ("max_nodes", np.uint32), ("child_used", np.uint32),
                            ("child_cap", np.uint32), ("arr_used", np.uint32), ("arr_cap", np.uint32),
                            ("status", np.uint32), ("iterations", np.uint32), ("rng_draws", np.uint32),
-                           ("viewer", np.uint8), ("training", np.uint8), ("has_model", np.uint8), ("pad0", np.uint8),
-                           ("gid", np.uint64), ("used_cards", np.uint8, 76), ("pad1", np.uint8, 4)])
+                           ("viewer", np.uint8), ("training", np.uint8), ("has_model", np.uint8), ("phase", np.uint8),
+                           ("gid", np.uint64), ("used_cards", np.uint8, 76), ("cur_node", np.uint32)])
 assert TREE_HDR_DTYPE.itemsize == 128
 NF_ROLE_PICK, NF_TERMINAL = 1, 2
 

@@ -206,6 +206,25 @@ void ctd_mccfr_tree_shape(uint32_t iterations, int ruleset, uint32_t* max_nodes,
 ctd_status ctd_mccfr(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32_t iterations, int ruleset,
                      ctd_mccfr_result* results, void* trees_out, float* elapsed_ms);
 
+/* ---- value model at depth-limited leaves (algorithms/models.py ValueOnlyNN(418, 512), eval mode) ----
+ * Weights are passed BatchNorm-folded and transposed to [in][out]: w1t [448][512] (rows 418..447 zero), b1 [512],
+ * w2t [512][256], b2 [256], w3t [256][128], b3 [128], w4t [128][6], b4 [6]  (value_model.fold() builds them from
+ * the reference's state_dict, run_utils.py:11-18). */
+ctd_status ctd_set_value_model(ctd_engine* e, const float* w1t, const float* b1, const float* w2t, const float* b2,
+                               const float* w3t, const float* b3, const float* w4t, const float* b4);
+/* CFRNode.model_inference (algorithms/deep_mccfr.py:364-374) for n feature rows of 448 floats (418 used):
+ * out6[i] = weight * square_and_normalize(model(features[i]))  (train_utils.py:143-145) */
+ctd_status ctd_value_eval(ctd_engine* e, uint32_t n, const float* features, float weight, float* out6);
+/* Game.encode_game (game/game.py:91-128) of roots [0,n) as their player to move sees them: n rows of 448 floats */
+ctd_status ctd_encode(ctd_engine* e, uint32_t n, float* features);
+/* CFRNode(game, ..., model=model, training=False).cfr_pred(iterations, max_depth) (run_utils.py:78-81,
+ * algorithms/deep_mccfr.py:207-229) on roots [0,n_roots).  Trees advance in waves: every tree walks until it needs a
+ * leaf value, the value model runs once on the batch of all waiting leaves, the trees resume.
+ * reward_weight is model_reward_weights (5 in the reference). */
+ctd_status ctd_mccfr_pred(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32_t iterations, uint32_t max_depth, int ruleset,
+                          float reward_weight, ctd_mccfr_result* results, void* trees_out, float* elapsed_ms,
+                          uint32_t* waves_out);
+
 /* number of kernels this engine has launched so far */
 uint64_t ctd_launch_count(const ctd_engine* e);
 

@@ -1159,6 +1159,32 @@ class Game:
         b[227] = self.ruleset
         return bytes(b)
 
+    def encode_game(self, player_override=None):
+        """Game.encode_game (game/game.py:34-128): the 418-feature value-model input, as a list of numbers."""
+        f = [0.0] * 418
+        for r in range(8):
+            f[r * 3 + self.variant[r]] = 1.0
+        cur = self.player if player_override is None else player_override
+        for p in range(6):
+            if self.role[p] < 8 and self.kr_conf[cur][p]:
+                f[24 + p * 8 + self.role[p]] = 1.0
+        for p in range(6):
+            f[72 + p] = float(self.count_points(p))
+            f[78 + p] = float(self.gold[p])
+            f[84 + p] = float(len(self.hand[p]))
+            for c in self.bld[p]:
+                f[90 + p * 40 + ctype(c)] += 1.0
+                f[330 + p * 5 + csuit(c)] += 1.0
+        f[360 + cur] = 1.0
+        f[366 + self.state] = 1.0
+        f[377] = 1.0 if self.ending else 0.0
+        for r in range(8):
+            vals = (self.dead[r], self.warrant[r], self.possessed[r], self.robbed[r], self.blackmail[r])
+            for i, v in enumerate(vals):
+                if v:
+                    f[378 + r * 5 + i] = 1.0
+        return f
+
     def pack_know(self, viewer):
         """The engine's 400-byte knowledge block of one observer (csrc/ctd_engine.cuh `CtdKnow`)."""
         b = bytearray(400)

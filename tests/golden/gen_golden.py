@@ -112,7 +112,8 @@ def gen_outcomes(name, n, procs=8):
 
 def _mccfr_one(args):
     """One CFR root + tree from the REAL reference (CFRNode.cfr_train) under Philox streams 0 (game) / 1 (tree)."""
-    gid, ruleset, back_hi, iters = args
+    gid, ruleset, back_hi, iters = args[:4]
+    deep = args[4] if len(args) > 4 else 0
     import zlib
     from copy import deepcopy
     from oracle.philox import PhiloxChance
@@ -152,8 +153,22 @@ def _mccfr_one(args):
     nodes = []
     if not g.terminal:
         H.set_chance(PhiloxChance(SEED, gid, stream=1))
-        rn = CFRNode(g, original_player_id=viewer)
-        rn.cfr_train(max_iterations=iters)
+        if deep:
+            # config 4: ValueOnlyNN(418, 512), default torch init under manual_seed(0), eval(), depth limit `deep`
+            import torch
+            from algorithms.models import ValueOnlyNN
+            from citadels_self_play_b200.value_model import ValueOnlyNN as Mirror
+            torch.set_num_threads(1)
+            torch.manual_seed(0)
+            model = ValueOnlyNN(418, 512).eval()
+            torch.manual_seed(0)
+            mirror = Mirror(418, 512).eval()
+            assert all(torch.equal(a, b) for a, b in zip(model.state_dict().values(), mirror.state_dict().values()))
+            rn = CFRNode(g, original_player_id=viewer, model=model, training=False, device="cpu")
+            rn.cfr_pred(max_iterations=iters, max_depth=deep)
+        else:
+            rn = CFRNode(g, original_player_id=viewer)
+            rn.cfr_train(max_iterations=iters)
 
         def walk(n):
             nodes.append(n)
@@ -173,14 +188,14 @@ def _mccfr_one(args):
     return out
 
 
-def gen_mccfr(name, ruleset, gids, back_hi, iters, procs=8):
+def gen_mccfr(name, ruleset, gids, back_hi, iters, procs=8, deep=0):
     with Pool(procs) as pool:
-        res = pool.map(_mccfr_one, [(g, ruleset, back_hi, iters) for g in gids], chunksize=1)
+        res = pool.map(_mccfr_one, [(g, ruleset, back_hi, iters, deep) for g in gids], chunksize=1)
     node_off = np.zeros(len(res) + 1, dtype=np.int64)
     node_off[1:] = np.cumsum([len(r["nchild"]) for r in res])
     cat = lambda k, dt: np.concatenate([np.asarray(r[k], dtype=dt).reshape(-1) for r in res])
     out = dict(seed=np.uint64(SEED), ruleset=np.int32(ruleset), iterations=np.int32(iters), back_hi=np.int32(back_hi),
-               gids=np.asarray(gids, dtype=np.uint64),
+               gids=np.asarray(gids, dtype=np.uint64), max_depth=np.int32(deep),
                roots=np.frombuffer(b"".join(r["root"] for r in res), dtype=np.uint8).reshape(-1, 256),
                knows=np.frombuffer(b"".join(r["know"] for r in res), dtype=np.uint8).reshape(-1, 400),
                used=np.frombuffer(b"".join(r["used"] for r in res), dtype=np.uint8).reshape(-1, 76),
@@ -206,5 +221,7 @@ if __name__ == "__main__":
         gen_mccfr("mccfr_preset.npz", 0, list(range(3000, 3024)), 20, 200)
         gen_mccfr("mccfr_preset_deep_back.npz", 0, list(range(3100, 3112)), 300, 200)
         gen_mccfr("mccfr_classic.npz", 1, list(range(103000, 103008)), 60, 200)
+    if what in ("all", "deep"):
+        gen_mccfr("deep_mccfr_preset.npz", 0, list(range(4000, 4016)), 120, 200, deep=10)
     if what in ("all", "outcomes"):
         gen_outcomes("ref_outcomes_preset.npz", 20000)

@@ -92,4 +92,32 @@ int hs_mccfr(const ctd_state* root, const CtdKnow* know, const uint8_t* used_car
   return (int)T.hdr->status;
 }
 int hs_sizeof_node() { return (int)sizeof(CtdNode); }
+
+// deep MCCFR on one root; `eval(features[448], pred[6])` stands in for the batched value kernel
+typedef void (*hs_eval_fn)(const float*, float*);
+int hs_mccfr_pred(const ctd_state* root, const CtdKnow* know, const uint8_t* used_cards, uint64_t seed, uint64_t gid,
+                  uint32_t iters, uint32_t max_depth, uint32_t max_nodes, uint32_t child_cap, uint32_t arr_cap,
+                  uint8_t* tree_buf, hs_eval_fn eval) {
+  static CtdKnow kn;
+  static uint64_t opts[CTD_MCCFR_OPT_CAP];
+  static uint8_t scratch[256];
+  static float feat[CTD_FEATURES_PAD], pred[8];
+  CtdWork& w = g_w;
+  memset(&w, 0, sizeof(w));
+  CtdTree T;
+  T.hdr = (CtdTreeHdr*)tree_buf;
+  T.nodes = (CtdNode*)(tree_buf + sizeof(CtdTreeHdr));
+  T.children = (CtdChild*)((uint8_t*)T.nodes + (size_t)max_nodes * sizeof(CtdNode));
+  T.arr = (double*)((uint8_t*)T.children + (size_t)child_cap * sizeof(CtdChild));
+  T.w = &w; T.kn = &kn; T.opts = opts; T.scratch = scratch;
+  memset(tree_buf, 0, ctd_tree_bytes(max_nodes, child_cap, arr_cap));
+  memcpy(T.hdr->used_cards, used_cards, 76);
+  ctd_unpack(root, w);
+  ctd_chance_init(w, seed, gid, 0);
+  w.stream = 1;
+  kn = *know;
+  ctd_tree_init(T, max_nodes, child_cap, arr_cap, know->viewer, gid, false, true);
+  while (ctd_cfr_pred_advance(T, iters, max_depth, feat, pred)) eval(feat, pred);
+  return (int)T.hdr->status;
+}
 }

@@ -71,3 +71,62 @@ def test_mccfr_fresh_roots_vs_oracle(engine):
         assert res["status"] == 0
         assert_same_tree(oracle_preorder(node), tree_preorder(out["trees"][i]), ("fresh", i))
         assert int(res["rng_draws"]) == node.game.chance.i
+
+
+# ---------------------------------------------------------------- deep MCCFR (config 4)
+def _model(seed=0, randomize_bn=False):
+    import torch
+    from citadels_self_play_b200.value_model import ValueOnlyNN
+    torch.manual_seed(seed)
+    m = ValueOnlyNN(418, 512).eval()
+    if randomize_bn:   # exercise the BatchNorm folding with non-trivial statistics
+        with torch.no_grad():
+            for bn in (m.bn1, m.bn2):
+                bn.running_mean.normal_(0, 0.3)
+                bn.running_var.uniform_(0.5, 2.0)
+                bn.weight.uniform_(0.5, 1.5)
+                bn.bias.normal_(0, 0.2)
+    return m
+
+
+@pytest.mark.parametrize("randomize_bn", [False, True])
+def test_value_kernel_vs_torch_fp32(engine, randomize_bn):
+    """ValueOnlyNN forward + square_and_normalize * 5: CUDA kernel vs torch fp32 on the CPU (the reference's own
+    arithmetic), tolerance 1e-5 relative (north_star)."""
+    from citadels_self_play_b200.value_model import reference_value
+    m = _model(3, randomize_bn)
+    engine.set_value_model(m)
+    engine.make_roots(256, seed=11, first_gid=0, back_lo=0, back_hi=300)
+    feats = engine.encode(256)
+    got = engine.value_eval(feats)
+    want = reference_value(m, feats)
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-6), np.abs(got - want).max()
+    assert np.allclose(got.sum(1), 5.0, rtol=1e-5)
+
+
+def test_encoder_vs_oracle(engine):
+    """Game.encode_game on device vs the oracle, exact (small integers in fp32)."""
+    from oracle import citadels_oracle as O
+    n = 96
+    engine.make_roots(n, seed=21, first_gid=500, back_lo=0, back_hi=400)
+    roots, knows, used, gids = engine.store_roots(n)
+    feats = engine.encode(n)
+    for i in range(n):
+        g = O.Game.unpack(roots[i].tobytes())
+        g.unpack_know(knows[i], used[i])
+        want = np.asarray(g.encode_game(5 if g.state == 0 else None), dtype=np.float32)
+        assert np.array_equal(feats[i], want), i
+
+
+def test_deep_trees_match_reference(engine):
+    """Config 4: deep MCCFR, 200 iterations, value model at depth 10 -- every node against the real reference's
+    cfr_pred trees.  Values to 1e-5 relative (gate 3); structure, game records and knowledge exact."""
+    G = MccfrGolden("deep_mccfr_preset.npz")
+    z = G.z
+    engine.set_value_model(_model(0))
+    engine.load_roots(z["roots"], z["knows"], z["used"], G.gids)
+    out = engine.mccfr_pred(G.n, iterations=G.iterations, max_depth=int(z["max_depth"]), seed=G.seed, trees=True)
+    assert out["waves"] >= 2
+    for r in range(G.n):
+        assert out["results"][r]["status"] == 0
+        assert_same_tree(G.nodes(r), tree_preorder(out["trees"][r]), ("deep", r), rtol=1e-5, atol=2e-6)

@@ -59,3 +59,79 @@ def test_kernel_mccfr_host_build_matches_reference(hostsim, name):
             continue
         assert st == 0
         assert_same_tree(G.nodes(r), tree_preorder(TreeView(buf, mn, cc, ac)), (name, r))
+
+
+# ---------------------------------------------------------------- deep MCCFR (config 4)
+def _model():
+    import torch
+    from citadels_self_play_b200.value_model import ValueOnlyNN
+    torch.set_num_threads(1)
+    torch.manual_seed(0)
+    return ValueOnlyNN(418, 512).eval()
+
+
+def test_oracle_deep_trees_match_reference():
+    """cfr_pred(200, max_depth=10) with ValueOnlyNN(418,512) under torch.manual_seed(0): oracle vs the real reference."""
+    from citadels_self_play_b200.value_model import reference_value
+    from oracle import citadels_oracle as O
+    from oracle.philox import PhiloxChance
+    G = MccfrGolden("deep_mccfr_preset.npz")
+    z = G.z
+    model = _model()
+
+    def value(g):
+        return reference_value(model, np.asarray(g.encode_game(), dtype=np.float32)[None, :], weight=1.0)[0]
+    for r in range(0, G.n, 2):
+        g = O.Game.unpack(z["roots"][r].tobytes(), PhiloxChance(G.seed, int(G.gids[r]), stream=1))
+        g.unpack_know(z["knows"][r], z["used"][r])
+        n = M.Node(g, g.player, model=value)
+        n.cfr_pred(G.iterations, int(z["max_depth"]))
+        assert_same_tree(G.nodes(r), oracle_preorder(n), ("deep", r), rtol=1e-7, atol=1e-10)
+
+
+def test_kernel_deep_mccfr_host_build_matches_reference(hostsim):
+    from citadels_self_play_b200.layout import TreeView, tree_bytes
+    from citadels_self_play_b200.value_model import reference_value
+    G = MccfrGolden("deep_mccfr_preset.npz")
+    z = G.z
+    model = _model()
+    u64, u32, vp = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p
+    EVAL = ctypes.CFUNCTYPE(None, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float))
+    hostsim.hs_mccfr_pred.argtypes = [vp, vp, vp, u64, u64, u32, u32, u32, u32, u32, vp, EVAL]
+
+    def ev(fp, pp):
+        p = reference_value(model, np.ctypeslib.as_array(fp, shape=(448,))[None, :])[0]
+        for i in range(6):
+            pp[i] = float(p[i])
+    cb = EVAL(ev)
+    mn = 6 * G.iterations + 256
+    cc = mn + 10 * (G.iterations + 2)
+    ac = 3 * cc + 180 * 64
+    buf = np.zeros(tree_bytes(mn, cc, ac), np.uint8)
+    for r in range(G.n):
+        root, know, used = (np.ascontiguousarray(z[k][r]) for k in ("roots", "knows", "used"))
+        st = hostsim.hs_mccfr_pred(root.ctypes.data, know.ctypes.data, used.ctypes.data, G.seed, int(G.gids[r]),
+                                   G.iterations, int(z["max_depth"]), mn, cc, ac, buf.ctypes.data, cb)
+        assert st == 0
+        assert_same_tree(G.nodes(r), tree_preorder(TreeView(buf, mn, cc, ac)), ("deep-host", r), rtol=1e-7, atol=1e-10)
+
+
+def test_oracle_encode_game_layout():
+    """Feature offsets of SURVEY.md Appendix D on a hand-built state."""
+    from oracle import citadels_oracle as O
+    g = O.Game(None, deal=False)
+    g.role = [0, 1, 2, 3, 4, 5]
+    g.kr_conf = [[q in (1, 4) for q in range(6)] for _ in range(6)]
+    g.bld[2] = [13, 13, 40]
+    g.gold[3] = -2
+    g.hand[4] = [1, 2, 3]
+    g.state, g.player, g.ending = 5, 2, True
+    g.possessed[6] = True
+    f = g.encode_game()
+    assert len(f) == 418
+    assert [i for i in range(24) if f[i]] == [r * 3 + g.variant[r] for r in range(8)]
+    assert [i for i in range(24, 72) if f[i]] == [24 + 1 * 8 + 1, 24 + 4 * 8 + 4]
+    assert f[72 + 2] == 4 + 4 + 6 and f[78 + 3] == -2 and f[84 + 4] == 3
+    assert f[90 + 2 * 40 + 13] == 2 and f[90 + 2 * 40 + 25] == 1
+    assert f[330 + 2 * 5 + 3] == 2 and f[330 + 2 * 5 + 0] == 1      # the rewritten Magic School counts as trade
+    assert f[360 + 2] == 1 and f[366 + 5] == 1 and f[377] == 1 and f[378 + 6 * 5 + 2] == 1
