@@ -395,6 +395,7 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_mccfr_pred(CtdPredArgs p) {
         ctd_chance_init(w, a.seed, a.gids[t], 0);
         w.stream = 1;
         w.err = 0;
+        T.kn->err = 0;  // the working set is rebuilt from the tree on the first node load of this wave
       }
       const bool was_waiting = T.hdr->phase == 2;
       bool wait = false;

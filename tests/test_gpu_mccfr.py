@@ -120,7 +120,8 @@ def test_encoder_vs_oracle(engine):
 
 def test_deep_trees_match_reference(engine):
     """Config 4: deep MCCFR, 200 iterations, value model at depth 10 -- every node against the real reference's
-    cfr_pred trees.  Values to 1e-5 relative (gate 3); structure, game records and knowledge exact."""
+    cfr_pred trees.  Structure, options, game records and knowledge exact; regrets / strategies / values to 1e-5 of
+    each array's scale (gate 3), the slack being fp32 summation order in the value model (torch CPU GEMV vs the kernel)."""
     G = MccfrGolden("deep_mccfr_preset.npz")
     z = G.z
     engine.set_value_model(_model(0))
@@ -129,4 +130,4 @@ def test_deep_trees_match_reference(engine):
     assert out["waves"] >= 2
     for r in range(G.n):
         assert out["results"][r]["status"] == 0
-        assert_same_tree(G.nodes(r), tree_preorder(out["trees"][r]), ("deep", r), rtol=1e-5, atol=2e-6)
+        assert_same_tree(G.nodes(r), tree_preorder(out["trees"][r]), ("deep", r), norm_rtol=1e-5)
