@@ -3,4 +3,8 @@ option.carry_out surface.  The compute path is hand-written sm_100a CUDA reached
 include/citadels_b200.h; importing this package does not need a GPU, using it does."""
 from .engine import Engine, EngineError, RULESET_PRESET, RULESET_CLASSIC, DEFAULT_SEED  # noqa: F401
 
-__all__ = ["Engine", "EngineError", "RULESET_PRESET", "RULESET_CLASSIC", "DEFAULT_SEED"]
+from .facade import (Game, Agent, option, Card, CFRNode, create_game, create_a_close_to_finished_game,  # noqa: F401
+                     create_a_random_game, run_mccfr)
+
+__all__ = ["Engine", "EngineError", "RULESET_PRESET", "RULESET_CLASSIC", "DEFAULT_SEED", "Game", "Agent", "option", "Card",
+           "CFRNode", "create_game", "create_a_close_to_finished_game", "create_a_random_game", "run_mccfr"]

@@ -355,6 +355,62 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_mccfr(CtdMccfrArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------ single-game entry points
+// The facade's Game object owns its record and the knowledge of all six observers on the host; these kernels run
+// one warp on device copies of them (op 0: new game, 1: enumerate, 2: step).
+struct CtdOneArgs {
+  int op;
+  uint64_t seed, gid;
+  int ruleset;
+  ctd_state* state;
+  CtdKnow* know6;        // may be null
+  uint8_t* used_cards;   // op 0
+  ctd_option* opts;      // op 1
+  uint32_t cap;
+  uint32_t* count;
+  ctd_option chosen;     // op 2
+  int8_t* winner;
+};
+__global__ void __launch_bounds__(32) ctd_k_one(CtdOneArgs a) {
+  __shared__ CtdWork w;
+  __shared__ CtdKnow kn[6];
+  __shared__ ctd_state stage;
+  const int lane = threadIdx.x;
+  if (a.op != 0) ctd_record_load(a.state, &stage, lane);
+  if (a.know6 != nullptr && a.op != 0)
+    for (int i = lane; i < (int)(6 * sizeof(CtdKnow) / 4); i += 32) ((uint32_t*)kn)[i] = ((const uint32_t*)a.know6)[i];
+  __syncwarp();
+  if (lane == 0) {
+    CtdKnowSet ks{a.know6 ? kn : nullptr, a.know6 ? 6 : 0};
+    if (a.op == 0) {
+      ctd_chance_init(w, a.seed, a.gid, 0);
+      ctd_deal_preset(w, a.ruleset, a.used_cards);
+      for (int o = 0; o < 6; ++o) ctd_kn_init(kn[o], o);
+      ctd_setup_round(w, ks);
+      ctd_pack(w, &stage);
+    } else if (a.op == 1) {
+      ctd_unpack(&stage, w);
+      CtdEmit e{a.opts, a.cap, 0, 0xFFFFFFFFu, 0};
+      ctd_enumerate(w, e, a.know6 ? &kn[0] : nullptr);
+      *a.count = e.n;
+    } else {
+      ctd_unpack(&stage, w);
+      w.k0 = (uint32_t)a.seed; w.k1 = (uint32_t)(a.seed >> 32);
+      w.stream = 0; w.tape = nullptr; w.tape_len = 0;
+      bool won = ctd_apply(w, a.chosen, ks);
+      *a.winner = won ? w.winner : (int8_t)-1;
+      for (int o = 0; o < ks.n; ++o) w.err |= kn[o].err;
+      ctd_pack(w, &stage);
+    }
+  }
+  __syncwarp();
+  if (a.op != 1) {
+    ctd_record_store(a.state, &stage, lane);
+    if (a.know6 != nullptr)
+      for (int i = lane; i < (int)(6 * sizeof(CtdKnow) / 4); i += 32) ((uint32_t*)a.know6)[i] = ((const uint32_t*)kn)[i];
+  }
+}
+
 // ------------------------------------------------------------------------------------------ deep MCCFR
 struct CtdPredArgs {
   CtdMccfrArgs m;
@@ -566,6 +622,7 @@ struct ctd_engine {
   float* d_pred;
   uint8_t* d_pending;
   uint32_t* d_n_pending;
+  uint8_t* d_one;  // single-game staging: state | know6 | used_cards | count | winner | opts
   char err[256];
 };
 
@@ -635,6 +692,7 @@ void ctd_destroy(ctd_engine* e) {
   if (e->d_pred) cudaFree(e->d_pred);
   if (e->d_pending) cudaFree(e->d_pending);
   if (e->d_n_pending) cudaFree(e->d_n_pending);
+  if (e->d_one) cudaFree(e->d_one);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
@@ -959,6 +1017,88 @@ ctd_status ctd_mccfr(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32_t it
   if (trees_out) CTD_CUDA(e, cudaMemcpyAsync(trees_out, e->d_trees, need, cudaMemcpyDeviceToHost, e->stream));
   CTD_CUDA(e, cudaStreamSynchronize(e->stream));
   if (elapsed_ms) CTD_CUDA(e, cudaEventElapsedTime(elapsed_ms, e->ev0, e->ev1));
+  return CTD_OK;
+}
+
+#define CTD_ONE_OPTS 4096
+#define CTD_ONE_KNOW_OFF 256
+#define CTD_ONE_USED_OFF (256 + 2400)
+#define CTD_ONE_COUNT_OFF (256 + 2400 + 80)
+#define CTD_ONE_WINNER_OFF (CTD_ONE_COUNT_OFF + 4)
+#define CTD_ONE_OPTS_OFF (CTD_ONE_COUNT_OFF + 8)
+#define CTD_ONE_BYTES (CTD_ONE_OPTS_OFF + CTD_ONE_OPTS * 8)
+static ctd_status ctd_one_buffer(ctd_engine* e) {
+  if (e->d_one) return CTD_OK;
+  CTD_CUDA(e, cudaMalloc((void**)&e->d_one, CTD_ONE_BYTES));
+  return CTD_OK;
+}
+static CtdOneArgs ctd_one_args(ctd_engine* e, int op, bool know) {
+  CtdOneArgs a;
+  memset(&a, 0, sizeof(a));
+  a.op = op; a.seed = e->seed;
+  a.state = (ctd_state*)e->d_one;
+  a.know6 = know ? (CtdKnow*)(e->d_one + CTD_ONE_KNOW_OFF) : nullptr;
+  a.used_cards = e->d_one + CTD_ONE_USED_OFF;
+  a.count = (uint32_t*)(e->d_one + CTD_ONE_COUNT_OFF);
+  a.winner = (int8_t*)(e->d_one + CTD_ONE_WINNER_OFF);
+  a.opts = (ctd_option*)(e->d_one + CTD_ONE_OPTS_OFF);
+  a.cap = CTD_ONE_OPTS;
+  return a;
+}
+
+ctd_status ctd_game_new(ctd_engine* e, uint64_t seed, uint64_t gid, int ruleset, ctd_state* state, void* know6, uint8_t* used_cards) {
+  if (!e || !state || (ruleset != CTD_RULESET_PRESET && ruleset != CTD_RULESET_CLASSIC)) return CTD_EARG;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  ctd_status s = ctd_one_buffer(e);
+  if (s != CTD_OK) return s;
+  CtdOneArgs a = ctd_one_args(e, 0, true);
+  a.seed = seed; a.gid = gid; a.ruleset = ruleset;
+  ctd_k_one<<<1, 32, 0, e->stream>>>(a);
+  e->launches++;
+  CTD_CUDA(e, cudaGetLastError());
+  CTD_CUDA(e, cudaMemcpyAsync(state, e->d_one, sizeof(ctd_state), cudaMemcpyDeviceToHost, e->stream));
+  if (know6) CTD_CUDA(e, cudaMemcpyAsync(know6, e->d_one + CTD_ONE_KNOW_OFF, 2400, cudaMemcpyDeviceToHost, e->stream));
+  if (used_cards) CTD_CUDA(e, cudaMemcpyAsync(used_cards, e->d_one + CTD_ONE_USED_OFF, 76, cudaMemcpyDeviceToHost, e->stream));
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  return CTD_OK;
+}
+
+ctd_status ctd_game_options(ctd_engine* e, const ctd_state* state, const void* know6, ctd_option* opts, uint32_t cap, uint32_t* count) {
+  if (!e || !state || !opts || !count) return CTD_EARG;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  ctd_status s = ctd_one_buffer(e);
+  if (s != CTD_OK) return s;
+  CTD_CUDA(e, cudaMemcpyAsync(e->d_one, state, sizeof(ctd_state), cudaMemcpyHostToDevice, e->stream));
+  if (know6) CTD_CUDA(e, cudaMemcpyAsync(e->d_one + CTD_ONE_KNOW_OFF, know6, 2400, cudaMemcpyHostToDevice, e->stream));
+  CtdOneArgs a = ctd_one_args(e, 1, know6 != nullptr);
+  ctd_k_one<<<1, 32, 0, e->stream>>>(a);
+  e->launches++;
+  CTD_CUDA(e, cudaGetLastError());
+  CTD_CUDA(e, cudaMemcpyAsync(count, a.count, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  uint32_t n = *count < cap ? *count : cap;
+  if (n > CTD_ONE_OPTS) n = CTD_ONE_OPTS;
+  CTD_CUDA(e, cudaMemcpyAsync(opts, a.opts, (size_t)n * sizeof(ctd_option), cudaMemcpyDeviceToHost, e->stream));
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  return *count > cap || *count > CTD_ONE_OPTS ? CTD_ECAP : CTD_OK;
+}
+
+ctd_status ctd_game_step(ctd_engine* e, uint64_t seed, ctd_state* state, void* know6, ctd_option chosen, int8_t* winner) {
+  if (!e || !state || !winner) return CTD_EARG;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  ctd_status s = ctd_one_buffer(e);
+  if (s != CTD_OK) return s;
+  CTD_CUDA(e, cudaMemcpyAsync(e->d_one, state, sizeof(ctd_state), cudaMemcpyHostToDevice, e->stream));
+  if (know6) CTD_CUDA(e, cudaMemcpyAsync(e->d_one + CTD_ONE_KNOW_OFF, know6, 2400, cudaMemcpyHostToDevice, e->stream));
+  CtdOneArgs a = ctd_one_args(e, 2, know6 != nullptr);
+  a.seed = seed; a.chosen = chosen;
+  ctd_k_one<<<1, 32, 0, e->stream>>>(a);
+  e->launches++;
+  CTD_CUDA(e, cudaGetLastError());
+  CTD_CUDA(e, cudaMemcpyAsync(state, e->d_one, sizeof(ctd_state), cudaMemcpyDeviceToHost, e->stream));
+  if (know6) CTD_CUDA(e, cudaMemcpyAsync(know6, e->d_one + CTD_ONE_KNOW_OFF, 2400, cudaMemcpyDeviceToHost, e->stream));
+  CTD_CUDA(e, cudaMemcpyAsync(winner, a.winner, 1, cudaMemcpyDeviceToHost, e->stream));
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
   return CTD_OK;
 }
 

@@ -140,6 +140,18 @@ ctd_status ctd_states_dev(ctd_engine* e, void** dev_ptr);
  * Slots with a tape draw chance from it instead of Philox.  n == 0 clears all tapes. */
 ctd_status ctd_set_tapes(ctd_engine* e, uint32_t n, const uint8_t* tape, const uint32_t* tape_off);
 
+/* ---- one game at a time (what the Python facade's Game / Agent.get_options / option.carry_out call) ----
+ * The caller owns the record, the knowledge of all six observers (6 x CTD_KNOW_BYTES, may be NULL when CFR will
+ * not be run from this game) and Game.used_cards (76 bytes). */
+/* Game(preset=True); game.setup_round()  (run_utils.py:20-27) */
+ctd_status ctd_game_new(ctd_engine* e, uint64_t seed, uint64_t gid, int ruleset, ctd_state* state, void* know6,
+                        uint8_t* used_cards);
+/* game.get_options_from_state()  (game/game.py:415-418) */
+ctd_status ctd_game_options(ctd_engine* e, const ctd_state* state, const void* know6, ctd_option* opts, uint32_t cap,
+                            uint32_t* count);
+/* option.carry_out(game)  (game/option.py:118-122); *winner = winning seat or -1 */
+ctd_status ctd_game_step(ctd_engine* e, uint64_t seed, ctd_state* state, void* know6, ctd_option chosen, int8_t* winner);
+
 /* ---- the hot path ---- */
 /* Game.get_options_from_state / Agent.get_options (game/game.py:415-418, game/agent.py:50-83) for slots
  * [0,n): opts[i*stride .. i*stride+counts[i]) in the reference's list order.  Terminal slots report 0.
