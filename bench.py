@@ -105,6 +105,32 @@ def cpu_playouts(games_per_core, cores, gid0=0):
     return sum(r[0] for r in res), wall
 
 
+def _cpu_mccfr_worker(args):
+    seed, gid0, n, iters = args
+    from oracle import mccfr_oracle as M
+    from oracle.philox import PhiloxChance
+    its = 0
+    t0 = time.perf_counter()
+    for i in range(n):
+        g, _ = M.make_root(seed, gid0 + i, 0, 0, 20)
+        if g.terminal:
+            continue
+        g.chance = PhiloxChance(seed, gid0 + i, stream=1)
+        M.Node(g, g.player).cfr_train(iters)
+        its += iters
+    return its, time.perf_counter() - t0
+
+
+def cpu_mccfr(roots_per_core, cores, iters=200):
+    """run_mccfr(game, max_iterations=200) on near-terminal roots (oracle port), all host cores."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_mccfr_worker, [(SEED, 10_000 + c * roots_per_core, roots_per_core, iters) for c in range(cores)])
+    return sum(r[0] for r in res), time.perf_counter() - t0
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -142,6 +168,8 @@ def main():
     ap.add_argument("--ref-games-per-core", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ruleset", type=int, default=0)
+    ap.add_argument("--no-mccfr", action="store_true", help="skip the secondary MCCFR measurement")
+    ap.add_argument("--mccfr-roots", type=int, default=4096)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -166,8 +194,10 @@ def main():
     G = args.games
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
+    from citadels_self_play_b200 import sharding
+
     def gid0(step):  # disjoint global ids per (step, rank)
-        return (step * world + rank) * G
+        return sharding.first_gid(step, rank, world, G)
 
     def barrier():
         torch.cuda.synchronize()
@@ -212,7 +242,38 @@ def main():
     e2e_wall = time.perf_counter() - t1
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- secondary metric: MCCFR iterations/s (BASELINE configs[2] pure, configs[3] deep), same roots on every rank ----
+    mccfr = None
+    if not args.no_mccfr:
+        R, IT = args.mccfr_roots, 200
+        eng2 = Engine(capacity=R, device=local)
+        eng2.make_roots(R, seed=SEED, first_gid=sharding.first_gid(0, rank, world, R), back_lo=0, back_hi=20)
+        pure_it = pure_ms = deep_it = deep_ms = 0
+        eng2.mccfr(R, iterations=IT, seed=SEED)
+        for _ in range(2):
+            o = eng2.mccfr(R, iterations=IT, seed=SEED)
+            pure_it += int(o["results"]["iterations"].sum())
+            pure_ms += o["kernel_ms"]
+        from citadels_self_play_b200.value_model import ValueOnlyNN
+        torch.manual_seed(0)
+        eng2.set_value_model(ValueOnlyNN(418, 512).eval())
+        eng2.mccfr_pred(R, iterations=IT, max_depth=10, seed=SEED)
+        for _ in range(2):
+            o = eng2.mccfr_pred(R, iterations=IT, max_depth=10, seed=SEED)
+            deep_it += int(o["results"]["iterations"].sum())
+            deep_ms += o["kernel_ms"]
+        bad = int((o["results"]["status"] > 1).sum())
+        mccfr = [pure_it, pure_ms, deep_it, deep_ms, bad]
+        eng2.close()
+
     # ---- the only collective: outcome statistics, after the timed region ----
+    if mccfr is not None:
+        mt = torch.tensor(mccfr[1::2], dtype=torch.float64, device="cuda")
+        mi = torch.tensor([mccfr[0], mccfr[2], mccfr[4]], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(mt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(mi, op=dist.ReduceOp.SUM)
+        mccfr = [int(mi[0]), float(mt[0]), int(mi[1]), float(mt[1]), int(mi[2])]
     t = torch.tensor([wall, e2e_wall, kernel_ms], dtype=torch.float64, device="cuda")
     s = torch.tensor([env_steps, e2e_steps, errors, launches] + wins, dtype=torch.int64, device="cuda")
     if world > 1:
@@ -246,6 +307,19 @@ def main():
             "gpu_launches": launches, "clocks": clocks,
             "outcomes": {"games": G * args.steps * world, "errors": errors, "wins": wins},
         }
+        if mccfr is not None:
+            line["mccfr"] = {
+                "unit": "MCCFR iterations/s (one iteration = one node-step, algorithms/deep_mccfr.py:194-204)",
+                "roots_per_gpu": args.mccfr_roots, "iterations_per_root": 200, "root_step_back": "0..20",
+                "pure_it_per_s": mccfr[0] / (mccfr[1] / 1e3), "deep_it_per_s": mccfr[2] / (mccfr[3] / 1e3),
+                "deep_max_depth": 10, "deep_model": "ValueOnlyNN(418,512), torch.manual_seed(0) init",
+                "roofline_frac_hbm_2048B_per_it": (mccfr[0] / world / (mccfr[1] / 1e3)) * 2048 / 1e9 / peak,
+                "trees_with_error_status": mccfr[4]}
+            if not args.no_cpu_baseline:
+                cores = os.cpu_count() or 1
+                ci, cw = cpu_mccfr(3, cores)
+                line["mccfr"]["cpu_baseline"] = {"value": ci / cw, "unit": "iterations/s", "cores": cores, "kind": "port",
+                                                 "sample": "%d roots x 200 iterations, oracle port of run_mccfr" % (3 * cores)}
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             per_core = 12

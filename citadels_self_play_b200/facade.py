@@ -421,7 +421,7 @@ class CFRNode:
         self._index = 0
         self._children = None
         # skip_false_choice advances the caller's game (algorithms/deep_mccfr.py:19-20, :37-49)
-        g._rec = self._tree.nodes[0]["game"].copy()
+        g._rec = np.array(self._tree.nodes[0]["game"])
         g._know[v * KNOW_BYTES:(v + 1) * KNOW_BYTES] = np.frombuffer(self._tree.nodes[0]["know"].tobytes(), dtype=np.uint8)
         self._fill()
 
@@ -445,7 +445,7 @@ class CFRNode:
             for desc, idx in self._tree.child_list(self._index):
                 cg = Game.__new__(Game)
                 cg._engine, cg.seed, cg.gid, cg._fresh = self.game._engine, self.game.seed, self.game.gid, False
-                cg._rec = self._tree.nodes[idx]["game"].copy()
+                cg._rec = np.array(self._tree.nodes[idx]["game"])
                 cg._know = self.game._know.copy()   # only the searching player's block is tracked inside a tree
                 v = self.original_player_id
                 cg._know[v * KNOW_BYTES:(v + 1) * KNOW_BYTES] = np.frombuffer(self._tree.nodes[idx]["know"].tobytes(), dtype=np.uint8)
