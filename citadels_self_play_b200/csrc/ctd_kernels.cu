@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <new>
+#include <stddef.h>
 
 #include "ctd_engine.cuh"
 #include "ctd_warp.cuh"
@@ -124,21 +125,18 @@ struct CtdPlayoutArgs {
   ctd_state* slots;  // non-null: continue from slots[0..n) instead of dealing new games
 };
 
-// per-warp partial statistics, kept in lane 0's registers and flushed once
-struct CtdWarpStats {
-  unsigned long long games, steps, steps_sq, errors, max_steps;
-  unsigned long long wins[6];
-  long long psum[6];
-  unsigned long long psq[6];
-};
-
+// Outcome statistics are accumulated per block in shared memory (one shared atomic per field and game) and flushed
+// to HBM once per block.
 __global__ void __launch_bounds__(CTD_BLOCK, CTD_PLAYOUT_MIN_BLOCKS) ctd_k_playout(CtdPlayoutArgs a) {
   __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
   __shared__ ctd_state stage[CTD_WARPS_PER_BLOCK];
+  __shared__ uint64_t choose_buf[CTD_WARPS_PER_BLOCK][CTD_CHOOSE_BUF];
+  __shared__ unsigned long long bst[sizeof(ctd_playout_stats) / 8];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   CtdWork& w = works[wib];
-  CtdWarpStats st;
-  memset(&st, 0, sizeof(st));
+  if (threadIdx.x < sizeof(ctd_playout_stats) / 8) bst[threadIdx.x] = 0;
+  __syncthreads();
+  ctd_playout_stats* bs = reinterpret_cast<ctd_playout_stats*>(bst);
   for (;;) {
     unsigned long long g = 0;
     if (lane == 0) g = atomicAdd(a.counter, 1ull);
@@ -160,48 +158,43 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_PLAYOUT_MIN_BLOCKS) ctd_k_playo
     for (;;) {
       bool stop = (w.gflags & 2) || w.err || (w.steps - steps0) >= a.max_steps;
       if (stop) break;
-      // warp-cooperative: count the legal options, draw k, select the k-th (ctd_warp.cuh)
-      uint64_t d = ctd_warp_choose(w, lane);
+      uint64_t d = ctd_warp_choose(w, lane, choose_buf[wib]);
       if (lane == 0) {
         if (d == 0) w.err |= CTD_ERR_REF_RAISE;
         else ctd_apply(w, d);
       }
       __syncwarp();
     }
-    if (lane == 0) {
-      if (!(w.gflags & 2) && !w.err) w.err |= CTD_ERR_MAXSTEPS;
-      const uint32_t ns = w.steps - steps0;
+    if (lane == 0 && !(w.gflags & 2) && !w.err) w.err |= CTD_ERR_MAXSTEPS;
+    __syncwarp();
+    const uint32_t ns = w.steps - steps0;
+    if (lane < 6) {  // per-seat fields: one lane per seat
+      const int pts = w.points[lane];
+      if (a.points6) a.points6[g * 6 + lane] = (int8_t)pts;
+      atomicAdd((unsigned long long*)&bs->points_sum[lane], (unsigned long long)(long long)pts);
+      atomicAdd((unsigned long long*)&bs->points_sq[lane], (unsigned long long)(pts * pts));
+      if (w.winner == lane) atomicAdd((unsigned long long*)&bs->wins[lane], 1ull);
+    } else if (lane == 6) {
       if (a.winner) a.winner[g] = w.winner;
       if (a.steps) a.steps[g] = (uint16_t)ns;
-      if (a.points6)
-        for (int p = 0; p < 6; ++p) a.points6[g * 6 + p] = w.points[p];
-      st.games += 1;
-      st.steps += ns;
-      st.steps_sq += (unsigned long long)ns * ns;
-      if (ns > st.max_steps) st.max_steps = ns;
-      if (w.err) st.errors += 1;
-      if (w.winner >= 0) st.wins[w.winner] += 1;
-      for (int p = 0; p < 6; ++p) {
-        st.psum[p] += w.points[p];
-        st.psq[p] += (unsigned long long)((int)w.points[p] * (int)w.points[p]);
-      }
-      if (a.slots != nullptr) ctd_pack(w, &stage[wib]);
+      atomicAdd((unsigned long long*)&bs->games, 1ull);
+      atomicAdd((unsigned long long*)&bs->steps, (unsigned long long)ns);
+      atomicAdd((unsigned long long*)&bs->steps_sq, (unsigned long long)ns * ns);
+      if (w.err) atomicAdd((unsigned long long*)&bs->errors, 1ull);
+      atomicMax((unsigned long long*)&bs->max_steps, (unsigned long long)ns);
     }
-    if (a.slots != nullptr) ctd_record_store(&a.slots[g], &stage[wib], lane);
+    if (a.slots != nullptr) {
+      if (lane == 0) ctd_pack(w, &stage[wib]);
+      ctd_record_store(&a.slots[g], &stage[wib], lane);
+    }
     __syncwarp();
   }
-  if (lane == 0 && st.games != 0 && a.stats != nullptr) {
-    ctd_playout_stats* s = a.stats;
-    atomicAdd((unsigned long long*)&s->games, st.games);
-    atomicAdd((unsigned long long*)&s->steps, st.steps);
-    atomicAdd((unsigned long long*)&s->steps_sq, st.steps_sq);
-    atomicAdd((unsigned long long*)&s->errors, st.errors);
-    atomicMax((unsigned long long*)&s->max_steps, st.max_steps);
-    for (int p = 0; p < 6; ++p) {
-      atomicAdd((unsigned long long*)&s->wins[p], st.wins[p]);
-      atomicAdd((unsigned long long*)&s->points_sum[p], (unsigned long long)st.psum[p]);
-      atomicAdd((unsigned long long*)&s->points_sq[p], st.psq[p]);
-    }
+  __syncthreads();
+  if (a.stats != nullptr && threadIdx.x < sizeof(ctd_playout_stats) / 8 && bst[threadIdx.x] != 0) {
+    unsigned long long* gs = reinterpret_cast<unsigned long long*>(a.stats);
+    const int maxi = offsetof(ctd_playout_stats, max_steps) / 8;
+    if ((int)threadIdx.x == maxi) atomicMax(&gs[maxi], bst[threadIdx.x]);
+    else atomicAdd(&gs[threadIdx.x], bst[threadIdx.x]);
   }
 }
 

@@ -4,17 +4,24 @@
 #pragma once
 #include "ctd_engine.cuh"
 
+#define CTD_CHOOSE_BUF 64 /* descriptors kept from the counting pass; the preset ruleset never exceeds 59 */
+
 #ifdef __CUDACC__
-__device__ __forceinline__ uint64_t ctd_warp_choose(CtdWork& w, int lane) {
+// `buf` is CTD_CHOOSE_BUF descriptors of shared memory owned by this warp.
+__device__ __forceinline__ uint64_t ctd_warp_choose(CtdWork& w, int lane, uint64_t* buf) {
   uint64_t d = 0;
   if (lane == 0) {
-    CtdEmit e{nullptr, 0, 0, 0xFFFFFFFFu, 0};
+    CtdEmit e{buf, CTD_CHOOSE_BUF, 0, 0xFFFFFFFFu, 0};
     ctd_enumerate(w, e);
     if (e.n != 0) {
       uint32_t k = ctd_randbelow(w, e.n);
-      CtdEmit e2{nullptr, 0, 0, k, 0};
-      ctd_enumerate(w, e2);
-      d = e2.got;
+      if (k < CTD_CHOOSE_BUF) {
+        d = buf[k];
+      } else {  // rare (classic Magician): select by a second pass
+        CtdEmit e2{buf, 0, 0, k, 0};
+        ctd_enumerate(w, e2);
+        d = e2.got;
+      }
     }
   }
   return __shfl_sync(0xFFFFFFFFu, d, 0);
