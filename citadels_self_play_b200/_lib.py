@@ -33,6 +33,7 @@ SIGNATURES = {
     "ctd_set_tapes": (_i, [c_void, _u32, c_void, c_void]),
     "ctd_enumerate": (_i, [c_void, _u32, c_void, c_void, _u32]),
     "ctd_step": (_i, [c_void, _u32, c_void, c_void]),
+    "ctd_choose_check": (_i, [c_void, _u32, c_void]),
     "ctd_playout": (_i, [c_void, _u64, _u64, _u64, _i, _u32, c_void, c_void, c_void, ctypes.POINTER(PlayoutStats)]),
     "ctd_playout_slots": (_i, [c_void, _u32, _u32, c_void, c_void]),
     "ctd_playout_dev": (_i, [c_void, _u64, _u64, _u64, _i, _u32, ctypes.POINTER(PlayoutStats),

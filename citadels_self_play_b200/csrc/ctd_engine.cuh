@@ -388,6 +388,7 @@ CTD_HD inline void ctd_clear_done(CtdWork& w) { w.done = 0; w.n_trade = 0; w.n_n
 
 // ------------------------------------------------------------------------------------------ round machine
 // Game.setup_round (game/game.py:144-171)
+template <bool KN = true>
 CTD_HD CTD_NI inline void ctd_setup_round(CtdWork& w, CtdKnowSet ks = CtdKnowSet{nullptr, 0}) {
   CTD_LOOP for (int r = 0; r < 8; ++r) w.rprops[r] = 0;
   w.used_len = 0;
@@ -408,7 +409,7 @@ CTD_HD CTD_NI inline void ctd_setup_round(CtdWork& w, CtdKnowSet ks = CtdKnowSet
   w.next_mode = CTD_NEXT_NONE;
   w.next_player = 0;
   w.wiz_target = 0xFF;  // Agent.substract_from_known_hand_confidences_and_clear_wizard (game/agent.py:100-109)
-  CTD_LOOP for (int i = 0; i < ks.n; ++i) ctd_kn_setup_round(ks.k[i]);
+  if (KN) CTD_LOOP for (int i = 0; i < ks.n; ++i) ctd_kn_setup_round(ks.k[i]);
 }
 
 // Game.refresh_used_roles (game/game.py:349-357); value+1 encoding keeps Bewitched (-1) sortable as 0
@@ -842,6 +843,7 @@ CTD_HD CTD_NI inline void ctd_apply_build(CtdWork& w, int p, int t, int replica)
 }
 
 // finish_main_sequnce_actions (game/option_functions.py:189-243).  Returns true when the game ended.
+template <bool KN>
 CTD_HD CTD_NI inline bool ctd_apply_finish(CtdWork& w, uint64_t d, CtdKnowSet ks) {
   const int p = CTD_OPT_PERP(d);
   const int pr = w.role[p];
@@ -851,8 +853,8 @@ CTD_HD CTD_NI inline bool ctd_apply_finish(CtdWork& w, uint64_t d, CtdKnowSet ks
     if (ctd_owns(w, p, 28) && w.n_hand[p] == 0) { ctd_draw_to_jd(w, p); ctd_draw_to_jd(w, p); }  // Park
     if (ctd_owns(w, p, 30) && w.n_hand[p] == 0) w.gold[p] += 1;                                  // Poorhouse
   }
-  if (CTD_OPT_CROWN(d)) { ctd_kn_confirm(ks, p, pr); ctd_move_crown(w, p); }
-  else if (dead) ctd_kn_confirm(ks, p, pr);
+  if (CTD_OPT_CROWN(d)) { if (KN) ctd_kn_confirm(ks, p, pr); ctd_move_crown(w, p); }
+  else if (KN && dead) ctd_kn_confirm(ks, p, pr);
   if (CTD_OPT_NEXT_WITCH(d)) {  // :211-230 the witch takes over the possessed role
     int wi = ctd_player_from_rank(w, 0);
     if (wi < 0) { w.err |= CTD_ERR_REF_RAISE; return false; }
@@ -861,7 +863,7 @@ CTD_HD CTD_NI inline bool ctd_apply_finish(CtdWork& w, uint64_t d, CtdKnowSet ks
     w.role[wi] = (uint8_t)pr;
     w.rprops[pr] &= (uint8_t)~CTD_RP_POSSESSED;
     w.role[p] = CTD_ROLE_BEWITCHED;
-    CTD_LOOP for (int i = 0; i < ks.n; ++i) {  // :222-226
+    if (KN) CTD_LOOP for (int i = 0; i < ks.n; ++i) {  // :222-226
       CtdKnow& k = ks.k[i];
       if (k.viewer != wi) k.kr[wi] = (uint16_t)(1u << pr);
       if (k.viewer != p) k.kr[p] = (uint16_t)(1u << 8);
@@ -872,7 +874,7 @@ CTD_HD CTD_NI inline bool ctd_apply_finish(CtdWork& w, uint64_t d, CtdKnowSet ks
   if (w.used_len == 0) { w.err |= CTD_ERR_REF_RAISE; return false; }
   if ((int)w.used_roles[w.used_len - 1] - 1 == pr) {  // last player of the round
     if (ctd_check_game_ending(w)) return true;
-    ctd_setup_round(w, ks);
+    ctd_setup_round<KN>(w, ks);
   } else {
     ctd_setup_next_player(w, p);
   }
@@ -880,6 +882,8 @@ CTD_HD CTD_NI inline bool ctd_apply_finish(CtdWork& w, uint64_t d, CtdKnowSet ks
 }
 
 // option.carry_out (game/option.py:118-122).  Returns true when this step ended the game.
+// KN = false instantiates the transition without the knowledge bookkeeping (the playout kernel: smaller image).
+template <bool KN = true>
 CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdKnowSet{nullptr, 0}) {
   const int k = CTD_OPT_KIND(d);
   const int p = CTD_OPT_PERP(d);
@@ -889,7 +893,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       int r = CTD_OPT_RANK(d);
       w.role[p] = (uint8_t)r;
       w.rtc_mask &= (uint8_t)~(1u << r);
-      CTD_LOOP for (int i = 0; i < ks.n; ++i) {  // only the picker's beliefs are written (:11-25)
+      if (KN) CTD_LOOP for (int i = 0; i < ks.n; ++i) {  // only the picker's beliefs are written (:11-25)
         CtdKnow& k = ks.k[i];
         if (k.viewer != p) continue;
         int me = 0;
@@ -913,7 +917,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
     case CTD_K_GOLD_OR_CARD: {  // carry_out_gold_or_card (:33-55)
       int r = w.role[p];
       if (r == CTD_ROLE_NONE) { w.err |= CTD_ERR_REF_RAISE; break; }
-      ctd_kn_confirm(ks, p, r);  // confirm_role_knowledges (:35)
+      if (KN) ctd_kn_confirm(ks, p, r);  // confirm_role_knowledges (:35)
       if (r >= 8) { w.err |= CTD_ERR_REF_RAISE; break; }
       if (w.rprops[r] & CTD_RP_ROBBED) {
         int th = ctd_player_from_rank(w, 1);
@@ -958,7 +962,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       }
       break;
     case CTD_K_BUILD: ctd_apply_build(w, p, CTD_OPT_CARD_A(d), CTD_OPT_REPLICA(d)); break;
-    case CTD_K_FINISH: won = ctd_apply_finish(w, d, ks); break;
+    case CTD_K_FINISH: won = ctd_apply_finish<KN>(w, d, ks); break;
     case CTD_K_SMITHY:  // carry_out_smithy (:131-138): the cards go to just_drawn_cards
       w.gold[p] -= 2;
       CTD_LOOP for (int i = 0; i < 3; ++i) ctd_draw_to_jd(w, p);
@@ -993,7 +997,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
     }
     case CTD_K_LIGHTHOUSE: {  // carry_out_lighthouse (:173-180)
       int t = CTD_OPT_CARD_A(d), c = t, n = w.n_deck;
-      CTD_LOOP for (int i = 0; i < ks.n; ++i)  // HandKnowledge(player_id=-1, hand=deepcopy(deck)) (:174)
+      if (KN) CTD_LOOP for (int i = 0; i < ks.n; ++i)  // HandKnowledge(player_id=-1, hand=deepcopy(deck)) (:174)
         if (ks.k[i].viewer == p) ctd_kn_add_hk(ks.k[i], -1, w.deck, n, w.deck_head, CTD_DECK_CAP - 1, false);
       CTD_LOOP for (int i = 0; i < n; ++i)
         if (ctd_ctype(ctd_dk(w, i)) == t) {
@@ -1070,7 +1074,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       break;
     }
     case CTD_K_LOOK_AT_HAND:  // carry_out_wizard_hand_looking (:305-310)
-      CTD_LOOP for (int i = 0; i < ks.n; ++i) {
+      if (KN) CTD_LOOP for (int i = 0; i < ks.n; ++i) {
         CtdKnow& k = ks.k[i];
         int q = CTD_OPT_TARGET(d), n = w.n_hand[q];
         if (n > CTD_KN_WIZ_CAP) { k.err |= CTD_ERR_OVERFLOW; n = CTD_KN_WIZ_CAP; }
@@ -1089,7 +1093,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       int q = CTD_OPT_TARGET(d), t = CTD_OPT_CARD_A(d);
       ctd_append(w, w.hand[p], w.n_hand[p], CTD_HAND_CAP, ctd_take_like(w.hand[q], w.n_hand[q], t));
       if (CTD_OPT_BUILD(d)) ctd_apply_build(w, p, t, ctd_count_type(w.bld[p], w.n_bld[p], t));
-      CTD_LOOP for (int i = 0; i < ks.n; ++i) {  // the looked-at copy loses the card too (:320, :326)
+      if (KN) CTD_LOOP for (int i = 0; i < ks.n; ++i) {  // the looked-at copy loses the card too (:320, :326)
         CtdKnow& k = ks.k[i];
         CTD_LOOP for (int j = 0; j < k.wiz_n; ++j)
           if (ctd_ctype(k.wiz_cards[j]) == t) {

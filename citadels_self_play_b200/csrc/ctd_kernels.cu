@@ -113,6 +113,44 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_step(ctd_state* slots, uint32
   ctd_record_store(&slots[slot], &stage[wib], lane);
 }
 
+// Checker for the warp-cooperative chooser: for every slot, the cooperative count and the cooperative k-th option for
+// every k must equal the scalar enumerator's list.  mismatches[slot] = number of differing entries (+1e6 if the counts differ).
+__global__ void __launch_bounds__(CTD_BLOCK) ctd_k_choose_check(const ctd_state* slots, uint32_t n, uint32_t* mismatches,
+                                                                uint64_t* scratch_opts, uint32_t cap) {
+  __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
+  __shared__ ctd_state stage[CTD_WARPS_PER_BLOCK];
+  __shared__ uint64_t choose_buf[CTD_WARPS_PER_BLOCK][CTD_CHOOSE_BUF];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t slot = blockIdx.x * CTD_WARPS_PER_BLOCK + wib;
+  if (slot >= n) return;
+  CtdWork& w = works[wib];
+  ctd_record_load(&slots[slot], &stage[wib], lane);
+  uint64_t* ref = scratch_opts + (size_t)slot * cap;
+  uint32_t nref = 0;
+  if (lane == 0) {
+    ctd_unpack(&stage[wib], w);
+    CtdEmit e{ref, cap, 0, 0xFFFFFFFFu, 0};
+    ctd_enumerate(w, e);
+    nref = e.n;
+  }
+  nref = __shfl_sync(CTD_FULL, nref, 0);
+  __syncwarp();
+  uint32_t bad = 0, cnt = 0;
+  if (nref == 0) {
+    if (lane == 0) mismatches[slot] = 0;
+    return;
+  }
+  for (uint32_t k = 0; k < nref && k < cap; ++k) {
+    uint64_t d = ctd_warp_choose(w, lane, choose_buf[wib], &cnt, (int)k);
+    __syncwarp();
+    if (cnt != nref) { bad += 1000000; break; }
+    uint64_t want = ref[k];
+    // discard_and_draw ordinals are reproduced too, so compare everything
+    if (d != want) ++bad;
+  }
+  if (lane == 0) mismatches[slot] = bad;
+}
+
 struct CtdPlayoutArgs {
   uint64_t n_games, seed, first_gid;
   int ruleset;
@@ -150,7 +188,9 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_PLAYOUT_MIN_BLOCKS) ctd_k_playo
         w.tape = nullptr; w.tape_len = 0;
       }
     } else if (lane == 0) {
-      ctd_new_game(w, a.seed, a.first_gid + g, a.ruleset);
+      ctd_chance_init(w, a.seed, a.first_gid + g, 0);
+      ctd_deal_preset(w, a.ruleset);
+      ctd_setup_round<false>(w);
     }
     __syncwarp();
     const uint32_t steps0 = w.steps;
@@ -161,7 +201,7 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_PLAYOUT_MIN_BLOCKS) ctd_k_playo
       uint64_t d = ctd_warp_choose(w, lane, choose_buf[wib]);
       if (lane == 0) {
         if (d == 0) w.err |= CTD_ERR_REF_RAISE;
-        else ctd_apply(w, d);
+        else ctd_apply<false>(w, d);
       }
       __syncwarp();
     }
@@ -788,6 +828,23 @@ ctd_status ctd_enumerate(ctd_engine* e, uint32_t n, ctd_option* opts, uint32_t* 
   CTD_CUDA(e, cudaStreamSynchronize(e->stream));
   for (uint32_t i = 0; i < n; ++i)
     if (counts[i] > stride) return CTD_ECAP;
+  return CTD_OK;
+}
+
+ctd_status ctd_choose_check(ctd_engine* e, uint32_t n, uint32_t* mismatches) {
+  if (!e || !mismatches || n > e->capacity) return CTD_EARG;
+  if (n == 0) return CTD_OK;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  const uint32_t cap = 4096;
+  size_t ob = (size_t)n * cap * sizeof(ctd_option);
+  ctd_status s = ctd_scratch(e, ob + (size_t)n * 4);
+  if (s != CTD_OK) return s;
+  uint32_t* d_mis = (uint32_t*)((char*)e->d_scratch + ob);
+  ctd_k_choose_check<<<ctd_blocks(n), CTD_BLOCK, 0, e->stream>>>(e->d_slots, n, d_mis, (uint64_t*)e->d_scratch, cap);
+  e->launches++;
+  CTD_CUDA(e, cudaGetLastError());
+  CTD_CUDA(e, cudaMemcpyAsync(mismatches, d_mis, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
   return CTD_OK;
 }
 

@@ -87,6 +87,12 @@ class Engine:
                 return opts, counts
             stride = int(max(counts.max(), stride * 2))
 
+    def choose_check(self, n):
+        """Test hook: cooperative count/select of the playout kernel vs the enumerated list, per slot."""
+        mis = np.empty(n, dtype=np.uint32)
+        self._check(self._lib.ctd_choose_check(self._h, n, mis.ctypes.data), "ctd_choose_check")
+        return mis
+
     def step(self, chosen):
         c = np.ascontiguousarray(chosen, dtype=np.uint64)
         winner = np.empty(len(c), dtype=np.int8)

@@ -157,6 +157,9 @@ ctd_status ctd_game_step(ctd_engine* e, uint64_t seed, ctd_state* state, void* k
  * [0,n): opts[i*stride .. i*stride+counts[i]) in the reference's list order.  Terminal slots report 0.
  * counts[i] > stride => only the first `stride` were written (status CTD_ECAP). */
 ctd_status ctd_enumerate(ctd_engine* e, uint32_t n, ctd_option* opts, uint32_t* counts, uint32_t stride);
+/* (test hook) the fused playout kernel picks its option with a warp-cooperative count/select; this runs that path on
+ * slots [0,n) for every k and reports how many picks differ from the ctd_enumerate list (0 everywhere = identical). */
+ctd_status ctd_choose_check(ctd_engine* e, uint32_t n, uint32_t* mismatches);
 /* option.carry_out(game) (game/option.py:118-122) for slots [0,n): chosen[i] == 0 skips slot i.
  * winner[i] = winning seat when that step ended the game, else -1 (the reference returns the winner
  * Agent or a falsy value). */

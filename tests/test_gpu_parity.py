@@ -35,6 +35,9 @@ def _replay(engine, name, with_tape):
     for k in range(maxlen):
         live = np.nonzero(lens > k)[0]
         opts, counts = engine.enumerate(n, stride=64)
+        if k % 3 == 0:   # the playout kernel's warp-cooperative chooser: every k of every state vs this list
+            mis = engine.choose_check(n)
+            assert not mis[live].any(), ("cooperative chooser differs", name, k, np.nonzero(mis)[0][:5], mis[mis > 0][:5])
         states = engine.store_states(n)
         idx = base[live] + k
         assert np.array_equal(counts[live], T.nopt[idx].astype(np.uint32)), "option count mismatch at step %d" % k
