@@ -225,7 +225,7 @@ struct CtdHK {
   uint16_t off;    // into pool
   uint16_t pad;
 };
-struct CtdKnow {
+struct alignas(16) CtdKnow {
   uint8_t viewer;
   uint8_t conf_mask;  // bit q: known_roles[*][q].confirmed (the same for every observer)
   uint8_t n_hk;

@@ -363,6 +363,7 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_mccfr(CtdMccfrArgs a) {
   __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
   __shared__ CtdKnow knows[CTD_WARPS_PER_BLOCK];
   __shared__ uint8_t scratch[CTD_WARPS_PER_BLOCK][256];
+  __shared__ __align__(16) ctd_state tstage[CTD_WARPS_PER_BLOCK];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   uint64_t* opts = a.opts_scratch + ((size_t)blockIdx.x * CTD_WARPS_PER_BLOCK + wib) * CTD_MCCFR_OPT_CAP;
   for (;;) {
@@ -372,14 +373,15 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_mccfr(CtdMccfrArgs a) {
     if (t >= a.n_roots) break;
     if (lane == 0) {
       CtdTree T = ctd_tree_at(a.trees + t * a.tree_stride, a.max_nodes, a.child_cap);
-      T.w = &works[wib]; T.kn = &knows[wib]; T.opts = opts; T.scratch = scratch[wib];
+      T.w = &works[wib]; T.kn = &knows[wib]; T.opts = opts; T.scratch = scratch[wib]; T.stage = &tstage[wib];
       CtdWork& w = *T.w;
       for (int i = 0; i < 76; ++i) T.hdr->used_cards[i] = a.used_cards[t * 76 + i];
-      ctd_unpack(&a.roots[t], w);
+      ctd_copy16(T.stage, &a.roots[t], (int)sizeof(ctd_state));
+      ctd_unpack(T.stage, w);
       ctd_chance_init(w, a.seed, a.gids[t], 0);
       w.stream = 1;
       w.err = 0;
-      *T.kn = a.knows[t];
+      ctd_copy16(T.kn, &a.knows[t], (int)sizeof(CtdKnow));
       ctd_tree_init(T, a.max_nodes, a.child_cap, a.arr_cap, T.kn->viewer, a.gids[t], false, false);
       ctd_cfr_train(T, a.iterations);
       if (a.results) ctd_write_result(T, &a.results[t]);
@@ -460,6 +462,7 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_mccfr_pred(CtdPredArgs p) {
   __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
   __shared__ CtdKnow knows[CTD_WARPS_PER_BLOCK];
   __shared__ uint8_t scratch[CTD_WARPS_PER_BLOCK][256];
+  __shared__ __align__(16) ctd_state tstage[CTD_WARPS_PER_BLOCK];
   const CtdMccfrArgs& a = p.m;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   uint64_t* opts = a.opts_scratch + ((size_t)blockIdx.x * CTD_WARPS_PER_BLOCK + wib) * CTD_MCCFR_OPT_CAP;
@@ -470,15 +473,16 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_mccfr_pred(CtdPredArgs p) {
     if (t >= a.n_roots) break;
     if (lane == 0) {
       CtdTree T = ctd_tree_at(a.trees + t * a.tree_stride, a.max_nodes, a.child_cap);
-      T.w = &works[wib]; T.kn = &knows[wib]; T.opts = opts; T.scratch = scratch[wib];
+      T.w = &works[wib]; T.kn = &knows[wib]; T.opts = opts; T.scratch = scratch[wib]; T.stage = &tstage[wib];
       CtdWork& w = *T.w;
       if (p.first) {
         for (int i = 0; i < 76; ++i) T.hdr->used_cards[i] = a.used_cards[t * 76 + i];
-        ctd_unpack(&a.roots[t], w);
+        ctd_copy16(T.stage, &a.roots[t], (int)sizeof(ctd_state));
+        ctd_unpack(T.stage, w);
         ctd_chance_init(w, a.seed, a.gids[t], 0);
         w.stream = 1;
         w.err = 0;
-        *T.kn = a.knows[t];
+        ctd_copy16(T.kn, &a.knows[t], (int)sizeof(CtdKnow));
         ctd_tree_init(T, a.max_nodes, a.child_cap, a.arr_cap, T.kn->viewer, a.gids[t], false, true);
       } else {
         ctd_chance_init(w, a.seed, a.gids[t], 0);

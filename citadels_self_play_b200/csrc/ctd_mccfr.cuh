@@ -81,7 +81,21 @@ struct CtdTree {
   CtdKnow* kn;      // working knowledge of the viewer
   uint64_t* opts;   // CTD_MCCFR_OPT_CAP descriptors
   uint8_t* scratch; // >= 256 bytes
+  ctd_state* stage; // 16-byte aligned staging record (shared memory on the device)
 };
+
+// 16-byte vector copy (both pointers 16-byte aligned, bytes a multiple of 16): the tree lives in HBM and its records
+// move as a handful of independent 128-bit transactions instead of hundreds of dependent byte accesses
+CTD_HD inline void ctd_copy16(void* dst, const void* src, int bytes) {
+  struct alignas(16) V { uint32_t x, y, z, w; };
+  V* d = (V*)dst;
+  const V* s = (const V*)src;
+  const int n = bytes / 16;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 8
+#endif
+  for (int i = 0; i < n; ++i) d[i] = s[i];
+}
 
 CTD_HD inline double ctd_uniform(CtdWork& w) { return (double)ctd_u32(w) / 4294967296.0; }
 
@@ -185,22 +199,20 @@ CTD_HD CTD_NI inline void ctd_sample_private(CtdWork& w, CtdKnow& k, const uint8
 
 // ------------------------------------------------------------------------------------------ node helpers
 CTD_HD inline void ctd_node_store(CtdTree& T, CtdNode& n) {
-  ctd_pack(*T.w, &n.game);
-  uint8_t* dst = (uint8_t*)&n.know;
-  const uint8_t* src = (const uint8_t*)T.kn;
-  CTD_LOOP for (int i = 0; i < (int)sizeof(CtdKnow); ++i) dst[i] = src[i];
+  ctd_pack(*T.w, T.stage);
+  ctd_copy16(&n.game, T.stage, (int)sizeof(ctd_state));
+  ctd_copy16(&n.know, T.kn, (int)sizeof(CtdKnow));
 }
 CTD_HD inline void ctd_node_load(CtdTree& T, const CtdNode& n) {
   // chance state lives in the working record and must survive a load
   CtdWork& w = *T.w;
   uint32_t k0 = w.k0, k1 = w.k1, draws = w.draws;
-  ctd_unpack(&n.game, w);
+  ctd_copy16(T.stage, &n.game, (int)sizeof(ctd_state));
+  ctd_unpack(T.stage, w);
   w.k0 = k0; w.k1 = k1; w.draws = draws; w.buf_blk = 0xFFFFFFFFu;
   w.g0 = (uint32_t)T.hdr->gid; w.g1 = (uint32_t)(T.hdr->gid >> 32);
   w.tape = nullptr; w.tape_len = 0; w.err = 0;
-  uint8_t* dst = (uint8_t*)T.kn;
-  const uint8_t* src = (const uint8_t*)&n.know;
-  CTD_LOOP for (int i = 0; i < (int)sizeof(CtdKnow); ++i) dst[i] = src[i];
+  ctd_copy16(T.kn, &n.know, (int)sizeof(CtdKnow));
 }
 
 // CFRNode.skip_false_choice (:37-49) on the working game

@@ -80,7 +80,8 @@ int hs_mccfr(const ctd_state* root, const CtdKnow* know, const uint8_t* used_car
   T.nodes = (CtdNode*)(tree_buf + sizeof(CtdTreeHdr));
   T.children = (CtdChild*)((uint8_t*)T.nodes + (size_t)max_nodes * sizeof(CtdNode));
   T.arr = (double*)((uint8_t*)T.children + (size_t)child_cap * sizeof(CtdChild));
-  T.w = &w; T.kn = &kn; T.opts = opts; T.scratch = scratch;
+  static ctd_state hs_stage __attribute__((aligned(16)));
+  T.w = &w; T.kn = &kn; T.opts = opts; T.scratch = scratch; T.stage = &hs_stage;
   memset(tree_buf, 0, ctd_tree_bytes(max_nodes, child_cap, arr_cap));
   memcpy(T.hdr->used_cards, used_cards, 76);
   ctd_unpack(root, w);
@@ -109,7 +110,8 @@ int hs_mccfr_pred(const ctd_state* root, const CtdKnow* know, const uint8_t* use
   T.nodes = (CtdNode*)(tree_buf + sizeof(CtdTreeHdr));
   T.children = (CtdChild*)((uint8_t*)T.nodes + (size_t)max_nodes * sizeof(CtdNode));
   T.arr = (double*)((uint8_t*)T.children + (size_t)child_cap * sizeof(CtdChild));
-  T.w = &w; T.kn = &kn; T.opts = opts; T.scratch = scratch;
+  static ctd_state hs_stage __attribute__((aligned(16)));
+  T.w = &w; T.kn = &kn; T.opts = opts; T.scratch = scratch; T.stage = &hs_stage;
   memset(tree_buf, 0, ctd_tree_bytes(max_nodes, child_cap, arr_cap));
   memcpy(T.hdr->used_cards, used_cards, 76);
   ctd_unpack(root, w);
