@@ -48,6 +48,7 @@ SIGNATURES = {
     "ctd_game_options": (_i, [c_void, c_void, c_void, c_void, _u32, ctypes.POINTER(_u32)]),
     "ctd_game_step": (_i, [c_void, _u64, c_void, c_void, _u64, ctypes.POINTER(ctypes.c_int8)]),
     "ctd_set_value_model": (_i, [c_void] + [c_void] * 8),
+    "ctd_set_value_backend": (_i, [c_void, _i]),
     "ctd_value_eval": (_i, [c_void, _u32, c_void, ctypes.c_float, c_void]),
     "ctd_encode": (_i, [c_void, _u32, c_void]),
     "ctd_mccfr_pred": (_i, [c_void, _u32, _u64, _u32, _u32, _i, ctypes.c_float, c_void, c_void,

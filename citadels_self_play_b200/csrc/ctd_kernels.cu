@@ -17,6 +17,7 @@
 #include "ctd_engine.cuh"
 #include "ctd_warp.cuh"
 #include "ctd_mccfr.cuh"
+#include "ctd_value_tc.cuh"
 
 #define CTD_WARPS_PER_BLOCK 8
 #define CTD_BLOCK (CTD_WARPS_PER_BLOCK * 32)
@@ -359,7 +360,10 @@ __device__ void ctd_write_result(CtdTree& T, ctd_mccfr_result* r) {
   for (uint32_t i = 0; i < na; ++i) { r->cumulative_regrets[i] = R[i]; r->strategy[i] = S[i]; r->cumulative_strategy[i] = C[i]; }
 }
 
-__global__ void __launch_bounds__(CTD_BLOCK) ctd_k_mccfr(CtdMccfrArgs a) {
+#ifndef CTD_MCCFR_MIN_BLOCKS
+#define CTD_MCCFR_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) ctd_k_mccfr(CtdMccfrArgs a) {
   __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
   __shared__ CtdKnow knows[CTD_WARPS_PER_BLOCK];
   __shared__ uint8_t scratch[CTD_WARPS_PER_BLOCK][256];
@@ -458,7 +462,7 @@ struct CtdPredArgs {
 };
 
 // one wave of CFRNode.cfr_pred for every tree: walk until a leaf value is needed (or the budget is spent)
-__global__ void __launch_bounds__(CTD_BLOCK) ctd_k_mccfr_pred(CtdPredArgs p) {
+__global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) ctd_k_mccfr_pred(CtdPredArgs p) {
   __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
   __shared__ CtdKnow knows[CTD_WARPS_PER_BLOCK];
   __shared__ uint8_t scratch[CTD_WARPS_PER_BLOCK][256];
@@ -659,6 +663,12 @@ struct ctd_engine {
   float* d_pred;
   uint8_t* d_pending;
   uint32_t* d_n_pending;
+  // tensor-core path of the value model: weights as [out][in], activations between layers, error flag
+  float* d_model_tc;
+  const float *tc_w1, *tc_w2, *tc_w3;
+  float *d_h1, *d_h2, *d_h3;
+  int* d_tc_err;
+  int value_backend;  // 0 = fp32 CUDA cores (ctd_k_value_mlp), 1 = tcgen05 split-TF32 (ctd_k_linear_tc)
   uint8_t* d_one;  // single-game staging: state | know6 | used_cards | count | winner | opts
   char err[256];
 };
@@ -694,6 +704,7 @@ ctd_status ctd_create(int device, uint32_t capacity, ctd_engine** out) {
   memset(e, 0, sizeof(*e));
   e->device = device;
   e->capacity = capacity;
+  e->value_backend = 1;  // dense layers on the tensor cores by default
   *out = e;
   CTD_CUDA(e, cudaSetDevice(device));
   CTD_CUDA(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
@@ -730,6 +741,11 @@ void ctd_destroy(ctd_engine* e) {
   if (e->d_pending) cudaFree(e->d_pending);
   if (e->d_n_pending) cudaFree(e->d_n_pending);
   if (e->d_one) cudaFree(e->d_one);
+  if (e->d_model_tc) cudaFree(e->d_model_tc);
+  if (e->d_h1) cudaFree(e->d_h1);
+  if (e->d_h2) cudaFree(e->d_h2);
+  if (e->d_h3) cudaFree(e->d_h3);
+  if (e->d_tc_err) cudaFree(e->d_tc_err);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
@@ -1166,6 +1182,39 @@ static ctd_status ctd_pred_buffers(ctd_engine* e) {
   CTD_CUDA(e, cudaMemsetAsync(e->d_pred, 0, (size_t)e->capacity * 8 * sizeof(float), e->stream));
   CTD_CUDA(e, cudaMemsetAsync(e->d_pending, 0, (size_t)e->capacity, e->stream));
   CTD_CUDA(e, cudaFuncSetAttribute(ctd_k_value_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CTD_MLP_SMEM));
+  CTD_CUDA(e, cudaFuncSetAttribute(ctd_k_linear_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CTD_TC_SMEM));
+  CTD_CUDA(e, cudaMalloc((void**)&e->d_h1, (size_t)e->capacity * 512 * sizeof(float)));
+  CTD_CUDA(e, cudaMalloc((void**)&e->d_h2, (size_t)e->capacity * 256 * sizeof(float)));
+  CTD_CUDA(e, cudaMalloc((void**)&e->d_h3, (size_t)e->capacity * 128 * sizeof(float)));
+  CTD_CUDA(e, cudaMalloc((void**)&e->d_tc_err, sizeof(int)));
+  CTD_CUDA(e, cudaMemsetAsync(e->d_tc_err, 0, sizeof(int), e->stream));
+  return CTD_OK;
+}
+
+// the value model on rows [0,n) of d_feat -> d_pred (rows with pending == 0 may be skipped)
+static ctd_status ctd_value_forward(ctd_engine* e, uint32_t n, const uint8_t* pending, float weight) {
+  if (e->value_backend == 0) {
+    ctd_k_value_mlp<<<(n + CTD_MLP_ROWS - 1) / CTD_MLP_ROWS, 256, CTD_MLP_SMEM, e->stream>>>(e->d_feat, pending, n, e->model, e->d_pred, weight);
+    e->launches++;
+    CTD_CUDA(e, cudaGetLastError());
+    return CTD_OK;
+  }
+  const int M = (int)n, gm = (M + CTD_TC_BM - 1) / CTD_TC_BM;
+  ctd_k_linear_tc<<<dim3(gm, 512 / CTD_TC_BN), 128, CTD_TC_SMEM, e->stream>>>(e->d_feat, CTD_FEATURES_PAD, e->tc_w1, CTD_FEATURES_PAD,
+                                                                              e->model.b1, e->d_h1, 512, M, CTD_FEATURES_PAD, 1, e->d_tc_err);
+  ctd_k_linear_tc<<<dim3(gm, 256 / CTD_TC_BN), 128, CTD_TC_SMEM, e->stream>>>(e->d_h1, 512, e->tc_w2, 512, e->model.b2, e->d_h2, 256, M, 512,
+                                                                              1, e->d_tc_err);
+  ctd_k_linear_tc<<<dim3(gm, 128 / CTD_TC_BN), 128, CTD_TC_SMEM, e->stream>>>(e->d_h2, 256, e->tc_w3, 256, e->model.b3, e->d_h3, 128, M, 256,
+                                                                              1, e->d_tc_err);
+  ctd_k_value_head<<<(n + 127) / 128, 128, 0, e->stream>>>(e->d_h3, e->model.w4t, e->model.b4, pending, n, e->d_pred, weight);
+  e->launches += 4;
+  CTD_CUDA(e, cudaGetLastError());
+  return CTD_OK;
+}
+
+ctd_status ctd_set_value_backend(ctd_engine* e, int backend) {
+  if (!e || (backend != 0 && backend != 1)) return CTD_EARG;
+  e->value_backend = backend;
   return CTD_OK;
 }
 
@@ -1187,6 +1236,19 @@ ctd_status ctd_set_value_model(ctd_engine* e, const float* w1t, const float* b1,
     *dst[i] = p;
     p += pad[i];
   }
+  {  // tensor-core layout: [out][in] (the reference's own nn.Linear layout), BN already folded
+    const size_t t1 = (size_t)512 * CTD_FEATURES_PAD, t2 = (size_t)256 * 512, t3 = (size_t)128 * 256;
+    float* h = new (std::nothrow) float[t1 + t2 + t3];
+    if (!h) return CTD_ENOMEM;
+    for (int o = 0; o < 512; ++o) for (int k = 0; k < CTD_FEATURES_PAD; ++k) h[(size_t)o * CTD_FEATURES_PAD + k] = w1t[(size_t)k * 512 + o];
+    for (int o = 0; o < 256; ++o) for (int k = 0; k < 512; ++k) h[t1 + (size_t)o * 512 + k] = w2t[(size_t)k * 256 + o];
+    for (int o = 0; o < 128; ++o) for (int k = 0; k < 256; ++k) h[t1 + t2 + (size_t)o * 256 + k] = w3t[(size_t)k * 128 + o];
+    if (!e->d_model_tc) CTD_CUDA(e, cudaMalloc((void**)&e->d_model_tc, (t1 + t2 + t3) * sizeof(float)));
+    cudaError_t c = cudaMemcpy(e->d_model_tc, h, (t1 + t2 + t3) * sizeof(float), cudaMemcpyHostToDevice);
+    delete[] h;
+    if (c != cudaSuccess) return ctd_fail(e, c, "upload tc weights");
+    e->tc_w1 = e->d_model_tc; e->tc_w2 = e->d_model_tc + t1; e->tc_w3 = e->d_model_tc + t1 + t2;
+  }
   CTD_CUDA(e, cudaStreamSynchronize(e->stream));
   return CTD_OK;
 }
@@ -1198,11 +1260,15 @@ ctd_status ctd_value_eval(ctd_engine* e, uint32_t n, const float* features, floa
   ctd_status s = ctd_pred_buffers(e);
   if (s != CTD_OK) return s;
   CTD_CUDA(e, cudaMemcpyAsync(e->d_feat, features, (size_t)n * CTD_FEATURES_PAD * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-  ctd_k_value_mlp<<<(n + CTD_MLP_ROWS - 1) / CTD_MLP_ROWS, 256, CTD_MLP_SMEM, e->stream>>>(e->d_feat, nullptr, n, e->model, e->d_pred, weight);
-  e->launches++;
-  CTD_CUDA(e, cudaGetLastError());
+  s = ctd_value_forward(e, n, nullptr, weight);
+  if (s != CTD_OK) return s;
   CTD_CUDA(e, cudaMemcpy2DAsync(out6, 6 * sizeof(float), e->d_pred, 8 * sizeof(float), 6 * sizeof(float), n, cudaMemcpyDeviceToHost, e->stream));
   CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (e->value_backend == 1) {
+    int terr = 0;
+    CTD_CUDA(e, cudaMemcpy(&terr, e->d_tc_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (terr) { snprintf(e->err, sizeof(e->err), "tcgen05 value kernel: mbarrier wait timed out"); return CTD_ECUDA; }
+  }
   return CTD_OK;
 }
 
@@ -1274,10 +1340,8 @@ ctd_status ctd_mccfr_pred(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32
     CTD_CUDA(e, cudaMemcpyAsync(&np, e->d_n_pending, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
     CTD_CUDA(e, cudaStreamSynchronize(e->stream));
     if (np == 0) break;
-    ctd_k_value_mlp<<<(n_roots + CTD_MLP_ROWS - 1) / CTD_MLP_ROWS, 256, CTD_MLP_SMEM, e->stream>>>(e->d_feat, e->d_pending, n_roots,
-                                                                                             e->model, e->d_pred, reward_weight);
-    e->launches++;
-    CTD_CUDA(e, cudaGetLastError());
+    s = ctd_value_forward(e, n_roots, e->d_pending, reward_weight);
+    if (s != CTD_OK) return s;
   }
   CTD_CUDA(e, cudaEventRecord(e->ev1, e->stream));
   if (results) CTD_CUDA(e, cudaMemcpyAsync(results, e->d_scratch, rb, cudaMemcpyDeviceToHost, e->stream));

@@ -178,6 +178,11 @@ class Engine:
         self._model_arrays = arrs   # keep alive during the copy
         self._check(self._lib.ctd_set_value_model(self._h, *[a.ctypes.data for a in arrs]), "ctd_set_value_model")
 
+    def set_value_backend(self, backend):
+        """'fp32' (CUDA cores) or 'tcgen05' (tensor cores, 3xTF32 split precision)."""
+        b = {"fp32": 0, "tcgen05": 1}[backend]
+        self._check(self._lib.ctd_set_value_backend(self._h, b), "ctd_set_value_backend")
+
     def value_eval(self, features, weight=5.0):
         f = np.zeros((len(features), 448), dtype=np.float32)
         f[:, :np.shape(features)[1]] = features

@@ -227,6 +227,8 @@ ctd_status ctd_mccfr(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32_t it
  * the reference's state_dict, run_utils.py:11-18). */
 ctd_status ctd_set_value_model(ctd_engine* e, const float* w1t, const float* b1, const float* w2t, const float* b2,
                                const float* w3t, const float* b3, const float* w4t, const float* b4);
+/* which kernels evaluate the dense layers: 0 = fp32 CUDA cores, 1 = tcgen05 tensor cores with 3xTF32 split precision */
+ctd_status ctd_set_value_backend(ctd_engine* e, int backend);
 /* CFRNode.model_inference (algorithms/deep_mccfr.py:364-374) for n feature rows of 448 floats (418 used):
  * out6[i] = weight * square_and_normalize(model(features[i]))  (train_utils.py:143-145) */
 ctd_status ctd_value_eval(ctd_engine* e, uint32_t n, const float* features, float weight, float* out6);
