@@ -42,15 +42,11 @@ __device__ __noinline__ uint64_t ctd_choose_scalar(CtdWork& w, int lane, uint64_
   return __shfl_sync(CTD_ALL, d, 0);
 }
 
-__device__ __forceinline__ uint32_t ctd_draw_uniform(CtdWork& w, int lane, uint32_t n, int want) {
-  if (want >= 0) return (uint32_t)want;
-  uint32_t k = 0;
-  if (lane == 0) k = ctd_randbelow(w, n);
-  return __shfl_sync(CTD_ALL, k, 0);
+// position of the k-th (0-based) set bit: the lane that owns it finds itself, one ballot tells everybody
+__device__ __forceinline__ int ctd_kth_bit(uint32_t mask, uint32_t k, int lane) {
+  const bool mine = ((mask >> lane) & 1) && (uint32_t)__popc(mask & ((1u << lane) - 1)) == k;
+  return __ffs(__ballot_sync(CTD_ALL, mine)) - 1;
 }
-
-// position of the k-th (0-based) set bit
-__device__ __forceinline__ int ctd_kth_bit(uint32_t mask, uint32_t k) { return (int)__fns(mask, 0, (int)k + 1); }
 
 // "first card of its type in this list" for lane < n (lanes beyond n never match anything)
 __device__ __forceinline__ bool ctd_first_of_type(int lane, int n, int t) {
@@ -59,177 +55,179 @@ __device__ __forceinline__ bool ctd_first_of_type(int lane, int n, int t) {
   return lane < n && (__ffs(m) - 1) == lane;
 }
 
+// printed cost by type, 3 bits each, ten types per 32-bit word (game/config.py:2-80)
+__device__ __forceinline__ int ctd_cost_w(int t) {
+  const uint32_t w0 = 1u | 2u << 3 | 4u << 6 | 2u << 9 | 5u << 12 | 3u << 15 | 2u << 18 | 3u << 21 | 5u << 24 | 1u << 27;
+  const uint32_t w1 = 2u | 3u << 3 | 1u << 6 | 4u << 9 | 3u << 12 | 5u << 15 | 5u << 18 | 3u << 21 | 6u << 24 | 2u << 27;
+  const uint32_t w2 = 6u | 5u << 3 | 5u << 6 | 6u << 9 | 5u << 12 | 6u << 15 | 6u << 18 | 3u << 21 | 6u << 24 | 3u << 27;
+  const uint32_t w3 = 5u | 5u << 3 | 6u << 6 | 5u << 9 | 4u << 12 | 6u << 15 | 5u << 18 | 4u << 21 | 0u << 24 | 5u << 27;
+  const int q = t / 10;
+  const uint32_t w = q == 0 ? w0 : (q == 1 ? w1 : (q == 2 ? w2 : w3));
+  return (int)((w >> (3 * (t - 10 * q))) & 7);
+}
+
 // Count the options of the game in `w`, draw k (or take `want` >= 0, used by the checker), return the k-th.
 // *count_out (optional) receives the number of options.  Every lane returns the same descriptor; 0 = none.
+// Structure: (A) classify the state and count -- all ballots happen here; (B) ONE draw; (C) select.
+enum { CTD_PM_ROLE_PICK, CTD_PM_GOLD_OR_CARD, CTD_PM_SINGLE, CTD_PM_KEEP, CTD_PM_KEEP_LIBRARY, CTD_PM_WITCH, CTD_PM_MAIN };
+
 __device__ __noinline__ uint64_t ctd_warp_choose(CtdWork& w, int lane, uint64_t* buf, uint32_t* count_out = nullptr,
                                                  int want = -1) {
-  if ((w.gflags & 2) || w.player >= 6) return ctd_choose_scalar(w, lane, buf, count_out, want);
   const int p = w.player, st = w.state;
+  if ((w.gflags & 2) || p >= 6) return ctd_choose_scalar(w, lane, buf, count_out, want);
+  const uint64_t me = (uint64_t)p << 6;
+  int mode = -1;
+  uint32_t total = 0, m0 = 0, m1 = 0, m2 = 0;   // mode-specific masks
+  uint64_t single = 0;
+  // main-round class counts
+  uint32_t c_build = 0, c_char = 0, c_beg = 0, c_wgold = 0, c_smithy = 0, c_lab = 0, c_ms = 0, c_ws = 0, c_mus = 0;
+  int nm = 0, nh = 0;
+  uint64_t own = 0;
   if (st == 0) {  // pick_role_options: one per role still on offer, rank ascending
-    const uint32_t m = w.rtc_mask, n = __popc(m);
-    if (count_out) *count_out = n;
-    if (n == 0) return 0;
-    const uint32_t k = ctd_draw_uniform(w, lane, n, want);
-    return ctd_opt(CTD_K_ROLE_PICK, p) | ctd_f_rank(ctd_kth_bit(m, k));
+    mode = CTD_PM_ROLE_PICK; m0 = w.rtc_mask; total = __popc(m0);
+  } else {
+    const int role = w.role[p];
+    if (role >= 8) return ctd_choose_scalar(w, lane, buf, count_out, want);  // None / Bewitched: error paths
+    nm = role * 3 + w.variant[role];
+    const int rp = w.rprops[role];
+    if (rp & CTD_RP_DEAD) return ctd_choose_scalar(w, lane, buf, count_out, want);
+    if (st == 1) {
+      mode = CTD_PM_GOLD_OR_CARD; total = w.n_deck > 1 ? 2 : 1;
+    } else if (st == 3 && !(rp & CTD_RP_BLACKMAIL)) {
+      mode = CTD_PM_SINGLE; total = 1; single = CTD_K_EMPTY | me;
+    } else if (st == 6) {
+      mode = CTD_PM_SINGLE; total = 1; single = (uint64_t)(w.gold[p] > 0 ? CTD_K_GRAVEYARD : CTD_K_EMPTY) | me;
+    } else if (st == 2 || st == 5) {
+      const int nb = w.n_bld[p];
+      {  // which building types do I own: lanes OR their building's bit
+        uint64_t bit = 0;
+        if (lane < nb) bit = 1ull << ctd_ctype(w.bld[p][lane]);
+        own = (uint64_t)__reduce_or_sync(CTD_ALL, (uint32_t)bit) | ((uint64_t)__reduce_or_sync(CTD_ALL, (uint32_t)(bit >> 32)) << 32);
+      }
+      if (st == 2) {  // which_card_to_keep_options
+        const int n = w.n_jd[p];
+        if (n > 32) return ctd_choose_scalar(w, lane, buf, count_out, want);
+        if ((own >> 20) & 1) {  // Library: every pair i < j, no de-duplication
+          mode = CTD_PM_KEEP_LIBRARY; m0 = (uint32_t)n; total = (uint32_t)(n * (n - 1) / 2);
+        } else {
+          mode = CTD_PM_KEEP;
+          m0 = __ballot_sync(CTD_ALL, ctd_first_of_type(lane, n, lane < n ? ctd_ctype(w.jd[p][lane]) : 0));
+          total = __popc(m0);
+        }
+      } else if (nm == CTD_WITCH) {
+        mode = CTD_PM_WITCH; total = 7;
+      } else if (rp & CTD_RP_POSSESSED) {
+        mode = CTD_PM_SINGLE; total = 1;
+        single = CTD_K_FINISH | me | ctd_f_next_witch(1) | ctd_f_crown(nm == CTD_KING || nm == CTD_PATRICIAN);
+      } else {
+        // ------------------------------------------------------------ main_round_options, the reference's order
+        nh = w.n_hand[p];
+        const bool lighthouse = ((own >> 29) & 1) && (w.pflags[p] & CTD_PF_LIGHTHOUSE);
+        const uint32_t tier_ab = (1u << CTD_SPY) | (1u << CTD_WIZARD) | (1u << CTD_KING) | (1u << CTD_ABBOT) | (1u << CTD_ALCHEMIST) |
+                                 (1u << CTD_NAVIGATOR) | (1u << CTD_WARLORD) | (1u << CTD_ASSASSIN) | (1u << CTD_THIEF) |
+                                 (1u << CTD_MAGICIAN) | (1u << CTD_BISHOP) | (1u << CTD_MERCHANT) | (1u << CTD_ARCHITECT);
+        if (nh > 32 || lighthouse || !((tier_ab >> nm) & 1)) return ctd_choose_scalar(w, lane, buf, count_out, want);
+        mode = CTD_PM_MAIN;
+        const int gold = w.gold[p], done = w.done;
+        const int hc = lane < nh ? w.hand[p][lane] : 0, ht = ctd_ctype(hc);
+        const bool hfirst = ctd_first_of_type(lane, nh, ht);
+        const bool unique = hc >= 16 && hc < 40;
+        if (w.n_trade + w.n_nontrade < ctd_build_limit(nm)) {  // 1. builds (Factory makes uniques dearer)
+          const int cost = ctd_cost_w(ht) + ((((own >> 35) & 1) && unique) ? 1 : 0);
+          m0 = __ballot_sync(CTD_ALL, hfirst && cost <= gold);
+        }
+        c_build = __popc(m0);
+        if (!(done & CTD_DM_CHARACTER)) {  // 2. character
+          if (nm == CTD_SPY) c_char = 25;
+          else if (nm == CTD_ASSASSIN) c_char = 7;
+          else if (nm == CTD_THIEF) c_char = 6;
+          else if (nm == CTD_NAVIGATOR) c_char = 2;
+          else if (nm == CTD_KING || nm == CTD_BISHOP || nm == CTD_MERCHANT || nm == CTD_ARCHITECT) c_char = 1;
+          else if (nm == CTD_WIZARD) {
+            m1 = __ballot_sync(CTD_ALL, lane < 6 && lane != p && w.n_hand[lane < 6 ? lane : 0] > 0);
+            c_char = __popc(m1);
+          } else if (nm == CTD_ABBOT) {
+            m1 = __ballot_sync(CTD_ALL, lane < nh && ctd_csuit(hc) == CTD_SUIT_RELIGION);
+            c_char = m1 ? __popc(m1) + 1 : 0;
+          } else if (nm == CTD_MAGICIAN) {
+            c_char = 5 + __reduce_add_sync(CTD_ALL, lane < nh ? ctd_magician_count(nh, lane + 1) : 0u);
+          } else if (nm == CTD_WARLORD) {
+            // lane = (seat, slot): seats 0..2 in m1, seats 3..5 in m2, ten building slots per seat (cities of >= 7 are immune)
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+              const int q = half * 3 + lane / 10, i = lane % 10;
+              const int nq = lane < 30 ? w.n_bld[q] : 0;
+              const bool live = lane < 30 && nq < 7 && i < nq && ctd_name(w, q) != CTD_BISHOP;
+              const int c = live ? w.bld[q][i] : 0, t = ctd_ctype(c);
+              const uint32_t grp = __match_any_sync(CTD_ALL, live ? (q << 6) | t : 1024 + lane);
+              const bool ok = live && (__ffs(grp) - 1) == lane && ctd_cost_w(t) - 1 <= gold && t != 17;
+              const uint32_t mm = __ballot_sync(CTD_ALL, ok);
+              if (half == 0) m1 = mm; else m2 = mm;
+            }
+            c_char = __popc(m1) + __popc(m2);
+          }
+        }
+        c_beg = (nm == CTD_ABBOT && !(done & CTD_DM_BEGGED)) ? 1 : 0;
+        c_wgold = (nm == CTD_WARLORD && !(done & CTD_DM_TAKE_GOLD)) ? 1 : 0;
+        c_smithy = (((own >> 21) & 1) && gold >= 2 && !(done & CTD_DM_SMITHY)) ? 1 : 0;
+        c_lab = (((own >> 22) & 1) && !(done & CTD_DM_LAB)) ? (uint32_t)nh : 0;
+        c_ms = (((own >> 25) & 1) && !(done & CTD_DM_MAGIC_SCHOOL)) ? 5 : 0;
+        if ((own >> 27) & 1)
+          c_ws = (uint32_t)(w.n_bld[0] + w.n_bld[1] + w.n_bld[2] + w.n_bld[3] + w.n_bld[4] + w.n_bld[5] - nb);
+        uint32_t m_mus = 0;
+        if (((own >> 34) & 1) && !(done & CTD_DM_MUSEUM)) m_mus = __ballot_sync(CTD_ALL, hfirst);
+        c_mus = __popc(m_mus);
+        if (nm != CTD_WARLORD) m2 = m_mus;          // m2 is free unless the Warlord uses it ...
+        else single = m_mus;                        // ... then the museum mask travels in `single`
+        total = c_build + c_char + c_beg + c_wgold + c_smithy + c_lab + c_ms + c_ws + c_mus + 1;
+      }
+    } else {
+      return ctd_choose_scalar(w, lane, buf, count_out, want);
+    }
   }
-  const int role = w.role[p];
-  if (role >= 8) return ctd_choose_scalar(w, lane, buf, count_out, want);  // None / Bewitched: rare, error paths
-  const int nm = role * 3 + w.variant[role];
-  const int rp = w.rprops[role];
-  if (rp & CTD_RP_DEAD) return ctd_choose_scalar(w, lane, buf, count_out, want);
-  if (st == 1) {  // gold_or_card_options
-    const uint32_t n = w.n_deck > 1 ? 2 : 1;
-    if (count_out) *count_out = n;
-    const uint32_t k = ctd_draw_uniform(w, lane, n, want);
-    return ctd_opt(CTD_K_GOLD_OR_CARD, p) | ctd_f_named(k == 0 ? CTD_N_GOLD : CTD_N_CARD);
+  if (count_out) *count_out = total;
+  if (total == 0) return 0;
+  // ---------------------------------------------------------------- (B) one draw
+  uint32_t k;
+  if (want >= 0) {
+    k = (uint32_t)want;
+  } else {
+    k = 0;
+    if (lane == 0) k = ctd_randbelow(w, total);
+    k = __shfl_sync(CTD_ALL, k, 0);
   }
-  if (st == 3 && !(rp & CTD_RP_BLACKMAIL)) {
-    if (count_out) *count_out = 1;
-    ctd_draw_uniform(w, lane, 1, want);
-    return ctd_opt(CTD_K_EMPTY, p);
-  }
-  if (st == 6) {
-    if (count_out) *count_out = 1;
-    ctd_draw_uniform(w, lane, 1, want);
-    return ctd_opt(w.gold[p] > 0 ? CTD_K_GRAVEYARD : CTD_K_EMPTY, p);
-  }
-  const int nb = w.n_bld[p];
-  // which building types do I own (64-bit mask by type) -- lanes OR their building's bit
-  uint32_t own_lo, own_hi;
-  {
-    uint64_t bit = 0;
-    if (lane < nb) bit = 1ull << ctd_ctype(w.bld[p][lane]);
-    own_lo = __reduce_or_sync(CTD_ALL, (uint32_t)bit);
-    own_hi = __reduce_or_sync(CTD_ALL, (uint32_t)(bit >> 32));
-  }
-  const uint64_t own = (uint64_t)own_lo | ((uint64_t)own_hi << 32);
-  if (st == 2) {  // which_card_to_keep_options
-    const int n = w.n_jd[p];
-    if (n > 32) return ctd_choose_scalar(w, lane, buf, count_out, want);
-    const int t = lane < n ? ctd_ctype(w.jd[p][lane]) : 0;
-    if ((own >> 20) & 1) {  // Library: every pair i < j, no de-duplication
-      const uint32_t cnt = (uint32_t)(n * (n - 1) / 2);
-      if (count_out) *count_out = cnt;
-      if (cnt == 0) return 0;
-      uint32_t k = ctd_draw_uniform(w, lane, cnt, want);
+  // ---------------------------------------------------------------- (C) select
+  switch (mode) {
+    case CTD_PM_ROLE_PICK: return CTD_K_ROLE_PICK | me | ctd_f_rank(ctd_kth_bit(m0, k, lane));
+    case CTD_PM_GOLD_OR_CARD: return CTD_K_GOLD_OR_CARD | me | ctd_f_named(k == 0 ? CTD_N_GOLD : CTD_N_CARD);
+    case CTD_PM_SINGLE: return single;
+    case CTD_PM_KEEP: return CTD_K_KEEP | me | ctd_f_a(ctd_ctype(w.jd[p][ctd_kth_bit(m0, k, lane)]));
+    case CTD_PM_KEEP_LIBRARY: {
+      const int n = (int)m0;
       int i = 0;
       while (k >= (uint32_t)(n - 1 - i)) { k -= (uint32_t)(n - 1 - i); ++i; }
-      const int j = i + 1 + (int)k;
-      return ctd_opt(CTD_K_KEEP, p) | ctd_f_a(ctd_ctype(w.jd[p][i])) | ctd_f_b(ctd_ctype(w.jd[p][j]));
+      return CTD_K_KEEP | me | ctd_f_a(ctd_ctype(w.jd[p][i])) | ctd_f_b(ctd_ctype(w.jd[p][i + 1 + (int)k]));
     }
-    const uint32_t m = __ballot_sync(CTD_ALL, ctd_first_of_type(lane, n, t));
-    const uint32_t cnt = __popc(m);
-    if (count_out) *count_out = cnt;
-    if (cnt == 0) return 0;
-    const uint32_t k = ctd_draw_uniform(w, lane, cnt, want);
-    return ctd_opt(CTD_K_KEEP, p) | ctd_f_a(ctd_ctype(w.jd[p][ctd_kth_bit(m, k)]));
+    case CTD_PM_WITCH: return CTD_K_BEWITCHING | me | ctd_f_rank(1 + (int)k);
+    default: break;
   }
-  if (st != 5) return ctd_choose_scalar(w, lane, buf, count_out, want);
-  if (nm == CTD_WITCH) {  // witch_options: ranks 1..7
-    if (count_out) *count_out = 7;
-    const uint32_t k = ctd_draw_uniform(w, lane, 7, want);
-    return ctd_opt(CTD_K_BEWITCHING, p) | ctd_f_rank(1 + (int)k);
-  }
-  if (rp & CTD_RP_POSSESSED) {
-    if (count_out) *count_out = 1;
-    ctd_draw_uniform(w, lane, 1, want);
-    return ctd_opt(CTD_K_FINISH, p) | ctd_f_next_witch(1) | ctd_f_crown(nm == CTD_KING || nm == CTD_PATRICIAN);
-  }
-  // ---------------------------------------------------------------- main_round_options, in the reference's order
-  const int nh = w.n_hand[p];
-  const bool lighthouse = ((own >> 29) & 1) && (w.pflags[p] & CTD_PF_LIGHTHOUSE);
-  const bool tier_ab = nm == CTD_SPY || nm == CTD_WIZARD || nm == CTD_KING || nm == CTD_ABBOT || nm == CTD_ALCHEMIST ||
-                       nm == CTD_NAVIGATOR || nm == CTD_WARLORD || nm == CTD_ASSASSIN || nm == CTD_THIEF ||
-                       nm == CTD_MAGICIAN || nm == CTD_BISHOP || nm == CTD_MERCHANT || nm == CTD_ARCHITECT;
-  if (nh > 32 || lighthouse || !tier_ab) return ctd_choose_scalar(w, lane, buf, count_out, want);
-  const int gold = w.gold[p];
-  const int done = w.done;
-  const int hc = lane < nh ? w.hand[p][lane] : 0;
-  const int ht = ctd_ctype(hc);
-  const bool hfirst = ctd_first_of_type(lane, nh, ht);
-  // 1. builds
-  uint32_t m_build = 0;
-  if (w.n_trade + w.n_nontrade < ctd_build_limit(nm)) {
-    const bool factory = (own >> 35) & 1;
-    m_build = __ballot_sync(CTD_ALL, hfirst && ctd_build_cost(hc, factory) <= gold);
-  }
-  const uint32_t c_build = __popc(m_build);
-  // 2. character
-  uint32_t c_char = 0, m_char = 0, m_war[6] = {0, 0, 0, 0, 0, 0};
-  if (!(done & CTD_DM_CHARACTER)) {
-    switch (nm) {
-      case CTD_ASSASSIN: c_char = 7; break;
-      case CTD_THIEF: c_char = 6; break;
-      case CTD_SPY: c_char = 25; break;
-      case CTD_MAGICIAN: {
-        uint32_t c = lane < nh ? ctd_magician_count(nh, lane + 1) : 0;
-        c_char = 5 + __reduce_add_sync(CTD_ALL, c);
-        break;
-      }
-      case CTD_WIZARD:
-        m_char = __ballot_sync(CTD_ALL, lane < 6 && lane != p && w.n_hand[lane < 6 ? lane : 0] > 0);
-        c_char = __popc(m_char);
-        break;
-      case CTD_KING: case CTD_BISHOP: case CTD_MERCHANT: case CTD_ARCHITECT: c_char = 1; break;
-      case CTD_ABBOT: {
-        m_char = __ballot_sync(CTD_ALL, lane < nh && ctd_csuit(hc) == CTD_SUIT_RELIGION);
-        const uint32_t n = __popc(m_char);
-        c_char = n > 0 ? n + 1 : 0;
-        break;
-      }
-      case CTD_NAVIGATOR: c_char = 2; break;
-      case CTD_WARLORD:
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-          const int nq = w.n_bld[q];
-          if (nq >= 7 || ctd_name(w, q) == CTD_BISHOP) continue;  // uniform per q
-          const int c = lane < nq ? w.bld[q][lane] : 0;
-          const int t = ctd_ctype(c);
-          const bool first = ctd_first_of_type(lane, nq, t);
-          m_war[q] = __ballot_sync(CTD_ALL, first && ctd_ccost(c) - 1 <= gold && t != 17);
-          c_char += __popc(m_war[q]);
-        }
-        break;
-      default: break;
-    }
-  }
-  const uint32_t c_beg = (nm == CTD_ABBOT && !(done & CTD_DM_BEGGED)) ? 1 : 0;
-  const uint32_t c_war_gold = (nm == CTD_WARLORD && !(done & CTD_DM_TAKE_GOLD)) ? 1 : 0;
-  // 3..8 unique buildings
-  const uint32_t c_smithy = (((own >> 21) & 1) && gold >= 2 && !(done & CTD_DM_SMITHY)) ? 1 : 0;
-  const uint32_t c_lab = (((own >> 22) & 1) && !(done & CTD_DM_LAB)) ? (uint32_t)nh : 0;
-  const uint32_t c_ms = (((own >> 25) & 1) && !(done & CTD_DM_MAGIC_SCHOOL)) ? 5 : 0;
-  uint32_t c_ws = 0;
-  if ((own >> 27) & 1)
-    for (int q = 0; q < 6; ++q) c_ws += q != p ? w.n_bld[q] : 0;
-  uint32_t m_mus = 0;
-  if (((own >> 34) & 1) && !(done & CTD_DM_MUSEUM)) m_mus = __ballot_sync(CTD_ALL, hfirst);
-  const uint32_t c_mus = __popc(m_mus);
-  const uint32_t total = c_build + c_char + c_beg + c_war_gold + c_smithy + c_lab + c_ms + c_ws + c_mus + 1;
-  if (count_out) *count_out = total;
-  uint32_t k = ctd_draw_uniform(w, lane, total, want);
-  // ---------------------------------------------------------------- select the k-th
   if (k < c_build) {
-    const int c = w.hand[p][ctd_kth_bit(m_build, k)], t = ctd_ctype(c);
+    const int t = ctd_ctype(w.hand[p][ctd_kth_bit(m0, k, lane)]);
     const int rep = (((own >> t) & 1) && !w.replicas[p]) ? w.replicas[p] + 1 : 0;
-    return ctd_opt(CTD_K_BUILD, p) | ctd_f_a(t) | ctd_f_replica(rep);
+    return CTD_K_BUILD | me | ctd_f_a(t) | ctd_f_replica(rep);
   }
   k -= c_build;
   if (k < c_char) {
+    int q = (int)k / 5;            // Spy: five suits per other seat; Magician swaps: one per other seat
+    q += q >= p ? 1 : 0;
+    int q1 = (int)k;
+    q1 += q1 >= p ? 1 : 0;
     switch (nm) {
-      case CTD_ASSASSIN: return ctd_opt(CTD_K_ASSASSINATION, p) | ctd_f_rank(1 + (int)k);
-      case CTD_THIEF: return ctd_opt(CTD_K_STEAL, p) | ctd_f_rank(2 + (int)k);
-      case CTD_SPY: {
-        int q = (int)k / 5;
-        q += q >= p ? 1 : 0;
-        return ctd_opt(CTD_K_SPY, p) | ctd_f_target(q) | ctd_f_named(CTD_N_TRADE + (int)k % 5);
-      }
+      case CTD_ASSASSIN: return CTD_K_ASSASSINATION | me | ctd_f_rank(1 + (int)k);
+      case CTD_THIEF: return CTD_K_STEAL | me | ctd_f_rank(2 + (int)k);
+      case CTD_SPY: return CTD_K_SPY | me | ctd_f_target(q) | ctd_f_named(CTD_N_TRADE + (int)k % 5);
       case CTD_MAGICIAN: {
-        if (k < 5) {
-          int q = (int)k;
-          q += q >= p ? 1 : 0;
-          return ctd_opt(CTD_K_MAGIC_HAND_CHANGE, p) | ctd_f_target(q);
-        }
+        if (k < 5) return CTD_K_MAGIC_HAND_CHANGE | me | ctd_f_target(q1);
         k -= 5;  // every discard_and_draw option has the same effect; recover (r, j) for the descriptor
         int r = 1;
         for (; r <= nh; ++r) {
@@ -237,46 +235,50 @@ __device__ __noinline__ uint64_t ctd_warp_choose(CtdWork& w, int lane, uint64_t*
           if (k < c) break;
           k -= c;
         }
-        return ctd_opt(CTD_K_DISCARD_AND_DRAW, p) | ctd_f_r(r) | ctd_f_j(k);
+        return CTD_K_DISCARD_AND_DRAW | me | ctd_f_r(r) | ctd_f_j(k);
       }
-      case CTD_WIZARD: return ctd_opt(CTD_K_LOOK_AT_HAND, p) | ctd_f_target(ctd_kth_bit(m_char, k));
-      case CTD_KING: return ctd_opt(CTD_K_TAKE_CROWN_KING, p);
-      case CTD_BISHOP: return ctd_opt(CTD_K_BISHOP, p);
-      case CTD_MERCHANT: return ctd_opt(CTD_K_MERCHANT, p);
-      case CTD_ARCHITECT: return ctd_opt(CTD_K_ARCHITECT, p);
-      case CTD_ABBOT: return ctd_opt(CTD_K_ABBOT, p) | ctd_f_count((int)k) | ctd_f_r((int)__popc(m_char));
-      case CTD_NAVIGATOR: return ctd_opt(CTD_K_NAVIGATOR, p) | ctd_f_named(k == 0 ? CTD_N_4GOLD : CTD_N_4CARD);
-      default:  // CTD_WARLORD
-        for (int q = 0; q < 6; ++q) {
-          const uint32_t c = __popc(m_war[q]);
-          if (k < c) return ctd_opt(CTD_K_WARLORD, p) | ctd_f_target(q) | ctd_f_a(ctd_ctype(w.bld[q][ctd_kth_bit(m_war[q], k)]));
-          k -= c;
-        }
-        return 0;
+      case CTD_WIZARD: return CTD_K_LOOK_AT_HAND | me | ctd_f_target(ctd_kth_bit(m1, k, lane));
+      case CTD_KING: return CTD_K_TAKE_CROWN_KING | me;
+      case CTD_BISHOP: return CTD_K_BISHOP | me;
+      case CTD_MERCHANT: return CTD_K_MERCHANT | me;
+      case CTD_ARCHITECT: return CTD_K_ARCHITECT | me;
+      case CTD_ABBOT: return CTD_K_ABBOT | me | ctd_f_count((int)k) | ctd_f_r((int)__popc(m1));
+      case CTD_NAVIGATOR: return CTD_K_NAVIGATOR | me | ctd_f_named(k == 0 ? CTD_N_4GOLD : CTD_N_4CARD);
+      default: {  // CTD_WARLORD: (seat, slot) lanes, seats 0..2 then 3..5
+        const uint32_t c1 = __popc(m1);
+        const uint32_t mm = k < c1 ? m1 : m2;
+        const int l = ctd_kth_bit(mm, k < c1 ? k : k - c1, lane);
+        const int q2 = (k < c1 ? 0 : 3) + l / 10;
+        return CTD_K_WARLORD | me | ctd_f_target(q2) | ctd_f_a(ctd_ctype(w.bld[q2][l % 10]));
+      }
     }
   }
   k -= c_char;
-  if (k < c_beg) return ctd_opt(CTD_K_ABBOT_BEG, p);
+  if (k < c_beg) return CTD_K_ABBOT_BEG | me;
   k -= c_beg;
-  if (k < c_war_gold) return ctd_opt(CTD_K_TAKE_GOLD_WAR, p);
-  k -= c_war_gold;
-  if (k < c_smithy) return ctd_opt(CTD_K_SMITHY, p);
+  if (k < c_wgold) return CTD_K_TAKE_GOLD_WAR | me;
+  k -= c_wgold;
+  if (k < c_smithy) return CTD_K_SMITHY | me;
   k -= c_smithy;
-  if (k < c_lab) return ctd_opt(CTD_K_LAB, p) | ctd_f_a(ctd_ctype(w.hand[p][k]));
+  if (k < c_lab) return CTD_K_LAB | me | ctd_f_a(ctd_ctype(w.hand[p][k]));
   k -= c_lab;
-  if (k < c_ms) return ctd_opt(CTD_K_MAGIC_SCHOOL, p) | ctd_f_named(CTD_N_TRADE + (int)k);
+  if (k < c_ms) return CTD_K_MAGIC_SCHOOL | me | ctd_f_named(CTD_N_TRADE + (int)k);
   k -= c_ms;
   if (k < c_ws) {
-    for (int q = 0; q < 6; ++q) {
+    int q = 0;
+    for (;; ++q) {
       if (q == p) continue;
       const uint32_t c = w.n_bld[q];
-      if (k < c) return ctd_opt(CTD_K_WEAPON_STORAGE, p) | ctd_f_target(q) | ctd_f_a(ctd_ctype(w.bld[q][k]));
+      if (k < c) break;
       k -= c;
     }
-    return 0;
+    return CTD_K_WEAPON_STORAGE | me | ctd_f_target(q) | ctd_f_a(ctd_ctype(w.bld[q][k]));
   }
   k -= c_ws;
-  if (k < c_mus) return ctd_opt(CTD_K_MUSEUM, p) | ctd_f_a(ctd_ctype(w.hand[p][ctd_kth_bit(m_mus, k)]));
-  return ctd_opt(CTD_K_FINISH, p);
+  if (k < c_mus) {
+    const uint32_t m_mus = nm != CTD_WARLORD ? m2 : (uint32_t)single;
+    return CTD_K_MUSEUM | me | ctd_f_a(ctd_ctype(w.hand[p][ctd_kth_bit(m_mus, k, lane)]));
+  }
+  return CTD_K_FINISH | me;
 }
 #endif
