@@ -237,7 +237,7 @@ def main():
     e2e_steps = 0
     for k in range(args.steps):
         out = eng.playout(G, seed=SEED, first_gid=gid0(k), ruleset=args.ruleset, outputs=True)
-        e2e_steps += int(out["steps"].astype("int64").sum())
+        e2e_steps += out["stats"]["steps"]          # per-game winner / scores / steps are in out[...] on the host
     barrier()
     e2e_wall = time.perf_counter() - t1
     clocks = sampler.stop() if rank == 0 else None

@@ -331,7 +331,7 @@ CTD_HD CTD_NI inline int ctd_take_like(uint8_t* a, uint8_t& n, int t) {
     if (ctd_ctype(a[i]) == t) return ctd_remove_at(a, n, i);
   return t;
 }
-CTD_HD inline void ctd_append(CtdWork& w, uint8_t* a, uint8_t& n, int cap, int c) {
+CTD_HD CTD_NI inline void ctd_append(CtdWork& w, uint8_t* a, uint8_t& n, int cap, int c) {
   if (n >= cap) { w.err |= CTD_ERR_OVERFLOW; return; }
   a[n++] = (uint8_t)c;
 }

@@ -669,6 +669,8 @@ struct ctd_engine {
   float *d_h1, *d_h2, *d_h3;
   int* d_tc_err;
   int value_backend;  // 0 = fp32 CUDA cores (ctd_k_value_mlp), 1 = tcgen05 split-TF32 (ctd_k_linear_tc)
+  uint8_t* h_pinned;  // pinned host staging for result copies
+  size_t pinned_bytes;
   uint8_t* d_one;  // single-game staging: state | know6 | used_cards | count | winner | opts
   char err[256];
 };
@@ -690,6 +692,15 @@ static ctd_status ctd_scratch(ctd_engine* e, size_t bytes) {
   e->scratch_bytes = 0;
   CTD_CUDA(e, cudaMalloc(&e->d_scratch, bytes));
   e->scratch_bytes = bytes;
+  return CTD_OK;
+}
+static ctd_status ctd_pinned(ctd_engine* e, size_t bytes) {
+  if (bytes <= e->pinned_bytes) return CTD_OK;
+  if (e->h_pinned) CTD_CUDA(e, cudaFreeHost(e->h_pinned));
+  e->h_pinned = nullptr;
+  e->pinned_bytes = 0;
+  CTD_CUDA(e, cudaHostAlloc((void**)&e->h_pinned, bytes, cudaHostAllocDefault));
+  e->pinned_bytes = bytes;
   return CTD_OK;
 }
 static CtdTapes ctd_tapes(const ctd_engine* e) { return CtdTapes{e->d_tape, e->d_tape_off, e->n_tapes}; }
@@ -741,6 +752,7 @@ void ctd_destroy(ctd_engine* e) {
   if (e->d_pending) cudaFree(e->d_pending);
   if (e->d_n_pending) cudaFree(e->d_n_pending);
   if (e->d_one) cudaFree(e->d_one);
+  if (e->h_pinned) cudaFreeHost(e->h_pinned);
   if (e->d_model_tc) cudaFree(e->d_model_tc);
   if (e->d_h1) cudaFree(e->d_h1);
   if (e->d_h2) cudaFree(e->d_h2);
@@ -944,12 +956,15 @@ ctd_status ctd_playout(ctd_engine* e, uint64_t n_games, uint64_t seed, uint64_t 
   a.winner = (int8_t*)e->d_scratch;
   a.points6 = (int8_t*)e->d_scratch + wb;
   a.steps = (uint16_t*)((char*)e->d_scratch + wb + pb);
+  s = ctd_pinned(e, wb + pb + sb);   // results come back through pinned host memory in one DMA
+  if (s != CTD_OK) return s;
   s = ctd_playout_launch(e, a, stats, nullptr);
   if (s != CTD_OK) return s;
-  if (winner) CTD_CUDA(e, cudaMemcpyAsync(winner, a.winner, n_games, cudaMemcpyDeviceToHost, e->stream));
-  if (points6) CTD_CUDA(e, cudaMemcpyAsync(points6, a.points6, n_games * 6, cudaMemcpyDeviceToHost, e->stream));
-  if (steps) CTD_CUDA(e, cudaMemcpyAsync(steps, a.steps, sb, cudaMemcpyDeviceToHost, e->stream));
+  CTD_CUDA(e, cudaMemcpyAsync(e->h_pinned, e->d_scratch, wb + pb + sb, cudaMemcpyDeviceToHost, e->stream));
   CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (winner) memcpy(winner, e->h_pinned, n_games);
+  if (points6) memcpy(points6, e->h_pinned + wb, n_games * 6);
+  if (steps) memcpy(steps, e->h_pinned + wb + pb, sb);
   return CTD_OK;
 }
 
