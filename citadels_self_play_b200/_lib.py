@@ -53,6 +53,8 @@ SIGNATURES = {
     "ctd_encode": (_i, [c_void, _u32, c_void]),
     "ctd_mccfr_pred": (_i, [c_void, _u32, _u64, _u32, _u32, _i, ctypes.c_float, c_void, c_void,
                             ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_u32)]),
+    "ctd_mccfr_targets": (_i, [c_void, _u32, _u64, _u32, _i, ctypes.c_double, ctypes.POINTER(_u32), ctypes.POINTER(_u32),
+                               c_void, c_void, c_void, c_void]),
     "ctd_mccfr": (_i, [c_void, _u32, _u64, _u32, _i, c_void, c_void, ctypes.POINTER(ctypes.c_float)]),
 }
 

@@ -394,6 +394,93 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) ctd_k_mccfr(C
   }
 }
 
+// ------------------------------------------------------------------------------------------ training targets
+// CFRNode.get_all_targets / build_train_targets (algorithms/deep_mccfr.py:258-274, :321-345): depth-first pre-order
+// over the tree, one record per node that has children and node_value.sum() >= threshold.  Role-pick nodes are
+// encoded from the viewpoint of a random seat i = randint(0, 5) (Philox stream 3 of the tree, one draw per emitted
+// role-pick node) and export row i of their regret matrix.
+struct CtdTargetArgs {
+  uint32_t n_roots;
+  const uint8_t* trees;
+  size_t tree_stride;
+  uint32_t max_nodes, child_cap;
+  uint64_t seed;
+  double threshold;
+  int fill;                 // 0: count only; 1: write records
+  uint32_t* n_targets;      // [n_roots]
+  uint32_t* n_options;      // [n_roots] sum of K over the tree's targets
+  const uint32_t* rec_off;  // [n_roots] (fill) first record of the tree
+  const uint32_t* opt_off;  // [n_roots] (fill) first option slot of the tree
+  float* feat;              // [records][CTD_FEATURES_PAD]
+  ctd_target_meta* meta;    // [records]
+  ctd_option* options;      // [option slots]
+  double* regrets;          // [option slots]
+};
+
+__global__ void __launch_bounds__(CTD_BLOCK) ctd_k_targets(CtdTargetArgs a) {
+  __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
+  __shared__ CtdKnow knows[CTD_WARPS_PER_BLOCK];
+  __shared__ __align__(16) ctd_state tstage[CTD_WARPS_PER_BLOCK];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t t = blockIdx.x * CTD_WARPS_PER_BLOCK + wib;
+  if (t >= a.n_roots || lane != 0) return;
+  CtdTree T = ctd_tree_at(const_cast<uint8_t*>(a.trees) + t * a.tree_stride, a.max_nodes, a.child_cap);
+  T.w = &works[wib]; T.kn = &knows[wib]; T.stage = &tstage[wib];
+  const CtdTreeHdr& h = *T.hdr;
+  uint32_t nrec = 0, nopt = 0, rp_draws = 0;
+  if (h.n_nodes != 0 && !(h.status & CTD_TREE_TERMINAL_ROOT)) {
+    int cur = 0;
+    for (;;) {
+      const CtdNode& n = T.nodes[cur];
+      const uint32_t K = n.n_children;
+      double vs = 0.0;
+      for (int i = 0; i < 6; ++i) vs += n.V[i];
+      if (K != 0 && vs >= a.threshold) {
+        const bool rp = n.flags & CTD_NF_ROLE_PICK;
+        uint32_t seat = n.game.player;
+        if (rp) {
+          uint32_t r[4];
+          ctd_philox(rp_draws >> 2, 3u, (uint32_t)h.gid, (uint32_t)(h.gid >> 32), (uint32_t)a.seed, (uint32_t)(a.seed >> 32), r);
+          seat = (uint32_t)(((uint64_t)r[rp_draws & 3] * 6) >> 32);
+          ++rp_draws;
+        }
+        if (a.fill) {
+          const uint32_t rec = a.rec_off[t] + nrec, ko = a.opt_off[t] + nopt;
+          ctd_node_load(T, n);
+          ctd_encode_game(*T.w, *T.kn, (int)seat, a.feat + (size_t)rec * CTD_FEATURES_PAD);
+          ctd_target_meta& m = a.meta[rec];
+          m.tree = t; m.node = (uint32_t)cur; m.n_options = K; m.option_offset = ko; m.seat = seat; m.role_pick = rp ? 1 : 0;
+          for (int i = 0; i < 6; ++i) m.node_value[i] = n.V[i];
+          const double* R = ctd_R(T, n) + (rp ? seat * 10 : 0);
+          double rs = 0.0;
+          for (uint32_t i = 0; i < K; ++i) rs += R[i];
+          for (uint32_t i = 0; i < K; ++i) {
+            a.options[ko + i] = T.children[n.child_off + i].desc;
+            a.regrets[ko + i] = rs == 0.0 ? 1.0 : R[i];   // all-zero regrets are exported as ones (:333-334, :342-343)
+          }
+        }
+        ++nrec;
+        nopt += K;
+      }
+      // pre-order successor: first child, else next sibling of the nearest ancestor that has one
+      if (K != 0) { cur = (int)T.children[n.child_off].node; continue; }
+      int c = cur;
+      for (;;) {
+        const int par = T.nodes[c].parent;
+        if (par < 0) { c = -1; break; }
+        const CtdNode& pn = T.nodes[par];
+        uint32_t i = 0;
+        while (i < pn.n_children && (int)T.children[pn.child_off + i].node != c) ++i;
+        if (i + 1 < pn.n_children) { c = (int)T.children[pn.child_off + i + 1].node; break; }
+        c = par;
+      }
+      if (c < 0) break;
+      cur = c;
+    }
+  }
+  if (!a.fill) { a.n_targets[t] = nrec; a.n_options[t] = nopt; }
+}
+
 // ------------------------------------------------------------------------------------------ single-game entry points
 // The facade's Game object owns its record and the knowledge of all six observers on the host; these kernels run
 // one warp on device copies of them (op 0: new game, 1: enumerate, 2: step).
@@ -1185,6 +1272,74 @@ ctd_status ctd_game_step(ctd_engine* e, uint64_t seed, ctd_state* state, void* k
   CTD_CUDA(e, cudaMemcpyAsync(winner, a.winner, 1, cudaMemcpyDeviceToHost, e->stream));
   CTD_CUDA(e, cudaStreamSynchronize(e->stream));
   return CTD_OK;
+}
+
+// CFRNode.get_all_targets over the trees of the last ctd_mccfr / ctd_mccfr_pred call (they stay on the device).
+// Call once with all output pointers NULL to size the buffers (*n_records, *n_option_slots), then again to fill.
+static ctd_status ctd_pred_buffers(ctd_engine* e);
+ctd_status ctd_mccfr_targets(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32_t iterations, int ruleset, double threshold,
+                             uint32_t* n_records, uint32_t* n_option_slots, float* features, ctd_target_meta* meta,
+                             ctd_option* options, double* regrets) {
+  if (!e || !n_records || !n_option_slots || n_roots > e->capacity || !e->d_trees) return CTD_EARG;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  uint32_t mn, cc, ac;
+  uint64_t stride;
+  ctd_mccfr_tree_shape(iterations, ruleset, &mn, &cc, &ac, &stride);
+  if ((size_t)stride * n_roots > e->trees_bytes) return CTD_EARG;
+  ctd_status s = ctd_pred_buffers(e);
+  if (s != CTD_OK) return s;
+  // counts
+  size_t cb = (size_t)n_roots * sizeof(uint32_t);
+  uint32_t* d_cnt = nullptr;
+  CTD_CUDA(e, cudaMalloc((void**)&d_cnt, 4 * cb));
+  CtdTargetArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_roots = n_roots; a.trees = e->d_trees; a.tree_stride = stride; a.max_nodes = mn; a.child_cap = cc; a.seed = seed;
+  a.threshold = threshold; a.n_targets = d_cnt; a.n_options = d_cnt + n_roots;
+  ctd_k_targets<<<ctd_blocks(n_roots), CTD_BLOCK, 0, e->stream>>>(a);
+  e->launches++;
+  uint32_t* h_cnt = new (std::nothrow) uint32_t[4 * (size_t)n_roots];
+  if (!h_cnt) { cudaFree(d_cnt); return CTD_ENOMEM; }
+  cudaError_t c = cudaMemcpyAsync(h_cnt, d_cnt, 2 * cb, cudaMemcpyDeviceToHost, e->stream);
+  if (c == cudaSuccess) c = cudaStreamSynchronize(e->stream);
+  if (c != cudaSuccess) { delete[] h_cnt; cudaFree(d_cnt); return ctd_fail(e, c, "ctd_k_targets count"); }
+  uint32_t nrec = 0, nopt = 0;
+  for (uint32_t t = 0; t < n_roots; ++t) {
+    h_cnt[2 * n_roots + t] = nrec; h_cnt[3 * n_roots + t] = nopt;
+    nrec += h_cnt[t]; nopt += h_cnt[n_roots + t];
+  }
+  const bool fill = features && meta && options && regrets;
+  if (fill && (nrec > *n_records || nopt > *n_option_slots)) { delete[] h_cnt; cudaFree(d_cnt); return CTD_ECAP; }
+  *n_records = nrec; *n_option_slots = nopt;
+  ctd_status rs = CTD_OK;
+  if (fill && nrec != 0) {
+    float* d_feat = nullptr; ctd_target_meta* d_meta = nullptr; ctd_option* d_opt = nullptr; double* d_reg = nullptr;
+    c = cudaMemcpyAsync(d_cnt + 2 * n_roots, h_cnt + 2 * n_roots, 2 * cb, cudaMemcpyHostToDevice, e->stream);
+    if (c == cudaSuccess) c = cudaMalloc((void**)&d_feat, (size_t)nrec * CTD_FEATURES_PAD * sizeof(float));
+    if (c == cudaSuccess) c = cudaMalloc((void**)&d_meta, (size_t)nrec * sizeof(ctd_target_meta));
+    if (c == cudaSuccess) c = cudaMalloc((void**)&d_opt, (size_t)(nopt + 1) * sizeof(ctd_option));
+    if (c == cudaSuccess) c = cudaMalloc((void**)&d_reg, (size_t)(nopt + 1) * sizeof(double));
+    if (c == cudaSuccess) {
+      a.fill = 1; a.rec_off = d_cnt + 2 * n_roots; a.opt_off = d_cnt + 3 * n_roots;
+      a.feat = d_feat; a.meta = d_meta; a.options = d_opt; a.regrets = d_reg;
+      ctd_k_targets<<<ctd_blocks(n_roots), CTD_BLOCK, 0, e->stream>>>(a);
+      e->launches++;
+      c = cudaGetLastError();
+    }
+    if (c == cudaSuccess) c = cudaMemcpyAsync(features, d_feat, (size_t)nrec * CTD_FEATURES_PAD * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
+    if (c == cudaSuccess) c = cudaMemcpyAsync(meta, d_meta, (size_t)nrec * sizeof(ctd_target_meta), cudaMemcpyDeviceToHost, e->stream);
+    if (c == cudaSuccess) c = cudaMemcpyAsync(options, d_opt, (size_t)nopt * sizeof(ctd_option), cudaMemcpyDeviceToHost, e->stream);
+    if (c == cudaSuccess) c = cudaMemcpyAsync(regrets, d_reg, (size_t)nopt * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+    if (c == cudaSuccess) c = cudaStreamSynchronize(e->stream);
+    if (d_feat) cudaFree(d_feat);
+    if (d_meta) cudaFree(d_meta);
+    if (d_opt) cudaFree(d_opt);
+    if (d_reg) cudaFree(d_reg);
+    if (c != cudaSuccess) rs = ctd_fail(e, c, "ctd_k_targets fill");
+  }
+  delete[] h_cnt;
+  cudaFree(d_cnt);
+  return rs;
 }
 
 static ctd_status ctd_pred_buffers(ctd_engine* e) {

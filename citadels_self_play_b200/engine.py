@@ -4,7 +4,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from .layout import STATE_BYTES, KNOW_BYTES, MCCFR_RESULT_DTYPE, TreeView
+from .layout import STATE_BYTES, KNOW_BYTES, MCCFR_RESULT_DTYPE, TARGET_META_DTYPE, TreeView, encode_options
 
 RULESET_PRESET, RULESET_CLASSIC = 0, 1
 DEFAULT_SEED = 0xC17ADE15
@@ -210,6 +210,35 @@ class Engine:
         if trees:
             views = [TreeView(buf[i], mn, cc, ac) for i in range(n_roots)]
         return dict(results=res, trees=views, kernel_ms=ms.value, waves=waves.value)
+
+    def mccfr_targets(self, n_roots, iterations=200, seed=DEFAULT_SEED, ruleset=RULESET_PRESET, threshold=15.0):
+        """CFRNode.get_all_targets() for every tree of the last mccfr()/mccfr_pred() call with the same arguments.
+        -> dict(features[R,418] f32, meta[R], options[S] u64, regrets[S] f64)."""
+        nr, ns = ctypes.c_uint32(0), ctypes.c_uint32(0)
+        self._check(self._lib.ctd_mccfr_targets(self._h, n_roots, seed, iterations, ruleset, threshold, ctypes.byref(nr),
+                                                ctypes.byref(ns), None, None, None, None), "ctd_mccfr_targets")
+        feats = np.zeros((nr.value, 448), dtype=np.float32)
+        meta = np.zeros(nr.value, dtype=TARGET_META_DTYPE)
+        opts = np.zeros(max(ns.value, 1), dtype=np.uint64)
+        regs = np.zeros(max(ns.value, 1), dtype=np.float64)
+        if nr.value:
+            self._check(self._lib.ctd_mccfr_targets(self._h, n_roots, seed, iterations, ruleset, threshold, ctypes.byref(nr),
+                                                    ctypes.byref(ns), feats.ctypes.data, meta.ctypes.data, opts.ctypes.data,
+                                                    regs.ctypes.data), "ctd_mccfr_targets")
+        return dict(features=feats[:, :418], meta=meta, options=opts[:ns.value], regrets=regs[:ns.value])
+
+    @staticmethod
+    def targets_as_tuples(t):
+        """The reference's pickle format (generate_test_data.py:25, train_from_scratch.py): a list of
+        (model_input float32[418], options_input float32[1,K,131], node_value float64[6], decision_dist float64[K])."""
+        import torch
+        out = []
+        for i, m in enumerate(t["meta"]):
+            o, k = int(m["option_offset"]), int(m["n_options"])
+            out.append((torch.from_numpy(t["features"][i].copy()),
+                        torch.from_numpy(encode_options(t["options"][o:o + k])).unsqueeze(0),
+                        torch.from_numpy(np.array(m["node_value"])), torch.from_numpy(t["regrets"][o:o + k].copy())))
+        return out
 
     def sync(self):
         self._check(self._lib.ctd_sync(self._h), "ctd_sync")

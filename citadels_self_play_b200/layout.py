@@ -114,3 +114,34 @@ MCCFR_RESULT_DTYPE = np.dtype([("status", np.uint32), ("n_nodes", np.uint32), ("
                                ("node_value", np.float64, 6), ("winning_probabilities", np.float64, 6),
                                ("options", np.uint64, 128), ("cumulative_regrets", np.float64, 180),
                                ("strategy", np.float64, 180), ("cumulative_strategy", np.float64, 180)])
+
+TARGET_META_DTYPE = np.dtype([("tree", np.uint32), ("node", np.uint32), ("n_options", np.uint32), ("option_offset", np.uint32),
+                              ("seat", np.uint32), ("role_pick", np.uint32), ("node_value", np.float64, 6)])
+assert TARGET_META_DTYPE.itemsize == 72
+
+
+def encode_options(descs):
+    """option.encode_option (game/option.py:52-115) for a list of descriptors -> float32[K, 131].
+    Bit layout: [0,47) kind, [47,53) perpetrator, [53,59) target, [60,68) role rank, [76,89) named choice,
+    [89,129) card type, [129] replica, [130] number of "card" entries (Abbot).  The reference's elif chain means a
+    `target` attribute suppresses everything after it, and tuple choices (Library pairs) set no card bits."""
+    out = np.zeros((len(descs), 131), dtype=np.float32)
+    for i, d in enumerate(descs):
+        f = opt_fields(d)
+        name = KIND_NAMES[f["kind"]]
+        out[i, f["kind"]] = 1
+        out[i, f["perp"] + 47] = 1
+        if f["target"] >= 0:
+            out[i, f["target"] + 53] = 1
+        elif name == "role_pick":
+            out[i, f["rank"] + 60] = 1
+        elif f["named"] >= 0:
+            out[i, f["named"] + 76] = 1
+        elif name in ("laboratory_choice", "lighthouse_choice", "museum_choice", "build"):
+            out[i, f["a"] + 89] = 1
+        elif name == "which_card_to_keep":
+            if f["b"] < 0:
+                out[i, f["a"] + 89] = 1
+        elif name == "abbot_gold_or_card":
+            out[i, 130] = f["count"]
+    return out

@@ -242,6 +242,25 @@ ctd_status ctd_mccfr_pred(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32
                           float reward_weight, ctd_mccfr_result* results, void* trees_out, float* elapsed_ms,
                           uint32_t* waves_out);
 
+/* ---- training targets (algorithms/deep_mccfr.py:258-274, :321-345; tuple format generate_test_data.py:25) ---- */
+typedef struct ctd_target_meta {
+  uint32_t tree;           /* root index */
+  uint32_t node;           /* node index inside the tree block */
+  uint32_t n_options;      /* K = len(node.children) */
+  uint32_t option_offset;  /* first of the K entries in options[] / regrets[] */
+  uint32_t seat;           /* gamestate.player_id the state was encoded with (random seat for role-pick nodes) */
+  uint32_t role_pick;
+  double node_value[6];    /* target_node_value */
+} ctd_target_meta;
+/* CFRNode.get_all_targets() over the trees left on the device by the last ctd_mccfr / ctd_mccfr_pred call with the
+ * same (n_roots, iterations, ruleset): one record per node with children and node_value.sum() >= threshold (the
+ * reference always uses 15, algorithms/deep_mccfr.py:268,:321), depth-first pre-order per tree.  Call once with the
+ * four output pointers NULL to learn the sizes, then with buffers of *n_records rows of 448 floats / metas and
+ * *n_option_slots descriptors / doubles (regrets: row `seat` of a role-pick node's matrix; all-zero rows become ones). */
+ctd_status ctd_mccfr_targets(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32_t iterations, int ruleset, double threshold,
+                             uint32_t* n_records, uint32_t* n_option_slots, float* features, ctd_target_meta* meta,
+                             ctd_option* options, double* regrets);
+
 /* number of kernels this engine has launched so far */
 uint64_t ctd_launch_count(const ctd_engine* e);
 

@@ -274,3 +274,49 @@ def run_from_root(root_rec, know_blob, used_cards, seed, gid, iterations):
     n = Node(g, g.player)
     n.cfr_train(iterations)
     return n
+
+
+# ------------------------------------------------------------------ training targets (algorithms/deep_mccfr.py:258-345)
+def encode_option(d):
+    """option.encode_option (game/option.py:52-115) from a descriptor -> list of 131 numbers."""
+    e = [0.0] * 131
+    k, name = O.d_kind(d), O.KIND_NAMES[O.d_kind(d)]
+    e[k] = 1.0
+    e[O.d_perp(d) + 47] = 1.0
+    if O.d_target(d) >= 0:                       # "target" in attributes
+        e[O.d_target(d) + 53] = 1.0
+    elif name == "role_pick":                    # choice is a role name
+        e[O.d_rank(d) + 60] = 1.0
+    elif O.d_named(d) >= 0:                      # choice is one of the 13 named strings
+        e[O.d_named(d) + 76] = 1.0
+    elif name in ("laboratory_choice", "lighthouse_choice", "museum_choice"):   # choice is a Card
+        e[O.d_a(d) + 89] = 1.0
+    elif name == "which_card_to_keep":           # choice is a list [card]; Library pairs are tuples -> no bits
+        if O.d_b(d) < 0:
+            e[O.d_a(d) + 89] = 1.0
+    elif name == "build":                        # built_card
+        e[O.d_a(d) + 89] = 1.0
+    elif name == "abbot_gold_or_card":
+        e[130] = float(O.d_count(d))
+    return e
+
+
+def get_all_targets(root, seed, gid, threshold=15):
+    """CFRNode.get_all_targets (:258-274) -> list of (features[418], options[K][131], node_value[6], regrets[K])."""
+    from .philox import PhiloxChance
+    ch = PhiloxChance(seed, gid, stream=3)
+    out = []
+    for n in root.walk():
+        if not n.children or n.V.sum() < threshold:
+            continue
+        if n.role_pick:
+            i = ch.randbelow(6)
+            feats = n.game.encode_game(i)
+            dist = np.array(n.R[i], dtype=float)
+        else:
+            feats = n.game.encode_game()
+            dist = np.array(n.R, dtype=float)
+        if dist.sum() == 0:
+            dist = np.ones_like(dist)
+        out.append((feats, [encode_option(c[0]) for c in n.children], np.array(n.V), dist))
+    return out

@@ -175,6 +175,14 @@ def _mccfr_one(args):
             for _, c in n.children:
                 walk(c)
         walk(rn)
+    if nodes and not deep:
+        # CFRNode.get_all_targets() of the same tree, viewpoint seats from Philox stream 3
+        H.set_chance(PhiloxChance(SEED, gid, stream=3))
+        tg = nodes[0].get_all_targets()
+        out["t_feat"] = [t[0].numpy() for t in tg]
+        out["t_opts"] = [t[1].numpy()[0] for t in tg]
+        out["t_val"] = [t[2].numpy() for t in tg]
+        out["t_dist"] = [t[3].numpy() for t in tg]
     out["nchild"] = [len(n.children) for n in nodes]
     out["desc"] = [H.ref_descriptors([c[0]])[0] if c[0].name != "discard_and_draw" else 0 for n in nodes for c in n.children]
     out["V"] = [list(n.node_value) for n in nodes]
@@ -205,6 +213,18 @@ def gen_mccfr(name, ruleset, gids, back_hi, iters, procs=8, deep=0):
                V=cat("V", np.float64).reshape(-1, 6), P=cat("P", np.float64).reshape(-1, 6), narr=cat("narr", np.int32),
                R=cat("R", np.float64), S=cat("S", np.float64), C=cat("C", np.float64),
                game_crc=cat("game_crc", np.uint32), know_crc=cat("know_crc", np.uint32))
+    if not deep:
+        tcount = [len(r.get("t_feat", [])) for r in res]
+        out["t_off"] = np.concatenate([[0], np.cumsum(tcount)]).astype(np.int64)
+        feats = [f for r in res for f in r.get("t_feat", [])]
+        out["t_feat"] = np.asarray(feats, dtype=np.float32).reshape(-1, 418)
+        out["t_val"] = np.asarray([v for r in res for v in r.get("t_val", [])], dtype=np.float64).reshape(-1, 6)
+        ks = [len(o) for r in res for o in r.get("t_opts", [])]
+        out["t_k"] = np.asarray(ks, dtype=np.int32)
+        out["t_opts"] = (np.concatenate([o for r in res for o in r.get("t_opts", [])]).astype(np.float32)
+                         if ks else np.zeros((0, 131), np.float32))
+        out["t_dist"] = (np.concatenate([d for r in res for d in r.get("t_dist", [])]).astype(np.float64)
+                         if ks else np.zeros(0))
     path = os.path.join(HERE, name)
     np.savez_compressed(path, **out)
     print(name, "roots", len(gids), "nodes", int(node_off[-1]), "bytes", os.path.getsize(path))
@@ -221,6 +241,8 @@ if __name__ == "__main__":
         gen_mccfr("mccfr_preset.npz", 0, list(range(3000, 3024)), 20, 200)
         gen_mccfr("mccfr_preset_deep_back.npz", 0, list(range(3100, 3112)), 300, 200)
         gen_mccfr("mccfr_classic.npz", 1, list(range(103000, 103008)), 60, 200)
+    if what in ("all", "mccfr2000"):
+        gen_mccfr("mccfr_preset_2000it.npz", 0, list(range(3200, 3206)), 45, 2000)
     if what in ("all", "deep"):
         gen_mccfr("deep_mccfr_preset.npz", 0, list(range(4000, 4016)), 120, 200, deep=10)
     if what in ("all", "outcomes"):

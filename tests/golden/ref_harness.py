@@ -234,6 +234,8 @@ def patch_cfr_chance():
     np.random.choice = np_choice
     _random.random = lambda: _state["chance"].uniform()
     _random.choice = rnd_choice
+    import algorithms.deep_mccfr as dm
+    dm.randint = lambda a, b: a + _state["chance"].randbelow(b - a + 1)   # build_train_targets' viewpoint seat
 
 
 def ref_knowledge(g):

@@ -15,7 +15,7 @@ def engine():
     e.close()
 
 
-@pytest.mark.parametrize("name", ["mccfr_preset.npz", "mccfr_preset_deep_back.npz", "mccfr_classic.npz"])
+@pytest.mark.parametrize("name", ["mccfr_preset.npz", "mccfr_preset_deep_back.npz", "mccfr_classic.npz", "mccfr_preset_2000it.npz"])
 def test_trees_match_reference(engine, name):
     """SURVEY 8(d) parity gate 3: every node of trees grown by the real reference's CFRNode.cfr_train(200) --
     options, regrets, strategies, values (1e-9 relative; the gate asks 1e-5), game record and knowledge block."""
@@ -142,3 +142,30 @@ def test_deep_trees_match_reference(engine):
     for r in range(G.n):
         assert out["results"][r]["status"] == 0
         assert_same_tree(G.nodes(r), tree_preorder(out["trees"][r]), ("deep", r), norm_rtol=1e-5)
+
+
+
+# ---------------------------------------------------------------- training targets (BASELINE configs[4])
+@pytest.mark.parametrize("name", ["mccfr_preset.npz", "mccfr_preset_2000it.npz", "mccfr_classic.npz"])
+def test_training_targets_match_reference(engine, name):
+    """CFRNode.get_all_targets() of the real reference (tuple format of generate_test_data.py:25) vs ctd_mccfr_targets:
+    features and option encodings exact, node values and regret rows to 1e-9."""
+    from citadels_self_play_b200 import Engine
+    G = MccfrGolden(name)
+    z = G.z
+    engine.load_roots(z["roots"], z["knows"], z["used"], G.gids)
+    engine.mccfr(G.n, iterations=G.iterations, seed=G.seed, ruleset=G.ruleset)
+    t = engine.mccfr_targets(G.n, iterations=G.iterations, seed=G.seed, ruleset=G.ruleset)
+    assert len(t["meta"]) == int(z["t_off"][-1])
+    assert np.array_equal(np.bincount(t["meta"]["tree"], minlength=G.n), np.diff(z["t_off"]))
+    assert np.array_equal(t["features"], z["t_feat"])
+    assert np.array_equal(t["meta"]["n_options"], z["t_k"])
+    assert np.allclose(t["meta"]["node_value"], z["t_val"], rtol=1e-12)
+    assert np.allclose(t["regrets"], z["t_dist"], rtol=1e-9, atol=1e-12)
+    tuples = Engine.targets_as_tuples(t)
+    got = np.concatenate([x[1][0].numpy() for x in tuples]) if tuples else np.zeros((0, 131), np.float32)
+    assert got.shape == z["t_opts"].shape
+    assert np.array_equal(got, z["t_opts"])
+    if tuples:
+        mi, oi, nv, dd = tuples[0]
+        assert mi.shape == (418,) and oi.shape[0] == 1 and oi.shape[2] == 131 and nv.shape == (6,) and dd.shape == (oi.shape[1],)

@@ -10,7 +10,7 @@ from oracle import mccfr_oracle as M
 from tests.mccfr_util import MccfrGolden, oracle_preorder, tree_preorder, assert_same_tree
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FIXTURES = ["mccfr_preset.npz", "mccfr_preset_deep_back.npz", "mccfr_classic.npz"]
+FIXTURES = ["mccfr_preset.npz", "mccfr_preset_deep_back.npz", "mccfr_classic.npz", "mccfr_preset_2000it.npz"]
 
 
 @pytest.mark.parametrize("name", FIXTURES)
@@ -135,3 +135,38 @@ def test_oracle_encode_game_layout():
     assert f[90 + 2 * 40 + 13] == 2 and f[90 + 2 * 40 + 25] == 1
     assert f[330 + 2 * 5 + 3] == 2 and f[330 + 2 * 5 + 0] == 1      # the rewritten Magic School counts as trade
     assert f[360 + 2] == 1 and f[366 + 5] == 1 and f[377] == 1 and f[378 + 6 * 5 + 2] == 1
+
+
+# ---------------------------------------------------------------- training targets (get_all_targets)
+@pytest.mark.parametrize("name", FIXTURES)
+def test_oracle_training_targets_match_reference(name):
+    """CFRNode.get_all_targets(): 418 features, 131-wide option encodings, node values and regret rows of the real
+    reference vs the oracle's restatement (including encode_option's elif-chain quirks)."""
+    G = MccfrGolden(name)
+    z = G.z
+    koff = np.concatenate([[0], np.cumsum(z["t_k"])])
+    for r in range(0, G.n, 1 if G.iterations > 200 else 2):
+        if z["terminal"][r]:
+            continue
+        n = M.run_from_root(z["roots"][r], z["knows"][r], z["used"][r], G.seed, int(G.gids[r]), G.iterations)
+        tg = M.get_all_targets(n, G.seed, int(G.gids[r]))
+        lo, hi = int(z["t_off"][r]), int(z["t_off"][r + 1])
+        assert len(tg) == hi - lo
+        for j, (feat, opts, val, dist) in enumerate(tg):
+            i = lo + j
+            assert np.array_equal(np.asarray(feat, dtype=np.float32), z["t_feat"][i])
+            k0, k1 = int(koff[i]), int(koff[i + 1])
+            ref_opts = z["t_opts"][k0:k1]
+            got = np.asarray(opts, dtype=np.float32)
+            if G.ruleset == 1:   # discard_and_draw descriptors carry no card list: compare everything but the card bits
+                mask = np.ones(131, bool)
+                mask[89:129] = False
+                rows = ref_opts[:, O_DISCARD] == 1
+                assert np.array_equal(got[~rows], ref_opts[~rows]) and np.array_equal(got[rows][:, mask], ref_opts[rows][:, mask])
+            else:
+                assert np.array_equal(got, ref_opts), (r, j)
+            assert np.allclose(val, z["t_val"][i], rtol=1e-12)
+            assert np.allclose(dist, z["t_dist"][k0:k1], rtol=1e-9, atol=1e-12)
+
+
+O_DISCARD = 25   # index of discard_and_draw in game/option.py:34-45
