@@ -263,17 +263,29 @@ def main():
             deep_it += int(o["results"]["iterations"].sum())
             deep_ms += o["kernel_ms"]
         bad = int((o["results"]["status"] > 1).sum())
-        mccfr = [pure_it, pure_ms, deep_it, deep_ms, bad]
         eng2.close()
+        # BASELINE configs[4]: training-data generation, 2000 iterations, roots stepped back 1..100, nodes with >= 200 backprops
+        R5 = max(64, args.mccfr_roots // 4)
+        eng3 = Engine(capacity=R5, device=local)
+        eng3.make_roots(R5, seed=SEED, first_gid=sharding.first_gid(1, rank, world, R5), back_lo=1, back_hi=100)
+        eng3.mccfr(R5, iterations=2000, seed=SEED)
+        o5 = eng3.mccfr(R5, iterations=2000, seed=SEED)
+        t5 = time.perf_counter()
+        tg = eng3.mccfr_targets(R5, iterations=2000, seed=SEED, threshold=200.0)
+        t5 = time.perf_counter() - t5
+        gen_it, gen_ms, gen_targets = int(o5["results"]["iterations"].sum()), o5["kernel_ms"], len(tg["meta"])
+        bad += int((o5["results"]["status"] > 1).sum())
+        eng3.close()
+        mccfr = [pure_it, pure_ms, deep_it, deep_ms, bad, gen_it, gen_ms, gen_targets, t5 * 1e3]
 
     # ---- the only collective: outcome statistics, after the timed region ----
     if mccfr is not None:
-        mt = torch.tensor(mccfr[1::2], dtype=torch.float64, device="cuda")
-        mi = torch.tensor([mccfr[0], mccfr[2], mccfr[4]], dtype=torch.int64, device="cuda")
-        if world > 1:
+        mt = torch.tensor([mccfr[1], mccfr[3], mccfr[6], mccfr[8]], dtype=torch.float64, device="cuda")
+        mi = torch.tensor([mccfr[0], mccfr[2], mccfr[4], mccfr[5], mccfr[7]], dtype=torch.int64, device="cuda")
+        if world > 1:   # the data-gen collective: per-rank counts summed (targets themselves stay on their rank)
             dist.all_reduce(mt, op=dist.ReduceOp.MAX)
             dist.all_reduce(mi, op=dist.ReduceOp.SUM)
-        mccfr = [int(mi[0]), float(mt[0]), int(mi[1]), float(mt[1]), int(mi[2])]
+        mccfr = [int(mi[0]), float(mt[0]), int(mi[1]), float(mt[1]), int(mi[2]), int(mi[3]), float(mt[2]), int(mi[4]), float(mt[3])]
     t = torch.tensor([wall, e2e_wall, kernel_ms], dtype=torch.float64, device="cuda")
     s = torch.tensor([env_steps, e2e_steps, errors, launches] + wins, dtype=torch.int64, device="cuda")
     if world > 1:
@@ -314,7 +326,10 @@ def main():
                 "pure_it_per_s": mccfr[0] / (mccfr[1] / 1e3), "deep_it_per_s": mccfr[2] / (mccfr[3] / 1e3),
                 "deep_max_depth": 10, "deep_model": "ValueOnlyNN(418,512), torch.manual_seed(0) init",
                 "roofline_frac_hbm_2048B_per_it": (mccfr[0] / world / (mccfr[1] / 1e3)) * 2048 / 1e9 / peak,
-                "trees_with_error_status": mccfr[4]}
+                "trees_with_error_status": mccfr[4],
+                "datagen_2000it": {"roots_per_gpu": max(64, args.mccfr_roots // 4), "root_step_back": "1..100",
+                                   "it_per_s": mccfr[5] / (mccfr[6] / 1e3), "targets": mccfr[7], "usefulness_threshold": 200,
+                                   "targets_export_ms": mccfr[8]}}
             if not args.no_cpu_baseline:
                 cores = os.cpu_count() or 1
                 ci, cw = cpu_mccfr(3, cores)
