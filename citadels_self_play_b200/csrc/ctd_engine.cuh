@@ -14,6 +14,7 @@
 // traces without a GPU; that build is a test vehicle, never a fallback of the product.
 #pragma once
 #include <stdint.h>
+#include <stddef.h>
 #include "../../include/citadels_b200.h"
 
 #if defined(__CUDACC__)
@@ -22,10 +23,12 @@
 // instruction footprint (not the arithmetic) is what the SM front end sees; one copy of each helper.
 #define CTD_NI __noinline__
 #define CTD_LOOP _Pragma("unroll 1")
+#define CTD_UNROLL _Pragma("unroll")
 #else
 #define CTD_HD
 #define CTD_NI
 #define CTD_LOOP
+#define CTD_UNROLL
 #endif
 
 // ------------------------------------------------------------------------------------------ constants
@@ -114,14 +117,13 @@ CTD_HD inline uint64_t ctd_f_r(int r) { return (uint64_t)(r & 0x3F) << 45; }
 CTD_HD inline uint64_t ctd_f_j(uint32_t j) { return (uint64_t)(j & 0x3FF) << 51; }
 
 // ------------------------------------------------------------------------------------------ working record
-struct CtdWork {
+struct alignas(16) CtdWork {
   uint8_t hand[6][CTD_HAND_CAP];
   uint8_t bld[6][CTD_BLD_CAP];
   uint8_t mus[6][CTD_MUS_CAP];
   uint8_t jd[6][CTD_JD_CAP];
   uint8_t deck[CTD_DECK_CAP];  // ring: element i is deck[(deck_head + i) & 127]
   uint8_t disc[CTD_DISC_CAP];
-  uint8_t scratch[128];
   uint8_t n_hand[6], n_bld[6], n_mus[6], n_jd[6];
   uint8_t deck_head, n_deck, n_disc;
   int8_t gold[6];
@@ -137,6 +139,9 @@ struct CtdWork {
   uint8_t wiz_target;
   int8_t points[6];
   uint8_t warrant_building, ruleset, err;
+  uint8_t snap_pad[11];
+  // ---- everything above is the game itself: CTD_SNAP_BYTES, copied verbatim into MCCFR tree nodes ----
+  uint8_t scratch[128];
   // chance: Philox4x32-10 keyed (seed, gid) or a recorded tape
   uint32_t k0, k1, g0, g1;
   uint32_t stream;  // Philox counter word 1: 0 = game chance, 1 = CFR tree
@@ -147,6 +152,9 @@ struct CtdWork {
   uint32_t tape_pos, tape_len;
   uint32_t steps;
 };
+
+#define CTD_SNAP_BYTES 1136
+static_assert(offsetof(CtdWork, scratch) == CTD_SNAP_BYTES, "CtdWork snapshot region");
 
 // ------------------------------------------------------------------------------------------ chance
 CTD_HD CTD_NI inline void ctd_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
@@ -1199,20 +1207,39 @@ CTD_HD CTD_NI inline void ctd_new_game(CtdWork& w, uint64_t seed, uint64_t gid, 
 // ------------------------------------------------------------------------------------------ pack / unpack
 // Scalar forms (definition of the layout); ctd_warp.cuh has the lane-parallel device forms.
 CTD_HD CTD_NI inline void ctd_pack(const CtdWork& w, ctd_state* s) {
-  uint8_t* raw = (uint8_t*)s;
-  CTD_LOOP for (int i = 0; i < CTD_STATE_BYTES; ++i) raw[i] = 0;
+  {  // zero the record with eight-byte stores (ctd_state is 8-byte aligned)
+    uint64_t* z = (uint64_t*)s;
+    CTD_LOOP for (int i = 0; i < CTD_STATE_BYTES / 8; ++i) z[i] = 0;
+  }
   int pos = 0, c = 0;
   bool ovf = false;
-  auto put = [&](const uint8_t* a, int n) {
-    s->off[c++] = (uint8_t)pos;
-    CTD_LOOP for (int i = 0; i < n; ++i) { if (pos < 128) s->arena[pos++] = a[i]; else ovf = true; }
-  };
+  uint8_t* arena = s->arena;
   CTD_LOOP for (int p = 0; p < 6; ++p) {
-    put(w.hand[p], w.n_hand[p]); put(w.bld[p], w.n_bld[p]); put(w.mus[p], w.n_mus[p]); put(w.jd[p], w.n_jd[p]);
+    const uint8_t* src[4] = {w.hand[p], w.bld[p], w.mus[p], w.jd[p]};
+    const int len[4] = {w.n_hand[p], w.n_bld[p], w.n_mus[p], w.n_jd[p]};
+    CTD_UNROLL for (int k = 0; k < 4; ++k) {
+      s->off[c++] = (uint8_t)pos;
+      int n = len[k];
+      if (pos + n > 128) { ovf = true; n = 128 - pos; }
+      const uint8_t* a = src[k];
+      CTD_LOOP for (int i = 0; i < n; ++i) arena[pos + i] = a[i];
+      pos += n;
+    }
   }
   s->off[c++] = (uint8_t)pos;
-  CTD_LOOP for (int i = 0; i < w.n_deck; ++i) { if (pos < 128) s->arena[pos++] = w.deck[(w.deck_head + i) & (CTD_DECK_CAP - 1)]; else ovf = true; }
-  put(w.disc, w.n_disc);
+  {
+    int n = w.n_deck;
+    if (pos + n > 128) { ovf = true; n = 128 - pos; }
+    CTD_LOOP for (int i = 0; i < n; ++i) arena[pos + i] = w.deck[(w.deck_head + i) & (CTD_DECK_CAP - 1)];
+    pos += n;
+  }
+  s->off[c++] = (uint8_t)pos;
+  {
+    int n = w.n_disc;
+    if (pos + n > 128) { ovf = true; n = 128 - pos; }
+    CTD_LOOP for (int i = 0; i < n; ++i) arena[pos + i] = w.disc[i];
+    pos += n;
+  }
   s->off[c] = (uint8_t)pos;
   CTD_LOOP for (int p = 0; p < 6; ++p) {
     s->gold[p] = w.gold[p]; s->role[p] = w.role[p]; s->replicas[p] = w.replicas[p]; s->pflags[p] = w.pflags[p];
@@ -1232,24 +1259,43 @@ CTD_HD CTD_NI inline void ctd_pack(const CtdWork& w, ctd_state* s) {
 }
 
 CTD_HD CTD_NI inline void ctd_unpack(const ctd_state* s, CtdWork& w) {
-  int c = 0;
-  auto get = [&](uint8_t* a, uint8_t& n, int cap) {
-    int b = s->off[c], e = s->off[c + 1];
-    ++c;
-    int len = e - b;
-    if (len < 0) len = 0;
-    if (len > cap) { len = cap; w.err |= CTD_ERR_OVERFLOW; }
-    CTD_LOOP for (int i = 0; i < len; ++i) a[i] = s->arena[(b + i) & 127];
-    n = (uint8_t)len;
-  };
   w.err = s->err;
+  const uint8_t* arena = s->arena;
+  int c = 0;
   CTD_LOOP for (int p = 0; p < 6; ++p) {
-    get(w.hand[p], w.n_hand[p], CTD_HAND_CAP); get(w.bld[p], w.n_bld[p], CTD_BLD_CAP);
-    get(w.mus[p], w.n_mus[p], CTD_MUS_CAP); get(w.jd[p], w.n_jd[p], CTD_JD_CAP);
+    uint8_t* dst[4] = {w.hand[p], w.bld[p], w.mus[p], w.jd[p]};
+    uint8_t* cnt[4] = {&w.n_hand[p], &w.n_bld[p], &w.n_mus[p], &w.n_jd[p]};
+    const int cap[4] = {CTD_HAND_CAP, CTD_BLD_CAP, CTD_MUS_CAP, CTD_JD_CAP};
+    CTD_UNROLL for (int k = 0; k < 4; ++k) {
+      const int b = s->off[c] & 127;
+      int len = (int)s->off[c + 1] - (int)s->off[c];
+      ++c;
+      if (len < 0) len = 0;
+      if (len > cap[k]) { len = cap[k]; w.err |= CTD_ERR_OVERFLOW; }
+      if (b + len > 128) len = 128 - b;
+      uint8_t* a = dst[k];
+      CTD_LOOP for (int i = 0; i < len; ++i) a[i] = arena[b + i];
+      *cnt[k] = (uint8_t)len;
+    }
   }
   w.deck_head = 0;
-  get(w.deck, w.n_deck, CTD_DECK_CAP - 1);
-  get(w.disc, w.n_disc, CTD_DISC_CAP);
+  {
+    const int b = s->off[24] & 127;
+    int len = (int)s->off[25] - (int)s->off[24];
+    if (len < 0) len = 0;
+    if (len > CTD_DECK_CAP - 1) { len = CTD_DECK_CAP - 1; w.err |= CTD_ERR_OVERFLOW; }
+    if (b + len > 128) len = 128 - b;
+    CTD_LOOP for (int i = 0; i < len; ++i) w.deck[i] = arena[b + i];
+    w.n_deck = (uint8_t)len;
+  }
+  {
+    const int b = s->off[25] & 127;
+    int len = (int)s->off[26] - (int)s->off[25];
+    if (len < 0) len = 0;
+    if (b + len > 128) len = 128 - b;
+    CTD_LOOP for (int i = 0; i < len; ++i) w.disc[i] = arena[b + i];
+    w.n_disc = (uint8_t)len;
+  }
   CTD_LOOP for (int p = 0; p < 6; ++p) {
     w.gold[p] = s->gold[p]; w.role[p] = s->role[p]; w.replicas[p] = s->replicas[p]; w.pflags[p] = s->pflags[p];
     w.order[p] = s->order[p]; w.used_roles[p] = s->used_roles[p]; w.points[p] = s->points[p];

@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_targets(CtdTargetArgs a) {
       for (int i = 0; i < 6; ++i) vs += n.V[i];
       if (K != 0 && vs >= a.threshold) {
         const bool rp = n.flags & CTD_NF_ROLE_PICK;
-        uint32_t seat = n.game.player;
+        uint32_t seat = n.player;
         if (rp) {
           uint32_t r[4];
           ctd_philox(rp_draws >> 2, 3u, (uint32_t)h.gid, (uint32_t)(h.gid >> 32), (uint32_t)a.seed, (uint32_t)(a.seed >> 32), r);
@@ -538,6 +538,19 @@ __global__ void __launch_bounds__(32) ctd_k_one(CtdOneArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------ deep MCCFR
+// export pass: pack the game record of every node of every tree (one warp per tree, only when trees are copied out)
+__global__ void __launch_bounds__(CTD_BLOCK) ctd_k_pack_trees(uint8_t* trees, size_t tree_stride, uint32_t n_roots, uint32_t max_nodes,
+                                                              uint32_t child_cap) {
+  __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
+  __shared__ __align__(16) ctd_state tstage[CTD_WARPS_PER_BLOCK];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t t = blockIdx.x * CTD_WARPS_PER_BLOCK + wib;
+  if (t >= n_roots || lane != 0) return;
+  CtdTree T = ctd_tree_at(trees + t * tree_stride, max_nodes, child_cap);
+  T.w = &works[wib]; T.stage = &tstage[wib];
+  ctd_tree_pack_nodes(T);
+}
+
 struct CtdPredArgs {
   CtdMccfrArgs m;
   uint32_t max_depth;
@@ -1186,7 +1199,12 @@ ctd_status ctd_mccfr(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32_t it
   CTD_CUDA(e, cudaGetLastError());
   CTD_CUDA(e, cudaEventRecord(e->ev1, e->stream));
   if (results) CTD_CUDA(e, cudaMemcpyAsync(results, e->d_scratch, rb, cudaMemcpyDeviceToHost, e->stream));
-  if (trees_out) CTD_CUDA(e, cudaMemcpyAsync(trees_out, e->d_trees, need, cudaMemcpyDeviceToHost, e->stream));
+  if (trees_out) {
+    ctd_k_pack_trees<<<ctd_blocks(n_roots), CTD_BLOCK, 0, e->stream>>>(e->d_trees, stride, n_roots, mn, cc);
+    e->launches++;
+    CTD_CUDA(e, cudaGetLastError());
+    CTD_CUDA(e, cudaMemcpyAsync(trees_out, e->d_trees, need, cudaMemcpyDeviceToHost, e->stream));
+  }
   CTD_CUDA(e, cudaStreamSynchronize(e->stream));
   if (elapsed_ms) CTD_CUDA(e, cudaEventElapsedTime(elapsed_ms, e->ev0, e->ev1));
   return CTD_OK;
@@ -1515,7 +1533,12 @@ ctd_status ctd_mccfr_pred(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32
   }
   CTD_CUDA(e, cudaEventRecord(e->ev1, e->stream));
   if (results) CTD_CUDA(e, cudaMemcpyAsync(results, e->d_scratch, rb, cudaMemcpyDeviceToHost, e->stream));
-  if (trees_out) CTD_CUDA(e, cudaMemcpyAsync(trees_out, e->d_trees, need, cudaMemcpyDeviceToHost, e->stream));
+  if (trees_out) {
+    ctd_k_pack_trees<<<ctd_blocks(n_roots), CTD_BLOCK, 0, e->stream>>>(e->d_trees, stride, n_roots, mn, cc);
+    e->launches++;
+    CTD_CUDA(e, cudaGetLastError());
+    CTD_CUDA(e, cudaMemcpyAsync(trees_out, e->d_trees, need, cudaMemcpyDeviceToHost, e->stream));
+  }
   CTD_CUDA(e, cudaStreamSynchronize(e->stream));
   if (elapsed_ms) CTD_CUDA(e, cudaEventElapsedTime(elapsed_ms, e->ev0, e->ev1));
   if (waves_out) *waves_out = waves + 1;

@@ -37,11 +37,15 @@ struct CtdNode {
   double V[6];         // node_value
   double P[6];         // winning_probabilities
   float pred[6];       // pred_node_value (deep MCCFR)
-  uint8_t pad1[8];
-  ctd_state game;
+  uint8_t order[6];    // game.turn_orders_for_roles (role-pick nodes weight their strategy by it)
+  uint8_t gstate;      // game.gamestate.state
+  int8_t winner;       // game winner (terminal nodes)
+  ctd_state game;      // packed record: filled by ctd_tree_pack_nodes when the tree is exported, not on the hot path
   CtdKnow know;
+  uint8_t snap[CTD_SNAP_BYTES];  // the working record verbatim: node <-> shared memory is a plain vector copy
 };
-static_assert(sizeof(CtdNode) == 160 + 256 + 400, "CtdNode layout");
+static_assert(sizeof(CtdNode) == 160 + 256 + 400 + CTD_SNAP_BYTES, "CtdNode layout");
+static_assert(offsetof(CtdNode, game) % 16 == 0 && offsetof(CtdNode, know) % 16 == 0 && offsetof(CtdNode, snap) % 16 == 0, "CtdNode alignment");
 
 struct CtdChild {
   uint64_t desc;
@@ -199,17 +203,27 @@ CTD_HD CTD_NI inline void ctd_sample_private(CtdWork& w, CtdKnow& k, const uint8
 
 // ------------------------------------------------------------------------------------------ node helpers
 CTD_HD inline void ctd_node_store(CtdTree& T, CtdNode& n) {
-  ctd_pack(*T.w, T.stage);
-  ctd_copy16(&n.game, T.stage, (int)sizeof(ctd_state));
+  const CtdWork& w = *T.w;
+  ctd_copy16(n.snap, &w, CTD_SNAP_BYTES);
   ctd_copy16(&n.know, T.kn, (int)sizeof(CtdKnow));
+  CTD_LOOP for (int i = 0; i < 6; ++i) n.order[i] = w.order[i];
+  n.gstate = w.state;
+  n.winner = w.winner;
+}
+// export form: the 256-byte packed record of a node (tests, facade, ctd_mccfr trees_out)
+CTD_HD inline void ctd_node_pack(CtdTree& T, CtdNode& n) {
+  CtdWork& w = *T.w;
+  ctd_copy16(&w, n.snap, CTD_SNAP_BYTES);
+  w.draws = 0; w.tape_pos = 0; w.steps = 0;
+  w.g0 = (uint32_t)T.hdr->gid; w.g1 = (uint32_t)(T.hdr->gid >> 32);
+  ctd_pack(w, T.stage);
+  ctd_copy16(&n.game, T.stage, (int)sizeof(ctd_state));
 }
 CTD_HD inline void ctd_node_load(CtdTree& T, const CtdNode& n) {
   // chance state lives in the working record and must survive a load
   CtdWork& w = *T.w;
-  uint32_t k0 = w.k0, k1 = w.k1, draws = w.draws;
-  ctd_copy16(T.stage, &n.game, (int)sizeof(ctd_state));
-  ctd_unpack(T.stage, w);
-  w.k0 = k0; w.k1 = k1; w.draws = draws; w.buf_blk = 0xFFFFFFFFu;
+  ctd_copy16(&w, n.snap, CTD_SNAP_BYTES);   // the chance fields sit outside the snapshot and survive
+  w.buf_blk = 0xFFFFFFFFu;
   w.g0 = (uint32_t)T.hdr->gid; w.g1 = (uint32_t)(T.hdr->gid >> 32);
   w.tape = nullptr; w.tape_len = 0; w.err = 0;
   ctd_copy16(T.kn, &n.know, (int)sizeof(CtdKnow));
@@ -245,6 +259,7 @@ CTD_HD CTD_NI inline int ctd_new_node(CtdTree& T, int parent, int depth) {
   n.player = T.w->player;
   n.flags = (uint8_t)((T.w->state == 0 ? CTD_NF_ROLE_PICK : 0) | ((T.w->gflags & 2) ? CTD_NF_TERMINAL : 0));
   n.n_children = 0; n.child_cap = 0; n.child_off = 0; n.arr_off = 0; n.visits = 0; n.pad0 = 0;
+  { uint64_t* z = (uint64_t*)&n.game; CTD_LOOP for (int i = 0; i < (int)sizeof(ctd_state) / 8; ++i) z[i] = 0; }
   CTD_LOOP for (int i = 0; i < 6; ++i) { n.V[i] = 0.0; n.P[i] = 0.0; n.pred[i] = 0.f; }
   ctd_node_store(T, n);
   return idx;
@@ -273,8 +288,8 @@ CTD_HD inline uint64_t ctd_carried_form(const CtdWork& w, uint64_t d) {
 // "sample if it is not the same player's turn as in the parent" (:139-140, :157-158)
 CTD_HD inline void ctd_maybe_sample(CtdTree& T, const CtdNode& n) {
   bool root = n.parent < 0;
-  if (root || T.w->player != T.nodes[n.parent].game.player) {
-    bool role_sample = root ? false : T.nodes[n.parent].game.state != 0;
+  if (root || T.w->player != T.nodes[n.parent].player) {
+    bool role_sample = root ? false : T.nodes[n.parent].gstate != 0;
     ctd_sample_private(*T.w, *T.kn, T.hdr->used_cards, role_sample, T.scratch);
   }
 }
@@ -285,7 +300,7 @@ CTD_HD CTD_NI inline void ctd_expand(CtdTree& T, int ni) {
   CtdWork& w = *T.w;
   CtdKnowSet ks{T.kn, 1};
   const int viewer = T.hdr->viewer;
-  if (n.game.state == 0 && n.n_children == 0) {
+  if (n.gstate == 0 && n.n_children == 0) {
     // expand_role_pick (:102-131): ten uniformly random role-pick phases, the stored option is the last pick
     n.flags |= CTD_NF_ROLE_PICK;
     if (!ctd_reserve(T, n, 10, 180)) return;
@@ -406,7 +421,7 @@ CTD_HD CTD_NI inline int ctd_action_choice(CtdTree& T, int ni) {
     double s = 0.0;
     CTD_LOOP for (int a = 0; a < 10; ++a) {
       double v = 0.0;
-      CTD_LOOP for (int i = 0; i < 6; ++i) v += C[n.game.order[i] * 10 + a] * (double)(6 - i);
+      CTD_LOOP for (int i = 0; i < 6; ++i) v += C[n.order[i] * 10 + a] * (double)(6 - i);
       avg[a] = v / 15.0;
     }
     CTD_LOOP for (int a = 0; a < 10; ++a) s += avg[a];
@@ -479,7 +494,7 @@ CTD_HD CTD_NI inline void ctd_cfr_train(CtdTree& T, uint32_t iters) {
     node = ctd_action_choice(T, node);
     if (T.nodes[node].flags & CTD_NF_TERMINAL) {
       double reward[6] = {0, 0, 0, 0, 0, 0};
-      reward[T.nodes[node].game.winner] = 1.0;
+      reward[T.nodes[node].winner] = 1.0;
       ctd_backpropagate(T, node, reward);
       ctd_update_strategy(T, node);
       node = 0;
@@ -559,7 +574,7 @@ CTD_HD CTD_NI inline bool ctd_cfr_pred_advance(CtdTree& T, uint32_t iters, uint3
     if (n.depth > max_depth && !(n.flags & CTD_NF_TERMINAL)) {
       if (!(n.flags & CTD_NF_HAS_PRED)) {
         ctd_node_load(T, n);
-        ctd_encode_game(*T.w, *T.kn, n.game.state == 0 ? 5 : n.game.player, feat);
+        ctd_encode_game(*T.w, *T.kn, n.gstate == 0 ? 5 : n.player, feat);
         ctd_expand(T, node);
         h.cur_node = (uint32_t)node;
         h.phase = 2;
@@ -574,7 +589,7 @@ CTD_HD CTD_NI inline bool ctd_cfr_pred_advance(CtdTree& T, uint32_t iters, uint3
       node = 0;
     } else if (n.flags & CTD_NF_TERMINAL) {
       double reward[6] = {0, 0, 0, 0, 0, 0};
-      reward[n.game.winner] = 1.0;
+      reward[n.winner] = 1.0;
       ctd_backpropagate(T, node, reward);
       ctd_update_strategy(T, node);
       node = 0;
@@ -588,4 +603,10 @@ CTD_HD CTD_NI inline bool ctd_cfr_pred_advance(CtdTree& T, uint32_t iters, uint3
   h.phase = 3;
   h.rng_draws = T.w->draws;
   return false;
+}
+
+// fill the packed game record of every node (export only)
+CTD_HD CTD_NI inline void ctd_tree_pack_nodes(CtdTree& T) {
+  const uint32_t n = T.hdr->n_nodes;
+  CTD_LOOP for (uint32_t i = 0; i < n; ++i) ctd_node_pack(T, T.nodes[i]);
 }

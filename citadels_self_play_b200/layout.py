@@ -62,9 +62,10 @@ assert KNOW_DTYPE.itemsize == KNOW_BYTES
 NODE_DTYPE = np.dtype([("parent", np.int32), ("depth", np.uint16), ("player", np.uint8), ("flags", np.uint8),
                        ("n_children", np.uint32), ("child_cap", np.uint32), ("child_off", np.uint32),
                        ("arr_off", np.uint32), ("visits", np.uint32), ("pad0", np.uint32), ("V", np.float64, 6),
-                       ("P", np.float64, 6), ("pred", np.float32, 6), ("pad1", np.uint8, 8), ("game", STATE_DTYPE),
-                       ("know", KNOW_DTYPE)])
-assert NODE_DTYPE.itemsize == 816
+                       ("P", np.float64, 6), ("pred", np.float32, 6), ("order", np.uint8, 6), ("gstate", np.uint8),
+                       ("winner", np.int8), ("game", STATE_DTYPE), ("know", KNOW_DTYPE), ("snap", np.uint8, 1136)])
+NODE_BYTES = NODE_DTYPE.itemsize
+assert NODE_BYTES == 816 + 1136
 CHILD_DTYPE = np.dtype([("desc", np.uint64), ("node", np.uint32), ("pad", np.uint32)])
 TREE_HDR_DTYPE = np.dtype([("n_nodes", np.uint32), ("max_nodes", np.uint32), ("child_used", np.uint32),
                            ("child_cap", np.uint32), ("arr_used", np.uint32), ("arr_cap", np.uint32),
@@ -76,7 +77,7 @@ NF_ROLE_PICK, NF_TERMINAL = 1, 2
 
 
 def tree_bytes(max_nodes, child_cap, arr_cap):
-    return 128 + max_nodes * 816 + child_cap * 16 + arr_cap * 8
+    return 128 + max_nodes * NODE_BYTES + child_cap * 16 + arr_cap * 8
 
 
 class TreeView:
@@ -86,8 +87,8 @@ class TreeView:
         buf = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf
         self.hdr = buf[:128].view(TREE_HDR_DTYPE)[0]
         o = 128
-        self.nodes = buf[o:o + max_nodes * 816].view(NODE_DTYPE)
-        o += max_nodes * 816
+        self.nodes = buf[o:o + max_nodes * NODE_BYTES].view(NODE_DTYPE)
+        o += max_nodes * NODE_BYTES
         self.children = buf[o:o + child_cap * 16].view(CHILD_DTYPE)
         o += child_cap * 16
         self.arr = buf[o:o + arr_cap * 8].view(np.float64)

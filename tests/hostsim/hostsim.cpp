@@ -90,6 +90,7 @@ int hs_mccfr(const ctd_state* root, const CtdKnow* know, const uint8_t* used_car
   kn = *know;
   ctd_tree_init(T, max_nodes, child_cap, arr_cap, know->viewer, gid, false, false);
   ctd_cfr_train(T, iters);
+  ctd_tree_pack_nodes(T);
   return (int)T.hdr->status;
 }
 int hs_sizeof_node() { return (int)sizeof(CtdNode); }
@@ -120,6 +121,7 @@ int hs_mccfr_pred(const ctd_state* root, const CtdKnow* know, const uint8_t* use
   kn = *know;
   ctd_tree_init(T, max_nodes, child_cap, arr_cap, know->viewer, gid, false, true);
   while (ctd_cfr_pred_advance(T, iters, max_depth, feat, pred)) eval(feat, pred);
+  ctd_tree_pack_nodes(T);
   return (int)T.hdr->status;
 }
 }
