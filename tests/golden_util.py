@@ -7,7 +7,8 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 class Traces:
     def __init__(self, name):
-        z = np.load(os.path.join(GOLDEN, name))
+        with np.load(os.path.join(GOLDEN, name)) as f:
+            z = {k: f[k] for k in f.files}
         self.seed = int(z["seed"])
         self.ruleset = int(z["ruleset"])
         self.gids = z["gids"].astype(np.uint64)

@@ -8,7 +8,8 @@ from tests.golden_util import GOLDEN
 
 class MccfrGolden:
     def __init__(self, name):
-        z = np.load(os.path.join(GOLDEN, name))
+        with np.load(os.path.join(GOLDEN, name)) as f:
+            z = {k: f[k] for k in f.files}      # decompress once (NpzFile re-reads on every access)
         self.z = z
         self.seed = int(z["seed"])
         self.ruleset = int(z["ruleset"])
@@ -40,16 +41,21 @@ def oracle_preorder(node):
 
 def tree_preorder(tv):
     """Engine tree block (layout.TreeView) -> the same per-node dicts."""
+    from citadels_self_play_b200.layout import NODE_DTYPE
+    raw = tv.nodes.view(np.uint8).reshape(len(tv.nodes), NODE_DTYPE.itemsize)
+    g0, k0 = NODE_DTYPE.fields["game"][1], NODE_DTYPE.fields["know"][1]
+    child_desc, child_node = tv.children["desc"], tv.children["node"]
+    nch, coff = tv.nodes["n_children"], tv.nodes["child_off"]
+    V, P = tv.nodes["V"], tv.nodes["P"]
     stack = [0]
     while stack:
         i = stack.pop()
-        n = tv.nodes[i]
-        kids = tv.child_list(i)
+        k, o = int(nch[i]), int(coff[i])
         R, S, C = tv.arrays(i)
-        yield dict(nchild=len(kids), desc=np.asarray([k[0] for k in kids], dtype=np.uint64), V=n["V"], P=n["P"],
+        yield dict(nchild=k, desc=child_desc[o:o + k], V=V[i], P=P[i],
                    R=np.asarray(R).ravel(), S=np.asarray(S).ravel(), C=np.asarray(C).ravel(),
-                   game_crc=zlib.crc32(n["game"].tobytes()[:228]), know_crc=zlib.crc32(n["know"].tobytes()))
-        stack.extend(k[1] for k in reversed(kids))
+                   game_crc=zlib.crc32(raw[i, g0:g0 + 228].tobytes()), know_crc=zlib.crc32(raw[i, k0:k0 + 400].tobytes()))
+        stack.extend(int(x) for x in child_node[o:o + k][::-1])
 
 
 def assert_same_tree(a, b, what, rtol=1e-9, atol=1e-12, norm_rtol=None):

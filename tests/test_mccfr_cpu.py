@@ -17,7 +17,9 @@ FIXTURES = ["mccfr_preset.npz", "mccfr_preset_deep_back.npz", "mccfr_classic.npz
 def test_oracle_trees_match_reference(name):
     G = MccfrGolden(name)
     z = G.z
-    for r in range(G.n):
+    # the Python oracle does ~100 iterations/s: every root of the 200-iteration sets, half of the 2000-iteration set
+    roots = range(0, G.n, 2) if G.iterations > 200 else range(G.n)
+    for r in roots:
         g, step = M.make_root(G.seed, int(G.gids[r]), G.ruleset, 0, G.back_hi)
         assert step == int(z["root_step"][r])
         assert g.pack()[:228] == z["roots"][r][:228].tobytes()
@@ -145,7 +147,7 @@ def test_oracle_training_targets_match_reference(name):
     G = MccfrGolden(name)
     z = G.z
     koff = np.concatenate([[0], np.cumsum(z["t_k"])])
-    for r in range(0, G.n, 1 if G.iterations > 200 else 2):
+    for r in (range(0, G.n, 2) if G.iterations > 200 else range(G.n)):
         if z["terminal"][r]:
             continue
         n = M.run_from_root(z["roots"][r], z["knows"][r], z["used"][r], G.seed, int(G.gids[r]), G.iterations)
