@@ -533,13 +533,33 @@ CTD_HD CTD_NI inline void ctd_deal_preset(CtdWork& w, int ruleset, uint8_t* used
   ctd_shuffle(w, 76, [d](int i) -> uint8_t& { return d[i]; });
   if (used_cards_out != nullptr)  // self.used_cards = deepcopy(self.deck) (game/game.py:424)
     CTD_LOOP for (int i = 0; i < 76; ++i) used_cards_out[i] = w.deck[i];
-  const uint8_t hands[6][6] = {{0, 0, 16, 17, 18, 19}, {1, 1, 20, 21, 22, 23}, {2, 3, 24, 25, 26, 27},
-                               {3, 4, 28, 29, 30, 31}, {4, 0, 32, 33, 34, 35}, {0, 1, 36, 37, 39, 0}};
-  CTD_LOOP for (int p = 0; p < 6; ++p)
-    CTD_LOOP for (int k = 0; k < 6; ++k) {
-      int c = ctd_take_like(w.deck, w.n_deck, hands[p][k]);  // head == 0 here, the ring is linear
-      w.hand[p][w.n_hand[p]++] = (uint8_t)c;
+  // The fixed hands ({0,0,16,17,18,19} {1,1,20,21,22,23} {2,3,24,25,26,27} {3,4,28,29,30,31} {4,0,32,33,34,35}
+  // {0,1,36,37,39,0}) are pulled one card at a time with get_a_card_like_it (first match in the shuffled deck), seat
+  // by seat.  The i-th request for type t therefore receives the i-th copy of t in deck order, so one pass over the
+  // deck serves all 36 requests: slot = (seat << 3 | position in hand) of the next unserved request for that type.
+  CTD_LOOP for (int p = 0; p < 6; ++p) w.n_hand[p] = 6;
+  uint8_t served[5] = {0, 0, 0, 0, 0};
+  const uint8_t slot_common[5][5] = {{0 << 3 | 0, 0 << 3 | 1, 4 << 3 | 1, 5 << 3 | 0, 5 << 3 | 5},
+                                     {1 << 3 | 0, 1 << 3 | 1, 5 << 3 | 1, 0xFF, 0xFF},
+                                     {2 << 3 | 0, 0xFF, 0xFF, 0xFF, 0xFF},
+                                     {2 << 3 | 1, 3 << 3 | 0, 0xFF, 0xFF, 0xFF},
+                                     {3 << 3 | 1, 4 << 3 | 0, 0xFF, 0xFF, 0xFF}};
+  uint32_t unique_done = 0;  // bit (t - 16): the single request for unique type t has been served
+  int out = 0;
+  CTD_LOOP for (int j = 0; j < 76; ++j) {
+    const int t = w.deck[j];
+    int slot = 0xFF;
+    if (t < 5) {
+      if (served[t] < 5) { slot = slot_common[t][served[t]]; if (slot != 0xFF) ++served[t]; }
+    } else if (t >= 16 && !((unique_done >> (t - 16)) & 1)) {
+      unique_done |= 1u << (t - 16);
+      const int u = t == 39 ? 22 : t - 16;  // 16,17,18..37,39 -> 0..22 (the second Keep is never requested)
+      slot = ((u >> 2) << 3) | (2 + (u & 3));
     }
+    if (slot != 0xFF) w.hand[slot >> 3][slot & 7] = (uint8_t)t;
+    else w.deck[out++] = (uint8_t)t;
+  }
+  w.n_deck = (uint8_t)out;
 }
 
 // ------------------------------------------------------------------------------------------ enumeration
@@ -857,9 +877,11 @@ CTD_HD CTD_NI inline bool ctd_apply_finish(CtdWork& w, uint64_t d, CtdKnowSet ks
   const int pr = w.role[p];
   if (pr >= 8) { w.err |= CTD_ERR_REF_RAISE; return false; }
   const bool dead = w.rprops[pr] & CTD_RP_DEAD;
-  if (!dead) {
-    if (ctd_owns(w, p, 28) && w.n_hand[p] == 0) { ctd_draw_to_jd(w, p); ctd_draw_to_jd(w, p); }  // Park
-    if (ctd_owns(w, p, 30) && w.n_hand[p] == 0) w.gold[p] += 1;                                  // Poorhouse
+  if (!dead && w.n_hand[p] == 0) {
+    uint64_t own = 0;
+    CTD_LOOP for (int i = 0; i < w.n_bld[p]; ++i) own |= 1ull << ctd_ctype(w.bld[p][i]);
+    if ((own >> 28) & 1) { ctd_draw_to_jd(w, p); ctd_draw_to_jd(w, p); }  // Park: into just_drawn_cards
+    if ((own >> 30) & 1) w.gold[p] += 1;                                  // Poorhouse
   }
   if (CTD_OPT_CROWN(d)) { if (KN) ctd_kn_confirm(ks, p, pr); ctd_move_crown(w, p); }
   else if (KN && dead) ctd_kn_confirm(ks, p, pr);
