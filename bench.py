@@ -26,6 +26,16 @@ SEED = 0xC17ADE15
 METRIC = "env steps/sec (batched 6p random playouts)"
 
 
+def _traffic(games_per_launch):
+    """DRAM bytes per launch of the playout kernel from the committed ncu capture, scaled by games per launch."""
+    p = os.path.join(ROOT, "profiles", "r01_playout_traffic.json")
+    try:
+        t = json.load(open(p))
+        return (t["dram_bytes_read"] + t["dram_bytes_write"]) * (games_per_launch / t["games"])
+    except Exception:
+        return None
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -310,7 +320,8 @@ def main():
                        "l2": "no HBM-resident inputs (games are generated on device); 256 MiB flush between iterations",
                        "parallelism": "games sharded by global id, %d rank(s), no step-path collective" % world},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": _traffic(G), "traffic_source": "profiles/r01_playout_traffic.json (ncu, bytes per launch)",
+                         "peak_source": peak_src,
                          "note": "algorithmic 512 B/env step (SURVEY 8(d)); the fused kernel keeps the game in shared "
                                  "memory for its ~420 steps, so the real limiter is instruction issue (see profiles/)",
                          "kernel_env_steps_per_s_per_gpu": per_gpu_kernel},
