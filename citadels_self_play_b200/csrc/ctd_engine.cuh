@@ -139,7 +139,10 @@ struct alignas(16) CtdWork {
   uint8_t wiz_target;
   int8_t points[6];
   uint8_t warrant_building, ruleset, err;
-  uint8_t snap_pad[11];
+  uint8_t seer_mask;   // game.seer_taken_card_from (seat order) as a mask
+  uint8_t n_seven;     // game.seven_drawn_cards
+  uint8_t seven[7];
+  uint8_t snap_pad[2];
   // ---- everything above is the game itself: CTD_SNAP_BYTES, copied verbatim into MCCFR tree nodes ----
   uint8_t scratch[128];
   // chance: Philox4x32-10 keyed (seed, gid) or a recorded tape
@@ -192,6 +195,16 @@ CTD_HD inline uint32_t ctd_u32(CtdWork& w) {
   return w.buf[w.draws++ & 3];
 }
 CTD_HD inline uint32_t ctd_randbelow(CtdWork& w, uint32_t n) { return (uint32_t)(((uint64_t)ctd_u32(w) * n) >> 32); }
+// a chance draw that is part of the game itself (role variants, crown seat of a random game): one tape byte in replay mode
+CTD_HD inline uint32_t ctd_randbelow_any(CtdWork& w, uint32_t n) {
+  if (w.tape != nullptr) {
+    if (w.tape_pos + 1 > w.tape_len) { w.err |= CTD_ERR_TAPE; return 0; }
+    uint32_t v = w.tape[w.tape_pos++];
+    if (v >= n) { w.err |= CTD_ERR_TAPE; v = 0; }
+    return v;
+  }
+  return ctd_randbelow(w, n);
+}
 
 // Shuffle n elements addressed through `at(i)`.  Philox: Fisher-Yates from the top (the loop shape of
 // CPython's random.shuffle); tape: new[k] = old[tape[k]].  n <= 1 consumes nothing.
@@ -526,7 +539,35 @@ CTD_HD CTD_NI inline void ctd_deal_preset(CtdWork& w, int ruleset, uint8_t* used
   ctd_clear_done(w);
   w.next_player = 0; w.next_mode = CTD_NEXT_NONE; w.crown = 3; w.gflags = 0; w.winner = -1;
   w.wiz_target = 0xFF; w.warrant_building = 0xFF; w.ruleset = (uint8_t)ruleset; w.err = 0; w.steps = 0;
+  w.seer_mask = 0; w.n_seven = 0;
+  CTD_LOOP for (int i = 0; i < 7; ++i) w.seven[i] = 0;
   w.n_disc = 0; w.deck_head = 0;
+  if (ruleset == CTD_RULESET_RANDOM) {
+    // Game.set_random_game (game/game.py:491-520): random.sample(uniques, 14) = first 14 of a 24-permutation, Deck()
+    // shuffle of the 66 cards, four cards each dealt round-robin from the top, a random variant per rank, a shuffled
+    // pick order, a random crown.
+    uint8_t* u = w.scratch;
+    CTD_LOOP for (int i = 0; i < 24; ++i) u[i] = (uint8_t)i;
+    ctd_shuffle(w, 24, [u](int i) -> uint8_t& { return u[i]; });
+    CTD_LOOP for (int i = 0; i < 52; ++i) w.deck[i] = (uint8_t)ctd_base_deck(i);
+    CTD_LOOP for (int i = 0; i < 14; ++i) w.deck[52 + i] = (uint8_t)ctd_base_deck(52 + u[i]);
+    w.n_deck = 66;
+    uint8_t* dk = w.deck;
+    ctd_shuffle(w, 66, [dk](int i) -> uint8_t& { return dk[i]; });
+    if (used_cards_out != nullptr) {
+      CTD_LOOP for (int i = 0; i < 76; ++i) used_cards_out[i] = i < 66 ? w.deck[i] : 0xFF;
+    }
+    CTD_LOOP for (int r = 0; r < 4; ++r)
+      CTD_LOOP for (int p = 0; p < 6; ++p) w.hand[p][r] = w.deck[r * 6 + p];
+    CTD_LOOP for (int p = 0; p < 6; ++p) w.n_hand[p] = 4;
+    w.deck_head = 24;
+    w.n_deck = 42;
+    CTD_LOOP for (int r = 0; r < 8; ++r) w.variant[r] = (uint8_t)ctd_randbelow_any(w, 3);
+    uint8_t* o = w.order;
+    ctd_shuffle(w, 6, [o](int i) -> uint8_t& { return o[i]; });
+    w.crown = (uint8_t)ctd_randbelow_any(w, 6);
+    return;
+  }
   CTD_LOOP for (int i = 0; i < 76; ++i) w.deck[i] = (uint8_t)ctd_base_deck(i);
   w.n_deck = 76;
   uint8_t* d = w.deck;
@@ -1276,7 +1317,9 @@ CTD_HD CTD_NI inline void ctd_pack(const CtdWork& w, ctd_state* s) {
   s->crown = w.crown; s->gflags = w.gflags; s->winner = w.winner; s->wiz_target = w.wiz_target;
   s->warrant_building = w.warrant_building; s->ruleset = w.ruleset;
   s->err = (uint8_t)(w.err | (ovf ? CTD_ERR_OVERFLOW : 0));
-  s->rng_draws = w.draws; s->tape_pos = w.tape_pos; s->steps = w.steps;
+  s->seer_mask = w.seer_mask; s->seven_n = w.n_seven;
+  CTD_LOOP for (int i = 0; i < 7; ++i) s->seven[i] = i < w.n_seven ? w.seven[i] : 0;
+  s->rng_draws = w.draws; s->tape_pos = (uint16_t)w.tape_pos; s->steps = (uint16_t)(w.steps > 65535u ? 65535u : w.steps);
   s->gid = (uint64_t)w.g0 | ((uint64_t)w.g1 << 32);
 }
 
@@ -1328,6 +1371,8 @@ CTD_HD CTD_NI inline void ctd_unpack(const ctd_state* s, CtdWork& w) {
   w.next_player = s->next_player; w.next_mode = s->next_mode; w.crown = s->crown; w.gflags = s->gflags;
   w.winner = s->winner; w.wiz_target = s->wiz_target; w.warrant_building = s->warrant_building;
   w.ruleset = s->ruleset;
+  w.seer_mask = s->seer_mask; w.n_seven = s->seven_n > 7 ? 7 : s->seven_n;
+  CTD_LOOP for (int i = 0; i < 7; ++i) w.seven[i] = s->seven[i];
   w.draws = s->rng_draws; w.buf_blk = 0xFFFFFFFFu; w.tape_pos = s->tape_pos; w.steps = s->steps;
   w.g0 = (uint32_t)s->gid; w.g1 = (uint32_t)(s->gid >> 32);
 }

@@ -12,8 +12,9 @@ STATE_DTYPE = np.dtype([
     ("state", np.uint8), ("player", np.uint8), ("done", np.uint8), ("done_builds", np.uint8),
     ("next_player", np.uint8), ("next_mode", np.uint8), ("crown", np.uint8), ("gflags", np.uint8),
     ("winner", np.int8), ("wiz_target", np.uint8), ("points", np.int8, 6), ("warrant_building", np.uint8),
-    ("ruleset", np.uint8), ("err", np.uint8), ("pad0", np.uint8, 3), ("rng_draws", np.uint32),
-    ("tape_pos", np.uint32), ("steps", np.uint32), ("pad1", np.uint32), ("gid", np.uint64)])
+    ("ruleset", np.uint8), ("err", np.uint8), ("seer_mask", np.uint8), ("seven_n", np.uint8), ("pad0", np.uint8),
+    ("rng_draws", np.uint32), ("tape_pos", np.uint16), ("steps", np.uint16), ("seven", np.uint8, 7), ("pad1", np.uint8),
+    ("gid", np.uint64)])
 assert STATE_DTYPE.itemsize == STATE_BYTES
 
 # option kinds: index in the reference's action list (game/option.py:34-45)

@@ -33,9 +33,11 @@ typedef enum {
 /* rulesets: which variant of each of the 8 ranks is in play (game/config.py:83-91) */
 #define CTD_RULESET_PRESET 0  /* Witch Spy Wizard King Abbot Alchemist Navigator Warlord, game/game.py:479-486 */
 #define CTD_RULESET_CLASSIC 1 /* Assassin Thief Magician King Bishop Merchant Architect Warlord */
+#define CTD_RULESET_RANDOM 2  /* Game(preset=False), game/game.py:491-520: 14 random uniques, 4 cards each, a random
+                                 variant per rank (all 24 characters), random pick order and crown */
 
-/* Packed game record.  Bytes [0,228) are reference-visible state (tests compare them bit for bit with a
- * dump of the reference Game); bytes [228,256) are engine-private. */
+/* Packed game record.  Bytes [0,228) plus seer_mask / seven_n / seven[] are reference-visible state (tests compare
+ * them bit for bit with a dump of the reference Game); the rest of [228,256) is engine-private. */
 #define CTD_STATE_BYTES 256
 #define CTD_STATE_VISIBLE_BYTES 228
 typedef struct ctd_state {
@@ -70,11 +72,14 @@ typedef struct ctd_state {
   uint8_t ruleset;
   /* ---- engine-private ---- */
   uint8_t err;           /* CTD_ERR_* flags */
-  uint8_t pad0[3];
+  uint8_t seer_mask;     /* game.seer_taken_card_from as a seat mask (it is always in seat order) */
+  uint8_t seven_n;       /* len(game.seven_drawn_cards) */
+  uint8_t pad0;
   uint32_t rng_draws;    /* Philox draws consumed by this game so far */
-  uint32_t tape_pos;     /* chance-tape cursor (replay mode) */
-  uint32_t steps;        /* env steps applied to this slot */
-  uint32_t pad1;
+  uint16_t tape_pos;     /* chance-tape cursor (replay mode) */
+  uint16_t steps;        /* env steps applied to this slot (saturating) */
+  uint8_t seven[7];      /* game.seven_drawn_cards (Scholar) */
+  uint8_t pad1;
   uint64_t gid;          /* Philox game id of this slot (counter words 2,3) */
 } ctd_state;
 
@@ -101,6 +106,10 @@ typedef uint64_t ctd_option;
 #define CTD_OPT_COUNT(d) ((int)(((d) >> 39) & 0x3F))
 #define CTD_OPT_R(d) ((int)(((d) >> 45) & 0x3F)) /* Magician: subset size; Abbot: length of the gold/card list */
 #define CTD_OPT_J(d) ((int)(((d) >> 51) & 0x3FF))
+/* field reuse by the deluxe characters: magistrate_warrant rank = real target, named = first fake, count = second fake;
+ * blackmail rank = real, named = fake; give_crown named = 0 gold / 1 card / 13 nothing; cardinal_exchange a = built card,
+ * build = factory flag, count = number of cards given, j = which thinned combination; diplomat_exchange a = taken,
+ * b = given; give_back_card: card type + 1 per seat of seer_mask in fields a, b, count, r, j (0 = none). */
 
 /* aggregate outcome statistics of a batch of playouts (what the reference's drivers tabulate from
  * compare_to_random.py:24-37 style loops) */

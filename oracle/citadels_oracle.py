@@ -45,10 +45,14 @@ NAME_NONE, NAME_BEWITCHED = 24, 25
 ROLE_NAMES = ["Assassin", "Witch", "Magistrate", "Thief", "Spy", "Blackmailer", "Magician", "Wizard", "Seer",
               "King", "Emperor", "Patrician", "Bishop", "Abbot", "Cardinal", "Merchant", "Alchemist", "Trader",
               "Architect", "Navigator", "Scholar", "Warlord", "Diplomat", "Marshal"]
-RULESET_PRESET, RULESET_CLASSIC = 0, 1
+RULESET_PRESET, RULESET_CLASSIC, RULESET_RANDOM = 0, 1, 2
+# unique_building_cards in list order (game/config.py:56-80)
+UNIQUE_CARDS = [16, 17, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 39]
+NAMED_NOTHING = 13   # give_crown's gold_or_card="nothing" (not in the reference's names table; descriptor only)
 RULESET_VARIANTS = {
     RULESET_PRESET: [1, 1, 1, 0, 1, 1, 1, 0],   # Witch Spy Wizard King Abbot Alchemist Navigator Warlord (game/game.py:479-486)
     RULESET_CLASSIC: [0, 0, 0, 0, 0, 0, 0, 0],  # Assassin Thief Magician King Bishop Merchant Architect Warlord
+    RULESET_RANDOM: [0, 0, 0, 0, 0, 0, 0, 0],   # drawn per game, Game.set_random_game (game/game.py:491-520)
 }
 
 # option kinds = index in game/option.py:34-45
@@ -113,6 +117,34 @@ def D(kind, perp, target=None, a=None, b=None, rank=None, named=None, replica=0,
     d |= (r & 0x3F) << 45
     d |= (j & 0x3FF) << 51
     return d
+
+
+def D_handout(perp, types):
+    """give_back_card: up to five card types (+1) in fields a, b, count, r, j."""
+    t = [(x + 1) for x in types] + [0] * (5 - len(types))
+    d = K["give_back_card"] | (perp << 6)
+    d |= t[0] << 12 | t[1] << 18 | t[2] << 39 | t[3] << 45 | t[4] << 51
+    return d
+
+
+def d_handout(d):
+    v = [(d >> 12) & 0x3F, (d >> 18) & 0x3F, (d >> 39) & 0x3F, (d >> 45) & 0x3F, (d >> 51) & 0x3F]
+    return [x - 1 for x in v if x]
+
+
+def unrank_combination(n, k, i):
+    """Indices of the i-th k-combination of range(n) in itertools.combinations order."""
+    out, x = [], 0
+    for r in range(k, 0, -1):
+        while True:
+            c = comb(n - x - 1, r - 1)
+            if i < c:
+                break
+            i -= c
+            x += 1
+        out.append(x)
+        x += 1
+    return out
 
 
 def d_kind(d): return d & 0x3F
@@ -207,8 +239,13 @@ class Game:
         self.kr_mask = [[0] * n for _ in range(n)]     # [observer][seat] bit r = rank r, bit 8 = Bewitched
         self.kr_conf = [[False] * n for _ in range(n)]
         self.kh = [[] for _ in range(n)]               # known_hands per observer
+        self.seer_from = []      # game.seer_taken_card_from
+        self.seven = []          # game.seven_drawn_cards
         if deal:
-            self._deal_preset()
+            if ruleset == RULESET_RANDOM:
+                self._deal_random()
+            else:
+                self._deal_preset()
 
     def _deal_preset(self):
         """game/game.py:420-477: Deck() shuffles the 76 cards, hands are pulled by type (first match)."""
@@ -274,8 +311,14 @@ class Game:
         for _ in range(n):
             if unknown:
                 self.deck.append(unknown.pop(0))
-        if any(self.blackmail) or any(self.warrant):
-            raise NotImplementedError("tier C: sample_warrants_and_blackmails")
+        # sample_warrants_and_blackmails (:321-336): re-roll which flagged rank carries the real one
+        for arr in (self.blackmail, self.warrant):
+            keys = [r for r in range(8) if arr[r]]
+            if keys:
+                perm = ch.perm(len(keys))
+                real = keys[perm[0]]
+                for r in keys:
+                    arr[r] = 1 if r == real else 2
         # roles
         kr = list(self.kr_mask[viewer])
         conf = list(self.kr_conf[viewer])
@@ -322,6 +365,24 @@ class Game:
             if ctype(c) == t:
                 del cards[i]
                 return
+
+    def _deal_random(self):
+        """Game.set_random_game, game/game.py:491-520.  Chance mapping: random.sample(uniques, 14) -> first 14 of
+        perm(24); Deck() shuffle -> perm(66); random.choice per rank -> randbelow(3); random.shuffle(order) -> perm(6);
+        random.randint(0, 5) -> randbelow(6)."""
+        ch = self.chance
+        pu = ch.perm(24)
+        base = BASE_DECK[:52] + [UNIQUE_CARDS[i] for i in pu[:14]]
+        perm = ch.perm(66)
+        self.deck = [base[i] for i in perm]
+        self.used_cards = list(self.deck)
+        for _ in range(4):
+            for p in range(6):
+                self.hand[p].append(self.deck.pop(0))
+        self.variant = [ch.randbelow(3) for _ in range(8)]
+        po = ch.perm(6)
+        self.order = [[0, 1, 2, 3, 4, 5][i] for i in po]
+        self.crown = ch.randbelow(6)
 
     # ------------------------------------------------------------------ list helpers (game/deck.py)
     @staticmethod
@@ -540,26 +601,36 @@ class Game:
                             D(K["blackmail_response"], p, named=NAMED["not_pay"])]
                 return [D(K["empty_option"], p)]
             if st == 4:
-                raise NotImplementedError("tier C: reveal_blackmail_as_blackmailer")
+                # game/agent_functions.py:40-41
+                q = self.next_player
+                return [D(K["reveal_blackmail_as_blackmailer"], p, target=q, named=NAMED["reveal"]),
+                        D(K["reveal_blackmail_as_blackmailer"], p, target=q, named=NAMED["not_reveal"])]
             if st == 6:
                 # game/agent_functions.py:150-153
                 if self.gold[p] > 0:
                     return [D(K["graveyard"], p)]
                 return [D(K["empty_option"], p)]
             if st == 7:
-                raise NotImplementedError("tier C: reveal_warrant_as_magistrate")
+                # game/agent_functions.py:43-44
+                q = self.next_player
+                return [D(K["reveal_warrant_as_magistrate"], p, target=q, named=NAMED["reveal"]),
+                        D(K["reveal_warrant_as_magistrate"], p, target=q, named=NAMED["not_reveal"])]
             if nm == WITCH:
                 # game/agent_functions.py:236-242: every rank > 0 of game.roles
                 return [D(K["bewitching"], p, rank=r) for r in range(1, 8)]
             if not self.possessed[self._prop_rank(p)]:
                 if st == 5:
                     return self._main_round_options(p)
+                if st == 8:
+                    return self._seer_give_back_options(p)
+                if st == 9:
+                    return self._scholar_give_back_options(p)
                 if st == 10:
                     return self._wizard_take_options(p)
-                raise NotImplementedError("tier C state %d" % st)
+                return None   # the reference falls off the if-chain and returns None
             return [D(K["finish_round"], p, next_witch=1, crown=nm in (KING, PATRICIAN))]
         if nm == EMPEROR and not (self.done & DM_CHARACTER):
-            raise NotImplementedError("tier C: dead emperor")
+            return self._emperor_options(p, dead=True)
         return [D(K["finish_round"], p, next_witch=0, crown=nm in (KING, PATRICIAN))]
 
     def _keep_options(self, p):
@@ -649,14 +720,128 @@ class Game:
                                 if (q, t) not in seen:
                                     seen.add((q, t))
                                     o.append(D(K["warlord_desctruction"], p, target=q, a=t))
+            elif nm == MAGISTRATE:  # :221-234
+                targets = list(range(1, 8))
+                for real in targets:
+                    for i in range(len(targets)):
+                        for j in range(i + 1, len(targets)):
+                            a, b = targets[i], targets[j]
+                            if real != a and real != b:
+                                o.append(D(K["magistrate_warrant"], p, rank=real, named=a, count=b))
+            elif nm == BLACKMAILER:  # :255-272 (possessed ranks cannot be blackmailed)
+                targets = [r for r in range(2, 8) if not self.possessed[r]]
+                for i in range(len(targets)):
+                    for j in range(i + 1, len(targets)):
+                        o.append(D(K["blackmail"], p, rank=targets[i], named=targets[j]))
+                        o.append(D(K["blackmail"], p, rank=targets[j], named=targets[i]))
+            elif nm == SEER:        # :328-329
+                o = [D(K["seer"], p)]
+            elif nm == EMPEROR:     # :368-382
+                o = self._emperor_options(p, dead=False)
+            elif nm == PATRICIAN:   # :384-386
+                o = [D(K["take_crown_pat"], p)]
+            elif nm == CARDINAL:    # :393-419
+                o = self._cardinal_options(p)
+            elif nm == TRADER:      # :446-448
+                o = [D(K["trader"], p)]
+            elif nm == SCHOLAR:     # :457-460
+                o = [D(K["scholar"], p)] if self.deck else []
+            elif nm == MARSHAL:     # :484-492
+                seen = set()
+                for q in range(6):
+                    if q != p and len(self.bld[q]) < 7:
+                        for c in self.bld[q]:
+                            t = ctype(c)
+                            if (ccost(c) <= self.gold[p] and ccost(c) <= 3 and not self._has(self.bld[p], t) and t != 17
+                                    and self.name(q) != BISHOP and (q, t) not in seen):
+                                seen.add((q, t))
+                                o.append(D(K["marshal_steal"], p, target=q, a=t))
+            elif nm == DIPLOMAT:    # :494-504
+                seen = set()
+                for q in range(6):
+                    if q != p and len(self.bld[q]) < 7:
+                        for e in self.bld[q]:
+                            for own in self.bld[p]:
+                                te, to = ctype(e), ctype(own)
+                                if (ccost(e) - ccost(own) <= self.gold[p] and te != 17 and self.name(q) != BISHOP
+                                        and not self._has(self.bld[p], te) and (q, te, to) not in seen):
+                                    seen.add((q, te, to))
+                                    o.append(D(K["diplomat_exchange"], p, target=q, a=te, b=to))
             elif nm in (NAME_NONE, NAME_BEWITCHED):
                 pass
-            else:
-                raise NotImplementedError("tier C role %s" % ROLE_NAMES[nm])
         if nm == ABBOT and not (self.done & DM_BEGGED):       # :199-202, :432-435
             o.append(D(K["abbot_beg"], p))
         if nm in (WARLORD, MARSHAL, DIPLOMAT) and not (self.done & DM_TAKE_GOLD):   # :204-207, :506-509
             o.append(D(K["take_gold_for_war"], p))
+        return o
+
+    def _emperor_options(self, p, dead):
+        """game/agent_functions.py:368-382."""
+        o = []
+        for q in range(6):
+            if q != p:
+                if self.hand[q] and not dead:
+                    o.append(D(K["give_crown"], p, target=q, named=NAMED["card"]))
+                if self.gold[q] and not dead:
+                    o.append(D(K["give_crown"], p, target=q, named=NAMED["gold"]))
+                if (not self.gold[q] and not self.hand[q]) or dead:
+                    o.append(D(K["give_crown"], p, target=q, named=NAMED_NOTHING))
+        return o
+
+    def _cardinal_options(self, p):
+        """game/agent_functions.py:393-419.  j = position of the kept combination among the thinned ones
+        (range(0, C, max(round(C/100), 1))); `build` carries the factory flag, `count` the number of cards to give."""
+        o = []
+        hand = self.hand[p]
+        factory_owned = self._has(self.bld[p], 35)
+        for q in range(6):
+            for c in hand:
+                t = ctype(c)
+                cost = ccost(c)
+                factory = False
+                replica = 0
+                if factory_owned and csuit(c) == SUIT_UNIQUE:
+                    cost += 1
+                    factory = True
+                if self._has(self.bld[p], t) and not self.replicas[p]:
+                    replica = self.replicas[p] + 1
+                if cost <= self.gold[q]:
+                    ex = max(self.gold[q] - cost, 0)
+                    if len(hand) - 1 >= ex:
+                        n_other = sum(1 for x in hand if ctype(x) != t)
+                        total = comb(n_other, ex)
+                        step = max(py_round_div100(total), 1)
+                        for j in range((total + step - 1) // step):
+                            o.append(D(K["cardinal_exchange"], p, target=q, a=t, replica=replica, build=factory, count=ex, j=j))
+        return o
+
+    def _seer_give_back_options(self, p):
+        """game/agent_functions.py:332-361: the enumeration itself shuffles (3 random fill-ins per card and position).
+        Descriptor: card type + 1 per player of seer_taken_card_from, in that order (0 = zip() ran out)."""
+        k = len(self.seer_from)
+        cards = self.hand[p]
+        o = []
+        for pos in range(k):
+            for card in cards:
+                remaining = [c for c in cards if ctype(c) != ctype(card)]
+                for _ in range(3):
+                    perm = self.chance.perm(len(remaining))
+                    remaining = [remaining[i] for i in perm]
+                    row = list(remaining[:k - 1])
+                    row.insert(pos, card)
+                    o.append(D_handout(p, [ctype(c) for c in row[:k]]))
+        return o
+
+    def _scholar_give_back_options(self, p):
+        """game/agent_functions.py:462-470: copy() is shallow, so get_a_card_like_it removes from the very list that is
+        being iterated: every call keeps shrinking game.seven_drawn_cards and every option shares what is left."""
+        o = []
+        i = 0
+        while i < len(self.seven):
+            t = ctype(self.seven[i])
+            self._remove_like(self.seven, t)
+            o.append(D(K["scholar_card_pick"], p, a=t))
+            i += 1
         return o
 
     def _main_round_options(self, p):
@@ -821,8 +1006,15 @@ class Game:
             self.lighthouse[p] = True
         if self.warrant[self._prop_rank(p)] == 0:
             self._to5(p)
-        else:
-            raise NotImplementedError("tier C: warrant interrupt")
+        else:   # :121-127 any warrant, real or fake, interrupts for the Magistrate
+            m = self.player_from_rank(0)
+            if m is None:
+                raise OracleError("no rank-0 player")
+            self.warrant_building = t
+            self.state = 7
+            self.player = m
+            self.next_player = p
+            self.next_mode = NEXT_ALIAS
 
     def _a_smithy(self, d):
         """game/option_functions.py:131-138 (cards go to just_drawn_cards)."""
@@ -1100,6 +1292,195 @@ class Game:
             self.next_player = p
             self.next_mode = NEXT_RESET_CA
 
+    # ---- tier C transitions -------------------------------------------------------------------------
+    def _a_warranting(self, d):
+        """game/option_functions.py:251-257."""
+        p = d_perp(d)
+        self.warrant[d_rank(d)] = 1
+        self.warrant[d_named(d)] = 2
+        self.warrant[d_count(d)] = 2
+        self._to5(p)
+        self.done |= DM_CHARACTER
+
+    def _a_magistrate_reveal(self, d):
+        """game/option_functions.py:94-100."""
+        p, q = d_perp(d), d_target(d)
+        if d_named(d) == NAMED["reveal"] and self.warrant[self._prop_rank(q)] == 1:
+            t = self.warrant_building
+            self.bld[p].append(self._take_like(self.bld[q], t))
+            self.gold[q] += COST_OF_TYPE[t]
+            self.warrant = [0] * 8
+        self._restore_next()
+
+    def _a_blackmail(self, d):
+        """game/option_functions.py:271-276."""
+        p = d_perp(d)
+        self.blackmail[d_rank(d)] = 1
+        self.blackmail[d_named(d)] = 2
+        self._to5(p)
+        self.done |= DM_CHARACTER
+
+    def _a_blackmail_response(self, d):
+        """game/option_functions.py:71-82 (int(gold/2) truncates toward zero)."""
+        p = d_perp(d)
+        bm = self.player_from_rank(1)
+        if bm is None:
+            raise OracleError("no rank-1 player")
+        if d_named(d) == NAMED["pay"]:
+            half = int(self.gold[p] / 2)
+            self.gold[bm] += half
+            self.gold[p] -= half
+            self._to5(p)
+        else:
+            self.state = 4
+            self.player = bm
+            self.next_player = p
+            self.next_mode = NEXT_EMPTY
+
+    def _a_blackmail_reveal(self, d):
+        """game/option_functions.py:85-92."""
+        p, q = d_perp(d), d_target(d)
+        if d_named(d) == NAMED["reveal"] and self.blackmail[self._prop_rank(q)] == 1:
+            self.gold[p] += self.gold[q]
+            self.gold[q] = 0
+            self.blackmail = [0] * 8
+        self._restore_next()
+
+    def _a_seer(self, d):
+        """game/option_functions.py:330-341."""
+        p = d_perp(d)
+        self.seer_from = []
+        for q in range(6):
+            if q != p and self.hand[q]:
+                perm = self.chance.perm(len(self.hand[q]))
+                self.hand[q] = [self.hand[q][i] for i in perm]
+                self._reshuffle_if_empty()
+                self.hand[p].append(self.hand[q].pop(0))
+                self.seer_from.append(q)
+        self.state = 8
+        self.player = p
+        self.done |= DM_CHARACTER
+        self.next_player = p
+        self.next_mode = NEXT_ALIAS
+
+    def _a_seer_give_back(self, d):
+        """game/option_functions.py:343-350."""
+        p = d_perp(d)
+        for q, t in zip(self.seer_from, d_handout(d)):
+            c = self._take_like(self.hand[p], t)
+            self.hand[q].append(c)
+            self.kh[p].append(HandKnowledge(q, [c]))
+        self.seer_from = []
+        self._restore_next()
+
+    def _a_emperor(self, d):
+        """game/option_functions.py:377-393."""
+        p, q = d_perp(d), d_target(d)
+        self.gold[p] += sum(1 for c in self.bld[p] if csuit(c) == SUIT_LORD)
+        if d_named(d) == NAMED["card"]:
+            perm = self.chance.perm(len(self.hand[q]))
+            self.hand[q] = [self.hand[q][i] for i in perm]
+            if self.hand[q]:
+                self.hand[p].append(self.hand[q].pop(0))
+        elif d_named(d) == NAMED["gold"]:
+            self.gold[p] += 1
+            self.gold[q] -= 1
+        self._confirm_role(p)
+        self._move_crown(q)
+        self._to5(p)
+        self.done |= DM_CHARACTER
+
+    def _a_patrician(self, d):
+        """game/option_functions.py:365-375."""
+        p = d_perp(d)
+        for _ in range(sum(1 for c in self.bld[p] if csuit(c) == SUIT_LORD)):
+            self._draw_to(self.hand[p])
+        if not self.witch[p]:
+            self._move_crown(p)
+        self._to5(p)
+        self.done |= DM_CHARACTER
+
+    def _a_cardinal(self, d):
+        """game/option_functions.py:422-439 (no trade/non-trade bookkeeping, no warrant check, gold clamped at 0)."""
+        p, q, t = d_perp(d), d_target(d), d_a(d)
+        c = self._take_like(self.hand[p], t)
+        self.bld[p].append(c)
+        self.gold[p] -= ccost(c) - (1 if d_build(d) else 0)
+        self.gold[p] = max(0, self.gold[p])
+        if d_replica(d):
+            self.replicas[p] = d_replica(d)
+        k = d_count(d)
+        if k:
+            self.gold[q] -= k
+            other = [x for x in self.hand[p] if ctype(x) != t]
+            total = comb(len(other), k)
+            step = max(py_round_div100(total), 1)
+            for i in unrank_combination(len(other), k, d_j(d) * step):
+                self.hand[q].append(self._take_like(self.hand[p], ctype(other[i])))
+        self._to5(p)
+        self.done |= DM_CHARACTER
+
+    def _a_trader(self, d):
+        """game/option_functions.py:455-461."""
+        self._a_suit_gold(d, SUIT_TRADE)
+        self.done |= DM_CHARACTER
+
+    def _a_scholar(self, d):
+        """game/option_functions.py:485-496."""
+        p = d_perp(d)
+        self.seven = []
+        for _ in range(min(7, len(self.deck))):
+            self._reshuffle_if_empty()
+            c = self.deck.pop(0)
+            self.hand[p].append(c)
+            self.seven.append(c)
+        self.state = 9
+        self.player = p
+        self.done |= DM_CHARACTER
+        self.next_player = p
+        self.next_mode = NEXT_ALIAS
+
+    def _a_scholar_pick(self, d):
+        """game/option_functions.py:498-502: puts back whatever the (shared, shrunk) unchosen list holds; the choice
+        itself has no effect."""
+        p = d_perp(d)
+        for c in self.seven:
+            self.deck.append(self._take_like(self.hand[p], ctype(c)))
+        self._restore_next()
+        self.seven = []
+
+    def _steal_or_swap_tail(self, p, q, t):
+        """check_if_building_is_replica / settle_museum (non-warlord branch) / settle_lighthouse (:573-606)."""
+        if sum(1 for x in self.bld[q] if ctype(x) == t) > 1:
+            self.replicas[q] -= 1
+        if t == 34:
+            self.mus[p] += self.mus[q]
+            self.mus[q] = []
+        if t == 29 and self.lighthouse[q]:
+            self.lighthouse[q] = False
+            self.lighthouse[p] = True
+        self._to5(p)
+        self.done |= DM_CHARACTER
+
+    def _a_marshal(self, d):
+        """game/option_functions.py:505-515."""
+        p, q, t = d_perp(d), d_target(d), d_a(d)
+        cost = COST_OF_TYPE[t]
+        self.gold[p] -= cost
+        self.gold[q] += cost
+        self.bld[p].append(self._take_like(self.bld[q], t))
+        self._steal_or_swap_tail(p, q, t)
+
+    def _a_diplomat(self, d):
+        """game/option_functions.py:538-551."""
+        p, q, t, g = d_perp(d), d_target(d), d_a(d), d_b(d)
+        money = abs(COST_OF_TYPE[t] - COST_OF_TYPE[g])
+        self.gold[p] -= money
+        self.gold[q] += money
+        self.bld[p].append(self._take_like(self.bld[q], t))
+        self.bld[q].append(self._take_like(self.bld[p], g))
+        self._steal_or_swap_tail(p, q, t)
+
     def _a_unimplemented(self, d):
         raise NotImplementedError(KIND_NAMES[d_kind(d)])
 
@@ -1157,6 +1538,10 @@ class Game:
             b[220 + p] = self.points[p] & 0xFF
         b[226] = self.warrant_building
         b[227] = self.ruleset
+        # tier C scratch state lives in the engine-private tail but is game state all the same
+        b[229] = sum(1 << q for q in self.seer_from)        # seer_taken_card_from is always in seat order
+        b[230] = len(self.seven)
+        b[240:240 + len(self.seven)] = bytes(self.seven)
         return bytes(b)
 
     def encode_game(self, player_override=None):
@@ -1260,6 +1645,8 @@ class Game:
             g.wiz_cards = list(g.hand[g.wiz_target])
         g.points = [s8(rec[220 + p]) for p in range(6)]
         g.warrant_building = rec[226]
+        g.seer_from = [q for q in range(6) if rec[229] >> q & 1]
+        g.seven = list(rec[240:240 + rec[230]])
         return g
 
 
@@ -1294,6 +1681,21 @@ Game._APPLY = {
     K["architect"]: Game._a_architect,
     K["navigator_gold_card"]: Game._a_navigator,
     K["warlord_desctruction"]: Game._a_warlord,
+    K["magistrate_warrant"]: Game._a_warranting,
+    K["reveal_warrant_as_magistrate"]: Game._a_magistrate_reveal,
+    K["blackmail"]: Game._a_blackmail,
+    K["blackmail_response"]: Game._a_blackmail_response,
+    K["reveal_blackmail_as_blackmailer"]: Game._a_blackmail_reveal,
+    K["seer"]: Game._a_seer,
+    K["give_back_card"]: Game._a_seer_give_back,
+    K["give_crown"]: Game._a_emperor,
+    K["take_crown_pat"]: Game._a_patrician,
+    K["cardinal_exchange"]: Game._a_cardinal,
+    K["trader"]: Game._a_trader,
+    K["scholar"]: Game._a_scholar,
+    K["scholar_card_pick"]: Game._a_scholar_pick,
+    K["marshal_steal"]: Game._a_marshal,
+    K["diplomat_exchange"]: Game._a_diplomat,
 }
 for _k in range(len(KIND_NAMES)):
     Game._APPLY.setdefault(_k, Game._a_unimplemented)

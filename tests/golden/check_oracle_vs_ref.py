@@ -22,6 +22,9 @@ def run_pair(gid, ruleset, verbose=True):
         rd = H.ref_descriptors(ropts)
         od = og.options()
         rp, op = H.ref_pack(rg, ruleset), og.pack()
+        if ruleset == 2 and H.ref_knowledge(rg) != og.knowledge():
+            print("KNOWLEDGE MISMATCH game", gid, "step", steps)
+            return False, steps
         if rp != op or rd != od:
             if verbose:
                 print("MISMATCH game", gid, "step", steps, "state", rg.gamestate.state, "player", rg.gamestate.player_id)

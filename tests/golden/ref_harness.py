@@ -30,6 +30,10 @@ def _driven_shuffle(x):
     x[:] = [x[i] for i in perm]
 
 
+def _raise_index():
+    raise IndexError("Cannot choose from an empty sequence")
+
+
 def load_reference():
     """Import the reference with plotting imports stubbed and shuffles routed through `_state['chance']`."""
     if "game.game" in sys.modules and getattr(sys.modules["game.game"], "_ctd_patched", False):
@@ -44,6 +48,10 @@ def load_reference():
     sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
     sys.setrecursionlimit(5000)
     _random.shuffle = _driven_shuffle          # before `from random import shuffle` in game/deck.py
+    # Game.set_random_game (game/game.py:491-520): sample / choice / randint through the same chance source
+    _random.sample = lambda pop, k: [pop[i] for i in _state["chance"].perm(len(pop))[:k]]
+    _random.randint = lambda a, b: a + _state["chance"].randbelow(b - a + 1)
+    _random.choice = lambda seq: _raise_index() if not len(seq) else seq[_state["chance"].randbelow(len(seq))]
     import game.deck
     import game.game
     game.deck.shuffle = _driven_shuffle
@@ -72,7 +80,7 @@ def card_code(card):
 def new_ref_game(chance, ruleset=O.RULESET_PRESET):
     gg = load_reference()
     set_chance(chance)
-    g = gg.Game(preset=True)
+    g = gg.Game(preset=(ruleset != O.RULESET_RANDOM))
     if ruleset == O.RULESET_CLASSIC:
         g.roles = dict(_CLASSIC)
     g.setup_round()
@@ -152,6 +160,11 @@ def ref_pack(g, ruleset=O.RULESET_PRESET):
     wb = getattr(g, "warrant_building", None)
     b[226] = 0xFF if wb is None else wb.type_ID
     b[227] = ruleset
+    b[229] = sum(1 << q for q in getattr(g, "seer_taken_card_from", []))
+    seven = getattr(g, "seven_drawn_cards", [])
+    seven = [card_code(c) for c in (seven.cards if hasattr(seven, "cards") else seven)]
+    b[230] = len(seven)
+    b[240:240 + len(seven)] = bytes(seven)
     return bytes(b)
 
 
@@ -160,6 +173,7 @@ def ref_descriptors(options):
     from game.config import role_to_role_id
     out = []
     r_counts = {}
+    card_key, card_j = None, 0
     for o in options:
         a = o.attributes
         k = O.K[o.name]
@@ -198,8 +212,30 @@ def ref_descriptors(options):
             j = r_counts.get(r, 0)
             r_counts[r] = j + 1
             d = O.D(k, p, r=r, j=j)
+        elif n == "magistrate_warrant":
+            d = O.D(k, p, rank=a["real_target"], named=a["fake_targets"][0], count=a["fake_targets"][1])
+        elif n == "blackmail":
+            d = O.D(k, p, rank=a["real_target"], named=a["fake_target"])
+        elif n in ("reveal_blackmail_as_blackmailer", "reveal_warrant_as_magistrate"):
+            d = O.D(k, p, target=a["target"], named=O.NAMED[a["choice"]])
+        elif n == "give_back_card":
+            d = O.D_handout(p, [c.type_ID for c in a["card_handouts"].values()])
+        elif n == "give_crown":
+            d = O.D(k, p, target=a["target"], named={"gold": 0, "card": 1, "nothing": O.NAMED_NOTHING}[a["gold_or_card"]])
+        elif n == "scholar_card_pick":
+            d = O.D(k, p, a=a["choice"].type_ID)
+        elif n == "cardinal_exchange":
+            key = (a["target"], id(a["built_card"]))
+            card_j = card_j + 1 if key == card_key else 0
+            card_key = key
+            d = O.D(k, p, target=a["target"], a=a["built_card"].type_ID, replica=a["replica"], build=a["factory"],
+                    count=len(a["cards_to_give"]), j=card_j)
+        elif n == "marshal_steal":
+            d = O.D(k, p, target=a["target"], a=a["choice"].type_ID)
+        elif n == "diplomat_exchange":
+            d = O.D(k, p, target=a["target"], a=a["choice"].type_ID, b=a["give"].type_ID)
         elif n in ("empty_option", "smithy_choice", "graveyard", "take_gold_for_war", "take_crown_king",
-                   "abbot_beg", "bishop", "merchant", "architect"):
+                   "abbot_beg", "bishop", "merchant", "architect", "seer", "take_crown_pat", "trader", "scholar"):
             d = O.D(k, p)
         else:
             raise NotImplementedError(n)
@@ -233,7 +269,6 @@ def patch_cfr_chance():
 
     np.random.choice = np_choice
     _random.random = lambda: _state["chance"].uniform()
-    _random.choice = rnd_choice
     import algorithms.deep_mccfr as dm
     dm.randint = lambda a, b: a + _state["chance"].randbelow(b - a + 1)   # build_train_targets' viewpoint seat
 
