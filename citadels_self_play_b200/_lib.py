@@ -45,7 +45,7 @@ SIGNATURES = {
     "ctd_mccfr_tree_shape": (None, [_u32, _i, ctypes.POINTER(_u32), ctypes.POINTER(_u32), ctypes.POINTER(_u32),
                                     ctypes.POINTER(_u64)]),
     "ctd_game_new": (_i, [c_void, _u64, _u64, _i, c_void, c_void, c_void]),
-    "ctd_game_options": (_i, [c_void, c_void, c_void, c_void, _u32, ctypes.POINTER(_u32)]),
+    "ctd_game_options": (_i, [c_void, _u64, c_void, c_void, c_void, _u32, ctypes.POINTER(_u32)]),
     "ctd_game_step": (_i, [c_void, _u64, c_void, c_void, _u64, ctypes.POINTER(ctypes.c_int8)]),
     "ctd_set_value_model": (_i, [c_void] + [c_void] * 8),
     "ctd_set_value_backend": (_i, [c_void, _i]),

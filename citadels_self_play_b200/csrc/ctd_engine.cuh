@@ -33,7 +33,7 @@
 
 // ------------------------------------------------------------------------------------------ constants
 #define CTD_HAND_CAP 48
-#define CTD_BLD_CAP 16
+#define CTD_BLD_CAP 32 /* the Cardinal builds without limit inside CFR's hypothetical games (19 seen) */
 #define CTD_MUS_CAP 32
 #define CTD_JD_CAP 32
 #define CTD_DECK_CAP 128 /* ring buffer, power of two */
@@ -156,7 +156,7 @@ struct alignas(16) CtdWork {
   uint32_t steps;
 };
 
-#define CTD_SNAP_BYTES 1136
+#define CTD_SNAP_BYTES 1232
 static_assert(offsetof(CtdWork, scratch) == CTD_SNAP_BYTES, "CtdWork snapshot region");
 
 // ------------------------------------------------------------------------------------------ chance
@@ -234,7 +234,7 @@ CTD_HD inline void ctd_shuffle(CtdWork& w, int n, At at) {
 // What one observer ("viewer") believes: Agent.known_roles / Agent.known_hands (game/agent.py:25-26,
 // game/helper_classes.py:37-71), plus the looked-at hand of whoever used the Wizard this round
 // (the HandKnowledge the state-10 enumerator reads, game/agent_functions.py:311).  Playouts do not carry it.
-#define CTD_KN_HK_MAX 8
+#define CTD_KN_HK_MAX 32 /* the Seer adds up to five one-card entries a round, each lives five rounds */
 #define CTD_KN_POOL 256
 #define CTD_KN_WIZ_CAP 48
 enum { CTD_HK_WIZARD = 1, CTD_HK_USED = 2 };
@@ -259,7 +259,7 @@ struct alignas(16) CtdKnow {
   uint8_t err;
   uint8_t pad[13];
 };
-static_assert(sizeof(CtdKnow) == 400, "CtdKnow layout");
+static_assert(sizeof(CtdKnow) == 592, "CtdKnow layout");
 struct CtdKnowSet {  // the observers being tracked: 1 (CFR viewer) or 6 (root generation); n == 0 in playouts
   CtdKnow* k;
   int n;
@@ -353,7 +353,11 @@ CTD_HD CTD_NI inline int ctd_take_like(uint8_t* a, uint8_t& n, int t) {
   return t;
 }
 CTD_HD CTD_NI inline void ctd_append(CtdWork& w, uint8_t* a, uint8_t& n, int cap, int c) {
-  if (n >= cap) { w.err |= CTD_ERR_OVERFLOW; return; }
+  if (n >= cap) {
+#ifdef CTD_HOST_DEBUG
+    fprintf(stderr, "overflow cap %d list-offset %ld state %d\n", cap, (long)(a - (uint8_t*)&w), w.state);
+#endif
+    w.err |= CTD_ERR_OVERFLOW; return; }
   a[n++] = (uint8_t)c;
 }
 CTD_HD inline uint8_t& ctd_dk(CtdWork& w, int i) { return w.deck[(w.deck_head + i) & (CTD_DECK_CAP - 1)]; }
@@ -546,7 +550,8 @@ CTD_HD CTD_NI inline void ctd_deal_preset(CtdWork& w, int ruleset, uint8_t* used
     // Game.set_random_game (game/game.py:491-520): random.sample(uniques, 14) = first 14 of a 24-permutation, Deck()
     // shuffle of the 66 cards, four cards each dealt round-robin from the top, a random variant per rank, a shuffled
     // pick order, a random crown.
-    uint8_t* u = w.scratch;
+    uint8_t ubuf[24];  // not w.scratch: the tape form of ctd_shuffle stages through it
+    uint8_t* u = ubuf;
     CTD_LOOP for (int i = 0; i < 24; ++i) u[i] = (uint8_t)i;
     ctd_shuffle(w, 24, [u](int i) -> uint8_t& { return u[i]; });
     CTD_LOOP for (int i = 0; i < 52; ++i) w.deck[i] = (uint8_t)ctd_base_deck(i);
@@ -650,6 +655,96 @@ CTD_HD CTD_NI inline uint32_t ctd_magician_count(int n, int r) {
   return (uint32_t)((c + step - 1) / step);
 }
 
+// ---- deluxe characters (tier C) ----
+#define CTD_N_NOTHING 13 /* give_crown's "nothing": descriptor only, not in the reference's names table */
+
+// emperor_options (game/agent_functions.py:368-382)
+template <class E>
+CTD_HD CTD_NI inline void ctd_emperor_options(const CtdWork& w, int p, bool dead, E& e) {
+  CTD_LOOP for (int q = 0; q < 6; ++q) {
+    if (q == p) continue;
+    const uint64_t base = ctd_opt(CTD_K_GIVE_CROWN, p) | ctd_f_target(q);
+    if (w.n_hand[q] != 0 && !dead) e.one(base | ctd_f_named(CTD_N_CARD));
+    if (w.gold[q] != 0 && !dead) e.one(base | ctd_f_named(CTD_N_GOLD));
+    if ((w.gold[q] == 0 && w.n_hand[q] == 0) || dead) e.one(base | ctd_f_named(CTD_N_NOTHING));
+  }
+}
+
+// cardinal_options (game/agent_functions.py:393-419): for every seat (own included) and every hand card the seat can
+// "afford", the combinations of (gold - cost) other cards to hand over, thinned to about a hundred per card
+template <class E>
+CTD_HD CTD_NI inline void ctd_cardinal_options(const CtdWork& w, int p, E& e) {
+  const uint8_t* hand = w.hand[p];
+  const int nh = w.n_hand[p];
+  uint64_t own = 0;
+  CTD_LOOP for (int i = 0; i < w.n_bld[p]; ++i) own |= 1ull << ctd_ctype(w.bld[p][i]);
+  const bool factory_owned = (own >> 35) & 1;
+  CTD_LOOP for (int q = 0; q < 6; ++q)
+    CTD_LOOP for (int i = 0; i < nh; ++i) {
+      const int c = hand[i], t = ctd_ctype(c);
+      const bool factory = factory_owned && ctd_csuit(c) == CTD_SUIT_UNIQUE;
+      const int cost = ctd_ccost(c) + (factory ? 1 : 0);
+      const int replica = (((own >> t) & 1) && !w.replicas[p]) ? w.replicas[p] + 1 : 0;
+      if (cost > w.gold[q]) continue;
+      const int ex = w.gold[q] - cost;
+      if (nh - 1 < ex) continue;
+      int n_other = 0;
+      CTD_LOOP for (int x = 0; x < nh; ++x) n_other += ctd_ctype(hand[x]) != t;
+      if (ex > n_other) continue;
+      const uint64_t total = ctd_binom(n_other, ex);
+      const uint64_t qd = total / 100, rem = total % 100;
+      uint64_t step = rem > 50 ? qd + 1 : (rem < 50 ? qd : qd + (qd & 1));
+      if (step < 1) step = 1;
+      const uint32_t cnt = (uint32_t)((total + step - 1) / step);
+      e.range(ctd_opt(CTD_K_CARDINAL, p) | ctd_f_target(q) | ctd_f_a(t) | ctd_f_replica(replica) | ctd_f_build(factory) | ctd_f_count(ex), cnt);
+    }
+}
+
+// seer_give_back_card (game/agent_functions.py:332-361).  The enumeration itself draws chance: for every position,
+// every hand card and three times over it shuffles the other cards (cumulatively) and takes the first k-1.
+template <class E>
+CTD_HD CTD_NI inline void ctd_seer_give_back_options(CtdWork& w, int p, E& e) {
+  int k = 0;
+  CTD_LOOP for (int q = 0; q < 6; ++q) k += (w.seer_mask >> q) & 1;
+  const int n = w.n_hand[p];
+  uint8_t rembuf[CTD_HAND_CAP];  // not w.scratch: the tape form of ctd_shuffle stages through it
+  uint8_t* rem = rembuf;
+  CTD_LOOP for (int pos = 0; pos < k; ++pos)
+    CTD_LOOP for (int ci = 0; ci < n; ++ci) {
+      const int card = w.hand[p][ci], tc = ctd_ctype(card);
+      int nr = 0;
+      CTD_LOOP for (int x = 0; x < n; ++x)
+        if (ctd_ctype(w.hand[p][x]) != tc) rem[nr++] = w.hand[p][x];
+      CTD_LOOP for (int rep = 0; rep < 3; ++rep) {
+        ctd_shuffle(w, nr, [rem](int i) -> uint8_t& { return rem[i]; });
+        // row = rem[:k-1] with the card inserted at `pos` (list.insert past the end appends); zip() stops at k
+        int take = nr < k - 1 ? nr : k - 1;
+        int ins = pos < take ? pos : take;
+        uint64_t d = ctd_opt(CTD_K_GIVE_BACK_CARD, p);
+        const int shift[5] = {12, 18, 39, 45, 51};
+        int out = 0;
+        CTD_LOOP for (int x = 0; x <= take && out < k && out < 5; ++x) {
+          if (x == ins) { d |= (uint64_t)(tc + 1) << shift[out++]; if (out >= k || out >= 5) break; }
+          if (x < take) d |= (uint64_t)(ctd_ctype(rem[x]) + 1) << shift[out++];
+        }
+        e.one(d);
+      }
+    }
+}
+
+// scholar_give_back_options (game/agent_functions.py:462-470).  copy() is shallow, so the reference removes from the
+// very list it iterates: every call shrinks seven_drawn_cards, and every option shares what is left.
+template <class E>
+CTD_HD CTD_NI inline void ctd_scholar_give_back_options(CtdWork& w, int p, E& e) {
+  int i = 0;
+  while (i < w.n_seven) {
+    const int t = ctd_ctype(w.seven[i]);
+    ctd_take_like(w.seven, w.n_seven, t);
+    e.one(ctd_opt(CTD_K_SCHOLAR_PICK, p) | ctd_f_a(t));
+    ++i;
+  }
+}
+
 // character_options (game/agent_functions.py:156-209) and the per-role enumerators it dispatches to
 template <class E>
 CTD_HD CTD_NI inline void ctd_character_options(const CtdWork& w, int p, int nm, E& e) {
@@ -705,7 +800,64 @@ CTD_HD CTD_NI inline void ctd_character_options(const CtdWork& w, int p, int nm,
           }
         }
         break;
-      default: break;  // tier C roles are outside the built tiers (caller flags CTD_ERR_UNIMPL)
+      case CTD_MAGISTRATE:  // :221-234  real target x pairs of fake targets among ranks 1..7
+        CTD_LOOP for (int real = 1; real < 8; ++real)
+          CTD_LOOP for (int a = 1; a < 8; ++a)
+            CTD_LOOP for (int b = a + 1; b < 8; ++b)
+              if (real != a && real != b)
+                e.one(ctd_opt(CTD_K_MAGISTRATE_WARRANT, p) | ctd_f_rank(real) | ctd_f_named(a) | ctd_f_count(b));
+        break;
+      case CTD_BLACKMAILER:  // :255-272  ordered pairs of un-possessed ranks 2..7
+        CTD_LOOP for (int a = 2; a < 8; ++a) {
+          if (w.rprops[a] & CTD_RP_POSSESSED) continue;
+          CTD_LOOP for (int b = a + 1; b < 8; ++b) {
+            if (w.rprops[b] & CTD_RP_POSSESSED) continue;
+            e.one(ctd_opt(CTD_K_BLACKMAIL, p) | ctd_f_rank(a) | ctd_f_named(b));
+            e.one(ctd_opt(CTD_K_BLACKMAIL, p) | ctd_f_rank(b) | ctd_f_named(a));
+          }
+        }
+        break;
+      case CTD_SEER: e.one(ctd_opt(CTD_K_SEER, p)); break;            // :328-329
+      case CTD_EMPEROR: ctd_emperor_options(w, p, false, e); break;   // :368-382
+      case CTD_PATRICIAN: e.one(ctd_opt(CTD_K_TAKE_CROWN_PAT, p)); break;  // :384-386
+      case CTD_CARDINAL: ctd_cardinal_options(w, p, e); break;        // :393-419
+      case CTD_TRADER: e.one(ctd_opt(CTD_K_TRADER, p)); break;        // :446-448
+      case CTD_SCHOLAR: if (w.n_deck != 0) e.one(ctd_opt(CTD_K_SCHOLAR, p)); break;  // :457-460
+      case CTD_MARSHAL:  // :484-492
+        CTD_LOOP for (int q = 0; q < 6; ++q) {
+          if (q == p || w.n_bld[q] >= 7 || ctd_name(w, q) == CTD_BISHOP) continue;
+          uint64_t seen = 0;
+          CTD_LOOP for (int i = 0; i < w.n_bld[q]; ++i) {
+            const int c = w.bld[q][i], t = ctd_ctype(c), cost = ctd_ccost(c);
+            if (cost <= w.gold[p] && cost <= 3 && !ctd_owns(w, p, t) && t != 17 && !((seen >> t) & 1)) {
+              seen |= 1ull << t;
+              e.one(ctd_opt(CTD_K_MARSHAL, p) | ctd_f_target(q) | ctd_f_a(t));
+            }
+          }
+        }
+        break;
+      case CTD_DIPLOMAT:  // :494-504
+        CTD_LOOP for (int q = 0; q < 6; ++q) {
+          if (q == p || w.n_bld[q] >= 7 || ctd_name(w, q) == CTD_BISHOP) continue;
+          CTD_LOOP for (int i = 0; i < w.n_bld[q]; ++i) {
+            const int te = ctd_ctype(w.bld[q][i]);
+            if (te == 17 || ctd_owns(w, p, te)) continue;
+            CTD_LOOP for (int j = 0; j < w.n_bld[p]; ++j) {
+              const int to = ctd_ctype(w.bld[p][j]);
+              if (ctd_cost_of_type(te) - ctd_cost_of_type(to) > w.gold[p]) continue;
+              // de-duplicate on (target, taken type, given type): any earlier pair of the same types in this city
+              bool dup = false;
+              CTD_LOOP for (int i2 = 0; i2 <= i && !dup; ++i2) {
+                if (ctd_ctype(w.bld[q][i2]) != te) continue;
+                const int jmax = i2 == i ? j : w.n_bld[p];
+                CTD_LOOP for (int j2 = 0; j2 < jmax && !dup; ++j2) dup = ctd_ctype(w.bld[p][j2]) == to;
+              }
+              if (!dup) e.one(ctd_opt(CTD_K_DIPLOMAT, p) | ctd_f_target(q) | ctd_f_a(te) | ctd_f_b(to));
+            }
+          }
+        }
+        break;
+      default: break;
     }
   }
   if (nm == CTD_ABBOT && !(w.done & CTD_DM_BEGGED)) e.one(ctd_opt(CTD_K_ABBOT_BEG, p));  // :199-202
@@ -844,8 +996,13 @@ CTD_HD CTD_NI inline void ctd_enumerate(CtdWork& w, E& e, const CtdKnow* kn = nu
       case 6:  // graveyard_options (:150-153)
         e.one(ctd_opt(w.gold[p] > 0 ? CTD_K_GRAVEYARD : CTD_K_EMPTY, p));
         return;
-      case 4: case 7:
-        w.err |= CTD_ERR_UNIMPL;
+      case 4:  // reveal_blackmail_as_blackmailer_options (:40-41)
+        e.one(ctd_opt(CTD_K_REVEAL_BLACKMAIL, p) | ctd_f_target(w.next_player) | ctd_f_named(CTD_N_REVEAL));
+        e.one(ctd_opt(CTD_K_REVEAL_BLACKMAIL, p) | ctd_f_target(w.next_player) | ctd_f_named(CTD_N_NOT_REVEAL));
+        return;
+      case 7:  // reveal_warrant_as_magistrate_options (:43-44)
+        e.one(ctd_opt(CTD_K_REVEAL_WARRANT, p) | ctd_f_target(w.next_player) | ctd_f_named(CTD_N_REVEAL));
+        e.one(ctd_opt(CTD_K_REVEAL_WARRANT, p) | ctd_f_target(w.next_player) | ctd_f_named(CTD_N_NOT_REVEAL));
         return;
       default: break;
     }
@@ -856,15 +1013,11 @@ CTD_HD CTD_NI inline void ctd_enumerate(CtdWork& w, E& e, const CtdKnow* kn = nu
     if (role == CTD_ROLE_BEWITCHED) { w.err |= CTD_ERR_REF_RAISE; return; }
     if (!(w.rprops[role] & CTD_RP_POSSESSED)) {
       if (st == 5) {
-        if (w.variant[role] == 2 || nm == CTD_BLACKMAILER || nm == CTD_SEER || nm == CTD_EMPEROR || nm == CTD_CARDINAL ||
-            nm == CTD_TRADER || nm == CTD_SCHOLAR || nm == CTD_DIPLOMAT || nm == CTD_MARSHAL || nm == CTD_MAGISTRATE ||
-            nm == CTD_PATRICIAN) {
-          w.err |= CTD_ERR_UNIMPL;
-          return;
-        }
         ctd_main_round_options(w, p, nm, e);
         return;
       }
+      if (st == 8) { ctd_seer_give_back_options(w, p, e); return; }
+      if (st == 9) { ctd_scholar_give_back_options(w, p, e); return; }
       if (st == 10) {
         int q = w.wiz_target;
         if (q >= 6) { w.err |= CTD_ERR_REF_RAISE; return; }
@@ -872,13 +1025,13 @@ CTD_HD CTD_NI inline void ctd_enumerate(CtdWork& w, E& e, const CtdKnow* kn = nu
         else ctd_wizard_take_options(w, p, w.hand[q], w.n_hand[q], e);
         return;
       }
-      w.err |= CTD_ERR_UNIMPL;
+      w.err |= CTD_ERR_REF_RAISE;  // the reference falls off its if-chain and returns None
       return;
     }
     e.one(ctd_opt(CTD_K_FINISH, p) | ctd_f_next_witch(1) | ctd_f_crown(king));
     return;
   }
-  if (nm == CTD_EMPEROR && !(w.done & CTD_DM_CHARACTER)) { w.err |= CTD_ERR_UNIMPL; return; }
+  if (nm == CTD_EMPEROR && !(w.done & CTD_DM_CHARACTER)) { ctd_emperor_options(w, p, true, e); return; }
   e.one(ctd_opt(CTD_K_FINISH, p) | ctd_f_crown(king));
 }
 
@@ -907,8 +1060,17 @@ CTD_HD CTD_NI inline void ctd_apply_build(CtdWork& w, int p, int t, int replica)
   if (t == 29) w.pflags[p] |= CTD_PF_LIGHTHOUSE;
   int r = w.role[p];
   if (r >= 8) { w.err |= CTD_ERR_REF_RAISE; return; }
-  if (!(w.rprops[r] & CTD_RP_WARRANT)) ctd_to5(w, p);
-  else w.err |= CTD_ERR_UNIMPL;  // tier C: magistrate interrupt
+  if (!(w.rprops[r] & CTD_RP_WARRANT)) {
+    ctd_to5(w, p);
+  } else {  // :121-127 any warrant, real or fake, interrupts for the Magistrate
+    int m = ctd_player_from_rank(w, 0);
+    if (m < 0) { w.err |= CTD_ERR_REF_RAISE; return; }
+    w.warrant_building = (uint8_t)t;
+    w.state = 7;
+    w.player = (uint8_t)m;
+    w.next_player = (uint8_t)p;
+    w.next_mode = CTD_NEXT_ALIAS;
+  }
 }
 
 // finish_main_sequnce_actions (game/option_functions.py:189-243).  Returns true when the game ended.
@@ -1251,6 +1413,207 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
         w.next_player = (uint8_t)p;
         w.next_mode = CTD_NEXT_RESET_CA;  // GameState(..., already_done_moves=["character_ability"]) (:535)
       }
+      break;
+    }
+    // ---- deluxe characters (tier C) ----
+    case CTD_K_MAGISTRATE_WARRANT:  // carry_out_warranting (:251-257)
+      w.rprops[CTD_OPT_RANK(d)] = (uint8_t)((w.rprops[CTD_OPT_RANK(d)] & ~CTD_RP_WARRANT) | (1 << 1));
+      w.rprops[CTD_OPT_NAMED(d)] = (uint8_t)((w.rprops[CTD_OPT_NAMED(d)] & ~CTD_RP_WARRANT) | (2 << 1));
+      w.rprops[CTD_OPT_COUNT(d)] = (uint8_t)((w.rprops[CTD_OPT_COUNT(d)] & ~CTD_RP_WARRANT) | (2 << 1));
+      ctd_to5(w, p);
+      w.done |= CTD_DM_CHARACTER;
+      break;
+    case CTD_K_REVEAL_WARRANT: {  // carry_out_magistrate_reaveal (:94-100)
+      const int q = CTD_OPT_TARGET(d), rq = w.role[q];
+      if (rq >= 8) { w.err |= CTD_ERR_REF_RAISE; break; }
+      if (CTD_OPT_NAMED(d) == CTD_N_REVEAL && ((w.rprops[rq] & CTD_RP_WARRANT) >> 1) == 1) {
+        const int t = w.warrant_building;
+        ctd_append(w, w.bld[p], w.n_bld[p], CTD_BLD_CAP, ctd_take_like(w.bld[q], w.n_bld[q], t));
+        w.gold[q] += (int8_t)ctd_cost_of_type(t);
+        CTD_LOOP for (int r = 0; r < 8; ++r) w.rprops[r] &= (uint8_t)~CTD_RP_WARRANT;
+      }
+      ctd_restore_next(w);
+      break;
+    }
+    case CTD_K_BLACKMAIL:  // carry_out_blackmail (:271-276)
+      w.rprops[CTD_OPT_RANK(d)] = (uint8_t)((w.rprops[CTD_OPT_RANK(d)] & ~CTD_RP_BLACKMAIL) | (1 << 5));
+      w.rprops[CTD_OPT_NAMED(d)] = (uint8_t)((w.rprops[CTD_OPT_NAMED(d)] & ~CTD_RP_BLACKMAIL) | (2 << 5));
+      ctd_to5(w, p);
+      w.done |= CTD_DM_CHARACTER;
+      break;
+    case CTD_K_BLACKMAIL_RESPONSE: {  // carry_out_respond_to_blackmail (:71-82); int(gold/2) truncates toward zero
+      const int bm = ctd_player_from_rank(w, 1);
+      if (bm < 0) { w.err |= CTD_ERR_REF_RAISE; break; }
+      if (CTD_OPT_NAMED(d) == CTD_N_PAY) {
+        const int half = w.gold[p] / 2;
+        w.gold[bm] += (int8_t)half;
+        w.gold[p] -= (int8_t)half;
+        ctd_to5(w, p);
+      } else {
+        w.state = 4;
+        w.player = (uint8_t)bm;
+        w.next_player = (uint8_t)p;
+        w.next_mode = CTD_NEXT_EMPTY;
+      }
+      break;
+    }
+    case CTD_K_REVEAL_BLACKMAIL: {  // carry_out_responding_to_blackmail_response (:85-92)
+      const int q = CTD_OPT_TARGET(d), rq = w.role[q];
+      if (rq >= 8) { w.err |= CTD_ERR_REF_RAISE; break; }
+      if (CTD_OPT_NAMED(d) == CTD_N_REVEAL && ((w.rprops[rq] & CTD_RP_BLACKMAIL) >> 5) == 1) {
+        w.gold[p] += w.gold[q];
+        w.gold[q] = 0;
+        CTD_LOOP for (int r = 0; r < 8; ++r) w.rprops[r] &= (uint8_t)~CTD_RP_BLACKMAIL;
+      }
+      ctd_restore_next(w);
+      break;
+    }
+    case CTD_K_SEER: {  // carry_out_seer_take_a_card (:330-341): shuffle each hand, take its first card
+      w.seer_mask = 0;
+      CTD_LOOP for (int q = 0; q < 6; ++q) {
+        if (q == p || w.n_hand[q] == 0) continue;
+        uint8_t* h = w.hand[q];
+        ctd_shuffle(w, w.n_hand[q], [h](int i) -> uint8_t& { return h[i]; });
+        ctd_reshuffle_if_empty(w);
+        ctd_append(w, w.hand[p], w.n_hand[p], CTD_HAND_CAP, ctd_remove_at(w.hand[q], w.n_hand[q], 0));
+        w.seer_mask |= (uint8_t)(1u << q);
+      }
+      w.state = 8;
+      w.player = (uint8_t)p;
+      w.done |= CTD_DM_CHARACTER;
+      w.next_player = (uint8_t)p;
+      w.next_mode = CTD_NEXT_ALIAS;
+      break;
+    }
+    case CTD_K_GIVE_BACK_CARD: {  // carry_out_seer_give_back_cards (:343-350)
+      const int shift[5] = {12, 18, 39, 45, 51};
+      int idx = 0;
+      CTD_LOOP for (int q = 0; q < 6 && idx < 5; ++q) {
+        if (!((w.seer_mask >> q) & 1)) continue;
+        const int tv = (int)((d >> shift[idx++]) & 0x3F);
+        if (tv == 0) break;  // zip() ran out of cards
+        const int c = ctd_take_like(w.hand[p], w.n_hand[p], tv - 1);
+        ctd_append(w, w.hand[q], w.n_hand[q], CTD_HAND_CAP, c);
+        if (KN) CTD_LOOP for (int i = 0; i < ks.n; ++i)
+          if (ks.k[i].viewer == p) { uint8_t cc = (uint8_t)c; ctd_kn_add_hk(ks.k[i], q, &cc, 1, 0, 0xFFFF, false); }
+      }
+      w.seer_mask = 0;
+      ctd_restore_next(w);
+      break;
+    }
+    case CTD_K_GIVE_CROWN: {  // carry_out_emperor (:377-393)
+      const int q = CTD_OPT_TARGET(d);
+      w.gold[p] += (int8_t)ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_LORD);
+      if (CTD_OPT_NAMED(d) == CTD_N_CARD) {
+        uint8_t* h = w.hand[q];
+        ctd_shuffle(w, w.n_hand[q], [h](int i) -> uint8_t& { return h[i]; });
+        if (w.n_hand[q] != 0) ctd_append(w, w.hand[p], w.n_hand[p], CTD_HAND_CAP, ctd_remove_at(w.hand[q], w.n_hand[q], 0));
+      } else if (CTD_OPT_NAMED(d) == CTD_N_GOLD) {
+        w.gold[p] += 1;
+        w.gold[q] -= 1;
+      }
+      if (w.role[p] == CTD_ROLE_NONE) { w.err |= CTD_ERR_REF_RAISE; break; }
+      if (KN) ctd_kn_confirm(ks, p, w.role[p]);
+      ctd_move_crown(w, q);
+      ctd_to5(w, p);
+      w.done |= CTD_DM_CHARACTER;
+      break;
+    }
+    case CTD_K_TAKE_CROWN_PAT: {  // carry_out_take_crown_patrician (:365-375)
+      const int n = ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_LORD);
+      CTD_LOOP for (int i = 0; i < n; ++i) ctd_draw_to_hand(w, p);
+      if (!(w.pflags[p] & CTD_PF_WITCH)) ctd_move_crown(w, p);
+      ctd_to5(w, p);
+      w.done |= CTD_DM_CHARACTER;
+      break;
+    }
+    case CTD_K_CARDINAL: {  // carry_out_cardinal (:422-439): no build bookkeeping, no warrant check, gold clamped at 0
+      const int q = CTD_OPT_TARGET(d), t = CTD_OPT_CARD_A(d), kc = CTD_OPT_COUNT(d);
+      const int c = ctd_take_like(w.hand[p], w.n_hand[p], t);
+      ctd_append(w, w.bld[p], w.n_bld[p], CTD_BLD_CAP, c);
+      int g = w.gold[p] - (ctd_ccost(c) - CTD_OPT_BUILD(d));
+      w.gold[p] = (int8_t)(g < 0 ? 0 : g);
+      if (CTD_OPT_REPLICA(d)) w.replicas[p] = (int8_t)CTD_OPT_REPLICA(d);
+      if (kc != 0) {
+        w.gold[q] -= (int8_t)kc;
+        // other_cards = hand without the built type, in hand order; hand over the (j * step)-th kc-combination
+        uint8_t* other = w.scratch;
+        int no = 0;
+        CTD_LOOP for (int x = 0; x < w.n_hand[p]; ++x)
+          if (ctd_ctype(w.hand[p][x]) != t) other[no++] = w.hand[p][x];
+        const uint64_t total = ctd_binom(no, kc);
+        const uint64_t qd = total / 100, rem = total % 100;
+        uint64_t step = rem > 50 ? qd + 1 : (rem < 50 ? qd : qd + (qd & 1));
+        if (step < 1) step = 1;
+        uint64_t idx = (uint64_t)CTD_OPT_J(d) * step;
+        int x = 0;
+        CTD_LOOP for (int r = kc; r > 0; --r) {  // unrank in itertools.combinations order
+          for (;;) {
+            const uint64_t cnt = ctd_binom(no - x - 1, r - 1);
+            if (idx < cnt) break;
+            idx -= cnt;
+            ++x;
+            if (x >= no) break;
+          }
+          if (x >= no) { w.err |= CTD_ERR_REF_RAISE; break; }
+          ctd_append(w, w.hand[q], w.n_hand[q], CTD_HAND_CAP, ctd_take_like(w.hand[p], w.n_hand[p], ctd_ctype(other[x])));
+          ++x;
+        }
+      }
+      ctd_to5(w, p);
+      w.done |= CTD_DM_CHARACTER;
+      break;
+    }
+    case CTD_K_TRADER:  // carry_out_trader (:455-461)
+      w.gold[p] += (int8_t)ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_TRADE);
+      ctd_to5(w, p);
+      w.done |= CTD_DM_CHARACTER;
+      break;
+    case CTD_K_SCHOLAR: {  // carry_out_scholar_draw (:485-496)
+      w.n_seven = 0;
+      const int n = w.n_deck < 7 ? w.n_deck : 7;
+      CTD_LOOP for (int i = 0; i < n; ++i) {
+        const int c = ctd_draw(w);
+        if (c < 0) break;
+        ctd_append(w, w.hand[p], w.n_hand[p], CTD_HAND_CAP, c);
+        w.seven[w.n_seven++] = (uint8_t)c;
+      }
+      w.state = 9;
+      w.player = (uint8_t)p;
+      w.done |= CTD_DM_CHARACTER;
+      w.next_player = (uint8_t)p;
+      w.next_mode = CTD_NEXT_ALIAS;
+      break;
+    }
+    case CTD_K_SCHOLAR_PICK:  // carry_out_scholar_put_back (:498-502): returns what the shrunk shared list still holds
+      CTD_LOOP for (int i = 0; i < w.n_seven; ++i) ctd_deck_push(w, ctd_take_like(w.hand[p], w.n_hand[p], ctd_ctype(w.seven[i])));
+      ctd_restore_next(w);
+      w.n_seven = 0;
+      CTD_LOOP for (int i = 0; i < 7; ++i) w.seven[i] = 0;
+      break;
+    case CTD_K_MARSHAL:
+    case CTD_K_DIPLOMAT: {  // carry_out_marshal (:505-515) / carry_out_diplomat (:538-551)
+      const int q = CTD_OPT_TARGET(d), t = CTD_OPT_CARD_A(d);
+      const int money = k == CTD_K_MARSHAL ? ctd_cost_of_type(t)
+                                           : (ctd_cost_of_type(t) > ctd_cost_of_type(CTD_OPT_CARD_B(d))
+                                                  ? ctd_cost_of_type(t) - ctd_cost_of_type(CTD_OPT_CARD_B(d))
+                                                  : ctd_cost_of_type(CTD_OPT_CARD_B(d)) - ctd_cost_of_type(t));
+      w.gold[p] -= (int8_t)money;
+      w.gold[q] += (int8_t)money;
+      ctd_append(w, w.bld[p], w.n_bld[p], CTD_BLD_CAP, ctd_take_like(w.bld[q], w.n_bld[q], t));
+      if (k == CTD_K_DIPLOMAT)
+        ctd_append(w, w.bld[q], w.n_bld[q], CTD_BLD_CAP, ctd_take_like(w.bld[p], w.n_bld[p], CTD_OPT_CARD_B(d)));
+      if (ctd_count_type(w.bld[q], w.n_bld[q], t) > 1) w.replicas[q] -= 1;
+      if (t == 34) {  // settle_museum, non-warlord branch: the tucked cards follow the Museum
+        CTD_LOOP for (int i = 0; i < w.n_mus[q]; ++i) ctd_append(w, w.mus[p], w.n_mus[p], CTD_MUS_CAP, w.mus[q][i]);
+        w.n_mus[q] = 0;
+      }
+      if (t == 29 && (w.pflags[q] & CTD_PF_LIGHTHOUSE)) {
+        w.pflags[q] &= (uint8_t)~CTD_PF_LIGHTHOUSE;
+        w.pflags[p] |= CTD_PF_LIGHTHOUSE;
+      }
+      ctd_to5(w, p);
+      w.done |= CTD_DM_CHARACTER;
       break;
     }
     default: w.err |= CTD_ERR_UNIMPL; break;

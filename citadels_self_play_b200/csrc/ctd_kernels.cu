@@ -71,8 +71,11 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_reset(ctd_state* slots, uint3
   ctd_record_store(&slots[slot], &stage[wib], lane);
 }
 
-__global__ void __launch_bounds__(CTD_BLOCK) ctd_k_enumerate(const ctd_state* slots, uint32_t n, ctd_option* opts,
-                                                             uint32_t* counts, uint32_t stride, uint8_t* errs) {
+// Enumeration is read-only except in two states of the deluxe characters: the Seer's give-back list is built with
+// fresh shuffles (chance is consumed) and the Scholar's list shrinks game.seven_drawn_cards; those records are written back.
+__global__ void __launch_bounds__(CTD_BLOCK) ctd_k_enumerate(ctd_state* slots, uint32_t n, ctd_option* opts,
+                                                             uint32_t* counts, uint32_t stride, uint8_t* errs, uint64_t seed,
+                                                             CtdTapes tapes) {
   __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
   __shared__ ctd_state stage[CTD_WARPS_PER_BLOCK];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -80,13 +83,22 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_enumerate(const ctd_state* sl
   if (slot >= n) return;
   CtdWork& w = works[wib];
   ctd_record_load(&slots[slot], &stage[wib], lane);
+  int dirty = 0;
   if (lane == 0) {
     ctd_unpack(&stage[wib], w);
+    w.k0 = (uint32_t)seed; w.k1 = (uint32_t)(seed >> 32);
+    w.stream = 0;
+    ctd_attach_tape(w, tapes, slot);
+    dirty = (w.state == 8 || w.state == 9) && !(w.gflags & 2);
     CtdEmit e{opts + (size_t)slot * stride, stride, 0, 0xFFFFFFFFu, 0};
     ctd_enumerate(w, e);
     counts[slot] = e.n;
     errs[slot] = w.err;
+    dirty = dirty && e.n <= stride;   // a list that did not fit is enumerated again by the caller: leave the record alone
+    if (dirty) ctd_pack(w, &stage[wib]);
   }
+  dirty = __shfl_sync(CTD_FULL, dirty, 0);
+  if (dirty) ctd_record_store(&slots[slot], &stage[wib], lane);
 }
 
 __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_step(ctd_state* slots, uint32_t n, const ctd_option* chosen,
@@ -137,7 +149,7 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_choose_check(const ctd_state*
   nref = __shfl_sync(CTD_FULL, nref, 0);
   __syncwarp();
   uint32_t bad = 0, cnt = 0;
-  if (nref == 0) {
+  if (nref == 0 || w.state == 8 || w.state == 9) {  // impure enumerations: both paths are the scalar enumerator anyway
     if (lane == 0) mismatches[slot] = 0;
     return;
   }
@@ -516,9 +528,12 @@ __global__ void __launch_bounds__(32) ctd_k_one(CtdOneArgs a) {
       ctd_pack(w, &stage);
     } else if (a.op == 1) {
       ctd_unpack(&stage, w);
+      w.k0 = (uint32_t)a.seed; w.k1 = (uint32_t)(a.seed >> 32);
+      w.stream = 0; w.tape = nullptr; w.tape_len = 0;
       CtdEmit e{a.opts, a.cap, 0, 0xFFFFFFFFu, 0};
       ctd_enumerate(w, e, a.know6 ? &kn[0] : nullptr);
       *a.count = e.n;
+      if (e.n <= a.cap) ctd_pack(w, &stage);   // Seer / Scholar enumerations change the record (a list that does not fit is asked for again)
     } else {
       ctd_unpack(&stage, w);
       w.k0 = (uint32_t)a.seed; w.k1 = (uint32_t)(a.seed >> 32);
@@ -530,8 +545,8 @@ __global__ void __launch_bounds__(32) ctd_k_one(CtdOneArgs a) {
     }
   }
   __syncwarp();
+  ctd_record_store(a.state, &stage, lane);
   if (a.op != 1) {
-    ctd_record_store(a.state, &stage, lane);
     if (a.know6 != nullptr)
       for (int i = lane; i < (int)(6 * sizeof(CtdKnow) / 4); i += 32) ((uint32_t*)a.know6)[i] = ((const uint32_t*)kn)[i];
   }
@@ -889,7 +904,7 @@ ctd_status ctd_set_seed(ctd_engine* e, uint64_t seed) {
 }
 
 ctd_status ctd_reset(ctd_engine* e, uint32_t n, uint64_t seed, uint64_t first_gid, int ruleset) {
-  if (!e || n > e->capacity || (ruleset != CTD_RULESET_PRESET && ruleset != CTD_RULESET_CLASSIC)) return CTD_EARG;
+  if (!e || n > e->capacity || (ruleset < CTD_RULESET_PRESET || ruleset > CTD_RULESET_RANDOM)) return CTD_EARG;
   if (n == 0) return CTD_OK;
   CTD_CUDA(e, cudaSetDevice(e->device));
   e->seed = seed;
@@ -952,7 +967,7 @@ ctd_status ctd_enumerate(ctd_engine* e, uint32_t n, ctd_option* opts, uint32_t* 
   ctd_option* d_opts = (ctd_option*)e->d_scratch;
   uint32_t* d_counts = (uint32_t*)((char*)e->d_scratch + ob);
   uint8_t* d_errs = (uint8_t*)e->d_scratch + ob + cb_al;
-  ctd_k_enumerate<<<ctd_blocks(n), CTD_BLOCK, 0, e->stream>>>(e->d_slots, n, d_opts, d_counts, stride, d_errs);
+  ctd_k_enumerate<<<ctd_blocks(n), CTD_BLOCK, 0, e->stream>>>(e->d_slots, n, d_opts, d_counts, stride, d_errs, e->seed, ctd_tapes(e));
   e->launches++;
   CTD_CUDA(e, cudaGetLastError());
   CTD_CUDA(e, cudaMemcpyAsync(counts, d_counts, cb, cudaMemcpyDeviceToHost, e->stream));
@@ -1030,7 +1045,7 @@ static ctd_status ctd_playout_launch(ctd_engine* e, CtdPlayoutArgs& a, ctd_playo
 
 ctd_status ctd_playout_dev(ctd_engine* e, uint64_t n_games, uint64_t seed, uint64_t first_gid, int ruleset,
                            uint32_t max_steps, ctd_playout_stats* stats, float* elapsed_ms) {
-  if (!e || (ruleset != CTD_RULESET_PRESET && ruleset != CTD_RULESET_CLASSIC)) return CTD_EARG;
+  if (!e || (ruleset < CTD_RULESET_PRESET || ruleset > CTD_RULESET_RANDOM)) return CTD_EARG;
   CTD_CUDA(e, cudaSetDevice(e->device));
   CtdPlayoutArgs a;
   memset(&a, 0, sizeof(a));
@@ -1044,7 +1059,7 @@ ctd_status ctd_playout_dev(ctd_engine* e, uint64_t n_games, uint64_t seed, uint6
 
 ctd_status ctd_playout(ctd_engine* e, uint64_t n_games, uint64_t seed, uint64_t first_gid, int ruleset,
                        uint32_t max_steps, int8_t* winner, int8_t* points6, uint16_t* steps, ctd_playout_stats* stats) {
-  if (!e || (ruleset != CTD_RULESET_PRESET && ruleset != CTD_RULESET_CLASSIC)) return CTD_EARG;
+  if (!e || (ruleset < CTD_RULESET_PRESET || ruleset > CTD_RULESET_RANDOM)) return CTD_EARG;
   if (n_games == 0) { if (stats) memset(stats, 0, sizeof(*stats)); return CTD_OK; }
   CTD_CUDA(e, cudaSetDevice(e->device));
   size_t wb = (n_games + 255) & ~(size_t)255, pb = (n_games * 6 + 255) & ~(size_t)255, sb = n_games * 2;
@@ -1102,7 +1117,7 @@ static ctd_status ctd_root_buffers(ctd_engine* e) {
 
 ctd_status ctd_make_roots(ctd_engine* e, uint32_t n, uint64_t seed, uint64_t first_gid, int ruleset, uint32_t back_lo,
                           uint32_t back_hi, uint32_t* root_step) {
-  if (!e || n > e->capacity || back_hi < back_lo || (ruleset != CTD_RULESET_PRESET && ruleset != CTD_RULESET_CLASSIC))
+  if (!e || n > e->capacity || back_hi < back_lo || (ruleset < CTD_RULESET_PRESET || ruleset > CTD_RULESET_RANDOM))
     return CTD_EARG;
   if (n == 0) return CTD_OK;
   CTD_CUDA(e, cudaSetDevice(e->device));
@@ -1210,10 +1225,11 @@ ctd_status ctd_mccfr(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32_t it
   return CTD_OK;
 }
 
-#define CTD_ONE_OPTS 4096
+#define CTD_ONE_OPTS 16384 /* the Cardinal's lists reach ~8000 options */
 #define CTD_ONE_KNOW_OFF 256
-#define CTD_ONE_USED_OFF (256 + 2400)
-#define CTD_ONE_COUNT_OFF (256 + 2400 + 80)
+#define CTD_ONE_KNOW6 (6 * CTD_KNOW_BYTES)
+#define CTD_ONE_USED_OFF (256 + CTD_ONE_KNOW6)
+#define CTD_ONE_COUNT_OFF (256 + CTD_ONE_KNOW6 + 80)
 #define CTD_ONE_WINNER_OFF (CTD_ONE_COUNT_OFF + 4)
 #define CTD_ONE_OPTS_OFF (CTD_ONE_COUNT_OFF + 8)
 #define CTD_ONE_BYTES (CTD_ONE_OPTS_OFF + CTD_ONE_OPTS * 8)
@@ -1237,7 +1253,7 @@ static CtdOneArgs ctd_one_args(ctd_engine* e, int op, bool know) {
 }
 
 ctd_status ctd_game_new(ctd_engine* e, uint64_t seed, uint64_t gid, int ruleset, ctd_state* state, void* know6, uint8_t* used_cards) {
-  if (!e || !state || (ruleset != CTD_RULESET_PRESET && ruleset != CTD_RULESET_CLASSIC)) return CTD_EARG;
+  if (!e || !state || (ruleset < CTD_RULESET_PRESET || ruleset > CTD_RULESET_RANDOM)) return CTD_EARG;
   CTD_CUDA(e, cudaSetDevice(e->device));
   ctd_status s = ctd_one_buffer(e);
   if (s != CTD_OK) return s;
@@ -1247,24 +1263,28 @@ ctd_status ctd_game_new(ctd_engine* e, uint64_t seed, uint64_t gid, int ruleset,
   e->launches++;
   CTD_CUDA(e, cudaGetLastError());
   CTD_CUDA(e, cudaMemcpyAsync(state, e->d_one, sizeof(ctd_state), cudaMemcpyDeviceToHost, e->stream));
-  if (know6) CTD_CUDA(e, cudaMemcpyAsync(know6, e->d_one + CTD_ONE_KNOW_OFF, 2400, cudaMemcpyDeviceToHost, e->stream));
+  if (know6) CTD_CUDA(e, cudaMemcpyAsync(know6, e->d_one + CTD_ONE_KNOW_OFF, CTD_ONE_KNOW6, cudaMemcpyDeviceToHost, e->stream));
   if (used_cards) CTD_CUDA(e, cudaMemcpyAsync(used_cards, e->d_one + CTD_ONE_USED_OFF, 76, cudaMemcpyDeviceToHost, e->stream));
   CTD_CUDA(e, cudaStreamSynchronize(e->stream));
   return CTD_OK;
 }
 
-ctd_status ctd_game_options(ctd_engine* e, const ctd_state* state, const void* know6, ctd_option* opts, uint32_t cap, uint32_t* count) {
+ctd_status ctd_game_options(ctd_engine* e, uint64_t seed, ctd_state* state, const void* know6, ctd_option* opts, uint32_t cap,
+                            uint32_t* count) {
   if (!e || !state || !opts || !count) return CTD_EARG;
   CTD_CUDA(e, cudaSetDevice(e->device));
   ctd_status s = ctd_one_buffer(e);
   if (s != CTD_OK) return s;
   CTD_CUDA(e, cudaMemcpyAsync(e->d_one, state, sizeof(ctd_state), cudaMemcpyHostToDevice, e->stream));
-  if (know6) CTD_CUDA(e, cudaMemcpyAsync(e->d_one + CTD_ONE_KNOW_OFF, know6, 2400, cudaMemcpyHostToDevice, e->stream));
+  if (know6) CTD_CUDA(e, cudaMemcpyAsync(e->d_one + CTD_ONE_KNOW_OFF, know6, CTD_ONE_KNOW6, cudaMemcpyHostToDevice, e->stream));
   CtdOneArgs a = ctd_one_args(e, 1, know6 != nullptr);
+  a.seed = seed;
+  if (cap < a.cap) a.cap = cap;   // a list the caller cannot take leaves the record untouched
   ctd_k_one<<<1, 32, 0, e->stream>>>(a);
   e->launches++;
   CTD_CUDA(e, cudaGetLastError());
   CTD_CUDA(e, cudaMemcpyAsync(count, a.count, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+  CTD_CUDA(e, cudaMemcpyAsync(state, e->d_one, sizeof(ctd_state), cudaMemcpyDeviceToHost, e->stream));
   CTD_CUDA(e, cudaStreamSynchronize(e->stream));
   uint32_t n = *count < cap ? *count : cap;
   if (n > CTD_ONE_OPTS) n = CTD_ONE_OPTS;
@@ -1279,14 +1299,14 @@ ctd_status ctd_game_step(ctd_engine* e, uint64_t seed, ctd_state* state, void* k
   ctd_status s = ctd_one_buffer(e);
   if (s != CTD_OK) return s;
   CTD_CUDA(e, cudaMemcpyAsync(e->d_one, state, sizeof(ctd_state), cudaMemcpyHostToDevice, e->stream));
-  if (know6) CTD_CUDA(e, cudaMemcpyAsync(e->d_one + CTD_ONE_KNOW_OFF, know6, 2400, cudaMemcpyHostToDevice, e->stream));
+  if (know6) CTD_CUDA(e, cudaMemcpyAsync(e->d_one + CTD_ONE_KNOW_OFF, know6, CTD_ONE_KNOW6, cudaMemcpyHostToDevice, e->stream));
   CtdOneArgs a = ctd_one_args(e, 2, know6 != nullptr);
   a.seed = seed; a.chosen = chosen;
   ctd_k_one<<<1, 32, 0, e->stream>>>(a);
   e->launches++;
   CTD_CUDA(e, cudaGetLastError());
   CTD_CUDA(e, cudaMemcpyAsync(state, e->d_one, sizeof(ctd_state), cudaMemcpyDeviceToHost, e->stream));
-  if (know6) CTD_CUDA(e, cudaMemcpyAsync(know6, e->d_one + CTD_ONE_KNOW_OFF, 2400, cudaMemcpyDeviceToHost, e->stream));
+  if (know6) CTD_CUDA(e, cudaMemcpyAsync(know6, e->d_one + CTD_ONE_KNOW_OFF, CTD_ONE_KNOW6, cudaMemcpyDeviceToHost, e->stream));
   CTD_CUDA(e, cudaMemcpyAsync(winner, a.winner, 1, cudaMemcpyDeviceToHost, e->stream));
   CTD_CUDA(e, cudaStreamSynchronize(e->stream));
   return CTD_OK;

@@ -6,7 +6,7 @@
 //   CtdTreeHdr | CtdNode[max_nodes] | CtdChild[child_cap] | double[arr_cap]
 //
 // CtdNode = 128 B header (parent, depth, player, flags, V[6], P[6], pred[6]) + the 256 B packed game record
-// + the 400 B knowledge block of the searching player.  A child entry is (option descriptor, node index);
+// + the 592 B knowledge block of the searching player.  A child entry is (option descriptor, node index);
 // regrets / strategy / cumulative strategy of an expanded node are 3 x K doubles in the array arena
 // (role-pick nodes: 3 x 6 x 10, stored [player][child] like the reference after its transposes, :129-131).
 // Everything is fp64 like the reference's numpy arrays.
@@ -17,8 +17,8 @@
 #include <math.h>
 #include "ctd_engine.cuh"
 
-#define CTD_MCCFR_OPT_CAP 2048 /* legal options of one state that expansion can materialise (preset max 59,
-                                  classic Magician hands reach ~1600); the buffer lives in HBM scratch, one per warp */
+#define CTD_MCCFR_OPT_CAP 4096 /* legal options of one state that expansion can materialise (preset max 59,
+                                  classic Magician hands reach ~1600, the Cardinal ~2600); the buffer lives in HBM scratch, one per warp */
 
 enum { CTD_NF_ROLE_PICK = 1, CTD_NF_TERMINAL = 2, CTD_NF_HAS_PRED = 4 };
 enum { CTD_TREE_OK = 0, CTD_TREE_TERMINAL_ROOT = 1, CTD_TREE_EPOOL = 2, CTD_TREE_EENGINE = 4, CTD_TREE_EOPTS = 8 };
@@ -44,7 +44,7 @@ struct CtdNode {
   CtdKnow know;
   uint8_t snap[CTD_SNAP_BYTES];  // the working record verbatim: node <-> shared memory is a plain vector copy
 };
-static_assert(sizeof(CtdNode) == 160 + 256 + 400 + CTD_SNAP_BYTES, "CtdNode layout");
+static_assert(sizeof(CtdNode) == 160 + 256 + 592 + CTD_SNAP_BYTES, "CtdNode layout");
 static_assert(offsetof(CtdNode, game) % 16 == 0 && offsetof(CtdNode, know) % 16 == 0 && offsetof(CtdNode, snap) % 16 == 0, "CtdNode alignment");
 
 struct CtdChild {
@@ -104,8 +104,7 @@ CTD_HD inline void ctd_copy16(void* dst, const void* src, int bytes) {
 CTD_HD inline double ctd_uniform(CtdWork& w) { return (double)ctd_u32(w) / 4294967296.0; }
 
 // ------------------------------------------------------------------------------------------ determinisation
-// Game.sample_private_information (game/game.py:215-242) and its helpers (:183-213, :245-357); tiers A/B have no
-// warrants or blackmails to re-roll.  `w`/`k` are the hypothetical game; k.viewer is player_character.
+// Game.sample_private_information (game/game.py:215-242) and its helpers (:183-213, :245-357).  `w`/`k` are the hypothetical game; k.viewer is player_character.
 CTD_HD CTD_NI inline void ctd_sample_private(CtdWork& w, CtdKnow& k, const uint8_t* used_cards, bool role_sample,
                                              uint8_t* scratch) {
   const int viewer = k.viewer;
@@ -129,7 +128,9 @@ CTD_HD CTD_NI inline void ctd_sample_private(CtdWork& w, CtdKnow& k, const uint8
       CTD_LOOP for (int i = 0; i < k.hk[h].n; ++i) ++cnt[ctd_ctype(k.pool[k.hk[h].off + i])];
   int nu = 0;
   CTD_LOOP for (int i = 0; i < 76; ++i) {
-    int c = used_cards[i], t = ctd_ctype(c);
+    int c = used_cards[i];
+    if (c == 0xFF) break;  // Game(preset=False) plays with 66 cards
+    int t = ctd_ctype(c);
     if (cnt[t] != 0) --cnt[t];
     else unknown[nu++] = (uint8_t)c;
   }
@@ -148,6 +149,20 @@ CTD_HD CTD_NI inline void ctd_sample_private(CtdWork& w, CtdKnow& k, const uint8
   int uh = 0;
   CTD_LOOP for (int i = 0; i < need; ++i)
     if (uh < nu) w.deck[w.n_deck++] = unknown[uh++];
+  // (3b) sample_warrants_and_blackmails (:321-336): which of the flagged ranks carries the real one is re-rolled,
+  // blackmails first
+  CTD_LOOP for (int pass = 0; pass < 2; ++pass) {
+    const int mask = pass == 0 ? CTD_RP_BLACKMAIL : CTD_RP_WARRANT, sh = pass == 0 ? 5 : 1;
+    uint8_t* keys = scratch + 192;
+    int nk = 0;
+    CTD_LOOP for (int r = 0; r < 8; ++r)
+      if (w.rprops[r] & mask) keys[nk++] = (uint8_t)r;
+    if (nk == 0) continue;
+    ctd_shuffle(w, nk, [keys](int i) -> uint8_t& { return keys[i]; });
+    const int real = keys[0];
+    CTD_LOOP for (int r = 0; r < 8; ++r)
+      if (w.rprops[r] & mask) w.rprops[r] = (uint8_t)((w.rprops[r] & ~mask) | ((r == real ? 1 : 2) << sh));
+  }
   // (4) roles the viewer can still believe in (:230-232, :298-310)
   uint16_t kr[6];
   CTD_LOOP for (int q = 0; q < 6; ++q) kr[q] = k.kr[q];
@@ -326,6 +341,8 @@ CTD_HD CTD_NI inline void ctd_expand(CtdTree& T, int ni) {
     ctd_enumerate(w, e, T.kn);
     if (e.n > CTD_MCCFR_OPT_CAP) { T.hdr->status |= CTD_TREE_EOPTS; return; }
     if (e.n == 0) { T.hdr->status |= CTD_TREE_EENGINE; return; }
+    // the reference enumerates on the node's own game (:134): the Scholar's list shrinks there, and every child is a copy of that
+    if (w.state == 9) ctd_copy16(n.snap, &w, CTD_SNAP_BYTES);
     const uint32_t K = e.n;
     if (!ctd_reserve(T, n, K, 3 * K)) return;
     // the option list must survive the children's own enumerations: park it in the child table

@@ -24,6 +24,12 @@ __device__ __noinline__ uint64_t ctd_choose_scalar(CtdWork& w, int lane, uint64_
   uint64_t d = 0;
   uint32_t n = 0;
   if (lane == 0) {
+    // the Seer's and the Scholar's enumerations are not pure (chance draws, shrinking list): remember what they touch
+    // so that a second selecting pass regenerates the same list
+    const uint32_t draws0 = w.draws, tape0 = w.tape_pos;
+    const uint8_t n7 = w.n_seven;
+    uint8_t s7[7];
+    for (int i = 0; i < 7; ++i) s7[i] = w.seven[i];
     CtdEmit e{buf, CTD_CHOOSE_BUF, 0, 0xFFFFFFFFu, 0};
     ctd_enumerate(w, e);
     n = e.n;
@@ -32,9 +38,13 @@ __device__ __noinline__ uint64_t ctd_choose_scalar(CtdWork& w, int lane, uint64_
       if (k < CTD_CHOOSE_BUF && k < n) {
         d = buf[k];
       } else if (k < n) {
+        const uint32_t draws1 = w.draws, tape1 = w.tape_pos;
+        w.draws = draws0; w.tape_pos = tape0; w.buf_blk = 0xFFFFFFFFu; w.n_seven = n7;
+        for (int i = 0; i < 7; ++i) w.seven[i] = s7[i];
         CtdEmit e2{buf, 0, 0, k, 0};
         ctd_enumerate(w, e2);
         d = e2.got;
+        w.draws = draws1; w.tape_pos = tape1; w.buf_blk = 0xFFFFFFFFu;
       }
     }
   }

@@ -20,7 +20,8 @@ Differences a caller can observe, all deliberate:
     steer the deal.  Choosing among options with `random.choice` is of course still the caller's randomness.
   * Game(preset=True) deals AND runs the first setup_round on the device; the first explicit setup_round() call is
     then a no-op, so `create_game()` behaves as in the reference (run_utils.py:20-27).
-  * Game(preset=False) (random role variants, tier C roles) is not built yet and raises NotImplementedError.
+  * Game(preset=False) deals the random game of game/game.py:491-520 on the device (14 random uniques, four cards
+    each, a random variant of every rank, random pick order and crown).
 """
 import copy
 import ctypes
@@ -190,6 +191,39 @@ class option:
         elif n == "discard_and_draw":
             a["subset_size"] = f["r"]       # every such option has the same effect (game/option_functions.py:295-300)
             a["ordinal"] = f["j"]
+        # ---- the ten deluxe characters (game/agent_functions.py:221-272, :328-419, :446-504)
+        elif n == "magistrate_warrant":
+            a["real_target"] = f["rank"]
+            a["fake_targets"] = [f["named"], f["count"]]
+        elif n == "blackmail":
+            a["real_target"] = f["rank"]
+            a["fake_target"] = f["named"]
+        elif n in ("reveal_blackmail_as_blackmailer", "reveal_warrant_as_magistrate"):
+            a["target"] = f["target"]
+            a["choice"] = NAMED_NAMES[f["named"]]
+        elif n == "give_crown":
+            a["target"] = f["target"]
+            a["gold_or_card"] = "nothing" if f["named"] == 13 else NAMED_NAMES[f["named"]]
+        elif n == "give_back_card":
+            # one card per seat the Seer took from, in seat order (game.seer_taken_card_from); zip() may run short
+            codes = [f["a"] + 1, f["b"] + 1, f["count"], f["r"], f["j"] & 0x3F]
+            a["card_handouts"] = [card(c - 1) for c in codes if c > 0]
+        elif n == "scholar_card_pick":
+            a["choice"] = card(f["a"])
+        elif n == "cardinal_exchange":
+            a["target"] = f["target"]
+            a["built_card"] = card(f["a"])
+            a["replica"] = f["replica"]
+            a["factory"] = bool(f["build"])
+            a["n_cards_to_give"] = f["count"]   # which f["count"]-subset of the other cards: ordinal j of the thinned list
+            a["ordinal"] = f["j"]
+        elif n == "marshal_steal":
+            a["target"] = f["target"]
+            a["choice"] = card(f["a"])
+        elif n == "diplomat_exchange":
+            a["target"] = f["target"]
+            a["choice"] = card(f["a"])
+            a["give"] = card(f["b"])
         return a
 
     def __eq__(self, other):
@@ -212,9 +246,9 @@ class Game:
     """game/game.py `Game` for the fixed rulesets: a 256-byte record, the six observers' knowledge and used_cards on
     the host; every transition runs on the device."""
 
-    def __init__(self, preset=True, engine=None, seed=DEFAULT_SEED, gid=None, ruleset=RULESET_PRESET):
-        if not preset:
-            raise NotImplementedError("Game(preset=False) (random role variants / tier C roles) is not built yet")
+    def __init__(self, preset=True, engine=None, seed=DEFAULT_SEED, gid=None, ruleset=None):
+        if ruleset is None:
+            ruleset = RULESET_PRESET if preset else 2   # Game(preset=False): CTD_RULESET_RANDOM (game/game.py:491-520)
         self._engine = engine or default_engine()
         self.seed = int(seed)
         self.gid = next(_gid_counter) if gid is None else int(gid)
@@ -264,17 +298,12 @@ class Game:
     def get_options_from_state(self):
         """game/game.py:415-418."""
         lib, h = self._engine._lib, self._engine._h
-        cap = 256
-        while True:
-            opts = np.zeros(cap, dtype=np.uint64)
-            n = ctypes.c_uint32()
-            st = self._engine._check(lib.ctd_game_options(h, self._rec.ctypes.data, self._know.ctypes.data, opts.ctypes.data,
-                                                          cap, ctypes.byref(n)), "ctd_game_options", allow=(3,))
-            if st == 0:
-                return [option(d, self) for d in opts[:n.value]]
-            if cap >= 4096:
-                raise EngineError("more than 4096 options")
-            cap = 4096
+        cap = 16384   # one call: the Seer's / Scholar's enumerations are not repeatable (they draw chance / shrink a list)
+        opts = np.zeros(cap, dtype=np.uint64)
+        n = ctypes.c_uint32()
+        self._engine._check(lib.ctd_game_options(h, self.seed, self._rec.ctypes.data, self._know.ctypes.data, opts.ctypes.data,
+                                                 cap, ctypes.byref(n)), "ctd_game_options")
+        return [option(d, self) for d in opts[:n.value]]
 
     def _step(self, desc):
         lib, h = self._engine._lib, self._engine._h

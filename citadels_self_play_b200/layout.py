@@ -53,20 +53,21 @@ def opt_fields(d):
 
 
 # ---- MCCFR tree block (csrc/ctd_mccfr.cuh) ----
-KNOW_BYTES = 400
+KNOW_BYTES = 592
+SNAP_BYTES = 1232   # CtdWork snapshot (csrc/ctd_engine.cuh CTD_SNAP_BYTES)
 HK_DTYPE = np.dtype([("pid", np.int8), ("conf", np.uint8), ("flags", np.uint8), ("n", np.uint8), ("off", np.uint16),
                      ("pad", np.uint16)])
 KNOW_DTYPE = np.dtype([("viewer", np.uint8), ("conf_mask", np.uint8), ("n_hk", np.uint8), ("wiz_n", np.uint8),
-                       ("kr", np.uint16, 6), ("hk", HK_DTYPE, 8), ("wiz_cards", np.uint8, 48), ("pool", np.uint8, 256),
+                       ("kr", np.uint16, 6), ("hk", HK_DTYPE, 32), ("wiz_cards", np.uint8, 48), ("pool", np.uint8, 256),
                        ("pool_used", np.uint16), ("err", np.uint8), ("pad", np.uint8, 13)])
 assert KNOW_DTYPE.itemsize == KNOW_BYTES
 NODE_DTYPE = np.dtype([("parent", np.int32), ("depth", np.uint16), ("player", np.uint8), ("flags", np.uint8),
                        ("n_children", np.uint32), ("child_cap", np.uint32), ("child_off", np.uint32),
                        ("arr_off", np.uint32), ("visits", np.uint32), ("pad0", np.uint32), ("V", np.float64, 6),
                        ("P", np.float64, 6), ("pred", np.float32, 6), ("order", np.uint8, 6), ("gstate", np.uint8),
-                       ("winner", np.int8), ("game", STATE_DTYPE), ("know", KNOW_DTYPE), ("snap", np.uint8, 1136)])
+                       ("winner", np.int8), ("game", STATE_DTYPE), ("know", KNOW_DTYPE), ("snap", np.uint8, SNAP_BYTES)])
 NODE_BYTES = NODE_DTYPE.itemsize
-assert NODE_BYTES == 816 + 1136
+assert NODE_BYTES == 160 + 256 + KNOW_BYTES + SNAP_BYTES
 CHILD_DTYPE = np.dtype([("desc", np.uint64), ("node", np.uint32), ("pad", np.uint32)])
 TREE_HDR_DTYPE = np.dtype([("n_nodes", np.uint32), ("max_nodes", np.uint32), ("child_used", np.uint32),
                            ("child_cap", np.uint32), ("arr_used", np.uint32), ("arr_cap", np.uint32),

@@ -155,8 +155,9 @@ ctd_status ctd_set_tapes(ctd_engine* e, uint32_t n, const uint8_t* tape, const u
 /* Game(preset=True); game.setup_round()  (run_utils.py:20-27) */
 ctd_status ctd_game_new(ctd_engine* e, uint64_t seed, uint64_t gid, int ruleset, ctd_state* state, void* know6,
                         uint8_t* used_cards);
-/* game.get_options_from_state()  (game/game.py:415-418) */
-ctd_status ctd_game_options(ctd_engine* e, const ctd_state* state, const void* know6, ctd_option* opts, uint32_t cap,
+/* game.get_options_from_state()  (game/game.py:415-418).  Not const: the Seer's give-back list is built with fresh
+ * shuffles and the Scholar's enumeration shrinks seven_drawn_cards in the reference too (game/agent_functions.py:332-361, :462-470) */
+ctd_status ctd_game_options(ctd_engine* e, uint64_t seed, ctd_state* state, const void* know6, ctd_option* opts, uint32_t cap,
                             uint32_t* count);
 /* option.carry_out(game)  (game/option.py:118-122); *winner = winning seat or -1 */
 ctd_status ctd_game_step(ctd_engine* e, uint64_t seed, ctd_state* state, void* know6, ctd_option chosen, int8_t* winner);
@@ -188,13 +189,13 @@ ctd_status ctd_playout_dev(ctd_engine* e, uint64_t n_games, uint64_t seed, uint6
                            uint32_t max_steps, ctd_playout_stats* stats, float* elapsed_ms);
 /* ---- MCCFR (algorithms/deep_mccfr.py CFRNode) ----
  * A CFR root is a game slot plus what its player to move has learnt (Agent.known_hands / known_roles,
- * game/agent.py:25-26) -- 400 bytes, layout `CtdKnow` in csrc/ctd_engine.cuh -- plus Game.used_cards in deal
+ * game/agent.py:25-26) -- 592 bytes, layout `CtdKnow` in csrc/ctd_engine.cuh -- plus Game.used_cards in deal
  * order (76 bytes, game/game.py:424) and the id that keys the tree's Philox stream. */
-#define CTD_KNOW_BYTES 400
+#define CTD_KNOW_BYTES 592
 #define CTD_MCCFR_MAX_RESULT 128
 typedef struct ctd_mccfr_result {
   uint32_t status;       /* 0 ok; 1 terminal root (the reference's run_mccfr raises ValueError); 2 node pool
-                            exhausted; 4 engine error; 8 more than 2048 options at an expanded node */
+                            exhausted; 4 engine error; 8 more than 4096 options at an expanded node */
   uint32_t n_nodes;
   uint32_t iterations;
   uint32_t rng_draws;

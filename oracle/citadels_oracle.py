@@ -379,10 +379,10 @@ class Game:
         for _ in range(4):
             for p in range(6):
                 self.hand[p].append(self.deck.pop(0))
-        self.variant = [ch.randbelow(3) for _ in range(8)]
+        self.variant = [ch.randbelow_game(3) for _ in range(8)]
         po = ch.perm(6)
         self.order = [[0, 1, 2, 3, 4, 5][i] for i in po]
-        self.crown = ch.randbelow(6)
+        self.crown = ch.randbelow_game(6)
 
     # ------------------------------------------------------------------ list helpers (game/deck.py)
     @staticmethod
@@ -1571,11 +1571,12 @@ class Game:
         return f
 
     def pack_know(self, viewer):
-        """The engine's 400-byte knowledge block of one observer (csrc/ctd_engine.cuh `CtdKnow`)."""
-        b = bytearray(400)
+        """The engine's 592-byte knowledge block of one observer (csrc/ctd_engine.cuh `CtdKnow`)."""
+        b = bytearray(592)   # header 16 | hk[32] x 8 | wiz_cards[48] @272 | pool[256] @320 | pool_used @576
         b[0] = viewer
         b[1] = sum(1 << q for q in range(6) if self.kr_conf[viewer][q])
         hks = self.kh[viewer]
+        assert len(hks) <= 32
         b[2] = len(hks)
         wiz = self.wiz_cards if self.wiz_target != 0xFF else []
         b[3] = len(wiz)
@@ -1585,10 +1586,10 @@ class Game:
         for i, h in enumerate(hks):
             struct.pack_into("<bBBBHH", b, 16 + 8 * i, h.pid, h.conf, (1 if h.wizard else 0) | (2 if h.used else 0),
                              len(h.cards), pos, 0)
-            b[128 + pos:128 + pos + len(h.cards)] = bytes(h.cards)
+            b[320 + pos:320 + pos + len(h.cards)] = bytes(h.cards)
             pos += len(h.cards)
-        b[80:80 + len(wiz)] = bytes(wiz)
-        struct.pack_into("<H", b, 384, pos)
+        b[272:272 + len(wiz)] = bytes(wiz)
+        struct.pack_into("<H", b, 576, pos)
         return bytes(b)
 
     def unpack_know(self, blob, used_cards):
@@ -1604,11 +1605,11 @@ class Game:
         self.kh[v] = []
         for i in range(n_hk):
             pid, conf, flags, n, off, _ = struct.unpack_from("<bBBBHH", blob, 16 + 8 * i)
-            h = HandKnowledge(pid, list(blob[128 + off:128 + off + n]), conf, bool(flags & 1))
+            h = HandKnowledge(pid, list(blob[320 + off:320 + off + n]), conf, bool(flags & 1))
             h.used = bool(flags & 2)
             self.kh[v].append(h)
-        self.wiz_cards = list(blob[80:80 + wiz_n])
-        self.used_cards = [int(c) for c in used_cards]
+        self.wiz_cards = list(blob[272:272 + wiz_n])
+        self.used_cards = [int(c) for c in used_cards if int(c) != 0xFF]   # 0xFF pads the 66-card random deal to 76
         return v
 
     @classmethod

@@ -59,6 +59,8 @@ class PhiloxChance:
     def randbelow(self, n):
         return (self.u32() * n) >> 32
 
+    randbelow_game = randbelow   # draws that belong to the game itself (role variants, crown seat): same stream
+
     def uniform(self):
         """[0,1) with 32 bits, as a float64 (CFR: HandKnowledge use test)."""
         return self.u32() / 4294967296.0
@@ -99,6 +101,13 @@ class TapeChance:
         assert v < n
         return v
 
+    def randbelow_game(self, n):
+        """A chance draw of the game itself (not the caller's option choice): one tape entry."""
+        v = self.tape[self.pos]
+        self.pos += 1
+        assert v < n
+        return v
+
 
 class RecordingChance:
     """Wraps another source and records the tape TapeChance would need."""
@@ -117,4 +126,9 @@ class RecordingChance:
     def randbelow(self, n):
         v = self.inner.randbelow(n)
         self.choices.append(v)
+        return v
+
+    def randbelow_game(self, n):
+        v = self.inner.randbelow(n)
+        self.tape.append(v)
         return v

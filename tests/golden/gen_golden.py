@@ -22,6 +22,11 @@ SEED = 0xC17ADE15
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+def visible(rec):
+    """Reference-visible bytes of a packed record: [0,228) + seer_mask, seven_n (229,230) + seven[] (240..246)."""
+    return bytes(rec[:228]) + bytes(rec[229:231]) + bytes(rec[240:247])
+
+
 def _one(args):
     gid, ruleset, full = args
     from oracle.philox import PhiloxChance, RecordingChance
@@ -37,7 +42,7 @@ def _one(args):
         rec = H.ref_pack(g, ruleset)
         db = np.asarray(d, dtype="<u8").tobytes()
         nopt.append(len(d))
-        hs.append(zlib.crc32(rec[:228]))
+        hs.append(zlib.crc32(visible(rec)))
         ho.append(zlib.crc32(db))
         if full:
             states.append(rec)
@@ -149,6 +154,7 @@ def _mccfr_one(args):
     root = H.ref_pack(g, ruleset)
     know = H.ref_pack_know(g, viewer)
     used = bytes(H.card_code(c) for c in g.used_cards.cards)
+    used += b"\xff" * (76 - len(used))   # Game(preset=False) plays with 66 cards
     out = dict(gid=gid, root=root, know=know, used=used, root_step=steps, terminal=bool(g.terminal))
     nodes = []
     if not g.terminal:
@@ -184,14 +190,14 @@ def _mccfr_one(args):
         out["t_val"] = [t[2].numpy() for t in tg]
         out["t_dist"] = [t[3].numpy() for t in tg]
     out["nchild"] = [len(n.children) for n in nodes]
-    out["desc"] = [H.ref_descriptors([c[0]])[0] if c[0].name != "discard_and_draw" else 0 for n in nodes for c in n.children]
+    out["desc"] = [H.ref_descriptors([c[0]])[0] if c[0].name not in ("discard_and_draw", "cardinal_exchange") else 0 for n in nodes for c in n.children]
     out["V"] = [list(n.node_value) for n in nodes]
     out["P"] = [list(n.winning_probabilities) for n in nodes]
     out["R"] = [float(x) for n in nodes for x in np.asarray(n.cumulative_regrets, dtype=float).ravel()]
     out["S"] = [float(x) for n in nodes for x in np.asarray(n.strategy, dtype=float).ravel()]
     out["C"] = [float(x) for n in nodes for x in np.asarray(n.cumulative_strategy, dtype=float).ravel()]
     out["narr"] = [int(np.asarray(n.cumulative_regrets).size) for n in nodes]
-    out["game_crc"] = [zlib.crc32(H.ref_pack(n.game, ruleset)[:228]) for n in nodes]
+    out["game_crc"] = [zlib.crc32(visible(H.ref_pack(n.game, ruleset))) for n in nodes]
     out["know_crc"] = [zlib.crc32(H.ref_pack_know(n.game, viewer)) for n in nodes]
     return out
 
@@ -205,7 +211,7 @@ def gen_mccfr(name, ruleset, gids, back_hi, iters, procs=8, deep=0):
     out = dict(seed=np.uint64(SEED), ruleset=np.int32(ruleset), iterations=np.int32(iters), back_hi=np.int32(back_hi),
                gids=np.asarray(gids, dtype=np.uint64), max_depth=np.int32(deep),
                roots=np.frombuffer(b"".join(r["root"] for r in res), dtype=np.uint8).reshape(-1, 256),
-               knows=np.frombuffer(b"".join(r["know"] for r in res), dtype=np.uint8).reshape(-1, 400),
+               knows=np.frombuffer(b"".join(r["know"] for r in res), dtype=np.uint8).reshape(-1, 592),
                used=np.frombuffer(b"".join(r["used"] for r in res), dtype=np.uint8).reshape(-1, 76),
                root_step=np.asarray([r["root_step"] for r in res], dtype=np.int32),
                terminal=np.asarray([r["terminal"] for r in res], dtype=bool),
@@ -237,10 +243,15 @@ if __name__ == "__main__":
         gen_traces("classic_traces.npz", 1, list(range(100000, 100300)))
         gen_traces("preset_full.npz", 0, list(range(2000, 2006)), full=True)
         gen_traces("classic_full.npz", 1, list(range(102000, 102004)), full=True)
+    if what in ("all", "traces", "random"):
+        gen_traces("random_traces.npz", 2, list(range(200000, 200500)))
+        gen_traces("random_full.npz", 2, list(range(202000, 202006)), full=True)
     if what in ("all", "mccfr"):
         gen_mccfr("mccfr_preset.npz", 0, list(range(3000, 3024)), 20, 200)
         gen_mccfr("mccfr_preset_deep_back.npz", 0, list(range(3100, 3112)), 300, 200)
         gen_mccfr("mccfr_classic.npz", 1, list(range(103000, 103008)), 60, 200)
+    if what in ("all", "mccfr", "mccfr_random"):
+        gen_mccfr("mccfr_random.npz", 2, list(range(203000, 203016)), 80, 200)
     if what in ("all", "mccfr2000"):
         gen_mccfr("mccfr_preset_2000it.npz", 0, list(range(3200, 3206)), 45, 2000)
     if what in ("all", "deep"):

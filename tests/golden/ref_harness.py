@@ -30,6 +30,11 @@ def _driven_shuffle(x):
     x[:] = [x[i] for i in perm]
 
 
+def _game_draw(n):
+    ch = _state["chance"]
+    return ch.randbelow_game(n) if hasattr(ch, "randbelow_game") else ch.randbelow(n)
+
+
 def _raise_index():
     raise IndexError("Cannot choose from an empty sequence")
 
@@ -50,8 +55,8 @@ def load_reference():
     _random.shuffle = _driven_shuffle          # before `from random import shuffle` in game/deck.py
     # Game.set_random_game (game/game.py:491-520): sample / choice / randint through the same chance source
     _random.sample = lambda pop, k: [pop[i] for i in _state["chance"].perm(len(pop))[:k]]
-    _random.randint = lambda a, b: a + _state["chance"].randbelow(b - a + 1)
-    _random.choice = lambda seq: _raise_index() if not len(seq) else seq[_state["chance"].randbelow(len(seq))]
+    _random.randint = lambda a, b: a + _game_draw(b - a + 1)
+    _random.choice = lambda seq: _raise_index() if not len(seq) else seq[_game_draw(len(seq))]
     import game.deck
     import game.game
     game.deck.shuffle = _driven_shuffle
@@ -290,12 +295,13 @@ def ref_knowledge(g):
 
 
 def ref_pack_know(g, viewer):
-    """Reference Agent.known_roles / known_hands of `viewer` -> the engine's 400-byte knowledge block."""
+    """Reference Agent.known_roles / known_hands of `viewer` -> the engine's 592-byte knowledge block."""
     import struct
     pl = g.players[viewer]
-    b = bytearray(400)
+    b = bytearray(592)   # header 16 | hk[32] x 8 | wiz_cards[48] @272 | pool[256] @320 | pool_used @576
     b[0] = viewer
     b[1] = sum(1 << q for q in range(6) if pl.known_roles[q].confirmed)
+    assert len(pl.known_hands) <= 32
     b[2] = len(pl.known_hands)
     wiz = [hk for p in g.players for hk in p.known_hands if hk.wizard]
     wcards = [card_code(c) for c in wiz[0].hand.cards] if wiz else []
@@ -310,8 +316,8 @@ def ref_pack_know(g, viewer):
         cards = [card_code(c) for c in hk.hand.cards]
         struct.pack_into("<bBBBHH", b, 16 + 8 * i, hk.player_id, hk.confidence,
                          (1 if hk.wizard else 0) | (2 if hk.used else 0), len(cards), pos, 0)
-        b[128 + pos:128 + pos + len(cards)] = bytes(cards)
+        b[320 + pos:320 + pos + len(cards)] = bytes(cards)
         pos += len(cards)
-    b[80:80 + len(wcards)] = bytes(wcards)
-    struct.pack_into("<H", b, 384, pos)
+    b[272:272 + len(wcards)] = bytes(wcards)
+    struct.pack_into("<H", b, 576, pos)
     return bytes(b)

@@ -5,6 +5,12 @@ import numpy as np
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
+def visible(rec):
+    """Reference-visible bytes of a packed record (include/citadels_b200.h): [0,228) + seer_mask, seven_n + seven[]."""
+    rec = bytes(rec)
+    return rec[:228] + rec[229:231] + rec[240:247]
+
+
 class Traces:
     def __init__(self, name):
         with np.load(os.path.join(GOLDEN, name)) as f:

@@ -1,6 +1,8 @@
 // Host build of the engine's rules code (ctd_engine.cuh) -- a TEST VEHICLE so the kernel logic can be
 // replayed against the golden traces without a GPU.  It is not part of the product and the package never
 // loads it (the product path fails loudly when the CUDA library is missing).
+#include <cstdio>
+#include <cstdlib>
 #include "../../citadels_self_play_b200/csrc/ctd_engine.cuh"
 #include "../../citadels_self_play_b200/csrc/ctd_mccfr.cuh"
 #include <string.h>
@@ -24,13 +26,17 @@ void hs_new_game(uint64_t seed, uint64_t gid, int ruleset, const uint8_t* tape, 
   ctd_setup_round(w);
   ctd_pack(w, out);
 }
-int hs_enumerate(const ctd_state* s, uint64_t* opts, uint32_t cap, uint8_t* err) {
+// enumeration may draw chance (Seer give-back) and may shrink seven_drawn_cards (Scholar): the record is written back
+int hs_enumerate(ctd_state* s, uint64_t* opts, uint32_t cap, uint8_t* err, uint64_t seed, uint64_t gid, const uint8_t* tape,
+                 uint32_t tape_len) {
   CtdWork& w = g_w;
   memset(&w, 0, sizeof(w));
   ctd_unpack(s, w);
+  chance_for(w, seed, gid, tape, tape_len);
   CtdEmit e{opts, cap, 0, 0xFFFFFFFFu, 0};
   ctd_enumerate(w, e);
   if (err) *err = w.err;
+  ctd_pack(w, s);
   return (int)e.n;
 }
 int hs_step(ctd_state* s, uint64_t d, uint64_t seed, uint64_t gid, const uint8_t* tape, uint32_t tape_len) {
@@ -48,15 +54,14 @@ int hs_playout(uint64_t seed, uint64_t gid, int ruleset, uint32_t max_steps, int
   CtdWork& w = g_w;
   memset(&w, 0, sizeof(w));
   ctd_new_game(w, seed, gid, ruleset);
-  uint64_t buf[8];
+  // one materialising pass (the Seer's / Scholar's enumerations are not pure, so no count-then-select here)
+  static uint64_t buf[8192];
   while (!(w.gflags & 2) && !w.err && w.steps < max_steps) {
-    CtdEmit e{buf, 0, 0, 0xFFFFFFFFu, 0};
+    CtdEmit e{buf, 8192, 0, 0xFFFFFFFFu, 0};
     ctd_enumerate(w, e);
-    if (e.n == 0) { w.err |= CTD_ERR_REF_RAISE; break; }
+    if (e.n == 0 || e.n > 8192) { w.err |= CTD_ERR_REF_RAISE; break; }
     uint32_t k = ctd_randbelow(w, e.n);
-    CtdEmit e2{buf, 0, 0, k, 0};
-    ctd_enumerate(w, e2);
-    ctd_apply(w, e2.got);
+    ctd_apply(w, buf[k]);
   }
   if (!(w.gflags & 2) && !w.err) w.err |= CTD_ERR_MAXSTEPS;
   for (int p = 0; p < 6; ++p) points6[p] = w.points[p];
@@ -91,6 +96,8 @@ int hs_mccfr(const ctd_state* root, const CtdKnow* know, const uint8_t* used_car
   ctd_tree_init(T, max_nodes, child_cap, arr_cap, know->viewer, gid, false, false);
   ctd_cfr_train(T, iters);
   ctd_tree_pack_nodes(T);
+  if (getenv("HS_DEBUG")) fprintf(stderr, "hs_mccfr gid %llu status %u w.err %u kn.err %u nodes %u\n", (unsigned long long)gid,
+                                  T.hdr->status, w.err, kn.err, T.hdr->n_nodes);
   return (int)T.hdr->status;
 }
 int hs_sizeof_node() { return (int)sizeof(CtdNode); }

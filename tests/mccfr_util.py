@@ -3,7 +3,7 @@ import os
 import zlib
 import numpy as np
 
-from tests.golden_util import GOLDEN
+from tests.golden_util import GOLDEN, visible
 
 
 class MccfrGolden:
@@ -35,7 +35,7 @@ def oracle_preorder(node):
     for n in node.walk():
         yield dict(nchild=len(n.children), desc=np.asarray([c[0] for c in n.children], dtype=np.uint64), V=n.V, P=n.P,
                    R=np.asarray(n.R, dtype=float).ravel(), S=np.asarray(n.s, dtype=float).ravel(),
-                   C=np.asarray(n.C, dtype=float).ravel(), game_crc=zlib.crc32(n.game.pack()[:228]),
+                   C=np.asarray(n.C, dtype=float).ravel(), game_crc=zlib.crc32(visible(n.game.pack())),
                    know_crc=zlib.crc32(n.game.pack_know(n.orig)))
 
 
@@ -54,7 +54,7 @@ def tree_preorder(tv):
         R, S, C = tv.arrays(i)
         yield dict(nchild=k, desc=child_desc[o:o + k], V=V[i], P=P[i],
                    R=np.asarray(R).ravel(), S=np.asarray(S).ravel(), C=np.asarray(C).ravel(),
-                   game_crc=zlib.crc32(raw[i, g0:g0 + 228].tobytes()), know_crc=zlib.crc32(raw[i, k0:k0 + 400].tobytes()))
+                   game_crc=zlib.crc32(visible(raw[i, g0:g0 + 256].tobytes())), know_crc=zlib.crc32(raw[i, k0:k0 + 592].tobytes()))
         stack.extend(int(x) for x in child_node[o:o + k][::-1])
 
 

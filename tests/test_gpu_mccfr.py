@@ -15,7 +15,7 @@ def engine():
     e.close()
 
 
-@pytest.mark.parametrize("name", ["mccfr_preset.npz", "mccfr_preset_deep_back.npz", "mccfr_classic.npz", "mccfr_preset_2000it.npz"])
+@pytest.mark.parametrize("name", ["mccfr_preset.npz", "mccfr_preset_deep_back.npz", "mccfr_classic.npz", "mccfr_random.npz", "mccfr_preset_2000it.npz"])
 def test_trees_match_reference(engine, name):
     """SURVEY 8(d) parity gate 3: every node of trees grown by the real reference's CFRNode.cfr_train(200) --
     options, regrets, strategies, values (1e-9 relative; the gate asks 1e-5), game record and knowledge block."""

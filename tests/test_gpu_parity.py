@@ -4,7 +4,7 @@ import zlib
 import numpy as np
 import pytest
 
-from tests.golden_util import Traces
+from tests.golden_util import Traces, visible
 
 pytestmark = pytest.mark.gpu
 
@@ -42,7 +42,7 @@ def _replay(engine, name, with_tape):
         idx = base[live] + k
         assert np.array_equal(counts[live], T.nopt[idx].astype(np.uint32)), "option count mismatch at step %d" % k
         for g, i in zip(live, idx):
-            assert zlib.crc32(states[g, :228].tobytes()) == int(T.state_crc[i]), (name, "state", int(g), k)
+            assert zlib.crc32(visible(states[g].tobytes())) == int(T.state_crc[i]), (name, "state", int(g), k)
             assert zlib.crc32(opts[g, :counts[g]].astype("<u8").tobytes()) == int(T.opts_crc[i]), (name, "opts", int(g), k)
         chosen = np.zeros(n, dtype=np.uint64)
         chosen[live] = opts[live, T.chosen[idx].astype(np.int64)]
@@ -67,7 +67,12 @@ def test_replay_classic_tapes(engine):
     assert _replay(engine, "classic_traces.npz", True) > 100000
 
 
-@pytest.mark.parametrize("name", ["preset_traces.npz", "classic_traces.npz"])
+def test_replay_random_tapes(engine):
+    """Game(preset=False): all 24 characters, random uniques / variants / order / crown (500 recorded reference games)."""
+    assert _replay(engine, "random_traces.npz", True) > 150000
+
+
+@pytest.mark.parametrize("name", ["preset_traces.npz", "classic_traces.npz", "random_traces.npz"])
 def test_fused_playout_matches_reference_finals(engine, name):
     """The fused Philox playout kernel reproduces the reference's terminal states for the golden gids."""
     T = Traces(name)
@@ -83,7 +88,7 @@ def test_fused_playout_matches_reference_finals(engine, name):
 def test_fused_playout_vs_oracle_fresh_seeds(engine):
     """Fresh (seed, gid) pairs the fixtures do not cover: CUDA vs the Python oracle, bit-exact outcomes."""
     from oracle import citadels_oracle as O
-    for ruleset, seed, gid0, n in ((0, 12345, 7_000_000, 48), (1, 0xDEADBEEFCAFE, 1 << 33, 32)):
+    for ruleset, seed, gid0, n in ((0, 12345, 7_000_000, 48), (1, 0xDEADBEEFCAFE, 1 << 33, 32), (2, 424242, 9_000_000, 32)):
         out = engine.playout(n, seed=seed, first_gid=gid0, ruleset=ruleset)
         for i in range(n):
             w, pts, steps, _ = O.playout(seed, gid0 + i, ruleset)
@@ -126,7 +131,7 @@ def test_distribution_vs_reference_sample(engine):
     Two-sample tests at the 99% level (chi-square with 5 dof: 15.09; |z| < 2.576 Bonferroni-relaxed to 3.2
     over the 13 z-tests)."""
     import os
-    from tests.golden_util import GOLDEN
+    from tests.golden_util import GOLDEN, visible
     ref = np.load(os.path.join(GOLDEN, "ref_outcomes_preset.npz"))
     n = 1 << 18
     out = engine.playout(n, seed=2024, first_gid=0)

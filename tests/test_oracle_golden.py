@@ -9,7 +9,7 @@ import pytest
 
 from oracle import citadels_oracle as O
 from oracle.philox import PhiloxChance, TapeChance, philox4x32_10
-from tests.golden_util import Traces
+from tests.golden_util import Traces, visible
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -35,7 +35,7 @@ def _oracle_replay(T, g, use_tape):
     for k in range(sl.start, sl.stop):
         opts = og.options()
         assert len(opts) == T.nopt[k]
-        assert zlib.crc32(og.pack()[:228]) == int(T.state_crc[k]), (g, k - sl.start)
+        assert zlib.crc32(visible(og.pack())) == int(T.state_crc[k]), (g, k - sl.start)
         assert zlib.crc32(np.asarray(opts, dtype="<u8").tobytes()) == int(T.opts_crc[k]), (g, k - sl.start)
         i = ch.randbelow(len(opts))
         assert i == T.chosen[k]
@@ -44,21 +44,21 @@ def _oracle_replay(T, g, use_tape):
     assert og.pack()[:228] == T.final[g][:228].tobytes()
 
 
-@pytest.mark.parametrize("name,count", [("preset_traces.npz", 60), ("classic_traces.npz", 30)])
+@pytest.mark.parametrize("name,count", [("preset_traces.npz", 60), ("classic_traces.npz", 30), ("random_traces.npz", 40)])
 def test_oracle_replays_golden_philox(name, count):
     T = Traces(name)
     for g in range(0, len(T), max(1, len(T) // count)):
         _oracle_replay(T, g, use_tape=False)
 
 
-@pytest.mark.parametrize("name,count", [("preset_traces.npz", 20), ("classic_traces.npz", 10)])
+@pytest.mark.parametrize("name,count", [("preset_traces.npz", 20), ("classic_traces.npz", 10), ("random_traces.npz", 15)])
 def test_oracle_replays_golden_tape(name, count):
     T = Traces(name)
     for g in range(3, len(T), max(1, len(T) // count)):
         _oracle_replay(T, g, use_tape=True)
 
 
-@pytest.mark.parametrize("name", ["preset_full.npz", "classic_full.npz"])
+@pytest.mark.parametrize("name", ["preset_full.npz", "classic_full.npz", "random_full.npz"])
 def test_oracle_full_states_and_descriptors(name):
     """Fixtures that keep every packed state and every descriptor: byte-for-byte, plus pack/unpack round trip."""
     T = Traces(name)
@@ -69,11 +69,12 @@ def test_oracle_full_states_and_descriptors(name):
         for k in range(sl.start, sl.stop):
             opts = og.options()
             rec = og.pack()
-            assert rec[:228] == T.states[k][:228].tobytes()
+            assert visible(rec) == visible(T.states[k].tobytes())
             assert opts == [int(x) for x in T.descs[T.desc_off[k]:T.desc_off[k + 1]]]
             rt = O.Game.unpack(rec)
-            assert rt.pack()[:228] == rec[:228]
-            assert rt.options() == opts
+            assert visible(rt.pack()) == visible(rec)
+            if og.state not in (8, 9):   # the Seer's / Scholar's enumerations are not pure (chance draws, shrinking list)
+                assert rt.options() == opts
             og.apply(opts[ch.randbelow(len(opts))])
 
 
@@ -85,13 +86,13 @@ def hostsim():
     lib = ctypes.CDLL(os.path.join(d, "libctd_hostsim.so"))
     u64, u32, vp, ci = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int
     lib.hs_new_game.argtypes = [u64, u64, ci, vp, u32, vp]
-    lib.hs_enumerate.argtypes = [vp, vp, u32, vp]
+    lib.hs_enumerate.argtypes = [vp, vp, u32, vp, u64, u64, vp, u32]
     lib.hs_step.argtypes = [vp, u64, u64, u64, vp, u32]
     lib.hs_playout.argtypes = [u64, u64, ci, u32, vp, vp, vp, vp]
     return lib
 
 
-@pytest.mark.parametrize("name,stride", [("preset_traces.npz", 4), ("classic_traces.npz", 3)])
+@pytest.mark.parametrize("name,stride", [("preset_traces.npz", 4), ("classic_traces.npz", 3), ("random_traces.npz", 2)])
 def test_kernel_rules_host_build_replays_tapes(hostsim, name, stride):
     """ctd_engine.cuh (the code the kernels run), compiled for the host, against recorded reference games."""
     T = Traces(name)
@@ -104,15 +105,15 @@ def test_kernel_rules_host_build_replays_tapes(hostsim, name, stride):
         hostsim.hs_new_game(T.seed, gid, T.ruleset, tape.ctypes.data, len(tape), st.ctypes.data)
         sl = T.game_steps(g)
         for k in range(sl.start, sl.stop):
-            n = hostsim.hs_enumerate(st.ctypes.data, opts.ctypes.data, 8192, err.ctypes.data)
+            n = hostsim.hs_enumerate(st.ctypes.data, opts.ctypes.data, 8192, err.ctypes.data, T.seed, gid, tape.ctypes.data, len(tape))
             assert n == T.nopt[k] and err[0] == 0
-            assert zlib.crc32(st[:228].tobytes()) == int(T.state_crc[k])
+            assert zlib.crc32(visible(st.tobytes())) == int(T.state_crc[k])
             assert zlib.crc32(opts[:n].astype("<u8").tobytes()) == int(T.opts_crc[k])
             hostsim.hs_step(st.ctypes.data, int(opts[T.chosen[k]]), T.seed, gid, tape.ctypes.data, len(tape))
         assert st[:228].tobytes() == T.final[g][:228].tobytes()
 
 
-@pytest.mark.parametrize("name", ["preset_traces.npz", "classic_traces.npz"])
+@pytest.mark.parametrize("name", ["preset_traces.npz", "classic_traces.npz", "random_traces.npz"])
 def test_kernel_rules_host_build_fused_playout(hostsim, name):
     T = Traces(name)
     for g in range(len(T)):
