@@ -550,8 +550,7 @@ CTD_HD CTD_NI inline void ctd_deal_preset(CtdWork& w, int ruleset, uint8_t* used
     // Game.set_random_game (game/game.py:491-520): random.sample(uniques, 14) = first 14 of a 24-permutation, Deck()
     // shuffle of the 66 cards, four cards each dealt round-robin from the top, a random variant per rank, a shuffled
     // pick order, a random crown.
-    uint8_t ubuf[24];  // not w.scratch: the tape form of ctd_shuffle stages through it
-    uint8_t* u = ubuf;
+    uint8_t* u = w.scratch + 96;  // the tape form of ctd_shuffle stages through scratch[0, n): keep clear of it
     CTD_LOOP for (int i = 0; i < 24; ++i) u[i] = (uint8_t)i;
     ctd_shuffle(w, 24, [u](int i) -> uint8_t& { return u[i]; });
     CTD_LOOP for (int i = 0; i < 52; ++i) w.deck[i] = (uint8_t)ctd_base_deck(i);
@@ -707,8 +706,7 @@ CTD_HD CTD_NI inline void ctd_seer_give_back_options(CtdWork& w, int p, E& e) {
   int k = 0;
   CTD_LOOP for (int q = 0; q < 6; ++q) k += (w.seer_mask >> q) & 1;
   const int n = w.n_hand[p];
-  uint8_t rembuf[CTD_HAND_CAP];  // not w.scratch: the tape form of ctd_shuffle stages through it
-  uint8_t* rem = rembuf;
+  uint8_t* rem = w.scratch + 64;  // <= 48 cards; the tape form of ctd_shuffle stages through scratch[0, n <= 48)
   CTD_LOOP for (int pos = 0; pos < k; ++pos)
     CTD_LOOP for (int ci = 0; ci < n; ++ci) {
       const int card = w.hand[p][ci], tc = ctd_ctype(card);

@@ -72,10 +72,12 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_reset(ctd_state* slots, uint3
 }
 
 // Enumeration is read-only except in two states of the deluxe characters: the Seer's give-back list is built with
-// fresh shuffles (chance is consumed) and the Scholar's list shrinks game.seven_drawn_cards; those records are written back.
-__global__ void __launch_bounds__(CTD_BLOCK) ctd_k_enumerate(ctd_state* slots, uint32_t n, ctd_option* opts,
+// fresh shuffles (chance is consumed) and the Scholar's list shrinks game.seven_drawn_cards.  Those records are written to
+// `shadow`; the host commits the shadow only when every list of the batch fitted (a caller that has to retry with a larger
+// stride must find the slots untouched).
+__global__ void __launch_bounds__(CTD_BLOCK) ctd_k_enumerate(const ctd_state* slots, uint32_t n, ctd_option* opts,
                                                              uint32_t* counts, uint32_t stride, uint8_t* errs, uint64_t seed,
-                                                             CtdTapes tapes) {
+                                                             CtdTapes tapes, ctd_state* shadow, uint32_t* any_dirty) {
   __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
   __shared__ ctd_state stage[CTD_WARPS_PER_BLOCK];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -83,22 +85,20 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_enumerate(ctd_state* slots, u
   if (slot >= n) return;
   CtdWork& w = works[wib];
   ctd_record_load(&slots[slot], &stage[wib], lane);
-  int dirty = 0;
   if (lane == 0) {
     ctd_unpack(&stage[wib], w);
     w.k0 = (uint32_t)seed; w.k1 = (uint32_t)(seed >> 32);
     w.stream = 0;
     ctd_attach_tape(w, tapes, slot);
-    dirty = (w.state == 8 || w.state == 9) && !(w.gflags & 2);
+    const bool dirty = (w.state == 8 || w.state == 9) && !(w.gflags & 2);
     CtdEmit e{opts + (size_t)slot * stride, stride, 0, 0xFFFFFFFFu, 0};
     ctd_enumerate(w, e);
     counts[slot] = e.n;
     errs[slot] = w.err;
-    dirty = dirty && e.n <= stride;   // a list that did not fit is enumerated again by the caller: leave the record alone
-    if (dirty) ctd_pack(w, &stage[wib]);
+    if (dirty) { ctd_pack(w, &stage[wib]); atomicOr(any_dirty, 1u); }
   }
-  dirty = __shfl_sync(CTD_FULL, dirty, 0);
-  if (dirty) ctd_record_store(&slots[slot], &stage[wib], lane);
+  __syncwarp();
+  ctd_record_store(&shadow[slot], &stage[wib], lane);
 }
 
 __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_step(ctd_state* slots, uint32_t n, const ctd_option* chosen,
@@ -961,20 +961,30 @@ ctd_status ctd_enumerate(ctd_engine* e, uint32_t n, ctd_option* opts, uint32_t* 
   if (n == 0) return CTD_OK;
   CTD_CUDA(e, cudaSetDevice(e->device));
   size_t ob = (size_t)n * stride * sizeof(ctd_option), cb = (size_t)n * sizeof(uint32_t);
-  size_t cb_al = (cb + 255) & ~(size_t)255;
-  ctd_status s = ctd_scratch(e, ob + cb_al + n);
+  size_t cb_al = (cb + 255) & ~(size_t)255, eb_al = ((size_t)n + 255) & ~(size_t)255;
+  ctd_status s = ctd_scratch(e, ob + cb_al + eb_al + 256 + (size_t)n * sizeof(ctd_state));
   if (s != CTD_OK) return s;
   ctd_option* d_opts = (ctd_option*)e->d_scratch;
   uint32_t* d_counts = (uint32_t*)((char*)e->d_scratch + ob);
   uint8_t* d_errs = (uint8_t*)e->d_scratch + ob + cb_al;
-  ctd_k_enumerate<<<ctd_blocks(n), CTD_BLOCK, 0, e->stream>>>(e->d_slots, n, d_opts, d_counts, stride, d_errs, e->seed, ctd_tapes(e));
+  uint32_t* d_dirty = (uint32_t*)((char*)e->d_scratch + ob + cb_al + eb_al);
+  ctd_state* d_shadow = (ctd_state*)((char*)e->d_scratch + ob + cb_al + eb_al + 256);
+  CTD_CUDA(e, cudaMemsetAsync(d_dirty, 0, 4, e->stream));
+  ctd_k_enumerate<<<ctd_blocks(n), CTD_BLOCK, 0, e->stream>>>(e->d_slots, n, d_opts, d_counts, stride, d_errs, e->seed, ctd_tapes(e),
+                                                              d_shadow, d_dirty);
   e->launches++;
   CTD_CUDA(e, cudaGetLastError());
+  uint32_t dirty = 0;
   CTD_CUDA(e, cudaMemcpyAsync(counts, d_counts, cb, cudaMemcpyDeviceToHost, e->stream));
+  CTD_CUDA(e, cudaMemcpyAsync(&dirty, d_dirty, 4, cudaMemcpyDeviceToHost, e->stream));
   CTD_CUDA(e, cudaMemcpyAsync(opts, d_opts, ob, cudaMemcpyDeviceToHost, e->stream));
   CTD_CUDA(e, cudaStreamSynchronize(e->stream));
   for (uint32_t i = 0; i < n; ++i)
     if (counts[i] > stride) return CTD_ECAP;
+  if (dirty) {  // Seer / Scholar enumerations changed their records: commit
+    CTD_CUDA(e, cudaMemcpyAsync(e->d_slots, d_shadow, (size_t)n * sizeof(ctd_state), cudaMemcpyDeviceToDevice, e->stream));
+    CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  }
   return CTD_OK;
 }
 

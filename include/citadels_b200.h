@@ -165,7 +165,9 @@ ctd_status ctd_game_step(ctd_engine* e, uint64_t seed, ctd_state* state, void* k
 /* ---- the hot path ---- */
 /* Game.get_options_from_state / Agent.get_options (game/game.py:415-418, game/agent.py:50-83) for slots
  * [0,n): opts[i*stride .. i*stride+counts[i]) in the reference's list order.  Terminal slots report 0.
- * counts[i] > stride => only the first `stride` were written (status CTD_ECAP). */
+ * counts[i] > stride => only the first `stride` were written (status CTD_ECAP) and no slot was changed: call again
+ * with a larger stride.  On CTD_OK the slots of a Seer / Scholar give-back state carry what their enumeration did in
+ * the reference too (chance draws, the shrunk seven_drawn_cards; game/agent_functions.py:332-361, :462-470). */
 ctd_status ctd_enumerate(ctd_engine* e, uint32_t n, ctd_option* opts, uint32_t* counts, uint32_t stride);
 /* (test hook) the fused playout kernel picks its option with a warp-cooperative count/select; this runs that path on
  * slots [0,n) for every k and reports how many picks differ from the ctd_enumerate list (0 everywhere = identical). */

@@ -33,9 +33,9 @@ def test_trees_match_reference(engine, name):
         root = next(G.nodes(r))
         k = root["nchild"]
         assert res["n_children"] == k
-        n = len(root["R"])
-        assert np.allclose(res["cumulative_regrets"][:n], root["R"], rtol=1e-9, atol=1e-12)
-        assert np.allclose(res["cumulative_strategy"][:n], root["C"], rtol=1e-9, atol=1e-12)
+        n = min(len(root["R"]), 128)   # ctd_mccfr_result keeps CTD_MCCFR_MAX_RESULT children; the trees above compare every array in full
+        assert np.allclose(res["cumulative_regrets"][:n], root["R"][:n], rtol=1e-9, atol=1e-12)
+        assert np.allclose(res["cumulative_strategy"][:n], root["C"][:n], rtol=1e-9, atol=1e-12)
         assert np.allclose(res["node_value"], root["V"], rtol=1e-9, atol=1e-12)
 
 
