@@ -32,6 +32,12 @@
 #endif
 
 // ------------------------------------------------------------------------------------------ constants
+#ifndef CTD_PLAYOUT_RING
+/* 1 = the fused playout computes 32 Philox blocks at a time, one per lane (ctd_warp.cuh ctd_ring_refill): 40 fewer warp
+ * instructions per env step (7 %) and bit-identical results, but no faster on B200 -- the kernel is bound by instruction
+ * fetch, not by issue slots (profiles/README.md, round-1 A/B table) -- so the simpler lane-0 stream is the default. */
+#define CTD_PLAYOUT_RING 0
+#endif
 #define CTD_HAND_CAP 48
 #define CTD_BLD_CAP 32 /* the Cardinal builds without limit inside CFR's hypothetical games (19 seen) */
 #define CTD_MUS_CAP 32
@@ -151,6 +157,10 @@ struct alignas(16) CtdWork {
   uint32_t draws;
   uint32_t buf[4];
   uint32_t buf_blk;
+  // playout kernel only: 32 Philox blocks computed one per lane (ctd_ring_refill in ctd_warp.cuh); ring[(b & 31) * 4 ..] holds
+  // block b for b in [ring_hi - 32, ring_hi).  ring == nullptr everywhere else (lane 0 computes blocks one at a time).
+  uint32_t* ring;
+  uint32_t ring_hi;
   const uint8_t* tape;
   uint32_t tape_pos, tape_len;
   uint32_t steps;
@@ -184,10 +194,21 @@ CTD_HD inline void ctd_chance_init(CtdWork& w, uint64_t seed, uint64_t gid, uint
   w.stream = 0;
   w.buf_blk = 0xFFFFFFFFu;
   w.tape = nullptr; w.tape_pos = 0; w.tape_len = 0;
+  w.ring = nullptr; w.ring_hi = 0;
 }
 
-CTD_HD inline uint32_t ctd_u32(CtdWork& w) {
+#ifndef CTD_U32_ATTR
+#if CTD_PLAYOUT_RING
+#define CTD_U32_ATTR CTD_NI /* one copy of the ring test + block refill */
+#else
+#define CTD_U32_ATTR
+#endif
+#endif
+CTD_HD CTD_U32_ATTR inline uint32_t ctd_u32(CtdWork& w) {
   uint32_t blk = w.draws >> 2;
+#if CTD_PLAYOUT_RING
+  if (w.ring != nullptr && w.ring_hi - 1u - blk < 32u) return w.ring[((blk & 31u) << 2) | (w.draws++ & 3u)];
+#endif
   if (blk != w.buf_blk) {
     ctd_philox(blk, w.stream, w.g0, w.g1, w.k0, w.k1, w.buf);
     w.buf_blk = blk;
@@ -1735,5 +1756,6 @@ CTD_HD CTD_NI inline void ctd_unpack(const ctd_state* s, CtdWork& w) {
   w.seer_mask = s->seer_mask; w.n_seven = s->seven_n > 7 ? 7 : s->seven_n;
   CTD_LOOP for (int i = 0; i < 7; ++i) w.seven[i] = s->seven[i];
   w.draws = s->rng_draws; w.buf_blk = 0xFFFFFFFFu; w.tape_pos = s->tape_pos; w.steps = s->steps;
+  w.ring = nullptr; w.ring_hi = 0;
   w.g0 = (uint32_t)s->gid; w.g1 = (uint32_t)(s->gid >> 32);
 }
