@@ -175,7 +175,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--games", type=int, default=1 << 20, help="games per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ref-games-per-core", type=int, default=24)
+    ap.add_argument("--ref-games-per-core", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ruleset", type=int, default=0)
     ap.add_argument("--no-mccfr", action="store_true", help="skip the secondary MCCFR measurement")
@@ -197,6 +197,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from citadels_self_play_b200 import Engine
@@ -241,15 +242,32 @@ def main():
     wall = time.perf_counter() - t0
     launches = eng.launches - launches0
 
-    # ---- end-to-end through the public API with host buffers (D2H of every game's result inside) ----
+    # ---- end-to-end through the public API with HOST buffers: every step copies G packed game records (256 B each) from
+    # pinned host memory into the engine's slots (ctd_load_states), plays them to terminal (ctd_playout_slots) and reads
+    # winner + step count of every game back to the host.  The records are made beforehand, untimed (two alternating sets).
+    eng_h = Engine(capacity=G, device=local)
+    host_sets = []
+    for j in range(min(2, max(args.steps, 1))):
+        buf = torch.empty((G, 256), dtype=torch.uint8, pin_memory=True).numpy()
+        eng_h.reset(G, seed=SEED, first_gid=gid0(2000 + j), ruleset=args.ruleset)
+        eng_h.store_states(G, out=buf)
+        host_sets.append(buf)
+    eng_h.load_states(host_sets[0])
+    eng_h.playout_slots(G)                                   # warm-up of this path
+    launches_h0 = eng_h.launches
     barrier()
     t1 = time.perf_counter()
     e2e_steps = 0
     for k in range(args.steps):
-        out = eng.playout(G, seed=SEED, first_gid=gid0(k), ruleset=args.ruleset, outputs=True)
-        e2e_steps += out["stats"]["steps"]          # per-game winner / scores / steps are in out[...] on the host
+        eng_h.load_states(host_sets[k % len(host_sets)])      # H2D 256*G bytes
+        w_host, s_host = eng_h.playout_slots(G)              # D2H 3*G bytes (int8 winner, uint16 steps per game)
+        e2e_steps += int(s_host.sum(dtype="int64"))
     barrier()
     e2e_wall = time.perf_counter() - t1
+    e2e_launches = eng_h.launches - launches_h0
+    assert (w_host >= 0).all()
+    eng_h.close()
+    del host_sets
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- secondary metric: MCCFR iterations/s (BASELINE configs[2] pure, configs[3] deep), same roots on every rank ----
@@ -316,7 +334,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": "%d preset 6-player games per GPU per step, dealt on device from Philox(seed, gid), "
                                    "uniform-random option to terminal (BASELINE configs[1])" % G,
-                       "ruleset": "preset" if args.ruleset == 0 else "classic", "games_per_gpu_per_step": G,
+                       "ruleset": ["preset", "classic", "random"][args.ruleset], "games_per_gpu_per_step": G,
                        "l2": "no HBM-resident inputs (games are generated on device); 256 MiB flush between iterations",
                        "parallelism": "games sharded by global id, %d rank(s), no step-path collective" % world},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -325,9 +343,10 @@ def main():
                          "note": "algorithmic 512 B/env step (SURVEY 8(d)); the fused kernel keeps the game in shared "
                                  "memory for its ~420 steps, so the real limiter is instruction issue (see profiles/)",
                          "kernel_env_steps_per_s_per_gpu": per_gpu_kernel},
-            "e2e": {"value": e2e_steps / e2e_wall, "unit": "env steps/s", "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": 9 * G + 184},
-            "gpu_launches": launches, "clocks": clocks,
+            "e2e": {"value": e2e_steps / e2e_wall, "unit": "env steps/s", "h2d_bytes_per_step": 256 * G * world,
+                    "d2h_bytes_per_step": 3 * G * world,
+                    "path": "Engine.load_states (pinned host records -> HBM) + Engine.playout_slots (winner, steps -> host)"},
+            "gpu_launches": launches, "gpu_launches_e2e": e2e_launches, "clocks": clocks,
             "outcomes": {"games": G * args.steps * world, "errors": errors, "wins": wins},
         }
         if mccfr is not None:
@@ -343,12 +362,12 @@ def main():
                                    "targets_export_ms": mccfr[8]}}
             if not args.no_cpu_baseline:
                 cores = os.cpu_count() or 1
-                ci, cw = cpu_mccfr(3, cores)
+                ci, cw = cpu_mccfr(12, cores)
                 line["mccfr"]["cpu_baseline"] = {"value": ci / cw, "unit": "iterations/s", "cores": cores, "kind": "port",
-                                                 "sample": "%d roots x 200 iterations, oracle port of run_mccfr" % (3 * cores)}
+                                                 "sample": "%d roots x 200 iterations, oracle port of run_mccfr" % (12 * cores)}
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            per_core = 12
+            per_core = 300   # ~5 s of work per core: pool start-up and imports amortised
             cs, cw = cpu_playouts(per_core, cores)
             line["cpu_baseline"] = {"value": cs / cw, "unit": "env steps/s", "cores": cores, "kind": "port",
                                     "sample": "%d preset games (%d per core), oracle port of run_utils.py:37-41"

@@ -30,6 +30,19 @@
 #define CTD_LOOP
 #define CTD_UNROLL
 #endif
+// On the device every CtdWork / CtdKnow lives in shared memory (all kernels declare them __shared__).  Telling the
+// compiler turns the generic LD.E / ST.E (+ descriptor moves and 64-bit address arithmetic) of the out-of-line rules code
+// into LDS / STS with immediate offsets.
+#if defined(__CUDA_ARCH__) && !defined(CTD_NO_ASSUME_SHARED)
+#define CTD_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
+#define CTD_ASSUME_GLOBAL(p) __builtin_assume(__isGlobal(p))
+#else
+#define CTD_ASSUME_SHARED(p)
+#define CTD_ASSUME_GLOBAL(p)
+#endif
+#define CTD_ASSUME_SHARED_K(p) CTD_ASSUME_SHARED(p)
+// (Only references to whole records carry the hint.  Hinting the raw list pointers of ctd_take_like & co. as well made
+// the kernels fault on the device -- either hint alone was fine, both together were not -- so those stay generic.)
 
 // ------------------------------------------------------------------------------------------ constants
 #ifndef CTD_PLAYOUT_RING
@@ -293,6 +306,7 @@ CTD_HD inline void ctd_kn_init(CtdKnow& k, int viewer) {
 }
 // Agent.substract_from_known_hand_confidences_and_clear_wizard + reset_known_roles (game/agent.py:100-114)
 CTD_HD CTD_NI inline void ctd_kn_setup_round(CtdKnow& k) {
+  CTD_ASSUME_SHARED_K(&k);
   int keep = 0;
   uint16_t pos = 0;
   CTD_LOOP for (int i = 0; i < k.n_hk; ++i) {
@@ -317,6 +331,7 @@ CTD_HD CTD_NI inline void ctd_kn_setup_round(CtdKnow& k) {
 }
 CTD_HD CTD_NI inline void ctd_kn_add_hk(CtdKnow& k, int pid, const uint8_t* cards, int n, int ring_head, int ring_mask,
                                         bool wizard) {
+  CTD_ASSUME_SHARED_K(&k);
   if (k.n_hk >= CTD_KN_HK_MAX || k.pool_used + n > CTD_KN_POOL) { k.err |= CTD_ERR_OVERFLOW; return; }
   CtdHK& h = k.hk[k.n_hk++];
   h.pid = (int8_t)pid; h.conf = 5; h.flags = wizard ? CTD_HK_WIZARD : 0; h.n = (uint8_t)n; h.off = k.pool_used; h.pad = 0;
@@ -325,6 +340,7 @@ CTD_HD CTD_NI inline void ctd_kn_add_hk(CtdKnow& k, int pid, const uint8_t* card
 }
 // remove the first card of type t from entry i (Deck.get_a_card_like_it on the HandKnowledge copy)
 CTD_HD CTD_NI inline void ctd_kn_hk_remove(CtdKnow& k, int i, int t) {
+  CTD_ASSUME_SHARED_K(&k);
   CtdHK& h = k.hk[i];
   CTD_LOOP for (int j = 0; j < h.n; ++j)
     if (ctd_ctype(k.pool[h.off + j]) == t) {
@@ -374,6 +390,7 @@ CTD_HD CTD_NI inline int ctd_take_like(uint8_t* a, uint8_t& n, int t) {
   return t;
 }
 CTD_HD CTD_NI inline void ctd_append(CtdWork& w, uint8_t* a, uint8_t& n, int cap, int c) {
+  CTD_ASSUME_SHARED(&w);
   if (n >= cap) {
 #ifdef CTD_HOST_DEBUG
     fprintf(stderr, "overflow cap %d list-offset %ld state %d\n", cap, (long)(a - (uint8_t*)&w), w.state);
@@ -391,6 +408,7 @@ CTD_HD inline void ctd_disc_push(CtdWork& w, int c) { ctd_append(w, w.disc, w.n_
 
 // reshuffle_deck_if_empty (game/option_functions.py:564-570)
 CTD_HD CTD_NI inline void ctd_reshuffle_if_empty(CtdWork& w) {
+  CTD_ASSUME_SHARED(&w);
   if (w.n_deck == 0 && w.n_disc != 0) {
     uint8_t* d = w.disc;
     ctd_shuffle(w, w.n_disc, [d](int i) -> uint8_t& { return d[i]; });
@@ -402,6 +420,7 @@ CTD_HD CTD_NI inline void ctd_reshuffle_if_empty(CtdWork& w) {
 }
 // reshuffle + draw_card; returns -1 for "Deck Empty" (game/deck.py:57-60), which add_card drops (:62-70)
 CTD_HD CTD_NI inline int ctd_draw(CtdWork& w) {
+  CTD_ASSUME_SHARED(&w);
   ctd_reshuffle_if_empty(w);
   if (w.n_deck == 0) return -1;
   int c = w.deck[w.deck_head];
@@ -425,6 +444,7 @@ CTD_HD inline int ctd_name(const CtdWork& w, int p) {
 }
 // Game.get_player_from_role_id (game/game.py:403-412); -1 when nobody holds it
 CTD_HD CTD_NI inline int ctd_player_from_rank(const CtdWork& w, int rank) {
+  CTD_ASSUME_SHARED(&w);
   int want = rank < 0 ? CTD_ROLE_BEWITCHED : rank;
   CTD_LOOP for (int p = 0; p < 6; ++p) if (w.role[p] == want) return p;
   return -1;
@@ -436,6 +456,7 @@ CTD_HD inline void ctd_clear_done(CtdWork& w) { w.done = 0; w.n_trade = 0; w.n_n
 // Game.setup_round (game/game.py:144-171)
 template <bool KN = true>
 CTD_HD CTD_NI inline void ctd_setup_round(CtdWork& w, CtdKnowSet ks = CtdKnowSet{nullptr, 0}) {
+  CTD_ASSUME_SHARED(&w);
   CTD_LOOP for (int r = 0; r < 8; ++r) w.rprops[r] = 0;
   w.used_len = 0;
   CTD_LOOP for (int i = 0; i < 6; ++i) w.used_roles[i] = 0;
@@ -460,6 +481,7 @@ CTD_HD CTD_NI inline void ctd_setup_round(CtdWork& w, CtdKnowSet ks = CtdKnowSet
 
 // Game.refresh_used_roles (game/game.py:349-357); value+1 encoding keeps Bewitched (-1) sortable as 0
 CTD_HD CTD_NI inline bool ctd_refresh_used_roles(CtdWork& w) {
+  CTD_ASSUME_SHARED(&w);
   uint8_t v[6];
   CTD_LOOP for (int p = 0; p < 6; ++p) {
     int r = w.role[p];
@@ -479,6 +501,7 @@ CTD_HD CTD_NI inline bool ctd_refresh_used_roles(CtdWork& w) {
 
 // Game.setup_next_player (game/game.py:391-401); current < 0 == None
 CTD_HD CTD_NI inline void ctd_setup_next_player(CtdWork& w, int current) {
+  CTD_ASSUME_SHARED(&w);
   int nxt;
   if (w.state == 0) {
     if (!ctd_refresh_used_roles(w)) return;
@@ -504,6 +527,7 @@ CTD_HD CTD_NI inline void ctd_setup_next_player(CtdWork& w, int current) {
 
 // Agent.count_points (game/agent.py:116-143)
 CTD_HD CTD_NI inline int ctd_count_points(const CtdWork& w, int p) {
+  CTD_ASSUME_SHARED(&w);
   int pts = 0;
   const uint8_t* b = w.bld[p];
   int n = w.n_bld[p];
@@ -524,6 +548,7 @@ CTD_HD CTD_NI inline int ctd_count_points(const CtdWork& w, int p) {
 
 // Game.check_game_ending (game/game.py:359-368): first arg-max wins
 CTD_HD CTD_NI inline bool ctd_check_game_ending(CtdWork& w) {
+  CTD_ASSUME_SHARED(&w);
   if (!(w.gflags & 1)) return false;
   int best = -1000, bi = 0;
   CTD_LOOP for (int p = 0; p < 6; ++p) {
@@ -538,6 +563,7 @@ CTD_HD CTD_NI inline bool ctd_check_game_ending(CtdWork& w) {
 
 // move_crown + troneroom_owner_gold (game/option_functions.py:625-631, :588-595)
 CTD_HD CTD_NI inline void ctd_move_crown(CtdWork& w, int target) {
+  CTD_ASSUME_SHARED(&w);
   w.crown = (uint8_t)target;
   CTD_LOOP for (int p = 0; p < 6; ++p)
     if (ctd_owns(w, p, 32)) { w.gold[p] += 1; break; }
@@ -552,6 +578,7 @@ CTD_HD inline void ctd_is_last_round(CtdWork& w) {
 
 // Game.set_preset (game/game.py:420-489): Deck() shuffles the 76 cards, fixed hands are pulled by type
 CTD_HD CTD_NI inline void ctd_deal_preset(CtdWork& w, int ruleset, uint8_t* used_cards_out = nullptr) {
+  CTD_ASSUME_SHARED(&w);
   CTD_LOOP for (int p = 0; p < 6; ++p) {
     w.n_hand[p] = w.n_bld[p] = w.n_mus[p] = w.n_jd[p] = 0;
     w.gold[p] = 2; w.role[p] = CTD_ROLE_NONE; w.replicas[p] = 0; w.pflags[p] = 0;
@@ -681,6 +708,7 @@ CTD_HD CTD_NI inline uint32_t ctd_magician_count(int n, int r) {
 // emperor_options (game/agent_functions.py:368-382)
 template <class E>
 CTD_HD CTD_NI inline void ctd_emperor_options(const CtdWork& w, int p, bool dead, E& e) {
+  CTD_ASSUME_SHARED(&w);
   CTD_LOOP for (int q = 0; q < 6; ++q) {
     if (q == p) continue;
     const uint64_t base = ctd_opt(CTD_K_GIVE_CROWN, p) | ctd_f_target(q);
@@ -694,6 +722,7 @@ CTD_HD CTD_NI inline void ctd_emperor_options(const CtdWork& w, int p, bool dead
 // "afford", the combinations of (gold - cost) other cards to hand over, thinned to about a hundred per card
 template <class E>
 CTD_HD CTD_NI inline void ctd_cardinal_options(const CtdWork& w, int p, E& e) {
+  CTD_ASSUME_SHARED(&w);
   const uint8_t* hand = w.hand[p];
   const int nh = w.n_hand[p];
   uint64_t own = 0;
@@ -724,6 +753,7 @@ CTD_HD CTD_NI inline void ctd_cardinal_options(const CtdWork& w, int p, E& e) {
 // every hand card and three times over it shuffles the other cards (cumulatively) and takes the first k-1.
 template <class E>
 CTD_HD CTD_NI inline void ctd_seer_give_back_options(CtdWork& w, int p, E& e) {
+  CTD_ASSUME_SHARED(&w);
   int k = 0;
   CTD_LOOP for (int q = 0; q < 6; ++q) k += (w.seer_mask >> q) & 1;
   const int n = w.n_hand[p];
@@ -755,6 +785,7 @@ CTD_HD CTD_NI inline void ctd_seer_give_back_options(CtdWork& w, int p, E& e) {
 // very list it iterates: every call shrinks seven_drawn_cards, and every option shares what is left.
 template <class E>
 CTD_HD CTD_NI inline void ctd_scholar_give_back_options(CtdWork& w, int p, E& e) {
+  CTD_ASSUME_SHARED(&w);
   int i = 0;
   while (i < w.n_seven) {
     const int t = ctd_ctype(w.seven[i]);
@@ -767,6 +798,7 @@ CTD_HD CTD_NI inline void ctd_scholar_give_back_options(CtdWork& w, int p, E& e)
 // character_options (game/agent_functions.py:156-209) and the per-role enumerators it dispatches to
 template <class E>
 CTD_HD CTD_NI inline void ctd_character_options(const CtdWork& w, int p, int nm, E& e) {
+  CTD_ASSUME_SHARED(&w);
   if (!(w.done & CTD_DM_CHARACTER)) {
     switch (nm) {
       case CTD_ASSASSIN:  // :213-218
@@ -887,6 +919,7 @@ CTD_HD CTD_NI inline void ctd_character_options(const CtdWork& w, int p, int nm,
 // main_round_options (game/agent_functions.py:133-147); concatenation order is observable
 template <class E>
 CTD_HD CTD_NI inline void ctd_main_round_options(const CtdWork& w, int p, int nm, E& e) {
+  CTD_ASSUME_SHARED(&w);
   const uint8_t* bld = w.bld[p];
   const int nb = w.n_bld[p];
   const uint8_t* hand = w.hand[p];
@@ -942,6 +975,7 @@ CTD_HD CTD_NI inline void ctd_main_round_options(const CtdWork& w, int p, int nm
 // (HandKnowledge.hand); in a playout it equals the target's current hand.  `replica` leaks across iterations.
 template <class E>
 CTD_HD CTD_NI inline void ctd_wizard_take_options(const CtdWork& w, int p, const uint8_t* cards, int n, E& e) {
+  CTD_ASSUME_SHARED(&w);
   int q = w.wiz_target;
   uint64_t own = 0;
   CTD_LOOP for (int i = 0; i < w.n_bld[p]; ++i) own |= 1ull << ctd_ctype(w.bld[p][i]);
@@ -968,6 +1002,7 @@ CTD_HD CTD_NI inline void ctd_wizard_take_options(const CtdWork& w, int p, const
 // Agent.get_options (game/agent.py:50-83).  An empty result with err set means the reference would raise.
 template <class E>
 CTD_HD CTD_NI inline void ctd_enumerate(CtdWork& w, E& e, const CtdKnow* kn = nullptr) {
+  CTD_ASSUME_SHARED(&w);
   if (w.gflags & 2) return;  // terminal: the reference's loops stop here
   const int p = w.player;
   const int st = w.state;
@@ -1070,6 +1105,7 @@ CTD_HD inline void ctd_restore_next(CtdWork& w) {
 
 // carry_out_building (game/option_functions.py:102-127)
 CTD_HD CTD_NI inline void ctd_apply_build(CtdWork& w, int p, int t, int replica) {
+  CTD_ASSUME_SHARED(&w);
   int c = ctd_take_like(w.hand[p], w.n_hand[p], t);
   ctd_append(w, w.bld[p], w.n_bld[p], CTD_BLD_CAP, c);
   if (ctd_name(w, p) != CTD_ALCHEMIST) w.gold[p] -= (int8_t)ctd_ccost(c);
@@ -1095,6 +1131,7 @@ CTD_HD CTD_NI inline void ctd_apply_build(CtdWork& w, int p, int t, int replica)
 // finish_main_sequnce_actions (game/option_functions.py:189-243).  Returns true when the game ended.
 template <bool KN>
 CTD_HD CTD_NI inline bool ctd_apply_finish(CtdWork& w, uint64_t d, CtdKnowSet ks) {
+  CTD_ASSUME_SHARED(&w);
   const int p = CTD_OPT_PERP(d);
   const int pr = w.role[p];
   if (pr >= 8) { w.err |= CTD_ERR_REF_RAISE; return false; }
@@ -1137,6 +1174,7 @@ CTD_HD CTD_NI inline bool ctd_apply_finish(CtdWork& w, uint64_t d, CtdKnowSet ks
 // KN = false instantiates the transition without the knowledge bookkeeping (the playout kernel: smaller image).
 template <bool KN = true>
 CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdKnowSet{nullptr, 0}) {
+  CTD_ASSUME_SHARED(&w);
   const int k = CTD_OPT_KIND(d);
   const int p = CTD_OPT_PERP(d);
   bool won = false;
@@ -1644,6 +1682,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
 
 // run_utils.create_game (run_utils.py:20-27)
 CTD_HD CTD_NI inline void ctd_new_game(CtdWork& w, uint64_t seed, uint64_t gid, int ruleset) {
+  CTD_ASSUME_SHARED(&w);
   ctd_chance_init(w, seed, gid, 0);
   ctd_deal_preset(w, ruleset);
   ctd_setup_round(w);
@@ -1652,6 +1691,7 @@ CTD_HD CTD_NI inline void ctd_new_game(CtdWork& w, uint64_t seed, uint64_t gid, 
 // ------------------------------------------------------------------------------------------ pack / unpack
 // Scalar forms (definition of the layout); ctd_warp.cuh has the lane-parallel device forms.
 CTD_HD CTD_NI inline void ctd_pack(const CtdWork& w, ctd_state* s) {
+  CTD_ASSUME_SHARED(&w);
   {  // zero the record with eight-byte stores (ctd_state is 8-byte aligned)
     uint64_t* z = (uint64_t*)s;
     CTD_LOOP for (int i = 0; i < CTD_STATE_BYTES / 8; ++i) z[i] = 0;
@@ -1706,6 +1746,7 @@ CTD_HD CTD_NI inline void ctd_pack(const CtdWork& w, ctd_state* s) {
 }
 
 CTD_HD CTD_NI inline void ctd_unpack(const ctd_state* s, CtdWork& w) {
+  CTD_ASSUME_SHARED(&w);
   w.err = s->err;
   const uint8_t* arena = s->arena;
   int c = 0;

@@ -88,6 +88,12 @@ struct CtdTree {
   ctd_state* stage; // 16-byte aligned staging record (shared memory on the device)
 };
 
+// address spaces of a tree's parts on the device: working set in shared memory, the tree block in HBM
+#define CTD_TREE_SPACES(T)                                                                                  \
+  CTD_ASSUME_SHARED((T).w); CTD_ASSUME_SHARED((T).kn); CTD_ASSUME_SHARED((T).stage);                         \
+  CTD_ASSUME_GLOBAL((T).hdr); CTD_ASSUME_GLOBAL((T).nodes); CTD_ASSUME_GLOBAL((T).children); CTD_ASSUME_GLOBAL((T).arr); \
+  CTD_ASSUME_GLOBAL((T).opts)
+
 // 16-byte vector copy (both pointers 16-byte aligned, bytes a multiple of 16): the tree lives in HBM and its records
 // move as a handful of independent 128-bit transactions instead of hundreds of dependent byte accesses
 CTD_HD inline void ctd_copy16(void* dst, const void* src, int bytes) {
@@ -101,12 +107,48 @@ CTD_HD inline void ctd_copy16(void* dst, const void* src, int bytes) {
   for (int i = 0; i < n; ++i) d[i] = s[i];
 }
 
+// The same copy with the address spaces spelled out (device only): the working record, the knowledge block and the
+// staging record live in shared memory, tree nodes in HBM.  Through generic pointers every 16 bytes cost ~9 instructions
+// (address arithmetic + descriptor moves around LD.E / ST.E); ld.shared.v4 / st.global.v4 with immediate offsets cost 2.
+#if defined(__CUDA_ARCH__)
+template <int BYTES>
+__device__ __forceinline__ void ctd_copy_s2g(void* gdst, const void* ssrc) {
+  static_assert(BYTES % 16 == 0, "vector copy");
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+  char* g = (char*)gdst;
+#pragma unroll
+  for (int i = 0; i < BYTES; i += 16) {
+    uint32_t x, y, z, w;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(s + i) : "memory");
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(g + i), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+  }
+}
+template <int BYTES>
+__device__ __forceinline__ void ctd_copy_g2s(void* sdst, const void* gsrc) {
+  static_assert(BYTES % 16 == 0, "vector copy");
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(sdst);
+  const char* g = (const char*)gsrc;
+#pragma unroll
+  for (int i = 0; i < BYTES; i += 16) {
+    uint32_t x, y, z, w;
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "l"(g + i) : "memory");
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(s + i), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+  }
+}
+#define CTD_COPY_S2G(dst, src, bytes) ctd_copy_s2g<bytes>(dst, src)
+#define CTD_COPY_G2S(dst, src, bytes) ctd_copy_g2s<bytes>(dst, src)
+#else
+#define CTD_COPY_S2G(dst, src, bytes) ctd_copy16(dst, src, bytes)
+#define CTD_COPY_G2S(dst, src, bytes) ctd_copy16(dst, src, bytes)
+#endif
+
 CTD_HD inline double ctd_uniform(CtdWork& w) { return (double)ctd_u32(w) / 4294967296.0; }
 
 // ------------------------------------------------------------------------------------------ determinisation
 // Game.sample_private_information (game/game.py:215-242) and its helpers (:183-213, :245-357).  `w`/`k` are the hypothetical game; k.viewer is player_character.
 CTD_HD CTD_NI inline void ctd_sample_private(CtdWork& w, CtdKnow& k, const uint8_t* used_cards, bool role_sample,
                                              uint8_t* scratch) {
+  CTD_ASSUME_SHARED(&w); CTD_ASSUME_SHARED(&k); CTD_ASSUME_SHARED(scratch);
   const int viewer = k.viewer;
   // (1) which HandKnowledge entries are believed this time: (confidence - 1) * 0.2 > random()   (:217-222)
   CTD_LOOP for (int i = 0; i < k.n_hk; ++i) {
@@ -219,8 +261,8 @@ CTD_HD CTD_NI inline void ctd_sample_private(CtdWork& w, CtdKnow& k, const uint8
 // ------------------------------------------------------------------------------------------ node helpers
 CTD_HD inline void ctd_node_store(CtdTree& T, CtdNode& n) {
   const CtdWork& w = *T.w;
-  ctd_copy16(n.snap, &w, CTD_SNAP_BYTES);
-  ctd_copy16(&n.know, T.kn, (int)sizeof(CtdKnow));
+  CTD_COPY_S2G(n.snap, &w, CTD_SNAP_BYTES);
+  CTD_COPY_S2G(&n.know, T.kn, (int)sizeof(CtdKnow));
   CTD_LOOP for (int i = 0; i < 6; ++i) n.order[i] = w.order[i];
   n.gstate = w.state;
   n.winner = w.winner;
@@ -237,15 +279,16 @@ CTD_HD inline void ctd_node_pack(CtdTree& T, CtdNode& n) {
 CTD_HD inline void ctd_node_load(CtdTree& T, const CtdNode& n) {
   // chance state lives in the working record and must survive a load
   CtdWork& w = *T.w;
-  ctd_copy16(&w, n.snap, CTD_SNAP_BYTES);   // the chance fields sit outside the snapshot and survive
+  CTD_COPY_G2S(&w, n.snap, CTD_SNAP_BYTES);   // the chance fields sit outside the snapshot and survive
   w.buf_blk = 0xFFFFFFFFu;
   w.g0 = (uint32_t)T.hdr->gid; w.g1 = (uint32_t)(T.hdr->gid >> 32);
   w.tape = nullptr; w.tape_len = 0; w.err = 0;
-  ctd_copy16(T.kn, &n.know, (int)sizeof(CtdKnow));
+  CTD_COPY_G2S(T.kn, &n.know, (int)sizeof(CtdKnow));
 }
 
 // CFRNode.skip_false_choice (:37-49) on the working game
 CTD_HD CTD_NI inline void ctd_skip_false_choice(CtdTree& T) {
+  CTD_TREE_SPACES(T);
   CtdWork& w = *T.w;
   CtdKnowSet ks{T.kn, 1};
   int i = 0;
@@ -263,6 +306,7 @@ CTD_HD CTD_NI inline void ctd_skip_false_choice(CtdTree& T) {
 
 // allocate a child node from the working game (CFRNode.__init__, :9-33); returns its index or -1
 CTD_HD CTD_NI inline int ctd_new_node(CtdTree& T, int parent, int depth) {
+  CTD_TREE_SPACES(T);
   CtdTreeHdr& h = *T.hdr;
   if (h.n_nodes >= h.max_nodes) { h.status |= CTD_TREE_EPOOL; return -1; }
   ctd_skip_false_choice(T);
@@ -274,7 +318,7 @@ CTD_HD CTD_NI inline int ctd_new_node(CtdTree& T, int parent, int depth) {
   n.player = T.w->player;
   n.flags = (uint8_t)((T.w->state == 0 ? CTD_NF_ROLE_PICK : 0) | ((T.w->gflags & 2) ? CTD_NF_TERMINAL : 0));
   n.n_children = 0; n.child_cap = 0; n.child_off = 0; n.arr_off = 0; n.visits = 0; n.pad0 = 0;
-  { uint64_t* z = (uint64_t*)&n.game; CTD_LOOP for (int i = 0; i < (int)sizeof(ctd_state) / 8; ++i) z[i] = 0; }
+  // n.game (the 256-byte packed form) is written by the export pass only (ctd_node_pack)
   CTD_LOOP for (int i = 0; i < 6; ++i) { n.V[i] = 0.0; n.P[i] = 0.0; n.pred[i] = 0.f; }
   ctd_node_store(T, n);
   return idx;
@@ -311,6 +355,7 @@ CTD_HD inline void ctd_maybe_sample(CtdTree& T, const CtdNode& n) {
 
 // CFRNode.expand (:93-179)
 CTD_HD CTD_NI inline void ctd_expand(CtdTree& T, int ni) {
+  CTD_TREE_SPACES(T);
   CtdNode& n = T.nodes[ni];
   CtdWork& w = *T.w;
   CtdKnowSet ks{T.kn, 1};
@@ -342,7 +387,7 @@ CTD_HD CTD_NI inline void ctd_expand(CtdTree& T, int ni) {
     if (e.n > CTD_MCCFR_OPT_CAP) { T.hdr->status |= CTD_TREE_EOPTS; return; }
     if (e.n == 0) { T.hdr->status |= CTD_TREE_EENGINE; return; }
     // the reference enumerates on the node's own game (:134): the Scholar's list shrinks there, and every child is a copy of that
-    if (w.state == 9) ctd_copy16(n.snap, &w, CTD_SNAP_BYTES);
+    if (w.state == 9) CTD_COPY_S2G(n.snap, &w, CTD_SNAP_BYTES);
     const uint32_t K = e.n;
     if (!ctd_reserve(T, n, K, 3 * K)) return;
     // the option list must survive the children's own enumerations: park it in the child table
@@ -394,6 +439,7 @@ CTD_HD inline double* ctd_C(CtdTree& T, const CtdNode& n) {
 
 // CFRNode.update_strategy (:292-319)
 CTD_HD CTD_NI inline void ctd_update_strategy(CtdTree& T, int ni) {
+  CTD_TREE_SPACES(T);
   CtdNode& n = T.nodes[ni];
   const int K = (int)n.n_children;
   if (K == 0) return;  // empty arrays: numpy no-ops
@@ -423,6 +469,7 @@ CTD_HD CTD_NI inline void ctd_update_strategy(CtdTree& T, int ni) {
 // CFRNode.action_choice (:67-91), non-live: sample a child from the (weighted) cumulative strategy.
 // Inverse CDF on one uniform draw: cdf = cumsum(p); cdf /= cdf[-1]; first index with u < cdf.
 CTD_HD CTD_NI inline int ctd_action_choice(CtdTree& T, int ni) {
+  CTD_TREE_SPACES(T);
   CtdNode& n = T.nodes[ni];
   const int K = (int)n.n_children;
   double* C = ctd_C(T, n);
@@ -454,6 +501,7 @@ CTD_HD CTD_NI inline int ctd_action_choice(CtdTree& T, int ni) {
 
 // CFRNode.backpropagate + update_regrets (:231-256, :276-290), iterative instead of recursive
 CTD_HD CTD_NI inline void ctd_backpropagate(CtdTree& T, int ni, const double reward[6]) {
+  CTD_TREE_SPACES(T);
   const bool training = T.hdr->training, model = T.hdr->has_model;
   for (int cur = ni; cur >= 0; cur = T.nodes[cur].parent) {
     CtdNode& n = T.nodes[cur];
@@ -491,6 +539,7 @@ CTD_HD CTD_NI inline void ctd_backpropagate(CtdTree& T, int ni, const double rew
 // Initialise the tree from the working game (root state + knowledge already in T.w / T.kn).
 CTD_HD CTD_NI inline void ctd_tree_init(CtdTree& T, uint32_t max_nodes, uint32_t child_cap, uint32_t arr_cap, int viewer,
                                         uint64_t gid, bool training, bool has_model) {
+  
   CtdTreeHdr& h = *T.hdr;
   h.n_nodes = 0; h.max_nodes = max_nodes; h.child_used = 0; h.child_cap = child_cap; h.arr_used = 0; h.arr_cap = arr_cap;
   h.status = 0; h.iterations = 0; h.rng_draws = 0; h.viewer = (uint8_t)viewer; h.training = training; h.has_model = has_model;
@@ -502,6 +551,7 @@ CTD_HD CTD_NI inline void ctd_tree_init(CtdTree& T, uint32_t max_nodes, uint32_t
 
 // run `iters` iterations of the pure-MCCFR loop; returns the node the walk is standing on
 CTD_HD CTD_NI inline void ctd_cfr_train(CtdTree& T, uint32_t iters) {
+  CTD_TREE_SPACES(T);
   CtdTreeHdr& h = *T.hdr;
   if (h.status & CTD_TREE_TERMINAL_ROOT) return;
   ctd_expand(T, 0);
@@ -532,6 +582,7 @@ CTD_HD CTD_NI inline void ctd_cfr_train(CtdTree& T, uint32_t iters) {
 // reads known_roles[current player][seat].confirmed, which is the same for every observer (conf_mask).
 // Role-pick nodes are encoded with player_id forced to 5 (algorithms/deep_mccfr.py:120-123).
 CTD_HD CTD_NI inline void ctd_encode_game(const CtdWork& w, const CtdKnow& k, int player, float* f) {
+  CTD_ASSUME_SHARED(&w);   // (k is a global record in ctd_k_encode)
   CTD_LOOP for (int i = 0; i < CTD_FEATURES_PAD; ++i) f[i] = 0.f;
   CTD_LOOP for (int r = 0; r < 8; ++r) f[r * 3 + w.variant[r]] = 1.f;
   CTD_LOOP for (int p = 0; p < 6; ++p) {
@@ -564,6 +615,7 @@ CTD_HD CTD_NI inline void ctd_encode_game(const CtdWork& w, const CtdKnow& k, in
 // with `pred` = model_reward_weights * square_and_normalize(model(features)) (:126,:147,:178; train_utils.py:143-145).
 // Returns false when all iterations are done.
 CTD_HD CTD_NI inline bool ctd_cfr_pred_advance(CtdTree& T, uint32_t iters, uint32_t max_depth, float* feat, const float* pred) {
+  CTD_TREE_SPACES(T);
   CtdTreeHdr& h = *T.hdr;
   if (h.phase == 3 || (h.status & CTD_TREE_TERMINAL_ROOT)) { h.phase = 3; return false; }
   T.w->draws = h.rng_draws;
@@ -624,6 +676,7 @@ CTD_HD CTD_NI inline bool ctd_cfr_pred_advance(CtdTree& T, uint32_t iters, uint3
 
 // fill the packed game record of every node (export only)
 CTD_HD CTD_NI inline void ctd_tree_pack_nodes(CtdTree& T) {
+  
   const uint32_t n = T.hdr->n_nodes;
   CTD_LOOP for (uint32_t i = 0; i < n; ++i) ctd_node_pack(T, T.nodes[i]);
 }

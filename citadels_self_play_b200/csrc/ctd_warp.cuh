@@ -38,6 +38,7 @@ __device__ __forceinline__ void ctd_ring_refill(CtdWork& w, int lane) {
 
 // scalar fallback: lane 0 materialises the list, draws k, picks
 __device__ __noinline__ uint64_t ctd_choose_scalar(CtdWork& w, int lane, uint64_t* buf, uint32_t* count_out, int want) {
+  CTD_ASSUME_SHARED(&w);
   uint64_t d = 0;
   uint32_t n = 0;
   if (lane == 0) {

@@ -53,8 +53,9 @@ class Engine:
         a = np.ascontiguousarray(states, dtype=np.uint8).reshape(-1, STATE_BYTES)
         self._check(self._lib.ctd_load_states(self._h, first_slot, len(a), a.ctypes.data), "ctd_load_states")
 
-    def store_states(self, n, first_slot=0):
-        a = np.empty((n, STATE_BYTES), dtype=np.uint8)
+    def store_states(self, n, first_slot=0, out=None):
+        a = np.empty((n, STATE_BYTES), dtype=np.uint8) if out is None else out
+        assert a.dtype == np.uint8 and a.shape == (n, STATE_BYTES) and a.flags.c_contiguous
         self._check(self._lib.ctd_store_states(self._h, first_slot, n, a.ctypes.data), "ctd_store_states")
         return a
 
