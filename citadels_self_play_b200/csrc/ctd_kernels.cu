@@ -412,7 +412,7 @@ __device__ void ctd_write_result(CtdTree& T, ctd_mccfr_result* r) {
 __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) ctd_k_mccfr(CtdMccfrArgs a) {
   __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
   __shared__ CtdKnow knows[CTD_WARPS_PER_BLOCK];
-  __shared__ uint8_t scratch[CTD_WARPS_PER_BLOCK][256];
+  __shared__ __align__(16) uint8_t scratch[CTD_WARPS_PER_BLOCK][384];
   __shared__ __align__(16) ctd_state tstage[CTD_WARPS_PER_BLOCK];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   uint64_t* opts = a.opts_scratch + ((size_t)blockIdx.x * CTD_WARPS_PER_BLOCK + wib) * CTD_MCCFR_OPT_CAP;
@@ -432,6 +432,7 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) ctd_k_mccfr(C
       w.stream = 1;
       w.err = 0;
       ctd_copy16(T.kn, &a.knows[t], (int)sizeof(CtdKnow));
+      ctd_tree_stage_used(T);
       ctd_tree_init(T, a.max_nodes, a.child_cap, a.arr_cap, T.kn->viewer, a.gids[t], false, false);
       ctd_cfr_train(T, a.iterations);
       if (a.results) ctd_write_result(T, &a.results[t]);
@@ -614,7 +615,7 @@ struct CtdPredArgs {
 __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) ctd_k_mccfr_pred(CtdPredArgs p) {
   __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
   __shared__ CtdKnow knows[CTD_WARPS_PER_BLOCK];
-  __shared__ uint8_t scratch[CTD_WARPS_PER_BLOCK][256];
+  __shared__ __align__(16) uint8_t scratch[CTD_WARPS_PER_BLOCK][384];
   __shared__ __align__(16) ctd_state tstage[CTD_WARPS_PER_BLOCK];
   const CtdMccfrArgs& a = p.m;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -643,6 +644,7 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) ctd_k_mccfr_p
         w.err = 0;
         T.kn->err = 0;  // the working set is rebuilt from the tree on the first node load of this wave
       }
+      ctd_tree_stage_used(T);
       const bool was_waiting = T.hdr->phase == 2;
       bool wait = false;
       if (T.hdr->phase != 3) wait = ctd_cfr_pred_advance(T, a.iterations, p.max_depth, p.feat + t * CTD_FEATURES_PAD, p.pred + t * 8);

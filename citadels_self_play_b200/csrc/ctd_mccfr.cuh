@@ -68,7 +68,7 @@ struct CtdTreeHdr {
   uint8_t used_cards[76];  // Game.used_cards in deal order (game/game.py:424); constant over the tree
   uint32_t cur_node;     // node the walk stands on (deep MCCFR is resumed across kernel launches)
 };
-static_assert(sizeof(CtdTreeHdr) == 128, "CtdTreeHdr layout");
+static_assert(sizeof(CtdTreeHdr) == 128 && offsetof(CtdTreeHdr, used_cards) % 16 == 0, "CtdTreeHdr layout");
 
 CTD_HD inline size_t ctd_tree_bytes(uint32_t max_nodes, uint32_t child_cap, uint32_t arr_cap) {
   return sizeof(CtdTreeHdr) + (size_t)max_nodes * sizeof(CtdNode) + (size_t)child_cap * sizeof(CtdChild) +
@@ -84,7 +84,7 @@ struct CtdTree {
   CtdWork* w;       // working game (shared memory on the device)
   CtdKnow* kn;      // working knowledge of the viewer
   uint64_t* opts;   // CTD_MCCFR_OPT_CAP descriptors
-  uint8_t* scratch; // >= 256 bytes
+  uint8_t* scratch; // >= 384 bytes, 16-byte aligned: [0,256) determinisation scratch, [256,336) Game.used_cards staged on chip
   ctd_state* stage; // 16-byte aligned staging record (shared memory on the device)
 };
 
@@ -159,7 +159,7 @@ CTD_HD CTD_NI inline void ctd_sample_private(CtdWork& w, CtdKnow& k, const uint8
   // (2) get_unknown_cards: used_cards minus everything visible, first occurrence per removal  (:183-213)
   uint8_t* unknown = scratch;       // <= 76
   uint8_t* cnt = scratch + 128;     // removals pending per type
-  CTD_LOOP for (int t = 0; t < 40; ++t) cnt[t] = 0;
+  { uint32_t* c4 = (uint32_t*)cnt; CTD_LOOP for (int t = 0; t < 10; ++t) c4[t] = 0; }
   CTD_LOOP for (int p = 0; p < 6; ++p) {
     CTD_LOOP for (int i = 0; i < w.n_bld[p]; ++i) ++cnt[ctd_ctype(w.bld[p][i])];
     CTD_LOOP for (int i = 0; i < w.n_mus[p]; ++i) ++cnt[ctd_ctype(w.mus[p][i])];
@@ -344,12 +344,16 @@ CTD_HD inline uint64_t ctd_carried_form(const CtdWork& w, uint64_t d) {
   return d;
 }
 
+// Game.used_cards is constant over a tree and read 76 bytes at a time by every determinisation: keep a copy next to the
+// working set (shared memory on the device) instead of walking the tree header in HBM.  Call once per (re)attached tree.
+CTD_HD inline void ctd_tree_stage_used(CtdTree& T) { ctd_copy16(T.scratch + 256, T.hdr->used_cards, 80); }
+
 // "sample if it is not the same player's turn as in the parent" (:139-140, :157-158)
 CTD_HD inline void ctd_maybe_sample(CtdTree& T, const CtdNode& n) {
   bool root = n.parent < 0;
   if (root || T.w->player != T.nodes[n.parent].player) {
     bool role_sample = root ? false : T.nodes[n.parent].gstate != 0;
-    ctd_sample_private(*T.w, *T.kn, T.hdr->used_cards, role_sample, T.scratch);
+    ctd_sample_private(*T.w, *T.kn, T.scratch + 256, role_sample, T.scratch);
   }
 }
 

@@ -77,7 +77,7 @@ int hs_mccfr(const ctd_state* root, const CtdKnow* know, const uint8_t* used_car
              uint32_t iters, uint32_t max_nodes, uint32_t child_cap, uint32_t arr_cap, uint8_t* tree_buf) {
   static CtdKnow kn;
   static uint64_t opts[CTD_MCCFR_OPT_CAP];
-  static uint8_t scratch[256];
+  static uint8_t scratch[384] __attribute__((aligned(16)));
   CtdWork& w = g_w;
   memset(&w, 0, sizeof(w));
   CtdTree T;
@@ -89,6 +89,7 @@ int hs_mccfr(const ctd_state* root, const CtdKnow* know, const uint8_t* used_car
   T.w = &w; T.kn = &kn; T.opts = opts; T.scratch = scratch; T.stage = &hs_stage;
   memset(tree_buf, 0, ctd_tree_bytes(max_nodes, child_cap, arr_cap));
   memcpy(T.hdr->used_cards, used_cards, 76);
+  ctd_tree_stage_used(T);
   ctd_unpack(root, w);
   ctd_chance_init(w, seed, gid, 0);
   w.stream = 1;
@@ -109,7 +110,7 @@ int hs_mccfr_pred(const ctd_state* root, const CtdKnow* know, const uint8_t* use
                   uint8_t* tree_buf, hs_eval_fn eval) {
   static CtdKnow kn;
   static uint64_t opts[CTD_MCCFR_OPT_CAP];
-  static uint8_t scratch[256];
+  static uint8_t scratch[384] __attribute__((aligned(16)));
   static float feat[CTD_FEATURES_PAD], pred[8];
   CtdWork& w = g_w;
   memset(&w, 0, sizeof(w));
@@ -122,6 +123,7 @@ int hs_mccfr_pred(const ctd_state* root, const CtdKnow* know, const uint8_t* use
   T.w = &w; T.kn = &kn; T.opts = opts; T.scratch = scratch; T.stage = &hs_stage;
   memset(tree_buf, 0, ctd_tree_bytes(max_nodes, child_cap, arr_cap));
   memcpy(T.hdr->used_cards, used_cards, 76);
+  ctd_tree_stage_used(T);
   ctd_unpack(root, w);
   ctd_chance_init(w, seed, gid, 0);
   w.stream = 1;
