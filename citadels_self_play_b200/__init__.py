@@ -6,5 +6,7 @@ from .engine import Engine, EngineError, RULESET_PRESET, RULESET_CLASSIC, DEFAUL
 from .facade import (Game, Agent, option, Card, CFRNode, create_game, create_a_close_to_finished_game,  # noqa: F401
                      create_a_random_game, run_mccfr)
 
-__all__ = ["Engine", "EngineError", "RULESET_PRESET", "RULESET_CLASSIC", "DEFAULT_SEED", "Game", "Agent", "option", "Card",
+from . import arena  # noqa: F401,E402  (compare_to_random.py semantics: play_games / play_games_batched)
+
+__all__ = ["arena", "Engine", "EngineError", "RULESET_PRESET", "RULESET_CLASSIC", "DEFAULT_SEED", "Game", "Agent", "option", "Card",
            "CFRNode", "create_game", "create_a_close_to_finished_game", "create_a_random_game", "run_mccfr"]
