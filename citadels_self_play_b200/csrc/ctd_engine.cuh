@@ -571,9 +571,13 @@ CTD_HD CTD_NI inline void ctd_move_crown(CtdWork& w, int target) {
 
 // Game.is_last_round (game/game.py:173-181)
 CTD_HD inline void ctd_is_last_round(CtdWork& w) {
-  if (!(w.gflags & 1))
-    CTD_LOOP for (int p = 0; p < 6; ++p)
-      if (w.n_bld[p] == 7) { w.gflags |= 1; w.pflags[p] |= CTD_PF_FIRST7; }
+  if (w.gflags & 1) return;
+  // runs after every carry_out: one flat test first, the per-seat loop only in the step that completes a city
+  const bool any = (w.n_bld[0] == 7) | (w.n_bld[1] == 7) | (w.n_bld[2] == 7) | (w.n_bld[3] == 7) | (w.n_bld[4] == 7) |
+                   (w.n_bld[5] == 7);
+  if (!any) return;
+  CTD_LOOP for (int p = 0; p < 6; ++p)
+    if (w.n_bld[p] == 7) { w.gflags |= 1; w.pflags[p] |= CTD_PF_FIRST7; }
 }
 
 // Game.set_preset (game/game.py:420-489): Deck() shuffles the 76 cards, fixed hands are pulled by type
