@@ -218,7 +218,11 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_PLAYOUT_MIN_BLOCKS) ctd_k_playo
       __syncwarp();
     } else {
       if (lane == 0) {
+#ifdef CTD_EXPERIMENT_GID_MASK   /* developer experiment: many warps play the SAME game (upper bound of what instruction-stream alignment could give) */
+        ctd_chance_init(w, a.seed, a.first_gid + (g & CTD_EXPERIMENT_GID_MASK), 0);
+#else
         ctd_chance_init(w, a.seed, a.first_gid + g, 0);
+#endif
 #if CTD_PLAYOUT_RING
         w.ring = rings[wib];
 #endif
