@@ -410,6 +410,9 @@ __device__ void ctd_write_result(CtdTree& T, ctd_mccfr_result* r) {
   for (uint32_t i = 0; i < na; ++i) { r->cumulative_regrets[i] = R[i]; r->strategy[i] = S[i]; r->cumulative_strategy[i] = C[i]; }
 }
 
+#ifndef CTD_MCCFR_ALL_LANES
+#define CTD_MCCFR_ALL_LANES 1
+#endif
 #ifndef CTD_MCCFR_MIN_BLOCKS
 #define CTD_MCCFR_MIN_BLOCKS 3 /* 80 registers: fewer spills on the single active lane; 24 trees per SM resident (measured best at the 4096-root configuration) */
 #endif
@@ -425,7 +428,11 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) ctd_k_mccfr(C
     if (lane == 0) t = atomicAdd(a.counter, 1ull);
     t = __shfl_sync(CTD_FULL, t, 0);
     if (t >= a.n_roots) break;
-    if (lane == 0) {
+    // Every lane runs the same scalar search on the same data (identical values to identical addresses, control flow
+    // uniform, the warp stays converged): no lane does anything the others do not, but leaf operations that are
+    // lane-parallel by nature -- moving a 1.8 KB node between HBM and the working set -- can split their work over the
+    // lanes without restructuring the walk (CTD_MCCFR_ALL_LANES=0 restores the one-lane form).
+    if (CTD_MCCFR_ALL_LANES || lane == 0) {
       CtdTree T = ctd_tree_at(a.trees + t * a.tree_stride, a.max_nodes, a.child_cap);
       T.w = &works[wib]; T.kn = &knows[wib]; T.opts = opts; T.scratch = scratch[wib]; T.stage = &tstage[wib];
       CtdWork& w = *T.w;
@@ -629,7 +636,7 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) ctd_k_mccfr_p
     if (lane == 0) t = atomicAdd(a.counter, 1ull);
     t = __shfl_sync(CTD_FULL, t, 0);
     if (t >= a.n_roots) break;
-    if (lane == 0) {
+    if (CTD_MCCFR_ALL_LANES || lane == 0) {   // all lanes on the same scalar walk, see ctd_k_mccfr
       CtdTree T = ctd_tree_at(a.trees + t * a.tree_stride, a.max_nodes, a.child_cap);
       T.w = &works[wib]; T.kn = &knows[wib]; T.opts = opts; T.scratch = scratch[wib]; T.stage = &tstage[wib];
       CtdWork& w = *T.w;
@@ -654,7 +661,7 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) ctd_k_mccfr_p
       if (T.hdr->phase != 3) wait = ctd_cfr_pred_advance(T, a.iterations, p.max_depth, p.feat + t * CTD_FEATURES_PAD, p.pred + t * 8);
       (void)was_waiting;
       p.pending[t] = wait ? 1 : 0;
-      if (wait) atomicAdd(p.n_pending, 1u);
+      if (wait && lane == 0) atomicAdd(p.n_pending, 1u);
       if (!wait && a.results) ctd_write_result(T, &a.results[t]);
     }
     __syncwarp();

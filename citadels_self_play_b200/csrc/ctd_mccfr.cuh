@@ -111,29 +111,39 @@ CTD_HD inline void ctd_copy16(void* dst, const void* src, int bytes) {
 // staging record live in shared memory, tree nodes in HBM.  Through generic pointers every 16 bytes cost ~9 instructions
 // (address arithmetic + descriptor moves around LD.E / ST.E); ld.shared.v4 / st.global.v4 with immediate offsets cost 2.
 #if defined(__CUDA_ARCH__)
+// Callers run either on one lane (export / target walks) or with the whole warp converged on the same scalar code
+// (the search kernels, see ctd_k_mccfr): the active lanes split the 16-byte chunks between them.
 template <int BYTES>
 __device__ __forceinline__ void ctd_copy_s2g(void* gdst, const void* ssrc) {
   static_assert(BYTES % 16 == 0, "vector copy");
+  const unsigned m = __activemask();
+  const int nl = __popc(m), rank = __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
   char* g = (char*)gdst;
-#pragma unroll
-  for (int i = 0; i < BYTES; i += 16) {
+  __syncwarp(m);   // every lane's (identical) stores to the source are in place
+#pragma unroll 4
+  for (int i = rank * 16; i < BYTES; i += nl * 16) {
     uint32_t x, y, z, w;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(s + i) : "memory");
     asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(g + i), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
   }
+  __syncwarp(m);
 }
 template <int BYTES>
 __device__ __forceinline__ void ctd_copy_g2s(void* sdst, const void* gsrc) {
   static_assert(BYTES % 16 == 0, "vector copy");
+  const unsigned m = __activemask();
+  const int nl = __popc(m), rank = __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(sdst);
   const char* g = (const char*)gsrc;
-#pragma unroll
-  for (int i = 0; i < BYTES; i += 16) {
+  __syncwarp(m);
+#pragma unroll 4
+  for (int i = rank * 16; i < BYTES; i += nl * 16) {
     uint32_t x, y, z, w;
     asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "l"(g + i) : "memory");
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(s + i), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
   }
+  __syncwarp(m);   // the destination is complete for every lane
 }
 #define CTD_COPY_S2G(dst, src, bytes) ctd_copy_s2g<bytes>(dst, src)
 #define CTD_COPY_G2S(dst, src, bytes) ctd_copy_g2s<bytes>(dst, src)
@@ -329,6 +339,13 @@ CTD_HD inline bool ctd_reserve(CtdTree& T, CtdNode& n, uint32_t kids, uint32_t d
   if (h.child_used + kids > h.child_cap || h.arr_used + doubles > h.arr_cap) { h.status |= CTD_TREE_EPOOL; return false; }
   n.child_off = h.child_used; n.child_cap = kids; h.child_used += kids;
   n.arr_off = h.arr_used; h.arr_used += doubles;
+#if defined(__CUDA_ARCH__)
+  if (__activemask() == 0xFFFFFFFFu) {   // converged warp: the lanes split the zero-fill
+    for (uint32_t i = threadIdx.x & 31u; i < doubles; i += 32u) T.arr[n.arr_off + i] = 0.0;
+    __syncwarp();
+    return true;
+  }
+#endif
   CTD_LOOP for (uint32_t i = 0; i < doubles; ++i) T.arr[n.arr_off + i] = 0.0;
   return true;
 }
