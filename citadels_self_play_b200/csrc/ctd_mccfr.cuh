@@ -604,6 +604,12 @@ CTD_HD CTD_NI inline void ctd_cfr_train(CtdTree& T, uint32_t iters) {
 // Role-pick nodes are encoded with player_id forced to 5 (algorithms/deep_mccfr.py:120-123).
 CTD_HD CTD_NI inline void ctd_encode_game(const CtdWork& w, const CtdKnow& k, int player, float* f) {
   CTD_ASSUME_SHARED(&w);   // (k is a global record in ctd_k_encode)
+#if defined(__CUDA_ARCH__)
+  if (__activemask() == 0xFFFFFFFFu) {   // converged warp (search kernels): the lanes split the zero-fill
+    for (int i = threadIdx.x & 31; i < CTD_FEATURES_PAD; i += 32) f[i] = 0.f;
+    __syncwarp();
+  } else
+#endif
   CTD_LOOP for (int i = 0; i < CTD_FEATURES_PAD; ++i) f[i] = 0.f;
   CTD_LOOP for (int r = 0; r < 8; ++r) f[r * 3 + w.variant[r]] = 1.f;
   CTD_LOOP for (int p = 0; p < 6; ++p) {
