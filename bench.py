@@ -141,7 +141,7 @@ def cpu_mccfr(roots_per_core, cores, iters=200):
     return sum(r[0] for r in res), time.perf_counter() - t0
 
 
-def run_reference_arm(args, rank, world):
+def run_reference_arm(args, rank, world, emit):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
@@ -164,7 +164,7 @@ def run_reference_arm(args, rank, world):
             "cpu_baseline": {"value": v, "unit": "env steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "env steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
@@ -185,9 +185,20 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries the one JSON line and nothing else: library chatter written straight to fd 1 (NCCL prints its
+    # version there under NCCL_DEBUG=VERSION) goes to stderr until the line is printed
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(_real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
 
     if args.impl == "reference":
-        run_reference_arm(args, rank, world)
+        run_reference_arm(args, rank, world, emit)
         return
 
     import torch
@@ -372,7 +383,7 @@ def main():
             line["cpu_baseline"] = {"value": cs / cw, "unit": "env steps/s", "cores": cores, "kind": "port",
                                     "sample": "%d preset games (%d per core), oracle port of run_utils.py:37-41"
                                               % (per_core * cores, per_core)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
