@@ -83,32 +83,36 @@ def gen_traces(name, ruleset, gids, full=False, procs=8):
     print(name, "games", len(gids), "steps", len(nopt), "bytes", os.path.getsize(path))
 
 
-def _mt_game(gid):
+def _mt_game(args):
+    """One game of the unmodified reference under CPython's own Mersenne Twister (random.seed(gid)): shuffles, sample /
+    choice / randint of set_random_game and the caller's option choice all draw from `random`."""
+    gid, ruleset = args
     import random
     from tests.golden import ref_harness as H
-    gg = H.load_reference()
+    H.load_reference()
 
     class MT:
         def perm(self, n):
             idx = list(range(n))
             random.Random.shuffle(random._inst, idx)
             return idx
-    H.set_chance(MT())
+
+        def randbelow(self, n):
+            return random._inst.randrange(n)
     random.seed(gid)
-    g = gg.Game(preset=True)
-    g.setup_round()
+    g = H.new_ref_game(MT(), ruleset)
     steps = 0
     while True:
         opts = g.get_options_from_state()
         steps += 1
-        if opts[random.randrange(len(opts))].carry_out(g):
+        if opts[random._inst.randrange(len(opts))].carry_out(g):
             break
     return [int(g.rewards.argmax())] + [int(x) for x in g.points] + [steps]
 
 
-def gen_outcomes(name, n, procs=8):
+def gen_outcomes(name, n, ruleset=0, procs=8):
     with Pool(procs) as pool:
-        res = pool.map(_mt_game, range(n), chunksize=16)
+        res = pool.map(_mt_game, [(g, ruleset) for g in range(n)], chunksize=16)
     a = np.asarray(res, dtype=np.int16)
     path = os.path.join(HERE, name)
     np.savez_compressed(path, winner=a[:, 0].astype(np.int8), points=a[:, 1:7].astype(np.int8), steps=a[:, 7])
@@ -258,3 +262,6 @@ if __name__ == "__main__":
         gen_mccfr("deep_mccfr_preset.npz", 0, list(range(4000, 4016)), 120, 200, deep=10)
     if what in ("all", "outcomes"):
         gen_outcomes("ref_outcomes_preset.npz", 20000)
+    if what in ("all", "outcomes", "outcomes_bc"):
+        gen_outcomes("ref_outcomes_classic.npz", 12000, ruleset=1)
+        gen_outcomes("ref_outcomes_random.npz", 12000, ruleset=2)

@@ -125,18 +125,27 @@ def test_determinism_and_sharding_invariance(engine):
     assert a["stats"]["wins"] == [x + y for x, y in zip(b1["stats"]["wins"], b2["stats"]["wins"])]
 
 
-def test_distribution_vs_reference_sample(engine):
+@pytest.mark.parametrize("fixture,ruleset", [("ref_outcomes_preset.npz", 0), ("ref_outcomes_classic.npz", 1),
+                                             ("ref_outcomes_random.npz", 2)])
+def test_distribution_vs_reference_sample(engine, fixture, ruleset):
     """SURVEY 8(d) parity gate 2: winner multinomial and per-seat mean score of 2^18 GPU playouts against
-    20,000 games of the unmodified reference under its own Mersenne Twister (tests/golden/ref_outcomes_preset.npz).
+    games of the unmodified reference under its own Mersenne Twister (tests/golden/ref_outcomes_*.npz: 20,000 preset
+    games, 12,000 each of the classic eight and of Game(preset=False)).
     Two-sample tests at the 99% level (chi-square with 5 dof: 15.09; |z| < 2.576 Bonferroni-relaxed to 3.2
     over the 13 z-tests)."""
     import os
-    from tests.golden_util import GOLDEN, visible
-    ref = np.load(os.path.join(GOLDEN, "ref_outcomes_preset.npz"))
+    from tests.golden_util import GOLDEN
+    ref = np.load(os.path.join(GOLDEN, fixture))
     n = 1 << 18
-    out = engine.playout(n, seed=2024, first_gid=0)
+    out = engine.playout(n, seed=2024 + ruleset, first_gid=0, ruleset=ruleset)
     st = out["stats"]
-    assert st["errors"] == 0 and st["games"] == n
+    assert st["games"] == n
+    # Game(preset=False) under uniform random play has games that never end (every hand and the deck empty, nobody can
+    # build: the reference loops forever as well; seed 2026 gid 109177 is one).  The engine stops them at max_steps and
+    # flags them; nothing else may be flagged.
+    capped = out["steps"] == 4096
+    assert st["errors"] == int(capped.sum()) and (out["winner"][capped] == -1).all()
+    assert st["errors"] == 0 if ruleset != 2 else st["errors"] <= 3
     rw = np.bincount(ref["winner"], minlength=6).astype(np.float64)
     gw = np.asarray(st["wins"], dtype=np.float64)
     nr, ng = rw.sum(), gw.sum()
@@ -144,10 +153,10 @@ def test_distribution_vs_reference_sample(engine):
     chi2 = (((rw - nr * pooled) ** 2) / (nr * pooled)).sum() + (((gw - ng * pooled) ** 2) / (ng * pooled)).sum()
     assert chi2 < 15.09, ("winner distribution", chi2, rw / nr, gw / ng)
     rp = ref["points"].astype(np.float64)
-    gp = out["points"].astype(np.float64)
+    gp = out["points"][~capped].astype(np.float64)
     z = (gp.mean(0) - rp.mean(0)) / np.sqrt(gp.var(0) / ng + rp.var(0) / nr)
     assert np.all(np.abs(z) < 3.2), ("mean points", z)
-    rs, gs = ref["steps"].astype(np.float64), out["steps"].astype(np.float64)
+    rs, gs = ref["steps"].astype(np.float64), out["steps"][~capped].astype(np.float64)
     zs = (gs.mean() - rs.mean()) / np.sqrt(gs.var() / ng + rs.var() / nr)
     assert abs(zs) < 3.2, ("steps", gs.mean(), rs.mean(), zs)
-    assert abs(gs.std() - rs.std()) < 2.0
+    assert abs(gs.std() - rs.std()) < (2.0 if ruleset == 0 else 3.0)
