@@ -619,7 +619,8 @@ struct CtdPredArgs {
   float* feat;        // [n_roots][CTD_FEATURES_PAD]
   float* pred;        // [n_roots][8]
   uint8_t* pending;   // [n_roots]
-  uint32_t* n_pending;
+  uint32_t* n_pending;   // [0] trees waiting for a leaf value, [1] trees that yielded mid-walk
+  uint32_t budget;       // iterations a tree may walk in one wave
 };
 
 // one wave of CFRNode.cfr_pred for every tree: walk until a leaf value is needed (or the budget is spent)
@@ -656,13 +657,13 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) ctd_k_mccfr_p
         T.kn->err = 0;  // the working set is rebuilt from the tree on the first node load of this wave
       }
       ctd_tree_stage_used(T);
-      const bool was_waiting = T.hdr->phase == 2;
-      bool wait = false;
-      if (T.hdr->phase != 3) wait = ctd_cfr_pred_advance(T, a.iterations, p.max_depth, p.feat + t * CTD_FEATURES_PAD, p.pred + t * 8);
-      (void)was_waiting;
-      p.pending[t] = wait ? 1 : 0;
-      if (wait && lane == 0) atomicAdd(p.n_pending, 1u);
-      if (!wait && a.results) ctd_write_result(T, &a.results[t]);
+      int r = CTD_PRED_DONE;
+      if (T.hdr->phase != 3)
+        r = ctd_cfr_pred_advance(T, a.iterations, p.max_depth, p.feat + t * CTD_FEATURES_PAD, p.pred + t * 8, p.budget);
+      p.pending[t] = r == CTD_PRED_WAIT ? 1 : 0;
+      if (r == CTD_PRED_WAIT && lane == 0) atomicAdd(p.n_pending, 1u);
+      if (r == CTD_PRED_YIELD && lane == 0) atomicAdd(p.n_pending + 1, 1u);
+      if (r == CTD_PRED_DONE && a.results) ctd_write_result(T, &a.results[t]);
     }
     __syncwarp();
   }
@@ -1442,7 +1443,7 @@ static ctd_status ctd_pred_buffers(ctd_engine* e) {
   CTD_CUDA(e, cudaMalloc((void**)&e->d_feat, (size_t)e->capacity * CTD_FEATURES_PAD * sizeof(float)));
   CTD_CUDA(e, cudaMalloc((void**)&e->d_pred, (size_t)e->capacity * 8 * sizeof(float)));
   CTD_CUDA(e, cudaMalloc((void**)&e->d_pending, (size_t)e->capacity));
-  CTD_CUDA(e, cudaMalloc((void**)&e->d_n_pending, sizeof(uint32_t)));
+  CTD_CUDA(e, cudaMalloc((void**)&e->d_n_pending, 2 * sizeof(uint32_t)));
   CTD_CUDA(e, cudaMemsetAsync(e->d_feat, 0, (size_t)e->capacity * CTD_FEATURES_PAD * sizeof(float), e->stream));
   CTD_CUDA(e, cudaMemsetAsync(e->d_pred, 0, (size_t)e->capacity * 8 * sizeof(float), e->stream));
   CTD_CUDA(e, cudaMemsetAsync(e->d_pending, 0, (size_t)e->capacity, e->stream));
@@ -1577,6 +1578,11 @@ ctd_status ctd_mccfr_pred(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32
   a.n_roots = n_roots; a.roots = e->d_slots; a.knows = e->d_knows; a.used_cards = e->d_used_cards; a.gids = e->d_gids;
   a.seed = seed; a.iterations = iterations; a.max_nodes = mn; a.child_cap = cc; a.arr_cap = ac;
   a.trees = e->d_trees; a.tree_stride = stride; a.results = (ctd_mccfr_result*)e->d_scratch; a.counter = e->d_counter;
+  {  // wave budget: trees that never reach the depth limit would otherwise walk all their iterations in the first wave
+    const char* env = getenv("CTD_PRED_BUDGET");
+    p.budget = env ? (uint32_t)strtoul(env, nullptr, 10) : 16u;
+    if (p.budget == 0) p.budget = 0xFFFFFFFFu;
+  }
   p.max_depth = max_depth; p.feat = e->d_feat; p.pred = e->d_pred; p.pending = e->d_pending; p.n_pending = e->d_n_pending;
   int per_sm = 0;
   CTD_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctd_k_mccfr_pred, CTD_BLOCK, 0));
@@ -1594,19 +1600,21 @@ ctd_status ctd_mccfr_pred(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32
   CTD_CUDA(e, cudaEventRecord(e->ev0, e->stream));
   uint32_t waves = 0;
   for (;; ++waves) {
-    if (waves > iterations + 2) { snprintf(e->err, sizeof(e->err), "ctd_mccfr_pred: wave limit"); return CTD_ECAP; }
+    if (waves > 2 * iterations + 4) { snprintf(e->err, sizeof(e->err), "ctd_mccfr_pred: wave limit"); return CTD_ECAP; }
     CTD_CUDA(e, cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream));
-    CTD_CUDA(e, cudaMemsetAsync(e->d_n_pending, 0, sizeof(uint32_t), e->stream));
+    CTD_CUDA(e, cudaMemsetAsync(e->d_n_pending, 0, 2 * sizeof(uint32_t), e->stream));
     p.first = waves == 0;
     ctd_k_mccfr_pred<<<grid, CTD_BLOCK, 0, e->stream>>>(p);
     e->launches++;
     CTD_CUDA(e, cudaGetLastError());
-    uint32_t np = 0;
-    CTD_CUDA(e, cudaMemcpyAsync(&np, e->d_n_pending, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    uint32_t np[2] = {0, 0};
+    CTD_CUDA(e, cudaMemcpyAsync(np, e->d_n_pending, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
     CTD_CUDA(e, cudaStreamSynchronize(e->stream));
-    if (np == 0) break;
-    s = ctd_value_forward(e, n_roots, e->d_pending, reward_weight);
-    if (s != CTD_OK) return s;
+    if (np[0] == 0 && np[1] == 0) break;
+    if (np[0] != 0) {
+      s = ctd_value_forward(e, n_roots, e->d_pending, reward_weight);
+      if (s != CTD_OK) return s;
+    }
   }
   CTD_CUDA(e, cudaEventRecord(e->ev1, e->stream));
   if (results) CTD_CUDA(e, cudaMemcpyAsync(results, e->d_scratch, rb, cudaMemcpyDeviceToHost, e->stream));

@@ -641,10 +641,15 @@ CTD_HD CTD_NI inline void ctd_encode_game(const CtdWork& w, const CtdKnow& k, in
 // the node, and returns true: the caller evaluates the value model on the batch of all waiting trees and calls again
 // with `pred` = model_reward_weights * square_and_normalize(model(features)) (:126,:147,:178; train_utils.py:143-145).
 // Returns false when all iterations are done.
-CTD_HD CTD_NI inline bool ctd_cfr_pred_advance(CtdTree& T, uint32_t iters, uint32_t max_depth, float* feat, const float* pred) {
+// Returns 0 = finished, 1 = waiting for the value of the leaf in `feat`, 2 = yielded after `budget` iterations of this
+// call (the walk resumes from hdr.cur_node; bounding a wave this way keeps trees that never reach the depth limit from
+// holding up the batch evaluation every other tree is waiting for).
+enum { CTD_PRED_DONE = 0, CTD_PRED_WAIT = 1, CTD_PRED_YIELD = 2 };
+CTD_HD CTD_NI inline int ctd_cfr_pred_advance(CtdTree& T, uint32_t iters, uint32_t max_depth, float* feat, const float* pred,
+                                              uint32_t budget = 0xFFFFFFFFu) {
   CTD_TREE_SPACES(T);
   CtdTreeHdr& h = *T.hdr;
-  if (h.phase == 3 || (h.status & CTD_TREE_TERMINAL_ROOT)) { h.phase = 3; return false; }
+  if (h.phase == 3 || (h.status & CTD_TREE_TERMINAL_ROOT)) { h.phase = 3; return CTD_PRED_DONE; }
   T.w->draws = h.rng_draws;
   T.w->buf_blk = 0xFFFFFFFFu;
   if (h.phase == 0) {
@@ -663,7 +668,13 @@ CTD_HD CTD_NI inline bool ctd_cfr_pred_advance(CtdTree& T, uint32_t iters, uint3
     ++h.iterations;
   }
   int node = (int)h.cur_node;
+  uint32_t done = 0;
   while (h.iterations < iters && !(h.status & ~CTD_TREE_TERMINAL_ROOT)) {
+    if (done++ >= budget) {   // phase stays 1: walking
+      h.cur_node = (uint32_t)node;
+      h.rng_draws = T.w->draws;
+      return CTD_PRED_YIELD;
+    }
     ctd_update_strategy(T, node);
     node = ctd_action_choice(T, node);
     CtdNode& n = T.nodes[node];
@@ -675,7 +686,7 @@ CTD_HD CTD_NI inline bool ctd_cfr_pred_advance(CtdTree& T, uint32_t iters, uint3
         h.cur_node = (uint32_t)node;
         h.phase = 2;
         h.rng_draws = T.w->draws;
-        return true;
+        return CTD_PRED_WAIT;
       }
       ctd_expand(T, node);
       double reward[6];
@@ -698,7 +709,7 @@ CTD_HD CTD_NI inline bool ctd_cfr_pred_advance(CtdTree& T, uint32_t iters, uint3
   h.cur_node = 0;
   h.phase = 3;
   h.rng_draws = T.w->draws;
-  return false;
+  return CTD_PRED_DONE;
 }
 
 // fill the packed game record of every node (export only)

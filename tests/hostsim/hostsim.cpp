@@ -129,7 +129,13 @@ int hs_mccfr_pred(const ctd_state* root, const CtdKnow* know, const uint8_t* use
   w.stream = 1;
   kn = *know;
   ctd_tree_init(T, max_nodes, child_cap, arr_cap, know->viewer, gid, false, true);
-  while (ctd_cfr_pred_advance(T, iters, max_depth, feat, pred)) eval(feat, pred);
+  // a small per-call budget exercises the yield / resume path of the wave scheduler as well
+  const uint32_t budget = getenv("HS_PRED_BUDGET") ? (uint32_t)atoi(getenv("HS_PRED_BUDGET")) : 7u;
+  for (;;) {
+    const int r = ctd_cfr_pred_advance(T, iters, max_depth, feat, pred, budget);
+    if (r == CTD_PRED_DONE) break;
+    if (r == CTD_PRED_WAIT) eval(feat, pred);
+  }
   ctd_tree_pack_nodes(T);
   return (int)T.hdr->status;
 }
