@@ -1580,7 +1580,7 @@ ctd_status ctd_mccfr_pred(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32
   a.trees = e->d_trees; a.tree_stride = stride; a.results = (ctd_mccfr_result*)e->d_scratch; a.counter = e->d_counter;
   {  // wave budget: trees that never reach the depth limit would otherwise walk all their iterations in the first wave
     const char* env = getenv("CTD_PRED_BUDGET");
-    p.budget = env ? (uint32_t)strtoul(env, nullptr, 10) : 16u;
+    p.budget = env ? (uint32_t)strtoul(env, nullptr, 10) : 20u;   // measured best at 4096 roots x 200 iterations (8: 8.4e6, 20: 1.12e7, 64: 8.9e6, unbounded: 7.3e6 it/s)
     if (p.budget == 0) p.budget = 0xFFFFFFFFu;
   }
   p.max_depth = max_depth; p.feat = e->d_feat; p.pred = e->d_pred; p.pending = e->d_pending; p.n_pending = e->d_n_pending;
