@@ -50,7 +50,7 @@ SIGNATURES = {
     "ctd_set_value_model": (_i, [c_void] + [c_void] * 8),
     "ctd_set_value_backend": (_i, [c_void, _i]),
     "ctd_value_eval": (_i, [c_void, _u32, c_void, ctypes.c_float, c_void]),
-    "ctd_encode": (_i, [c_void, _u32, c_void]),
+    "ctd_encode": (_i, [c_void, _u32, _i, c_void]),
     "ctd_mccfr_pred": (_i, [c_void, _u32, _u64, _u32, _u32, _i, ctypes.c_float, c_void, c_void,
                             ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_u32)]),
     "ctd_mccfr_targets": (_i, [c_void, _u32, _u64, _u32, _i, ctypes.c_double, ctypes.POINTER(_u32), ctypes.POINTER(_u32),

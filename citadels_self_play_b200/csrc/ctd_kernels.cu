@@ -776,7 +776,8 @@ __global__ void __launch_bounds__(256) ctd_k_value_mlp(const float* __restrict__
 #define CTD_MLP_SMEM ((CTD_FEATURES_PAD + 512 + 256 + 128) * CTD_MLP_ROWS * sizeof(float))
 
 // features of the games in slots [0,n) as their player to move sees them (role-pick states: player 5)
-__global__ void __launch_bounds__(CTD_BLOCK) ctd_k_encode(const ctd_state* slots, const CtdKnow* knows, uint32_t n, float* feat) {
+__global__ void __launch_bounds__(CTD_BLOCK) ctd_k_encode(const ctd_state* slots, const CtdKnow* knows, uint32_t n, float* feat,
+                                                          int cfr_role_pick) {
   __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
   __shared__ ctd_state stage[CTD_WARPS_PER_BLOCK];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -786,7 +787,7 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_encode(const ctd_state* slots
   if (lane == 0) {
     CtdWork& w = works[wib];
     ctd_unpack(&stage[wib], w);
-    ctd_encode_game(w, knows[slot], w.state == 0 ? 5 : w.player, feat + (size_t)slot * CTD_FEATURES_PAD);
+    ctd_encode_game(w, knows[slot], (w.state == 0 && cfr_role_pick) ? 5 : w.player, feat + (size_t)slot * CTD_FEATURES_PAD);
   }
 }
 
@@ -1538,13 +1539,13 @@ ctd_status ctd_value_eval(ctd_engine* e, uint32_t n, const float* features, floa
   return CTD_OK;
 }
 
-ctd_status ctd_encode(ctd_engine* e, uint32_t n, float* features) {
+ctd_status ctd_encode(ctd_engine* e, uint32_t n, int cfr_role_pick, float* features) {
   if (!e || !features || n > e->capacity || !e->d_knows) return CTD_EARG;
   if (n == 0) return CTD_OK;
   CTD_CUDA(e, cudaSetDevice(e->device));
   ctd_status s = ctd_pred_buffers(e);
   if (s != CTD_OK) return s;
-  ctd_k_encode<<<ctd_blocks(n), CTD_BLOCK, 0, e->stream>>>(e->d_slots, e->d_knows, n, e->d_feat);
+  ctd_k_encode<<<ctd_blocks(n), CTD_BLOCK, 0, e->stream>>>(e->d_slots, e->d_knows, n, e->d_feat, cfr_role_pick);
   e->launches++;
   CTD_CUDA(e, cudaGetLastError());
   CTD_CUDA(e, cudaMemcpyAsync(features, e->d_feat, (size_t)n * CTD_FEATURES_PAD * sizeof(float), cudaMemcpyDeviceToHost, e->stream));

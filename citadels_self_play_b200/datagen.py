@@ -1,0 +1,76 @@
+"""The reference's two data-generation drivers as batched engine calls.
+
+  get_mccfr_targets(...)    train_from_scratch.get_mccfr_targets / simulate_game (train_from_scratch.py:23-64):
+                            roots = create_a_random_game(100) (random play, stepped back 1..100 decisions),
+                            run_mccfr(max_iterations, training=True), position_root.get_all_targets(threshold);
+                            batches of roots are searched in one launch until enough targets exist.
+                            (With training=True the reference never evaluates the model inside the search --
+                            deep_mccfr.py:119-126 guards every inference with `not self.training` -- so the pre-training and
+                            the later rounds run the same pure MCCFR; `model` is accepted for signature parity only.)
+  generate_test_data(...)   generate_test_data.setup_game (generate_test_data.py:9-29): roots stepped back 1..30, one tuple per
+                            root (game_input, options_input, node_value, target_decision_dist) with
+                            run_utils.create_target_strategy (run_utils.py:99-108).
+
+Both return the reference's pickle tuples: (float32[418], float32[1,K,131], float64[6], float64[K]).
+Note (SURVEY.md discrepancy 3): the reference passes usefulness_treshold down but build_train_targets ignores it and uses 15;
+here the threshold given is the threshold applied (pass 15 for the reference's effective behaviour).
+"""
+import numpy as np
+
+from .engine import Engine, DEFAULT_SEED, RULESET_PRESET
+from .layout import encode_options
+
+
+def get_mccfr_targets(model=None, minimum_sufficient_nodes=5000, base_usefullness_treshold=200, pretrain=False,
+                      max_iterations=2000, engine=None, roots_per_batch=1024, seed=DEFAULT_SEED, first_gid=0,
+                      ruleset=RULESET_PRESET, back=(1, 100), stats=None):
+    own = engine is None
+    eng = engine or Engine(capacity=roots_per_batch)
+    targets, batches, gid = [], 0, int(first_gid)
+    try:
+        while len(targets) < minimum_sufficient_nodes:
+            eng.make_roots(roots_per_batch, seed=seed, first_gid=gid, ruleset=ruleset, back_lo=back[0], back_hi=back[1])
+            eng.mccfr(roots_per_batch, iterations=max_iterations, seed=seed, ruleset=ruleset)
+            t = eng.mccfr_targets(roots_per_batch, iterations=max_iterations, seed=seed, ruleset=ruleset,
+                                  threshold=float(base_usefullness_treshold))
+            targets += Engine.targets_as_tuples(t)
+            gid += roots_per_batch
+            batches += 1
+            if batches > 10000:
+                raise RuntimeError("get_mccfr_targets: no targets are being produced (threshold too high for max_iterations?)")
+    finally:
+        if stats is not None:
+            stats.update(batches=batches, roots=batches * roots_per_batch, targets=len(targets))
+        if own:
+            eng.close()
+    return targets
+
+
+def generate_test_data(n_roots, max_iterations=200, engine=None, seed=DEFAULT_SEED, first_gid=0, ruleset=RULESET_PRESET,
+                       back=(1, 30), rng=None):
+    import torch
+    rng = rng or np.random.default_rng(seed & 0xFFFFFFFF)
+    own = engine is None
+    eng = engine or Engine(capacity=n_roots)
+    out = []
+    try:
+        eng.make_roots(n_roots, seed=seed, first_gid=first_gid, ruleset=ruleset, back_lo=back[0], back_hi=back[1])
+        feats = eng.encode(n_roots, cfr_role_pick=False)  # game.encode_game() of the position handed to run_mccfr
+        res = eng.mccfr(n_roots, iterations=max_iterations, seed=seed, ruleset=ruleset)["results"]
+        for i, r in enumerate(res):
+            k = int(r["n_children"])
+            if r["status"] != 0 or k == 0 or k > len(r["options"]):
+                continue                                  # terminal root (ValueError in the reference) / meaningless state
+            if r["role_pick"]:
+                dist = np.array(r["cumulative_regrets"][:60]).reshape(6, 10)[int(rng.integers(0, 6))]
+            else:
+                dist = np.array(r["cumulative_regrets"][:k])
+            if dist.sum() == 0:
+                dist = np.ones_like(dist)
+            out.append((torch.from_numpy(np.array(feats[i][:418], dtype=np.float32)),
+                        torch.from_numpy(encode_options(np.array(r["options"][:k]))).unsqueeze(0),
+                        torch.from_numpy(np.array(r["node_value"])), torch.from_numpy(dist)))
+    finally:
+        if own:
+            eng.close()
+    return out

@@ -191,9 +191,10 @@ class Engine:
         self._check(self._lib.ctd_value_eval(self._h, len(f), f.ctypes.data, weight, out.ctypes.data), "ctd_value_eval")
         return out
 
-    def encode(self, n):
+    def encode(self, n, cfr_role_pick=True):
+        """Game.encode_game of roots [0,n); cfr_role_pick: role-pick states seen by "player 5" as inside CFRNode."""
         f = np.empty((n, 448), dtype=np.float32)
-        self._check(self._lib.ctd_encode(self._h, n, f.ctypes.data), "ctd_encode")
+        self._check(self._lib.ctd_encode(self._h, n, 1 if cfr_role_pick else 0, f.ctypes.data), "ctd_encode")
         return f[:, :418]
 
     def mccfr_pred(self, n_roots, iterations=200, max_depth=10, seed=DEFAULT_SEED, ruleset=RULESET_PRESET, weight=5.0,

@@ -322,11 +322,7 @@ class Game:
         viewer = 0 if self._rec["player"] == 0xFF else int(self._rec["player"])
         e.load_roots(np.frombuffer(self._rec.tobytes(), dtype=np.uint8), self._know[viewer * KNOW_BYTES:(viewer + 1) * KNOW_BYTES],
                      self._used, np.array([self.gid], dtype=np.uint64))
-        f = e.encode(1)[0]
-        if self._rec["state"] == 0:   # the kernel encodes role-pick states as the search does (player 5)
-            f = f.copy()
-            f[360:366] = 0
-            f[360 + viewer] = 1
+        f = e.encode(1, cfr_role_pick=False)[0]
         return torch.from_numpy(np.ascontiguousarray(f))
 
     def record(self):

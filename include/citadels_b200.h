@@ -244,8 +244,10 @@ ctd_status ctd_set_value_backend(ctd_engine* e, int backend);
 /* CFRNode.model_inference (algorithms/deep_mccfr.py:364-374) for n feature rows of 448 floats (418 used):
  * out6[i] = weight * square_and_normalize(model(features[i]))  (train_utils.py:143-145) */
 ctd_status ctd_value_eval(ctd_engine* e, uint32_t n, const float* features, float weight, float* out6);
-/* Game.encode_game (game/game.py:91-128) of roots [0,n) as their player to move sees them: n rows of 448 floats */
-ctd_status ctd_encode(ctd_engine* e, uint32_t n, float* features);
+/* Game.encode_game (game/game.py:91-128) of roots [0,n) as their player to move sees them: n rows of 448 floats.
+ * cfr_role_pick != 0 encodes role-pick states with player_id forced to 5, as CFRNode.expand_role_pick does
+ * (algorithms/deep_mccfr.py:120-123); 0 is the plain game.encode_game() a caller gets (generate_test_data.py:14). */
+ctd_status ctd_encode(ctd_engine* e, uint32_t n, int cfr_role_pick, float* features);
 /* CFRNode(game, ..., model=model, training=False).cfr_pred(iterations, max_depth) (run_utils.py:78-81,
  * algorithms/deep_mccfr.py:207-229) on roots [0,n_roots).  Trees advance in waves: every tree walks until it needs a
  * leaf value, the value model runs once on the batch of all waiting leaves, the trees resume.
