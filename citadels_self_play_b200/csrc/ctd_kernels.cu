@@ -250,11 +250,17 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_PLAYOUT_MIN_BLOCKS) ctd_k_playo
 #else
       uint64_t d = ctd_warp_choose(w, lane, choose_buf[wib]);
 #endif
+#ifdef CTD_PLAYOUT_ALL_LANES   /* experiment: every lane runs the transition (identical values), no divergence around it */
+      if (d == 0) w.err |= CTD_ERR_REF_RAISE;
+      else ctd_apply<false>(w, d);
+      __syncwarp();
+#else
       if (lane == 0) {
         if (d == 0) w.err |= CTD_ERR_REF_RAISE;
         else ctd_apply<false>(w, d);
       }
       __syncwarp();
+#endif
     }
     if (lane == 0 && !(w.gflags & 2) && !w.err) w.err |= CTD_ERR_MAXSTEPS;
     __syncwarp();

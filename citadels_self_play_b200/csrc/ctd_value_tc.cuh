@@ -8,11 +8,13 @@
 // x2 = rna(x - x0 - x1): 33 mantissa bits, i.e. exact), and the six products of weight >= 2^-22,
 //   x0.w0 + x0.w1 + x1.w0 + x0.w2 + x1.w1 + x2.w0,
 // are accumulated in fp32 in TMEM.  The layers are tiny (757 kFLOP per leaf), so six passes cost nothing.
-// Measured on B200 (profiles/r01_value_tc_accuracy.md): with the operands represented exactly, the remaining error
-// against torch fp32 is ~2e-5 absolute on outputs of scale 5 and is bit-identical whether the products go to one TMEM
-// accumulator or are spread over four -- i.e. it is the tensor core's internal summation of the eight products of one
-// instruction, not the split and not the accumulator chain.  That is the accuracy floor of this path; the fp32
-// CUDA-core kernel (ctd_k_value_mlp, ~3e-6) stays selectable (ctd_set_value_backend) where tighter parity is wanted.
+// Measured on B200 (profiles/r01_value_tc_accuracy.md): with the operands represented exactly the remaining error comes
+// from the accumulator update -- every instruction rounds (toward zero, it seems: the error is a bias) once when it adds
+// its eight products to the fp32 accumulator in TMEM, at the accumulator's magnitude.  Padding instructions with zeros
+// (twice the instructions) doubles the error; dealing the K slices over FOUR accumulators (all 512 TMEM columns), each a
+// quarter of the magnitude, and summing them in fp32 registers in the epilogue divides it by four: 1.0e-5 max / 1.2e-6 mean
+// absolute on outputs of scale 5, and deep-MCCFR trees within 3.3e-6 of the reference's (the fp32 CUDA-core kernel
+// ctd_k_value_mlp: 3.2e-6), against 1.3e-5 with one accumulator.  ctd_set_value_backend selects the fp32 kernel.
 //
 // One CTA (128 threads) computes a 128 x 128 output tile:
 //   * all four warps stream K in slices of 32 floats: 16-byte global loads, split into hi/lo, st.shared into the
@@ -20,8 +22,9 @@
 //     8-row groups SBO = 1024 B apart), two stages so the loads of slice s+1 overlap the MMAs of slice s;
 //   * one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M = 128, N = 128, K = 8 per instruction)
 //     and tcgen05.commit's to the stage's mbarrier, which is what frees the stage for the next load;
-//   * the accumulator (128 lanes x 128 columns fp32) lives in TMEM; the epilogue reads it back with
-//     tcgen05.ld.32x32b (each warp its own 32 lanes, one row per thread), adds the bias, applies ReLU and stores.
+//   * four accumulators (128 lanes x 128 columns fp32 each) live in TMEM, K slice kk of every stage goes to accumulator kk;
+//     the epilogue reads them back with tcgen05.ld.32x32b (each warp its own 32 lanes, one row per thread), sums them,
+//     adds the bias, applies ReLU and stores.
 // Weights total 1.5 MB and stay L2-resident; activations between layers round-trip through L2 (M x 512 floats).
 #pragma once
 #include <stdint.h>
@@ -32,7 +35,14 @@
 #define CTD_TC_TERMS 3
 #define CTD_TC_TILE_BYTES (128 * CTD_TC_BK * 4)                   /* 16 KB: one operand tile, one split term */
 #define CTD_TC_STAGE_BYTES (2 * CTD_TC_TERMS * CTD_TC_TILE_BYTES) /* A0 A1 A2 B0 B1 B2 */
-#define CTD_TC_SMEM (2 * CTD_TC_STAGE_BYTES + 1024)      /* two stages + alignment slack */
+#ifndef CTD_TC_HALF_K
+#define CTD_TC_HALF_K 0 /* experiment (1): every instruction carries four real products and four zeros -- twice the instructions, and the error DOUBLES (6.8e-5 vs 1.8e-5): the rounding happens once per instruction when the accumulator is updated */
+#endif
+#ifndef CTD_TC_ACCS
+#define CTD_TC_ACCS 4 /* TMEM accumulators the K slices are dealt over (each rounds once per instruction at its own, smaller, magnitude); summed in fp32 registers in the epilogue */
+#endif
+#define CTD_TC_ZERO_BYTES (CTD_TC_HALF_K ? CTD_TC_TILE_BYTES : 0)   /* a tile of zeros the padded K half is read from */
+#define CTD_TC_SMEM (2 * CTD_TC_STAGE_BYTES + CTD_TC_ZERO_BYTES + 1024)      /* two stages + zero tile + alignment slack */
 #define CTD_TC_SPIN_LIMIT (1u << 24)
 
 __device__ __forceinline__ uint32_t ctd_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -117,7 +127,7 @@ __global__ void __launch_bounds__(128) ctd_k_linear_tc(const float* __restrict__
   const int m0 = blockIdx.x * CTD_TC_BM, n0 = blockIdx.y * CTD_TC_BN;
 
   if (warp == 0) {  // TMEM: 128 columns for the fp32 accumulator tile
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ctd_smem_u32(&tmem_base_slot)), "r"(128u));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ctd_smem_u32(&tmem_base_slot)), "r"((uint32_t)(128 * CTD_TC_ACCS)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
@@ -130,6 +140,15 @@ __global__ void __launch_bounds__(128) ctd_k_linear_tc(const float* __restrict__
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_base_slot;
 
+#if CTD_TC_HALF_K
+  // The residual error of this path is made inside the instruction, when it sums its eight products
+  // (profiles/r01_value_tc_accuracy.md).  Halve it: an instruction's second K core column is read from a tile of zeros (the
+  // descriptor's leading-dimension offset points there), so it sums four real products; the other column gets its own
+  // instruction.  Twice the MMAs, which these tiny layers do not notice.
+  uint8_t* zero_tile = smem + 2 * CTD_TC_STAGE_BYTES;
+  for (int i = tid * 16; i < CTD_TC_TILE_BYTES; i += 128 * 16) *reinterpret_cast<float4*>(zero_tile + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  const uint32_t zero_addr = ctd_smem_u32(zero_tile);
+#endif
   const int stages = K / CTD_TC_BK;
   bool ok = true;
   for (int s = 0; s < stages; ++s) {
@@ -154,16 +173,27 @@ __global__ void __launch_bounds__(128) ctd_k_linear_tc(const float* __restrict__
 #pragma unroll
       for (int kk = 0; kk < CTD_TC_BK / 8; ++kk) {  // K = 8 per instruction = two 16-byte core columns
         const uint32_t ko = (uint32_t)kk * 256;
-        uint32_t acc = (s | kk) != 0;
+        const uint32_t tmem_acc = tmem_d + (uint32_t)((kk % CTD_TC_ACCS) * 128);   // K slice kk of every stage -> accumulator kk
+        uint32_t acc = CTD_TC_ACCS == 1 ? (uint32_t)((s | kk) != 0) : (uint32_t)(s != 0 || kk >= CTD_TC_ACCS);
         // smallest products first: (i, j) with i + j = 2, then 1, then 0
 #pragma unroll
         for (int sum = CTD_TC_TERMS - 1; sum >= 0; --sum)
 #pragma unroll
           for (int i = 0; i <= sum; ++i) {
             const int j = sum - i;
-            ctd_umma_tf32(tmem_d, ctd_umma_desc(a0 + i * CTD_TC_TILE_BYTES + ko, 128, 1024),
+#if CTD_TC_HALF_K
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {   // core column `half` of this K = 8 slice, padded with a column of zeros
+              const uint32_t aa = a0 + i * CTD_TC_TILE_BYTES + ko + half * 128;
+              const uint32_t bb = b0 + j * CTD_TC_TILE_BYTES + ko + half * 128;
+              ctd_umma_tf32(tmem_acc, ctd_umma_desc(aa, zero_addr - aa, 1024), ctd_umma_desc(bb, zero_addr - bb, 1024), acc);
+              acc = 1;
+            }
+#else
+            ctd_umma_tf32(tmem_acc, ctd_umma_desc(a0 + i * CTD_TC_TILE_BYTES + ko, 128, 1024),
                           ctd_umma_desc(b0 + j * CTD_TC_TILE_BYTES + ko, 128, 1024), acc);
             acc = 1;
+#endif
           }
       }
       // arrives on the stage barrier when every MMA issued so far has completed (implies fence::before_thread_sync)
@@ -181,7 +211,12 @@ __global__ void __launch_bounds__(128) ctd_k_linear_tc(const float* __restrict__
 #pragma unroll 1
   for (int c0 = 0; c0 < CTD_TC_BN; c0 += 32) {
     uint32_t v[32];
-    const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+    float sum[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) sum[j] = 0.f;
+#pragma unroll 1
+    for (int ai = 0; ai < CTD_TC_ACCS; ++ai) {
+    const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ai * 128 + c0);
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -191,6 +226,12 @@ __global__ void __launch_bounds__(128) ctd_k_linear_tc(const float* __restrict__
           "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
           "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(v[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(sum[j]);
     if (ok && row < M) {
       float* y = Y + (size_t)row * ldy + n0 + c0;
 #pragma unroll
@@ -207,7 +248,7 @@ __global__ void __launch_bounds__(128) ctd_k_linear_tc(const float* __restrict__
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(128u));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)(128 * CTD_TC_ACCS)));
 }
 
 // fc4 (128 -> 6) and model_reward_weights * square_and_normalize (train_utils.py:143-145): one row per thread

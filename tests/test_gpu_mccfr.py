@@ -129,17 +129,23 @@ def test_encoder_vs_oracle(engine):
         assert np.array_equal(feats[i], want), i
 
 
-def test_deep_trees_match_reference(engine):
+@pytest.mark.parametrize("name", ["deep_mccfr_preset.npz", "deep_mccfr_classic.npz", "deep_mccfr_random.npz"])
+def test_deep_trees_match_reference(engine, name):
     """Config 4: deep MCCFR, 200 iterations, value model at depth 10 -- every node against the real reference's
-    cfr_pred trees.  Structure, options, game records and knowledge exact; regrets / strategies / values to 1e-5 of
-    each array's scale (gate 3), the slack being fp32 summation order in the value model (torch CPU GEMV vs the kernel)."""
-    G = MccfrGolden("deep_mccfr_preset.npz")
+    cfr_pred trees (preset eight, classic eight, random 24-character rulesets).  Structure, options, game records and
+    knowledge exact; regrets / strategies / values to 1e-5 of each array's scale (gate 3), the slack being fp32
+    summation order in the value model (torch CPU GEMV vs the kernel)."""
+    G = MccfrGolden(name)
     z = G.z
     engine.set_value_model(_model(0))
     engine.load_roots(z["roots"], z["knows"], z["used"], G.gids)
-    out = engine.mccfr_pred(G.n, iterations=G.iterations, max_depth=int(z["max_depth"]), seed=G.seed, trees=True)
+    out = engine.mccfr_pred(G.n, iterations=G.iterations, max_depth=int(z["max_depth"]), seed=G.seed, ruleset=G.ruleset,
+                            trees=True)
     assert out["waves"] >= 2
     for r in range(G.n):
+        if z["terminal"][r]:
+            assert out["results"][r]["status"] == 1
+            continue
         assert out["results"][r]["status"] == 0
         assert_same_tree(G.nodes(r), tree_preorder(out["trees"][r]), ("deep", r), norm_rtol=1e-5)
 

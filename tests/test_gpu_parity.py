@@ -160,3 +160,29 @@ def test_distribution_vs_reference_sample(engine, fixture, ruleset):
     zs = (gs.mean() - rs.mean()) / np.sqrt(gs.var() / ng + rs.var() / nr)
     assert abs(zs) < 3.2, ("steps", gs.mean(), rs.mean(), zs)
     assert abs(gs.std() - rs.std()) < (2.0 if ruleset == 0 else 3.0)
+
+
+def test_full_size_properties_one_million_games():
+    """BASELINE configs[1] at full size (2^20 games): size-independent properties -- determinism, shard invariance of the
+    outcome statistics (the multi-GPU rule: rank r plays ids [r*G/N, (r+1)*G/N)), and internal consistency of the counters."""
+    from citadels_self_play_b200 import Engine
+    e = Engine(capacity=64)
+    n = 1 << 20
+    a = e.playout(n, seed=0xC17ADE15, first_gid=0, outputs=False)["stats"]
+    b = e.playout(n, seed=0xC17ADE15, first_gid=0, outputs=False)["stats"]
+    keys = ("games", "steps", "steps_sq", "wins", "points_sum", "points_sq", "errors", "max_steps")
+    assert all(a[k] == b[k] for k in keys)
+    parts = [e.playout(n // 8, seed=0xC17ADE15, first_gid=r * (n // 8), outputs=False)["stats"] for r in range(8)]
+    for k in ("games", "steps", "steps_sq", "errors"):
+        assert a[k] == sum(p[k] for p in parts), k
+    for k in ("wins", "points_sum", "points_sq"):
+        assert list(a[k]) == [sum(p[k][i] for p in parts) for i in range(6)], k
+    assert a["max_steps"] == max(p["max_steps"] for p in parts)
+    assert a["games"] == n and a["errors"] == 0 and sum(a["wins"]) == n
+    mean = a["steps"] / n
+    assert 410 < mean < 428 and 244 <= a["max_steps"] < 1200          # reference: 418.6 +- 65.4 steps per game
+    out = e.playout(1 << 16, seed=0xC17ADE15, first_gid=0)            # per-game rows agree with the counters
+    assert int(out["steps"].astype(np.int64).sum()) == out["stats"]["steps"]
+    assert list(np.bincount(out["winner"], minlength=6)) == list(out["stats"]["wins"])
+    assert [int(x) for x in out["points"].astype(np.int64).sum(0)] == list(out["stats"]["points_sum"])
+    e.close()

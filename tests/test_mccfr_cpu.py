@@ -73,18 +73,24 @@ def _model():
     return ValueOnlyNN(418, 512).eval()
 
 
-def test_oracle_deep_trees_match_reference():
+DEEP = ["deep_mccfr_preset.npz", "deep_mccfr_classic.npz", "deep_mccfr_random.npz"]
+
+
+@pytest.mark.parametrize("name", DEEP)
+def test_oracle_deep_trees_match_reference(name):
     """cfr_pred(200, max_depth=10) with ValueOnlyNN(418,512) under torch.manual_seed(0): oracle vs the real reference."""
     from citadels_self_play_b200.value_model import reference_value
     from oracle import citadels_oracle as O
     from oracle.philox import PhiloxChance
-    G = MccfrGolden("deep_mccfr_preset.npz")
+    G = MccfrGolden(name)
     z = G.z
     model = _model()
 
     def value(g):
         return reference_value(model, np.asarray(g.encode_game(), dtype=np.float32)[None, :], weight=1.0)[0]
     for r in range(0, G.n, 2):
+        if z["terminal"][r]:
+            continue
         g = O.Game.unpack(z["roots"][r].tobytes(), PhiloxChance(G.seed, int(G.gids[r]), stream=1))
         g.unpack_know(z["knows"][r], z["used"][r])
         n = M.Node(g, g.player, model=value)
@@ -92,10 +98,11 @@ def test_oracle_deep_trees_match_reference():
         assert_same_tree(G.nodes(r), oracle_preorder(n), ("deep", r), rtol=1e-7, atol=1e-10)
 
 
-def test_kernel_deep_mccfr_host_build_matches_reference(hostsim):
+@pytest.mark.parametrize("name", DEEP)
+def test_kernel_deep_mccfr_host_build_matches_reference(hostsim, name):
     from citadels_self_play_b200.layout import TreeView, tree_bytes
     from citadels_self_play_b200.value_model import reference_value
-    G = MccfrGolden("deep_mccfr_preset.npz")
+    G = MccfrGolden(name)
     z = G.z
     model = _model()
     u64, u32, vp = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p
@@ -107,12 +114,14 @@ def test_kernel_deep_mccfr_host_build_matches_reference(hostsim):
         for i in range(6):
             pp[i] = float(p[i])
     cb = EVAL(ev)
-    mn = 6 * G.iterations + 256
+    mn = 6 * G.iterations + 256 + (8192 if G.ruleset != 0 else 0)
     cc = mn + 10 * (G.iterations + 2)
     ac = 3 * cc + 180 * 64
     buf = np.zeros(tree_bytes(mn, cc, ac), np.uint8)
     for r in range(G.n):
         root, know, used = (np.ascontiguousarray(z[k][r]) for k in ("roots", "knows", "used"))
+        if z["terminal"][r]:
+            continue
         st = hostsim.hs_mccfr_pred(root.ctypes.data, know.ctypes.data, used.ctypes.data, G.seed, int(G.gids[r]),
                                    G.iterations, int(z["max_depth"]), mn, cc, ac, buf.ctypes.data, cb)
         assert st == 0
