@@ -24,11 +24,20 @@
 #define CTD_NI __noinline__
 #define CTD_LOOP _Pragma("unroll 1")
 #define CTD_UNROLL _Pragma("unroll")
+#ifdef CTD_HOT_UNROLL   /* experiment: fewer taken branches in the hottest tiny loops */
+#define CTD_LOOP_HOT4 _Pragma("unroll 4")
+#define CTD_LOOP_HOTFULL _Pragma("unroll")
+#else
+#define CTD_LOOP_HOT4 _Pragma("unroll 1")
+#define CTD_LOOP_HOTFULL _Pragma("unroll 1")
+#endif
 #else
 #define CTD_HD
 #define CTD_NI
 #define CTD_LOOP
 #define CTD_UNROLL
+#define CTD_LOOP_HOT4
+#define CTD_LOOP_HOTFULL
 #endif
 // On the device every CtdWork / CtdKnow lives in shared memory (all kernels declare them __shared__).  Telling the
 // compiler turns the generic LD.E / ST.E (+ descriptor moves and 64-bit address arithmetic) of the out-of-line rules code
@@ -185,7 +194,7 @@ static_assert(offsetof(CtdWork, scratch) == CTD_SNAP_BYTES, "CtdWork snapshot re
 // ------------------------------------------------------------------------------------------ chance
 CTD_HD CTD_NI inline void ctd_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
                               uint32_t out[4]) {
-  CTD_LOOP for (int i = 0; i < 10; ++i) {
+  CTD_LOOP_HOTFULL for (int i = 0; i < 10; ++i) {
     uint64_t p0 = (uint64_t)0xD2511F53u * c0;
     uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
     uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -363,29 +372,29 @@ CTD_HD inline void ctd_kn_confirm(CtdKnowSet ks, int seat, int role) {
 
 // ------------------------------------------------------------------------------------------ list helpers
 CTD_HD CTD_NI inline bool ctd_has(const uint8_t* a, int n, int t) {
-  CTD_LOOP for (int i = 0; i < n; ++i) if (ctd_ctype(a[i]) == t) return true;
+  CTD_LOOP_HOT4 for (int i = 0; i < n; ++i) if (ctd_ctype(a[i]) == t) return true;
   return false;
 }
 CTD_HD CTD_NI inline int ctd_count_type(const uint8_t* a, int n, int t) {
   int k = 0;
-  CTD_LOOP for (int i = 0; i < n; ++i) k += ctd_ctype(a[i]) == t;
+  CTD_LOOP_HOT4 for (int i = 0; i < n; ++i) k += ctd_ctype(a[i]) == t;
   return k;
 }
 CTD_HD CTD_NI inline int ctd_count_suit(const uint8_t* a, int n, int s) {
   int k = 0;
-  CTD_LOOP for (int i = 0; i < n; ++i) k += ctd_csuit(a[i]) == s;
+  CTD_LOOP_HOT4 for (int i = 0; i < n; ++i) k += ctd_csuit(a[i]) == s;
   return k;
 }
 CTD_HD inline int ctd_remove_at(uint8_t* a, uint8_t& n, int i) {
   int c = a[i];
-  CTD_LOOP for (int k = i; k + 1 < n; ++k) a[k] = a[k + 1];
+  CTD_LOOP_HOT4 for (int k = i; k + 1 < n; ++k) a[k] = a[k + 1];
   --n;
   return c;
 }
 // Deck.get_a_card_like_it (game/deck.py:49-55): first card of that type; the requested card is fabricated
 // when none matches.
 CTD_HD CTD_NI inline int ctd_take_like(uint8_t* a, uint8_t& n, int t) {
-  CTD_LOOP for (int i = 0; i < n; ++i)
+  CTD_LOOP_HOT4 for (int i = 0; i < n; ++i)
     if (ctd_ctype(a[i]) == t) return ctd_remove_at(a, n, i);
   return t;
 }
