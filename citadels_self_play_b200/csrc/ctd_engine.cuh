@@ -17,7 +17,14 @@
 #include <stddef.h>
 #include "../../include/citadels_b200.h"
 
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) && defined(CTD_DEVICE_ONLY)
+#define CTD_HD __device__ /* a second translation unit must not emit host copies of the inline rules code */
+#define CTD_NI __noinline__
+#define CTD_LOOP _Pragma("unroll 1")
+#define CTD_UNROLL _Pragma("unroll")
+#define CTD_LOOP_HOT4 _Pragma("unroll 1")
+#define CTD_LOOP_HOTFULL _Pragma("unroll 1")
+#elif defined(__CUDACC__)
 #define CTD_HD __host__ __device__
 // out-of-line on the device: the playout kernel's warps sit at unrelated points of the rules code, so the
 // instruction footprint (not the arithmetic) is what the SM front end sees; one copy of each helper.
@@ -54,6 +61,14 @@
 // the kernels fault on the device -- either hint alone was fine, both together were not -- so those stay generic.)
 
 // ------------------------------------------------------------------------------------------ constants
+// CTD_FIXED_PRESET (set by ctd_playout_preset.cu only): the translation unit plays the preset ruleset exclusively -- Witch,
+// Spy, Wizard, King, Abbot, Alchemist, Navigator, Warlord (game/game.py:479-486) -- so every option kind and character
+// outside it is unreachable and the compiler drops that code.
+#ifdef CTD_FIXED_PRESET
+#define CTD_NOT_PRESET() __builtin_unreachable()
+#else
+#define CTD_NOT_PRESET() ((void)0)
+#endif
 #ifndef CTD_PLAYOUT_RING
 /* 1 = the fused playout computes 32 Philox blocks at a time, one per lane (ctd_warp.cuh ctd_ring_refill): 40 fewer warp
  * instructions per env step (7 %) and bit-identical results, but no faster on B200 -- the kernel is bound by instruction
@@ -814,10 +829,10 @@ CTD_HD CTD_NI inline void ctd_character_options(const CtdWork& w, int p, int nm,
   CTD_ASSUME_SHARED(&w);
   if (!(w.done & CTD_DM_CHARACTER)) {
     switch (nm) {
-      case CTD_ASSASSIN:  // :213-218
+      case CTD_ASSASSIN: CTD_NOT_PRESET();  // :213-218
         CTD_LOOP for (int r = 1; r < 8; ++r) e.one(ctd_opt(CTD_K_ASSASSINATION, p) | ctd_f_rank(r));
         break;
-      case CTD_THIEF:  // :246-253
+      case CTD_THIEF: CTD_NOT_PRESET();  // :246-253
         CTD_LOOP for (int r = 2; r < 8; ++r) e.one(ctd_opt(CTD_K_STEAL, p) | ctd_f_rank(r));
         break;
       case CTD_SPY:  // :274-281
@@ -825,7 +840,7 @@ CTD_HD CTD_NI inline void ctd_character_options(const CtdWork& w, int p, int nm,
           if (q != p)
             CTD_LOOP for (int s = 0; s < 5; ++s) e.one(ctd_opt(CTD_K_SPY, p) | ctd_f_target(q) | ctd_f_named(CTD_N_TRADE + s));
         break;
-      case CTD_MAGICIAN: {  // :284-296
+      case CTD_MAGICIAN: CTD_NOT_PRESET(); {  // :284-296
         CTD_LOOP for (int q = 0; q < 6; ++q)
           if (q != p) e.one(ctd_opt(CTD_K_MAGIC_HAND_CHANGE, p) | ctd_f_target(q));
         int n = w.n_hand[p];
@@ -837,16 +852,16 @@ CTD_HD CTD_NI inline void ctd_character_options(const CtdWork& w, int p, int nm,
           if (q != p && w.n_hand[q] > 0) e.one(ctd_opt(CTD_K_LOOK_AT_HAND, p) | ctd_f_target(q));
         break;
       case CTD_KING: e.one(ctd_opt(CTD_K_TAKE_CROWN_KING, p)); break;  // :364-366
-      case CTD_BISHOP: e.one(ctd_opt(CTD_K_BISHOP, p)); break;         // :389-391
+      case CTD_BISHOP: CTD_NOT_PRESET(); e.one(ctd_opt(CTD_K_BISHOP, p)); break;         // :389-391
       case CTD_ABBOT: {                                                // :422-430
         int n = ctd_count_suit(w.hand[p], w.n_hand[p], CTD_SUIT_RELIGION);
         if (n > 0)
           CTD_LOOP for (int k = 0; k <= n; ++k) e.one(ctd_opt(CTD_K_ABBOT, p) | ctd_f_count(k) | ctd_f_r(n));
         break;
       }
-      case CTD_MERCHANT: e.one(ctd_opt(CTD_K_MERCHANT, p)); break;    // :438-440
+      case CTD_MERCHANT: CTD_NOT_PRESET(); e.one(ctd_opt(CTD_K_MERCHANT, p)); break;    // :438-440
       case CTD_ALCHEMIST: break;                                       // :442-444
-      case CTD_ARCHITECT: e.one(ctd_opt(CTD_K_ARCHITECT, p)); break;  // :451-452
+      case CTD_ARCHITECT: CTD_NOT_PRESET(); e.one(ctd_opt(CTD_K_ARCHITECT, p)); break;  // :451-452
       case CTD_NAVIGATOR:                                              // :454-455
         e.one(ctd_opt(CTD_K_NAVIGATOR, p) | ctd_f_named(CTD_N_4GOLD));
         e.one(ctd_opt(CTD_K_NAVIGATOR, p) | ctd_f_named(CTD_N_4CARD));
@@ -864,14 +879,14 @@ CTD_HD CTD_NI inline void ctd_character_options(const CtdWork& w, int p, int nm,
           }
         }
         break;
-      case CTD_MAGISTRATE:  // :221-234  real target x pairs of fake targets among ranks 1..7
+      case CTD_MAGISTRATE: CTD_NOT_PRESET();  // :221-234  real target x pairs of fake targets among ranks 1..7
         CTD_LOOP for (int real = 1; real < 8; ++real)
           CTD_LOOP for (int a = 1; a < 8; ++a)
             CTD_LOOP for (int b = a + 1; b < 8; ++b)
               if (real != a && real != b)
                 e.one(ctd_opt(CTD_K_MAGISTRATE_WARRANT, p) | ctd_f_rank(real) | ctd_f_named(a) | ctd_f_count(b));
         break;
-      case CTD_BLACKMAILER:  // :255-272  ordered pairs of un-possessed ranks 2..7
+      case CTD_BLACKMAILER: CTD_NOT_PRESET();  // :255-272  ordered pairs of un-possessed ranks 2..7
         CTD_LOOP for (int a = 2; a < 8; ++a) {
           if (w.rprops[a] & CTD_RP_POSSESSED) continue;
           CTD_LOOP for (int b = a + 1; b < 8; ++b) {
@@ -881,13 +896,13 @@ CTD_HD CTD_NI inline void ctd_character_options(const CtdWork& w, int p, int nm,
           }
         }
         break;
-      case CTD_SEER: e.one(ctd_opt(CTD_K_SEER, p)); break;            // :328-329
-      case CTD_EMPEROR: ctd_emperor_options(w, p, false, e); break;   // :368-382
-      case CTD_PATRICIAN: e.one(ctd_opt(CTD_K_TAKE_CROWN_PAT, p)); break;  // :384-386
-      case CTD_CARDINAL: ctd_cardinal_options(w, p, e); break;        // :393-419
-      case CTD_TRADER: e.one(ctd_opt(CTD_K_TRADER, p)); break;        // :446-448
-      case CTD_SCHOLAR: if (w.n_deck != 0) e.one(ctd_opt(CTD_K_SCHOLAR, p)); break;  // :457-460
-      case CTD_MARSHAL:  // :484-492
+      case CTD_SEER: CTD_NOT_PRESET(); e.one(ctd_opt(CTD_K_SEER, p)); break;            // :328-329
+      case CTD_EMPEROR: CTD_NOT_PRESET(); ctd_emperor_options(w, p, false, e); break;   // :368-382
+      case CTD_PATRICIAN: CTD_NOT_PRESET(); e.one(ctd_opt(CTD_K_TAKE_CROWN_PAT, p)); break;  // :384-386
+      case CTD_CARDINAL: CTD_NOT_PRESET(); ctd_cardinal_options(w, p, e); break;        // :393-419
+      case CTD_TRADER: CTD_NOT_PRESET(); e.one(ctd_opt(CTD_K_TRADER, p)); break;        // :446-448
+      case CTD_SCHOLAR: CTD_NOT_PRESET(); if (w.n_deck != 0) e.one(ctd_opt(CTD_K_SCHOLAR, p)); break;  // :457-460
+      case CTD_MARSHAL: CTD_NOT_PRESET();  // :484-492
         CTD_LOOP for (int q = 0; q < 6; ++q) {
           if (q == p || w.n_bld[q] >= 7 || ctd_name(w, q) == CTD_BISHOP) continue;
           uint64_t seen = 0;
@@ -900,7 +915,7 @@ CTD_HD CTD_NI inline void ctd_character_options(const CtdWork& w, int p, int nm,
           }
         }
         break;
-      case CTD_DIPLOMAT:  // :494-504
+      case CTD_DIPLOMAT: CTD_NOT_PRESET();  // :494-504
         CTD_LOOP for (int q = 0; q < 6; ++q) {
           if (q == p || w.n_bld[q] >= 7 || ctd_name(w, q) == CTD_BISHOP) continue;
           CTD_LOOP for (int i = 0; i < w.n_bld[q]; ++i) {
@@ -1327,12 +1342,12 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       ctd_to5(w, p);
       w.done |= CTD_DM_TAKE_GOLD;
       break;
-    case CTD_K_ASSASSINATION:  // carry_out_assasination (:245-249)
+    case CTD_K_ASSASSINATION: CTD_NOT_PRESET();  // carry_out_assasination (:245-249)
       w.rprops[CTD_OPT_RANK(d)] |= CTD_RP_DEAD;
       ctd_to5(w, p);
       w.done |= CTD_DM_CHARACTER;
       break;
-    case CTD_K_STEAL:  // carry_out_stealing (:265-269)
+    case CTD_K_STEAL: CTD_NOT_PRESET();  // carry_out_stealing (:265-269)
       w.rprops[CTD_OPT_RANK(d)] |= CTD_RP_ROBBED;
       ctd_to5(w, p);
       w.done |= CTD_DM_CHARACTER;
@@ -1353,7 +1368,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       w.done |= CTD_DM_CHARACTER;
       break;
     }
-    case CTD_K_MAGIC_HAND_CHANGE: {  // carry_out_magicking (:291-293)
+    case CTD_K_MAGIC_HAND_CHANGE: CTD_NOT_PRESET(); {  // carry_out_magicking (:291-293)
       int q = CTD_OPT_TARGET(d);
       int n = w.n_hand[p] > w.n_hand[q] ? w.n_hand[p] : w.n_hand[q];
       CTD_LOOP for (int i = 0; i < n; ++i) { uint8_t a = w.hand[p][i]; w.hand[p][i] = w.hand[q][i]; w.hand[q][i] = a; }
@@ -1362,7 +1377,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       w.done |= CTD_DM_CHARACTER;
       break;
     }
-    case CTD_K_DISCARD_AND_DRAW: {  // carry_out_magicking (:295-300): ignores the option's cards and removes
+    case CTD_K_DISCARD_AND_DRAW: CTD_NOT_PRESET(); {  // carry_out_magicking (:295-300): ignores the option's cards and removes
                                     // while iterating; draws as many cards as are left in hand
       int i = 0;
       CTD_LOOP while (i < w.n_hand[p]) {
@@ -1418,12 +1433,12 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       ctd_to5(w, p);
       w.done |= CTD_DM_CHARACTER;
       break;
-    case CTD_K_BISHOP:  // carry_out_bishop (:397-403)
+    case CTD_K_BISHOP: CTD_NOT_PRESET();  // carry_out_bishop (:397-403)
       w.gold[p] += (int8_t)ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_RELIGION);
       ctd_to5(w, p);
       w.done |= CTD_DM_CHARACTER;
       break;
-    case CTD_K_MERCHANT:  // carry_out_merchant (:442-449)
+    case CTD_K_MERCHANT: CTD_NOT_PRESET();  // carry_out_merchant (:442-449)
       w.gold[p] += (int8_t)(ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_TRADE) + 1);
       ctd_to5(w, p);
       w.done |= CTD_DM_CHARACTER;
@@ -1447,7 +1462,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       w.done |= CTD_DM_BEGGED;
       break;
     }
-    case CTD_K_ARCHITECT:  // carry_out_architect (:464-471)
+    case CTD_K_ARCHITECT: CTD_NOT_PRESET();  // carry_out_architect (:464-471)
       ctd_draw_to_hand(w, p);
       ctd_draw_to_hand(w, p);
       ctd_to5(w, p);
@@ -1486,14 +1501,14 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       break;
     }
     // ---- deluxe characters (tier C) ----
-    case CTD_K_MAGISTRATE_WARRANT:  // carry_out_warranting (:251-257)
+    case CTD_K_MAGISTRATE_WARRANT: CTD_NOT_PRESET();  // carry_out_warranting (:251-257)
       w.rprops[CTD_OPT_RANK(d)] = (uint8_t)((w.rprops[CTD_OPT_RANK(d)] & ~CTD_RP_WARRANT) | (1 << 1));
       w.rprops[CTD_OPT_NAMED(d)] = (uint8_t)((w.rprops[CTD_OPT_NAMED(d)] & ~CTD_RP_WARRANT) | (2 << 1));
       w.rprops[CTD_OPT_COUNT(d)] = (uint8_t)((w.rprops[CTD_OPT_COUNT(d)] & ~CTD_RP_WARRANT) | (2 << 1));
       ctd_to5(w, p);
       w.done |= CTD_DM_CHARACTER;
       break;
-    case CTD_K_REVEAL_WARRANT: {  // carry_out_magistrate_reaveal (:94-100)
+    case CTD_K_REVEAL_WARRANT: CTD_NOT_PRESET(); {  // carry_out_magistrate_reaveal (:94-100)
       const int q = CTD_OPT_TARGET(d), rq = w.role[q];
       if (rq >= 8) { w.err |= CTD_ERR_REF_RAISE; break; }
       if (CTD_OPT_NAMED(d) == CTD_N_REVEAL && ((w.rprops[rq] & CTD_RP_WARRANT) >> 1) == 1) {
@@ -1505,13 +1520,13 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       ctd_restore_next(w);
       break;
     }
-    case CTD_K_BLACKMAIL:  // carry_out_blackmail (:271-276)
+    case CTD_K_BLACKMAIL: CTD_NOT_PRESET();  // carry_out_blackmail (:271-276)
       w.rprops[CTD_OPT_RANK(d)] = (uint8_t)((w.rprops[CTD_OPT_RANK(d)] & ~CTD_RP_BLACKMAIL) | (1 << 5));
       w.rprops[CTD_OPT_NAMED(d)] = (uint8_t)((w.rprops[CTD_OPT_NAMED(d)] & ~CTD_RP_BLACKMAIL) | (2 << 5));
       ctd_to5(w, p);
       w.done |= CTD_DM_CHARACTER;
       break;
-    case CTD_K_BLACKMAIL_RESPONSE: {  // carry_out_respond_to_blackmail (:71-82); int(gold/2) truncates toward zero
+    case CTD_K_BLACKMAIL_RESPONSE: CTD_NOT_PRESET(); {  // carry_out_respond_to_blackmail (:71-82); int(gold/2) truncates toward zero
       const int bm = ctd_player_from_rank(w, 1);
       if (bm < 0) { w.err |= CTD_ERR_REF_RAISE; break; }
       if (CTD_OPT_NAMED(d) == CTD_N_PAY) {
@@ -1527,7 +1542,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       }
       break;
     }
-    case CTD_K_REVEAL_BLACKMAIL: {  // carry_out_responding_to_blackmail_response (:85-92)
+    case CTD_K_REVEAL_BLACKMAIL: CTD_NOT_PRESET(); {  // carry_out_responding_to_blackmail_response (:85-92)
       const int q = CTD_OPT_TARGET(d), rq = w.role[q];
       if (rq >= 8) { w.err |= CTD_ERR_REF_RAISE; break; }
       if (CTD_OPT_NAMED(d) == CTD_N_REVEAL && ((w.rprops[rq] & CTD_RP_BLACKMAIL) >> 5) == 1) {
@@ -1538,7 +1553,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       ctd_restore_next(w);
       break;
     }
-    case CTD_K_SEER: {  // carry_out_seer_take_a_card (:330-341): shuffle each hand, take its first card
+    case CTD_K_SEER: CTD_NOT_PRESET(); {  // carry_out_seer_take_a_card (:330-341): shuffle each hand, take its first card
       w.seer_mask = 0;
       CTD_LOOP for (int q = 0; q < 6; ++q) {
         if (q == p || w.n_hand[q] == 0) continue;
@@ -1555,7 +1570,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       w.next_mode = CTD_NEXT_ALIAS;
       break;
     }
-    case CTD_K_GIVE_BACK_CARD: {  // carry_out_seer_give_back_cards (:343-350)
+    case CTD_K_GIVE_BACK_CARD: CTD_NOT_PRESET(); {  // carry_out_seer_give_back_cards (:343-350)
       const int shift[5] = {12, 18, 39, 45, 51};
       int idx = 0;
       CTD_LOOP for (int q = 0; q < 6 && idx < 5; ++q) {
@@ -1571,7 +1586,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       ctd_restore_next(w);
       break;
     }
-    case CTD_K_GIVE_CROWN: {  // carry_out_emperor (:377-393)
+    case CTD_K_GIVE_CROWN: CTD_NOT_PRESET(); {  // carry_out_emperor (:377-393)
       const int q = CTD_OPT_TARGET(d);
       w.gold[p] += (int8_t)ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_LORD);
       if (CTD_OPT_NAMED(d) == CTD_N_CARD) {
@@ -1589,7 +1604,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       w.done |= CTD_DM_CHARACTER;
       break;
     }
-    case CTD_K_TAKE_CROWN_PAT: {  // carry_out_take_crown_patrician (:365-375)
+    case CTD_K_TAKE_CROWN_PAT: CTD_NOT_PRESET(); {  // carry_out_take_crown_patrician (:365-375)
       const int n = ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_LORD);
       CTD_LOOP for (int i = 0; i < n; ++i) ctd_draw_to_hand(w, p);
       if (!(w.pflags[p] & CTD_PF_WITCH)) ctd_move_crown(w, p);
@@ -1597,7 +1612,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       w.done |= CTD_DM_CHARACTER;
       break;
     }
-    case CTD_K_CARDINAL: {  // carry_out_cardinal (:422-439): no build bookkeeping, no warrant check, gold clamped at 0
+    case CTD_K_CARDINAL: CTD_NOT_PRESET(); {  // carry_out_cardinal (:422-439): no build bookkeeping, no warrant check, gold clamped at 0
       const int q = CTD_OPT_TARGET(d), t = CTD_OPT_CARD_A(d), kc = CTD_OPT_COUNT(d);
       const int c = ctd_take_like(w.hand[p], w.n_hand[p], t);
       ctd_append(w, w.bld[p], w.n_bld[p], CTD_BLD_CAP, c);
@@ -1634,12 +1649,12 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       w.done |= CTD_DM_CHARACTER;
       break;
     }
-    case CTD_K_TRADER:  // carry_out_trader (:455-461)
+    case CTD_K_TRADER: CTD_NOT_PRESET();  // carry_out_trader (:455-461)
       w.gold[p] += (int8_t)ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_TRADE);
       ctd_to5(w, p);
       w.done |= CTD_DM_CHARACTER;
       break;
-    case CTD_K_SCHOLAR: {  // carry_out_scholar_draw (:485-496)
+    case CTD_K_SCHOLAR: CTD_NOT_PRESET(); {  // carry_out_scholar_draw (:485-496)
       w.n_seven = 0;
       const int n = w.n_deck < 7 ? w.n_deck : 7;
       CTD_LOOP for (int i = 0; i < n; ++i) {
@@ -1655,14 +1670,14 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       w.next_mode = CTD_NEXT_ALIAS;
       break;
     }
-    case CTD_K_SCHOLAR_PICK:  // carry_out_scholar_put_back (:498-502): returns what the shrunk shared list still holds
+    case CTD_K_SCHOLAR_PICK: CTD_NOT_PRESET();  // carry_out_scholar_put_back (:498-502): returns what the shrunk shared list still holds
       CTD_LOOP for (int i = 0; i < w.n_seven; ++i) ctd_deck_push(w, ctd_take_like(w.hand[p], w.n_hand[p], ctd_ctype(w.seven[i])));
       ctd_restore_next(w);
       w.n_seven = 0;
       CTD_LOOP for (int i = 0; i < 7; ++i) w.seven[i] = 0;
       break;
-    case CTD_K_MARSHAL:
-    case CTD_K_DIPLOMAT: {  // carry_out_marshal (:505-515) / carry_out_diplomat (:538-551)
+    case CTD_K_MARSHAL: CTD_NOT_PRESET();
+    case CTD_K_DIPLOMAT: CTD_NOT_PRESET(); {  // carry_out_marshal (:505-515) / carry_out_diplomat (:538-551)
       const int q = CTD_OPT_TARGET(d), t = CTD_OPT_CARD_A(d);
       const int money = k == CTD_K_MARSHAL ? ctd_cost_of_type(t)
                                            : (ctd_cost_of_type(t) > ctd_cost_of_type(CTD_OPT_CARD_B(d))

@@ -16,26 +16,13 @@
 
 #include "ctd_engine.cuh"
 #include "ctd_warp.cuh"
+#include "ctd_playout.cuh"
 #include "ctd_mccfr.cuh"
 #include "ctd_value_tc.cuh"
 
-#define CTD_WARPS_PER_BLOCK 8
-#define CTD_BLOCK (CTD_WARPS_PER_BLOCK * 32)
-#ifndef CTD_PLAYOUT_MIN_BLOCKS
-#define CTD_PLAYOUT_MIN_BLOCKS 8
-#endif
-#define CTD_FULL 0xFFFFFFFFu
 
 // ------------------------------------------------------------------------------------------ device helpers
-// move one 256 B record between HBM and the warp's shared staging buffer: 32 lanes x 8 B
-__device__ __forceinline__ void ctd_record_load(const ctd_state* g, ctd_state* s, int lane) {
-  reinterpret_cast<uint64_t*>(s)[lane] = reinterpret_cast<const uint64_t*>(g)[lane];
-  __syncwarp();
-}
-__device__ __forceinline__ void ctd_record_store(ctd_state* g, const ctd_state* s, int lane) {
-  __syncwarp();
-  reinterpret_cast<uint64_t*>(g)[lane] = reinterpret_cast<const uint64_t*>(s)[lane];
-}
+// (ctd_record_load / ctd_record_store live in ctd_playout.cuh)
 
 struct CtdTapes {
   const uint8_t* tape;
@@ -164,136 +151,9 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_choose_check(const ctd_state*
   if (lane == 0) mismatches[slot] = bad;
 }
 
-struct CtdPlayoutArgs {
-  uint64_t n_games, seed, first_gid;
-  int ruleset;
-  uint32_t max_steps;
-  int8_t* winner;    // [n] or null
-  int8_t* points6;   // [n][6] or null
-  uint16_t* steps;   // [n] or null
-  ctd_playout_stats* stats;
-  unsigned long long* counter;
-  ctd_state* slots;  // non-null: continue from slots[0..n) instead of dealing new games
-};
-
-// Outcome statistics are accumulated per block in shared memory (one shared atomic per field and game) and flushed
-// to HBM once per block.
-__global__ void __launch_bounds__(CTD_BLOCK, CTD_PLAYOUT_MIN_BLOCKS) ctd_k_playout(CtdPlayoutArgs a) {
-  __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
-  // the record staging area (game start / end) and the scalar chooser's option buffer (inside a step) are never live together;
-  // shared memory is kept small because what is left of the 256 KB is the L1 that holds lane 0's stack
-  __shared__ __align__(16) uint64_t scratch_u64[CTD_WARPS_PER_BLOCK][CTD_CHOOSE_BUF];
-  static_assert(sizeof(ctd_state) <= CTD_CHOOSE_BUF * 8, "stage aliases the option buffer");
-#if CTD_PLAYOUT_RING
-  __shared__ __align__(16) uint32_t rings[CTD_WARPS_PER_BLOCK][128];
-#endif
-  __shared__ unsigned long long bst[sizeof(ctd_playout_stats) / 8];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-#ifdef CTD_NO_STAGE_ALIAS
-  __shared__ ctd_state stage[CTD_WARPS_PER_BLOCK];
-#else
-  ctd_state* const stage = reinterpret_cast<ctd_state*>(scratch_u64[0]);   // stage[wib] == scratch_u64[wib]
-#endif
-  uint64_t (*choose_buf)[CTD_CHOOSE_BUF] = scratch_u64;
-  CtdWork& w = works[wib];
-  if (threadIdx.x < sizeof(ctd_playout_stats) / 8) bst[threadIdx.x] = 0;
-  __syncthreads();
-  ctd_playout_stats* bs = reinterpret_cast<ctd_playout_stats*>(bst);
-  for (;;) {
-    unsigned long long g = 0;
-    if (lane == 0) g = atomicAdd(a.counter, 1ull);
-    g = __shfl_sync(CTD_FULL, g, 0);
-    if (g >= a.n_games) break;
-    if (a.slots != nullptr) {
-      ctd_record_load(&a.slots[g], &stage[wib], lane);
-      if (lane == 0) {
-        ctd_unpack(&stage[wib], w);
-        w.k0 = (uint32_t)a.seed; w.k1 = (uint32_t)(a.seed >> 32);
-        w.stream = 0;
-        w.tape = nullptr; w.tape_len = 0;
-#if CTD_PLAYOUT_RING
-        w.ring = rings[wib]; w.ring_hi = 0;
-#endif
-      }
-      __syncwarp();
-    } else {
-      if (lane == 0) {
-#ifdef CTD_EXPERIMENT_GID_MASK   /* developer experiment: many warps play the SAME game (upper bound of what instruction-stream alignment could give) */
-        ctd_chance_init(w, a.seed, a.first_gid + (g & CTD_EXPERIMENT_GID_MASK), 0);
-#else
-        ctd_chance_init(w, a.seed, a.first_gid + g, 0);
-#endif
-#if CTD_PLAYOUT_RING
-        w.ring = rings[wib];
-#endif
-      }
-      __syncwarp();
-#if CTD_PLAYOUT_RING
-      ctd_ring_refill(w, lane);   // the deal's 76-card shuffle and the first round's role shuffle come out of one refill
-#endif
-      if (lane == 0) {
-        ctd_deal_preset(w, a.ruleset);
-        ctd_setup_round<false>(w);
-      }
-      __syncwarp();
-    }
-    const uint32_t steps0 = w.steps;
-    // ---- the hot loop: run_utils.py:37-41 ----
-    for (;;) {
-      bool stop = (w.gflags & 2) || w.err || (w.steps - steps0) >= a.max_steps;
-      if (stop) break;
-#if CTD_PLAYOUT_RING
-      ctd_ring_refill(w, lane);
-#endif
-#if CTD_PLAYOUT_RING
-      uint64_t d = ctd_warp_choose(w, lane, choose_buf[wib], nullptr, -1, rings[wib]);
-#else
-      uint64_t d = ctd_warp_choose(w, lane, choose_buf[wib]);
-#endif
-#ifdef CTD_PLAYOUT_ALL_LANES   /* experiment: every lane runs the transition (identical values), no divergence around it */
-      if (d == 0) w.err |= CTD_ERR_REF_RAISE;
-      else ctd_apply<false>(w, d);
-      __syncwarp();
-#else
-      if (lane == 0) {
-        if (d == 0) w.err |= CTD_ERR_REF_RAISE;
-        else ctd_apply<false>(w, d);
-      }
-      __syncwarp();
-#endif
-    }
-    if (lane == 0 && !(w.gflags & 2) && !w.err) w.err |= CTD_ERR_MAXSTEPS;
-    __syncwarp();
-    const uint32_t ns = w.steps - steps0;
-    if (lane < 6) {  // per-seat fields: one lane per seat
-      const int pts = w.points[lane];
-      if (a.points6) a.points6[g * 6 + lane] = (int8_t)pts;
-      atomicAdd((unsigned long long*)&bs->points_sum[lane], (unsigned long long)(long long)pts);
-      atomicAdd((unsigned long long*)&bs->points_sq[lane], (unsigned long long)(pts * pts));
-      if (w.winner == lane) atomicAdd((unsigned long long*)&bs->wins[lane], 1ull);
-    } else if (lane == 6) {
-      if (a.winner) a.winner[g] = w.winner;
-      if (a.steps) a.steps[g] = (uint16_t)ns;
-      atomicAdd((unsigned long long*)&bs->games, 1ull);
-      atomicAdd((unsigned long long*)&bs->steps, (unsigned long long)ns);
-      atomicAdd((unsigned long long*)&bs->steps_sq, (unsigned long long)ns * ns);
-      if (w.err) atomicAdd((unsigned long long*)&bs->errors, 1ull);
-      atomicMax((unsigned long long*)&bs->max_steps, (unsigned long long)ns);
-    }
-    if (a.slots != nullptr) {
-      if (lane == 0) ctd_pack(w, &stage[wib]);
-      ctd_record_store(&a.slots[g], &stage[wib], lane);
-    }
-    __syncwarp();
-  }
-  __syncthreads();
-  if (a.stats != nullptr && threadIdx.x < sizeof(ctd_playout_stats) / 8 && bst[threadIdx.x] != 0) {
-    unsigned long long* gs = reinterpret_cast<unsigned long long*>(a.stats);
-    const int maxi = offsetof(ctd_playout_stats, max_steps) / 8;
-    if ((int)threadIdx.x == maxi) atomicMax(&gs[maxi], bst[threadIdx.x]);
-    else atomicAdd(&gs[threadIdx.x], bst[threadIdx.x]);
-  }
-}
+// the same kernel specialised for the preset eight, compiled in ctd_playout_preset.cu
+cudaError_t ctd_playout_preset_launch(const CtdPlayoutArgs& a, int grid, cudaStream_t stream);
+cudaError_t ctd_playout_preset_blocks_per_sm(int* per_sm);
 
 // ------------------------------------------------------------------------------------------ CFR roots + MCCFR
 // run_utils.create_a_close_to_finished_game / create_a_random_game (run_utils.py:29-72): play a preset game to
@@ -800,6 +660,7 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_encode(const ctd_state* slots
 // ------------------------------------------------------------------------------------------ host side / C ABI
 struct ctd_engine {
   int device;
+  uint32_t slots_preset_n;  // slots [0, slots_preset_n) are known to hold preset-ruleset games (ctd_reset / ctd_load_states)
   uint32_t capacity;
   ctd_state* d_slots;
   cudaStream_t stream;
@@ -963,6 +824,7 @@ ctd_status ctd_reset(ctd_engine* e, uint32_t n, uint64_t seed, uint64_t first_gi
   if (n == 0) return CTD_OK;
   CTD_CUDA(e, cudaSetDevice(e->device));
   e->seed = seed;
+  e->slots_preset_n = ruleset == CTD_RULESET_PRESET ? n : 0;
   ctd_k_reset<<<ctd_blocks(n), CTD_BLOCK, 0, e->stream>>>(e->d_slots, n, seed, first_gid, ruleset, ctd_tapes(e));
   e->launches++;
   CTD_CUDA(e, cudaGetLastError());
@@ -972,6 +834,15 @@ ctd_status ctd_reset(ctd_engine* e, uint32_t n, uint64_t seed, uint64_t first_gi
 ctd_status ctd_load_states(ctd_engine* e, uint32_t first_slot, uint32_t n, const ctd_state* states) {
   if (!e || !states || (uint64_t)first_slot + n > e->capacity) return CTD_EARG;
   CTD_CUDA(e, cudaSetDevice(e->device));
+  {  // keep track of the leading run of slots known to hold preset-ruleset games (picks the specialised playout kernel)
+    bool all_preset = true;
+    for (uint32_t i = 0; i < n && all_preset; ++i) all_preset = states[i].ruleset == CTD_RULESET_PRESET;
+    if (all_preset && first_slot <= e->slots_preset_n) {
+      if (first_slot + n > e->slots_preset_n) e->slots_preset_n = first_slot + n;
+    } else if (!all_preset && first_slot < e->slots_preset_n) {
+      e->slots_preset_n = first_slot;
+    }
+  }
   CTD_CUDA(e, cudaMemcpyAsync(e->d_slots + first_slot, states, (size_t)n * sizeof(ctd_state), cudaMemcpyHostToDevice,
                               e->stream));
   CTD_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -989,6 +860,7 @@ ctd_status ctd_store_states(ctd_engine* e, uint32_t first_slot, uint32_t n, ctd_
 
 ctd_status ctd_states_dev(ctd_engine* e, void** dev_ptr) {
   if (!e || !dev_ptr) return CTD_EARG;
+  e->slots_preset_n = 0;   // the caller may write the slots behind the engine's back
   *dev_ptr = e->d_slots;
   return CTD_OK;
 }
@@ -1079,9 +951,10 @@ ctd_status ctd_step(ctd_engine* e, uint32_t n, const ctd_option* chosen, int8_t*
 }
 
 // persistent grid: enough CTAs to fill every SM at the kernel's occupancy
-static ctd_status ctd_playout_grid(ctd_engine* e, uint64_t n_games, int* grid) {
+static ctd_status ctd_playout_grid(ctd_engine* e, uint64_t n_games, int* grid, bool preset) {
   int per_sm = 0;
-  CTD_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctd_k_playout, CTD_BLOCK, 0));
+  if (preset) CTD_CUDA(e, ctd_playout_preset_blocks_per_sm(&per_sm));
+  else CTD_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctd_k_playout, CTD_BLOCK, 0));
   if (per_sm < 1) per_sm = 1;
   uint64_t want = (uint64_t)e->sm_count * per_sm;
   uint64_t need = (n_games + CTD_WARPS_PER_BLOCK - 1) / CTD_WARPS_PER_BLOCK;
@@ -1091,17 +964,23 @@ static ctd_status ctd_playout_grid(ctd_engine* e, uint64_t n_games, int* grid) {
 }
 
 static ctd_status ctd_playout_launch(ctd_engine* e, CtdPlayoutArgs& a, ctd_playout_stats* stats, float* elapsed_ms) {
+  // every game of this launch is known to play the preset eight: the specialised kernel (ctd_playout_preset.cu)
+  const bool preset = a.slots == nullptr ? a.ruleset == CTD_RULESET_PRESET : a.n_games <= e->slots_preset_n;
   int grid = 1;
-  ctd_status s = ctd_playout_grid(e, a.n_games, &grid);
+  ctd_status s = ctd_playout_grid(e, a.n_games, &grid, preset);
   if (s != CTD_OK) return s;
   CTD_CUDA(e, cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream));
   CTD_CUDA(e, cudaMemsetAsync(e->d_stats, 0, sizeof(ctd_playout_stats), e->stream));
   a.counter = e->d_counter;
   a.stats = e->d_stats;
   CTD_CUDA(e, cudaEventRecord(e->ev0, e->stream));
-  ctd_k_playout<<<grid, CTD_BLOCK, 0, e->stream>>>(a);
+  if (preset) {
+    CTD_CUDA(e, ctd_playout_preset_launch(a, grid, e->stream));
+  } else {
+    ctd_k_playout<<<grid, CTD_BLOCK, 0, e->stream>>>(a);
+    CTD_CUDA(e, cudaGetLastError());
+  }
   e->launches++;
-  CTD_CUDA(e, cudaGetLastError());
   CTD_CUDA(e, cudaEventRecord(e->ev1, e->stream));
   if (stats) CTD_CUDA(e, cudaMemcpyAsync(stats, e->d_stats, sizeof(ctd_playout_stats), cudaMemcpyDeviceToHost, e->stream));
   (void)elapsed_ms;
@@ -1188,6 +1067,7 @@ ctd_status ctd_make_roots(ctd_engine* e, uint32_t n, uint64_t seed, uint64_t fir
   CTD_CUDA(e, cudaSetDevice(e->device));
   ctd_status s = ctd_root_buffers(e);
   if (s != CTD_OK) return s;
+  e->slots_preset_n = 0;
   e->seed = seed;
   CtdRootArgs a{n, seed, first_gid, ruleset, back_lo, back_hi, e->d_slots, e->d_knows, e->d_used_cards, e->d_gids,
                 e->d_root_step};
@@ -1203,6 +1083,7 @@ ctd_status ctd_make_roots(ctd_engine* e, uint32_t n, uint64_t seed, uint64_t fir
 ctd_status ctd_load_roots(ctd_engine* e, uint32_t n, const ctd_state* roots, const void* knows, const uint8_t* used_cards,
                           const uint64_t* gids) {
   if (!e || n > e->capacity || !roots || !knows || !used_cards || !gids) return CTD_EARG;
+  e->slots_preset_n = 0;
   CTD_CUDA(e, cudaSetDevice(e->device));
   ctd_status s = ctd_root_buffers(e);
   if (s != CTD_OK) return s;

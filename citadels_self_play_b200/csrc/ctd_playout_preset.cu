@@ -1,0 +1,19 @@
+// ctd_playout_preset.cu -- the fused playout kernel specialised for the preset ruleset (see ctd_playout.cuh).
+// Device code only: CTD_DEVICE_ONLY keeps this translation unit from emitting host copies of the inline rules functions
+// (ctd_kernels.cu owns those); the two units share nothing but the launch wrappers below.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#define CTD_DEVICE_ONLY 1
+#define CTD_FIXED_PRESET 1
+#define CTD_PLAYOUT_KERNEL_NAME ctd_k_playout_preset
+#include "ctd_playout.cuh"
+
+cudaError_t ctd_playout_preset_launch(const CtdPlayoutArgs& a, int grid, cudaStream_t stream) {
+  ctd_k_playout_preset<<<grid, CTD_BLOCK, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t ctd_playout_preset_blocks_per_sm(int* per_sm) {
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, ctd_k_playout_preset, CTD_BLOCK, 0);
+}

@@ -37,7 +37,7 @@ __device__ __forceinline__ void ctd_ring_refill(CtdWork& w, int lane) {
 }
 
 // scalar fallback: lane 0 materialises the list, draws k, picks
-__device__ __noinline__ uint64_t ctd_choose_scalar(CtdWork& w, int lane, uint64_t* buf, uint32_t* count_out, int want) {
+static __device__ __noinline__ uint64_t ctd_choose_scalar(CtdWork& w, int lane, uint64_t* buf, uint32_t* count_out, int want) {
   CTD_ASSUME_SHARED(&w);
   uint64_t d = 0;
   uint32_t n = 0;
@@ -104,7 +104,7 @@ enum { CTD_PM_ROLE_PICK, CTD_PM_GOLD_OR_CARD, CTD_PM_SINGLE, CTD_PM_KEEP, CTD_PM
 #endif
 // `ring` (playout kernel): the warp's Philox ring, refilled at the top of the step, so the one draw of the cooperative
 // path is a broadcast read by every lane instead of lane-0 code followed by a shuffle.
-__device__ CTD_CHOOSE_ATTR uint64_t ctd_warp_choose(CtdWork& w, int lane, uint64_t* buf, uint32_t* count_out = nullptr,
+static __device__ CTD_CHOOSE_ATTR uint64_t ctd_warp_choose(CtdWork& w, int lane, uint64_t* buf, uint32_t* count_out = nullptr,
                                                  int want = -1, const uint32_t* ring = nullptr) {
   const int p = w.player, st = w.state;
   if ((w.gflags & 2) || p >= 6) return ctd_choose_scalar(w, lane, buf, count_out, want);
@@ -261,10 +261,10 @@ __device__ CTD_CHOOSE_ATTR uint64_t ctd_warp_choose(CtdWork& w, int lane, uint64
     int q1 = (int)k;
     q1 += q1 >= p ? 1 : 0;
     switch (nm) {
-      case CTD_ASSASSIN: return CTD_K_ASSASSINATION | me | ctd_f_rank(1 + (int)k);
-      case CTD_THIEF: return CTD_K_STEAL | me | ctd_f_rank(2 + (int)k);
+      case CTD_ASSASSIN: CTD_NOT_PRESET(); return CTD_K_ASSASSINATION | me | ctd_f_rank(1 + (int)k);
+      case CTD_THIEF: CTD_NOT_PRESET(); return CTD_K_STEAL | me | ctd_f_rank(2 + (int)k);
       case CTD_SPY: return CTD_K_SPY | me | ctd_f_target(q) | ctd_f_named(CTD_N_TRADE + (int)k % 5);
-      case CTD_MAGICIAN: {
+      case CTD_MAGICIAN: CTD_NOT_PRESET(); {
         if (k < 5) return CTD_K_MAGIC_HAND_CHANGE | me | ctd_f_target(q1);
         k -= 5;  // every discard_and_draw option has the same effect; recover (r, j) for the descriptor
         int r = 1;
@@ -277,9 +277,9 @@ __device__ CTD_CHOOSE_ATTR uint64_t ctd_warp_choose(CtdWork& w, int lane, uint64
       }
       case CTD_WIZARD: return CTD_K_LOOK_AT_HAND | me | ctd_f_target(ctd_kth_bit(m1, k, lane));
       case CTD_KING: return CTD_K_TAKE_CROWN_KING | me;
-      case CTD_BISHOP: return CTD_K_BISHOP | me;
-      case CTD_MERCHANT: return CTD_K_MERCHANT | me;
-      case CTD_ARCHITECT: return CTD_K_ARCHITECT | me;
+      case CTD_BISHOP: CTD_NOT_PRESET(); return CTD_K_BISHOP | me;
+      case CTD_MERCHANT: CTD_NOT_PRESET(); return CTD_K_MERCHANT | me;
+      case CTD_ARCHITECT: CTD_NOT_PRESET(); return CTD_K_ARCHITECT | me;
       case CTD_ABBOT: return CTD_K_ABBOT | me | ctd_f_count((int)k) | ctd_f_r((int)__popc(m1));
       case CTD_NAVIGATOR: return CTD_K_NAVIGATOR | me | ctd_f_named(k == 0 ? CTD_N_4GOLD : CTD_N_4CARD);
       default: {  // CTD_WARLORD: (seat, slot) lanes, seats 0..2 then 3..5
