@@ -78,7 +78,7 @@
 #define CTD_HAND_CAP 48
 #define CTD_BLD_CAP 32 /* the Cardinal builds without limit inside CFR's hypothetical games (19 seen) */
 #define CTD_MUS_CAP 32
-#define CTD_JD_CAP 32
+#define CTD_JD_CAP 48 /* Smithy / Park draw into just_drawn_cards and nothing empties it until the next card pick: 33 seen in 5e5 classic games */
 #define CTD_DECK_CAP 128 /* ring buffer, power of two */
 #define CTD_DISC_CAP 128
 
@@ -203,7 +203,7 @@ struct alignas(16) CtdWork {
   uint32_t steps;
 };
 
-#define CTD_SNAP_BYTES 1232
+#define CTD_SNAP_BYTES 1328
 static_assert(offsetof(CtdWork, scratch) == CTD_SNAP_BYTES, "CtdWork snapshot region");
 
 // ------------------------------------------------------------------------------------------ chance

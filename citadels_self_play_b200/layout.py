@@ -54,7 +54,7 @@ def opt_fields(d):
 
 # ---- MCCFR tree block (csrc/ctd_mccfr.cuh) ----
 KNOW_BYTES = 592
-SNAP_BYTES = 1232   # CtdWork snapshot (csrc/ctd_engine.cuh CTD_SNAP_BYTES)
+SNAP_BYTES = 1328   # CtdWork snapshot (csrc/ctd_engine.cuh CTD_SNAP_BYTES)
 HK_DTYPE = np.dtype([("pid", np.int8), ("conf", np.uint8), ("flags", np.uint8), ("n", np.uint8), ("off", np.uint16),
                      ("pad", np.uint16)])
 KNOW_DTYPE = np.dtype([("viewer", np.uint8), ("conf_mask", np.uint8), ("n_hk", np.uint8), ("wiz_n", np.uint8),
