@@ -61,7 +61,7 @@
 // the kernels fault on the device -- either hint alone was fine, both together were not -- so those stay generic.)
 
 // ------------------------------------------------------------------------------------------ constants
-// CTD_FIXED_PRESET (set by ctd_playout_preset.cu only): the translation unit plays the preset ruleset exclusively -- Witch,
+// CTD_FIXED_PRESET (set by ctd_preset_playout.cu / ctd_preset_search.cu only): the translation unit plays the preset ruleset exclusively -- Witch,
 // Spy, Wizard, King, Abbot, Alchemist, Navigator, Warlord (game/game.py:479-486) -- so every option kind and character
 // outside it is unreachable and the compiler drops that code.
 #ifdef CTD_FIXED_PRESET

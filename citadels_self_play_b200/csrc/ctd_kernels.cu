@@ -18,6 +18,7 @@
 #include "ctd_warp.cuh"
 #include "ctd_playout.cuh"
 #include "ctd_mccfr.cuh"
+#include "ctd_search.cuh"
 #include "ctd_value_tc.cuh"
 
 
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_choose_check(const ctd_state*
   if (lane == 0) mismatches[slot] = bad;
 }
 
-// the same kernel specialised for the preset eight, compiled in ctd_playout_preset.cu
+// the same kernel specialised for the preset eight, compiled in ctd_preset_playout.cu
 cudaError_t ctd_playout_preset_launch(const CtdPlayoutArgs& a, int grid, cudaStream_t stream);
 cudaError_t ctd_playout_preset_blocks_per_sm(int* per_sm);
 
@@ -236,87 +237,12 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_make_roots(CtdRootArgs a) {
   ctd_record_store(&a.roots[slot], &stage[wib], lane);
 }
 
-struct CtdMccfrArgs {
-  uint32_t n_roots;
-  const ctd_state* roots;
-  const CtdKnow* knows;
-  const uint8_t* used_cards;
-  const uint64_t* gids;
-  uint64_t seed;
-  uint32_t iterations;
-  uint32_t max_nodes, child_cap, arr_cap;
-  uint8_t* trees;
-  size_t tree_stride;
-  ctd_mccfr_result* results;
-  unsigned long long* counter;
-  uint64_t* opts_scratch;  // [gridDim.x * CTD_WARPS_PER_BLOCK][CTD_MCCFR_OPT_CAP]
-};
-
-__device__ __forceinline__ CtdTree ctd_tree_at(uint8_t* base, uint32_t max_nodes, uint32_t child_cap) {
-  CtdTree T;
-  T.hdr = (CtdTreeHdr*)base;
-  T.nodes = (CtdNode*)(base + sizeof(CtdTreeHdr));
-  T.children = (CtdChild*)((uint8_t*)T.nodes + (size_t)max_nodes * sizeof(CtdNode));
-  T.arr = (double*)((uint8_t*)T.children + (size_t)child_cap * sizeof(CtdChild));
-  return T;
-}
-
-__device__ void ctd_write_result(CtdTree& T, ctd_mccfr_result* r) {
-  const CtdTreeHdr& h = *T.hdr;
-  const CtdNode& n = T.nodes[0];
-  r->status = h.status; r->n_nodes = h.n_nodes; r->iterations = h.iterations; r->rng_draws = h.rng_draws;
-  r->n_children = n.n_children; r->role_pick = (n.flags & CTD_NF_ROLE_PICK) ? 1 : 0;
-  r->viewer = h.viewer; r->player = n.player;
-  for (int i = 0; i < 6; ++i) { r->node_value[i] = n.V[i]; r->winning_probabilities[i] = n.P[i]; }
-  const uint32_t K = n.n_children < CTD_MCCFR_MAX_RESULT ? n.n_children : CTD_MCCFR_MAX_RESULT;
-  const bool rp = n.flags & CTD_NF_ROLE_PICK;
-  const uint32_t na = n.n_children == 0 ? 0 : (rp ? 60 : K);
-  for (uint32_t i = 0; i < K; ++i) r->options[i] = T.children[n.child_off + i].desc;
-  const double *R = ctd_R(T, n), *S = ctd_S(T, n), *C = ctd_C(T, n);
-  for (uint32_t i = 0; i < na; ++i) { r->cumulative_regrets[i] = R[i]; r->strategy[i] = S[i]; r->cumulative_strategy[i] = C[i]; }
-}
-
-#ifndef CTD_MCCFR_ALL_LANES
-#define CTD_MCCFR_ALL_LANES 1
-#endif
-#ifndef CTD_MCCFR_MIN_BLOCKS
-#define CTD_MCCFR_MIN_BLOCKS 3 /* 80 registers: fewer spills on the single active lane; 24 trees per SM resident (measured best at the 4096-root configuration) */
-#endif
-__global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) ctd_k_mccfr(CtdMccfrArgs a) {
-  __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
-  __shared__ CtdKnow knows[CTD_WARPS_PER_BLOCK];
-  __shared__ __align__(16) uint8_t scratch[CTD_WARPS_PER_BLOCK][384];
-  __shared__ __align__(16) ctd_state tstage[CTD_WARPS_PER_BLOCK];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  uint64_t* opts = a.opts_scratch + ((size_t)blockIdx.x * CTD_WARPS_PER_BLOCK + wib) * CTD_MCCFR_OPT_CAP;
-  for (;;) {
-    unsigned long long t = 0;
-    if (lane == 0) t = atomicAdd(a.counter, 1ull);
-    t = __shfl_sync(CTD_FULL, t, 0);
-    if (t >= a.n_roots) break;
-    // Every lane runs the same scalar search on the same data (identical values to identical addresses, control flow
-    // uniform, the warp stays converged): no lane does anything the others do not, but leaf operations that are
-    // lane-parallel by nature -- moving a 1.8 KB node between HBM and the working set -- can split their work over the
-    // lanes without restructuring the walk (CTD_MCCFR_ALL_LANES=0 restores the one-lane form).
-    if (CTD_MCCFR_ALL_LANES || lane == 0) {
-      CtdTree T = ctd_tree_at(a.trees + t * a.tree_stride, a.max_nodes, a.child_cap);
-      T.w = &works[wib]; T.kn = &knows[wib]; T.opts = opts; T.scratch = scratch[wib]; T.stage = &tstage[wib];
-      CtdWork& w = *T.w;
-      for (int i = 0; i < 76; ++i) T.hdr->used_cards[i] = a.used_cards[t * 76 + i];
-      ctd_copy16(T.stage, &a.roots[t], (int)sizeof(ctd_state));
-      ctd_unpack(T.stage, w);
-      ctd_chance_init(w, a.seed, a.gids[t], 0);
-      w.stream = 1;
-      w.err = 0;
-      ctd_copy16(T.kn, &a.knows[t], (int)sizeof(CtdKnow));
-      ctd_tree_stage_used(T);
-      ctd_tree_init(T, a.max_nodes, a.child_cap, a.arr_cap, T.kn->viewer, a.gids[t], false, false);
-      ctd_cfr_train(T, a.iterations);
-      if (a.results) ctd_write_result(T, &a.results[t]);
-    }
-    __syncwarp();
-  }
-}
+// (CtdMccfrArgs, ctd_tree_at, ctd_write_result, ctd_k_mccfr and ctd_k_mccfr_pred live in ctd_search.cuh)
+// the same kernels specialised for the preset eight, compiled in ctd_preset_search.cu
+cudaError_t ctd_mccfr_preset_launch(const CtdMccfrArgs& a, int grid, cudaStream_t stream);
+cudaError_t ctd_mccfr_preset_blocks_per_sm(int* per_sm);
+cudaError_t ctd_mccfr_pred_preset_launch(const CtdPredArgs& p, int grid, cudaStream_t stream);
+cudaError_t ctd_mccfr_pred_preset_blocks_per_sm(int* per_sm);
 
 // ------------------------------------------------------------------------------------------ training targets
 // CFRNode.get_all_targets / build_train_targets (algorithms/deep_mccfr.py:258-274, :321-345): depth-first pre-order
@@ -476,63 +402,6 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_pack_trees(uint8_t* trees, si
   CtdTree T = ctd_tree_at(trees + t * tree_stride, max_nodes, child_cap);
   T.w = &works[wib]; T.stage = &tstage[wib];
   ctd_tree_pack_nodes(T);
-}
-
-struct CtdPredArgs {
-  CtdMccfrArgs m;
-  uint32_t max_depth;
-  int first;          // 1: build the trees' roots in this launch
-  float* feat;        // [n_roots][CTD_FEATURES_PAD]
-  float* pred;        // [n_roots][8]
-  uint8_t* pending;   // [n_roots]
-  uint32_t* n_pending;   // [0] trees waiting for a leaf value, [1] trees that yielded mid-walk
-  uint32_t budget;       // iterations a tree may walk in one wave
-};
-
-// one wave of CFRNode.cfr_pred for every tree: walk until a leaf value is needed (or the budget is spent)
-__global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) ctd_k_mccfr_pred(CtdPredArgs p) {
-  __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
-  __shared__ CtdKnow knows[CTD_WARPS_PER_BLOCK];
-  __shared__ __align__(16) uint8_t scratch[CTD_WARPS_PER_BLOCK][384];
-  __shared__ __align__(16) ctd_state tstage[CTD_WARPS_PER_BLOCK];
-  const CtdMccfrArgs& a = p.m;
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  uint64_t* opts = a.opts_scratch + ((size_t)blockIdx.x * CTD_WARPS_PER_BLOCK + wib) * CTD_MCCFR_OPT_CAP;
-  for (;;) {
-    unsigned long long t = 0;
-    if (lane == 0) t = atomicAdd(a.counter, 1ull);
-    t = __shfl_sync(CTD_FULL, t, 0);
-    if (t >= a.n_roots) break;
-    if (CTD_MCCFR_ALL_LANES || lane == 0) {   // all lanes on the same scalar walk, see ctd_k_mccfr
-      CtdTree T = ctd_tree_at(a.trees + t * a.tree_stride, a.max_nodes, a.child_cap);
-      T.w = &works[wib]; T.kn = &knows[wib]; T.opts = opts; T.scratch = scratch[wib]; T.stage = &tstage[wib];
-      CtdWork& w = *T.w;
-      if (p.first) {
-        for (int i = 0; i < 76; ++i) T.hdr->used_cards[i] = a.used_cards[t * 76 + i];
-        ctd_copy16(T.stage, &a.roots[t], (int)sizeof(ctd_state));
-        ctd_unpack(T.stage, w);
-        ctd_chance_init(w, a.seed, a.gids[t], 0);
-        w.stream = 1;
-        w.err = 0;
-        ctd_copy16(T.kn, &a.knows[t], (int)sizeof(CtdKnow));
-        ctd_tree_init(T, a.max_nodes, a.child_cap, a.arr_cap, T.kn->viewer, a.gids[t], false, true);
-      } else {
-        ctd_chance_init(w, a.seed, a.gids[t], 0);
-        w.stream = 1;
-        w.err = 0;
-        T.kn->err = 0;  // the working set is rebuilt from the tree on the first node load of this wave
-      }
-      ctd_tree_stage_used(T);
-      int r = CTD_PRED_DONE;
-      if (T.hdr->phase != 3)
-        r = ctd_cfr_pred_advance(T, a.iterations, p.max_depth, p.feat + t * CTD_FEATURES_PAD, p.pred + t * 8, p.budget);
-      p.pending[t] = r == CTD_PRED_WAIT ? 1 : 0;
-      if (r == CTD_PRED_WAIT && lane == 0) atomicAdd(p.n_pending, 1u);
-      if (r == CTD_PRED_YIELD && lane == 0) atomicAdd(p.n_pending + 1, 1u);
-      if (r == CTD_PRED_DONE && a.results) ctd_write_result(T, &a.results[t]);
-    }
-    __syncwarp();
-  }
 }
 
 // ValueOnlyNN.forward in eval mode (algorithms/models.py:17-23) with BatchNorm folded into fc1/fc2, then
@@ -964,7 +833,7 @@ static ctd_status ctd_playout_grid(ctd_engine* e, uint64_t n_games, int* grid, b
 }
 
 static ctd_status ctd_playout_launch(ctd_engine* e, CtdPlayoutArgs& a, ctd_playout_stats* stats, float* elapsed_ms) {
-  // every game of this launch is known to play the preset eight: the specialised kernel (ctd_playout_preset.cu)
+  // every game of this launch is known to play the preset eight: the specialised kernel (ctd_preset_playout.cu)
   const bool preset = a.slots == nullptr ? a.ruleset == CTD_RULESET_PRESET : a.n_games <= e->slots_preset_n;
   int grid = 1;
   ctd_status s = ctd_playout_grid(e, a.n_games, &grid, preset);
@@ -1142,7 +1011,9 @@ ctd_status ctd_mccfr(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32_t it
   a.seed = seed; a.iterations = iterations; a.max_nodes = mn; a.child_cap = cc; a.arr_cap = ac;
   a.trees = e->d_trees; a.tree_stride = stride; a.results = (ctd_mccfr_result*)e->d_scratch; a.counter = e->d_counter;
   int per_sm = 0;
-  CTD_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctd_k_mccfr, CTD_BLOCK, 0));
+  const bool preset = ruleset == CTD_RULESET_PRESET;   // the roots were made / loaded for this ruleset: specialised kernel
+  if (preset) CTD_CUDA(e, ctd_mccfr_preset_blocks_per_sm(&per_sm));
+  else CTD_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctd_k_mccfr, CTD_BLOCK, 0));
   if (per_sm < 1) per_sm = 1;
   uint64_t want = (uint64_t)e->sm_count * per_sm, needb = (n_roots + CTD_WARPS_PER_BLOCK - 1) / CTD_WARPS_PER_BLOCK;
   int grid = (int)(needb < want ? needb : want);
@@ -1155,7 +1026,8 @@ ctd_status ctd_mccfr(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32_t it
   }
   a.opts_scratch = e->d_opts_scratch;
   CTD_CUDA(e, cudaEventRecord(e->ev0, e->stream));
-  ctd_k_mccfr<<<grid, CTD_BLOCK, 0, e->stream>>>(a);
+  if (preset) CTD_CUDA(e, ctd_mccfr_preset_launch(a, grid, e->stream));
+  else ctd_k_mccfr<<<grid, CTD_BLOCK, 0, e->stream>>>(a);
   e->launches++;
   CTD_CUDA(e, cudaGetLastError());
   CTD_CUDA(e, cudaEventRecord(e->ev1, e->stream));
@@ -1473,7 +1345,9 @@ ctd_status ctd_mccfr_pred(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32
   }
   p.max_depth = max_depth; p.feat = e->d_feat; p.pred = e->d_pred; p.pending = e->d_pending; p.n_pending = e->d_n_pending;
   int per_sm = 0;
-  CTD_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctd_k_mccfr_pred, CTD_BLOCK, 0));
+  const bool preset = ruleset == CTD_RULESET_PRESET;
+  if (preset) CTD_CUDA(e, ctd_mccfr_pred_preset_blocks_per_sm(&per_sm));
+  else CTD_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctd_k_mccfr_pred, CTD_BLOCK, 0));
   if (per_sm < 1) per_sm = 1;
   uint64_t want = (uint64_t)e->sm_count * per_sm, needb = (n_roots + CTD_WARPS_PER_BLOCK - 1) / CTD_WARPS_PER_BLOCK;
   int grid = (int)(needb < want ? needb : want);
@@ -1492,7 +1366,8 @@ ctd_status ctd_mccfr_pred(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32
     CTD_CUDA(e, cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream));
     CTD_CUDA(e, cudaMemsetAsync(e->d_n_pending, 0, 2 * sizeof(uint32_t), e->stream));
     p.first = waves == 0;
-    ctd_k_mccfr_pred<<<grid, CTD_BLOCK, 0, e->stream>>>(p);
+    if (preset) CTD_CUDA(e, ctd_mccfr_pred_preset_launch(p, grid, e->stream));
+    else ctd_k_mccfr_pred<<<grid, CTD_BLOCK, 0, e->stream>>>(p);
     e->launches++;
     CTD_CUDA(e, cudaGetLastError());
     uint32_t np[2] = {0, 0};

@@ -1,5 +1,5 @@
 // ctd_playout.cuh -- the fused random-playout kernel (run_utils.py:37-41 for a batch of games), shared by two translation
-// units: ctd_kernels.cu instantiates it for any ruleset (ctd_k_playout), ctd_playout_preset.cu with CTD_FIXED_PRESET, where
+// units: ctd_kernels.cu instantiates it for any ruleset (ctd_k_playout), ctd_preset_playout.cu with CTD_FIXED_PRESET, where
 // every option kind and character outside the preset eight (game/game.py:479-486) is marked unreachable
 // (ctd_k_playout_preset: 7.9 k instead of 10.6 k instructions, +5 % env steps/s -- the kernel is instruction-fetch bound).
 #pragma once

@@ -1,4 +1,6 @@
-// ctd_playout_preset.cu -- the fused playout kernel specialised for the preset ruleset (see ctd_playout.cuh).
+// ctd_preset_playout.cu -- the fused playout kernel specialised for the preset ruleset (see ctd_playout.cuh).  One kernel
+// per translation unit on purpose: the kernel is sensitive to what else ptxas lays out next to it (1.02e9 env steps/s alone,
+// 9.5e8 with the search kernels in the same unit).
 // Device code only: CTD_DEVICE_ONLY keeps this translation unit from emitting host copies of the inline rules functions
 // (ctd_kernels.cu owns those); the two units share nothing but the launch wrappers below.
 #include <cuda_runtime.h>

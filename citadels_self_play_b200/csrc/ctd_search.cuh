@@ -1,0 +1,165 @@
+// ctd_search.cuh -- the two MCCFR search kernels (cfr_train / one wave of cfr_pred), shared by two translation units like
+// ctd_playout.cuh: ctd_kernels.cu instantiates them for any ruleset, ctd_preset_search.cu with CTD_FIXED_PRESET (everything
+// outside the preset eight unreachable) -- both kernels are instruction-fetch bound, so the smaller image is the faster one.
+#pragma once
+#include "ctd_playout.cuh"
+#include "ctd_mccfr.cuh"
+
+#ifndef CTD_MCCFR_KERNEL_NAME
+#define CTD_MCCFR_KERNEL_NAME ctd_k_mccfr
+#define CTD_MCCFR_PRED_KERNEL_NAME ctd_k_mccfr_pred
+#endif
+
+struct CtdMccfrArgs {
+  uint32_t n_roots;
+  const ctd_state* roots;
+  const CtdKnow* knows;
+  const uint8_t* used_cards;
+  const uint64_t* gids;
+  uint64_t seed;
+  uint32_t iterations;
+  uint32_t max_nodes, child_cap, arr_cap;
+  uint8_t* trees;
+  size_t tree_stride;
+  ctd_mccfr_result* results;
+  unsigned long long* counter;
+  uint64_t* opts_scratch;  // [gridDim.x * CTD_WARPS_PER_BLOCK][CTD_MCCFR_OPT_CAP]
+};
+
+__device__ __forceinline__ CtdTree ctd_tree_at(uint8_t* base, uint32_t max_nodes, uint32_t child_cap) {
+  CtdTree T;
+  T.hdr = (CtdTreeHdr*)base;
+  T.nodes = (CtdNode*)(base + sizeof(CtdTreeHdr));
+  T.children = (CtdChild*)((uint8_t*)T.nodes + (size_t)max_nodes * sizeof(CtdNode));
+  T.arr = (double*)((uint8_t*)T.children + (size_t)child_cap * sizeof(CtdChild));
+  return T;
+}
+
+static __device__ void ctd_write_result(CtdTree& T, ctd_mccfr_result* r) {
+  const CtdTreeHdr& h = *T.hdr;
+  const CtdNode& n = T.nodes[0];
+  r->status = h.status; r->n_nodes = h.n_nodes; r->iterations = h.iterations; r->rng_draws = h.rng_draws;
+  if (h.n_nodes == 0) { r->n_children = 0; r->role_pick = 0; r->viewer = 0; r->player = 0; return; }   // refused root: no tree
+  r->n_children = n.n_children; r->role_pick = (n.flags & CTD_NF_ROLE_PICK) ? 1 : 0;
+  r->viewer = h.viewer; r->player = n.player;
+  for (int i = 0; i < 6; ++i) { r->node_value[i] = n.V[i]; r->winning_probabilities[i] = n.P[i]; }
+  const uint32_t K = n.n_children < CTD_MCCFR_MAX_RESULT ? n.n_children : CTD_MCCFR_MAX_RESULT;
+  const bool rp = n.flags & CTD_NF_ROLE_PICK;
+  const uint32_t na = n.n_children == 0 ? 0 : (rp ? 60 : K);
+  for (uint32_t i = 0; i < K; ++i) r->options[i] = T.children[n.child_off + i].desc;
+  const double *R = ctd_R(T, n), *S = ctd_S(T, n), *C = ctd_C(T, n);
+  for (uint32_t i = 0; i < na; ++i) { r->cumulative_regrets[i] = R[i]; r->strategy[i] = S[i]; r->cumulative_strategy[i] = C[i]; }
+}
+
+#ifndef CTD_MCCFR_ALL_LANES
+#define CTD_MCCFR_ALL_LANES 1
+#endif
+#ifndef CTD_MCCFR_MIN_BLOCKS
+#define CTD_MCCFR_MIN_BLOCKS 3 /* 80 registers: fewer spills on the single active lane; 24 trees per SM resident (measured best at the 4096-root configuration) */
+#endif
+__global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) CTD_MCCFR_KERNEL_NAME(CtdMccfrArgs a) {
+  __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
+  __shared__ CtdKnow knows[CTD_WARPS_PER_BLOCK];
+  __shared__ __align__(16) uint8_t scratch[CTD_WARPS_PER_BLOCK][384];
+  __shared__ __align__(16) ctd_state tstage[CTD_WARPS_PER_BLOCK];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint64_t* opts = a.opts_scratch + ((size_t)blockIdx.x * CTD_WARPS_PER_BLOCK + wib) * CTD_MCCFR_OPT_CAP;
+  for (;;) {
+    unsigned long long t = 0;
+    if (lane == 0) t = atomicAdd(a.counter, 1ull);
+    t = __shfl_sync(CTD_FULL, t, 0);
+    if (t >= a.n_roots) break;
+    // Every lane runs the same scalar search on the same data (identical values to identical addresses, control flow
+    // uniform, the warp stays converged): no lane does anything the others do not, but leaf operations that are
+    // lane-parallel by nature -- moving a 1.8 KB node between HBM and the working set -- can split their work over the
+    // lanes without restructuring the walk (CTD_MCCFR_ALL_LANES=0 restores the one-lane form).
+    if (CTD_MCCFR_ALL_LANES || lane == 0) {
+      CtdTree T = ctd_tree_at(a.trees + t * a.tree_stride, a.max_nodes, a.child_cap);
+      T.w = &works[wib]; T.kn = &knows[wib]; T.opts = opts; T.scratch = scratch[wib]; T.stage = &tstage[wib];
+      CtdWork& w = *T.w;
+      for (int i = 0; i < 76; ++i) T.hdr->used_cards[i] = a.used_cards[t * 76 + i];
+      ctd_copy16(T.stage, &a.roots[t], (int)sizeof(ctd_state));
+      ctd_unpack(T.stage, w);
+      ctd_chance_init(w, a.seed, a.gids[t], 0);
+      w.stream = 1;
+      w.err = 0;
+      ctd_copy16(T.kn, &a.knows[t], (int)sizeof(CtdKnow));
+      ctd_tree_stage_used(T);
+#ifdef CTD_FIXED_PRESET
+      if (w.ruleset != CTD_RULESET_PRESET) {   // the caller named the wrong ruleset for this root: refuse, do not run
+        T.hdr->n_nodes = 0; T.hdr->iterations = 0; T.hdr->rng_draws = 0; T.hdr->status = CTD_TREE_EENGINE;
+        if (a.results) { a.results[t].status = CTD_TREE_EENGINE; a.results[t].n_nodes = 0; a.results[t].n_children = 0; a.results[t].iterations = 0; }
+      } else
+#endif
+      {
+      ctd_tree_init(T, a.max_nodes, a.child_cap, a.arr_cap, T.kn->viewer, a.gids[t], false, false);
+      ctd_cfr_train(T, a.iterations);
+      if (a.results) ctd_write_result(T, &a.results[t]);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+struct CtdPredArgs {
+  CtdMccfrArgs m;
+  uint32_t max_depth;
+  int first;          // 1: build the trees' roots in this launch
+  float* feat;        // [n_roots][CTD_FEATURES_PAD]
+  float* pred;        // [n_roots][8]
+  uint8_t* pending;   // [n_roots]
+  uint32_t* n_pending;   // [0] trees waiting for a leaf value, [1] trees that yielded mid-walk
+  uint32_t budget;       // iterations a tree may walk in one wave
+};
+
+// one wave of CFRNode.cfr_pred for every tree: walk until a leaf value is needed (or the budget is spent)
+__global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) CTD_MCCFR_PRED_KERNEL_NAME(CtdPredArgs p) {
+  __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
+  __shared__ CtdKnow knows[CTD_WARPS_PER_BLOCK];
+  __shared__ __align__(16) uint8_t scratch[CTD_WARPS_PER_BLOCK][384];
+  __shared__ __align__(16) ctd_state tstage[CTD_WARPS_PER_BLOCK];
+  const CtdMccfrArgs& a = p.m;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint64_t* opts = a.opts_scratch + ((size_t)blockIdx.x * CTD_WARPS_PER_BLOCK + wib) * CTD_MCCFR_OPT_CAP;
+  for (;;) {
+    unsigned long long t = 0;
+    if (lane == 0) t = atomicAdd(a.counter, 1ull);
+    t = __shfl_sync(CTD_FULL, t, 0);
+    if (t >= a.n_roots) break;
+    if (CTD_MCCFR_ALL_LANES || lane == 0) {   // all lanes on the same scalar walk, see ctd_k_mccfr
+      CtdTree T = ctd_tree_at(a.trees + t * a.tree_stride, a.max_nodes, a.child_cap);
+      T.w = &works[wib]; T.kn = &knows[wib]; T.opts = opts; T.scratch = scratch[wib]; T.stage = &tstage[wib];
+      CtdWork& w = *T.w;
+      if (p.first) {
+        for (int i = 0; i < 76; ++i) T.hdr->used_cards[i] = a.used_cards[t * 76 + i];
+        ctd_copy16(T.stage, &a.roots[t], (int)sizeof(ctd_state));
+        ctd_unpack(T.stage, w);
+        ctd_chance_init(w, a.seed, a.gids[t], 0);
+        w.stream = 1;
+        w.err = 0;
+        ctd_copy16(T.kn, &a.knows[t], (int)sizeof(CtdKnow));
+#ifdef CTD_FIXED_PRESET
+        if (w.ruleset != CTD_RULESET_PRESET) {   // the caller named the wrong ruleset for this root: refuse, do not run
+          T.hdr->n_nodes = 0; T.hdr->iterations = 0; T.hdr->rng_draws = 0; T.hdr->status = CTD_TREE_EENGINE; T.hdr->phase = 3;
+        } else
+#endif
+        ctd_tree_init(T, a.max_nodes, a.child_cap, a.arr_cap, T.kn->viewer, a.gids[t], false, true);
+      } else {
+        ctd_chance_init(w, a.seed, a.gids[t], 0);
+        w.stream = 1;
+        w.err = 0;
+        T.kn->err = 0;  // the working set is rebuilt from the tree on the first node load of this wave
+      }
+      ctd_tree_stage_used(T);
+      int r = CTD_PRED_DONE;
+      if (T.hdr->phase != 3)
+        r = ctd_cfr_pred_advance(T, a.iterations, p.max_depth, p.feat + t * CTD_FEATURES_PAD, p.pred + t * 8, p.budget);
+      p.pending[t] = r == CTD_PRED_WAIT ? 1 : 0;
+      if (r == CTD_PRED_WAIT && lane == 0) atomicAdd(p.n_pending, 1u);
+      if (r == CTD_PRED_YIELD && lane == 0) atomicAdd(p.n_pending + 1, 1u);
+      if (r == CTD_PRED_DONE && a.results) ctd_write_result(T, &a.results[t]);
+    }
+    __syncwarp();
+  }
+}
+

@@ -104,3 +104,12 @@ def test_ragged_batch_mixed_rulesets_and_lengths(engine):
     fin = engine.store_states(64)
     assert (fin[:, 228] == 0).all() and (fin[:, 217] & 2).all()
     assert np.array_equal(fin[:, 227], mixed[:, 227])               # every game kept its ruleset
+
+
+def test_wrong_ruleset_named_for_a_search_is_refused_not_run(engine):
+    """The preset-specialised search kernels must not be handed roots of another ruleset: status 4 per tree, no crash."""
+    engine.make_roots(8, seed=3, first_gid=100, ruleset=1, back_lo=0, back_hi=30)      # classic roots ...
+    out = engine.mccfr(8, iterations=20, seed=3, ruleset=0)                             # ... searched "as preset"
+    assert (out["results"]["status"] == 4).all() and (out["results"]["n_nodes"] == 0).all()
+    out = engine.mccfr(8, iterations=20, seed=3, ruleset=1)                             # the handle is still fine
+    assert (out["results"]["status"] <= 1).all() and (out["results"]["n_nodes"] > 0).any()
