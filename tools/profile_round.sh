@@ -12,7 +12,7 @@ python tools/playout_perf.py 16384 > $out/${tag}_playout_plain.log 2>&1 || exit 
 ncu --set full --clock-control none --import-source on -k regex:ctd_k_playout -s 1 -c 1 -f -o $out/${tag}_playout \
   python tools/playout_perf.py 16384 > $out/${tag}_ncu_playout.log 2>&1
 REPS=1 python tools/mccfr_perf.py 2048 200 both > $out/${tag}_mccfr_plain.log 2>&1 || exit 1
-REPS=1 ncu --set full --clock-control none --import-source on -k regex:'ctd_k_mccfr$' -c 1 -f -o $out/${tag}_mccfr \
+REPS=1 ncu --set full --clock-control none --import-source on -k regex:'ctd_k_mccfr(_preset)?$' -c 1 -f -o $out/${tag}_mccfr \
   python tools/mccfr_perf.py 2048 200 pure > $out/${tag}_ncu_mccfr.log 2>&1
 REPS=1 ncu --set full --clock-control none --import-source on -k regex:ctd_k_mccfr_pred -s 2 -c 1 -f -o $out/${tag}_mccfr_pred \
   python tools/mccfr_perf.py 2048 200 deep > $out/${tag}_ncu_mccfr_pred.log 2>&1
