@@ -42,6 +42,7 @@ struct CtdPlayoutArgs {
   ctd_state* slots;  // non-null: continue from slots[0..n) instead of dealing new games
 };
 
+#ifndef CTD_NO_PLAYOUT_KERNEL
 // Outcome statistics are accumulated per block in shared memory (one shared atomic per field and game) and flushed
 // to HBM once per block.
 __global__ void __launch_bounds__(CTD_BLOCK, CTD_PLAYOUT_MIN_BLOCKS) CTD_PLAYOUT_KERNEL_NAME(CtdPlayoutArgs a) {
@@ -160,4 +161,4 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_PLAYOUT_MIN_BLOCKS) CTD_PLAYOUT
     else atomicAdd(&gs[threadIdx.x], bst[threadIdx.x]);
   }
 }
-
+#endif  // CTD_NO_PLAYOUT_KERNEL

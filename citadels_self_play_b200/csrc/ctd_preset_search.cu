@@ -1,14 +1,16 @@
-// ctd_preset_search.cu -- the MCCFR search kernels specialised for the preset ruleset (see ctd_search.cuh).
-// Device code only, like ctd_preset_playout.cu.
+// ctd_preset_search.cu -- cfr_train (ctd_k_mccfr) specialised for the preset ruleset (see ctd_search.cuh).  Device code only,
+// one kernel per translation unit: out-of-line device functions are compiled once per unit, under the tightest register
+// bound of the kernels that call them, so a kernel shares its unit only with itself.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
 
 #define CTD_DEVICE_ONLY 1
 #define CTD_FIXED_PRESET 1
-#define CTD_PLAYOUT_KERNEL_NAME ctd_k_playout_preset_unused
+#define CTD_NO_PLAYOUT_KERNEL 1
+#define CTD_NO_PRED_KERNEL 1
 #define CTD_MCCFR_KERNEL_NAME ctd_k_mccfr_preset
-#define CTD_MCCFR_PRED_KERNEL_NAME ctd_k_mccfr_pred_preset
+#define CTD_MCCFR_PRED_KERNEL_NAME ctd_k_mccfr_pred_preset_unused
 #include "ctd_search.cuh"
 
 cudaError_t ctd_mccfr_preset_launch(const CtdMccfrArgs& a, int grid, cudaStream_t stream) {
@@ -17,11 +19,4 @@ cudaError_t ctd_mccfr_preset_launch(const CtdMccfrArgs& a, int grid, cudaStream_
 }
 cudaError_t ctd_mccfr_preset_blocks_per_sm(int* per_sm) {
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, ctd_k_mccfr_preset, CTD_BLOCK, 0);
-}
-cudaError_t ctd_mccfr_pred_preset_launch(const CtdPredArgs& p, int grid, cudaStream_t stream) {
-  ctd_k_mccfr_pred_preset<<<grid, CTD_BLOCK, 0, stream>>>(p);
-  return cudaGetLastError();
-}
-cudaError_t ctd_mccfr_pred_preset_blocks_per_sm(int* per_sm) {
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, ctd_k_mccfr_pred_preset, CTD_BLOCK, 0);
 }

@@ -57,6 +57,7 @@ static __device__ void ctd_write_result(CtdTree& T, ctd_mccfr_result* r) {
 #ifndef CTD_MCCFR_MIN_BLOCKS
 #define CTD_MCCFR_MIN_BLOCKS 3 /* 80 registers: fewer spills on the single active lane; 24 trees per SM resident (measured best at the 4096-root configuration) */
 #endif
+#ifndef CTD_NO_TRAIN_KERNEL
 __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) CTD_MCCFR_KERNEL_NAME(CtdMccfrArgs a) {
   __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
   __shared__ CtdKnow knows[CTD_WARPS_PER_BLOCK];
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) CTD_MCCFR_KER
     __syncwarp();
   }
 }
+#endif  // CTD_NO_TRAIN_KERNEL
 
 struct CtdPredArgs {
   CtdMccfrArgs m;
@@ -112,6 +114,7 @@ struct CtdPredArgs {
   uint32_t budget;       // iterations a tree may walk in one wave
 };
 
+#ifndef CTD_NO_PRED_KERNEL
 // one wave of CFRNode.cfr_pred for every tree: walk until a leaf value is needed (or the budget is spent)
 __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) CTD_MCCFR_PRED_KERNEL_NAME(CtdPredArgs p) {
   __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
@@ -162,4 +165,4 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) CTD_MCCFR_PRE
     __syncwarp();
   }
 }
-
+#endif  // CTD_NO_PRED_KERNEL
