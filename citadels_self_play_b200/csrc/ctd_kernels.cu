@@ -14,6 +14,11 @@
 #include <new>
 #include <stddef.h>
 
+// the playout and search kernels are compiled one per translation unit (ctd_generic_*.cu, ctd_preset_*.cu): out-of-line
+// device functions are compiled once per unit under the tightest register bound of their callers
+#define CTD_NO_PLAYOUT_KERNEL 1
+#define CTD_NO_TRAIN_KERNEL 1
+#define CTD_NO_PRED_KERNEL 1
 #include "ctd_engine.cuh"
 #include "ctd_warp.cuh"
 #include "ctd_playout.cuh"
@@ -153,6 +158,8 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_choose_check(const ctd_state*
 }
 
 // the same kernel specialised for the preset eight, compiled in ctd_preset_playout.cu
+cudaError_t ctd_playout_generic_launch(const CtdPlayoutArgs& a, int grid, cudaStream_t stream);
+cudaError_t ctd_playout_generic_blocks_per_sm(int* per_sm);
 cudaError_t ctd_playout_preset_launch(const CtdPlayoutArgs& a, int grid, cudaStream_t stream);
 cudaError_t ctd_playout_preset_blocks_per_sm(int* per_sm);
 
@@ -239,6 +246,10 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_make_roots(CtdRootArgs a) {
 
 // (CtdMccfrArgs, ctd_tree_at, ctd_write_result, ctd_k_mccfr and ctd_k_mccfr_pred live in ctd_search.cuh)
 // the same kernels specialised for the preset eight, compiled in ctd_preset_search.cu
+cudaError_t ctd_mccfr_generic_launch(const CtdMccfrArgs& a, int grid, cudaStream_t stream);
+cudaError_t ctd_mccfr_generic_blocks_per_sm(int* per_sm);
+cudaError_t ctd_mccfr_pred_generic_launch(const CtdPredArgs& p, int grid, cudaStream_t stream);
+cudaError_t ctd_mccfr_pred_generic_blocks_per_sm(int* per_sm);
 cudaError_t ctd_mccfr_preset_launch(const CtdMccfrArgs& a, int grid, cudaStream_t stream);
 cudaError_t ctd_mccfr_preset_blocks_per_sm(int* per_sm);
 cudaError_t ctd_mccfr_pred_preset_launch(const CtdPredArgs& p, int grid, cudaStream_t stream);
@@ -823,7 +834,7 @@ ctd_status ctd_step(ctd_engine* e, uint32_t n, const ctd_option* chosen, int8_t*
 static ctd_status ctd_playout_grid(ctd_engine* e, uint64_t n_games, int* grid, bool preset) {
   int per_sm = 0;
   if (preset) CTD_CUDA(e, ctd_playout_preset_blocks_per_sm(&per_sm));
-  else CTD_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctd_k_playout, CTD_BLOCK, 0));
+  else CTD_CUDA(e, ctd_playout_generic_blocks_per_sm(&per_sm));
   if (per_sm < 1) per_sm = 1;
   uint64_t want = (uint64_t)e->sm_count * per_sm;
   uint64_t need = (n_games + CTD_WARPS_PER_BLOCK - 1) / CTD_WARPS_PER_BLOCK;
@@ -846,8 +857,7 @@ static ctd_status ctd_playout_launch(ctd_engine* e, CtdPlayoutArgs& a, ctd_playo
   if (preset) {
     CTD_CUDA(e, ctd_playout_preset_launch(a, grid, e->stream));
   } else {
-    ctd_k_playout<<<grid, CTD_BLOCK, 0, e->stream>>>(a);
-    CTD_CUDA(e, cudaGetLastError());
+    CTD_CUDA(e, ctd_playout_generic_launch(a, grid, e->stream));
   }
   e->launches++;
   CTD_CUDA(e, cudaEventRecord(e->ev1, e->stream));
@@ -1013,7 +1023,7 @@ ctd_status ctd_mccfr(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32_t it
   int per_sm = 0;
   const bool preset = ruleset == CTD_RULESET_PRESET;   // the roots were made / loaded for this ruleset: specialised kernel
   if (preset) CTD_CUDA(e, ctd_mccfr_preset_blocks_per_sm(&per_sm));
-  else CTD_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctd_k_mccfr, CTD_BLOCK, 0));
+  else CTD_CUDA(e, ctd_mccfr_generic_blocks_per_sm(&per_sm));
   if (per_sm < 1) per_sm = 1;
   uint64_t want = (uint64_t)e->sm_count * per_sm, needb = (n_roots + CTD_WARPS_PER_BLOCK - 1) / CTD_WARPS_PER_BLOCK;
   int grid = (int)(needb < want ? needb : want);
@@ -1027,7 +1037,7 @@ ctd_status ctd_mccfr(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32_t it
   a.opts_scratch = e->d_opts_scratch;
   CTD_CUDA(e, cudaEventRecord(e->ev0, e->stream));
   if (preset) CTD_CUDA(e, ctd_mccfr_preset_launch(a, grid, e->stream));
-  else ctd_k_mccfr<<<grid, CTD_BLOCK, 0, e->stream>>>(a);
+  else CTD_CUDA(e, ctd_mccfr_generic_launch(a, grid, e->stream));
   e->launches++;
   CTD_CUDA(e, cudaGetLastError());
   CTD_CUDA(e, cudaEventRecord(e->ev1, e->stream));
@@ -1347,7 +1357,7 @@ ctd_status ctd_mccfr_pred(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32
   int per_sm = 0;
   const bool preset = ruleset == CTD_RULESET_PRESET;
   if (preset) CTD_CUDA(e, ctd_mccfr_pred_preset_blocks_per_sm(&per_sm));
-  else CTD_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctd_k_mccfr_pred, CTD_BLOCK, 0));
+  else CTD_CUDA(e, ctd_mccfr_pred_generic_blocks_per_sm(&per_sm));
   if (per_sm < 1) per_sm = 1;
   uint64_t want = (uint64_t)e->sm_count * per_sm, needb = (n_roots + CTD_WARPS_PER_BLOCK - 1) / CTD_WARPS_PER_BLOCK;
   int grid = (int)(needb < want ? needb : want);
@@ -1367,7 +1377,7 @@ ctd_status ctd_mccfr_pred(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32
     CTD_CUDA(e, cudaMemsetAsync(e->d_n_pending, 0, 2 * sizeof(uint32_t), e->stream));
     p.first = waves == 0;
     if (preset) CTD_CUDA(e, ctd_mccfr_pred_preset_launch(p, grid, e->stream));
-    else ctd_k_mccfr_pred<<<grid, CTD_BLOCK, 0, e->stream>>>(p);
+    else CTD_CUDA(e, ctd_mccfr_pred_generic_launch(p, grid, e->stream));
     e->launches++;
     CTD_CUDA(e, cudaGetLastError());
     uint32_t np[2] = {0, 0};
