@@ -352,7 +352,7 @@ def main():
                          "traffic": _traffic(G), "traffic_source": "profiles/r01_playout_traffic.json (ncu, bytes per launch)",
                          "peak_source": peak_src,
                          "note": "algorithmic 512 B/env step (SURVEY 8(d)); the fused kernel keeps the game in shared "
-                                 "memory for its ~420 steps, so the real limiter is instruction issue (see profiles/)",
+                                 "memory for its ~420 steps (4 B of DRAM traffic per step), so the real limiter is the SM front end: instruction fetch (see profiles/README.md)",
                          "kernel_env_steps_per_s_per_gpu": per_gpu_kernel},
             "e2e": {"value": e2e_steps / e2e_wall, "unit": "env steps/s", "h2d_bytes_per_step": 256 * G * world,
                     "d2h_bytes_per_step": 3 * G * world,
