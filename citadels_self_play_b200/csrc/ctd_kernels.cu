@@ -544,6 +544,11 @@ struct ctd_engine {
   uint32_t capacity;
   ctd_state* d_slots;
   cudaStream_t stream;
+  cudaStream_t stream2;            // second stream of the deep-MCCFR wave pipeline (created on first use)
+  unsigned long long* d_counter2;
+  uint32_t* d_n_pending2;
+  cudaEvent_t ev_join;
+  uint32_t* h_np;                  // pinned host words the waves report into
   bool own_stream;
   uint64_t seed;
   uint64_t launches;
@@ -650,6 +655,10 @@ void ctd_destroy(ctd_engine* e) {
   if (e->d_tape_off) cudaFree(e->d_tape_off);
   if (e->d_scratch) cudaFree(e->d_scratch);
   if (e->d_counter) cudaFree(e->d_counter);
+  if (e->d_counter2) cudaFree(e->d_counter2);
+  if (e->d_n_pending2) cudaFree(e->d_n_pending2);
+  if (e->h_np) cudaFreeHost(e->h_np);
+  if (e->stream2) { cudaStreamDestroy(e->stream2); cudaEventDestroy(e->ev_join); }
   if (e->d_stats) cudaFree(e->d_stats);
   if (e->d_knows) cudaFree(e->d_knows);
   if (e->d_used_cards) cudaFree(e->d_used_cards);
@@ -1214,6 +1223,7 @@ static ctd_status ctd_pred_buffers(ctd_engine* e) {
   CTD_CUDA(e, cudaMalloc((void**)&e->d_pred, (size_t)e->capacity * 8 * sizeof(float)));
   CTD_CUDA(e, cudaMalloc((void**)&e->d_pending, (size_t)e->capacity));
   CTD_CUDA(e, cudaMalloc((void**)&e->d_n_pending, 2 * sizeof(uint32_t)));
+  CTD_CUDA(e, cudaMallocHost((void**)&e->h_np, 4 * sizeof(uint32_t)));
   CTD_CUDA(e, cudaMemsetAsync(e->d_feat, 0, (size_t)e->capacity * CTD_FEATURES_PAD * sizeof(float), e->stream));
   CTD_CUDA(e, cudaMemsetAsync(e->d_pred, 0, (size_t)e->capacity * 8 * sizeof(float), e->stream));
   CTD_CUDA(e, cudaMemsetAsync(e->d_pending, 0, (size_t)e->capacity, e->stream));
@@ -1228,21 +1238,25 @@ static ctd_status ctd_pred_buffers(ctd_engine* e) {
 }
 
 // the value model on rows [0,n) of d_feat -> d_pred (rows with pending == 0 may be skipped)
-static ctd_status ctd_value_forward(ctd_engine* e, uint32_t n, const uint8_t* pending, float weight) {
+// rows [row0, row0 + n) of the feature matrix (`pending` is the mask of those rows), on `st`
+static ctd_status ctd_value_forward(ctd_engine* e, uint32_t n, const uint8_t* pending, float weight, uint32_t row0 = 0,
+                                    cudaStream_t st = nullptr) {
+  if (st == nullptr) st = e->stream;
+  const float* feat = e->d_feat + (size_t)row0 * CTD_FEATURES_PAD;
+  float* pred = e->d_pred + (size_t)row0 * 8;
   if (e->value_backend == 0) {
-    ctd_k_value_mlp<<<(n + CTD_MLP_ROWS - 1) / CTD_MLP_ROWS, 256, CTD_MLP_SMEM, e->stream>>>(e->d_feat, pending, n, e->model, e->d_pred, weight);
+    ctd_k_value_mlp<<<(n + CTD_MLP_ROWS - 1) / CTD_MLP_ROWS, 256, CTD_MLP_SMEM, st>>>(feat, pending, n, e->model, pred, weight);
     e->launches++;
     CTD_CUDA(e, cudaGetLastError());
     return CTD_OK;
   }
+  float *h1 = e->d_h1 + (size_t)row0 * 512, *h2 = e->d_h2 + (size_t)row0 * 256, *h3 = e->d_h3 + (size_t)row0 * 128;
   const int M = (int)n, gm = (M + CTD_TC_BM - 1) / CTD_TC_BM;
-  ctd_k_linear_tc<<<dim3(gm, 512 / CTD_TC_BN), 128, CTD_TC_SMEM, e->stream>>>(e->d_feat, CTD_FEATURES_PAD, e->tc_w1, CTD_FEATURES_PAD,
-                                                                              e->model.b1, e->d_h1, 512, M, CTD_FEATURES_PAD, 1, e->d_tc_err);
-  ctd_k_linear_tc<<<dim3(gm, 256 / CTD_TC_BN), 128, CTD_TC_SMEM, e->stream>>>(e->d_h1, 512, e->tc_w2, 512, e->model.b2, e->d_h2, 256, M, 512,
-                                                                              1, e->d_tc_err);
-  ctd_k_linear_tc<<<dim3(gm, 128 / CTD_TC_BN), 128, CTD_TC_SMEM, e->stream>>>(e->d_h2, 256, e->tc_w3, 256, e->model.b3, e->d_h3, 128, M, 256,
-                                                                              1, e->d_tc_err);
-  ctd_k_value_head<<<(n + 127) / 128, 128, 0, e->stream>>>(e->d_h3, e->model.w4t, e->model.b4, pending, n, e->d_pred, weight);
+  ctd_k_linear_tc<<<dim3(gm, 512 / CTD_TC_BN), 128, CTD_TC_SMEM, st>>>(feat, CTD_FEATURES_PAD, e->tc_w1, CTD_FEATURES_PAD, e->model.b1, h1, 512,
+                                                                       M, CTD_FEATURES_PAD, 1, e->d_tc_err);
+  ctd_k_linear_tc<<<dim3(gm, 256 / CTD_TC_BN), 128, CTD_TC_SMEM, st>>>(h1, 512, e->tc_w2, 512, e->model.b2, h2, 256, M, 512, 1, e->d_tc_err);
+  ctd_k_linear_tc<<<dim3(gm, 128 / CTD_TC_BN), 128, CTD_TC_SMEM, st>>>(h2, 256, e->tc_w3, 256, e->model.b3, h3, 128, M, 256, 1, e->d_tc_err);
+  ctd_k_value_head<<<(n + 127) / 128, 128, 0, st>>>(h3, e->model.w4t, e->model.b4, pending, n, pred, weight);
   e->launches += 4;
   CTD_CUDA(e, cudaGetLastError());
   return CTD_OK;
@@ -1359,35 +1373,76 @@ ctd_status ctd_mccfr_pred(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32
   if (preset) CTD_CUDA(e, ctd_mccfr_pred_preset_blocks_per_sm(&per_sm));
   else CTD_CUDA(e, ctd_mccfr_pred_generic_blocks_per_sm(&per_sm));
   if (per_sm < 1) per_sm = 1;
-  uint64_t want = (uint64_t)e->sm_count * per_sm, needb = (n_roots + CTD_WARPS_PER_BLOCK - 1) / CTD_WARPS_PER_BLOCK;
-  int grid = (int)(needb < want ? needb : want);
-  size_t ob = (size_t)grid * CTD_WARPS_PER_BLOCK * CTD_MCCFR_OPT_CAP * sizeof(uint64_t);
+  // Two groups of trees take turns: each group's waves (walk kernel -> batched leaf evaluation -> walk kernel ...) run on
+  // their own stream, so the tail of one group's wave -- a few trees with expensive expansions -- overlaps with the other
+  // group's kernel instead of idling the GPU.  Trees are independent, results do not depend on the grouping.
+  const char* genv = getenv("CTD_PRED_GROUPS");
+  const int G = (genv ? atoi(genv) : 2) >= 2 && n_roots >= 1024 ? 2 : 1;
+  if (G == 2 && !e->stream2) {
+    CTD_CUDA(e, cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+    CTD_CUDA(e, cudaMalloc((void**)&e->d_counter2, sizeof(unsigned long long)));
+    CTD_CUDA(e, cudaMalloc((void**)&e->d_n_pending2, 2 * sizeof(uint32_t)));
+    CTD_CUDA(e, cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+  }
+  const uint32_t split = G == 2 ? ((n_roots / 2 + 7) & ~7u) : n_roots;
+  const uint32_t g_first[2] = {0, split}, g_n[2] = {split, n_roots - split};
+  cudaStream_t g_stream[2] = {e->stream, G == 2 ? e->stream2 : e->stream};
+  unsigned long long* g_counter[2] = {e->d_counter, e->d_counter2};
+  uint32_t* g_pending[2] = {e->d_n_pending, e->d_n_pending2};
+  int g_grid[2];
+  size_t g_opts_off[2] = {0, 0}, ob = 0;
+  for (int g = 0; g < G; ++g) {
+    uint64_t want = (uint64_t)e->sm_count * per_sm, needb = (g_n[g] + CTD_WARPS_PER_BLOCK - 1) / CTD_WARPS_PER_BLOCK;
+    g_grid[g] = (int)(needb < want ? needb : want);
+    g_opts_off[g] = ob;
+    ob += (size_t)g_grid[g] * CTD_WARPS_PER_BLOCK * CTD_MCCFR_OPT_CAP;
+  }
+  ob *= sizeof(uint64_t);
   if (ob > e->opts_scratch_bytes) {
     if (e->d_opts_scratch) CTD_CUDA(e, cudaFree(e->d_opts_scratch));
     e->d_opts_scratch = nullptr; e->opts_scratch_bytes = 0;
     CTD_CUDA(e, cudaMalloc((void**)&e->d_opts_scratch, ob));
     e->opts_scratch_bytes = ob;
   }
-  a.opts_scratch = e->d_opts_scratch;
   CTD_CUDA(e, cudaEventRecord(e->ev0, e->stream));
-  uint32_t waves = 0;
-  for (;; ++waves) {
-    if (waves > 2 * iterations + 4) { snprintf(e->err, sizeof(e->err), "ctd_mccfr_pred: wave limit"); return CTD_ECAP; }
-    CTD_CUDA(e, cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream));
-    CTD_CUDA(e, cudaMemsetAsync(e->d_n_pending, 0, 2 * sizeof(uint32_t), e->stream));
-    p.first = waves == 0;
-    if (preset) CTD_CUDA(e, ctd_mccfr_pred_preset_launch(p, grid, e->stream));
-    else CTD_CUDA(e, ctd_mccfr_pred_generic_launch(p, grid, e->stream));
+  if (G == 2) CTD_CUDA(e, cudaStreamWaitEvent(e->stream2, e->ev0, 0));
+  uint32_t waves = 0, g_waves[2] = {0, 0};
+  bool g_done[2] = {false, G == 1};
+  uint32_t* h_np = e->h_np;   // pinned: [group][2]
+  auto launch_wave = [&](int g) -> ctd_status {
+    CtdPredArgs q = p;
+    q.m.first_root = g_first[g]; q.m.n_roots = g_n[g]; q.m.counter = g_counter[g]; q.n_pending = g_pending[g];
+    q.m.opts_scratch = e->d_opts_scratch + g_opts_off[g];
+    q.first = g_waves[g] == 0;
+    CTD_CUDA(e, cudaMemsetAsync(g_counter[g], 0, sizeof(unsigned long long), g_stream[g]));
+    CTD_CUDA(e, cudaMemsetAsync(g_pending[g], 0, 2 * sizeof(uint32_t), g_stream[g]));
+    if (preset) CTD_CUDA(e, ctd_mccfr_pred_preset_launch(q, g_grid[g], g_stream[g]));
+    else CTD_CUDA(e, ctd_mccfr_pred_generic_launch(q, g_grid[g], g_stream[g]));
     e->launches++;
-    CTD_CUDA(e, cudaGetLastError());
-    uint32_t np[2] = {0, 0};
-    CTD_CUDA(e, cudaMemcpyAsync(np, e->d_n_pending, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
-    CTD_CUDA(e, cudaStreamSynchronize(e->stream));
-    if (np[0] == 0 && np[1] == 0) break;
-    if (np[0] != 0) {
-      s = ctd_value_forward(e, n_roots, e->d_pending, reward_weight);
+    CTD_CUDA(e, cudaMemcpyAsync(h_np + 2 * g, g_pending[g], 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, g_stream[g]));
+    ++g_waves[g];
+    return CTD_OK;
+  };
+  for (int g = 0; g < G; ++g) { s = launch_wave(g); if (s != CTD_OK) return s; }
+  while (!(g_done[0] && g_done[1])) {
+    for (int g = 0; g < G; ++g) {
+      if (g_done[g]) continue;
+      CTD_CUDA(e, cudaStreamSynchronize(g_stream[g]));
+      const uint32_t waiting = h_np[2 * g], yielded = h_np[2 * g + 1];
+      if (waiting == 0 && yielded == 0) { g_done[g] = true; continue; }
+      if (g_waves[g] > 2 * iterations + 4) { snprintf(e->err, sizeof(e->err), "ctd_mccfr_pred: wave limit"); return CTD_ECAP; }
+      if (waiting != 0) {
+        s = ctd_value_forward(e, g_n[g], e->d_pending + g_first[g], reward_weight, g_first[g], g_stream[g]);
+        if (s != CTD_OK) return s;
+      }
+      s = launch_wave(g);
       if (s != CTD_OK) return s;
     }
+  }
+  waves = (g_waves[0] > g_waves[1] ? g_waves[0] : g_waves[1]) - 1;
+  if (G == 2) {   // join: the engine's stream continues after both groups
+    CTD_CUDA(e, cudaEventRecord(e->ev_join, e->stream2));
+    CTD_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_join, 0));
   }
   CTD_CUDA(e, cudaEventRecord(e->ev1, e->stream));
   if (results) CTD_CUDA(e, cudaMemcpyAsync(results, e->d_scratch, rb, cudaMemcpyDeviceToHost, e->stream));

@@ -24,6 +24,7 @@ struct CtdMccfrArgs {
   ctd_mccfr_result* results;
   unsigned long long* counter;
   uint64_t* opts_scratch;  // [gridDim.x * CTD_WARPS_PER_BLOCK][CTD_MCCFR_OPT_CAP]
+  uint32_t first_root;     // this launch covers trees [first_root, first_root + n_roots)
 };
 
 __device__ __forceinline__ CtdTree ctd_tree_at(uint8_t* base, uint32_t max_nodes, uint32_t child_cap) {
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) CTD_MCCFR_KER
     if (lane == 0) t = atomicAdd(a.counter, 1ull);
     t = __shfl_sync(CTD_FULL, t, 0);
     if (t >= a.n_roots) break;
+    t += a.first_root;
     // Every lane runs the same scalar search on the same data (identical values to identical addresses, control flow
     // uniform, the warp stays converged): no lane does anything the others do not, but leaf operations that are
     // lane-parallel by nature -- moving a 1.8 KB node between HBM and the working set -- can split their work over the
@@ -129,6 +131,7 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) CTD_MCCFR_PRE
     if (lane == 0) t = atomicAdd(a.counter, 1ull);
     t = __shfl_sync(CTD_FULL, t, 0);
     if (t >= a.n_roots) break;
+    t += a.first_root;
     if (CTD_MCCFR_ALL_LANES || lane == 0) {   // all lanes on the same scalar walk, see ctd_k_mccfr
       CtdTree T = ctd_tree_at(a.trees + t * a.tree_stride, a.max_nodes, a.child_cap);
       T.w = &works[wib]; T.kn = &knows[wib]; T.opts = opts; T.scratch = scratch[wib]; T.stage = &tstage[wib];
