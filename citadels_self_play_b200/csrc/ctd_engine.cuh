@@ -69,6 +69,13 @@
 #else
 #define CTD_NOT_PRESET() ((void)0)
 #endif
+// CTD_FIXED_CLASSIC (ctd_classic_playout.cu): the classic eight only -- Assassin, Thief, Magician, King, Bishop, Merchant,
+// Architect, Warlord (the characters BASELINE.json's north_star names; game/config.py:83-91, first variant of every rank).
+#ifdef CTD_FIXED_CLASSIC
+#define CTD_NOT_CLASSIC() __builtin_unreachable()
+#else
+#define CTD_NOT_CLASSIC() ((void)0)
+#endif
 #ifndef CTD_PLAYOUT_RING
 /* 1 = the fused playout computes 32 Philox blocks at a time, one per lane (ctd_warp.cuh ctd_ring_refill): 40 fewer warp
  * instructions per env step (7 %) and bit-identical results, but no faster on B200 -- the kernel is bound by instruction
@@ -835,7 +842,7 @@ CTD_HD CTD_NI inline void ctd_character_options(const CtdWork& w, int p, int nm,
       case CTD_THIEF: CTD_NOT_PRESET();  // :246-253
         CTD_LOOP for (int r = 2; r < 8; ++r) e.one(ctd_opt(CTD_K_STEAL, p) | ctd_f_rank(r));
         break;
-      case CTD_SPY:  // :274-281
+      case CTD_SPY: CTD_NOT_CLASSIC();  // :274-281
         CTD_LOOP for (int q = 0; q < 6; ++q)
           if (q != p)
             CTD_LOOP for (int s = 0; s < 5; ++s) e.one(ctd_opt(CTD_K_SPY, p) | ctd_f_target(q) | ctd_f_named(CTD_N_TRADE + s));
@@ -847,22 +854,22 @@ CTD_HD CTD_NI inline void ctd_character_options(const CtdWork& w, int p, int nm,
         CTD_LOOP for (int r = 1; r <= n; ++r) e.range(ctd_opt(CTD_K_DISCARD_AND_DRAW, p) | ctd_f_r(r), ctd_magician_count(n, r));
         break;
       }
-      case CTD_WIZARD:  // :298-308
+      case CTD_WIZARD: CTD_NOT_CLASSIC();  // :298-308
         CTD_LOOP for (int q = 0; q < 6; ++q)
           if (q != p && w.n_hand[q] > 0) e.one(ctd_opt(CTD_K_LOOK_AT_HAND, p) | ctd_f_target(q));
         break;
       case CTD_KING: e.one(ctd_opt(CTD_K_TAKE_CROWN_KING, p)); break;  // :364-366
       case CTD_BISHOP: CTD_NOT_PRESET(); e.one(ctd_opt(CTD_K_BISHOP, p)); break;         // :389-391
-      case CTD_ABBOT: {                                                // :422-430
+      case CTD_ABBOT: CTD_NOT_CLASSIC(); {                                                // :422-430
         int n = ctd_count_suit(w.hand[p], w.n_hand[p], CTD_SUIT_RELIGION);
         if (n > 0)
           CTD_LOOP for (int k = 0; k <= n; ++k) e.one(ctd_opt(CTD_K_ABBOT, p) | ctd_f_count(k) | ctd_f_r(n));
         break;
       }
       case CTD_MERCHANT: CTD_NOT_PRESET(); e.one(ctd_opt(CTD_K_MERCHANT, p)); break;    // :438-440
-      case CTD_ALCHEMIST: break;                                       // :442-444
+      case CTD_ALCHEMIST: CTD_NOT_CLASSIC(); break;                                       // :442-444
       case CTD_ARCHITECT: CTD_NOT_PRESET(); e.one(ctd_opt(CTD_K_ARCHITECT, p)); break;  // :451-452
-      case CTD_NAVIGATOR:                                              // :454-455
+      case CTD_NAVIGATOR: CTD_NOT_CLASSIC();                                              // :454-455
         e.one(ctd_opt(CTD_K_NAVIGATOR, p) | ctd_f_named(CTD_N_4GOLD));
         e.one(ctd_opt(CTD_K_NAVIGATOR, p) | ctd_f_named(CTD_N_4CARD));
         break;
@@ -879,14 +886,14 @@ CTD_HD CTD_NI inline void ctd_character_options(const CtdWork& w, int p, int nm,
           }
         }
         break;
-      case CTD_MAGISTRATE: CTD_NOT_PRESET();  // :221-234  real target x pairs of fake targets among ranks 1..7
+      case CTD_MAGISTRATE: CTD_NOT_PRESET(); CTD_NOT_CLASSIC();  // :221-234  real target x pairs of fake targets among ranks 1..7
         CTD_LOOP for (int real = 1; real < 8; ++real)
           CTD_LOOP for (int a = 1; a < 8; ++a)
             CTD_LOOP for (int b = a + 1; b < 8; ++b)
               if (real != a && real != b)
                 e.one(ctd_opt(CTD_K_MAGISTRATE_WARRANT, p) | ctd_f_rank(real) | ctd_f_named(a) | ctd_f_count(b));
         break;
-      case CTD_BLACKMAILER: CTD_NOT_PRESET();  // :255-272  ordered pairs of un-possessed ranks 2..7
+      case CTD_BLACKMAILER: CTD_NOT_PRESET(); CTD_NOT_CLASSIC();  // :255-272  ordered pairs of un-possessed ranks 2..7
         CTD_LOOP for (int a = 2; a < 8; ++a) {
           if (w.rprops[a] & CTD_RP_POSSESSED) continue;
           CTD_LOOP for (int b = a + 1; b < 8; ++b) {
@@ -896,13 +903,13 @@ CTD_HD CTD_NI inline void ctd_character_options(const CtdWork& w, int p, int nm,
           }
         }
         break;
-      case CTD_SEER: CTD_NOT_PRESET(); e.one(ctd_opt(CTD_K_SEER, p)); break;            // :328-329
-      case CTD_EMPEROR: CTD_NOT_PRESET(); ctd_emperor_options(w, p, false, e); break;   // :368-382
-      case CTD_PATRICIAN: CTD_NOT_PRESET(); e.one(ctd_opt(CTD_K_TAKE_CROWN_PAT, p)); break;  // :384-386
-      case CTD_CARDINAL: CTD_NOT_PRESET(); ctd_cardinal_options(w, p, e); break;        // :393-419
-      case CTD_TRADER: CTD_NOT_PRESET(); e.one(ctd_opt(CTD_K_TRADER, p)); break;        // :446-448
-      case CTD_SCHOLAR: CTD_NOT_PRESET(); if (w.n_deck != 0) e.one(ctd_opt(CTD_K_SCHOLAR, p)); break;  // :457-460
-      case CTD_MARSHAL: CTD_NOT_PRESET();  // :484-492
+      case CTD_SEER: CTD_NOT_PRESET(); CTD_NOT_CLASSIC(); e.one(ctd_opt(CTD_K_SEER, p)); break;            // :328-329
+      case CTD_EMPEROR: CTD_NOT_PRESET(); CTD_NOT_CLASSIC(); ctd_emperor_options(w, p, false, e); break;   // :368-382
+      case CTD_PATRICIAN: CTD_NOT_PRESET(); CTD_NOT_CLASSIC(); e.one(ctd_opt(CTD_K_TAKE_CROWN_PAT, p)); break;  // :384-386
+      case CTD_CARDINAL: CTD_NOT_PRESET(); CTD_NOT_CLASSIC(); ctd_cardinal_options(w, p, e); break;        // :393-419
+      case CTD_TRADER: CTD_NOT_PRESET(); CTD_NOT_CLASSIC(); e.one(ctd_opt(CTD_K_TRADER, p)); break;        // :446-448
+      case CTD_SCHOLAR: CTD_NOT_PRESET(); CTD_NOT_CLASSIC(); if (w.n_deck != 0) e.one(ctd_opt(CTD_K_SCHOLAR, p)); break;  // :457-460
+      case CTD_MARSHAL: CTD_NOT_PRESET(); CTD_NOT_CLASSIC();  // :484-492
         CTD_LOOP for (int q = 0; q < 6; ++q) {
           if (q == p || w.n_bld[q] >= 7 || ctd_name(w, q) == CTD_BISHOP) continue;
           uint64_t seen = 0;
@@ -915,7 +922,7 @@ CTD_HD CTD_NI inline void ctd_character_options(const CtdWork& w, int p, int nm,
           }
         }
         break;
-      case CTD_DIPLOMAT: CTD_NOT_PRESET();  // :494-504
+      case CTD_DIPLOMAT: CTD_NOT_PRESET(); CTD_NOT_CLASSIC();  // :494-504
         CTD_LOOP for (int q = 0; q < 6; ++q) {
           if (q == p || w.n_bld[q] >= 7 || ctd_name(w, q) == CTD_BISHOP) continue;
           CTD_LOOP for (int i = 0; i < w.n_bld[q]; ++i) {
@@ -1352,12 +1359,12 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       ctd_to5(w, p);
       w.done |= CTD_DM_CHARACTER;
       break;
-    case CTD_K_BEWITCHING:  // carry_out_bewitching (:259-262)
+    case CTD_K_BEWITCHING: CTD_NOT_CLASSIC();  // carry_out_bewitching (:259-262)
       w.rprops[CTD_OPT_RANK(d)] |= CTD_RP_POSSESSED;
       w.pflags[p] |= CTD_PF_WITCH;
       ctd_setup_next_player(w, p);
       break;
-    case CTD_K_SPY: {  // carry_out_spying (:278-288)
+    case CTD_K_SPY: CTD_NOT_CLASSIC(); {  // carry_out_spying (:278-288)
       int q = CTD_OPT_TARGET(d), s = CTD_OPT_NAMED(d) - CTD_N_TRADE;
       int n = ctd_count_suit(w.hand[q], w.n_hand[q], s);
       int steal = n < w.gold[q] ? n : w.gold[q];
@@ -1391,7 +1398,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       w.done |= CTD_DM_CHARACTER;
       break;
     }
-    case CTD_K_LOOK_AT_HAND:  // carry_out_wizard_hand_looking (:305-310)
+    case CTD_K_LOOK_AT_HAND: CTD_NOT_CLASSIC();  // carry_out_wizard_hand_looking (:305-310)
       if (KN) CTD_LOOP for (int i = 0; i < ks.n; ++i) {
         CtdKnow& k = ks.k[i];
         int q = CTD_OPT_TARGET(d), n = w.n_hand[q];
@@ -1407,7 +1414,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       w.next_player = (uint8_t)p;
       w.next_mode = CTD_NEXT_ALIAS;
       break;
-    case CTD_K_TAKE_FROM_HAND: {  // carry_out_wizard_take_from_hand (:312-328)
+    case CTD_K_TAKE_FROM_HAND: CTD_NOT_CLASSIC(); {  // carry_out_wizard_take_from_hand (:312-328)
       int q = CTD_OPT_TARGET(d), t = CTD_OPT_CARD_A(d);
       ctd_append(w, w.hand[p], w.n_hand[p], CTD_HAND_CAP, ctd_take_like(w.hand[q], w.n_hand[q], t));
       if (CTD_OPT_BUILD(d)) ctd_apply_build(w, p, t, ctd_count_type(w.bld[p], w.n_bld[p], t));
@@ -1443,7 +1450,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       ctd_to5(w, p);
       w.done |= CTD_DM_CHARACTER;
       break;
-    case CTD_K_ABBOT: {  // carry_out_abbot (:405-412)
+    case CTD_K_ABBOT: CTD_NOT_CLASSIC(); {  // carry_out_abbot (:405-412)
       int n = CTD_OPT_R(d), kc = CTD_OPT_COUNT(d);  // the option carries its own gold/card list
       w.gold[p] += (int8_t)(n - kc);
       CTD_LOOP for (int i = 0; i < kc; ++i) ctd_draw_to_hand(w, p);
@@ -1451,7 +1458,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       w.done |= CTD_DM_CHARACTER;
       break;
     }
-    case CTD_K_ABBOT_BEG: {  // carry_out_abbot_beg (:414-420): first richest seat pays, may be the abbot
+    case CTD_K_ABBOT_BEG: CTD_NOT_CLASSIC(); {  // carry_out_abbot_beg (:414-420): first richest seat pays, may be the abbot
       int rich = 0;
       CTD_LOOP for (int q = 1; q < 6; ++q) if (w.gold[q] > w.gold[rich]) rich = q;
       w.gold[rich] -= 1;
@@ -1468,7 +1475,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       ctd_to5(w, p);
       w.done |= CTD_DM_CHARACTER;
       break;
-    case CTD_K_NAVIGATOR:  // carry_out_navigator (:473-483)
+    case CTD_K_NAVIGATOR: CTD_NOT_CLASSIC();  // carry_out_navigator (:473-483)
       if (CTD_OPT_NAMED(d) == CTD_N_4CARD) CTD_LOOP for (int i = 0; i < 4; ++i) ctd_draw_to_hand(w, p);
       else w.gold[p] += 4;
       ctd_to5(w, p);
@@ -1501,14 +1508,14 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       break;
     }
     // ---- deluxe characters (tier C) ----
-    case CTD_K_MAGISTRATE_WARRANT: CTD_NOT_PRESET();  // carry_out_warranting (:251-257)
+    case CTD_K_MAGISTRATE_WARRANT: CTD_NOT_PRESET(); CTD_NOT_CLASSIC();  // carry_out_warranting (:251-257)
       w.rprops[CTD_OPT_RANK(d)] = (uint8_t)((w.rprops[CTD_OPT_RANK(d)] & ~CTD_RP_WARRANT) | (1 << 1));
       w.rprops[CTD_OPT_NAMED(d)] = (uint8_t)((w.rprops[CTD_OPT_NAMED(d)] & ~CTD_RP_WARRANT) | (2 << 1));
       w.rprops[CTD_OPT_COUNT(d)] = (uint8_t)((w.rprops[CTD_OPT_COUNT(d)] & ~CTD_RP_WARRANT) | (2 << 1));
       ctd_to5(w, p);
       w.done |= CTD_DM_CHARACTER;
       break;
-    case CTD_K_REVEAL_WARRANT: CTD_NOT_PRESET(); {  // carry_out_magistrate_reaveal (:94-100)
+    case CTD_K_REVEAL_WARRANT: CTD_NOT_PRESET(); CTD_NOT_CLASSIC(); {  // carry_out_magistrate_reaveal (:94-100)
       const int q = CTD_OPT_TARGET(d), rq = w.role[q];
       if (rq >= 8) { w.err |= CTD_ERR_REF_RAISE; break; }
       if (CTD_OPT_NAMED(d) == CTD_N_REVEAL && ((w.rprops[rq] & CTD_RP_WARRANT) >> 1) == 1) {
@@ -1520,13 +1527,13 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       ctd_restore_next(w);
       break;
     }
-    case CTD_K_BLACKMAIL: CTD_NOT_PRESET();  // carry_out_blackmail (:271-276)
+    case CTD_K_BLACKMAIL: CTD_NOT_PRESET(); CTD_NOT_CLASSIC();  // carry_out_blackmail (:271-276)
       w.rprops[CTD_OPT_RANK(d)] = (uint8_t)((w.rprops[CTD_OPT_RANK(d)] & ~CTD_RP_BLACKMAIL) | (1 << 5));
       w.rprops[CTD_OPT_NAMED(d)] = (uint8_t)((w.rprops[CTD_OPT_NAMED(d)] & ~CTD_RP_BLACKMAIL) | (2 << 5));
       ctd_to5(w, p);
       w.done |= CTD_DM_CHARACTER;
       break;
-    case CTD_K_BLACKMAIL_RESPONSE: CTD_NOT_PRESET(); {  // carry_out_respond_to_blackmail (:71-82); int(gold/2) truncates toward zero
+    case CTD_K_BLACKMAIL_RESPONSE: CTD_NOT_PRESET(); CTD_NOT_CLASSIC(); {  // carry_out_respond_to_blackmail (:71-82); int(gold/2) truncates toward zero
       const int bm = ctd_player_from_rank(w, 1);
       if (bm < 0) { w.err |= CTD_ERR_REF_RAISE; break; }
       if (CTD_OPT_NAMED(d) == CTD_N_PAY) {
@@ -1542,7 +1549,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       }
       break;
     }
-    case CTD_K_REVEAL_BLACKMAIL: CTD_NOT_PRESET(); {  // carry_out_responding_to_blackmail_response (:85-92)
+    case CTD_K_REVEAL_BLACKMAIL: CTD_NOT_PRESET(); CTD_NOT_CLASSIC(); {  // carry_out_responding_to_blackmail_response (:85-92)
       const int q = CTD_OPT_TARGET(d), rq = w.role[q];
       if (rq >= 8) { w.err |= CTD_ERR_REF_RAISE; break; }
       if (CTD_OPT_NAMED(d) == CTD_N_REVEAL && ((w.rprops[rq] & CTD_RP_BLACKMAIL) >> 5) == 1) {
@@ -1553,7 +1560,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       ctd_restore_next(w);
       break;
     }
-    case CTD_K_SEER: CTD_NOT_PRESET(); {  // carry_out_seer_take_a_card (:330-341): shuffle each hand, take its first card
+    case CTD_K_SEER: CTD_NOT_PRESET(); CTD_NOT_CLASSIC(); {  // carry_out_seer_take_a_card (:330-341): shuffle each hand, take its first card
       w.seer_mask = 0;
       CTD_LOOP for (int q = 0; q < 6; ++q) {
         if (q == p || w.n_hand[q] == 0) continue;
@@ -1570,7 +1577,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       w.next_mode = CTD_NEXT_ALIAS;
       break;
     }
-    case CTD_K_GIVE_BACK_CARD: CTD_NOT_PRESET(); {  // carry_out_seer_give_back_cards (:343-350)
+    case CTD_K_GIVE_BACK_CARD: CTD_NOT_PRESET(); CTD_NOT_CLASSIC(); {  // carry_out_seer_give_back_cards (:343-350)
       const int shift[5] = {12, 18, 39, 45, 51};
       int idx = 0;
       CTD_LOOP for (int q = 0; q < 6 && idx < 5; ++q) {
@@ -1586,7 +1593,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       ctd_restore_next(w);
       break;
     }
-    case CTD_K_GIVE_CROWN: CTD_NOT_PRESET(); {  // carry_out_emperor (:377-393)
+    case CTD_K_GIVE_CROWN: CTD_NOT_PRESET(); CTD_NOT_CLASSIC(); {  // carry_out_emperor (:377-393)
       const int q = CTD_OPT_TARGET(d);
       w.gold[p] += (int8_t)ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_LORD);
       if (CTD_OPT_NAMED(d) == CTD_N_CARD) {
@@ -1604,7 +1611,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       w.done |= CTD_DM_CHARACTER;
       break;
     }
-    case CTD_K_TAKE_CROWN_PAT: CTD_NOT_PRESET(); {  // carry_out_take_crown_patrician (:365-375)
+    case CTD_K_TAKE_CROWN_PAT: CTD_NOT_PRESET(); CTD_NOT_CLASSIC(); {  // carry_out_take_crown_patrician (:365-375)
       const int n = ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_LORD);
       CTD_LOOP for (int i = 0; i < n; ++i) ctd_draw_to_hand(w, p);
       if (!(w.pflags[p] & CTD_PF_WITCH)) ctd_move_crown(w, p);
@@ -1612,7 +1619,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       w.done |= CTD_DM_CHARACTER;
       break;
     }
-    case CTD_K_CARDINAL: CTD_NOT_PRESET(); {  // carry_out_cardinal (:422-439): no build bookkeeping, no warrant check, gold clamped at 0
+    case CTD_K_CARDINAL: CTD_NOT_PRESET(); CTD_NOT_CLASSIC(); {  // carry_out_cardinal (:422-439): no build bookkeeping, no warrant check, gold clamped at 0
       const int q = CTD_OPT_TARGET(d), t = CTD_OPT_CARD_A(d), kc = CTD_OPT_COUNT(d);
       const int c = ctd_take_like(w.hand[p], w.n_hand[p], t);
       ctd_append(w, w.bld[p], w.n_bld[p], CTD_BLD_CAP, c);
@@ -1649,12 +1656,12 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       w.done |= CTD_DM_CHARACTER;
       break;
     }
-    case CTD_K_TRADER: CTD_NOT_PRESET();  // carry_out_trader (:455-461)
+    case CTD_K_TRADER: CTD_NOT_PRESET(); CTD_NOT_CLASSIC();  // carry_out_trader (:455-461)
       w.gold[p] += (int8_t)ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_TRADE);
       ctd_to5(w, p);
       w.done |= CTD_DM_CHARACTER;
       break;
-    case CTD_K_SCHOLAR: CTD_NOT_PRESET(); {  // carry_out_scholar_draw (:485-496)
+    case CTD_K_SCHOLAR: CTD_NOT_PRESET(); CTD_NOT_CLASSIC(); {  // carry_out_scholar_draw (:485-496)
       w.n_seven = 0;
       const int n = w.n_deck < 7 ? w.n_deck : 7;
       CTD_LOOP for (int i = 0; i < n; ++i) {
@@ -1670,14 +1677,14 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       w.next_mode = CTD_NEXT_ALIAS;
       break;
     }
-    case CTD_K_SCHOLAR_PICK: CTD_NOT_PRESET();  // carry_out_scholar_put_back (:498-502): returns what the shrunk shared list still holds
+    case CTD_K_SCHOLAR_PICK: CTD_NOT_PRESET(); CTD_NOT_CLASSIC();  // carry_out_scholar_put_back (:498-502): returns what the shrunk shared list still holds
       CTD_LOOP for (int i = 0; i < w.n_seven; ++i) ctd_deck_push(w, ctd_take_like(w.hand[p], w.n_hand[p], ctd_ctype(w.seven[i])));
       ctd_restore_next(w);
       w.n_seven = 0;
       CTD_LOOP for (int i = 0; i < 7; ++i) w.seven[i] = 0;
       break;
-    case CTD_K_MARSHAL: CTD_NOT_PRESET();
-    case CTD_K_DIPLOMAT: CTD_NOT_PRESET(); {  // carry_out_marshal (:505-515) / carry_out_diplomat (:538-551)
+    case CTD_K_MARSHAL: CTD_NOT_PRESET(); CTD_NOT_CLASSIC();
+    case CTD_K_DIPLOMAT: CTD_NOT_PRESET(); CTD_NOT_CLASSIC(); {  // carry_out_marshal (:505-515) / carry_out_diplomat (:538-551)
       const int q = CTD_OPT_TARGET(d), t = CTD_OPT_CARD_A(d);
       const int money = k == CTD_K_MARSHAL ? ctd_cost_of_type(t)
                                            : (ctd_cost_of_type(t) > ctd_cost_of_type(CTD_OPT_CARD_B(d))

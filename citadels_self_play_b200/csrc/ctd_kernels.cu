@@ -160,6 +160,8 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_choose_check(const ctd_state*
 // the same kernel specialised for the preset eight, compiled in ctd_preset_playout.cu
 cudaError_t ctd_playout_generic_launch(const CtdPlayoutArgs& a, int grid, cudaStream_t stream);
 cudaError_t ctd_playout_generic_blocks_per_sm(int* per_sm);
+cudaError_t ctd_playout_classic_launch(const CtdPlayoutArgs& a, int grid, cudaStream_t stream);
+cudaError_t ctd_playout_classic_blocks_per_sm(int* per_sm);
 cudaError_t ctd_playout_preset_launch(const CtdPlayoutArgs& a, int grid, cudaStream_t stream);
 cudaError_t ctd_playout_preset_blocks_per_sm(int* per_sm);
 
@@ -840,9 +842,10 @@ ctd_status ctd_step(ctd_engine* e, uint32_t n, const ctd_option* chosen, int8_t*
 }
 
 // persistent grid: enough CTAs to fill every SM at the kernel's occupancy
-static ctd_status ctd_playout_grid(ctd_engine* e, uint64_t n_games, int* grid, bool preset) {
+static ctd_status ctd_playout_grid(ctd_engine* e, uint64_t n_games, int* grid, bool preset, bool classic) {
   int per_sm = 0;
   if (preset) CTD_CUDA(e, ctd_playout_preset_blocks_per_sm(&per_sm));
+  else if (classic) CTD_CUDA(e, ctd_playout_classic_blocks_per_sm(&per_sm));
   else CTD_CUDA(e, ctd_playout_generic_blocks_per_sm(&per_sm));
   if (per_sm < 1) per_sm = 1;
   uint64_t want = (uint64_t)e->sm_count * per_sm;
@@ -855,8 +858,9 @@ static ctd_status ctd_playout_grid(ctd_engine* e, uint64_t n_games, int* grid, b
 static ctd_status ctd_playout_launch(ctd_engine* e, CtdPlayoutArgs& a, ctd_playout_stats* stats, float* elapsed_ms) {
   // every game of this launch is known to play the preset eight: the specialised kernel (ctd_preset_playout.cu)
   const bool preset = a.slots == nullptr ? a.ruleset == CTD_RULESET_PRESET : a.n_games <= e->slots_preset_n;
+  const bool classic = a.slots == nullptr && a.ruleset == CTD_RULESET_CLASSIC;   // fresh deals of the classic eight
   int grid = 1;
-  ctd_status s = ctd_playout_grid(e, a.n_games, &grid, preset);
+  ctd_status s = ctd_playout_grid(e, a.n_games, &grid, preset, classic);
   if (s != CTD_OK) return s;
   CTD_CUDA(e, cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream));
   CTD_CUDA(e, cudaMemsetAsync(e->d_stats, 0, sizeof(ctd_playout_stats), e->stream));
@@ -865,6 +869,8 @@ static ctd_status ctd_playout_launch(ctd_engine* e, CtdPlayoutArgs& a, ctd_playo
   CTD_CUDA(e, cudaEventRecord(e->ev0, e->stream));
   if (preset) {
     CTD_CUDA(e, ctd_playout_preset_launch(a, grid, e->stream));
+  } else if (classic) {
+    CTD_CUDA(e, ctd_playout_classic_launch(a, grid, e->stream));
   } else {
     CTD_CUDA(e, ctd_playout_generic_launch(a, grid, e->stream));
   }

@@ -263,7 +263,7 @@ static __device__ CTD_CHOOSE_ATTR uint64_t ctd_warp_choose(CtdWork& w, int lane,
     switch (nm) {
       case CTD_ASSASSIN: CTD_NOT_PRESET(); return CTD_K_ASSASSINATION | me | ctd_f_rank(1 + (int)k);
       case CTD_THIEF: CTD_NOT_PRESET(); return CTD_K_STEAL | me | ctd_f_rank(2 + (int)k);
-      case CTD_SPY: return CTD_K_SPY | me | ctd_f_target(q) | ctd_f_named(CTD_N_TRADE + (int)k % 5);
+      case CTD_SPY: CTD_NOT_CLASSIC(); return CTD_K_SPY | me | ctd_f_target(q) | ctd_f_named(CTD_N_TRADE + (int)k % 5);
       case CTD_MAGICIAN: CTD_NOT_PRESET(); {
         if (k < 5) return CTD_K_MAGIC_HAND_CHANGE | me | ctd_f_target(q1);
         k -= 5;  // every discard_and_draw option has the same effect; recover (r, j) for the descriptor
@@ -275,13 +275,13 @@ static __device__ CTD_CHOOSE_ATTR uint64_t ctd_warp_choose(CtdWork& w, int lane,
         }
         return CTD_K_DISCARD_AND_DRAW | me | ctd_f_r(r) | ctd_f_j(k);
       }
-      case CTD_WIZARD: return CTD_K_LOOK_AT_HAND | me | ctd_f_target(ctd_kth_bit(m1, k, lane));
+      case CTD_WIZARD: CTD_NOT_CLASSIC(); return CTD_K_LOOK_AT_HAND | me | ctd_f_target(ctd_kth_bit(m1, k, lane));
       case CTD_KING: return CTD_K_TAKE_CROWN_KING | me;
       case CTD_BISHOP: CTD_NOT_PRESET(); return CTD_K_BISHOP | me;
       case CTD_MERCHANT: CTD_NOT_PRESET(); return CTD_K_MERCHANT | me;
       case CTD_ARCHITECT: CTD_NOT_PRESET(); return CTD_K_ARCHITECT | me;
-      case CTD_ABBOT: return CTD_K_ABBOT | me | ctd_f_count((int)k) | ctd_f_r((int)__popc(m1));
-      case CTD_NAVIGATOR: return CTD_K_NAVIGATOR | me | ctd_f_named(k == 0 ? CTD_N_4GOLD : CTD_N_4CARD);
+      case CTD_ABBOT: CTD_NOT_CLASSIC(); return CTD_K_ABBOT | me | ctd_f_count((int)k) | ctd_f_r((int)__popc(m1));
+      case CTD_NAVIGATOR: CTD_NOT_CLASSIC(); return CTD_K_NAVIGATOR | me | ctd_f_named(k == 0 ? CTD_N_4GOLD : CTD_N_4CARD);
       default: {  // CTD_WARLORD: (seat, slot) lanes, seats 0..2 then 3..5
         const uint32_t c1 = __popc(m1);
         const uint32_t mm = k < c1 ? m1 : m2;
