@@ -94,23 +94,23 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------- CPU arm
 def _cpu_worker(args):
-    seed, gid0, n = args
+    seed, gid0, n, ruleset = args
     from oracle import citadels_oracle as O
     steps = 0
     t0 = time.perf_counter()
     for i in range(n):
-        steps += O.playout(seed, gid0 + i)[2]
+        steps += O.playout(seed, gid0 + i, ruleset)[2]
     return steps, time.perf_counter() - t0
 
 
-def cpu_playouts(games_per_core, cores, gid0=0):
+def cpu_playouts(games_per_core, cores, gid0=0, ruleset=0):
     """The reference's random-playout loop (run_utils.py:37-41) as restated in oracle/ (a Python port of a
     Python reference), on `cores` processes.  Returns (env_steps, wall_seconds)."""
     import multiprocessing as mp
     ctx = mp.get_context("fork")
     t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(SEED, gid0 + c * games_per_core, games_per_core) for c in range(cores)])
+        res = pool.map(_cpu_worker, [(SEED, gid0 + c * games_per_core, games_per_core, ruleset) for c in range(cores)])
     wall = time.perf_counter() - t0
     return sum(r[0] for r in res), wall
 
@@ -147,19 +147,19 @@ def run_reference_arm(args, rank, world, emit):
     cores = os.cpu_count() or 1
     per_core = max(1, args.ref_games_per_core)
     for _ in range(args.warmup):
-        cpu_playouts(1, cores)
+        cpu_playouts(1, cores, ruleset=args.ruleset)
     tot_steps, tot_wall = 0, 0.0
     for k in range(args.steps):
-        s, w = cpu_playouts(per_core, cores, gid0=1000 + k * cores * per_core)
+        s, w = cpu_playouts(per_core, cores, gid0=1000 + k * cores * per_core, ruleset=args.ruleset)
         tot_steps += s
         tot_wall += w
     v = tot_steps / tot_wall
-    sample = "%d games per step (%d per core x %d cores) of the preset random playout, oracle port" % (
-        per_core * cores, per_core, cores)
+    sample = "%d games per step (%d per core x %d cores) of the %s random playout, oracle port" % (
+        per_core * cores, per_core, cores, ["preset", "classic", "random-ruleset"][args.ruleset])
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "env steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_wall / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "preset 6p random playouts to terminal (BASELINE configs[1]), bounded CPU sample",
+            "config": {"workload": "%s 6p random playouts to terminal (BASELINE configs[1]), bounded CPU sample" % ["preset", "classic", "random-ruleset"][args.ruleset],
                        "sample": sample},
             "cpu_baseline": {"value": v, "unit": "env steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "env steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -343,8 +343,8 @@ def main():
             "metric": METRIC, "value": value, "unit": "env steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "%d preset 6-player games per GPU per step, dealt on device from Philox(seed, gid), "
-                                   "uniform-random option to terminal (BASELINE configs[1])" % G,
+            "config": {"workload": "%d %s 6-player games per GPU per step, dealt on device from Philox(seed, gid), "
+                                   "uniform-random option to terminal (BASELINE configs[1])" % (G, ["preset", "classic", "random-ruleset"][args.ruleset]),
                        "ruleset": ["preset", "classic", "random"][args.ruleset], "games_per_gpu_per_step": G,
                        "l2": "no HBM-resident inputs (games are generated on device); 256 MiB flush between iterations",
                        "parallelism": "games sharded by global id, %d rank(s), no step-path collective" % world},
@@ -379,10 +379,10 @@ def main():
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             per_core = 300   # ~5 s of work per core: pool start-up and imports amortised
-            cs, cw = cpu_playouts(per_core, cores)
+            cs, cw = cpu_playouts(per_core, cores, ruleset=args.ruleset)
             line["cpu_baseline"] = {"value": cs / cw, "unit": "env steps/s", "cores": cores, "kind": "port",
-                                    "sample": "%d preset games (%d per core), oracle port of run_utils.py:37-41"
-                                              % (per_core * cores, per_core)}
+                                    "sample": "%d %s games (%d per core), oracle port of run_utils.py:37-41"
+                                              % (per_core * cores, ["preset", "classic", "random-ruleset"][args.ruleset], per_core)}
         emit(line)
     eng.close()
     if world > 1:
