@@ -186,3 +186,33 @@ def test_full_size_properties_one_million_games():
     assert list(np.bincount(out["winner"], minlength=6)) == list(out["stats"]["wins"])
     assert [int(x) for x in out["points"].astype(np.int64).sum(0)] == list(out["stats"]["points_sum"])
     e.close()
+
+
+def _oracle_outcomes(args):
+    seed, gid0, n, ruleset = args
+    from oracle import citadels_oracle as O
+    return [O.playout(seed, gid0 + i, ruleset)[:3] for i in range(n)]
+
+
+@pytest.mark.parametrize("ruleset,n", [(0, 4096), (1, 2048), (2, 1024)])
+def test_fused_playout_vs_oracle_thousands_of_games(engine, ruleset, n):
+    """The three playout kernels (preset-specialised, classic-specialised, generic) against the oracle on thousands of fresh
+    games each, bit-exact winner / six scores / step count (the oracle runs on the host cores in a process pool)."""
+    import multiprocessing as mp
+    import os
+    seed, gid0 = 0xABCDEF12 + ruleset, 3_000_000
+    out = engine.playout(n, seed=seed, first_gid=gid0, ruleset=ruleset)
+    cores = min(16, os.cpu_count() or 1)
+    per = (n + cores - 1) // cores
+    jobs = [(seed, gid0 + c * per, min(per, n - c * per), ruleset) for c in range(cores) if c * per < n]
+    with mp.get_context("spawn").Pool(len(jobs)) as pool:     # not fork: this process holds a CUDA context
+        res = [r for chunk in pool.map(_oracle_outcomes, jobs) for r in chunk]
+    assert len(res) == n
+    ow = np.array([r[0] for r in res], dtype=np.int8)
+    op = np.array([r[1] for r in res], dtype=np.int8)
+    os_ = np.array([r[2] for r in res], dtype=np.int64)
+    capped = os_ >= 4096                        # never-ending games of the random rulesets: both sides stop at the cap
+    assert np.array_equal(out["steps"].astype(np.int64)[~capped], os_[~capped])
+    assert np.array_equal(out["winner"][~capped], ow[~capped])
+    assert np.array_equal(out["points"][~capped], op[~capped])
+    assert capped.sum() <= 1 and out["stats"]["errors"] == int(capped.sum())
