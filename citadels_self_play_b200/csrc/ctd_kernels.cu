@@ -1002,8 +1002,9 @@ ctd_status ctd_store_roots(ctd_engine* e, uint32_t n, ctd_state* roots, void* kn
 
 void ctd_mccfr_tree_shape(uint32_t iterations, int ruleset, uint32_t* max_nodes, uint32_t* child_cap, uint32_t* arr_cap,
                           uint64_t* bytes) {
-  // measured on the reference: <= 3.6 nodes per iteration (preset); a classic Magician expands ~1600 options at once
-  uint32_t extra = ruleset == CTD_RULESET_CLASSIC ? 8192 : 0;
+  // measured on the reference: <= 3.6 nodes per iteration (preset); a classic Magician expands ~1600 options at once, the
+  // Cardinal of the random rulesets up to CTD_MCCFR_OPT_CAP (4096) and more than once per tree
+  uint32_t extra = ruleset == CTD_RULESET_CLASSIC ? 8192 : (ruleset == CTD_RULESET_RANDOM ? 16384 : 0);
   uint32_t mn = 8 * iterations + 512 + extra, cc = mn + 10 * (iterations + 2), ac = 3 * cc + 180 * 64;
   if (max_nodes) *max_nodes = mn;
   if (child_cap) *child_cap = cc;

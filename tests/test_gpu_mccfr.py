@@ -73,6 +73,46 @@ def test_mccfr_fresh_roots_vs_oracle(engine):
         assert int(res["rng_draws"]) == node.game.chance.i
 
 
+def _oracle_root_summary(args):
+    """(root R, C, V, number of nodes, draws) of one oracle tree -- runs in a worker process."""
+    root, know, used, seed, gid, iters = args
+    from oracle import mccfr_oracle as M
+    node = M.run_from_root(root, know, used, seed, gid, iters)
+    return (np.asarray(node.R, dtype=float).ravel(), np.asarray(node.C, dtype=float).ravel(), np.asarray(node.V, dtype=float),
+            sum(1 for _ in node.walk()), node.game.chance.i)
+
+
+@pytest.mark.parametrize("ruleset,n", [(0, 192), (1, 64), (2, 64)])
+def test_mccfr_hundreds_of_fresh_roots_vs_oracle(engine, ruleset, n):
+    """The search kernels (preset-specialised and generic) on hundreds of fresh roots: tree size, number of chance draws
+    and the root's regrets / cumulative strategy / values against the oracle (process pool on the host cores)."""
+    import multiprocessing as mp
+    import os
+    seed, gid0, iters = 31415 + ruleset, 120_000, 200
+    engine.make_roots(n, seed=seed, first_gid=gid0, ruleset=ruleset, back_lo=0, back_hi=40)
+    roots, knows, used, gids = engine.store_roots(n)
+    res = engine.mccfr(n, iterations=iters, seed=seed, ruleset=ruleset)["results"]
+    live = [i for i in range(n) if not (roots[i, 217] & 2)]
+    assert all(res[i]["status"] == 1 for i in range(n) if i not in live)
+    jobs = [(roots[i], knows[i], used[i], seed, int(gids[i]), iters) for i in live]
+    with mp.get_context("spawn").Pool(min(16, os.cpu_count() or 1)) as pool:      # not fork: this process holds a CUDA context
+        want = pool.map(_oracle_root_summary, jobs, chunksize=2)
+    flagged = 0
+    for i, (R, C, V, nodes, draws) in zip(live, want):
+        r = res[i]
+        if ruleset == 2 and r["status"] == 4:
+            # a hypothetical game of this tree outgrew a container (a city of more than 32 districts: the Cardinal builds
+            # without limit and CFR's determinisation does not conserve cards): reported per tree, never silently wrong
+            flagged += 1
+            continue
+        assert r["status"] == 0 and int(r["n_nodes"]) == nodes and int(r["rng_draws"]) == draws, (ruleset, i)
+        k = min(len(R), 60 if r["role_pick"] else 128)
+        assert np.allclose(r["cumulative_regrets"][:k], R[:k], rtol=1e-9, atol=1e-12), (ruleset, i)
+        assert np.allclose(r["cumulative_strategy"][:k], C[:k], rtol=1e-9, atol=1e-12), (ruleset, i)
+        assert np.allclose(r["node_value"], V, rtol=1e-9, atol=1e-12), (ruleset, i)
+    assert flagged <= 2
+
+
 # ---------------------------------------------------------------- deep MCCFR (config 4)
 def _model(seed=0, randomize_bn=False):
     import torch
