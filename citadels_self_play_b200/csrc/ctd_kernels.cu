@@ -542,7 +542,8 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_encode(const ctd_state* slots
 // ------------------------------------------------------------------------------------------ host side / C ABI
 struct ctd_engine {
   int device;
-  uint32_t slots_preset_n;  // slots [0, slots_preset_n) are known to hold preset-ruleset games (ctd_reset / ctd_load_states)
+  uint32_t slots_rs_n;      // slots [0, slots_rs_n) are known to hold games of ruleset slots_rs (ctd_reset / ctd_load_states):
+  int slots_rs;             // lets ctd_playout_slots pick a specialised kernel
   uint32_t capacity;
   ctd_state* d_slots;
   cudaStream_t stream;
@@ -715,7 +716,7 @@ ctd_status ctd_reset(ctd_engine* e, uint32_t n, uint64_t seed, uint64_t first_gi
   if (n == 0) return CTD_OK;
   CTD_CUDA(e, cudaSetDevice(e->device));
   e->seed = seed;
-  e->slots_preset_n = ruleset == CTD_RULESET_PRESET ? n : 0;
+  e->slots_rs = ruleset; e->slots_rs_n = n;
   ctd_k_reset<<<ctd_blocks(n), CTD_BLOCK, 0, e->stream>>>(e->d_slots, n, seed, first_gid, ruleset, ctd_tapes(e));
   e->launches++;
   CTD_CUDA(e, cudaGetLastError());
@@ -725,13 +726,16 @@ ctd_status ctd_reset(ctd_engine* e, uint32_t n, uint64_t seed, uint64_t first_gi
 ctd_status ctd_load_states(ctd_engine* e, uint32_t first_slot, uint32_t n, const ctd_state* states) {
   if (!e || !states || (uint64_t)first_slot + n > e->capacity) return CTD_EARG;
   CTD_CUDA(e, cudaSetDevice(e->device));
-  {  // keep track of the leading run of slots known to hold preset-ruleset games (picks the specialised playout kernel)
-    bool all_preset = true;
-    for (uint32_t i = 0; i < n && all_preset; ++i) all_preset = states[i].ruleset == CTD_RULESET_PRESET;
-    if (all_preset && first_slot <= e->slots_preset_n) {
-      if (first_slot + n > e->slots_preset_n) e->slots_preset_n = first_slot + n;
-    } else if (!all_preset && first_slot < e->slots_preset_n) {
-      e->slots_preset_n = first_slot;
+  if (n != 0) {  // keep track of the leading run of slots known to hold games of one ruleset (picks a specialised playout kernel)
+    const int rs = states[0].ruleset;
+    bool uniform = true;
+    for (uint32_t i = 1; i < n && uniform; ++i) uniform = states[i].ruleset == rs;
+    if (uniform && first_slot == 0 && n >= e->slots_rs_n) {
+      e->slots_rs = rs; e->slots_rs_n = n;                         // the run is replaced
+    } else if (uniform && rs == e->slots_rs && first_slot <= e->slots_rs_n) {
+      if (first_slot + n > e->slots_rs_n) e->slots_rs_n = first_slot + n;   // the run is extended
+    } else if (first_slot < e->slots_rs_n) {
+      e->slots_rs_n = first_slot;                                  // the run is cut where foreign records begin
     }
   }
   CTD_CUDA(e, cudaMemcpyAsync(e->d_slots + first_slot, states, (size_t)n * sizeof(ctd_state), cudaMemcpyHostToDevice,
@@ -751,7 +755,7 @@ ctd_status ctd_store_states(ctd_engine* e, uint32_t first_slot, uint32_t n, ctd_
 
 ctd_status ctd_states_dev(ctd_engine* e, void** dev_ptr) {
   if (!e || !dev_ptr) return CTD_EARG;
-  e->slots_preset_n = 0;   // the caller may write the slots behind the engine's back
+  e->slots_rs_n = 0;   // the caller may write the slots behind the engine's back
   *dev_ptr = e->d_slots;
   return CTD_OK;
 }
@@ -857,8 +861,8 @@ static ctd_status ctd_playout_grid(ctd_engine* e, uint64_t n_games, int* grid, b
 
 static ctd_status ctd_playout_launch(ctd_engine* e, CtdPlayoutArgs& a, ctd_playout_stats* stats, float* elapsed_ms) {
   // every game of this launch is known to play the preset eight: the specialised kernel (ctd_preset_playout.cu)
-  const bool preset = a.slots == nullptr ? a.ruleset == CTD_RULESET_PRESET : a.n_games <= e->slots_preset_n;
-  const bool classic = a.slots == nullptr && a.ruleset == CTD_RULESET_CLASSIC;   // fresh deals of the classic eight
+  const int rs = a.slots == nullptr ? a.ruleset : (a.n_games <= e->slots_rs_n ? e->slots_rs : -1);
+  const bool preset = rs == CTD_RULESET_PRESET, classic = rs == CTD_RULESET_CLASSIC;
   int grid = 1;
   ctd_status s = ctd_playout_grid(e, a.n_games, &grid, preset, classic);
   if (s != CTD_OK) return s;
@@ -961,7 +965,7 @@ ctd_status ctd_make_roots(ctd_engine* e, uint32_t n, uint64_t seed, uint64_t fir
   CTD_CUDA(e, cudaSetDevice(e->device));
   ctd_status s = ctd_root_buffers(e);
   if (s != CTD_OK) return s;
-  e->slots_preset_n = 0;
+  e->slots_rs_n = 0;
   e->seed = seed;
   CtdRootArgs a{n, seed, first_gid, ruleset, back_lo, back_hi, e->d_slots, e->d_knows, e->d_used_cards, e->d_gids,
                 e->d_root_step};
@@ -977,7 +981,7 @@ ctd_status ctd_make_roots(ctd_engine* e, uint32_t n, uint64_t seed, uint64_t fir
 ctd_status ctd_load_roots(ctd_engine* e, uint32_t n, const ctd_state* roots, const void* knows, const uint8_t* used_cards,
                           const uint64_t* gids) {
   if (!e || n > e->capacity || !roots || !knows || !used_cards || !gids) return CTD_EARG;
-  e->slots_preset_n = 0;
+  e->slots_rs_n = 0;
   CTD_CUDA(e, cudaSetDevice(e->device));
   ctd_status s = ctd_root_buffers(e);
   if (s != CTD_OK) return s;
