@@ -341,7 +341,9 @@ def main():
         achieved = per_gpu_kernel * BYTES_PER_STEP / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "env steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
+            "device_ms_per_step": kernel_ms / max(args.steps, 1),   # CUDA events on the engine's stream around the kernel, max over ranks
+            "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": "%d %s 6-player games per GPU per step, dealt on device from Philox(seed, gid), "
                                    "uniform-random option to terminal (BASELINE configs[1])" % (G, ["preset", "classic", "random-ruleset"][args.ruleset]),
