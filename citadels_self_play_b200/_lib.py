@@ -39,23 +39,25 @@ SIGNATURES = {
     "ctd_playout_dev": (_i, [c_void, _u64, _u64, _u64, _i, _u32, ctypes.POINTER(PlayoutStats),
                              ctypes.POINTER(ctypes.c_float)]),
     "ctd_launch_count": (_u64, [c_void]),
-    "ctd_make_roots": (_i, [c_void, _u32, _u64, _u64, _i, _u32, _u32, c_void]),
+    "ctd_make_roots": (_i, [c_void, _u32, _u64, _u64, _i, _u32, _u32, _i, c_void]),
     "ctd_load_roots": (_i, [c_void, _u32, c_void, c_void, c_void, c_void]),
     "ctd_store_roots": (_i, [c_void, _u32, c_void, c_void, c_void, c_void]),
-    "ctd_mccfr_tree_shape": (None, [_u32, _i, ctypes.POINTER(_u32), ctypes.POINTER(_u32), ctypes.POINTER(_u32),
-                                    ctypes.POINTER(_u64)]),
+    "ctd_mccfr_tree_shape": (None, [_u32, _i, _u32, ctypes.POINTER(_u32), ctypes.POINTER(_u32), ctypes.POINTER(_u64)]),
+    "ctd_mccfr_export": (_i, [c_void, _u32, _u32, c_void, c_void, _u64]),
+    "ctd_mccfr_root_children": (_i, [c_void, _u32, _u32, _u32, c_void, c_void, c_void, c_void]),
     "ctd_game_new": (_i, [c_void, _u64, _u64, _i, c_void, c_void, c_void]),
     "ctd_game_options": (_i, [c_void, _u64, c_void, c_void, c_void, _u32, ctypes.POINTER(_u32)]),
     "ctd_game_step": (_i, [c_void, _u64, c_void, c_void, _u64, ctypes.POINTER(ctypes.c_int8)]),
+    "ctd_game_sample": (_i, [c_void, _u64, c_void, c_void, c_void, _i, _i]),
     "ctd_set_value_model": (_i, [c_void] + [c_void] * 8),
     "ctd_set_value_backend": (_i, [c_void, _i]),
     "ctd_value_eval": (_i, [c_void, _u32, c_void, ctypes.c_float, c_void]),
     "ctd_encode": (_i, [c_void, _u32, _i, c_void]),
-    "ctd_mccfr_pred": (_i, [c_void, _u32, _u64, _u32, _u32, _i, ctypes.c_float, c_void, c_void,
+    "ctd_mccfr_pred": (_i, [c_void, _u32, _u64, _u32, _u32, _i, ctypes.c_float, c_void,
                             ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_u32)]),
     "ctd_mccfr_targets": (_i, [c_void, _u32, _u64, _u32, _i, ctypes.c_double, ctypes.POINTER(_u32), ctypes.POINTER(_u32),
                                c_void, c_void, c_void, c_void]),
-    "ctd_mccfr": (_i, [c_void, _u32, _u64, _u32, _i, c_void, c_void, ctypes.POINTER(ctypes.c_float)]),
+    "ctd_mccfr": (_i, [c_void, _u32, _u64, _u32, _i, c_void, ctypes.POINTER(ctypes.c_float)]),
 }
 
 _lib = None

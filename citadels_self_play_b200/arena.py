@@ -20,7 +20,7 @@ import random
 import numpy as np
 
 from .engine import Engine, EngineError, DEFAULT_SEED, RULESET_PRESET
-from .layout import KNOW_BYTES, opt_fields
+from .layout import KNOW_BYTES
 from . import facade as F
 
 
@@ -45,21 +45,14 @@ def play_games(sim_number, model=None, engine=None, seed=DEFAULT_SEED, first_gid
     return winners
 
 
-def _live_choice(res, game, options, nprng):
-    """CFRNode.action_choice(live=True) from one ctd_mccfr_result record."""
-    k = int(res["n_children"])
-    if not res["role_pick"]:
-        if k == 0:
-            raise ValueError("a terminal root has no children (the reference raises ValueError here too)")
-        if k > len(res["options"]):
-            raise EngineError("root with %d children: more than a result record holds" % k)
-        c = np.array(res["cumulative_strategy"][:k])
-        i = nprng.choice(k, p=c / c.sum())
-        return F.option(int(res["options"][i]), game)
-    # role-pick root: the searching player's strategy row indexed by the ranks on offer (game/game.py:312-317)
-    ranks = [opt_fields(o.desc)["rank"] for o in options]
-    sub = np.array(res["strategy"][:60]).reshape(6, 10)[game.gamestate.player_id][ranks]
-    return options[nprng.choice(len(options), p=sub / sub.sum())]
+def _live_choice(res, game, options, nprng=None):
+    """CFRNode.action_choice(live=True) from one ctd_mccfr_result record: the kernel drew the decision from the tree's own
+    chance stream right after the search (cumulative-strategy draw, or the role-preference quirk of game/game.py:312-317 at a
+    role-pick root)."""
+    d = int(res["live_option"])
+    if d == 0:
+        raise ValueError("a terminal root has no children (the reference raises ValueError here too)")
+    return F.option(d, game)
 
 
 def search_batch(engine, games, decision_no, model=None, iterations=2000, max_depth=10, weight=5.0):
@@ -68,7 +61,7 @@ def search_batch(engine, games, decision_no, model=None, iterations=2000, max_de
     recs = np.stack([np.frombuffer(g._rec.tobytes(), dtype=np.uint8) for g in games])
     knows = np.stack([g._know[g.gamestate.player_id * KNOW_BYTES:(g.gamestate.player_id + 1) * KNOW_BYTES] for g in games])
     used = np.stack([g._used for g in games])
-    gids = np.array([(g.gid & ((1 << 40) - 1)) | (int(t) << 40) for g, t in zip(games, decision_no)], dtype=np.uint64)
+    gids = np.array([F.tree_gid(g.gid, t) for g, t in zip(games, decision_no)], dtype=np.uint64)
     engine.load_roots(recs, knows, used, gids)
     ruleset = int(games[0]._rec["ruleset"])
     seed = games[0].seed
@@ -80,8 +73,8 @@ def search_batch(engine, games, decision_no, model=None, iterations=2000, max_de
     res = out["results"]
     bad = res["status"] & ~np.uint32(1)
     if bad.any():
-        raise EngineError("MCCFR status %d in a batched search (2 node pool exhausted, 4 engine error, 8 option overflow)"
-                          % int(bad.max()))
+        raise EngineError("MCCFR status %d in a batched search (2 device memory exhausted, 4 container capacity, 16 the reference "
+                          "raises for this root)" % int(bad.max()))
     return res
 
 

@@ -82,10 +82,22 @@
  * fetch, not by issue slots (profiles/README.md, round-1 A/B table) -- so the simpler lane-0 stream is the default. */
 #define CTD_PLAYOUT_RING 0
 #endif
+// Container capacities.  The fused playout units (ctd_*_playout.cu) define CTD_SMALL_CAPS: real games of the fixed rulesets
+// stay far below them (hand 25, city 9, museum 14, just_drawn 33 over 5e5 games) and the working record is what occupies
+// their shared memory.  Everything that touches CFR trees uses the large set: hypothetical games inside a tree do not end
+// when a city jumps past seven districts (Game.is_last_round tests == 7, game/game.py:173-181) and run on for hundreds of
+// steps (cities of 42, hands of 31, museums of 21 seen in 4096 random-ruleset trees of 200 iterations).
+#ifdef CTD_SMALL_CAPS
 #define CTD_HAND_CAP 48
-#define CTD_BLD_CAP 32 /* the Cardinal builds without limit inside CFR's hypothetical games (19 seen) */
+#define CTD_BLD_CAP 32
 #define CTD_MUS_CAP 32
-#define CTD_JD_CAP 48 /* Smithy / Park draw into just_drawn_cards and nothing empties it until the next card pick: 33 seen in 5e5 classic games */
+#define CTD_JD_CAP 48
+#elif !defined(CTD_HAND_CAP)
+#define CTD_HAND_CAP 64
+#define CTD_BLD_CAP 64
+#define CTD_MUS_CAP 48
+#define CTD_JD_CAP 48
+#endif /* Smithy / Park draw into just_drawn_cards and nothing empties it until the next card pick: 33 seen in 5e5 classic games */
 #define CTD_DECK_CAP 128 /* ring buffer, power of two */
 #define CTD_DISC_CAP 128
 
@@ -174,9 +186,11 @@ struct alignas(16) CtdWork {
   uint8_t jd[6][CTD_JD_CAP];
   uint8_t deck[CTD_DECK_CAP];  // ring: element i is deck[(deck_head + i) & 127]
   uint8_t disc[CTD_DISC_CAP];
+  int32_t gold[6];     // Agent.gold: a Python int in the reference; in run-away hypothetical games inside CFR trees a robbed
+                       // seat that is sampled as the Thief doubles its own purse every round (11114 seen in 200 iterations)
+  int16_t points[6];   // Game.points at terminal (a 32-district city scores far beyond a signed byte)
   uint8_t n_hand[6], n_bld[6], n_mus[6], n_jd[6];
   uint8_t deck_head, n_deck, n_disc;
-  int8_t gold[6];
   uint8_t role[6];
   int8_t replicas[6];
   uint8_t pflags[6];
@@ -187,12 +201,11 @@ struct alignas(16) CtdWork {
   uint8_t used_len, rtc_mask, state, player, done, n_trade, n_nontrade, next_player, next_mode, crown, gflags;
   int8_t winner;
   uint8_t wiz_target;
-  int8_t points[6];
   uint8_t warrant_building, ruleset, err;
   uint8_t seer_mask;   // game.seer_taken_card_from (seat order) as a mask
   uint8_t n_seven;     // game.seven_drawn_cards
   uint8_t seven[7];
-  uint8_t snap_pad[2];
+  uint8_t snap_pad[10];
   // ---- everything above is the game itself: CTD_SNAP_BYTES, copied verbatim into MCCFR tree nodes ----
   uint8_t scratch[128];
   // chance: Philox4x32-10 keyed (seed, gid) or a recorded tape
@@ -210,8 +223,8 @@ struct alignas(16) CtdWork {
   uint32_t steps;
 };
 
-#define CTD_SNAP_BYTES 1328
-static_assert(offsetof(CtdWork, scratch) == CTD_SNAP_BYTES, "CtdWork snapshot region");
+#define CTD_SNAP_BYTES (6 * (CTD_HAND_CAP + CTD_BLD_CAP + CTD_MUS_CAP + CTD_JD_CAP) + CTD_DECK_CAP + CTD_DISC_CAP + 144)
+static_assert(offsetof(CtdWork, scratch) == CTD_SNAP_BYTES && CTD_SNAP_BYTES % 16 == 0, "CtdWork snapshot region");
 
 // ------------------------------------------------------------------------------------------ chance
 CTD_HD CTD_NI inline void ctd_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
@@ -584,7 +597,7 @@ CTD_HD CTD_NI inline bool ctd_check_game_ending(CtdWork& w) {
   int best = -1000, bi = 0;
   CTD_LOOP for (int p = 0; p < 6; ++p) {
     int pts = ctd_count_points(w, p);
-    w.points[p] = (int8_t)pts;
+    w.points[p] = (int16_t)pts;
     if (pts > best) { best = pts; bi = p; }
   }
   w.gflags |= 2;
@@ -1143,7 +1156,7 @@ CTD_HD CTD_NI inline void ctd_apply_build(CtdWork& w, int p, int t, int replica)
   CTD_ASSUME_SHARED(&w);
   int c = ctd_take_like(w.hand[p], w.n_hand[p], t);
   ctd_append(w, w.bld[p], w.n_bld[p], CTD_BLD_CAP, c);
-  if (ctd_name(w, p) != CTD_ALCHEMIST) w.gold[p] -= (int8_t)ctd_ccost(c);
+  if (ctd_name(w, p) != CTD_ALCHEMIST) w.gold[p] -= (int32_t)ctd_ccost(c);
   if (replica) w.replicas[p] = (int8_t)replica;
   if (ctd_csuit(c) == CTD_SUIT_TRADE) { if (w.n_trade < 15) ++w.n_trade; }
   else { if (w.n_nontrade < 15) ++w.n_nontrade; }
@@ -1248,8 +1261,8 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
         int th = ctd_player_from_rank(w, 1);
         if (th < 0) { w.err |= CTD_ERR_REF_RAISE; break; }
         int g = w.gold[p];
-        w.gold[th] += (int8_t)g;  // thief may be p itself only if p holds rank 1, which is never robbed by itself
-        w.gold[p] = (int8_t)(th == p ? g : 0);
+        w.gold[th] += (int32_t)g;  // thief may be p itself only if p holds rank 1, which is never robbed by itself
+        w.gold[p] = (int32_t)(th == p ? g : 0);
         if (th == p) w.gold[p] = 0;
       }
       if (CTD_OPT_NAMED(d) == CTD_N_GOLD) {
@@ -1345,7 +1358,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       ctd_restore_next(w);
       break;
     case CTD_K_TAKE_GOLD_WAR:  // carry_out_take_gold_for_war (:553-559)
-      w.gold[p] += (int8_t)ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_WAR);
+      w.gold[p] += (int32_t)ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_WAR);
       ctd_to5(w, p);
       w.done |= CTD_DM_TAKE_GOLD;
       break;
@@ -1368,8 +1381,8 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       int q = CTD_OPT_TARGET(d), s = CTD_OPT_NAMED(d) - CTD_N_TRADE;
       int n = ctd_count_suit(w.hand[q], w.n_hand[q], s);
       int steal = n < w.gold[q] ? n : w.gold[q];
-      w.gold[p] += (int8_t)steal;
-      w.gold[q] -= (int8_t)steal;
+      w.gold[p] += (int32_t)steal;
+      w.gold[q] -= (int32_t)steal;
       ctd_draw_to_hand(w, p);
       ctd_to5(w, p);
       w.done |= CTD_DM_CHARACTER;
@@ -1435,24 +1448,24 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       break;
     }
     case CTD_K_TAKE_CROWN_KING:  // carry_out_take_crown_king (:354-363)
-      w.gold[p] += (int8_t)ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_LORD);
+      w.gold[p] += (int32_t)ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_LORD);
       if (!(w.pflags[p] & CTD_PF_WITCH)) ctd_move_crown(w, p);
       ctd_to5(w, p);
       w.done |= CTD_DM_CHARACTER;
       break;
     case CTD_K_BISHOP: CTD_NOT_PRESET();  // carry_out_bishop (:397-403)
-      w.gold[p] += (int8_t)ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_RELIGION);
+      w.gold[p] += (int32_t)ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_RELIGION);
       ctd_to5(w, p);
       w.done |= CTD_DM_CHARACTER;
       break;
     case CTD_K_MERCHANT: CTD_NOT_PRESET();  // carry_out_merchant (:442-449)
-      w.gold[p] += (int8_t)(ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_TRADE) + 1);
+      w.gold[p] += (int32_t)(ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_TRADE) + 1);
       ctd_to5(w, p);
       w.done |= CTD_DM_CHARACTER;
       break;
     case CTD_K_ABBOT: CTD_NOT_CLASSIC(); {  // carry_out_abbot (:405-412)
       int n = CTD_OPT_R(d), kc = CTD_OPT_COUNT(d);  // the option carries its own gold/card list
-      w.gold[p] += (int8_t)(n - kc);
+      w.gold[p] += (int32_t)(n - kc);
       CTD_LOOP for (int i = 0; i < kc; ++i) ctd_draw_to_hand(w, p);
       ctd_to5(w, p);
       w.done |= CTD_DM_CHARACTER;
@@ -1484,7 +1497,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
     case CTD_K_WARLORD: {  // carry_out_warlord (:517-535) with settle_museum / settle_lighthouse (:573-586)
       int q = CTD_OPT_TARGET(d), t = CTD_OPT_CARD_A(d);
       int c = ctd_take_like(w.bld[q], w.n_bld[q], t);
-      w.gold[p] -= (int8_t)(ctd_ccost(c) - 1);
+      w.gold[p] -= (int32_t)(ctd_ccost(c) - 1);
       ctd_disc_push(w, c);
       if (ctd_count_type(w.bld[q], w.n_bld[q], t) > 1) w.replicas[q] -= 1;
       if (t == 34) {
@@ -1521,7 +1534,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       if (CTD_OPT_NAMED(d) == CTD_N_REVEAL && ((w.rprops[rq] & CTD_RP_WARRANT) >> 1) == 1) {
         const int t = w.warrant_building;
         ctd_append(w, w.bld[p], w.n_bld[p], CTD_BLD_CAP, ctd_take_like(w.bld[q], w.n_bld[q], t));
-        w.gold[q] += (int8_t)ctd_cost_of_type(t);
+        w.gold[q] += (int32_t)ctd_cost_of_type(t);
         CTD_LOOP for (int r = 0; r < 8; ++r) w.rprops[r] &= (uint8_t)~CTD_RP_WARRANT;
       }
       ctd_restore_next(w);
@@ -1538,8 +1551,8 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       if (bm < 0) { w.err |= CTD_ERR_REF_RAISE; break; }
       if (CTD_OPT_NAMED(d) == CTD_N_PAY) {
         const int half = w.gold[p] / 2;
-        w.gold[bm] += (int8_t)half;
-        w.gold[p] -= (int8_t)half;
+        w.gold[bm] += (int32_t)half;
+        w.gold[p] -= (int32_t)half;
         ctd_to5(w, p);
       } else {
         w.state = 4;
@@ -1595,7 +1608,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
     }
     case CTD_K_GIVE_CROWN: CTD_NOT_PRESET(); CTD_NOT_CLASSIC(); {  // carry_out_emperor (:377-393)
       const int q = CTD_OPT_TARGET(d);
-      w.gold[p] += (int8_t)ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_LORD);
+      w.gold[p] += (int32_t)ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_LORD);
       if (CTD_OPT_NAMED(d) == CTD_N_CARD) {
         uint8_t* h = w.hand[q];
         ctd_shuffle(w, w.n_hand[q], [h](int i) -> uint8_t& { return h[i]; });
@@ -1624,10 +1637,10 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       const int c = ctd_take_like(w.hand[p], w.n_hand[p], t);
       ctd_append(w, w.bld[p], w.n_bld[p], CTD_BLD_CAP, c);
       int g = w.gold[p] - (ctd_ccost(c) - CTD_OPT_BUILD(d));
-      w.gold[p] = (int8_t)(g < 0 ? 0 : g);
+      w.gold[p] = (int32_t)(g < 0 ? 0 : g);
       if (CTD_OPT_REPLICA(d)) w.replicas[p] = (int8_t)CTD_OPT_REPLICA(d);
       if (kc != 0) {
-        w.gold[q] -= (int8_t)kc;
+        w.gold[q] -= (int32_t)kc;
         // other_cards = hand without the built type, in hand order; hand over the (j * step)-th kc-combination
         uint8_t* other = w.scratch;
         int no = 0;
@@ -1657,7 +1670,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       break;
     }
     case CTD_K_TRADER: CTD_NOT_PRESET(); CTD_NOT_CLASSIC();  // carry_out_trader (:455-461)
-      w.gold[p] += (int8_t)ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_TRADE);
+      w.gold[p] += (int32_t)ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_TRADE);
       ctd_to5(w, p);
       w.done |= CTD_DM_CHARACTER;
       break;
@@ -1690,8 +1703,8 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
                                            : (ctd_cost_of_type(t) > ctd_cost_of_type(CTD_OPT_CARD_B(d))
                                                   ? ctd_cost_of_type(t) - ctd_cost_of_type(CTD_OPT_CARD_B(d))
                                                   : ctd_cost_of_type(CTD_OPT_CARD_B(d)) - ctd_cost_of_type(t));
-      w.gold[p] -= (int8_t)money;
-      w.gold[q] += (int8_t)money;
+      w.gold[p] -= (int32_t)money;
+      w.gold[q] += (int32_t)money;
       ctd_append(w, w.bld[p], w.n_bld[p], CTD_BLD_CAP, ctd_take_like(w.bld[q], w.n_bld[q], t));
       if (k == CTD_K_DIPLOMAT)
         ctd_append(w, w.bld[q], w.n_bld[q], CTD_BLD_CAP, ctd_take_like(w.bld[p], w.n_bld[p], CTD_OPT_CARD_B(d)));
@@ -1710,6 +1723,17 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
     }
     default: w.err |= CTD_ERR_UNIMPL; break;
   }
+#ifdef CTD_HOST_DEBUG
+  {  // container / purse maxima over everything this process played (cap study: tools/scan_status_cpu.py with HS_LIB=debug build)
+    static int mx[5] = {0, 0, 0, 0, 0};
+    bool up = false;
+    for (int q = 0; q < 6; ++q) {
+      const int v[5] = {w.n_hand[q], w.n_bld[q], w.n_mus[q], w.n_jd[q], w.gold[q] < 0 ? -w.gold[q] : w.gold[q]};
+      for (int i = 0; i < 5; ++i) if (v[i] > mx[i]) { mx[i] = v[i]; up = true; }
+    }
+    if (up) fprintf(stderr, "MAX hand %d city %d museum %d just_drawn %d |gold| %d (steps %u)\n", mx[0], mx[1], mx[2], mx[3], mx[4], w.steps);
+  }
+#endif
   ctd_is_last_round(w);
   ++w.steps;
   return won;
@@ -1762,8 +1786,18 @@ CTD_HD CTD_NI inline void ctd_pack(const CtdWork& w, ctd_state* s) {
   }
   s->off[c] = (uint8_t)pos;
   CTD_LOOP for (int p = 0; p < 6; ++p) {
-    s->gold[p] = w.gold[p]; s->role[p] = w.role[p]; s->replicas[p] = w.replicas[p]; s->pflags[p] = w.pflags[p];
-    s->order[p] = w.order[p]; s->used_roles[p] = w.used_roles[p]; s->points[p] = w.points[p];
+    // gold = sign-extended low byte + 256 * (2-bit signed page in gold_hi): -640 .. 383; records written before the page
+    // existed (page 0) read back unchanged
+    const int g = w.gold[p], lo = (int)(int8_t)(uint8_t)g, page = (g - lo) >> 8;
+    if (page < -2 || page > 1) ovf = true;
+    s->gold[p] = (int8_t)lo;
+    if (p < 4) s->gold_hi03 |= (uint8_t)((page & 3) << (2 * p));
+    else s->gold_hi45 |= (uint8_t)((page & 3) << (2 * (p - 4)));
+    const int pts = w.points[p];
+    if (pts < -128 || pts > 127) ovf = true;
+    s->points[p] = (int8_t)(pts < -128 ? -128 : (pts > 127 ? 127 : pts));
+    s->role[p] = w.role[p]; s->replicas[p] = w.replicas[p]; s->pflags[p] = w.pflags[p];
+    s->order[p] = w.order[p]; s->used_roles[p] = w.used_roles[p];
   }
   CTD_LOOP for (int r = 0; r < 8; ++r) { s->rprops[r] = w.rprops[r]; s->variant[r] = w.variant[r]; }
   s->used_len = w.used_len; s->rtc_mask = w.rtc_mask; s->state = w.state; s->player = w.player; s->done = w.done;
@@ -1820,7 +1854,9 @@ CTD_HD CTD_NI inline void ctd_unpack(const ctd_state* s, CtdWork& w) {
     w.n_disc = (uint8_t)len;
   }
   CTD_LOOP for (int p = 0; p < 6; ++p) {
-    w.gold[p] = s->gold[p]; w.role[p] = s->role[p]; w.replicas[p] = s->replicas[p]; w.pflags[p] = s->pflags[p];
+    const int page2 = p < 4 ? (s->gold_hi03 >> (2 * p)) & 3 : (s->gold_hi45 >> (2 * (p - 4))) & 3;
+    w.gold[p] = (int32_t)((int)s->gold[p] + 256 * ((page2 ^ 2) - 2));
+    w.role[p] = s->role[p]; w.replicas[p] = s->replicas[p]; w.pflags[p] = s->pflags[p];
     w.order[p] = s->order[p]; w.used_roles[p] = s->used_roles[p]; w.points[p] = s->points[p];
   }
   CTD_LOOP for (int r = 0; r < 8; ++r) { w.rprops[r] = s->rprops[r]; w.variant[r] = s->variant[r]; }

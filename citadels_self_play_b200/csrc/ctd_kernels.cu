@@ -175,22 +175,13 @@ struct CtdRootArgs {
   uint64_t seed, first_gid;
   int ruleset;
   uint32_t back_lo, back_hi;
+  int flavour;          // CTD_ROOTS_CLOSE_TO_FINISHED / CTD_ROOTS_RANDOM_GAME
   ctd_state* roots;
   CtdKnow* knows;
   uint8_t* used_cards;  // [n][76]
   uint64_t* gids;
   uint32_t* root_step;  // [n] index of the root in the game's step sequence
 };
-
-__device__ __forceinline__ uint64_t ctd_lane0_choose(CtdWork& w, const CtdKnow* kn) {
-  CtdEmit e{nullptr, 0, 0, 0xFFFFFFFFu, 0};
-  ctd_enumerate(w, e, kn);
-  if (e.n == 0) return 0;
-  uint32_t k = ctd_randbelow(w, e.n);
-  CtdEmit e2{nullptr, 0, 0, k, 0};
-  ctd_enumerate(w, e2, kn);
-  return e2.got;
-}
 
 __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_make_roots(CtdRootArgs a) {
   __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
@@ -203,43 +194,11 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_make_roots(CtdRootArgs a) {
   CtdKnow* kn = knows[wib];
   if (lane == 0) {
     const uint64_t gid = a.first_gid + slot;
-    // pass 1: length of the game
-    ctd_new_game(w, a.seed, gid, a.ruleset);
-    while (!(w.gflags & 2) && !w.err && w.steps < 4096) {
-      uint64_t d = ctd_lane0_choose(w, nullptr);
-      if (d == 0) { w.err |= CTD_ERR_REF_RAISE; break; }
-      ctd_apply(w, d);
-    }
-    const uint32_t T = w.steps;
-    uint32_t r[4];
-    ctd_philox(0u, 2u, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)a.seed, (uint32_t)(a.seed >> 32), r);
-    const uint32_t u = a.back_lo + (uint32_t)(((uint64_t)r[0] * (a.back_hi - a.back_lo + 1)) >> 32);
-    const uint32_t k = T > u ? T - u : 0;
-    // pass 2: replay with knowledge
-    ctd_chance_init(w, a.seed, gid, 0);
-    ctd_deal_preset(w, a.ruleset, a.used_cards + (size_t)slot * 76);
-    for (int o = 0; o < 6; ++o) ctd_kn_init(kn[o], o);
-    CtdKnowSet ks{kn, 6};
-    ctd_setup_round(w, ks);
-    int limit = 0;
-    for (;;) {
-      if ((w.gflags & 2) || w.err) break;
-      CtdEmit e{nullptr, 0, 0, 0xFFFFFFFFu, 0};
-      ctd_enumerate(w, e, &kn[0]);
-      if (e.n == 0) { w.err |= CTD_ERR_REF_RAISE; break; }
-      if (w.steps >= k) {  // `while len(options) < 2 and limit < 100` (run_utils.py:46-50)
-        if (e.n >= 2 || limit >= 100) break;
-        ++limit;
-      }
-      uint32_t pick = ctd_randbelow(w, e.n);
-      CtdEmit e2{nullptr, 0, 0, pick, 0};
-      ctd_enumerate(w, e2, &kn[0]);
-      ctd_apply(w, e2.got, ks);
-    }
-    a.root_step[slot] = w.steps;
+    uint32_t step = 0;
+    const int viewer = ctd_make_root(w, kn, a.seed, gid, a.ruleset, a.back_lo, a.back_hi, a.flavour,
+                                     a.used_cards + (size_t)slot * 76, &step);
+    a.root_step[slot] = step;
     a.gids[slot] = gid;
-    int viewer = w.player < 6 ? w.player : 0;
-    for (int o = 0; o < 6; ++o) w.err |= kn[o].err;
     a.knows[slot] = kn[viewer];
     ctd_pack(w, &stage[wib]);
   }
@@ -264,9 +223,7 @@ cudaError_t ctd_mccfr_pred_preset_blocks_per_sm(int* per_sm);
 // role-pick node) and export row i of their regret matrix.
 struct CtdTargetArgs {
   uint32_t n_roots;
-  const uint8_t* trees;
-  size_t tree_stride;
-  uint32_t max_nodes, child_cap;
+  CtdTreeHdr* hdrs;
   uint64_t seed;
   double threshold;
   int fill;                 // 0: count only; 1: write records
@@ -287,14 +244,16 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_targets(CtdTargetArgs a) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t t = blockIdx.x * CTD_WARPS_PER_BLOCK + wib;
   if (t >= a.n_roots || lane != 0) return;
-  CtdTree T = ctd_tree_at(const_cast<uint8_t*>(a.trees) + t * a.tree_stride, a.max_nodes, a.child_cap);
+  CtdTree T;
   T.w = &works[wib]; T.kn = &knows[wib]; T.stage = &tstage[wib];
+  ctd_tree_attach(T, &a.hdrs[t], CtdArena{a.hdrs[t].arena, nullptr, 0});
   const CtdTreeHdr& h = *T.hdr;
   uint32_t nrec = 0, nopt = 0, rp_draws = 0;
-  if (h.n_nodes != 0 && !(h.status & CTD_TREE_TERMINAL_ROOT)) {
+  // trees that stopped early (arena exhausted, engine limit, the reference raises) are not training data
+  if (h.n_nodes != 0 && h.status == CTD_TREE_OK) {
     int cur = 0;
     for (;;) {
-      const CtdNode& n = T.nodes[cur];
+      const CtdNode& n = ctd_node(T, cur);
       const uint32_t K = n.n_children;
       double vs = 0.0;
       for (int i = 0; i < 6; ++i) vs += n.V[i];
@@ -315,10 +274,11 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_targets(CtdTargetArgs a) {
           m.tree = t; m.node = (uint32_t)cur; m.n_options = K; m.option_offset = ko; m.seat = seat; m.role_pick = rp ? 1 : 0;
           for (int i = 0; i < 6; ++i) m.node_value[i] = n.V[i];
           const double* R = ctd_R(T, n) + (rp ? seat * 10 : 0);
+          const CtdChild* kids = ctd_kids(T, n);
           double rs = 0.0;
           for (uint32_t i = 0; i < K; ++i) rs += R[i];
           for (uint32_t i = 0; i < K; ++i) {
-            a.options[ko + i] = T.children[n.child_off + i].desc;
+            a.options[ko + i] = kids[i].desc;
             a.regrets[ko + i] = rs == 0.0 ? 1.0 : R[i];   // all-zero regrets are exported as ones (:333-334, :342-343)
           }
         }
@@ -326,15 +286,16 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_targets(CtdTargetArgs a) {
         nopt += K;
       }
       // pre-order successor: first child, else next sibling of the nearest ancestor that has one
-      if (K != 0) { cur = (int)T.children[n.child_off].node; continue; }
+      if (K != 0) { cur = (int)ctd_kids(T, n)[0].node; continue; }
       int c = cur;
       for (;;) {
-        const int par = T.nodes[c].parent;
+        const int par = ctd_node(T, c).parent;
         if (par < 0) { c = -1; break; }
-        const CtdNode& pn = T.nodes[par];
+        const CtdNode& pn = ctd_node(T, par);
+        const CtdChild* pk = ctd_kids(T, pn);
         uint32_t i = 0;
-        while (i < pn.n_children && (int)T.children[pn.child_off + i].node != c) ++i;
-        if (i + 1 < pn.n_children) { c = (int)T.children[pn.child_off + i + 1].node; break; }
+        while (i < pn.n_children && (int)pk[i].node != c) ++i;
+        if (i + 1 < pn.n_children) { c = (int)pk[i + 1].node; break; }
         c = par;
       }
       if (c < 0) break;
@@ -359,11 +320,13 @@ struct CtdOneArgs {
   uint32_t* count;
   ctd_option chosen;     // op 2
   int8_t* winner;
+  int viewer, role_sample;  // op 3
 };
 __global__ void __launch_bounds__(32) ctd_k_one(CtdOneArgs a) {
   __shared__ CtdWork w;
   __shared__ CtdKnow kn[6];
   __shared__ ctd_state stage;
+  __shared__ __align__(16) uint8_t sscratch[384];
   const int lane = threadIdx.x;
   if (a.op != 0) ctd_record_load(a.state, &stage, lane);
   if (a.know6 != nullptr && a.op != 0)
@@ -385,6 +348,14 @@ __global__ void __launch_bounds__(32) ctd_k_one(CtdOneArgs a) {
       ctd_enumerate(w, e, a.know6 ? &kn[0] : nullptr);
       *a.count = e.n;
       if (e.n <= a.cap) ctd_pack(w, &stage);   // Seer / Scholar enumerations change the record (a list that does not fit is asked for again)
+    } else if (a.op == 3) {   // Game.sample_private_information (game/game.py:215-242) from seat a.viewer's knowledge
+      ctd_unpack(&stage, w);
+      w.k0 = (uint32_t)a.seed; w.k1 = (uint32_t)(a.seed >> 32);
+      w.stream = 0; w.tape = nullptr; w.tape_len = 0;
+      for (int i = 0; i < 80; ++i) sscratch[256 + i] = i < 76 ? a.used_cards[i] : 0xFF;
+      ctd_sample_private(w, kn[a.viewer], sscratch + 256, a.role_sample != 0, sscratch);
+      w.err |= kn[a.viewer].err;
+      ctd_pack(w, &stage);
     } else {
       ctd_unpack(&stage, w);
       w.k0 = (uint32_t)a.seed; w.k1 = (uint32_t)(a.seed >> 32);
@@ -404,17 +375,35 @@ __global__ void __launch_bounds__(32) ctd_k_one(CtdOneArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------ deep MCCFR
-// export pass: pack the game record of every node of every tree (one warp per tree, only when trees are copied out)
-__global__ void __launch_bounds__(CTD_BLOCK) ctd_k_pack_trees(uint8_t* trees, size_t tree_stride, uint32_t n_roots, uint32_t max_nodes,
-                                                              uint32_t child_cap) {
+// export pass: every tree as a compact block (ctd_tree_export), one warp per tree, only when trees are copied out
+__global__ void __launch_bounds__(CTD_BLOCK) ctd_k_export_trees(CtdTreeHdr* hdrs, uint32_t first, uint32_t n, const uint64_t* out_off,
+                                                                uint8_t* out) {
   __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
   __shared__ __align__(16) ctd_state tstage[CTD_WARPS_PER_BLOCK];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t t = blockIdx.x * CTD_WARPS_PER_BLOCK + wib;
-  if (t >= n_roots || lane != 0) return;
-  CtdTree T = ctd_tree_at(trees + t * tree_stride, max_nodes, child_cap);
+  if (t >= n || lane != 0) return;
+  CtdTree T;
   T.w = &works[wib]; T.stage = &tstage[wib];
-  ctd_tree_pack_nodes(T);
+  ctd_tree_attach(T, &hdrs[first + t], CtdArena{hdrs[first + t].arena, nullptr, 0});
+  ctd_tree_export(T, out + out_off[t]);
+}
+
+// root arrays of one tree beyond what a result record holds (ctd_mccfr_root_children)
+__global__ void ctd_k_root_children(CtdTreeHdr* hdrs, uint32_t tree, uint32_t first, uint32_t count, ctd_option* options, double* R,
+                                    double* S, double* C) {
+  CtdTree T;
+  ctd_tree_attach(T, &hdrs[tree], CtdArena{hdrs[tree].arena, nullptr, 0});
+  if (T.hdr->n_nodes == 0) return;
+  const CtdNode& n = ctd_node(T, 0);
+  const CtdChild* kids = ctd_kids(T, n);
+  const double *r = ctd_R(T, n), *s = ctd_S(T, n), *c = ctd_C(T, n);
+  const bool rp = n.flags & CTD_NF_ROLE_PICK;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    const uint32_t k = first + i;
+    options[i] = k < n.n_children ? kids[k].desc : 0;
+    if (!rp) { R[i] = k < n.n_children ? r[k] : 0.0; S[i] = k < n.n_children ? s[k] : 0.0; C[i] = k < n.n_children ? c[k] : 0.0; }
+  }
 }
 
 // ValueOnlyNN.forward in eval mode (algorithms/models.py:17-23) with BatchNorm folded into fc1/fc2, then
@@ -540,6 +529,7 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_encode(const ctd_state* slots
 }
 
 // ------------------------------------------------------------------------------------------ host side / C ABI
+#define CTD_MAX_ARENAS 6
 struct ctd_engine {
   int device;
   uint32_t slots_rs_n;      // slots [0, slots_rs_n) are known to hold games of ruleset slots_rs (ctd_reset / ctd_load_states):
@@ -571,8 +561,17 @@ struct ctd_engine {
   uint8_t* d_used_cards;
   uint64_t* d_gids;
   uint32_t* d_root_step;
-  uint8_t* d_trees;
-  size_t trees_bytes;
+  // MCCFR trees: one 256-byte header per root + arenas the trees allocate from (arena 0: the whole batch; 1..: retries of
+  // trees that found an arena exhausted, each with a larger budget per tree)
+  CtdTreeHdr* d_hdrs;
+  uint8_t* d_arena[CTD_MAX_ARENAS];
+  size_t arena_bytes[CTD_MAX_ARENAS];
+  unsigned long long* d_arena_used;   // [CTD_MAX_ARENAS]
+  uint32_t trees_n;                   // roots searched by the last ctd_mccfr / ctd_mccfr_pred call
+  ctd_mccfr_result* d_results;
+  size_t results_n;
+  uint32_t* d_list;                   // retry lists
+  size_t list_n;
   uint64_t* d_opts_scratch;
   size_t opts_scratch_bytes;
   // value model (BN folded, transposed) and deep-MCCFR batch buffers
@@ -667,7 +666,11 @@ void ctd_destroy(ctd_engine* e) {
   if (e->d_used_cards) cudaFree(e->d_used_cards);
   if (e->d_gids) cudaFree(e->d_gids);
   if (e->d_root_step) cudaFree(e->d_root_step);
-  if (e->d_trees) cudaFree(e->d_trees);
+  if (e->d_hdrs) cudaFree(e->d_hdrs);
+  for (int i = 0; i < CTD_MAX_ARENAS; ++i) if (e->d_arena[i]) cudaFree(e->d_arena[i]);
+  if (e->d_arena_used) cudaFree(e->d_arena_used);
+  if (e->d_results) cudaFree(e->d_results);
+  if (e->d_list) cudaFree(e->d_list);
   if (e->d_opts_scratch) cudaFree(e->d_opts_scratch);
   if (e->d_model) cudaFree(e->d_model);
   if (e->d_feat) cudaFree(e->d_feat);
@@ -958,8 +961,9 @@ static ctd_status ctd_root_buffers(ctd_engine* e) {
 }
 
 ctd_status ctd_make_roots(ctd_engine* e, uint32_t n, uint64_t seed, uint64_t first_gid, int ruleset, uint32_t back_lo,
-                          uint32_t back_hi, uint32_t* root_step) {
-  if (!e || n > e->capacity || back_hi < back_lo || (ruleset < CTD_RULESET_PRESET || ruleset > CTD_RULESET_RANDOM))
+                          uint32_t back_hi, int flavour, uint32_t* root_step) {
+  if (!e || n > e->capacity || back_hi < back_lo || (ruleset < CTD_RULESET_PRESET || ruleset > CTD_RULESET_RANDOM) ||
+      (flavour != CTD_ROOTS_CLOSE_TO_FINISHED && flavour != CTD_ROOTS_RANDOM_GAME))
     return CTD_EARG;
   if (n == 0) return CTD_OK;
   CTD_CUDA(e, cudaSetDevice(e->device));
@@ -967,7 +971,7 @@ ctd_status ctd_make_roots(ctd_engine* e, uint32_t n, uint64_t seed, uint64_t fir
   if (s != CTD_OK) return s;
   e->slots_rs_n = 0;
   e->seed = seed;
-  CtdRootArgs a{n, seed, first_gid, ruleset, back_lo, back_hi, e->d_slots, e->d_knows, e->d_used_cards, e->d_gids,
+  CtdRootArgs a{n, seed, first_gid, ruleset, back_lo, back_hi, flavour, e->d_slots, e->d_knows, e->d_used_cards, e->d_gids,
                 e->d_root_step};
   ctd_k_make_roots<<<ctd_blocks(n), CTD_BLOCK, 0, e->stream>>>(a);
   e->launches++;
@@ -1004,72 +1008,347 @@ ctd_status ctd_store_roots(ctd_engine* e, uint32_t n, ctd_state* roots, void* kn
   return CTD_OK;
 }
 
-void ctd_mccfr_tree_shape(uint32_t iterations, int ruleset, uint32_t* max_nodes, uint32_t* child_cap, uint32_t* arr_cap,
-                          uint64_t* bytes) {
-  // measured on the reference: <= 3.6 nodes per iteration (preset); a classic Magician expands ~1600 options at once, the
-  // Cardinal of the random rulesets up to CTD_MCCFR_OPT_CAP (4096) and more than once per tree
-  uint32_t extra = ruleset == CTD_RULESET_CLASSIC ? 8192 : (ruleset == CTD_RULESET_RANDOM ? 16384 : 0);
-  uint32_t mn = 8 * iterations + 512 + extra, cc = mn + 10 * (iterations + 2), ac = 3 * cc + 180 * 64;
-  if (max_nodes) *max_nodes = mn;
-  if (child_cap) *child_cap = cc;
-  if (arr_cap) *arr_cap = ac;
-  if (bytes) *bytes = (uint64_t)((ctd_tree_bytes(mn, cc, ac) + 255) & ~(size_t)255);
+// ---- memory plan of a search
+// chunk 0 of a tree: the smallest power of two >= 2 x iterations (measured on the reference: 1.7 nodes per iteration on average,
+// <= 3.6 for 99 % of preset trees), at least 64
+static uint32_t ctd_n0_log2(uint32_t iterations) {
+  uint32_t k = 6;
+  while (k < 20 && (1ull << k) < 2ull * iterations) ++k;
+  return k;
+}
+// arena bytes budgeted per tree: chunk 0 plus half of it again for the trees that outgrow it, the node arrays, slab slack.
+// The classic Magician expands ~1600 children at once and the Cardinal of the random rulesets thousands, more than once per tree:
+// those rulesets get a larger share.  A budget is an average, not a limit: trees borrow from each other, and a tree that finds
+// the arena exhausted is searched again from a larger one (ctd_search below).
+static uint64_t ctd_tree_budget(uint32_t iterations, int ruleset) {
+  const uint64_t n0 = 1ull << ctd_n0_log2(iterations);
+  uint64_t b = n0 * sizeof(CtdNode) * 3 / 2 + (uint64_t)iterations * 10 * 40 + 4 * CTD_SLAB_UNITS * CTD_ARENA_UNIT;
+  if (ruleset == CTD_RULESET_CLASSIC) b *= 4;
+  if (ruleset == CTD_RULESET_RANDOM) b *= 8;
+  return b;
+}
+void ctd_mccfr_tree_shape(uint32_t iterations, int ruleset, uint32_t n_roots, uint32_t* first_chunk_nodes, uint32_t* node_bytes,
+                          uint64_t* arena_bytes) {
+  if (first_chunk_nodes) *first_chunk_nodes = 1u << ctd_n0_log2(iterations);
+  if (node_bytes) *node_bytes = (uint32_t)sizeof(CtdNode);
+  if (arena_bytes) *arena_bytes = ctd_tree_budget(iterations, ruleset) * n_roots + (64ull << 20);
 }
 
-ctd_status ctd_mccfr(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32_t iterations, int ruleset,
-                     ctd_mccfr_result* results, void* trees_out, float* elapsed_ms) {
-  if (!e || n_roots > e->capacity || !e->d_knows) return CTD_EARG;
-  if (n_roots == 0) return CTD_OK;
-  CTD_CUDA(e, cudaSetDevice(e->device));
-  uint32_t mn, cc, ac;
-  uint64_t stride;
-  ctd_mccfr_tree_shape(iterations, ruleset, &mn, &cc, &ac, &stride);
-  size_t need = (size_t)stride * n_roots;
-  if (need > e->trees_bytes) {
-    if (e->d_trees) CTD_CUDA(e, cudaFree(e->d_trees));
-    e->d_trees = nullptr; e->trees_bytes = 0;
-    CTD_CUDA(e, cudaMalloc((void**)&e->d_trees, need));
-    e->trees_bytes = need;
+static ctd_status ctd_ensure_arena(ctd_engine* e, int idx, size_t bytes) {
+  if (!e->d_arena_used) {
+    CTD_CUDA(e, cudaMalloc((void**)&e->d_arena_used, CTD_MAX_ARENAS * sizeof(unsigned long long)));
   }
-  size_t rb = (size_t)n_roots * sizeof(ctd_mccfr_result);
-  ctd_status s = ctd_scratch(e, rb);
-  if (s != CTD_OK) return s;
-  CTD_CUDA(e, cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream));
-  CtdMccfrArgs a;
-  memset(&a, 0, sizeof(a));
-  a.n_roots = n_roots; a.roots = e->d_slots; a.knows = e->d_knows; a.used_cards = e->d_used_cards; a.gids = e->d_gids;
-  a.seed = seed; a.iterations = iterations; a.max_nodes = mn; a.child_cap = cc; a.arr_cap = ac;
-  a.trees = e->d_trees; a.tree_stride = stride; a.results = (ctd_mccfr_result*)e->d_scratch; a.counter = e->d_counter;
+  if (!e->d_hdrs) {
+    CTD_CUDA(e, cudaMalloc((void**)&e->d_hdrs, (size_t)e->capacity * sizeof(CtdTreeHdr)));
+    CTD_CUDA(e, cudaMemsetAsync(e->d_hdrs, 0, (size_t)e->capacity * sizeof(CtdTreeHdr), e->stream));
+  }
+  if (bytes > e->arena_bytes[idx]) {
+    if (e->d_arena[idx]) { CTD_CUDA(e, cudaStreamSynchronize(e->stream)); CTD_CUDA(e, cudaFree(e->d_arena[idx])); }
+    e->d_arena[idx] = nullptr; e->arena_bytes[idx] = 0;
+    size_t free_b = 0, total_b = 0;
+    CTD_CUDA(e, cudaMemGetInfo(&free_b, &total_b));
+    if (bytes > free_b - free_b / 8) bytes = free_b - free_b / 8;   // leave an eighth of what is free to everybody else
+    bytes &= ~(size_t)255;
+    cudaError_t c = cudaMalloc((void**)&e->d_arena[idx], bytes);
+    if (c != cudaSuccess) { (void)cudaGetLastError(); snprintf(e->err, sizeof(e->err), "tree arena of %zu bytes: %s", bytes, cudaGetErrorString(c)); return CTD_ENOMEM; }
+    e->arena_bytes[idx] = bytes;
+  }
+  const unsigned long long one = 1;   // offset 0 means "none"
+  CTD_CUDA(e, cudaMemcpyAsync(e->d_arena_used + idx, &one, sizeof(one), cudaMemcpyHostToDevice, e->stream));
+  return CTD_OK;
+}
+static CtdArena ctd_arena_of(ctd_engine* e, int idx) {
+  return CtdArena{e->d_arena[idx], e->d_arena_used + idx, (unsigned long long)(e->arena_bytes[idx] / CTD_ARENA_UNIT)};
+}
+static ctd_status ctd_ensure_results(ctd_engine* e, uint32_t n) {
+  if (n <= e->results_n) return CTD_OK;
+  if (e->d_results) CTD_CUDA(e, cudaFree(e->d_results));
+  e->d_results = nullptr; e->results_n = 0;
+  CTD_CUDA(e, cudaMalloc((void**)&e->d_results, (size_t)n * sizeof(ctd_mccfr_result)));
+  e->results_n = n;
+  return CTD_OK;
+}
+static ctd_status ctd_ensure_opts(ctd_engine* e, size_t warps) {
+  const size_t ob = warps * CTD_MCCFR_OPT_CAP * sizeof(uint64_t);
+  if (ob <= e->opts_scratch_bytes) return CTD_OK;
+  if (e->d_opts_scratch) CTD_CUDA(e, cudaFree(e->d_opts_scratch));
+  e->d_opts_scratch = nullptr; e->opts_scratch_bytes = 0;
+  CTD_CUDA(e, cudaMalloc((void**)&e->d_opts_scratch, ob));
+  e->opts_scratch_bytes = ob;
+  return CTD_OK;
+}
+
+// what one search call asks for
+struct CtdSearch {
+  uint32_t n_roots;
+  uint64_t seed;
+  uint32_t iterations;
+  int ruleset;
+  bool deep;
+  uint32_t max_depth;
+  float weight;
+};
+static ctd_status ctd_value_forward(ctd_engine* e, uint32_t n, const uint8_t* pending, float weight, uint32_t row0, cudaStream_t st);
+static ctd_status ctd_pred_buffers(ctd_engine* e);
+
+// one pass of pure MCCFR over `n` trees (d_list: their root indices, or null for roots [0, n)) allocating from arena `ai`
+static ctd_status ctd_pure_pass(ctd_engine* e, const CtdSearch& sp, const uint32_t* d_list, uint32_t n, int ai) {
+  const bool preset = sp.ruleset == CTD_RULESET_PRESET;   // the roots were made / loaded for this ruleset: specialised kernel
   int per_sm = 0;
-  const bool preset = ruleset == CTD_RULESET_PRESET;   // the roots were made / loaded for this ruleset: specialised kernel
   if (preset) CTD_CUDA(e, ctd_mccfr_preset_blocks_per_sm(&per_sm));
   else CTD_CUDA(e, ctd_mccfr_generic_blocks_per_sm(&per_sm));
   if (per_sm < 1) per_sm = 1;
-  uint64_t want = (uint64_t)e->sm_count * per_sm, needb = (n_roots + CTD_WARPS_PER_BLOCK - 1) / CTD_WARPS_PER_BLOCK;
-  int grid = (int)(needb < want ? needb : want);
-  size_t ob = (size_t)grid * CTD_WARPS_PER_BLOCK * CTD_MCCFR_OPT_CAP * sizeof(uint64_t);
-  if (ob > e->opts_scratch_bytes) {
-    if (e->d_opts_scratch) CTD_CUDA(e, cudaFree(e->d_opts_scratch));
-    e->d_opts_scratch = nullptr; e->opts_scratch_bytes = 0;
-    CTD_CUDA(e, cudaMalloc((void**)&e->d_opts_scratch, ob));
-    e->opts_scratch_bytes = ob;
-  }
-  a.opts_scratch = e->d_opts_scratch;
-  CTD_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+  const uint64_t want = (uint64_t)e->sm_count * per_sm, needb = (n + CTD_WARPS_PER_BLOCK - 1) / CTD_WARPS_PER_BLOCK;
+  const int grid = (int)(needb < want ? needb : want);
+  ctd_status s = ctd_ensure_opts(e, (size_t)grid * CTD_WARPS_PER_BLOCK);
+  if (s != CTD_OK) return s;
+  CtdMccfrArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_roots = n; a.tree_list = d_list; a.roots = e->d_slots; a.knows = e->d_knows; a.used_cards = e->d_used_cards; a.gids = e->d_gids;
+  a.seed = sp.seed; a.iterations = sp.iterations; a.n0_log2 = ctd_n0_log2(sp.iterations); a.hdrs = e->d_hdrs; a.arena = ctd_arena_of(e, ai);
+  a.results = e->d_results; a.counter = e->d_counter; a.opts_scratch = e->d_opts_scratch;
+  CTD_CUDA(e, cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream));
   if (preset) CTD_CUDA(e, ctd_mccfr_preset_launch(a, grid, e->stream));
   else CTD_CUDA(e, ctd_mccfr_generic_launch(a, grid, e->stream));
   e->launches++;
   CTD_CUDA(e, cudaGetLastError());
-  CTD_CUDA(e, cudaEventRecord(e->ev1, e->stream));
-  if (results) CTD_CUDA(e, cudaMemcpyAsync(results, e->d_scratch, rb, cudaMemcpyDeviceToHost, e->stream));
-  if (trees_out) {
-    ctd_k_pack_trees<<<ctd_blocks(n_roots), CTD_BLOCK, 0, e->stream>>>(e->d_trees, stride, n_roots, mn, cc);
-    e->launches++;
-    CTD_CUDA(e, cudaGetLastError());
-    CTD_CUDA(e, cudaMemcpyAsync(trees_out, e->d_trees, need, cudaMemcpyDeviceToHost, e->stream));
+  return CTD_OK;
+}
+
+// one pass of deep MCCFR over `n` trees.  Trees advance in waves: every tree walks until it needs a leaf value (or has spent
+// its wave budget), the value model runs on the batch of all waiting leaves, the trees resume.
+static ctd_status ctd_deep_pass(ctd_engine* e, const CtdSearch& sp, const uint32_t* d_list, uint32_t n, int ai, uint32_t* waves_out) {
+  CtdPredArgs p;
+  memset(&p, 0, sizeof(p));
+  CtdMccfrArgs& a = p.m;
+  a.roots = e->d_slots; a.knows = e->d_knows; a.used_cards = e->d_used_cards; a.gids = e->d_gids;
+  a.seed = sp.seed; a.iterations = sp.iterations; a.n0_log2 = ctd_n0_log2(sp.iterations); a.hdrs = e->d_hdrs; a.arena = ctd_arena_of(e, ai);
+  a.results = e->d_results;
+  {  // wave budget: trees that never reach the depth limit would otherwise walk all their iterations in the first wave
+    const char* env = getenv("CTD_PRED_BUDGET");
+    p.budget = env ? (uint32_t)strtoul(env, nullptr, 10) : 20u;   // measured best at 4096 roots x 200 iterations (8: 8.4e6, 20: 1.12e7, 64: 8.9e6, unbounded: 7.3e6 it/s)
+    if (p.budget == 0) p.budget = 0xFFFFFFFFu;
   }
+  p.max_depth = sp.max_depth; p.feat = e->d_feat; p.pred = e->d_pred; p.pending = e->d_pending;
+  int per_sm = 0;
+  const bool preset = sp.ruleset == CTD_RULESET_PRESET;
+  if (preset) CTD_CUDA(e, ctd_mccfr_pred_preset_blocks_per_sm(&per_sm));
+  else CTD_CUDA(e, ctd_mccfr_pred_generic_blocks_per_sm(&per_sm));
+  if (per_sm < 1) per_sm = 1;
+  // Two groups of trees take turns: each group's waves (walk kernel -> batched leaf evaluation -> walk kernel ...) run on
+  // their own stream, so the tail of one group's wave -- a few trees with expensive expansions -- overlaps with the other
+  // group's kernel instead of idling the GPU.  Trees are independent, results do not depend on the grouping.
+  const char* genv = getenv("CTD_PRED_GROUPS");
+  const int G = (genv ? atoi(genv) : 2) >= 2 && n >= 1024 ? 2 : 1;
+  if (G == 2 && !e->stream2) {
+    CTD_CUDA(e, cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+    CTD_CUDA(e, cudaMalloc((void**)&e->d_counter2, sizeof(unsigned long long)));
+    CTD_CUDA(e, cudaMalloc((void**)&e->d_n_pending2, 2 * sizeof(uint32_t)));
+    CTD_CUDA(e, cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+  }
+  const uint32_t split = G == 2 ? ((n / 2 + 7) & ~7u) : n;
+  const uint32_t g_first[2] = {0, split}, g_n[2] = {split, n - split};
+  cudaStream_t g_stream[2] = {e->stream, G == 2 ? e->stream2 : e->stream};
+  unsigned long long* g_counter[2] = {e->d_counter, e->d_counter2};
+  uint32_t* g_pending[2] = {e->d_n_pending, e->d_n_pending2};
+  int g_grid[2];
+  size_t g_opts_off[2] = {0, 0}, warps = 0;
+  for (int g = 0; g < G; ++g) {
+    uint64_t want = (uint64_t)e->sm_count * per_sm, needb = (g_n[g] + CTD_WARPS_PER_BLOCK - 1) / CTD_WARPS_PER_BLOCK;
+    g_grid[g] = (int)(needb < want ? needb : want);
+    g_opts_off[g] = warps * CTD_MCCFR_OPT_CAP;
+    warps += (size_t)g_grid[g] * CTD_WARPS_PER_BLOCK;
+  }
+  ctd_status s = ctd_ensure_opts(e, warps);
+  if (s != CTD_OK) return s;
+  if (G == 2) {
+    CTD_CUDA(e, cudaEventRecord(e->ev_join, e->stream));
+    CTD_CUDA(e, cudaStreamWaitEvent(e->stream2, e->ev_join, 0));
+  }
+  uint32_t g_waves[2] = {0, 0};
+  bool g_done[2] = {false, G == 1};
+  uint32_t* h_np = e->h_np;   // pinned: [group][2]
+  auto launch_wave = [&](int g) -> ctd_status {
+    CtdPredArgs q = p;
+    q.m.tree_list = d_list ? d_list + g_first[g] : nullptr;
+    q.m.first_root = d_list ? 0 : g_first[g]; q.m.n_roots = g_n[g]; q.m.counter = g_counter[g]; q.n_pending = g_pending[g];
+    q.m.opts_scratch = e->d_opts_scratch + g_opts_off[g];
+    q.first = g_waves[g] == 0;
+    CTD_CUDA(e, cudaMemsetAsync(g_counter[g], 0, sizeof(unsigned long long), g_stream[g]));
+    CTD_CUDA(e, cudaMemsetAsync(g_pending[g], 0, 2 * sizeof(uint32_t), g_stream[g]));
+    if (preset) CTD_CUDA(e, ctd_mccfr_pred_preset_launch(q, g_grid[g], g_stream[g]));
+    else CTD_CUDA(e, ctd_mccfr_pred_generic_launch(q, g_grid[g], g_stream[g]));
+    e->launches++;
+    CTD_CUDA(e, cudaMemcpyAsync(h_np + 2 * g, g_pending[g], 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, g_stream[g]));
+    ++g_waves[g];
+    return CTD_OK;
+  };
+  for (int g = 0; g < G; ++g) { s = launch_wave(g); if (s != CTD_OK) return s; }
+  while (!(g_done[0] && g_done[1])) {
+    for (int g = 0; g < G; ++g) {
+      if (g_done[g]) continue;
+      CTD_CUDA(e, cudaStreamSynchronize(g_stream[g]));
+      const uint32_t waiting = h_np[2 * g], yielded = h_np[2 * g + 1];
+      if (waiting == 0 && yielded == 0) { g_done[g] = true; continue; }
+      if (g_waves[g] > 2 * sp.iterations + 4) { snprintf(e->err, sizeof(e->err), "ctd_mccfr_pred: wave limit"); return CTD_ECAP; }
+      if (waiting != 0) {
+        // the feature / pending rows are indexed by root: with a retry list the model runs over every row of the call and the
+        // pending mask picks the waiting ones
+        const uint32_t row0 = d_list ? 0 : g_first[g], rows = d_list ? sp.n_roots : g_n[g];
+        s = ctd_value_forward(e, rows, e->d_pending + row0, sp.weight, row0, g_stream[g]);
+        if (s != CTD_OK) return s;
+      }
+      s = launch_wave(g);
+      if (s != CTD_OK) return s;
+    }
+  }
+  if (G == 2) {   // join: the engine's stream continues after both groups
+    CTD_CUDA(e, cudaEventRecord(e->ev_join, e->stream2));
+    CTD_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_join, 0));
+  }
+  if (waves_out) *waves_out = g_waves[0] > g_waves[1] ? g_waves[0] : g_waves[1];
+  if (e->value_backend == 1) {   // a tcgen05 kernel that timed out on an mbarrier skips its stores: never hand such values to the trees silently
+    int terr = 0;
+    CTD_CUDA(e, cudaMemcpyAsync(&terr, e->d_tc_err, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+    if (terr) {
+      CTD_CUDA(e, cudaMemsetAsync(e->d_tc_err, 0, sizeof(int), e->stream));
+      snprintf(e->err, sizeof(e->err), "tcgen05 value kernel: mbarrier wait timed out");
+      return CTD_ECUDA;
+    }
+  }
+  return CTD_OK;
+}
+
+// The search proper.  The reference never refuses a root, so neither does this: all trees share arena 0; trees that found it
+// exhausted (status CTD_TREE_EPOOL) are searched again from scratch, by themselves, from a further arena with 16x the budget per
+// tree, and so on (a tree is a pure function of (seed, root, gid), so the second search is the same search).
+static ctd_status ctd_search(ctd_engine* e, const CtdSearch& sp, ctd_mccfr_result* results, float* elapsed_ms, uint32_t* waves_out) {
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  ctd_status s = ctd_ensure_results(e, sp.n_roots);
+  if (s != CTD_OK) return s;
+  if (sp.deep) { s = ctd_pred_buffers(e); if (s != CTD_OK) return s; }
+  uint64_t budget = ctd_tree_budget(sp.iterations, sp.ruleset);
+  size_t arena0 = (size_t)(budget * sp.n_roots + (64ull << 20));
+  if (const char* env = getenv("CTD_ARENA0_BYTES")) {   // test hook: a squeezed first arena exercises the retry path
+    arena0 = (size_t)strtoull(env, nullptr, 10);
+    if (e->d_arena[0] && e->arena_bytes[0] != arena0) { CTD_CUDA(e, cudaStreamSynchronize(e->stream)); CTD_CUDA(e, cudaFree(e->d_arena[0])); e->d_arena[0] = nullptr; e->arena_bytes[0] = 0; }
+  }
+  s = ctd_ensure_arena(e, 0, arena0);
+  if (s != CTD_OK) return s;
+  e->trees_n = sp.n_roots;
+  CTD_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+  s = sp.deep ? ctd_deep_pass(e, sp, nullptr, sp.n_roots, 0, waves_out) : ctd_pure_pass(e, sp, nullptr, sp.n_roots, 0);
+  if (s != CTD_OK) return s;
+  CTD_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+  // which trees ran out of arena?  (status word of every header: 256-byte stride, 4 bytes each)
+  uint32_t* st = new (std::nothrow) uint32_t[sp.n_roots];
+  if (!st) return CTD_ENOMEM;
+  ctd_status rs = CTD_OK;
+  for (int ai = 1; ai < CTD_MAX_ARENAS; ++ai) {
+    cudaError_t c = cudaMemcpy2DAsync(st, sizeof(uint32_t), (const uint8_t*)e->d_hdrs + offsetof(CtdTreeHdr, status), sizeof(CtdTreeHdr),
+                                      sizeof(uint32_t), sp.n_roots, cudaMemcpyDeviceToHost, e->stream);
+    if (c == cudaSuccess) c = cudaStreamSynchronize(e->stream);
+    if (c != cudaSuccess) { rs = ctd_fail(e, c, "tree status read-back"); break; }
+    uint32_t nf = 0;
+    for (uint32_t t = 0; t < sp.n_roots; ++t) if (st[t] & CTD_TREE_EPOOL) st[nf++] = t;
+    if (nf == 0) break;
+    if (nf > e->list_n) {
+      if (e->d_list) cudaFree(e->d_list);
+      e->d_list = nullptr; e->list_n = 0;
+      c = cudaMalloc((void**)&e->d_list, (size_t)nf * sizeof(uint32_t));
+      if (c != cudaSuccess) { rs = ctd_fail(e, c, "retry list"); break; }
+      e->list_n = nf;
+    }
+    c = cudaMemcpyAsync(e->d_list, st, (size_t)nf * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream);
+    if (c != cudaSuccess) { rs = ctd_fail(e, c, "retry list upload"); break; }
+    budget *= 16;
+    rs = ctd_ensure_arena(e, ai, (size_t)(budget * nf + (64ull << 20)));
+    if (rs != CTD_OK) break;
+    rs = sp.deep ? ctd_deep_pass(e, sp, e->d_list, nf, ai, nullptr) : ctd_pure_pass(e, sp, e->d_list, nf, ai);
+    if (rs != CTD_OK) break;
+    CTD_CUDA(e, cudaStreamSynchronize(e->stream));   // `st` is reused as the upload source
+  }
+  delete[] st;
+  if (rs != CTD_OK) return rs;
+  if (results) CTD_CUDA(e, cudaMemcpyAsync(results, e->d_results, (size_t)sp.n_roots * sizeof(ctd_mccfr_result), cudaMemcpyDeviceToHost, e->stream));
   CTD_CUDA(e, cudaStreamSynchronize(e->stream));
   if (elapsed_ms) CTD_CUDA(e, cudaEventElapsedTime(elapsed_ms, e->ev0, e->ev1));
+  return CTD_OK;
+}
+
+ctd_status ctd_mccfr(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32_t iterations, int ruleset,
+                     ctd_mccfr_result* results, float* elapsed_ms) {
+  if (!e || n_roots > e->capacity || !e->d_knows || (ruleset < CTD_RULESET_PRESET || ruleset > CTD_RULESET_RANDOM)) return CTD_EARG;
+  if (n_roots == 0) return CTD_OK;
+  CtdSearch sp{n_roots, seed, iterations, ruleset, false, 0, 0.f};
+  return ctd_search(e, sp, results, elapsed_ms, nullptr);
+}
+
+// trees of the last search, roots [first, first + n), as compact blocks (ctd_tree_export in csrc/ctd_mccfr.cuh)
+ctd_status ctd_mccfr_export(ctd_engine* e, uint32_t first, uint32_t n, uint64_t* sizes, void* buf, uint64_t buf_bytes) {
+  if (!e || !sizes || !e->d_hdrs || (uint64_t)first + n > e->trees_n) return CTD_EARG;
+  if (n == 0) return CTD_OK;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  CtdTreeHdr* hh = new (std::nothrow) CtdTreeHdr[n];
+  if (!hh) return CTD_ENOMEM;
+  cudaError_t c = cudaMemcpyAsync(hh, e->d_hdrs + first, (size_t)n * sizeof(CtdTreeHdr), cudaMemcpyDeviceToHost, e->stream);
+  if (c == cudaSuccess) c = cudaStreamSynchronize(e->stream);
+  if (c != cudaSuccess) { delete[] hh; return ctd_fail(e, c, "tree headers"); }
+  uint64_t total = 0;
+  uint64_t* off = new (std::nothrow) uint64_t[n];
+  if (!off) { delete[] hh; return CTD_ENOMEM; }
+  for (uint32_t i = 0; i < n; ++i) {
+    sizes[i] = (ctd_tree_export_bytes(hh[i].n_nodes, hh[i].child_used, hh[i].arr_used) + 15) & ~(uint64_t)15;
+    off[i] = total;
+    total += sizes[i];
+  }
+  delete[] hh;
+  ctd_status rs = CTD_OK;
+  if (buf) {
+    if (buf_bytes < total) { delete[] off; return CTD_ECAP; }
+    uint8_t* d_out = nullptr;
+    uint64_t* d_off = nullptr;
+    c = cudaMalloc((void**)&d_out, total);
+    if (c == cudaSuccess) c = cudaMalloc((void**)&d_off, (size_t)n * sizeof(uint64_t));
+    if (c == cudaSuccess) c = cudaMemcpyAsync(d_off, off, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream);
+    if (c == cudaSuccess) c = cudaMemsetAsync(d_out, 0, total, e->stream);
+    if (c == cudaSuccess) {
+      ctd_k_export_trees<<<ctd_blocks(n), CTD_BLOCK, 0, e->stream>>>(e->d_hdrs, first, n, d_off, d_out);
+      e->launches++;
+      c = cudaGetLastError();
+    }
+    if (c == cudaSuccess) c = cudaMemcpyAsync(buf, d_out, total, cudaMemcpyDeviceToHost, e->stream);
+    if (c == cudaSuccess) c = cudaStreamSynchronize(e->stream);
+    if (d_out) cudaFree(d_out);
+    if (d_off) cudaFree(d_off);
+    if (c != cudaSuccess) rs = ctd_fail(e, c, "tree export");
+  }
+  delete[] off;
+  return rs;
+}
+
+// children [first, first + count) of the root of tree `tree`: descriptors and, for vector nodes, regrets / strategy / cumulative
+// strategy (a result record holds the first CTD_MCCFR_MAX_RESULT; the Cardinal expands thousands)
+ctd_status ctd_mccfr_root_children(ctd_engine* e, uint32_t tree, uint32_t first, uint32_t count, ctd_option* options, double* R,
+                                   double* S, double* C) {
+  if (!e || !e->d_hdrs || tree >= e->trees_n || !options || !R || !S || !C) return CTD_EARG;
+  if (count == 0) return CTD_OK;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  const size_t ob = (size_t)count * sizeof(ctd_option), db = (size_t)count * sizeof(double);
+  ctd_status s = ctd_scratch(e, ob + 3 * db);
+  if (s != CTD_OK) return s;
+  ctd_option* d_o = (ctd_option*)e->d_scratch;
+  double* d_r = (double*)((char*)e->d_scratch + ob);
+  CTD_CUDA(e, cudaMemsetAsync(e->d_scratch, 0, ob + 3 * db, e->stream));
+  ctd_k_root_children<<<(count + 255) / 256 < 64 ? (count + 255) / 256 : 64, 256, 0, e->stream>>>(e->d_hdrs, tree, first, count, d_o, d_r, d_r + count, d_r + 2 * count);
+  e->launches++;
+  CTD_CUDA(e, cudaGetLastError());
+  CTD_CUDA(e, cudaMemcpyAsync(options, d_o, ob, cudaMemcpyDeviceToHost, e->stream));
+  CTD_CUDA(e, cudaMemcpyAsync(R, d_r, db, cudaMemcpyDeviceToHost, e->stream));
+  CTD_CUDA(e, cudaMemcpyAsync(S, d_r + count, db, cudaMemcpyDeviceToHost, e->stream));
+  CTD_CUDA(e, cudaMemcpyAsync(C, d_r + 2 * count, db, cudaMemcpyDeviceToHost, e->stream));
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
   return CTD_OK;
 }
 
@@ -1160,18 +1439,34 @@ ctd_status ctd_game_step(ctd_engine* e, uint64_t seed, ctd_state* state, void* k
   return CTD_OK;
 }
 
+ctd_status ctd_game_sample(ctd_engine* e, uint64_t seed, ctd_state* state, void* know6, const uint8_t* used_cards, int viewer,
+                           int role_sample) {
+  if (!e || !state || !know6 || !used_cards || viewer < 0 || viewer > 5) return CTD_EARG;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  ctd_status s = ctd_one_buffer(e);
+  if (s != CTD_OK) return s;
+  CTD_CUDA(e, cudaMemcpyAsync(e->d_one, state, sizeof(ctd_state), cudaMemcpyHostToDevice, e->stream));
+  CTD_CUDA(e, cudaMemcpyAsync(e->d_one + CTD_ONE_KNOW_OFF, know6, CTD_ONE_KNOW6, cudaMemcpyHostToDevice, e->stream));
+  CTD_CUDA(e, cudaMemcpyAsync(e->d_one + CTD_ONE_USED_OFF, used_cards, 76, cudaMemcpyHostToDevice, e->stream));
+  CtdOneArgs a = ctd_one_args(e, 3, true);
+  a.seed = seed; a.viewer = viewer; a.role_sample = role_sample;
+  ctd_k_one<<<1, 32, 0, e->stream>>>(a);
+  e->launches++;
+  CTD_CUDA(e, cudaGetLastError());
+  CTD_CUDA(e, cudaMemcpyAsync(state, e->d_one, sizeof(ctd_state), cudaMemcpyDeviceToHost, e->stream));
+  CTD_CUDA(e, cudaMemcpyAsync(know6, e->d_one + CTD_ONE_KNOW_OFF, CTD_ONE_KNOW6, cudaMemcpyDeviceToHost, e->stream));
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  return CTD_OK;
+}
+
 // CFRNode.get_all_targets over the trees of the last ctd_mccfr / ctd_mccfr_pred call (they stay on the device).
 // Call once with all output pointers NULL to size the buffers (*n_records, *n_option_slots), then again to fill.
-static ctd_status ctd_pred_buffers(ctd_engine* e);
 ctd_status ctd_mccfr_targets(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32_t iterations, int ruleset, double threshold,
                              uint32_t* n_records, uint32_t* n_option_slots, float* features, ctd_target_meta* meta,
                              ctd_option* options, double* regrets) {
-  if (!e || !n_records || !n_option_slots || n_roots > e->capacity || !e->d_trees) return CTD_EARG;
+  if (!e || !n_records || !n_option_slots || n_roots > e->trees_n || !e->d_hdrs) return CTD_EARG;
+  (void)iterations; (void)ruleset;   // the trees on the device know their own shape
   CTD_CUDA(e, cudaSetDevice(e->device));
-  uint32_t mn, cc, ac;
-  uint64_t stride;
-  ctd_mccfr_tree_shape(iterations, ruleset, &mn, &cc, &ac, &stride);
-  if ((size_t)stride * n_roots > e->trees_bytes) return CTD_EARG;
   ctd_status s = ctd_pred_buffers(e);
   if (s != CTD_OK) return s;
   // counts
@@ -1180,7 +1475,7 @@ ctd_status ctd_mccfr_targets(ctd_engine* e, uint32_t n_roots, uint64_t seed, uin
   CTD_CUDA(e, cudaMalloc((void**)&d_cnt, 4 * cb));
   CtdTargetArgs a;
   memset(&a, 0, sizeof(a));
-  a.n_roots = n_roots; a.trees = e->d_trees; a.tree_stride = stride; a.max_nodes = mn; a.child_cap = cc; a.seed = seed;
+  a.n_roots = n_roots; a.hdrs = e->d_hdrs; a.seed = seed;
   a.threshold = threshold; a.n_targets = d_cnt; a.n_options = d_cnt + n_roots;
   ctd_k_targets<<<ctd_blocks(n_roots), CTD_BLOCK, 0, e->stream>>>(a);
   e->launches++;
@@ -1250,8 +1545,8 @@ static ctd_status ctd_pred_buffers(ctd_engine* e) {
 
 // the value model on rows [0,n) of d_feat -> d_pred (rows with pending == 0 may be skipped)
 // rows [row0, row0 + n) of the feature matrix (`pending` is the mask of those rows), on `st`
-static ctd_status ctd_value_forward(ctd_engine* e, uint32_t n, const uint8_t* pending, float weight, uint32_t row0 = 0,
-                                    cudaStream_t st = nullptr) {
+static ctd_status ctd_value_forward(ctd_engine* e, uint32_t n, const uint8_t* pending, float weight, uint32_t row0,
+                                    cudaStream_t st) {
   if (st == nullptr) st = e->stream;
   const float* feat = e->d_feat + (size_t)row0 * CTD_FEATURES_PAD;
   float* pred = e->d_pred + (size_t)row0 * 8;
@@ -1321,7 +1616,7 @@ ctd_status ctd_value_eval(ctd_engine* e, uint32_t n, const float* features, floa
   ctd_status s = ctd_pred_buffers(e);
   if (s != CTD_OK) return s;
   CTD_CUDA(e, cudaMemcpyAsync(e->d_feat, features, (size_t)n * CTD_FEATURES_PAD * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-  s = ctd_value_forward(e, n, nullptr, weight);
+  s = ctd_value_forward(e, n, nullptr, weight, 0, nullptr);
   if (s != CTD_OK) return s;
   CTD_CUDA(e, cudaMemcpy2DAsync(out6, 6 * sizeof(float), e->d_pred, 8 * sizeof(float), 6 * sizeof(float), n, cudaMemcpyDeviceToHost, e->stream));
   CTD_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -1348,125 +1643,11 @@ ctd_status ctd_encode(ctd_engine* e, uint32_t n, int cfr_role_pick, float* featu
 }
 
 ctd_status ctd_mccfr_pred(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32_t iterations, uint32_t max_depth, int ruleset,
-                          float reward_weight, ctd_mccfr_result* results, void* trees_out, float* elapsed_ms, uint32_t* waves_out) {
-  if (!e || n_roots > e->capacity || !e->d_knows || !e->d_model) return CTD_EARG;
+                          float reward_weight, ctd_mccfr_result* results, float* elapsed_ms, uint32_t* waves_out) {
+  if (!e || n_roots > e->capacity || !e->d_knows || !e->d_model || (ruleset < CTD_RULESET_PRESET || ruleset > CTD_RULESET_RANDOM)) return CTD_EARG;
   if (n_roots == 0) return CTD_OK;
-  CTD_CUDA(e, cudaSetDevice(e->device));
-  ctd_status s = ctd_pred_buffers(e);
-  if (s != CTD_OK) return s;
-  uint32_t mn, cc, ac;
-  uint64_t stride;
-  ctd_mccfr_tree_shape(iterations, ruleset, &mn, &cc, &ac, &stride);
-  size_t need = (size_t)stride * n_roots;
-  if (need > e->trees_bytes) {
-    if (e->d_trees) CTD_CUDA(e, cudaFree(e->d_trees));
-    e->d_trees = nullptr; e->trees_bytes = 0;
-    CTD_CUDA(e, cudaMalloc((void**)&e->d_trees, need));
-    e->trees_bytes = need;
-  }
-  size_t rb = (size_t)n_roots * sizeof(ctd_mccfr_result);
-  s = ctd_scratch(e, rb);
-  if (s != CTD_OK) return s;
-  CtdPredArgs p;
-  memset(&p, 0, sizeof(p));
-  CtdMccfrArgs& a = p.m;
-  a.n_roots = n_roots; a.roots = e->d_slots; a.knows = e->d_knows; a.used_cards = e->d_used_cards; a.gids = e->d_gids;
-  a.seed = seed; a.iterations = iterations; a.max_nodes = mn; a.child_cap = cc; a.arr_cap = ac;
-  a.trees = e->d_trees; a.tree_stride = stride; a.results = (ctd_mccfr_result*)e->d_scratch; a.counter = e->d_counter;
-  {  // wave budget: trees that never reach the depth limit would otherwise walk all their iterations in the first wave
-    const char* env = getenv("CTD_PRED_BUDGET");
-    p.budget = env ? (uint32_t)strtoul(env, nullptr, 10) : 20u;   // measured best at 4096 roots x 200 iterations (8: 8.4e6, 20: 1.12e7, 64: 8.9e6, unbounded: 7.3e6 it/s)
-    if (p.budget == 0) p.budget = 0xFFFFFFFFu;
-  }
-  p.max_depth = max_depth; p.feat = e->d_feat; p.pred = e->d_pred; p.pending = e->d_pending; p.n_pending = e->d_n_pending;
-  int per_sm = 0;
-  const bool preset = ruleset == CTD_RULESET_PRESET;
-  if (preset) CTD_CUDA(e, ctd_mccfr_pred_preset_blocks_per_sm(&per_sm));
-  else CTD_CUDA(e, ctd_mccfr_pred_generic_blocks_per_sm(&per_sm));
-  if (per_sm < 1) per_sm = 1;
-  // Two groups of trees take turns: each group's waves (walk kernel -> batched leaf evaluation -> walk kernel ...) run on
-  // their own stream, so the tail of one group's wave -- a few trees with expensive expansions -- overlaps with the other
-  // group's kernel instead of idling the GPU.  Trees are independent, results do not depend on the grouping.
-  const char* genv = getenv("CTD_PRED_GROUPS");
-  const int G = (genv ? atoi(genv) : 2) >= 2 && n_roots >= 1024 ? 2 : 1;
-  if (G == 2 && !e->stream2) {
-    CTD_CUDA(e, cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
-    CTD_CUDA(e, cudaMalloc((void**)&e->d_counter2, sizeof(unsigned long long)));
-    CTD_CUDA(e, cudaMalloc((void**)&e->d_n_pending2, 2 * sizeof(uint32_t)));
-    CTD_CUDA(e, cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
-  }
-  const uint32_t split = G == 2 ? ((n_roots / 2 + 7) & ~7u) : n_roots;
-  const uint32_t g_first[2] = {0, split}, g_n[2] = {split, n_roots - split};
-  cudaStream_t g_stream[2] = {e->stream, G == 2 ? e->stream2 : e->stream};
-  unsigned long long* g_counter[2] = {e->d_counter, e->d_counter2};
-  uint32_t* g_pending[2] = {e->d_n_pending, e->d_n_pending2};
-  int g_grid[2];
-  size_t g_opts_off[2] = {0, 0}, ob = 0;
-  for (int g = 0; g < G; ++g) {
-    uint64_t want = (uint64_t)e->sm_count * per_sm, needb = (g_n[g] + CTD_WARPS_PER_BLOCK - 1) / CTD_WARPS_PER_BLOCK;
-    g_grid[g] = (int)(needb < want ? needb : want);
-    g_opts_off[g] = ob;
-    ob += (size_t)g_grid[g] * CTD_WARPS_PER_BLOCK * CTD_MCCFR_OPT_CAP;
-  }
-  ob *= sizeof(uint64_t);
-  if (ob > e->opts_scratch_bytes) {
-    if (e->d_opts_scratch) CTD_CUDA(e, cudaFree(e->d_opts_scratch));
-    e->d_opts_scratch = nullptr; e->opts_scratch_bytes = 0;
-    CTD_CUDA(e, cudaMalloc((void**)&e->d_opts_scratch, ob));
-    e->opts_scratch_bytes = ob;
-  }
-  CTD_CUDA(e, cudaEventRecord(e->ev0, e->stream));
-  if (G == 2) CTD_CUDA(e, cudaStreamWaitEvent(e->stream2, e->ev0, 0));
-  uint32_t waves = 0, g_waves[2] = {0, 0};
-  bool g_done[2] = {false, G == 1};
-  uint32_t* h_np = e->h_np;   // pinned: [group][2]
-  auto launch_wave = [&](int g) -> ctd_status {
-    CtdPredArgs q = p;
-    q.m.first_root = g_first[g]; q.m.n_roots = g_n[g]; q.m.counter = g_counter[g]; q.n_pending = g_pending[g];
-    q.m.opts_scratch = e->d_opts_scratch + g_opts_off[g];
-    q.first = g_waves[g] == 0;
-    CTD_CUDA(e, cudaMemsetAsync(g_counter[g], 0, sizeof(unsigned long long), g_stream[g]));
-    CTD_CUDA(e, cudaMemsetAsync(g_pending[g], 0, 2 * sizeof(uint32_t), g_stream[g]));
-    if (preset) CTD_CUDA(e, ctd_mccfr_pred_preset_launch(q, g_grid[g], g_stream[g]));
-    else CTD_CUDA(e, ctd_mccfr_pred_generic_launch(q, g_grid[g], g_stream[g]));
-    e->launches++;
-    CTD_CUDA(e, cudaMemcpyAsync(h_np + 2 * g, g_pending[g], 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, g_stream[g]));
-    ++g_waves[g];
-    return CTD_OK;
-  };
-  for (int g = 0; g < G; ++g) { s = launch_wave(g); if (s != CTD_OK) return s; }
-  while (!(g_done[0] && g_done[1])) {
-    for (int g = 0; g < G; ++g) {
-      if (g_done[g]) continue;
-      CTD_CUDA(e, cudaStreamSynchronize(g_stream[g]));
-      const uint32_t waiting = h_np[2 * g], yielded = h_np[2 * g + 1];
-      if (waiting == 0 && yielded == 0) { g_done[g] = true; continue; }
-      if (g_waves[g] > 2 * iterations + 4) { snprintf(e->err, sizeof(e->err), "ctd_mccfr_pred: wave limit"); return CTD_ECAP; }
-      if (waiting != 0) {
-        s = ctd_value_forward(e, g_n[g], e->d_pending + g_first[g], reward_weight, g_first[g], g_stream[g]);
-        if (s != CTD_OK) return s;
-      }
-      s = launch_wave(g);
-      if (s != CTD_OK) return s;
-    }
-  }
-  waves = (g_waves[0] > g_waves[1] ? g_waves[0] : g_waves[1]) - 1;
-  if (G == 2) {   // join: the engine's stream continues after both groups
-    CTD_CUDA(e, cudaEventRecord(e->ev_join, e->stream2));
-    CTD_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_join, 0));
-  }
-  CTD_CUDA(e, cudaEventRecord(e->ev1, e->stream));
-  if (results) CTD_CUDA(e, cudaMemcpyAsync(results, e->d_scratch, rb, cudaMemcpyDeviceToHost, e->stream));
-  if (trees_out) {
-    ctd_k_pack_trees<<<ctd_blocks(n_roots), CTD_BLOCK, 0, e->stream>>>(e->d_trees, stride, n_roots, mn, cc);
-    e->launches++;
-    CTD_CUDA(e, cudaGetLastError());
-    CTD_CUDA(e, cudaMemcpyAsync(trees_out, e->d_trees, need, cudaMemcpyDeviceToHost, e->stream));
-  }
-  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
-  if (elapsed_ms) CTD_CUDA(e, cudaEventElapsedTime(elapsed_ms, e->ev0, e->ev1));
-  if (waves_out) *waves_out = waves + 1;
-  return CTD_OK;
+  CtdSearch sp{n_roots, seed, iterations, ruleset, true, max_depth, reward_weight};
+  return ctd_search(e, sp, results, elapsed_ms, waves_out);
 }
 
 }  // extern "C"

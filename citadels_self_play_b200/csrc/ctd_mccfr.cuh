@@ -1,15 +1,24 @@
 // ctd_mccfr.cuh -- the reference's MCCFR tree search (algorithms/deep_mccfr.py `CFRNode`) on a flat node pool.
 //
 // One tree is private to one root state (algorithms/deep_mccfr.py:27-29) and is grown by sequential dependent
-// sampling, so a tree is owned by one warp and many trees run side by side.  A tree is one contiguous HBM block:
+// sampling, so a tree is owned by one warp and many trees run side by side.  The reference never refuses a root (its
+// trees are Python objects on the heap), so tree memory is not a fixed block per root: every tree takes what it needs
+// from ONE arena in HBM shared by all trees of a launch (a bump pointer advanced with atomicAdd, 64-byte units):
 //
-//   CtdTreeHdr | CtdNode[max_nodes] | CtdChild[child_cap] | double[arr_cap]
+//   CtdTreeHdr hdrs[n_roots]      256 B each: counters, status, the chunk table of the tree's nodes
+//   arena                         node chunks  : chunk 0 holds the first n0 = 2^k nodes of a tree (k chosen from the
+//                                                iteration budget so that the typical tree never leaves it), chunk c >= 1
+//                                                the nodes [n0 << (c-1), n0 << c) -- node i of chunk 0 is one multiply
+//                                                away, later chunks go through the table in the header
+//                                 node arrays  : one allocation per expanded node: CtdChild[child_cap] then 3 x K doubles
+//                                                (R | s | C; role-pick nodes 3 x 6 x 10, stored [player][child] like the
+//                                                reference after its transposes, :129-131); small ones are cut from
+//                                                16 KB slabs the tree owns, so a tree's arrays stay together
 //
-// CtdNode = 128 B header (parent, depth, player, flags, V[6], P[6], pred[6]) + the 256 B packed game record
-// + the 592 B knowledge block of the searching player.  A child entry is (option descriptor, node index);
-// regrets / strategy / cumulative strategy of an expanded node are 3 x K doubles in the array arena
-// (role-pick nodes: 3 x 6 x 10, stored [player][child] like the reference after its transposes, :129-131).
-// Everything is fp64 like the reference's numpy arrays.
+// CtdNode = 160 B header (parent, depth, player, flags, V[6], P[6], pred[6]) + the 592 B knowledge block of the searching
+// player + a verbatim snapshot of the working record.  Everything numeric is fp64 like the reference's numpy arrays.
+// Trees leave the device through ctd_tree_export: a compact block (header | nodes with their 256-byte packed game
+// records | children | arrays) whose offsets are local to the block.
 //
 // Chance: one Philox stream per tree (stream word 1, keyed by (seed, root id)); the mapping of the reference's
 // random calls onto it is written out in oracle/mccfr_oracle.py and is the same here.
@@ -17,11 +26,14 @@
 #include <math.h>
 #include "ctd_engine.cuh"
 
-#define CTD_MCCFR_OPT_CAP 4096 /* legal options of one state that expansion can materialise (preset max 59,
-                                  classic Magician hands reach ~1600, the Cardinal ~2600); the buffer lives in HBM scratch, one per warp */
+#define CTD_MCCFR_OPT_CAP 4096 /* descriptors in the per-warp option buffer (HBM scratch).  Longer lists (classic Magician hands
+                                  reach ~1600 options, the Cardinal ~8000) are enumerated straight into the arena */
 
 enum { CTD_NF_ROLE_PICK = 1, CTD_NF_TERMINAL = 2, CTD_NF_HAS_PRED = 4 };
-enum { CTD_TREE_OK = 0, CTD_TREE_TERMINAL_ROOT = 1, CTD_TREE_EPOOL = 2, CTD_TREE_EENGINE = 4, CTD_TREE_EOPTS = 8 };
+// tree status bits.  TERMINAL_ROOT and REF_RAISE are outcomes the reference has too (run_mccfr raises ValueError on a terminal
+// root; an exception inside the rules code propagates out of cfr_train); EPOOL and EENGINE are this engine's own limits.
+enum { CTD_TREE_OK = 0, CTD_TREE_TERMINAL_ROOT = 1, CTD_TREE_EPOOL = 2, CTD_TREE_EENGINE = 4, CTD_TREE_EOPTS = 8,
+       CTD_TREE_REF_RAISE = 16 };
 
 struct CtdNode {
   int32_t parent;
@@ -30,8 +42,8 @@ struct CtdNode {
   uint8_t flags;
   uint32_t n_children;
   uint32_t child_cap;
-  uint32_t child_off;  // first CtdChild
-  uint32_t arr_off;    // R | s | C
+  uint32_t child_off;  // arena offset (64-byte units) of CtdChild[child_cap] followed by the node's doubles; export: index of the first child
+  uint32_t arr_off;    // export only: index of the node's first double in the block's array section
   uint32_t visits;
   uint32_t pad0;
   double V[6];         // node_value
@@ -40,12 +52,19 @@ struct CtdNode {
   uint8_t order[6];    // game.turn_orders_for_roles (role-pick nodes weight their strategy by it)
   uint8_t gstate;      // game.gamestate.state
   int8_t winner;       // game winner (terminal nodes)
-  ctd_state game;      // packed record: filled by ctd_tree_pack_nodes when the tree is exported, not on the hot path
   CtdKnow know;
   uint8_t snap[CTD_SNAP_BYTES];  // the working record verbatim: node <-> shared memory is a plain vector copy
 };
-static_assert(sizeof(CtdNode) == 160 + 256 + 592 + CTD_SNAP_BYTES, "CtdNode layout");
-static_assert(offsetof(CtdNode, game) % 16 == 0 && offsetof(CtdNode, know) % 16 == 0 && offsetof(CtdNode, snap) % 16 == 0, "CtdNode alignment");
+static_assert(sizeof(CtdNode) == 160 + 592 + CTD_SNAP_BYTES, "CtdNode layout");
+static_assert(offsetof(CtdNode, know) % 16 == 0 && offsetof(CtdNode, snap) % 16 == 0 && sizeof(CtdNode) % 16 == 0, "CtdNode alignment");
+
+// a node as it leaves the device (ctd_tree_export): the same 160-byte header, the 256-byte packed game record, the knowledge block
+struct CtdNodeOut {
+  uint8_t head[160];
+  ctd_state game;
+  CtdKnow know;
+};
+static_assert(sizeof(CtdNodeOut) == 160 + 256 + 592, "CtdNodeOut layout");
 
 struct CtdChild {
   uint64_t desc;
@@ -53,10 +72,14 @@ struct CtdChild {
   uint32_t pad;
 };
 
+#define CTD_TREE_MAX_CHUNKS 24
+#define CTD_ARENA_UNIT 64u
+#define CTD_SLAB_UNITS 256u /* 16 KB */
 struct CtdTreeHdr {
-  uint32_t n_nodes, max_nodes;
-  uint32_t child_used, child_cap;
-  uint32_t arr_used, arr_cap;
+  uint32_t n_nodes;
+  uint32_t n0_log2;      // chunk 0 holds 2^n0_log2 nodes
+  uint32_t child_used;   // child slots reserved so far (what an export block needs)
+  uint32_t arr_used;     // doubles reserved so far
   uint32_t status;
   uint32_t iterations;
   uint32_t rng_draws;
@@ -65,22 +88,45 @@ struct CtdTreeHdr {
   uint8_t has_model;
   uint8_t phase;         // deep MCCFR walk: 0 not started, 1 walking, 2 waiting for a leaf value, 3 finished
   uint64_t gid;
-  uint8_t used_cards[76];  // Game.used_cards in deal order (game/game.py:424); constant over the tree
   uint32_t cur_node;     // node the walk stands on (deep MCCFR is resumed across kernel launches)
+  uint32_t slab_off;     // the tree's current slab for small allocations (arena units) and what is left of it
+  uint32_t slab_left;
+  uint32_t pad0;
+  uint8_t* arena;        // base of the arena this tree lives in
+  uint8_t used_cards[80];  // Game.used_cards in deal order (game/game.py:424), 76 used; constant over the tree
+  uint32_t chunk[CTD_TREE_MAX_CHUNKS];  // arena offset of node chunk c, 0 = not allocated yet
+  uint32_t pad1[4];
 };
-static_assert(sizeof(CtdTreeHdr) == 128 && offsetof(CtdTreeHdr, used_cards) % 16 == 0, "CtdTreeHdr layout");
+static_assert(sizeof(CtdTreeHdr) == 256 && offsetof(CtdTreeHdr, used_cards) % 16 == 0, "CtdTreeHdr layout");
 
-CTD_HD inline size_t ctd_tree_bytes(uint32_t max_nodes, uint32_t child_cap, uint32_t arr_cap) {
-  return sizeof(CtdTreeHdr) + (size_t)max_nodes * sizeof(CtdNode) + (size_t)child_cap * sizeof(CtdChild) +
-         (size_t)arr_cap * sizeof(double);
+// header of an export block (the first 128 bytes; numpy mirror: layout.TREE_HDR_DTYPE)
+struct CtdTreeHdrOut {
+  uint32_t n_nodes, max_nodes, child_used, child_cap, arr_used, arr_cap, status, iterations, rng_draws;
+  uint8_t viewer, training, has_model, phase;
+  uint64_t gid;
+  uint8_t used_cards[76];
+  uint32_t cur_node;
+};
+static_assert(sizeof(CtdTreeHdrOut) == 128, "CtdTreeHdrOut layout");
+CTD_HD inline size_t ctd_tree_export_bytes(uint32_t n_nodes, uint32_t child_used, uint32_t arr_used) {
+  return sizeof(CtdTreeHdrOut) + (size_t)n_nodes * sizeof(CtdNodeOut) + (size_t)child_used * sizeof(CtdChild) +
+         (size_t)arr_used * sizeof(double);
 }
+
+// the arena all trees of a launch allocate from
+struct CtdArena {
+  uint8_t* base;
+  unsigned long long* used;  // bump pointer, CTD_ARENA_UNIT units; starts at 1 so that offset 0 means "none"
+  unsigned long long cap;    // units
+};
 
 // a tree plus the on-chip working set of the warp that grows it
 struct CtdTree {
   CtdTreeHdr* hdr;
-  CtdNode* nodes;
-  CtdChild* children;
-  double* arr;
+  CtdNode* nodes0;  // chunk 0
+  uint32_t n0;      // nodes in chunk 0
+  uint8_t* abase;   // == hdr->arena
+  CtdArena ar;
   CtdWork* w;       // working game (shared memory on the device)
   CtdKnow* kn;      // working knowledge of the viewer
   uint64_t* opts;   // CTD_MCCFR_OPT_CAP descriptors
@@ -91,7 +137,7 @@ struct CtdTree {
 // address spaces of a tree's parts on the device: working set in shared memory, the tree block in HBM
 #define CTD_TREE_SPACES(T)                                                                                  \
   CTD_ASSUME_SHARED((T).w); CTD_ASSUME_SHARED((T).kn); CTD_ASSUME_SHARED((T).stage);                         \
-  CTD_ASSUME_GLOBAL((T).hdr); CTD_ASSUME_GLOBAL((T).nodes); CTD_ASSUME_GLOBAL((T).children); CTD_ASSUME_GLOBAL((T).arr); \
+  CTD_ASSUME_GLOBAL((T).hdr); CTD_ASSUME_GLOBAL((T).nodes0); CTD_ASSUME_GLOBAL((T).abase);                    \
   CTD_ASSUME_GLOBAL((T).opts)
 
 // 16-byte vector copy (both pointers 16-byte aligned, bytes a multiple of 16): the tree lives in HBM and its records
@@ -153,6 +199,66 @@ __device__ __forceinline__ void ctd_copy_g2s(void* sdst, const void* gsrc) {
 #endif
 
 CTD_HD inline double ctd_uniform(CtdWork& w) { return (double)ctd_u32(w) / 4294967296.0; }
+
+// ------------------------------------------------------------------------------------------ tree memory
+CTD_HD inline int ctd_clz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __clz((int)x);
+#else
+  return x ? __builtin_clz(x) : 32;
+#endif
+}
+// node i of a tree: chunk 0 directly, later chunks through the table in the header
+CTD_HD CTD_NI inline CtdNode* ctd_node_far(const CtdTree& T, uint32_t i) {
+  const uint32_t c = 32u - (uint32_t)ctd_clz32(i >> T.hdr->n0_log2);   // >= 1; chunk c holds [n0 << (c-1), n0 << c)
+  return (CtdNode*)(T.abase + (size_t)T.hdr->chunk[c] * CTD_ARENA_UNIT) + (i - (T.n0 << (c - 1)));
+}
+CTD_HD inline CtdNode& ctd_node(const CtdTree& T, uint32_t i) { return i < T.n0 ? T.nodes0[i] : *ctd_node_far(T, i); }
+CTD_HD inline CtdChild* ctd_kids(const CtdTree& T, const CtdNode& n) { return (CtdChild*)(T.abase + (size_t)n.child_off * CTD_ARENA_UNIT); }
+
+// `units` arena units, or 0 when the arena is exhausted.  On the device the active lanes of the warp (one lane, or all 32
+// converged on the same scalar code) make ONE allocation between them.
+CTD_HD inline uint32_t ctd_arena_alloc(CtdTree& T, uint32_t units) {
+  unsigned long long off;
+#if defined(__CUDA_ARCH__)
+  const unsigned m = __activemask();
+  const int leader = __ffs(m) - 1;
+  off = 0;
+  if ((int)(threadIdx.x & 31) == leader) off = atomicAdd(T.ar.used, (unsigned long long)units);
+  off = __shfl_sync(m, off, leader);
+#else
+  off = *T.ar.used;
+  *T.ar.used += units;
+#endif
+  if (off + units > T.ar.cap || off + units > 0xFFFFFFFFull) return 0;
+  return (uint32_t)off;
+}
+// small allocations come out of a slab the tree owns
+CTD_HD CTD_NI inline uint32_t ctd_tree_alloc(CtdTree& T, size_t bytes) {
+  CtdTreeHdr& h = *T.hdr;
+  const uint32_t units = (uint32_t)((bytes + CTD_ARENA_UNIT - 1) / CTD_ARENA_UNIT);
+  if (units > CTD_SLAB_UNITS / 4) return ctd_arena_alloc(T, units);
+  uint32_t left = h.slab_left, off = h.slab_off;
+  if (left < units) {
+    off = ctd_arena_alloc(T, CTD_SLAB_UNITS);
+    if (off == 0) return 0;
+    left = CTD_SLAB_UNITS;
+  }
+#if defined(__CUDA_ARCH__)
+  __syncwarp(__activemask());   // every lane has read the old slab state before any lane writes the new one
+#endif
+  h.slab_off = off + units;
+  h.slab_left = left - units;
+  return off;
+}
+// attach the working set to a tree block (the header was initialised by ctd_tree_init or by an earlier launch)
+CTD_HD inline void ctd_tree_attach(CtdTree& T, CtdTreeHdr* hdr, const CtdArena& ar) {
+  T.hdr = hdr;
+  T.ar = ar;
+  T.abase = hdr->arena;
+  T.n0 = 1u << hdr->n0_log2;
+  T.nodes0 = (CtdNode*)(T.abase + (size_t)hdr->chunk[0] * CTD_ARENA_UNIT);
+}
 
 // ------------------------------------------------------------------------------------------ determinisation
 // Game.sample_private_information (game/game.py:215-242) and its helpers (:183-213, :245-357).  `w`/`k` are the hypothetical game; k.viewer is player_character.
@@ -277,15 +383,6 @@ CTD_HD inline void ctd_node_store(CtdTree& T, CtdNode& n) {
   n.gstate = w.state;
   n.winner = w.winner;
 }
-// export form: the 256-byte packed record of a node (tests, facade, ctd_mccfr trees_out)
-CTD_HD inline void ctd_node_pack(CtdTree& T, CtdNode& n) {
-  CtdWork& w = *T.w;
-  ctd_copy16(&w, n.snap, CTD_SNAP_BYTES);
-  w.draws = 0; w.tape_pos = 0; w.steps = 0;
-  w.g0 = (uint32_t)T.hdr->gid; w.g1 = (uint32_t)(T.hdr->gid >> 32);
-  ctd_pack(w, T.stage);
-  ctd_copy16(&n.game, T.stage, (int)sizeof(ctd_state));
-}
 CTD_HD inline void ctd_node_load(CtdTree& T, const CtdNode& n) {
   // chance state lives in the working record and must survive a load
   CtdWork& w = *T.w;
@@ -318,35 +415,52 @@ CTD_HD CTD_NI inline void ctd_skip_false_choice(CtdTree& T) {
 CTD_HD CTD_NI inline int ctd_new_node(CtdTree& T, int parent, int depth) {
   CTD_TREE_SPACES(T);
   CtdTreeHdr& h = *T.hdr;
-  if (h.n_nodes >= h.max_nodes) { h.status |= CTD_TREE_EPOOL; return -1; }
+  const uint32_t idx = h.n_nodes;
+  if (idx >= T.n0) {   // beyond chunk 0: the first node of a chunk allocates it
+    const uint32_t c = 32u - (uint32_t)ctd_clz32(idx >> h.n0_log2);
+    if (c >= CTD_TREE_MAX_CHUNKS) { h.status |= CTD_TREE_EPOOL; return -1; }
+    if (idx == (T.n0 << (c - 1))) {
+      const size_t bytes = (size_t)(T.n0 << (c - 1)) * sizeof(CtdNode);
+      const uint32_t off = ctd_arena_alloc(T, (uint32_t)((bytes + CTD_ARENA_UNIT - 1) / CTD_ARENA_UNIT));
+      if (off == 0) { h.status |= CTD_TREE_EPOOL; return -1; }
+#if defined(__CUDA_ARCH__)
+      __syncwarp(__activemask());
+#endif
+      h.chunk[c] = off;
+    }
+  }
   ctd_skip_false_choice(T);
-  if (T.w->err || T.kn->err) { h.status |= CTD_TREE_EENGINE; }
-  int idx = (int)h.n_nodes++;
-  CtdNode& n = T.nodes[idx];
+  if ((T.w->err | T.kn->err) & CTD_ERR_OVERFLOW) h.status |= CTD_TREE_EENGINE;
+  if ((T.w->err | T.kn->err) & ~CTD_ERR_OVERFLOW) h.status |= CTD_TREE_REF_RAISE;
+  h.n_nodes = idx + 1;
+  CtdNode& n = ctd_node(T, idx);
   n.parent = parent;
   n.depth = (uint16_t)depth;
   n.player = T.w->player;
   n.flags = (uint8_t)((T.w->state == 0 ? CTD_NF_ROLE_PICK : 0) | ((T.w->gflags & 2) ? CTD_NF_TERMINAL : 0));
   n.n_children = 0; n.child_cap = 0; n.child_off = 0; n.arr_off = 0; n.visits = 0; n.pad0 = 0;
-  // n.game (the 256-byte packed form) is written by the export pass only (ctd_node_pack)
   CTD_LOOP for (int i = 0; i < 6; ++i) { n.V[i] = 0.0; n.P[i] = 0.0; n.pred[i] = 0.f; }
   ctd_node_store(T, n);
-  return idx;
+  return (int)idx;
 }
 
+// room for `kids` children and `doubles` array entries of node n (one allocation: children first, then the doubles)
 CTD_HD inline bool ctd_reserve(CtdTree& T, CtdNode& n, uint32_t kids, uint32_t doubles) {
   CtdTreeHdr& h = *T.hdr;
-  if (h.child_used + kids > h.child_cap || h.arr_used + doubles > h.arr_cap) { h.status |= CTD_TREE_EPOOL; return false; }
-  n.child_off = h.child_used; n.child_cap = kids; h.child_used += kids;
-  n.arr_off = h.arr_used; h.arr_used += doubles;
+  const uint32_t off = ctd_tree_alloc(T, (size_t)kids * sizeof(CtdChild) + (size_t)doubles * sizeof(double));
+  if (off == 0) { h.status |= CTD_TREE_EPOOL; return false; }
+  n.child_off = off; n.child_cap = kids;
+  h.child_used += kids;
+  h.arr_used += doubles;
+  double* a = (double*)(ctd_kids(T, n) + kids);
 #if defined(__CUDA_ARCH__)
   if (__activemask() == 0xFFFFFFFFu) {   // converged warp: the lanes split the zero-fill
-    for (uint32_t i = threadIdx.x & 31u; i < doubles; i += 32u) T.arr[n.arr_off + i] = 0.0;
+    for (uint32_t i = threadIdx.x & 31u; i < doubles; i += 32u) a[i] = 0.0;
     __syncwarp();
     return true;
   }
 #endif
-  CTD_LOOP for (uint32_t i = 0; i < doubles; ++i) T.arr[n.arr_off + i] = 0.0;
+  CTD_LOOP for (uint32_t i = 0; i < doubles; ++i) a[i] = 0.0;
   return true;
 }
 
@@ -368,8 +482,8 @@ CTD_HD inline void ctd_tree_stage_used(CtdTree& T) { ctd_copy16(T.scratch + 256,
 // "sample if it is not the same player's turn as in the parent" (:139-140, :157-158)
 CTD_HD inline void ctd_maybe_sample(CtdTree& T, const CtdNode& n) {
   bool root = n.parent < 0;
-  if (root || T.w->player != T.nodes[n.parent].player) {
-    bool role_sample = root ? false : T.nodes[n.parent].gstate != 0;
+  if (root || T.w->player != ctd_node(T, n.parent).player) {
+    bool role_sample = root ? false : ctd_node(T, n.parent).gstate != 0;
     ctd_sample_private(*T.w, *T.kn, T.scratch + 256, role_sample, T.scratch);
   }
 }
@@ -377,7 +491,7 @@ CTD_HD inline void ctd_maybe_sample(CtdTree& T, const CtdNode& n) {
 // CFRNode.expand (:93-179)
 CTD_HD CTD_NI inline void ctd_expand(CtdTree& T, int ni) {
   CTD_TREE_SPACES(T);
-  CtdNode& n = T.nodes[ni];
+  CtdNode& n = ctd_node(T, ni);
   CtdWork& w = *T.w;
   CtdKnowSet ks{T.kn, 1};
   const int viewer = T.hdr->viewer;
@@ -385,6 +499,7 @@ CTD_HD CTD_NI inline void ctd_expand(CtdTree& T, int ni) {
     // expand_role_pick (:102-131): ten uniformly random role-pick phases, the stored option is the last pick
     n.flags |= CTD_NF_ROLE_PICK;
     if (!ctd_reserve(T, n, 10, 180)) return;
+    CtdChild* kids = ctd_kids(T, n);
     CTD_LOOP for (int rep = 0; rep < 10; ++rep) {
       ctd_node_load(T, n);
       uint64_t d = 0;
@@ -397,7 +512,7 @@ CTD_HD CTD_NI inline void ctd_expand(CtdTree& T, int ni) {
       }
       int ci = ctd_new_node(T, ni, n.depth + 1);
       if (ci < 0) return;
-      T.children[n.child_off + n.n_children] = CtdChild{d, (uint32_t)ci, 0};
+      kids[n.n_children] = CtdChild{d, (uint32_t)ci, 0};
       ++n.n_children;
     }
   } else if (n.player == viewer && n.n_children == 0) {
@@ -405,32 +520,43 @@ CTD_HD CTD_NI inline void ctd_expand(CtdTree& T, int ni) {
     ctd_node_load(T, n);
     CtdEmit e{T.opts, CTD_MCCFR_OPT_CAP, 0, 0xFFFFFFFFu, 0};
     ctd_enumerate(w, e, T.kn);
-    if (e.n > CTD_MCCFR_OPT_CAP) { T.hdr->status |= CTD_TREE_EOPTS; return; }
-    if (e.n == 0) { T.hdr->status |= CTD_TREE_EENGINE; return; }
+    if (e.n == 0) { T.hdr->status |= w.err ? CTD_TREE_REF_RAISE : CTD_TREE_EENGINE; return; }
     // the reference enumerates on the node's own game (:134): the Scholar's list shrinks there, and every child is a copy of that
     if (w.state == 9) CTD_COPY_S2G(n.snap, &w, CTD_SNAP_BYTES);
     const uint32_t K = e.n;
     if (!ctd_reserve(T, n, K, 3 * K)) return;
+    CtdChild* kids = ctd_kids(T, n);
     // the option list must survive the children's own enumerations: park it in the child table
-    CTD_LOOP for (uint32_t i = 0; i < K; ++i) T.children[n.child_off + i] = CtdChild{T.opts[i], 0, 0};
+    if (K <= CTD_MCCFR_OPT_CAP) {
+      CTD_LOOP for (uint32_t i = 0; i < K; ++i) kids[i] = CtdChild{T.opts[i], 0, 0};
+    } else {
+      // a list longer than the option buffer (pure enumerations only: the Magician's discards, the Cardinal's exchanges): enumerate
+      // once more straight into the node's still unused doubles, move it over, zero the doubles again
+      uint64_t* big = (uint64_t*)(kids + K);
+      CtdEmit e2{big, K, 0, 0xFFFFFFFFu, 0};
+      ctd_enumerate(w, e2, T.kn);
+      CTD_LOOP for (uint32_t i = 0; i < K; ++i) kids[i] = CtdChild{big[i], 0, 0};
+      CTD_LOOP for (uint32_t i = 0; i < K; ++i) big[i] = 0;   // 0.0
+    }
     CTD_LOOP for (uint32_t i = 0; i < K; ++i) {
       ctd_node_load(T, n);
       ctd_maybe_sample(T, n);
-      uint64_t d = ctd_carried_form(w, T.children[n.child_off + i].desc);
+      uint64_t d = ctd_carried_form(w, kids[i].desc);
       ctd_apply(w, d, ks);
       int ci = ctd_new_node(T, ni, n.depth + 1);
       if (ci < 0) return;
-      T.children[n.child_off + i] = CtdChild{d, (uint32_t)ci, 0};
+      kids[i] = CtdChild{d, (uint32_t)ci, 0};
       ++n.n_children;
     }
   } else if (n.player != viewer && n.n_children < 10) {
     // expand_for_opponents (:153-179): one uniformly sampled option, kept only if it is new
     if (n.child_cap == 0 && !ctd_reserve(T, n, 10, 30)) return;
+    CtdChild* kids = ctd_kids(T, n);
     ctd_node_load(T, n);
     ctd_maybe_sample(T, n);
     CtdEmit e{T.opts, CTD_MCCFR_OPT_CAP, 0, 0xFFFFFFFFu, 0};
     ctd_enumerate(w, e, T.kn);
-    if (e.n == 0) { T.hdr->status |= CTD_TREE_EENGINE; return; }
+    if (e.n == 0) { T.hdr->status |= w.err ? CTD_TREE_REF_RAISE : CTD_TREE_EENGINE; return; }
     uint32_t pick = ctd_randbelow(w, e.n);
     uint64_t d;
     if (pick < CTD_MCCFR_OPT_CAP) d = T.opts[pick];
@@ -438,30 +564,31 @@ CTD_HD CTD_NI inline void ctd_expand(CtdTree& T, int ni) {
     d = ctd_carried_form(w, d);
     ctd_apply(w, d, ks);
     bool seen = false;
-    CTD_LOOP for (uint32_t i = 0; i < n.n_children; ++i) seen |= T.children[n.child_off + i].desc == d;
+    CTD_LOOP for (uint32_t i = 0; i < n.n_children; ++i) seen |= kids[i].desc == d;
     if (!seen) {
       int ci = ctd_new_node(T, ni, n.depth + 1);
       if (ci < 0) return;
-      T.children[n.child_off + n.n_children] = CtdChild{d, (uint32_t)ci, 0};
+      kids[n.n_children] = CtdChild{d, (uint32_t)ci, 0};
       ++n.n_children;
     }
   }
-  if (w.err || T.kn->err) T.hdr->status |= CTD_TREE_EENGINE;
+  if ((w.err | T.kn->err) & CTD_ERR_OVERFLOW) T.hdr->status |= CTD_TREE_EENGINE;
+  if ((w.err | T.kn->err) & ~CTD_ERR_OVERFLOW) T.hdr->status |= CTD_TREE_REF_RAISE;
 }
 
-// arrays of a node: vector nodes R[K] s[K] C[K] with K = child_cap; role-pick nodes [6][10] each
-CTD_HD inline double* ctd_R(CtdTree& T, const CtdNode& n) { return T.arr + n.arr_off; }
-CTD_HD inline double* ctd_S(CtdTree& T, const CtdNode& n) {
-  return T.arr + n.arr_off + ((n.flags & CTD_NF_ROLE_PICK) ? 60 : n.child_cap);
+// arrays of a node: vector nodes R[K] s[K] C[K] with K = child_cap; role-pick nodes [6][10] each.  They follow the child table.
+CTD_HD inline double* ctd_R(const CtdTree& T, const CtdNode& n) { return (double*)(ctd_kids(T, n) + n.child_cap); }
+CTD_HD inline double* ctd_S(const CtdTree& T, const CtdNode& n) {
+  return ctd_R(T, n) + ((n.flags & CTD_NF_ROLE_PICK) ? 60 : n.child_cap);
 }
-CTD_HD inline double* ctd_C(CtdTree& T, const CtdNode& n) {
-  return T.arr + n.arr_off + 2 * ((n.flags & CTD_NF_ROLE_PICK) ? 60 : n.child_cap);
+CTD_HD inline double* ctd_C(const CtdTree& T, const CtdNode& n) {
+  return ctd_R(T, n) + 2 * ((n.flags & CTD_NF_ROLE_PICK) ? 60 : n.child_cap);
 }
 
 // CFRNode.update_strategy (:292-319)
 CTD_HD CTD_NI inline void ctd_update_strategy(CtdTree& T, int ni) {
   CTD_TREE_SPACES(T);
-  CtdNode& n = T.nodes[ni];
+  CtdNode& n = ctd_node(T, ni);
   const int K = (int)n.n_children;
   if (K == 0) return;  // empty arrays: numpy no-ops
   double *R = ctd_R(T, n), *S = ctd_S(T, n), *C = ctd_C(T, n);
@@ -491,41 +618,51 @@ CTD_HD CTD_NI inline void ctd_update_strategy(CtdTree& T, int ni) {
 // Inverse CDF on one uniform draw: cdf = cumsum(p); cdf /= cdf[-1]; first index with u < cdf.
 CTD_HD CTD_NI inline int ctd_action_choice(CtdTree& T, int ni) {
   CTD_TREE_SPACES(T);
-  CtdNode& n = T.nodes[ni];
+  CtdNode& n = ctd_node(T, ni);
   const int K = (int)n.n_children;
   double* C = ctd_C(T, n);
-  double* cdf = (double*)T.opts;  // K <= CTD_MCCFR_OPT_CAP doubles; the option buffer is free here
+  const CtdChild* kids = ctd_kids(T, n);
   if (!(n.flags & CTD_NF_ROLE_PICK)) {
     double cs = 0.0;
     CTD_LOOP for (int a = 0; a < K; ++a) cs += C[a];
+    // cdf[a] = running sum of C[a] / cs; the draw is compared with cdf[a] / cdf[K-1].  No buffer: the running sum is formed
+    // twice with the same operations in the same order (K is unbounded: the Cardinal expands thousands of children)
+    double last = 0.0;
+    CTD_LOOP for (int a = 0; a < K; ++a) last += C[a] / cs;
+    const double u = ctd_uniform(*T.w);
     double run = 0.0;
-    CTD_LOOP for (int a = 0; a < K; ++a) { run += C[a] / cs; cdf[a] = run; }
-  } else {
-    // weighted_average_strategy (:51-65): weight 6-i for the i-th picker, divided by sum(order) = 15
-    double avg[10];
-    double s = 0.0;
-    CTD_LOOP for (int a = 0; a < 10; ++a) {
-      double v = 0.0;
-      CTD_LOOP for (int i = 0; i < 6; ++i) v += C[n.order[i] * 10 + a] * (double)(6 - i);
-      avg[a] = v / 15.0;
+    int i = 0;
+    CTD_LOOP for (; i < K - 1; ++i) {
+      run += C[i] / cs;
+      if (!(run / last <= u)) break;
     }
-    CTD_LOOP for (int a = 0; a < 10; ++a) s += avg[a];
-    double run = 0.0;
-    CTD_LOOP for (int a = 0; a < 10; ++a) { run += (s == 0.0 ? 1.0 / 10 : avg[a] / s); cdf[a] = run; }
+    return (int)kids[i].node;
   }
+  // weighted_average_strategy (:51-65): weight 6-i for the i-th picker, divided by sum(order) = 15
+  double cdf[10];
+  double avg[10];
+  double s = 0.0;
+  CTD_LOOP for (int a = 0; a < 10; ++a) {
+    double v = 0.0;
+    CTD_LOOP for (int i = 0; i < 6; ++i) v += C[n.order[i] * 10 + a] * (double)(6 - i);
+    avg[a] = v / 15.0;
+  }
+  CTD_LOOP for (int a = 0; a < 10; ++a) s += avg[a];
+  double run = 0.0;
+  CTD_LOOP for (int a = 0; a < 10; ++a) { run += (s == 0.0 ? 1.0 / 10 : avg[a] / s); cdf[a] = run; }
   const double last = cdf[K - 1];
   const double u = ctd_uniform(*T.w);
   int i = 0;
   while (i < K - 1 && cdf[i] / last <= u) ++i;
-  return (int)T.children[n.child_off + i].node;
+  return (int)kids[i].node;
 }
 
 // CFRNode.backpropagate + update_regrets (:231-256, :276-290), iterative instead of recursive
 CTD_HD CTD_NI inline void ctd_backpropagate(CtdTree& T, int ni, const double reward[6]) {
   CTD_TREE_SPACES(T);
   const bool training = T.hdr->training, model = T.hdr->has_model;
-  for (int cur = ni; cur >= 0; cur = T.nodes[cur].parent) {
-    CtdNode& n = T.nodes[cur];
+  for (int cur = ni; cur >= 0; cur = ctd_node(T, cur).parent) {
+    CtdNode& n = ctd_node(T, cur);
     double vs = 0.0;
     CTD_LOOP for (int i = 0; i < 6; ++i) vs += n.V[i];
     if (training || vs == 0.0 || !model) CTD_LOOP for (int i = 0; i < 6; ++i) n.V[i] += reward[i];
@@ -536,18 +673,19 @@ CTD_HD CTD_NI inline void ctd_backpropagate(CtdTree& T, int ni, const double rew
     const int K = (int)n.n_children;
     if (K == 0) continue;
     double* R = ctd_R(T, n);
+    const CtdChild* kids = ctd_kids(T, n);
     if (!(n.flags & CTD_NF_ROLE_PICK)) {
       const int pl = n.player;
       double m = -1e300;
       CTD_LOOP for (int a = 0; a < K; ++a) {
-        double v = T.nodes[T.children[n.child_off + a].node].P[pl];
+        double v = ctd_node(T, kids[a].node).P[pl];
         m = v > m ? v : m;
       }
-      CTD_LOOP for (int a = 0; a < K; ++a) R[a] += m - T.nodes[T.children[n.child_off + a].node].P[pl];
+      CTD_LOOP for (int a = 0; a < K; ++a) R[a] += m - ctd_node(T, kids[a].node).P[pl];
     } else {
       // max over PLAYERS (axis=0 after the transpose, :248-251)
       CTD_LOOP for (int a = 0; a < 10; ++a) {
-        const double* cp = T.nodes[T.children[n.child_off + a].node].P;
+        const double* cp = ctd_node(T, kids[a].node).P;
         double m = cp[0];
         CTD_LOOP for (int p = 1; p < 6; ++p) m = cp[p] > m ? cp[p] : m;
         CTD_LOOP for (int p = 0; p < 6; ++p) R[p * 10 + a] += m - cp[p];
@@ -558,31 +696,37 @@ CTD_HD CTD_NI inline void ctd_backpropagate(CtdTree& T, int ni, const double rew
 
 // CFRNode.cfr_train (:187-205) / cfr_pred without the model call (:207-229 needs pred, see ctd_kernels.cu).
 // Initialise the tree from the working game (root state + knowledge already in T.w / T.kn).
-CTD_HD CTD_NI inline void ctd_tree_init(CtdTree& T, uint32_t max_nodes, uint32_t child_cap, uint32_t arr_cap, int viewer,
+CTD_HD CTD_NI inline void ctd_tree_init(CtdTree& T, CtdTreeHdr* hdr, const CtdArena& ar, uint32_t n0_log2, int viewer,
                                         uint64_t gid, bool training, bool has_model) {
-  
-  CtdTreeHdr& h = *T.hdr;
-  h.n_nodes = 0; h.max_nodes = max_nodes; h.child_used = 0; h.child_cap = child_cap; h.arr_used = 0; h.arr_cap = arr_cap;
+  CtdTreeHdr& h = *hdr;
+  h.n_nodes = 0; h.n0_log2 = n0_log2; h.child_used = 0; h.arr_used = 0;
   h.status = 0; h.iterations = 0; h.rng_draws = 0; h.viewer = (uint8_t)viewer; h.training = training; h.has_model = has_model;
-  h.phase = 0; h.cur_node = 0; h.gid = gid;
+  h.phase = 0; h.cur_node = 0; h.gid = gid; h.slab_off = 0; h.slab_left = 0; h.pad0 = 0; h.arena = ar.base;
+  CTD_LOOP for (int c = 0; c < CTD_TREE_MAX_CHUNKS; ++c) h.chunk[c] = 0;
+  T.hdr = hdr; T.ar = ar; T.abase = ar.base; T.n0 = 1u << n0_log2; T.nodes0 = nullptr;
+  const size_t bytes = (size_t)T.n0 * sizeof(CtdNode);
+  const uint32_t off = ctd_arena_alloc(T, (uint32_t)((bytes + CTD_ARENA_UNIT - 1) / CTD_ARENA_UNIT));
+  if (off == 0) { h.status = CTD_TREE_EPOOL; return; }
+  h.chunk[0] = off;
+  T.nodes0 = (CtdNode*)(T.abase + (size_t)off * CTD_ARENA_UNIT);
   ctd_new_node(T, -1, 0);  // the root constructor runs skip_false_choice on the caller's game (:19-20)
-  if (T.nodes[0].flags & CTD_NF_TERMINAL) h.status |= CTD_TREE_TERMINAL_ROOT;
+  if (ctd_node(T, 0).flags & CTD_NF_TERMINAL) h.status |= CTD_TREE_TERMINAL_ROOT;
   h.rng_draws = T.w->draws;
 }
 
-// run `iters` iterations of the pure-MCCFR loop; returns the node the walk is standing on
+// run `iters` iterations of the pure-MCCFR loop
 CTD_HD CTD_NI inline void ctd_cfr_train(CtdTree& T, uint32_t iters) {
   CTD_TREE_SPACES(T);
   CtdTreeHdr& h = *T.hdr;
-  if (h.status & CTD_TREE_TERMINAL_ROOT) return;
+  if ((h.status & CTD_TREE_TERMINAL_ROOT) || h.n_nodes == 0) return;
   ctd_expand(T, 0);
   int node = 0;
   for (uint32_t it = 0; it < iters && !(h.status & ~CTD_TREE_TERMINAL_ROOT); ++it) {
     ctd_update_strategy(T, node);
     node = ctd_action_choice(T, node);
-    if (T.nodes[node].flags & CTD_NF_TERMINAL) {
+    if (ctd_node(T, node).flags & CTD_NF_TERMINAL) {
       double reward[6] = {0, 0, 0, 0, 0, 0};
-      reward[T.nodes[node].winner] = 1.0;
+      reward[ctd_node(T, node).winner] = 1.0;
       ctd_backpropagate(T, node, reward);
       ctd_update_strategy(T, node);
       node = 0;
@@ -593,6 +737,56 @@ CTD_HD CTD_NI inline void ctd_cfr_train(CtdTree& T, uint32_t iters) {
   }
   ctd_update_strategy(T, 0);
   h.rng_draws = T.w->draws;
+}
+
+// CFRNode.action_choice(live=True) at the root once the search is over (:67-75; run_utils.py:82,86): the decision a caller of
+// run_mccfr acts on.  Ordinary roots sample a child from the cumulative strategy; a role-pick root goes through
+// Game.get_option_from_role_preference (game/game.py:312-317): the `strategy` row of the player to move, which has one entry per
+// CHILD, is indexed by the RANKS still on offer (the reference's quirk, kept), normalised, and one of the role-pick options is
+// drawn.  The draw is the next one of the tree's own Philox stream (np.random.choice -> inverse CDF on one uniform, as in
+// ctd_action_choice).  Returns the option's descriptor; 0 for a terminal root (the reference raises ValueError there).
+CTD_HD CTD_NI inline uint64_t ctd_live_choice(CtdTree& T) {
+  CTD_TREE_SPACES(T);
+  const CtdTreeHdr& h = *T.hdr;
+  if (h.n_nodes == 0 || (h.status & ~CTD_TREE_TERMINAL_ROOT)) return 0;
+  CtdNode& n = ctd_node(T, 0);
+  const int K = (int)n.n_children;
+  if (K == 0) return 0;
+  CtdWork& w = *T.w;
+  if (!(n.flags & CTD_NF_ROLE_PICK)) {
+    w.draws = h.rng_draws; w.buf_blk = 0xFFFFFFFFu;
+    const double* C = ctd_C(T, n);
+    double cs = 0.0;
+    CTD_LOOP for (int a = 0; a < K; ++a) cs += C[a];
+    double last = 0.0;
+    CTD_LOOP for (int a = 0; a < K; ++a) last += C[a] / cs;
+    const double u = ctd_uniform(w);
+    double run = 0.0;
+    int i = 0;
+    CTD_LOOP for (; i < K - 1; ++i) {
+      run += C[i] / cs;
+      if (!(run / last <= u)) break;
+    }
+    return ctd_kids(T, n)[i].desc;
+  }
+  ctd_node_load(T, n);   // the root's game: which roles are on offer
+  w.draws = h.rng_draws; w.buf_blk = 0xFFFFFFFFu;
+  const double* S = ctd_S(T, n) + (int)n.player * 10;
+  double sub[8], tot = 0.0;
+  int ranks[8], m = 0;
+  CTD_LOOP for (int r = 0; r < 8; ++r)
+    if ((w.rtc_mask >> r) & 1) { ranks[m] = r; sub[m] = S[r]; tot += S[r]; ++m; }
+  if (m == 0) return 0;
+  double last = 0.0;
+  CTD_LOOP for (int j = 0; j < m; ++j) last += sub[j] / tot;
+  const double u = ctd_uniform(w);
+  double run = 0.0;
+  int i = 0;
+  CTD_LOOP for (; i < m - 1; ++i) {
+    run += sub[i] / tot;
+    if (!(run / last <= u)) break;
+  }
+  return ctd_opt(CTD_K_ROLE_PICK, w.player) | ctd_f_rank(ranks[i]);
 }
 
 // ------------------------------------------------------------------------------------------ deep MCCFR
@@ -649,7 +843,7 @@ CTD_HD CTD_NI inline int ctd_cfr_pred_advance(CtdTree& T, uint32_t iters, uint32
                                               uint32_t budget = 0xFFFFFFFFu) {
   CTD_TREE_SPACES(T);
   CtdTreeHdr& h = *T.hdr;
-  if (h.phase == 3 || (h.status & CTD_TREE_TERMINAL_ROOT)) { h.phase = 3; return CTD_PRED_DONE; }
+  if (h.phase == 3 || (h.status & CTD_TREE_TERMINAL_ROOT) || h.n_nodes == 0) { h.phase = 3; return CTD_PRED_DONE; }
   T.w->draws = h.rng_draws;
   T.w->buf_blk = 0xFFFFFFFFu;
   if (h.phase == 0) {
@@ -657,7 +851,7 @@ CTD_HD CTD_NI inline int ctd_cfr_pred_advance(CtdTree& T, uint32_t iters, uint32
     h.cur_node = 0;
     h.phase = 1;
   } else if (h.phase == 2) {
-    CtdNode& n = T.nodes[h.cur_node];
+    CtdNode& n = ctd_node(T, h.cur_node);
     double reward[6];
     CTD_LOOP for (int i = 0; i < 6; ++i) { n.pred[i] = pred[i]; reward[i] = (double)pred[i]; }
     n.flags |= CTD_NF_HAS_PRED;
@@ -677,7 +871,7 @@ CTD_HD CTD_NI inline int ctd_cfr_pred_advance(CtdTree& T, uint32_t iters, uint32
     }
     ctd_update_strategy(T, node);
     node = ctd_action_choice(T, node);
-    CtdNode& n = T.nodes[node];
+    CtdNode& n = ctd_node(T, node);
     if (n.depth > max_depth && !(n.flags & CTD_NF_TERMINAL)) {
       if (!(n.flags & CTD_NF_HAS_PRED)) {
         ctd_node_load(T, n);
@@ -712,9 +906,129 @@ CTD_HD CTD_NI inline int ctd_cfr_pred_advance(CtdTree& T, uint32_t iters, uint32
   return CTD_PRED_DONE;
 }
 
-// fill the packed game record of every node (export only)
-CTD_HD CTD_NI inline void ctd_tree_pack_nodes(CtdTree& T) {
-  
-  const uint32_t n = T.hdr->n_nodes;
-  CTD_LOOP for (uint32_t i = 0; i < n; ++i) ctd_node_pack(T, T.nodes[i]);
+// ------------------------------------------------------------------------------------------ CFR roots
+// run_utils.create_a_close_to_finished_game / create_a_random_game (run_utils.py:29-72): play game (seed, gid) uniformly
+// at random to terminal (T steps), then replay it from its (seed, gid) with the knowledge of all six observers tracked and
+// stop at the root:
+//   CTD_ROOTS_CLOSE_TO_FINISHED  u uniform in [back_lo, back_hi] (Philox stream word 2), root = step max(0, T - u), then along
+//                                the recorded game until the player to move has >= 2 options, at most 100 times
+//                                (run_utils.py:44-50 walks games[-m], games[-m+1], ...: m = u + 1); the searching player is
+//                                whoever is to move there
+//   CTD_ROOTS_RANDOM_GAME        m uniform in [back_lo, back_hi], root = games[-m] = step max(0, T + 1 - m) as it stands
+//                                (run_utils.py:52-72); run_mccfr fixes original_player_id = the player to move BEFORE
+//                                CFRNode.skip_false_choice advances through forced moves (run_utils.py:80-83,
+//                                algorithms/deep_mccfr.py:19-20), so the searching player may be the previous seat: the
+//                                root carries the knowledge of that seat and ctd_tree_init does the skipping
+// Leaves the root in `w`, the six observers' knowledge in kn6[0..6); returns the searching seat.
+// One uniformly random legal option without a list buffer: count, draw, enumerate again and keep the k-th.  The Seer's and the
+// Scholar's enumerations are not pure (fresh shuffles, a shrinking list: game/agent_functions.py:332-361, :462-470), so the second
+// pass starts from the state the first one started from and regenerates the same list; what is left behind is exactly one
+// enumeration plus one draw, as in `options = game.get_options_from_state(); choice(options)` (run_utils.py:38-39).
+struct CtdEnumSave {
+  uint32_t draws, tape_pos;
+  uint8_t n_seven, seven[7];
+};
+CTD_HD inline CtdEnumSave ctd_enum_save(const CtdWork& w) {
+  CtdEnumSave s;
+  s.draws = w.draws; s.tape_pos = w.tape_pos; s.n_seven = w.n_seven;
+  CTD_LOOP for (int i = 0; i < 7; ++i) s.seven[i] = w.seven[i];
+  return s;
+}
+CTD_HD inline uint64_t ctd_enum_select(CtdWork& w, const CtdKnow* kn, const CtdEnumSave& s, uint32_t k) {
+  const uint32_t draws1 = w.draws, tape1 = w.tape_pos;
+  w.draws = s.draws; w.tape_pos = s.tape_pos; w.buf_blk = 0xFFFFFFFFu; w.n_seven = s.n_seven;
+  CTD_LOOP for (int i = 0; i < 7; ++i) w.seven[i] = s.seven[i];
+  CtdEmit e2{nullptr, 0, 0, k, 0};
+  ctd_enumerate(w, e2, kn);
+  w.draws = draws1; w.tape_pos = tape1; w.buf_blk = 0xFFFFFFFFu;
+  return e2.got;
+}
+CTD_HD inline uint64_t ctd_choose_uniform(CtdWork& w, const CtdKnow* kn) {
+  const CtdEnumSave sv = ctd_enum_save(w);
+  CtdEmit e{nullptr, 0, 0, 0xFFFFFFFFu, 0};
+  ctd_enumerate(w, e, kn);
+  if (e.n == 0) return 0;
+  const uint32_t k = ctd_randbelow(w, e.n);
+  return ctd_enum_select(w, kn, sv, k);
+}
+CTD_HD CTD_NI inline int ctd_make_root(CtdWork& w, CtdKnow* kn6, uint64_t seed, uint64_t gid, int ruleset, uint32_t back_lo,
+                                       uint32_t back_hi, int flavour, uint8_t* used_cards, uint32_t* root_step) {
+  // pass 1: length of the game
+  ctd_new_game(w, seed, gid, ruleset);
+  while (!(w.gflags & 2) && !w.err && w.steps < 4096) {
+    uint64_t d = ctd_choose_uniform(w, nullptr);
+    if (d == 0) { w.err |= CTD_ERR_REF_RAISE; break; }
+    ctd_apply(w, d);
+  }
+  const uint32_t T = w.steps;
+  uint32_t r[4];
+  ctd_philox(0u, 2u, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  const uint32_t u = back_lo + (uint32_t)(((uint64_t)r[0] * (back_hi - back_lo + 1)) >> 32);
+  const uint32_t Tk = flavour == CTD_ROOTS_RANDOM_GAME ? T + 1 : T;
+  const uint32_t k = Tk > u ? Tk - u : 0;
+  // pass 2: replay with knowledge
+  ctd_chance_init(w, seed, gid, 0);
+  ctd_deal_preset(w, ruleset, used_cards);
+  for (int o = 0; o < 6; ++o) ctd_kn_init(kn6[o], o);
+  CtdKnowSet ks{kn6, 6};
+  ctd_setup_round(w, ks);
+  int limit = 0;
+  for (;;) {
+    if ((w.gflags & 2) || w.err) break;
+    if (flavour == CTD_ROOTS_RANDOM_GAME && w.steps >= k) break;
+    const CtdEnumSave sv = ctd_enum_save(w);
+    CtdEmit e{nullptr, 0, 0, 0xFFFFFFFFu, 0};
+    ctd_enumerate(w, e, &kn6[0]);
+    if (e.n == 0) { w.err |= CTD_ERR_REF_RAISE; break; }
+    if (w.steps >= k) {  // `while len(options) < 2 and limit < 100` (run_utils.py:46-50); the root keeps what this enumeration did to it
+      if (e.n >= 2 || limit >= 100) break;
+      ++limit;
+    }
+    const uint32_t pick = ctd_randbelow(w, e.n);
+    ctd_apply(w, ctd_enum_select(w, &kn6[0], sv, pick), ks);
+  }
+  if (root_step) *root_step = w.steps;
+  const int viewer = w.player < 6 ? w.player : 0;
+  for (int o = 0; o < 6; ++o) w.err |= kn6[o].err;
+  return viewer;
+}
+
+// ------------------------------------------------------------------------------------------ export
+// The tree as a compact block: CtdTreeHdrOut | CtdNodeOut[n_nodes] | CtdChild[child_used] | double[arr_used], child_off / arr_off
+// rewritten as indices into the block's own sections (nodes in index order).  `out` holds ctd_tree_export_bytes(...) bytes.
+CTD_HD CTD_NI inline void ctd_tree_export(CtdTree& T, uint8_t* out) {
+  const CtdTreeHdr& h = *T.hdr;
+  CtdTreeHdrOut* ho = (CtdTreeHdrOut*)out;
+  ho->n_nodes = h.n_nodes; ho->max_nodes = h.n_nodes; ho->child_used = h.child_used; ho->child_cap = h.child_used;
+  ho->arr_used = h.arr_used; ho->arr_cap = h.arr_used; ho->status = h.status; ho->iterations = h.iterations;
+  ho->rng_draws = h.rng_draws; ho->viewer = h.viewer; ho->training = h.training; ho->has_model = h.has_model; ho->phase = h.phase;
+  ho->gid = h.gid; ho->cur_node = h.cur_node;
+  CTD_LOOP for (int i = 0; i < 76; ++i) ho->used_cards[i] = h.used_cards[i];
+  CtdNodeOut* no = (CtdNodeOut*)(out + sizeof(CtdTreeHdrOut));
+  CtdChild* co = (CtdChild*)(no + h.n_nodes);
+  double* ao = (double*)(co + h.child_used);
+  uint32_t coff = 0, aoff = 0;
+  CtdWork& w = *T.w;
+  CTD_LOOP for (uint32_t i = 0; i < h.n_nodes; ++i) {
+    const CtdNode& n = ctd_node(T, i);
+    CtdNodeOut& o = no[i];
+    ctd_copy16(o.head, &n, 160);
+    ctd_copy16(&o.know, &n.know, (int)sizeof(CtdKnow));
+    ctd_copy16(&w, n.snap, CTD_SNAP_BYTES);
+    w.draws = 0; w.tape_pos = 0; w.steps = 0;
+    w.g0 = (uint32_t)h.gid; w.g1 = (uint32_t)(h.gid >> 32);
+    ctd_pack(w, T.stage);
+    ctd_copy16(&o.game, T.stage, (int)sizeof(ctd_state));
+    CtdNode* oh = (CtdNode*)o.head;   // only the 160-byte header part exists behind this pointer
+    oh->child_off = coff; oh->arr_off = aoff;
+    if (n.child_cap != 0) {
+      const CtdChild* kids = ctd_kids(T, n);
+      const uint32_t nd = (n.flags & CTD_NF_ROLE_PICK) ? 180u : 3u * n.child_cap;
+      const double* a = (const double*)(kids + n.child_cap);
+      CTD_LOOP for (uint32_t k = 0; k < n.child_cap; ++k) co[coff + k] = k < n.n_children ? kids[k] : CtdChild{0, 0, 0};
+      CTD_LOOP for (uint32_t k = 0; k < nd; ++k) ao[aoff + k] = a[k];
+      coff += n.child_cap;
+      aoff += nd;
+    }
+  }
 }

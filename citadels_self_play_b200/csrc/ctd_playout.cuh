@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_PLAYOUT_MIN_BLOCKS) CTD_PLAYOUT
     const uint32_t ns = w.steps - steps0;
     if (lane < 6) {  // per-seat fields: one lane per seat
       const int pts = w.points[lane];
-      if (a.points6) a.points6[g * 6 + lane] = (int8_t)pts;
+      if (a.points6) a.points6[g * 6 + lane] = (int8_t)(pts > 127 ? 127 : (pts < -128 ? -128 : pts));
       atomicAdd((unsigned long long*)&bs->points_sum[lane], (unsigned long long)(long long)pts);
       atomicAdd((unsigned long long*)&bs->points_sq[lane], (unsigned long long)(pts * pts));
       if (w.winner == lane) atomicAdd((unsigned long long*)&bs->wins[lane], 1ull);

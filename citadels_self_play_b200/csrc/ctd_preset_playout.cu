@@ -8,6 +8,7 @@
 #include <stddef.h>
 
 #define CTD_DEVICE_ONLY 1
+#define CTD_SMALL_CAPS 1   /* real games only: small containers, small working record (ctd_engine.cuh) */
 #define CTD_FIXED_PRESET 1
 #define CTD_PLAYOUT_KERNEL_NAME ctd_k_playout_preset
 #include "ctd_playout.cuh"

@@ -11,43 +11,38 @@
 #endif
 
 struct CtdMccfrArgs {
-  uint32_t n_roots;
+  uint32_t n_roots;            // work items of this launch
+  const uint32_t* tree_list;   // work item -> root index; null: root index = first_root + item
   const ctd_state* roots;
   const CtdKnow* knows;
   const uint8_t* used_cards;
   const uint64_t* gids;
   uint64_t seed;
   uint32_t iterations;
-  uint32_t max_nodes, child_cap, arr_cap;
-  uint8_t* trees;
-  size_t tree_stride;
+  uint32_t n0_log2;            // chunk 0 of every tree holds 2^n0_log2 nodes
+  CtdTreeHdr* hdrs;            // [capacity]
+  CtdArena arena;              // what trees initialised by this launch allocate from
   ctd_mccfr_result* results;
   unsigned long long* counter;
   uint64_t* opts_scratch;  // [gridDim.x * CTD_WARPS_PER_BLOCK][CTD_MCCFR_OPT_CAP]
-  uint32_t first_root;     // this launch covers trees [first_root, first_root + n_roots)
+  uint32_t first_root;
 };
-
-__device__ __forceinline__ CtdTree ctd_tree_at(uint8_t* base, uint32_t max_nodes, uint32_t child_cap) {
-  CtdTree T;
-  T.hdr = (CtdTreeHdr*)base;
-  T.nodes = (CtdNode*)(base + sizeof(CtdTreeHdr));
-  T.children = (CtdChild*)((uint8_t*)T.nodes + (size_t)max_nodes * sizeof(CtdNode));
-  T.arr = (double*)((uint8_t*)T.children + (size_t)child_cap * sizeof(CtdChild));
-  return T;
-}
 
 static __device__ void ctd_write_result(CtdTree& T, ctd_mccfr_result* r) {
   const CtdTreeHdr& h = *T.hdr;
-  const CtdNode& n = T.nodes[0];
   r->status = h.status; r->n_nodes = h.n_nodes; r->iterations = h.iterations; r->rng_draws = h.rng_draws;
+  r->live_option = ctd_live_choice(T);
   if (h.n_nodes == 0) { r->n_children = 0; r->role_pick = 0; r->viewer = 0; r->player = 0; return; }   // refused root: no tree
+  const CtdNode& n = ctd_node(T, 0);
   r->n_children = n.n_children; r->role_pick = (n.flags & CTD_NF_ROLE_PICK) ? 1 : 0;
   r->viewer = h.viewer; r->player = n.player;
   for (int i = 0; i < 6; ++i) { r->node_value[i] = n.V[i]; r->winning_probabilities[i] = n.P[i]; }
   const uint32_t K = n.n_children < CTD_MCCFR_MAX_RESULT ? n.n_children : CTD_MCCFR_MAX_RESULT;
   const bool rp = n.flags & CTD_NF_ROLE_PICK;
   const uint32_t na = n.n_children == 0 ? 0 : (rp ? 60 : K);
-  for (uint32_t i = 0; i < K; ++i) r->options[i] = T.children[n.child_off + i].desc;
+  if (n.n_children == 0) return;
+  const CtdChild* kids = ctd_kids(T, n);
+  for (uint32_t i = 0; i < K; ++i) r->options[i] = kids[i].desc;
   const double *R = ctd_R(T, n), *S = ctd_S(T, n), *C = ctd_C(T, n);
   for (uint32_t i = 0; i < na; ++i) { r->cumulative_regrets[i] = R[i]; r->strategy[i] = S[i]; r->cumulative_strategy[i] = C[i]; }
 }
@@ -71,31 +66,33 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) CTD_MCCFR_KER
     if (lane == 0) t = atomicAdd(a.counter, 1ull);
     t = __shfl_sync(CTD_FULL, t, 0);
     if (t >= a.n_roots) break;
-    t += a.first_root;
+    t = a.tree_list ? a.tree_list[t] : t + a.first_root;
     // Every lane runs the same scalar search on the same data (identical values to identical addresses, control flow
     // uniform, the warp stays converged): no lane does anything the others do not, but leaf operations that are
     // lane-parallel by nature -- moving a 1.8 KB node between HBM and the working set -- can split their work over the
     // lanes without restructuring the walk (CTD_MCCFR_ALL_LANES=0 restores the one-lane form).
     if (CTD_MCCFR_ALL_LANES || lane == 0) {
-      CtdTree T = ctd_tree_at(a.trees + t * a.tree_stride, a.max_nodes, a.child_cap);
+      CtdTree T;
       T.w = &works[wib]; T.kn = &knows[wib]; T.opts = opts; T.scratch = scratch[wib]; T.stage = &tstage[wib];
+      CtdTreeHdr* hdr = &a.hdrs[t];
       CtdWork& w = *T.w;
-      for (int i = 0; i < 76; ++i) T.hdr->used_cards[i] = a.used_cards[t * 76 + i];
+      for (int i = 0; i < 80; ++i) hdr->used_cards[i] = i < 76 ? a.used_cards[t * 76 + i] : 0;
       ctd_copy16(T.stage, &a.roots[t], (int)sizeof(ctd_state));
       ctd_unpack(T.stage, w);
       ctd_chance_init(w, a.seed, a.gids[t], 0);
       w.stream = 1;
       w.err = 0;
       ctd_copy16(T.kn, &a.knows[t], (int)sizeof(CtdKnow));
+      T.hdr = hdr;
       ctd_tree_stage_used(T);
 #ifdef CTD_FIXED_PRESET
       if (w.ruleset != CTD_RULESET_PRESET) {   // the caller named the wrong ruleset for this root: refuse, do not run
-        T.hdr->n_nodes = 0; T.hdr->iterations = 0; T.hdr->rng_draws = 0; T.hdr->status = CTD_TREE_EENGINE;
+        hdr->n_nodes = 0; hdr->iterations = 0; hdr->rng_draws = 0; hdr->status = CTD_TREE_EENGINE; hdr->child_used = 0; hdr->arr_used = 0;
         if (a.results) { a.results[t].status = CTD_TREE_EENGINE; a.results[t].n_nodes = 0; a.results[t].n_children = 0; a.results[t].iterations = 0; }
       } else
 #endif
       {
-      ctd_tree_init(T, a.max_nodes, a.child_cap, a.arr_cap, T.kn->viewer, a.gids[t], false, false);
+      ctd_tree_init(T, hdr, a.arena, a.n0_log2, T.kn->viewer, a.gids[t], false, false);
       ctd_cfr_train(T, a.iterations);
       if (a.results) ctd_write_result(T, &a.results[t]);
       }
@@ -131,34 +128,39 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) CTD_MCCFR_PRE
     if (lane == 0) t = atomicAdd(a.counter, 1ull);
     t = __shfl_sync(CTD_FULL, t, 0);
     if (t >= a.n_roots) break;
-    t += a.first_root;
+    t = a.tree_list ? a.tree_list[t] : t + a.first_root;
     if (CTD_MCCFR_ALL_LANES || lane == 0) {   // all lanes on the same scalar walk, see ctd_k_mccfr
-      CtdTree T = ctd_tree_at(a.trees + t * a.tree_stride, a.max_nodes, a.child_cap);
+      CtdTree T;
       T.w = &works[wib]; T.kn = &knows[wib]; T.opts = opts; T.scratch = scratch[wib]; T.stage = &tstage[wib];
+      CtdTreeHdr* hdr = &a.hdrs[t];
+      T.hdr = hdr;
       CtdWork& w = *T.w;
       if (p.first) {
-        for (int i = 0; i < 76; ++i) T.hdr->used_cards[i] = a.used_cards[t * 76 + i];
+        for (int i = 0; i < 80; ++i) hdr->used_cards[i] = i < 76 ? a.used_cards[t * 76 + i] : 0;
         ctd_copy16(T.stage, &a.roots[t], (int)sizeof(ctd_state));
         ctd_unpack(T.stage, w);
         ctd_chance_init(w, a.seed, a.gids[t], 0);
         w.stream = 1;
         w.err = 0;
         ctd_copy16(T.kn, &a.knows[t], (int)sizeof(CtdKnow));
+        ctd_tree_stage_used(T);
 #ifdef CTD_FIXED_PRESET
         if (w.ruleset != CTD_RULESET_PRESET) {   // the caller named the wrong ruleset for this root: refuse, do not run
-          T.hdr->n_nodes = 0; T.hdr->iterations = 0; T.hdr->rng_draws = 0; T.hdr->status = CTD_TREE_EENGINE; T.hdr->phase = 3;
+          hdr->n_nodes = 0; hdr->iterations = 0; hdr->rng_draws = 0; hdr->status = CTD_TREE_EENGINE; hdr->phase = 3;
+          hdr->child_used = 0; hdr->arr_used = 0; hdr->n0_log2 = a.n0_log2; hdr->arena = a.arena.base; hdr->chunk[0] = 0;
         } else
 #endif
-        ctd_tree_init(T, a.max_nodes, a.child_cap, a.arr_cap, T.kn->viewer, a.gids[t], false, true);
+        ctd_tree_init(T, hdr, a.arena, a.n0_log2, T.kn->viewer, a.gids[t], false, true);
       } else {
         ctd_chance_init(w, a.seed, a.gids[t], 0);
         w.stream = 1;
         w.err = 0;
         T.kn->err = 0;  // the working set is rebuilt from the tree on the first node load of this wave
+        ctd_tree_stage_used(T);
       }
-      ctd_tree_stage_used(T);
+      ctd_tree_attach(T, hdr, a.arena);
       int r = CTD_PRED_DONE;
-      if (T.hdr->phase != 3)
+      if (hdr->phase != 3)
         r = ctd_cfr_pred_advance(T, a.iterations, p.max_depth, p.feat + t * CTD_FEATURES_PAD, p.pred + t * 8, p.budget);
       p.pending[t] = r == CTD_PRED_WAIT ? 1 : 0;
       if (r == CTD_PRED_WAIT && lane == 0) atomicAdd(p.n_pending, 1u);

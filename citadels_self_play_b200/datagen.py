@@ -17,22 +17,31 @@ here the threshold given is the threshold applied (pass 15 for the reference's e
 """
 import numpy as np
 
-from .engine import Engine, DEFAULT_SEED, RULESET_PRESET
+from .engine import Engine, DEFAULT_SEED, RULESET_PRESET, ROOTS_RANDOM_GAME
 from .layout import encode_options
 
 
 def get_mccfr_targets(model=None, minimum_sufficient_nodes=5000, base_usefullness_treshold=200, pretrain=False,
                       max_iterations=2000, engine=None, roots_per_batch=1024, seed=DEFAULT_SEED, first_gid=0,
                       ruleset=RULESET_PRESET, back=(1, 100), stats=None):
+    """train_from_scratch.get_mccfr_targets (train_from_scratch.py:53-64) with simulate_game (:23-36) batched: every batch is
+    `roots_per_batch` roots of create_a_random_game(back[1]) searched in one launch.  Trees that did not complete (status other
+    than 0: terminal roots -- run_mccfr raises ValueError on them in the reference --, roots the reference itself raises on,
+    engine limits) contribute no targets (ctd_mccfr_targets skips them) and are counted in `stats`."""
     own = engine is None
     eng = engine or Engine(capacity=roots_per_batch)
     targets, batches, gid = [], 0, int(first_gid)
+    n_terminal = n_refused = 0
     try:
         while len(targets) < minimum_sufficient_nodes:
-            eng.make_roots(roots_per_batch, seed=seed, first_gid=gid, ruleset=ruleset, back_lo=back[0], back_hi=back[1])
-            eng.mccfr(roots_per_batch, iterations=max_iterations, seed=seed, ruleset=ruleset)
+            eng.make_roots(roots_per_batch, seed=seed, first_gid=gid, ruleset=ruleset, back_lo=back[0], back_hi=back[1],
+                           flavour=ROOTS_RANDOM_GAME)
+            st = eng.mccfr(roots_per_batch, iterations=max_iterations, seed=seed, ruleset=ruleset)["results"]["status"]
+            n_terminal += int((st == 1).sum())
+            n_refused += int((st > 1).sum())
             t = eng.mccfr_targets(roots_per_batch, iterations=max_iterations, seed=seed, ruleset=ruleset,
                                   threshold=float(base_usefullness_treshold))
+            assert not len(t["meta"]) or (st[t["meta"]["tree"]] == 0).all()
             targets += Engine.targets_as_tuples(t)
             gid += roots_per_batch
             batches += 1
@@ -40,7 +49,8 @@ def get_mccfr_targets(model=None, minimum_sufficient_nodes=5000, base_usefullnes
                 raise RuntimeError("get_mccfr_targets: no targets are being produced (threshold too high for max_iterations?)")
     finally:
         if stats is not None:
-            stats.update(batches=batches, roots=batches * roots_per_batch, targets=len(targets))
+            stats.update(batches=batches, roots=batches * roots_per_batch, targets=len(targets), terminal_roots=n_terminal,
+                         refused_roots=n_refused)
         if own:
             eng.close()
     return targets
@@ -59,16 +69,19 @@ def generate_test_data(n_roots, max_iterations=200, engine=None, seed=DEFAULT_SE
         res = eng.mccfr(n_roots, iterations=max_iterations, seed=seed, ruleset=ruleset)["results"]
         for i, r in enumerate(res):
             k = int(r["n_children"])
-            if r["status"] != 0 or k == 0 or k > len(r["options"]):
+            if r["status"] != 0 or k == 0:
                 continue                                  # terminal root (ValueError in the reference) / meaningless state
+            opts = np.array(r["options"][:k])
             if r["role_pick"]:
                 dist = np.array(r["cumulative_regrets"][:60]).reshape(6, 10)[int(rng.integers(0, 6))]
+            elif k > len(r["options"]):                   # more children than a result record holds: read them from the tree
+                opts, dist, _, _ = eng.root_children(i, 0, k)
             else:
                 dist = np.array(r["cumulative_regrets"][:k])
             if dist.sum() == 0:
                 dist = np.ones_like(dist)
             out.append((torch.from_numpy(np.array(feats[i][:418], dtype=np.float32)),
-                        torch.from_numpy(encode_options(np.array(r["options"][:k]))).unsqueeze(0),
+                        torch.from_numpy(encode_options(opts)).unsqueeze(0),
                         torch.from_numpy(np.array(r["node_value"])), torch.from_numpy(dist)))
     finally:
         if own:

@@ -6,7 +6,8 @@ import numpy as np
 from . import _lib
 from .layout import STATE_BYTES, KNOW_BYTES, MCCFR_RESULT_DTYPE, TARGET_META_DTYPE, TreeView, encode_options
 
-RULESET_PRESET, RULESET_CLASSIC = 0, 1
+RULESET_PRESET, RULESET_CLASSIC, RULESET_RANDOM = 0, 1, 2
+ROOTS_CLOSE_TO_FINISHED, ROOTS_RANDOM_GAME = 0, 1
 DEFAULT_SEED = 0xC17ADE15
 
 
@@ -126,11 +127,14 @@ class Engine:
         return winner, steps
 
     # ---- MCCFR ----
-    def make_roots(self, n, seed=DEFAULT_SEED, first_gid=0, ruleset=RULESET_PRESET, back_lo=0, back_hi=20):
-        """CFR roots on the device (run_utils.create_a_close_to_finished_game).  -> root_step[n]"""
+    def make_roots(self, n, seed=DEFAULT_SEED, first_gid=0, ruleset=RULESET_PRESET, back_lo=0, back_hi=20,
+                   flavour=ROOTS_CLOSE_TO_FINISHED):
+        """CFR roots on the device: run_utils.create_a_close_to_finished_game (default flavour) or
+        run_utils.create_a_random_game (ROOTS_RANDOM_GAME: games[-m], m in [back_lo, back_hi], the searching player fixed
+        before the forced moves are skipped).  -> root_step[n]"""
         steps = np.empty(n, dtype=np.uint32)
-        self._check(self._lib.ctd_make_roots(self._h, n, seed, first_gid, ruleset, back_lo, back_hi, steps.ctypes.data),
-                    "ctd_make_roots")
+        self._check(self._lib.ctd_make_roots(self._h, n, seed, first_gid, ruleset, back_lo, back_hi, flavour,
+                                             steps.ctypes.data), "ctd_make_roots")
         return steps
 
     def load_roots(self, roots, knows, used_cards, gids):
@@ -151,26 +155,37 @@ class Engine:
                     "ctd_store_roots")
         return r, k, u, g
 
-    def tree_shape(self, iterations, ruleset=RULESET_PRESET):
-        mn, cc, ac, by = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint64()
-        self._lib.ctd_mccfr_tree_shape(iterations, ruleset, ctypes.byref(mn), ctypes.byref(cc), ctypes.byref(ac),
-                                       ctypes.byref(by))
-        return mn.value, cc.value, ac.value, by.value
+    def tree_shape(self, iterations, ruleset=RULESET_PRESET, n_roots=1):
+        """-> (nodes in a tree's first chunk, bytes per node, bytes of the arena a search of n_roots trees starts with)."""
+        n0, nb, ab = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint64()
+        self._lib.ctd_mccfr_tree_shape(iterations, ruleset, n_roots, ctypes.byref(n0), ctypes.byref(nb), ctypes.byref(ab))
+        return n0.value, nb.value, ab.value
+
+    def export_trees(self, n, first=0):
+        """The trees of the last mccfr()/mccfr_pred() call, roots [first, first+n) -> [TreeView]."""
+        sizes = np.zeros(n, dtype=np.uint64)
+        self._check(self._lib.ctd_mccfr_export(self._h, first, n, sizes.ctypes.data, None, 0), "ctd_mccfr_export")
+        total = int(sizes.sum())
+        buf = np.zeros(max(total, 1), dtype=np.uint8)
+        self._check(self._lib.ctd_mccfr_export(self._h, first, n, sizes.ctypes.data, buf.ctypes.data, total), "ctd_mccfr_export")
+        off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        return [TreeView(buf[int(off[i]):int(off[i + 1])]) for i in range(n)]
+
+    def root_children(self, tree, first, count):
+        """Children [first, first+count) of the root of tree `tree` -> (options u64, R, s, C float64)."""
+        o = np.zeros(count, dtype=np.uint64)
+        r, s_, c = (np.zeros(count, dtype=np.float64) for _ in range(3))
+        self._check(self._lib.ctd_mccfr_root_children(self._h, tree, first, count, o.ctypes.data, r.ctypes.data, s_.ctypes.data,
+                                                      c.ctypes.data), "ctd_mccfr_root_children")
+        return o, r, s_, c
 
     def mccfr(self, n_roots, iterations=200, seed=DEFAULT_SEED, ruleset=RULESET_PRESET, trees=False):
         """CFRNode(...).cfr_train(iterations) on the loaded/made roots.  -> dict(results, trees, kernel_ms)"""
         res = np.zeros(n_roots, dtype=MCCFR_RESULT_DTYPE)
         ms = ctypes.c_float()
-        views = None
-        buf = None
-        if trees:
-            mn, cc, ac, by = self.tree_shape(iterations, ruleset)
-            buf = np.zeros((n_roots, by), dtype=np.uint8)
-        self._check(self._lib.ctd_mccfr(self._h, n_roots, seed, iterations, ruleset, res.ctypes.data,
-                                        buf.ctypes.data if trees else None, ctypes.byref(ms)), "ctd_mccfr")
-        if trees:
-            views = [TreeView(buf[i], mn, cc, ac) for i in range(n_roots)]
-        return dict(results=res, trees=views, kernel_ms=ms.value)
+        self._check(self._lib.ctd_mccfr(self._h, n_roots, seed, iterations, ruleset, res.ctypes.data, ctypes.byref(ms)),
+                    "ctd_mccfr")
+        return dict(results=res, trees=self.export_trees(n_roots) if trees else None, kernel_ms=ms.value)
 
     def set_value_model(self, model):
         """model: a ValueOnlyNN(418, 512) in eval mode (reference state_dict layout)."""
@@ -202,16 +217,9 @@ class Engine:
         """CFRNode(..., model).cfr_pred(iterations, max_depth) on the loaded/made roots."""
         res = np.zeros(n_roots, dtype=MCCFR_RESULT_DTYPE)
         ms, waves = ctypes.c_float(), ctypes.c_uint32()
-        views = buf = None
-        if trees:
-            mn, cc, ac, by = self.tree_shape(iterations, ruleset)
-            buf = np.zeros((n_roots, by), dtype=np.uint8)
         self._check(self._lib.ctd_mccfr_pred(self._h, n_roots, seed, iterations, max_depth, ruleset, weight, res.ctypes.data,
-                                             buf.ctypes.data if trees else None, ctypes.byref(ms), ctypes.byref(waves)),
-                    "ctd_mccfr_pred")
-        if trees:
-            views = [TreeView(buf[i], mn, cc, ac) for i in range(n_roots)]
-        return dict(results=res, trees=views, kernel_ms=ms.value, waves=waves.value)
+                                             ctypes.byref(ms), ctypes.byref(waves)), "ctd_mccfr_pred")
+        return dict(results=res, trees=self.export_trees(n_roots) if trees else None, kernel_ms=ms.value, waves=waves.value)
 
     def mccfr_targets(self, n_roots, iterations=200, seed=DEFAULT_SEED, ruleset=RULESET_PRESET, threshold=15.0):
         """CFRNode.get_all_targets() for every tree of the last mccfr()/mccfr_pred() call with the same arguments.

@@ -31,10 +31,18 @@ import numpy as np
 from . import _lib
 from .engine import Engine, EngineError, DEFAULT_SEED, RULESET_PRESET, RULESET_CLASSIC
 from .layout import (STATE_DTYPE, KNOW_BYTES, KIND_NAMES, KIND, NAMED_NAMES, SUIT_NAMES, ROLES, COST_OF_TYPE,
-                     SUIT_OF_TYPE, opt_fields, TreeView, NF_ROLE_PICK)
+                     SUIT_OF_TYPE, opt_fields, record_gold, TreeView, NF_ROLE_PICK, TREE_REF_RAISE)
 
 _default_engine = None
-_gid_counter = itertools.count(1 << 40)
+# Games made without an explicit gid take ids from the upper half of the 40-bit id space (explicit ids are expected below 2^39).
+# Bits 40.. of a tree's id carry the game's search counter: every run_mccfr of one game draws from its own Philox stream, as
+# arena.search_batch does with the decision number.
+GID_BITS = 40
+_gid_counter = itertools.count(1 << (GID_BITS - 1))
+
+
+def tree_gid(gid, search_no):
+    return (int(gid) & ((1 << GID_BITS) - 1)) | (int(search_no) << GID_BITS)
 
 
 def default_engine():
@@ -101,7 +109,7 @@ class Agent:
     buildings = property(lambda self: _Deck(self._seg(1)))
     museum_cards = property(lambda self: _Deck(self._seg(2)))
     just_drawn_cards = property(lambda self: _Deck(self._seg(3)))
-    gold = property(lambda self: int(self._game._rec["gold"][self.id]))
+    gold = property(lambda self: record_gold(self._game._rec, self.id))
     replicas = property(lambda self: int(self._game._rec["replicas"][self.id]))
     crown = property(lambda self: int(self._game._rec["crown"]) == self.id)
     can_use_lighthouse = property(lambda self: bool(self._game._rec["pflags"][self.id] & 1))
@@ -241,6 +249,12 @@ class option:
         """option.carry_out (game/option.py:118-122): returns the winning Agent when the game ended, else False."""
         return game._step(self.desc)
 
+    def encode_option(self):
+        """option.encode_option (game/option.py:52-115) -> torch.float32[1, 131]."""
+        import torch
+        from .layout import encode_options
+        return torch.from_numpy(encode_options([self.desc]))
+
 
 class Game:
     """game/game.py `Game` for the fixed rulesets: a 256-byte record, the six observers' knowledge and used_cards on
@@ -259,6 +273,7 @@ class Game:
         self._engine._check(lib.ctd_game_new(h, self.seed, self.gid, ruleset, self._rec.ctypes.data,
                                              self._know.ctypes.data, self._used.ctypes.data), "ctd_game_new")
         self._fresh = True
+        self._searches = 0      # run_mccfr calls made from this game so far (keys the search's chance stream)
         self.players = [Agent(self, i) for i in range(6)]
 
     # -- the reference's attributes ------------------------------------------------------------
@@ -329,10 +344,30 @@ class Game:
         """The packed 256-byte record (include/citadels_b200.h ctd_state)."""
         return self._rec.tobytes()
 
+    def get_option_from_role_preference(self, strategy):
+        """Game.get_option_from_role_preference (game/game.py:312-317): `strategy` is indexed by the RANKS of the roles on
+        offer (the caller, CFRNode.action_choice(live=True), passes a row with one entry per child -- the reference's quirk)."""
+        options = self.get_options_from_state()
+        role_ids = [opt_fields(o.desc)["rank"] for o in options]
+        substrategy = np.asarray(strategy, dtype=float)[role_ids]
+        substrategy = substrategy / substrategy.sum()
+        return options[np.random.choice(len(options), p=substrategy)]
+
+    def sample_private_information(self, player_character, role_sample=True):
+        """Game.sample_private_information (game/game.py:215-242): determinise what `player_character` cannot see, in place,
+        on the device (ctd_game_sample).  Inside searches this runs in the kernels; the method exists for callers that
+        determinise a game themselves."""
+        seat = player_character.id if hasattr(player_character, "id") else int(player_character)
+        lib, h = self._engine._lib, self._engine._h
+        self._engine._check(lib.ctd_game_sample(h, self.seed, self._rec.ctypes.data, self._know.ctypes.data, self._used.ctypes.data,
+                                                seat, 1 if role_sample else 0), "ctd_game_sample")
+        if self._rec["err"]:
+            raise EngineError("engine error flags 0x%x (2 = the reference would raise here)" % int(self._rec["err"]))
+
     def __deepcopy__(self, memo):
         g = Game.__new__(Game)
         g._engine = self._engine
-        g.seed, g.gid, g._fresh = self.seed, self.gid, self._fresh
+        g.seed, g.gid, g._fresh, g._searches = self.seed, self.gid, self._fresh, self._searches
         g._rec = self._rec.copy()
         g._know = self._know.copy()
         g._used = self._used.copy()
@@ -402,9 +437,8 @@ class CFRNode:
         self._tree = _tree
         self._index = _index
         self._children = None
+        self.live_option = None
         if _tree is None:
-            if training and model is not None:
-                raise NotImplementedError("training=True with a model (target generation) is a later row of the scope table")
             self.current_player_id = game.gamestate.player_id
             self.role_pick_node = game.gamestate.state == 0
             self.cumulative_regrets = np.array([])
@@ -430,7 +464,8 @@ class CFRNode:
         e = g._engine
         v = self.original_player_id
         e.load_roots(np.frombuffer(g._rec.tobytes(), dtype=np.uint8), g._know[v * KNOW_BYTES:(v + 1) * KNOW_BYTES], g._used,
-                     np.array([g.gid], dtype=np.uint64))
+                     np.array([tree_gid(g.gid, g._searches)], dtype=np.uint64))
+        g._searches += 1
         ruleset = int(g._rec["ruleset"])
         if max_depth is None:
             out = e.mccfr(1, iterations=iterations, seed=g.seed, ruleset=ruleset, trees=True)
@@ -440,11 +475,14 @@ class CFRNode:
                                weight=float(self.model_reward_weights), trees=True)
         res = out["results"][0]
         self.status = int(res["status"])
+        if self.status & TREE_REF_RAISE:
+            raise EngineError("MCCFR status %d: the reference raises inside its rules code for this root" % self.status)
         if self.status & ~1:
-            raise EngineError("MCCFR status %d (2 node pool exhausted, 4 engine error, 8 option overflow)" % self.status)
+            raise EngineError("MCCFR status %d (2 device memory exhausted, 4 container capacity)" % self.status)
         self._tree = out["trees"][0]
         self._index = 0
         self._children = None
+        self.live_option = int(res["live_option"])
         # skip_false_choice advances the caller's game (algorithms/deep_mccfr.py:19-20, :37-49)
         g._rec = np.array(self._tree.nodes[0]["game"])
         g._know[v * KNOW_BYTES:(v + 1) * KNOW_BYTES] = np.frombuffer(self._tree.nodes[0]["know"].tobytes(), dtype=np.uint8)
@@ -455,7 +493,9 @@ class CFRNode:
         self._run(max_iterations)
 
     def cfr_pred(self, max_iterations=2000, max_depth=20):
-        """algorithms/deep_mccfr.py:207-229."""
+        """algorithms/deep_mccfr.py:207-229.  With training=True the reference never consumes the model's output
+        (deep_mccfr.py:119-126, :147, :178 guard on `not self.training`; backpropagate always accumulates), so cfr_pred is
+        only meaningful with training=False, as in run_utils.run_mccfr."""
         if self.model is None:
             raise ValueError("cfr_pred needs a value model")
         self._run(max_iterations, max_depth)
@@ -469,7 +509,7 @@ class CFRNode:
             self._children = []
             for desc, idx in self._tree.child_list(self._index):
                 cg = Game.__new__(Game)
-                cg._engine, cg.seed, cg.gid, cg._fresh = self.game._engine, self.game.seed, self.game.gid, False
+                cg._engine, cg.seed, cg.gid, cg._fresh, cg._searches = self.game._engine, self.game.seed, self.game.gid, False, 0
                 cg._rec = np.array(self._tree.nodes[idx]["game"])
                 cg._know = self.game._know.copy()   # only the searching player's block is tracked inside a tree
                 v = self.original_player_id
@@ -489,21 +529,26 @@ class CFRNode:
         return self.game.rewards
 
     def action_choice(self, live=False):
-        """algorithms/deep_mccfr.py:67-91.  `live=True` at a role-pick node uses the preference quirk of
-        game/game.py:312-317 (strategy row of the player to move indexed by the ranks on offer)."""
+        """algorithms/deep_mccfr.py:67-91.  `live=True` on a searched root returns the decision the kernel drew from the tree's own
+        chance stream right after the search (ctd_mccfr_result.live_option: the cumulative-strategy draw, or at a role-pick root
+        the preference quirk of game/game.py:312-317); on any other node the draw comes from numpy like in the reference."""
         kids = self.children
         if not kids and not self.role_pick_node:
             raise ValueError("a terminal root has no children (the reference raises ValueError here too)")
+        if live and self.parent is None and self.live_option:
+            chosen = option(self.live_option, self.game)
+            if self.role_pick_node:
+                return None, chosen
+            for o, node in kids:
+                if o.desc == chosen.desc:
+                    return node, o
+            return None, chosen
         if not self.role_pick_node:
             p = self.cumulative_strategy / self.cumulative_strategy.sum()
             i = np.random.choice(range(len(kids)), p=p)
             return kids[i][1], kids[i][0]
         if live:
-            options = self.game.get_options_from_state()
-            ranks = [opt_fields(o.desc)["rank"] for o in options]
-            sub = self.strategy[self.game.gamestate.player_id][ranks]
-            sub = sub / sub.sum()
-            return None, options[np.random.choice(len(options), p=sub)]
+            return None, self.game.get_option_from_role_preference(self.strategy[self.game.gamestate.player_id])
         order = self.game.turn_orders_for_roles
         avg = np.zeros(self.cumulative_strategy.shape[1])
         for i, pl in enumerate(order):
@@ -515,7 +560,8 @@ class CFRNode:
 
 
 def run_mccfr(game, model=None, max_iterations=2000, training=False):
-    """run_utils.run_mccfr (run_utils.py:74-87)."""
+    """run_utils.run_mccfr (run_utils.py:74-87).  training=True runs cfr_train whether or not a model is given, as the
+    reference does (the model's output is never consumed in that mode)."""
     root = CFRNode(game, original_player_id=game.gamestate.player_id, model=model, training=training)
     if model is not None and not training:
         root.cfr_pred(max_iterations=max_iterations, max_depth=10)

@@ -12,8 +12,8 @@ STATE_DTYPE = np.dtype([
     ("state", np.uint8), ("player", np.uint8), ("done", np.uint8), ("done_builds", np.uint8),
     ("next_player", np.uint8), ("next_mode", np.uint8), ("crown", np.uint8), ("gflags", np.uint8),
     ("winner", np.int8), ("wiz_target", np.uint8), ("points", np.int8, 6), ("warrant_building", np.uint8),
-    ("ruleset", np.uint8), ("err", np.uint8), ("seer_mask", np.uint8), ("seven_n", np.uint8), ("pad0", np.uint8),
-    ("rng_draws", np.uint32), ("tape_pos", np.uint16), ("steps", np.uint16), ("seven", np.uint8, 7), ("pad1", np.uint8),
+    ("ruleset", np.uint8), ("err", np.uint8), ("seer_mask", np.uint8), ("seven_n", np.uint8), ("gold_hi03", np.uint8),
+    ("rng_draws", np.uint32), ("tape_pos", np.uint16), ("steps", np.uint16), ("seven", np.uint8, 7), ("gold_hi45", np.uint8),
     ("gid", np.uint64)])
 assert STATE_DTYPE.itemsize == STATE_BYTES
 
@@ -43,6 +43,12 @@ COST_OF_TYPE = [1, 2, 4, 2, 5, 3, 2, 3, 5, 1, 2, 3, 1, 4, 3, 5,
 SUIT_OF_TYPE = [0] * 6 + [1] * 4 + [2] * 3 + [3] * 3 + [4] * 24
 
 
+def record_gold(rec, seat):
+    """Agent.gold of `seat` from a packed record: signed low byte + 256 * signed 2-bit page (gold_hi03 / gold_hi45)."""
+    page = (int(rec["gold_hi03"]) >> (2 * seat)) & 3 if seat < 4 else (int(rec["gold_hi45"]) >> (2 * (seat - 4))) & 3
+    return int(rec["gold"][seat]) + 256 * ((page ^ 2) - 2)
+
+
 def opt_fields(d):
     d = int(d)
     rep = (d >> 32) & 0xF
@@ -52,9 +58,8 @@ def opt_fields(d):
                 crown=(d >> 38) & 1, count=(d >> 39) & 0x3F, r=(d >> 45) & 0x3F, j=(d >> 51) & 0x3FF)
 
 
-# ---- MCCFR tree block (csrc/ctd_mccfr.cuh) ----
+# ---- MCCFR tree export block (csrc/ctd_mccfr.cuh: CtdTreeHdrOut | CtdNodeOut[] | CtdChild[] | double[]) ----
 KNOW_BYTES = 592
-SNAP_BYTES = 1328   # CtdWork snapshot (csrc/ctd_engine.cuh CTD_SNAP_BYTES)
 HK_DTYPE = np.dtype([("pid", np.int8), ("conf", np.uint8), ("flags", np.uint8), ("n", np.uint8), ("off", np.uint16),
                      ("pad", np.uint16)])
 KNOW_DTYPE = np.dtype([("viewer", np.uint8), ("conf_mask", np.uint8), ("n_hk", np.uint8), ("wiz_n", np.uint8),
@@ -65,9 +70,9 @@ NODE_DTYPE = np.dtype([("parent", np.int32), ("depth", np.uint16), ("player", np
                        ("n_children", np.uint32), ("child_cap", np.uint32), ("child_off", np.uint32),
                        ("arr_off", np.uint32), ("visits", np.uint32), ("pad0", np.uint32), ("V", np.float64, 6),
                        ("P", np.float64, 6), ("pred", np.float32, 6), ("order", np.uint8, 6), ("gstate", np.uint8),
-                       ("winner", np.int8), ("game", STATE_DTYPE), ("know", KNOW_DTYPE), ("snap", np.uint8, SNAP_BYTES)])
+                       ("winner", np.int8), ("game", STATE_DTYPE), ("know", KNOW_DTYPE)])
 NODE_BYTES = NODE_DTYPE.itemsize
-assert NODE_BYTES == 160 + 256 + KNOW_BYTES + SNAP_BYTES
+assert NODE_BYTES == 160 + 256 + KNOW_BYTES
 CHILD_DTYPE = np.dtype([("desc", np.uint64), ("node", np.uint32), ("pad", np.uint32)])
 TREE_HDR_DTYPE = np.dtype([("n_nodes", np.uint32), ("max_nodes", np.uint32), ("child_used", np.uint32),
                            ("child_cap", np.uint32), ("arr_used", np.uint32), ("arr_cap", np.uint32),
@@ -76,24 +81,27 @@ TREE_HDR_DTYPE = np.dtype([("n_nodes", np.uint32), ("max_nodes", np.uint32), ("c
                            ("gid", np.uint64), ("used_cards", np.uint8, 76), ("cur_node", np.uint32)])
 assert TREE_HDR_DTYPE.itemsize == 128
 NF_ROLE_PICK, NF_TERMINAL = 1, 2
+# tree status bits (include/citadels_b200.h ctd_mccfr_result.status)
+TREE_TERMINAL_ROOT, TREE_EPOOL, TREE_EENGINE, TREE_REF_RAISE = 1, 2, 4, 16
 
 
-def tree_bytes(max_nodes, child_cap, arr_cap):
-    return 128 + max_nodes * NODE_BYTES + child_cap * 16 + arr_cap * 8
+def tree_bytes(n_nodes, child_used, arr_used):
+    return 128 + n_nodes * NODE_BYTES + child_used * 16 + arr_used * 8
 
 
 class TreeView:
-    """numpy views over one tree block as laid out by the kernels."""
+    """numpy views over one exported tree block (the sizes are in its header)."""
 
-    def __init__(self, buf, max_nodes, child_cap, arr_cap):
+    def __init__(self, buf):
         buf = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf
         self.hdr = buf[:128].view(TREE_HDR_DTYPE)[0]
+        nn, nc, na = int(self.hdr["n_nodes"]), int(self.hdr["child_used"]), int(self.hdr["arr_used"])
         o = 128
-        self.nodes = buf[o:o + max_nodes * NODE_BYTES].view(NODE_DTYPE)
-        o += max_nodes * NODE_BYTES
-        self.children = buf[o:o + child_cap * 16].view(CHILD_DTYPE)
-        o += child_cap * 16
-        self.arr = buf[o:o + arr_cap * 8].view(np.float64)
+        self.nodes = buf[o:o + nn * NODE_BYTES].view(NODE_DTYPE)
+        o += nn * NODE_BYTES
+        self.children = buf[o:o + nc * 16].view(CHILD_DTYPE)
+        o += nc * 16
+        self.arr = buf[o:o + na * 8].view(np.float64)
 
     def arrays(self, i):
         """(R, s, C) of node i shaped like the reference's numpy arrays."""
@@ -114,7 +122,7 @@ class TreeView:
 MCCFR_RESULT_DTYPE = np.dtype([("status", np.uint32), ("n_nodes", np.uint32), ("iterations", np.uint32),
                                ("rng_draws", np.uint32), ("n_children", np.uint32), ("role_pick", np.uint8),
                                ("viewer", np.uint8), ("player", np.uint8), ("pad", np.uint8),
-                               ("node_value", np.float64, 6), ("winning_probabilities", np.float64, 6),
+                               ("live_option", np.uint64), ("node_value", np.float64, 6), ("winning_probabilities", np.float64, 6),
                                ("options", np.uint64, 128), ("cumulative_regrets", np.float64, 180),
                                ("strategy", np.float64, 180), ("cumulative_strategy", np.float64, 180)])
 

@@ -45,7 +45,7 @@ typedef struct ctd_state {
                             museum_cards, just_drawn_cards (game/agent.py:12-20); then deck, discard_deck.
                             code 0..39 = type_ID; 40..43 = Magic School with suit trade/war/religion/lord */
   uint8_t off[28];       /* off[c] = start of container c in arena; off[26] = total cards */
-  int8_t gold[6];        /* Agent.gold (may go negative) */
+  int8_t gold[6];        /* Agent.gold (may go negative): low byte; see gold_hi03 / gold_hi45 for purses beyond a byte */
   uint8_t role[6];       /* 0..7 rank; 8 = None; 9 = "Bewitched" */
   int8_t replicas[6];    /* Agent.replicas (False == 0) */
   uint8_t pflags[6];     /* bit0 can_use_lighthouse, bit1 first_to_7, bit2 witch */
@@ -74,12 +74,13 @@ typedef struct ctd_state {
   uint8_t err;           /* CTD_ERR_* flags */
   uint8_t seer_mask;     /* game.seer_taken_card_from as a seat mask (it is always in seat order) */
   uint8_t seven_n;       /* len(game.seven_drawn_cards) */
-  uint8_t pad0;
+  uint8_t gold_hi03;     /* seats 0..3, two bits each: signed page p, gold = (int8) gold[seat] + 256 * p, p in -2..1 (0 in every
+                            finished game of the reference; run-away games of Game(preset=False) and CFR's hypothetical games need it) */
   uint32_t rng_draws;    /* Philox draws consumed by this game so far */
   uint16_t tape_pos;     /* chance-tape cursor (replay mode) */
   uint16_t steps;        /* env steps applied to this slot (saturating) */
   uint8_t seven[7];      /* game.seven_drawn_cards (Scholar) */
-  uint8_t pad1;
+  uint8_t gold_hi45;     /* seats 4, 5 (bits 0-3) */
   uint64_t gid;          /* Philox game id of this slot (counter words 2,3) */
 } ctd_state;
 
@@ -162,6 +163,12 @@ ctd_status ctd_game_options(ctd_engine* e, uint64_t seed, ctd_state* state, cons
 /* option.carry_out(game)  (game/option.py:118-122); *winner = winning seat or -1 */
 ctd_status ctd_game_step(ctd_engine* e, uint64_t seed, ctd_state* state, void* know6, ctd_option chosen, int8_t* winner);
 
+/* game.sample_private_information(game.players[viewer], role_sample) (game/game.py:215-242): determinise what seat `viewer`
+ * cannot see -- deck, the other hands, unconfirmed roles, which warrant / blackmail is real -- from its knowledge block, in place.
+ * (Inside ctd_mccfr / ctd_mccfr_pred the kernels do this themselves; this is the single-game form of the facade.) */
+ctd_status ctd_game_sample(ctd_engine* e, uint64_t seed, ctd_state* state, void* know6, const uint8_t* used_cards, int viewer,
+                           int role_sample);
+
 /* ---- the hot path ---- */
 /* Game.get_options_from_state / Agent.get_options (game/game.py:415-418, game/agent.py:50-83) for slots
  * [0,n): opts[i*stride .. i*stride+counts[i]) in the reference's list order.  Terminal slots report 0.
@@ -196,16 +203,21 @@ ctd_status ctd_playout_dev(ctd_engine* e, uint64_t n_games, uint64_t seed, uint6
 #define CTD_KNOW_BYTES 592
 #define CTD_MCCFR_MAX_RESULT 128
 typedef struct ctd_mccfr_result {
-  uint32_t status;       /* 0 ok; 1 terminal root (the reference's run_mccfr raises ValueError); 2 node pool
-                            exhausted; 4 engine error; 8 more than 4096 options at an expanded node */
+  uint32_t status;       /* 0 ok; bit 0 (1) terminal root -- the reference's run_mccfr raises ValueError; bit 4 (16) the reference
+                            raises inside its rules code for this root (an exception out of cfr_train).  Engine limits: bit 1 (2)
+                            device memory exhausted even after the retries; bit 2 (4) a container outgrew its capacity
+                            (csrc/ctd_engine.cuh: hands of 64, cities of 64, museums / just_drawn of 48) */
   uint32_t n_nodes;
   uint32_t iterations;
   uint32_t rng_draws;
-  uint32_t n_children;   /* len(root.children) */
+  uint32_t n_children;   /* len(root.children); the first CTD_MCCFR_MAX_RESULT are in this record, ctd_mccfr_root_children reads any range */
   uint8_t role_pick;     /* root.role_pick_node: the arrays below are [6][10] (player-major) */
   uint8_t viewer;        /* original_player_id */
   uint8_t player;        /* root.current_player_id */
   uint8_t pad;
+  ctd_option live_option;           /* run_mccfr's decision: root.action_choice(live=True)[1] (run_utils.py:82,86;
+                                       algorithms/deep_mccfr.py:67-75, game/game.py:312-317), drawn from the tree's own chance
+                                       stream right after the search; 0 for a terminal root (ValueError in the reference) */
   double node_value[6];             /* root.node_value */
   double winning_probabilities[6];  /* root.winning_probabilities */
   ctd_option options[CTD_MCCFR_MAX_RESULT];  /* option of child i */
@@ -215,23 +227,43 @@ typedef struct ctd_mccfr_result {
 } ctd_mccfr_result;
 
 /* run_utils.create_a_close_to_finished_game / create_a_random_game (run_utils.py:29-72) for slots [0,n): play game
- * (seed, first_gid+i) to terminal, step back u decisions (u uniform in [back_lo, back_hi]), move forward until the
- * player to move has >= 2 options.  Fills the slot, its knowledge block, used_cards and tree id on the device.
+ * (seed, first_gid+i) to terminal (T steps) and step back.
+ *   CTD_ROOTS_CLOSE_TO_FINISHED  u uniform in [back_lo, back_hi]; root = step max(0, T - u), then forward along the same game
+ *                                until the player to move has >= 2 options (run_utils.py:44-50; the reference's
+ *                                randint(1, 30) is u + 1); the searching player is the player to move at the root.
+ *   CTD_ROOTS_RANDOM_GAME        m uniform in [back_lo, back_hi]; root = games[-m] = step max(0, T + 1 - m), not moved forward
+ *                                (run_utils.py:52-72).  The searching player is the player to move there, BEFORE the forced
+ *                                moves CFRNode.skip_false_choice plays (run_utils.py:80-83, deep_mccfr.py:19-20).
+ * Fills the slot, the searching player's knowledge block, used_cards and tree id on the device.
  * root_step (may be NULL) receives the index of the root in the game's step sequence. */
+#define CTD_ROOTS_CLOSE_TO_FINISHED 0
+#define CTD_ROOTS_RANDOM_GAME 1
 ctd_status ctd_make_roots(ctd_engine* e, uint32_t n, uint64_t seed, uint64_t first_gid, int ruleset, uint32_t back_lo,
-                          uint32_t back_hi, uint32_t* root_step);
+                          uint32_t back_hi, int flavour, uint32_t* root_step);
 /* roots supplied by the caller (the facade's CFRNode(game, ...)) and read back */
 ctd_status ctd_load_roots(ctd_engine* e, uint32_t n, const ctd_state* roots, const void* knows, const uint8_t* used_cards,
                           const uint64_t* gids);
 ctd_status ctd_store_roots(ctd_engine* e, uint32_t n, ctd_state* roots, void* knows, uint8_t* used_cards, uint64_t* gids);
-/* size of one tree block for a given iteration budget */
-void ctd_mccfr_tree_shape(uint32_t iterations, int ruleset, uint32_t* max_nodes, uint32_t* child_cap, uint32_t* arr_cap,
-                          uint64_t* bytes);
+/* Tree memory.  The reference never refuses a root (its trees are Python objects), so trees are not fixed-size blocks: all trees
+ * of a call allocate nodes and arrays from one arena in HBM; a tree that finds it exhausted is searched again from a larger one.
+ * This reports the plan for n_roots trees: nodes in a tree's first chunk, bytes per node, bytes of the first arena. */
+void ctd_mccfr_tree_shape(uint32_t iterations, int ruleset, uint32_t n_roots, uint32_t* first_chunk_nodes, uint32_t* node_bytes,
+                          uint64_t* arena_bytes);
 /* CFRNode(game, original_player_id=game.gamestate.player_id).cfr_train(iterations) (run_utils.py:83-85,
  * algorithms/deep_mccfr.py:187-205) on roots [0,n_roots), one tree per warp.  results[n_roots] (may be NULL) gets
- * the root's arrays; trees_out (may be NULL) gets every tree block (n_roots * bytes of ctd_mccfr_tree_shape). */
+ * the root's arrays; the trees stay on the device for ctd_mccfr_targets / ctd_mccfr_export / ctd_mccfr_root_children. */
 ctd_status ctd_mccfr(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32_t iterations, int ruleset,
-                     ctd_mccfr_result* results, void* trees_out, float* elapsed_ms);
+                     ctd_mccfr_result* results, float* elapsed_ms);
+/* The trees of the last ctd_mccfr / ctd_mccfr_pred call, roots [first, first+n), as compact blocks back to back:
+ *   header (128 B) | nodes (1008 B: 160 B header, the 256-byte game record, the knowledge block) | children (16 B) | doubles
+ * (struct CtdTreeHdrOut / CtdNodeOut in csrc/ctd_mccfr.cuh; numpy mirror in layout.py).  sizes[n] always receives the byte size of
+ * every block; with buf == NULL nothing else happens, otherwise buf (buf_bytes >= the sum of sizes) is filled.
+ * This is what the facade's CFRNode.children walks (algorithms/deep_mccfr.py:24). */
+ctd_status ctd_mccfr_export(ctd_engine* e, uint32_t first, uint32_t n, uint64_t* sizes, void* buf, uint64_t buf_bytes);
+/* children [first, first+count) of the root of tree `tree`: option descriptors and, for vector roots, cumulative_regrets /
+ * strategy / cumulative_strategy (zeros for a role-pick root, whose 6 x 10 arrays are complete in the result record) */
+ctd_status ctd_mccfr_root_children(ctd_engine* e, uint32_t tree, uint32_t first, uint32_t count, ctd_option* options,
+                                   double* cumulative_regrets, double* strategy, double* cumulative_strategy);
 
 /* ---- value model at depth-limited leaves (algorithms/models.py ValueOnlyNN(418, 512), eval mode) ----
  * Weights are passed BatchNorm-folded and transposed to [in][out]: w1t [448][512] (rows 418..447 zero), b1 [512],
@@ -253,8 +285,7 @@ ctd_status ctd_encode(ctd_engine* e, uint32_t n, int cfr_role_pick, float* featu
  * leaf value, the value model runs once on the batch of all waiting leaves, the trees resume.
  * reward_weight is model_reward_weights (5 in the reference). */
 ctd_status ctd_mccfr_pred(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32_t iterations, uint32_t max_depth, int ruleset,
-                          float reward_weight, ctd_mccfr_result* results, void* trees_out, float* elapsed_ms,
-                          uint32_t* waves_out);
+                          float reward_weight, ctd_mccfr_result* results, float* elapsed_ms, uint32_t* waves_out);
 
 /* ---- training targets (algorithms/deep_mccfr.py:258-274, :321-345; tuple format generate_test_data.py:25) ---- */
 typedef struct ctd_target_meta {
@@ -267,7 +298,8 @@ typedef struct ctd_target_meta {
   double node_value[6];    /* target_node_value */
 } ctd_target_meta;
 /* CFRNode.get_all_targets() over the trees left on the device by the last ctd_mccfr / ctd_mccfr_pred call with the
- * same (n_roots, iterations, ruleset): one record per node with children and node_value.sum() >= threshold (the
+ * same n_roots (iterations / ruleset are ignored: the trees know their shape): one record per node of every tree that completed
+ * (status 0) with children and node_value.sum() >= threshold (the
  * reference always uses 15, algorithms/deep_mccfr.py:268,:321), depth-first pre-order per tree.  Call once with the
  * four output pointers NULL to learn the sizes, then with buffers of *n_records rows of 448 floats / metas and
  * *n_option_slots descriptors / doubles (regrets: row `seat` of a role-pick node's matrix; all-zero rows become ones). */

@@ -1506,8 +1506,15 @@ class Game:
         b = bytearray(256)
         b[0:128] = bytes(arena)
         b[128:155] = bytes(off)
+        s8 = lambda v: v - 256 if v >= 128 else v
         for p in range(6):
             b[156 + p] = self.gold[p] & 0xFF
+            # purses beyond a signed byte: 2-bit signed page next to the low byte (include/citadels_b200.h gold_hi03/45)
+            page = (self.gold[p] - s8(self.gold[p] & 0xFF)) >> 8
+            if p < 4:
+                b[231] |= (page & 3) << (2 * p)
+            else:
+                b[247] |= (page & 3) << (2 * (p - 4))
             b[162 + p] = self.role[p]
             b[168 + p] = int(self.replicas[p]) & 0xFF
             b[174 + p] = (1 if self.lighthouse[p] else 0) | (2 if self.first7[p] else 0) | (4 if self.witch[p] else 0)
@@ -1535,7 +1542,7 @@ class Game:
         b[218] = self.winner & 0xFF
         b[219] = self.wiz_target
         for p in range(6):
-            b[220 + p] = self.points[p] & 0xFF
+            b[220 + p] = max(-128, min(127, self.points[p])) & 0xFF   # the record saturates (engine sets its overflow flag)
         b[226] = self.warrant_building
         b[227] = self.ruleset
         # tier C scratch state lives in the engine-private tail but is game state all the same
@@ -1623,7 +1630,8 @@ class Game:
         g.deck, g.discard = seg[24], seg[25]
         s8 = lambda v: v - 256 if v >= 128 else v
         for p in range(6):
-            g.gold[p] = s8(rec[156 + p])
+            page = (rec[231] >> (2 * p)) & 3 if p < 4 else (rec[247] >> (2 * (p - 4))) & 3
+            g.gold[p] = s8(rec[156 + p]) + 256 * ((page ^ 2) - 2)
             g.role[p] = rec[162 + p]
             g.replicas[p] = s8(rec[168 + p])
             f = rec[174 + p]

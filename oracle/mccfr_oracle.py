@@ -6,6 +6,7 @@ reference.  Chance comes from one Philox stream per tree (oracle/philox.py, stre
                                                           cdf = cumsum(p); cdf /= cdf[-1]; searchsorted right)
   np.random.choice(range(n), uniform) in expand_*     -> randbelow(n)
   random.random() / random.choice / random.shuffle    -> uniform() / randbelow / perm
+  np.random.choice(options, p) in Game.get_option_from_role_preference (live role-pick decisions) -> inverse CDF, as above
 The reference harness (tests/golden/ref_harness.py) patches exactly those call sites of the real
 reference with the same mapping, which is how this file is pinned (tests/golden/check_mccfr_vs_ref.py).
 """
@@ -173,6 +174,21 @@ class Node:
         i = choice_p(ch, p)
         return self.children[i][1]
 
+    def live_choice(self):
+        """action_choice(live=True), :67-75 -- what run_mccfr returns (run_utils.py:82,86).  Ordinary roots: a child drawn from
+        the cumulative strategy, its stored option.  Role-pick roots: Game.get_option_from_role_preference (game/game.py:312-317)
+        on self.strategy[player to move]: that row has one entry per CHILD but is indexed by the RANKS on offer."""
+        ch = self.game.chance
+        if not self.role_pick:
+            if not self.children:
+                raise ValueError("a terminal root has no children")     # np.random.choice on an empty range
+            p = self.C / self.C.sum()
+            return self.children[choice_p(ch, p)][0]
+        opts = self.game.options()
+        sub = self.s[self.game.player][[O.d_rank(d) for d in opts]]
+        sub = sub / sub.sum()
+        return opts[choice_p(ch, sub)]
+
     def update_regrets(self):
         """:231-256."""
         if not self.role_pick:
@@ -242,20 +258,25 @@ class Node:
             yield from c.walk()
 
 
-def make_root(seed, gid, ruleset=O.RULESET_PRESET, back_lo=0, back_hi=20):
-    """Root construction as the engine defines it (ctd_make_roots, include/citadels_b200.h), restating
-    run_utils.create_a_close_to_finished_game (run_utils.py:29-50): play game (seed, gid) to terminal (T steps),
-    u = back_lo + randbelow(back_hi - back_lo + 1) from Philox stream word 2, k = max(0, T - u); replay to step k,
+def make_root(seed, gid, ruleset=O.RULESET_PRESET, back_lo=0, back_hi=20, flavour=0):
+    """Root construction as the engine defines it (ctd_make_roots, include/citadels_b200.h).
+    flavour 0 restates run_utils.create_a_close_to_finished_game (run_utils.py:29-50): play game (seed, gid) to terminal
+    (T steps), u = back_lo + randbelow(back_hi - back_lo + 1) from Philox stream word 2, k = max(0, T - u); replay to step k,
     then keep stepping while the player to move has fewer than 2 options (at most 100 times).
-    Returns (game, root_step)."""
+    flavour 1 restates run_utils.create_a_random_game (run_utils.py:52-72): m drawn the same way, root = games[-m] = the
+    state after max(0, T + 1 - m) steps, not moved forward (CFRNode.skip_false_choice does that, AFTER run_mccfr fixed the
+    searching player).
+    Returns (game, root_step); the searching player is game.player."""
     from .philox import PhiloxChance
     T = O.playout(seed, gid, ruleset)[2]
     u = back_lo + PhiloxChance(seed, gid, stream=2).randbelow(back_hi - back_lo + 1)
-    k = max(0, T - u)
+    k = max(0, (T + 1 if flavour == 1 else T) - u)
     ch = PhiloxChance(seed, gid)
     g = O.new_game(ch, ruleset)
     steps = limit = 0
     while not g.terminal:
+        if flavour == 1 and steps >= k:
+            break
         opts = g.options()
         if steps >= k:
             if len(opts) >= 2 or limit >= 100:

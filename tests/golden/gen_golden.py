@@ -206,6 +206,88 @@ def _mccfr_one(args):
     return out
 
 
+def _live_one(args):
+    """run_utils.run_mccfr(game, model, max_iterations) of the REAL reference on one root: the option it decides on
+    (root.action_choice(live=True)[1]) and the root's arrays.  Root as ctd_make_roots defines it; chance: Philox stream 0 for
+    the game, stream 1 for the search AND the decision after it (the reference draws both from the global RNGs in that order)."""
+    gid, ruleset, back_hi, iters, deep = args
+    from oracle.philox import PhiloxChance
+    from tests.golden import ref_harness as H
+    H.patch_cfr_chance()
+    import run_utils
+    ch = PhiloxChance(SEED, gid)
+    g = H.new_ref_game(ch, ruleset)
+    T = 0
+    while True:
+        H.set_chance(ch)
+        o = g.get_options_from_state()
+        T += 1
+        if o[ch.randbelow(len(o))].carry_out(g):
+            break
+    u = PhiloxChance(SEED, gid, stream=2).randbelow(back_hi + 1)
+    k = max(0, T - u)
+    ch = PhiloxChance(SEED, gid)
+    g = H.new_ref_game(ch, ruleset)
+    steps = limit = 0
+    while not g.terminal:
+        H.set_chance(ch)
+        o = g.get_options_from_state()
+        if steps >= k:
+            if len(o) >= 2 or limit >= 100:
+                break
+            limit += 1
+        o[ch.randbelow(len(o))].carry_out(g)
+        steps += 1
+    viewer = g.gamestate.player_id
+    out = dict(gid=gid, root=H.ref_pack(g, ruleset), know=H.ref_pack_know(g, viewer),
+               used=bytes(H.card_code(c) for c in g.used_cards.cards).ljust(76, b"\xff"), terminal=bool(g.terminal),
+               live=0, role_pick=False, nchild=0, draws=0)
+    if g.terminal:
+        return out
+    tree = PhiloxChance(SEED, gid, stream=1)
+    H.set_chance(tree)
+    model = None
+    if deep:
+        import torch
+        from algorithms.models import ValueOnlyNN
+        torch.set_num_threads(1)
+        torch.manual_seed(0)
+        model = ValueOnlyNN(418, 512).eval()
+        import algorithms.deep_mccfr as dm
+        _init = dm.CFRNode.__init__
+        if not getattr(dm.CFRNode, "_cpu_default", False):      # run_mccfr builds CFRNode with device="cuda:0": no GPU here
+            def init(self, *a, **kw):
+                kw["device"] = "cpu"
+                _init(self, *a, **kw)
+            dm.CFRNode.__init__ = init
+            dm.CFRNode._cpu_default = True
+    chosen, root = run_utils.run_mccfr(g, model=model, max_iterations=iters)
+    out["draws"] = tree.i
+    out["live"] = H.ref_descriptors([chosen])[0]
+    out["role_pick"] = bool(root.role_pick_node)
+    out["nchild"] = len(root.children)
+    return out
+
+
+def gen_live(name, ruleset, gids, back_hi, iters, deep=0, procs=8):
+    with Pool(procs) as pool:
+        res = pool.map(_live_one, [(g, ruleset, back_hi, iters, deep) for g in gids], chunksize=2)
+    out = dict(seed=np.uint64(SEED), ruleset=np.int32(ruleset), iterations=np.int32(iters), back_hi=np.int32(back_hi),
+               max_depth=np.int32(deep), gids=np.asarray(gids, dtype=np.uint64),
+               roots=np.frombuffer(b"".join(r["root"] for r in res), dtype=np.uint8).reshape(-1, 256),
+               knows=np.frombuffer(b"".join(r["know"] for r in res), dtype=np.uint8).reshape(-1, 592),
+               used=np.frombuffer(b"".join(r["used"] for r in res), dtype=np.uint8).reshape(-1, 76),
+               terminal=np.asarray([r["terminal"] for r in res], dtype=bool),
+               live=np.asarray([r["live"] for r in res], dtype=np.uint64),
+               role_pick=np.asarray([r["role_pick"] for r in res], dtype=bool),
+               nchild=np.asarray([r["nchild"] for r in res], dtype=np.int32),
+               draws=np.asarray([r["draws"] for r in res], dtype=np.int64))
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **out)
+    print(name, "roots", len(gids), "role-pick roots", int(out["role_pick"].sum()), "terminal", int(out["terminal"].sum()),
+          "bytes", os.path.getsize(path))
+
+
 def gen_mccfr(name, ruleset, gids, back_hi, iters, procs=8, deep=0):
     with Pool(procs) as pool:
         res = pool.map(_mccfr_one, [(g, ruleset, back_hi, iters, deep) for g in gids], chunksize=1)
@@ -260,6 +342,13 @@ if __name__ == "__main__":
         gen_mccfr("mccfr_preset_2000it.npz", 0, list(range(3200, 3206)), 45, 2000)
     if what in ("all", "deep"):
         gen_mccfr("deep_mccfr_preset.npz", 0, list(range(4000, 4016)), 120, 200, deep=10)
+    if what in ("all", "live"):
+        # run_mccfr's decisions (action_choice(live=True)): late-game roots, early roots (many role-pick roots), deluxe rulesets, deep
+        gen_live("live_choice_preset.npz", 0, list(range(5000, 5160)), 20, 200)
+        gen_live("live_choice_preset_early.npz", 0, list(range(5200, 5296)), 400, 120)
+        gen_live("live_choice_classic.npz", 1, list(range(105000, 105024)), 60, 120)
+        gen_live("live_choice_random.npz", 2, list(range(205000, 205024)), 80, 120)
+        gen_live("live_choice_deep_preset.npz", 0, list(range(5400, 5424)), 200, 200, deep=10)
     if what in ("all", "outcomes"):
         gen_outcomes("ref_outcomes_preset.npz", 20000)
     if what in ("all", "outcomes", "outcomes_bc"):

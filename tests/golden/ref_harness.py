@@ -258,7 +258,7 @@ def patch_cfr_chance():
         ch = _state["chance"]
         n = len(a)
         caller = sys._getframe(1).f_code.co_name
-        if caller == "action_choice":
+        if caller in ("action_choice", "get_option_from_role_preference"):
             cdf = np.cumsum(p)
             cdf = cdf / cdf[-1]
             i = min(int(np.searchsorted(cdf, ch.uniform(), side="right")), n - 1)

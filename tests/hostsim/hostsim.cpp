@@ -72,71 +72,91 @@ int hs_playout(uint64_t seed, uint64_t gid, int ruleset, uint32_t max_steps, int
 }
 int hs_sizeof_work() { return (int)sizeof(CtdWork); }
 
-// pure MCCFR on one root, tree built in `tree_buf` (ctd_tree_bytes(max_nodes, child_cap, arr_cap) bytes)
-int hs_mccfr(const ctd_state* root, const CtdKnow* know, const uint8_t* used_cards, uint64_t seed, uint64_t gid,
-             uint32_t iters, uint32_t max_nodes, uint32_t child_cap, uint32_t arr_cap, uint8_t* tree_buf) {
-  static CtdKnow kn;
-  static uint64_t opts[CTD_MCCFR_OPT_CAP];
-  static uint8_t scratch[384] __attribute__((aligned(16)));
+// ctd_make_roots for one root: record, the searching player's knowledge block, used_cards, root step; returns the searching seat
+int hs_make_root(uint64_t seed, uint64_t gid, int ruleset, uint32_t back_lo, uint32_t back_hi, int flavour, ctd_state* root,
+                 CtdKnow* know, uint8_t* used_cards, uint32_t* root_step) {
+  static CtdKnow kn6[6];
   CtdWork& w = g_w;
   memset(&w, 0, sizeof(w));
+  const int viewer = ctd_make_root(w, kn6, seed, gid, ruleset, back_lo, back_hi, flavour, used_cards, root_step);
+  *know = kn6[viewer];
+  ctd_pack(w, root);
+  return viewer;
+}
+
+// One tree on the host: `arena` (arena_bytes) is what the tree allocates from, the result is the compact export block in `out`
+// (out_cap bytes; *out_bytes receives its size).  Returns the tree status, or -1 when `out` is too small.
+struct HsTree {
+  CtdTreeHdr hdr;
+  unsigned long long used;
   CtdTree T;
-  T.hdr = (CtdTreeHdr*)tree_buf;
-  T.nodes = (CtdNode*)(tree_buf + sizeof(CtdTreeHdr));
-  T.children = (CtdChild*)((uint8_t*)T.nodes + (size_t)max_nodes * sizeof(CtdNode));
-  T.arr = (double*)((uint8_t*)T.children + (size_t)child_cap * sizeof(CtdChild));
-  static ctd_state hs_stage __attribute__((aligned(16)));
-  T.w = &w; T.kn = &kn; T.opts = opts; T.scratch = scratch; T.stage = &hs_stage;
-  memset(tree_buf, 0, ctd_tree_bytes(max_nodes, child_cap, arr_cap));
-  memcpy(T.hdr->used_cards, used_cards, 76);
+};
+static CtdKnow hs_kn;
+static uint64_t hs_opts[CTD_MCCFR_OPT_CAP];
+static uint8_t hs_scratch[384] __attribute__((aligned(16)));
+static ctd_state hs_stage __attribute__((aligned(16)));
+
+static void hs_tree_begin(HsTree& H, const ctd_state* root, const CtdKnow* know, const uint8_t* used_cards, uint64_t seed, uint64_t gid,
+                          uint32_t iters, uint8_t* arena, uint64_t arena_bytes, bool model) {
+  CtdWork& w = g_w;
+  memset(&w, 0, sizeof(w));
+  memset(&H.hdr, 0, sizeof(H.hdr));
+  H.used = 1;
+  CtdTree& T = H.T;
+  T.w = &w; T.kn = &hs_kn; T.opts = hs_opts; T.scratch = hs_scratch; T.stage = &hs_stage;
+  T.hdr = &H.hdr;
+  memcpy(H.hdr.used_cards, used_cards, 76);
   ctd_tree_stage_used(T);
   ctd_unpack(root, w);
   ctd_chance_init(w, seed, gid, 0);
   w.stream = 1;
-  kn = *know;
-  ctd_tree_init(T, max_nodes, child_cap, arr_cap, know->viewer, gid, false, false);
-  ctd_cfr_train(T, iters);
-  ctd_tree_pack_nodes(T);
-  if (getenv("HS_DEBUG")) fprintf(stderr, "hs_mccfr gid %llu status %u w.err %u kn.err %u nodes %u\n", (unsigned long long)gid,
-                                  T.hdr->status, w.err, kn.err, T.hdr->n_nodes);
-  return (int)T.hdr->status;
+  hs_kn = *know;
+  uint32_t k = 6;   // ctd_n0_log2 of the engine
+  while (k < 20 && (1ull << k) < 2ull * iters) ++k;
+  if (getenv("HS_N0_LOG2")) k = (uint32_t)atoi(getenv("HS_N0_LOG2"));   // tests: small first chunk exercises the chunk table
+  CtdArena ar{arena, &H.used, arena_bytes / CTD_ARENA_UNIT};
+  ctd_tree_init(T, &H.hdr, ar, k, know->viewer, gid, false, model);
+}
+static uint64_t hs_live = 0;
+extern "C" uint64_t hs_last_live_option() { return hs_live; }   // ctd_live_choice of the tree built last
+static int hs_tree_end(HsTree& H, uint8_t* out, uint64_t out_cap, uint64_t* out_bytes) {
+  hs_live = ctd_live_choice(H.T);
+  const uint64_t need = ctd_tree_export_bytes(H.hdr.n_nodes, H.hdr.child_used, H.hdr.arr_used);
+  if (out_bytes) *out_bytes = need;
+  if (getenv("HS_DEBUG")) fprintf(stderr, "hs tree gid %llu status %u w.err %u kn.err %u nodes %u arena units %llu\n", (unsigned long long)H.hdr.gid,
+                                  H.hdr.status, g_w.err, hs_kn.err, H.hdr.n_nodes, H.used);
+  if (out) {
+    if (need > out_cap) return -1;
+    memset(out, 0, need);
+    ctd_tree_export(H.T, out);
+  }
+  return (int)H.hdr.status;
+}
+
+int hs_mccfr(const ctd_state* root, const CtdKnow* know, const uint8_t* used_cards, uint64_t seed, uint64_t gid, uint32_t iters,
+             uint8_t* arena, uint64_t arena_bytes, uint8_t* out, uint64_t out_cap, uint64_t* out_bytes) {
+  static HsTree H;
+  hs_tree_begin(H, root, know, used_cards, seed, gid, iters, arena, arena_bytes, false);
+  ctd_cfr_train(H.T, iters);
+  return hs_tree_end(H, out, out_cap, out_bytes);
 }
 int hs_sizeof_node() { return (int)sizeof(CtdNode); }
 
 // deep MCCFR on one root; `eval(features[448], pred[6])` stands in for the batched value kernel
 typedef void (*hs_eval_fn)(const float*, float*);
 int hs_mccfr_pred(const ctd_state* root, const CtdKnow* know, const uint8_t* used_cards, uint64_t seed, uint64_t gid,
-                  uint32_t iters, uint32_t max_depth, uint32_t max_nodes, uint32_t child_cap, uint32_t arr_cap,
-                  uint8_t* tree_buf, hs_eval_fn eval) {
-  static CtdKnow kn;
-  static uint64_t opts[CTD_MCCFR_OPT_CAP];
-  static uint8_t scratch[384] __attribute__((aligned(16)));
+                  uint32_t iters, uint32_t max_depth, uint8_t* arena, uint64_t arena_bytes, uint8_t* out, uint64_t out_cap,
+                  uint64_t* out_bytes, hs_eval_fn eval) {
+  static HsTree H;
   static float feat[CTD_FEATURES_PAD], pred[8];
-  CtdWork& w = g_w;
-  memset(&w, 0, sizeof(w));
-  CtdTree T;
-  T.hdr = (CtdTreeHdr*)tree_buf;
-  T.nodes = (CtdNode*)(tree_buf + sizeof(CtdTreeHdr));
-  T.children = (CtdChild*)((uint8_t*)T.nodes + (size_t)max_nodes * sizeof(CtdNode));
-  T.arr = (double*)((uint8_t*)T.children + (size_t)child_cap * sizeof(CtdChild));
-  static ctd_state hs_stage __attribute__((aligned(16)));
-  T.w = &w; T.kn = &kn; T.opts = opts; T.scratch = scratch; T.stage = &hs_stage;
-  memset(tree_buf, 0, ctd_tree_bytes(max_nodes, child_cap, arr_cap));
-  memcpy(T.hdr->used_cards, used_cards, 76);
-  ctd_tree_stage_used(T);
-  ctd_unpack(root, w);
-  ctd_chance_init(w, seed, gid, 0);
-  w.stream = 1;
-  kn = *know;
-  ctd_tree_init(T, max_nodes, child_cap, arr_cap, know->viewer, gid, false, true);
+  hs_tree_begin(H, root, know, used_cards, seed, gid, iters, arena, arena_bytes, true);
   // a small per-call budget exercises the yield / resume path of the wave scheduler as well
   const uint32_t budget = getenv("HS_PRED_BUDGET") ? (uint32_t)atoi(getenv("HS_PRED_BUDGET")) : 7u;
   for (;;) {
-    const int r = ctd_cfr_pred_advance(T, iters, max_depth, feat, pred, budget);
+    const int r = ctd_cfr_pred_advance(H.T, iters, max_depth, feat, pred, budget);
     if (r == CTD_PRED_DONE) break;
     if (r == CTD_PRED_WAIT) eval(feat, pred);
   }
-  ctd_tree_pack_nodes(T);
-  return (int)T.hdr->status;
+  return hs_tree_end(H, out, out_cap, out_bytes);
 }
 }

@@ -38,10 +38,9 @@ def test_search_batch_decisions_are_legal_and_match_single_tree_searches():
         games.append(g)
     eng = Engine(capacity=16)
     res = arena.search_batch(eng, games, [0] * len(games), None, iterations=120)
-    nprng = np.random.default_rng(1)
     for g, r in zip(games, res):
         opts = g.get_options_from_state()
-        ch = arena._live_choice(r, g, opts, nprng)
+        ch = arena._live_choice(r, g, opts)
         assert ch.desc in [o.desc for o in opts]
         # the same root searched alone through the facade's CFRNode: same tree (stream keyed by the game id, decision 0)
         node = F.CFRNode(g, original_player_id=g.gamestate.player_id)

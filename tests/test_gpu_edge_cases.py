@@ -33,7 +33,8 @@ def test_argument_and_capacity_errors_are_status_codes(engine):
     assert lib.ctd_reset(None, 8, 1, 0, 0) == 1                     # null handle
     assert lib.ctd_enumerate(h, 8, None, cnt.ctypes.data, 8) == 1   # null output
     assert lib.ctd_enumerate(h, 8, buf.ctypes.data, cnt.ctypes.data, 0) == 1
-    assert lib.ctd_make_roots(h, 8, 1, 0, 0, 5, 2, None) == 1       # back_hi < back_lo
+    assert lib.ctd_make_roots(h, 8, 1, 0, 0, 5, 2, 0, None) == 1    # back_hi < back_lo
+    assert lib.ctd_make_roots(h, 8, 1, 0, 0, 1, 2, 7, None) == 1    # unknown flavour
     st = ctypes.c_void_p()
     assert lib.ctd_create(0, 0, ctypes.byref(st)) in (0, 1)         # zero capacity: accepted or refused, never a crash
     if st.value:

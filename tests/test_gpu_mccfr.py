@@ -37,23 +37,31 @@ def test_trees_match_reference(engine, name):
         assert np.allclose(res["cumulative_regrets"][:n], root["R"][:n], rtol=1e-9, atol=1e-12)
         assert np.allclose(res["cumulative_strategy"][:n], root["C"][:n], rtol=1e-9, atol=1e-12)
         assert np.allclose(res["node_value"], root["V"], rtol=1e-9, atol=1e-12)
+        if not res["role_pick"] and k:
+            # the full child arrays of a root, however many (ctd_mccfr_root_children; a result record stops at 128)
+            o, R, S, C = engine.root_children(r, 0, k)
+            assert np.array_equal(o, out["trees"][r].children["desc"][:k])
+            assert np.allclose(R, root["R"], rtol=1e-9, atol=1e-12) and np.allclose(C, root["C"], rtol=1e-9, atol=1e-12)
+            assert np.allclose(S, root["S"], rtol=1e-9, atol=1e-12)
 
 
 def test_make_roots_matches_oracle(engine):
     """Device root construction (two-pass replay with knowledge of all six observers) vs the oracle."""
     from oracle import mccfr_oracle as M
     seed, gid0, n = 777, 50_000, 48
-    for ruleset, lo, hi in ((0, 0, 20), (0, 1, 100), (1, 0, 60)):
-        steps = engine.make_roots(n, seed=seed, first_gid=gid0, ruleset=ruleset, back_lo=lo, back_hi=hi)
+    from tests.golden_util import visible
+    # (ruleset, back_lo, back_hi, flavour): create_a_close_to_finished_game and create_a_random_game, all three rulesets
+    for ruleset, lo, hi, flavour in ((0, 0, 20, 0), (0, 1, 100, 1), (1, 0, 60, 0), (2, 0, 80, 0), (2, 1, 100, 1)):
+        steps = engine.make_roots(n, seed=seed, first_gid=gid0, ruleset=ruleset, back_lo=lo, back_hi=hi, flavour=flavour)
         roots, knows, used, gids = engine.store_roots(n)
         for i in range(0, n, 3):
-            g, st = M.make_root(seed, gid0 + i, ruleset, lo, hi)
+            g, st = M.make_root(seed, gid0 + i, ruleset, lo, hi, flavour)
             assert st == int(steps[i]) and int(gids[i]) == gid0 + i
-            assert roots[i, :228].tobytes() == g.pack()[:228]
+            assert visible(roots[i].tobytes()) == visible(g.pack())
             assert roots[i, 228] == 0
             if not g.terminal:
                 assert knows[i].tobytes() == g.pack_know(g.player)
-            assert used[i].tobytes() == bytes(g.used_cards)
+            assert used[i].tobytes() == bytes(g.used_cards) + b"\xff" * (76 - len(g.used_cards))
 
 
 def test_mccfr_fresh_roots_vs_oracle(engine):
@@ -97,20 +105,57 @@ def test_mccfr_hundreds_of_fresh_roots_vs_oracle(engine, ruleset, n):
     jobs = [(roots[i], knows[i], used[i], seed, int(gids[i]), iters) for i in live]
     with mp.get_context("spawn").Pool(min(16, os.cpu_count() or 1)) as pool:      # not fork: this process holds a CUDA context
         want = pool.map(_oracle_root_summary, jobs, chunksize=2)
-    flagged = 0
     for i, (R, C, V, nodes, draws) in zip(live, want):
         r = res[i]
-        if ruleset == 2 and r["status"] == 4:
-            # a hypothetical game of this tree outgrew a container (a city of more than 32 districts: the Cardinal builds
-            # without limit and CFR's determinisation does not conserve cards): reported per tree, never silently wrong
-            flagged += 1
-            continue
+        # every non-terminal root completes, as in the reference (run-away hypothetical games of the random rulesets -- cities
+        # of 40 districts, purses of thousands -- included: csrc/ctd_engine.cuh container capacities)
         assert r["status"] == 0 and int(r["n_nodes"]) == nodes and int(r["rng_draws"]) == draws, (ruleset, i)
         k = min(len(R), 60 if r["role_pick"] else 128)
         assert np.allclose(r["cumulative_regrets"][:k], R[:k], rtol=1e-9, atol=1e-12), (ruleset, i)
         assert np.allclose(r["cumulative_strategy"][:k], C[:k], rtol=1e-9, atol=1e-12), (ruleset, i)
         assert np.allclose(r["node_value"], V, rtol=1e-9, atol=1e-12), (ruleset, i)
-    assert flagged <= 2
+
+
+def test_roots_the_fixed_pool_refused_now_complete(engine):
+    """The two preset roots of the 8-GPU driver run of round 1 that ended with status 2 (more than 8 nodes per iteration:
+    gids 11543 and 14440 under seed 0xC17ADE15, roots stepped back 0..20) and neighbours, against the oracle."""
+    from oracle import mccfr_oracle as M
+    seed = 0xC17ADE15
+    for gid0 in (11540, 14436):
+        engine.make_roots(8, seed=seed, first_gid=gid0, back_lo=0, back_hi=20)
+        roots, knows, used, gids = engine.store_roots(8)
+        out = engine.mccfr(8, iterations=200, seed=seed, trees=True)
+        assert int(out["results"]["n_nodes"].max()) > 2112          # what the fixed pool of round 1 held
+        for i in range(8):
+            assert out["results"][i]["status"] in (0, 1)
+            if out["results"][i]["n_nodes"] > 2112:
+                node = M.run_from_root(roots[i], knows[i], used[i], seed, int(gids[i]), 200)
+                assert_same_tree(oracle_preorder(node), tree_preorder(out["trees"][i]), ("big", gid0 + i))
+
+
+def test_exhausted_arena_is_retried(engine, monkeypatch):
+    """Tree memory: with the first arena squeezed to a sliver most trees find it exhausted; the engine searches them again from
+    further arenas and the call returns the same trees as an unconstrained run."""
+    n = 96
+    engine.make_roots(n, seed=99, first_gid=7000, back_lo=0, back_hi=20)
+    want = engine.mccfr(n, iterations=200, seed=99)["results"]
+    monkeypatch.setenv("CTD_ARENA0_BYTES", str(24 << 20))
+    got = engine.mccfr(n, iterations=200, seed=99)["results"]
+    monkeypatch.delenv("CTD_ARENA0_BYTES")
+    assert (got["status"] <= 1).all()
+    for f in ("status", "n_nodes", "rng_draws", "n_children", "cumulative_regrets", "cumulative_strategy", "node_value"):
+        assert np.array_equal(got[f], want[f]), f
+    from citadels_self_play_b200.value_model import ValueOnlyNN
+    import torch
+    torch.manual_seed(0)
+    engine.set_value_model(ValueOnlyNN(418, 512).eval())
+    want = engine.mccfr_pred(n, iterations=200, max_depth=10, seed=99)["results"]
+    monkeypatch.setenv("CTD_ARENA0_BYTES", str(24 << 20))
+    got = engine.mccfr_pred(n, iterations=200, max_depth=10, seed=99)["results"]
+    monkeypatch.delenv("CTD_ARENA0_BYTES")
+    assert (got["status"] <= 1).all()
+    for f in ("n_nodes", "rng_draws", "cumulative_regrets", "node_value"):
+        assert np.array_equal(got[f], want[f]), f
 
 
 # ---------------------------------------------------------------- deep MCCFR (config 4)

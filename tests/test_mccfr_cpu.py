@@ -38,30 +38,52 @@ def hostsim():
     subprocess.check_call(["make", "-s", "-C", d])
     lib = ctypes.CDLL(os.path.join(d, "libctd_hostsim.so"))
     u64, u32, vp = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p
-    lib.hs_mccfr.argtypes = [vp, vp, vp, u64, u64, u32, u32, u32, u32, vp]
+    lib.hs_mccfr.argtypes = [vp, vp, vp, u64, u64, u32, vp, u64, vp, u64, vp]
     return lib
+
+
+ARENA = np.zeros(192 << 20, np.uint8)     # what one host-built tree allocates from
+OUT = np.zeros(64 << 20, np.uint8)        # its export block
 
 
 @pytest.mark.parametrize("name", FIXTURES)
 def test_kernel_mccfr_host_build_matches_reference(hostsim, name):
     """ctd_mccfr.cuh (the code ctd_k_mccfr runs), compiled for the host, against the reference's trees."""
-    from citadels_self_play_b200.layout import TreeView, tree_bytes
+    from citadels_self_play_b200.layout import TreeView
     G = MccfrGolden(name)
     z = G.z
-    extra = 8192 if G.ruleset != 0 else 0
-    mn = 6 * G.iterations + 256 + extra
-    cc = mn + 10 * (G.iterations + 2)
-    ac = 3 * cc + 180 * 64
-    buf = np.zeros(tree_bytes(mn, cc, ac), np.uint8)
+    nb = ctypes.c_uint64()
     for r in range(G.n):
         root, know, used = (np.ascontiguousarray(z[k][r]) for k in ("roots", "knows", "used"))
         st = hostsim.hs_mccfr(root.ctypes.data, know.ctypes.data, used.ctypes.data, G.seed, int(G.gids[r]), G.iterations,
-                              mn, cc, ac, buf.ctypes.data)
+                              ARENA.ctypes.data, ARENA.nbytes, OUT.ctypes.data, OUT.nbytes, ctypes.byref(nb))
         if z["terminal"][r]:
             assert st == 1
             continue
         assert st == 0
-        assert_same_tree(G.nodes(r), tree_preorder(TreeView(buf, mn, cc, ac)), (name, r))
+        assert_same_tree(G.nodes(r), tree_preorder(TreeView(OUT[:nb.value])), (name, r))
+
+
+def test_kernel_tree_memory_chunks_and_exhaustion(hostsim, monkeypatch):
+    """Tree memory: a tree that outgrows its first chunk continues in further chunks (same tree, node for node), and an
+    exhausted arena is reported as status 2 (the engine then searches the tree again from a larger arena), never a crash."""
+    from citadels_self_play_b200.layout import TreeView
+    G = MccfrGolden("mccfr_preset.npz")
+    z = G.z
+    r = next(i for i in range(G.n) if not z["terminal"][i])
+    root, know, used = (np.ascontiguousarray(z[k][r]) for k in ("roots", "knows", "used"))
+    nb = ctypes.c_uint64()
+    args = (root.ctypes.data, know.ctypes.data, used.ctypes.data, G.seed, int(G.gids[r]), G.iterations)
+    monkeypatch.setenv("HS_N0_LOG2", "3")    # eight nodes in chunk 0: the tree lives almost entirely behind the chunk table
+    st = hostsim.hs_mccfr(*args, ARENA.ctypes.data, ARENA.nbytes, OUT.ctypes.data, OUT.nbytes, ctypes.byref(nb))
+    assert st == 0
+    assert_same_tree(G.nodes(r), tree_preorder(TreeView(OUT[:nb.value])), ("chunked", r))
+    monkeypatch.delenv("HS_N0_LOG2")
+    st = hostsim.hs_mccfr(*args, ARENA.ctypes.data, 1 << 20, None, 0, ctypes.byref(nb))   # chunk 0 alone needs 1.3 MB
+    assert st & 2
+    monkeypatch.setenv("HS_N0_LOG2", "5")
+    st = hostsim.hs_mccfr(*args, ARENA.ctypes.data, 300 << 10, None, 0, ctypes.byref(nb))   # runs dry mid-search
+    assert st & 2
 
 
 # ---------------------------------------------------------------- deep MCCFR (config 4)
@@ -100,32 +122,30 @@ def test_oracle_deep_trees_match_reference(name):
 
 @pytest.mark.parametrize("name", DEEP)
 def test_kernel_deep_mccfr_host_build_matches_reference(hostsim, name):
-    from citadels_self_play_b200.layout import TreeView, tree_bytes
+    from citadels_self_play_b200.layout import TreeView
     from citadels_self_play_b200.value_model import reference_value
     G = MccfrGolden(name)
     z = G.z
     model = _model()
     u64, u32, vp = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p
     EVAL = ctypes.CFUNCTYPE(None, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float))
-    hostsim.hs_mccfr_pred.argtypes = [vp, vp, vp, u64, u64, u32, u32, u32, u32, u32, vp, EVAL]
+    hostsim.hs_mccfr_pred.argtypes = [vp, vp, vp, u64, u64, u32, u32, vp, u64, vp, u64, vp, EVAL]
 
     def ev(fp, pp):
         p = reference_value(model, np.ctypeslib.as_array(fp, shape=(448,))[None, :])[0]
         for i in range(6):
             pp[i] = float(p[i])
     cb = EVAL(ev)
-    mn = 6 * G.iterations + 256 + (8192 if G.ruleset != 0 else 0)
-    cc = mn + 10 * (G.iterations + 2)
-    ac = 3 * cc + 180 * 64
-    buf = np.zeros(tree_bytes(mn, cc, ac), np.uint8)
+    nb = ctypes.c_uint64()
     for r in range(G.n):
         root, know, used = (np.ascontiguousarray(z[k][r]) for k in ("roots", "knows", "used"))
         if z["terminal"][r]:
             continue
         st = hostsim.hs_mccfr_pred(root.ctypes.data, know.ctypes.data, used.ctypes.data, G.seed, int(G.gids[r]),
-                                   G.iterations, int(z["max_depth"]), mn, cc, ac, buf.ctypes.data, cb)
+                                   G.iterations, int(z["max_depth"]), ARENA.ctypes.data, ARENA.nbytes, OUT.ctypes.data, OUT.nbytes,
+                                   ctypes.byref(nb), cb)
         assert st == 0
-        assert_same_tree(G.nodes(r), tree_preorder(TreeView(buf, mn, cc, ac)), ("deep-host", r), rtol=1e-7, atol=1e-10)
+        assert_same_tree(G.nodes(r), tree_preorder(TreeView(OUT[:nb.value])), ("deep-host", r), rtol=1e-7, atol=1e-10)
 
 
 def test_oracle_encode_game_layout():
@@ -182,3 +202,27 @@ def test_oracle_training_targets_match_reference(name):
 
 
 O_DISCARD = 25   # index of discard_and_draw in game/option.py:34-45
+
+
+@pytest.mark.parametrize("ruleset,flavour,lo,hi,gids", [
+    (0, 0, 0, 20, range(9000, 9012)), (0, 1, 1, 100, range(9100, 9112)),
+    (1, 0, 0, 60, range(109000, 109006)), (2, 0, 0, 80, list(range(209000, 209008)) + [204827]),
+    (2, 1, 1, 100, range(209100, 209106))])
+def test_kernel_root_construction_matches_oracle(hostsim, ruleset, flavour, lo, hi, gids):
+    """ctd_make_roots (both flavours: run_utils.create_a_close_to_finished_game / create_a_random_game) against the oracle's
+    make_root: root record, the searching player's knowledge block, used_cards, root step."""
+    from tests.golden_util import visible
+    u64, u32, vp, i32 = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int
+    hostsim.hs_make_root.argtypes = [u64, u64, i32, u32, u32, i32, vp, vp, vp, vp]
+    root, know, used, step = np.zeros(256, np.uint8), np.zeros(592, np.uint8), np.zeros(76, np.uint8), np.zeros(1, np.uint32)
+    SEED = 0xC17ADE15
+    for gid in gids:
+        viewer = hostsim.hs_make_root(SEED, gid, ruleset, lo, hi, flavour, root.ctypes.data, know.ctypes.data, used.ctypes.data,
+                                      step.ctypes.data)
+        g, steps = M.make_root(SEED, gid, ruleset, lo, hi, flavour)
+        assert steps == int(step[0]), (gid, steps, int(step[0]))
+        assert visible(g.pack()) == visible(root.tobytes()), gid
+        if not g.terminal:
+            assert viewer == g.player
+            assert g.pack_know(viewer) == know.tobytes(), gid
+            assert bytes(g.used_cards) + b"\xff" * (76 - len(g.used_cards)) == used.tobytes(), gid
