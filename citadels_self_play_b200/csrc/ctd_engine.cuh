@@ -300,6 +300,35 @@ CTD_HD inline void ctd_shuffle(CtdWork& w, int n, At at) {
     w.tape_pos += n;
     return;
   }
+#if defined(__CUDA_ARCH__) && defined(CTD_COOP_SHUFFLE)
+  // Search kernels: the whole warp runs this code converged.  The draws of a shuffle are known in advance (draw k bounds
+  // i = n-1-k), so 32 of them are produced at once -- every lane runs Philox for the block holding its draw and reduces it to a
+  // swap index -- and only the swaps themselves stay sequential.  Same draws, same order, same result as the loop below.
+  if (n >= 12 && __activemask() == 0xFFFFFFFFu) {
+    const int lane = threadIdx.x & 31;
+    int i = n - 1;
+    CTD_LOOP while (i > 0) {
+      const int cnt = i < 32 ? i : 32;               // swaps of this batch: i, i-1, ..., i-cnt+1
+      __syncwarp();
+      if (lane < cnt) {
+        const uint32_t dr = w.draws + (uint32_t)lane;
+        uint32_t r[4];
+        ctd_philox(dr >> 2, w.stream, w.g0, w.g1, w.k0, w.k1, r);
+        w.scratch[lane] = (uint8_t)(((uint64_t)r[dr & 3u] * (uint32_t)(i - lane + 1)) >> 32);
+      }
+      __syncwarp();
+      CTD_LOOP for (int k = 0; k < cnt; ++k) {
+        const int j = w.scratch[k];
+        const uint8_t a = at(i - k), b = at(j);
+        at(i - k) = b; at(j) = a;
+      }
+      __syncwarp();
+      w.draws += (uint32_t)cnt;
+      i -= cnt;
+    }
+    return;
+  }
+#endif
   CTD_LOOP for (int i = n - 1; i > 0; --i) {
     int j = (int)ctd_randbelow(w, (uint32_t)(i + 1));
     uint8_t a = at(i), b = at(j);
@@ -307,6 +336,14 @@ CTD_HD inline void ctd_shuffle(CtdWork& w, int n, At at) {
   }
 }
 
+
+// every shuffle of a contiguous byte array goes through one out-of-line copy (the kernels pay for their instruction footprint)
+#ifndef CTD_SHUFFLE_ATTR
+#define CTD_SHUFFLE_ATTR CTD_NI
+#endif
+CTD_HD CTD_SHUFFLE_ATTR inline void ctd_shuffle_bytes(CtdWork& w, uint8_t* a, int n) {
+  ctd_shuffle(w, n, [a](int i) -> uint8_t& { return a[i]; });
+}
 
 // ------------------------------------------------------------------------------------------ knowledge (CFR path)
 // What one observer ("viewer") believes: Agent.known_roles / Agent.known_hands (game/agent.py:25-26,
@@ -455,7 +492,7 @@ CTD_HD CTD_NI inline void ctd_reshuffle_if_empty(CtdWork& w) {
   CTD_ASSUME_SHARED(&w);
   if (w.n_deck == 0 && w.n_disc != 0) {
     uint8_t* d = w.disc;
-    ctd_shuffle(w, w.n_disc, [d](int i) -> uint8_t& { return d[i]; });
+    ctd_shuffle_bytes(w, d, w.n_disc);
     w.deck_head = 0;
     CTD_LOOP for (int i = 0; i < w.n_disc; ++i) w.deck[i] = w.disc[i];
     w.n_deck = w.n_disc;
@@ -507,7 +544,7 @@ CTD_HD CTD_NI inline void ctd_setup_round(CtdWork& w, CtdKnowSet ks = CtdKnowSet
   // random.shuffle(list(roles.items())); with 6 players exactly one role is popped face down
   uint8_t* s = w.scratch + 64;
   CTD_LOOP for (int i = 0; i < 8; ++i) s[i] = (uint8_t)i;
-  ctd_shuffle(w, 8, [s](int i) -> uint8_t& { return s[i]; });
+  ctd_shuffle_bytes(w, s, 8);
   w.rtc_mask = (uint8_t)(0xFF & ~(1u << s[7]));
   // turn order rotates by the crowned seat's id, applied to the already rotated list
   int c = w.crown;
@@ -648,12 +685,12 @@ CTD_HD CTD_NI inline void ctd_deal_preset(CtdWork& w, int ruleset, uint8_t* used
     // pick order, a random crown.
     uint8_t* u = w.scratch + 96;  // the tape form of ctd_shuffle stages through scratch[0, n): keep clear of it
     CTD_LOOP for (int i = 0; i < 24; ++i) u[i] = (uint8_t)i;
-    ctd_shuffle(w, 24, [u](int i) -> uint8_t& { return u[i]; });
+    ctd_shuffle_bytes(w, u, 24);
     CTD_LOOP for (int i = 0; i < 52; ++i) w.deck[i] = (uint8_t)ctd_base_deck(i);
     CTD_LOOP for (int i = 0; i < 14; ++i) w.deck[52 + i] = (uint8_t)ctd_base_deck(52 + u[i]);
     w.n_deck = 66;
     uint8_t* dk = w.deck;
-    ctd_shuffle(w, 66, [dk](int i) -> uint8_t& { return dk[i]; });
+    ctd_shuffle_bytes(w, dk, 66);
     if (used_cards_out != nullptr) {
       CTD_LOOP for (int i = 0; i < 76; ++i) used_cards_out[i] = i < 66 ? w.deck[i] : 0xFF;
     }
@@ -664,14 +701,14 @@ CTD_HD CTD_NI inline void ctd_deal_preset(CtdWork& w, int ruleset, uint8_t* used
     w.n_deck = 42;
     CTD_LOOP for (int r = 0; r < 8; ++r) w.variant[r] = (uint8_t)ctd_randbelow_any(w, 3);
     uint8_t* o = w.order;
-    ctd_shuffle(w, 6, [o](int i) -> uint8_t& { return o[i]; });
+    ctd_shuffle_bytes(w, o, 6);
     w.crown = (uint8_t)ctd_randbelow_any(w, 6);
     return;
   }
   CTD_LOOP for (int i = 0; i < 76; ++i) w.deck[i] = (uint8_t)ctd_base_deck(i);
   w.n_deck = 76;
   uint8_t* d = w.deck;
-  ctd_shuffle(w, 76, [d](int i) -> uint8_t& { return d[i]; });
+  ctd_shuffle_bytes(w, d, 76);
   if (used_cards_out != nullptr)  // self.used_cards = deepcopy(self.deck) (game/game.py:424)
     CTD_LOOP for (int i = 0; i < 76; ++i) used_cards_out[i] = w.deck[i];
   // The fixed hands ({0,0,16,17,18,19} {1,1,20,21,22,23} {2,3,24,25,26,27} {3,4,28,29,30,31} {4,0,32,33,34,35}
@@ -813,7 +850,7 @@ CTD_HD CTD_NI inline void ctd_seer_give_back_options(CtdWork& w, int p, E& e) {
       CTD_LOOP for (int x = 0; x < n; ++x)
         if (ctd_ctype(w.hand[p][x]) != tc) rem[nr++] = w.hand[p][x];
       CTD_LOOP for (int rep = 0; rep < 3; ++rep) {
-        ctd_shuffle(w, nr, [rem](int i) -> uint8_t& { return rem[i]; });
+        ctd_shuffle_bytes(w, rem, nr);
         // row = rem[:k-1] with the card inserted at `pos` (list.insert past the end appends); zip() stops at k
         int take = nr < k - 1 ? nr : k - 1;
         int ins = pos < take ? pos : take;
@@ -1578,7 +1615,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       CTD_LOOP for (int q = 0; q < 6; ++q) {
         if (q == p || w.n_hand[q] == 0) continue;
         uint8_t* h = w.hand[q];
-        ctd_shuffle(w, w.n_hand[q], [h](int i) -> uint8_t& { return h[i]; });
+        ctd_shuffle_bytes(w, h, w.n_hand[q]);
         ctd_reshuffle_if_empty(w);
         ctd_append(w, w.hand[p], w.n_hand[p], CTD_HAND_CAP, ctd_remove_at(w.hand[q], w.n_hand[q], 0));
         w.seer_mask |= (uint8_t)(1u << q);
@@ -1611,7 +1648,7 @@ CTD_HD CTD_NI inline bool ctd_apply(CtdWork& w, uint64_t d, CtdKnowSet ks = CtdK
       w.gold[p] += (int32_t)ctd_count_suit(w.bld[p], w.n_bld[p], CTD_SUIT_LORD);
       if (CTD_OPT_NAMED(d) == CTD_N_CARD) {
         uint8_t* h = w.hand[q];
-        ctd_shuffle(w, w.n_hand[q], [h](int i) -> uint8_t& { return h[i]; });
+        ctd_shuffle_bytes(w, h, w.n_hand[q]);
         if (w.n_hand[q] != 0) ctd_append(w, w.hand[p], w.n_hand[p], CTD_HAND_CAP, ctd_remove_at(w.hand[q], w.n_hand[q], 0));
       } else if (CTD_OPT_NAMED(d) == CTD_N_GOLD) {
         w.gold[p] += 1;

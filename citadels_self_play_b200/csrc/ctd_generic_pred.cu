@@ -4,6 +4,17 @@
 #include <stddef.h>
 
 #define CTD_DEVICE_ONLY 1
+// measured (round 2 A/B, 4096 roots): node moves, fp64 division / exp and the byte shuffle inlined at their uses are 10 % faster
+// than one out-of-line copy of each -- calls cost the search more (callee-saved registers through local memory on 32 lanes) than
+// the extra 30 KB of image
+#ifndef CTD_NODE_MOVE_ATTR
+#define CTD_NODE_MOVE_ATTR
+#define CTD_MATH_ATTR
+#define CTD_SHUFFLE_ATTR
+#endif
+#ifdef CTD_WANT_COOP_SHUFFLE   /* measured 6 % slower than the scalar loop (round 2 A/B): off */
+#define CTD_COOP_SHUFFLE 1   /* the warp runs the search converged: shuffles draw 32 swap indices at a time (ctd_engine.cuh) */
+#endif
 #define CTD_NO_PLAYOUT_KERNEL 1
 #define CTD_NO_TRAIN_KERNEL 1
 #define CTD_MCCFR_KERNEL_NAME ctd_k_mccfr_unused
@@ -11,9 +22,17 @@
 #include "ctd_search.cuh"
 
 cudaError_t ctd_mccfr_pred_generic_launch(const CtdPredArgs& p, int grid, cudaStream_t stream) {
-  ctd_k_mccfr_pred<<<grid, CTD_BLOCK, 0, stream>>>(p);
+  const size_t smem = p.fused ? CTD_PRED_FUSED_SMEM : 0;   // fused mode: per-warp activation buffers, more than 48 KB per block in all
+  static bool opted = false;
+  if (p.fused && !opted) {
+    cudaError_t c = cudaFuncSetAttribute(ctd_k_mccfr_pred, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CTD_PRED_FUSED_SMEM);
+    if (c != cudaSuccess) return c;
+    opted = true;
+  }
+  ctd_k_mccfr_pred<<<grid, CTD_BLOCK, smem, stream>>>(p);
   return cudaGetLastError();
 }
-cudaError_t ctd_mccfr_pred_generic_blocks_per_sm(int* per_sm) {
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, ctd_k_mccfr_pred, CTD_BLOCK, 0);
+// fused != 0: occupancy with the fused mode's dynamic shared memory
+cudaError_t ctd_mccfr_pred_generic_blocks_per_sm(int* per_sm, int fused) {
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, ctd_k_mccfr_pred, CTD_BLOCK, fused ? CTD_PRED_FUSED_SMEM : 0);
 }

@@ -210,11 +210,11 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_make_roots(CtdRootArgs a) {
 cudaError_t ctd_mccfr_generic_launch(const CtdMccfrArgs& a, int grid, cudaStream_t stream);
 cudaError_t ctd_mccfr_generic_blocks_per_sm(int* per_sm);
 cudaError_t ctd_mccfr_pred_generic_launch(const CtdPredArgs& p, int grid, cudaStream_t stream);
-cudaError_t ctd_mccfr_pred_generic_blocks_per_sm(int* per_sm);
+cudaError_t ctd_mccfr_pred_generic_blocks_per_sm(int* per_sm, int fused);
 cudaError_t ctd_mccfr_preset_launch(const CtdMccfrArgs& a, int grid, cudaStream_t stream);
 cudaError_t ctd_mccfr_preset_blocks_per_sm(int* per_sm);
 cudaError_t ctd_mccfr_pred_preset_launch(const CtdPredArgs& p, int grid, cudaStream_t stream);
-cudaError_t ctd_mccfr_pred_preset_blocks_per_sm(int* per_sm);
+cudaError_t ctd_mccfr_pred_preset_blocks_per_sm(int* per_sm, int fused);
 
 // ------------------------------------------------------------------------------------------ training targets
 // CFRNode.get_all_targets / build_train_targets (algorithms/deep_mccfr.py:258-274, :321-345): depth-first pre-order
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_targets(CtdTargetArgs a) {
   const uint32_t t = blockIdx.x * CTD_WARPS_PER_BLOCK + wib;
   if (t >= a.n_roots || lane != 0) return;
   CtdTree T;
-  T.w = &works[wib]; T.kn = &knows[wib]; T.stage = &tstage[wib];
+  T.w = &works[wib]; T.kn = &knows[wib]; T.stage = &tstage[wib]; T.vnet = nullptr; T.act = nullptr;
   ctd_tree_attach(T, &a.hdrs[t], CtdArena{a.hdrs[t].arena, nullptr, 0});
   const CtdTreeHdr& h = *T.hdr;
   uint32_t nrec = 0, nopt = 0, rp_draws = 0;
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(32) ctd_k_one(CtdOneArgs a) {
   __shared__ CtdWork w;
   __shared__ CtdKnow kn[6];
   __shared__ ctd_state stage;
-  __shared__ __align__(16) uint8_t sscratch[384];
+  __shared__ __align__(16) uint8_t sscratch[CTD_TREE_SCRATCH];
   const int lane = threadIdx.x;
   if (a.op != 0) ctd_record_load(a.state, &stage, lane);
   if (a.know6 != nullptr && a.op != 0)
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(32) ctd_k_one(CtdOneArgs a) {
       ctd_unpack(&stage, w);
       w.k0 = (uint32_t)a.seed; w.k1 = (uint32_t)(a.seed >> 32);
       w.stream = 0; w.tape = nullptr; w.tape_len = 0;
-      for (int i = 0; i < 80; ++i) sscratch[256 + i] = i < 76 ? a.used_cards[i] : 0xFF;
+      ctd_stage_used(sscratch + 256, a.used_cards);
       ctd_sample_private(w, kn[a.viewer], sscratch + 256, a.role_sample != 0, sscratch);
       w.err |= kn[a.viewer].err;
       ctd_pack(w, &stage);
@@ -1132,9 +1132,28 @@ static ctd_status ctd_deep_pass(ctd_engine* e, const CtdSearch& sp, const uint32
   p.max_depth = sp.max_depth; p.feat = e->d_feat; p.pred = e->d_pred; p.pending = e->d_pending;
   int per_sm = 0;
   const bool preset = sp.ruleset == CTD_RULESET_PRESET;
-  if (preset) CTD_CUDA(e, ctd_mccfr_pred_preset_blocks_per_sm(&per_sm));
-  else CTD_CUDA(e, ctd_mccfr_pred_generic_blocks_per_sm(&per_sm));
+  if (preset) CTD_CUDA(e, ctd_mccfr_pred_preset_blocks_per_sm(&per_sm, e->value_backend == 2));
+  else CTD_CUDA(e, ctd_mccfr_pred_generic_blocks_per_sm(&per_sm, e->value_backend == 2));
   if (per_sm < 1) per_sm = 1;
+  if (e->value_backend == 2) {
+    // fused: one launch; every warp walks its tree to the end and evaluates the leaves it meets itself (ctd_value_inline)
+    p.fused = 1; p.budget = 0xFFFFFFFFu; p.first = 1;
+    p.net = CtdValueNet{e->model.w1t, e->model.b1, e->model.w2t, e->model.b2, e->model.w3t, e->model.b3, e->model.w4t, e->model.b4, sp.weight};
+    const uint64_t want = (uint64_t)e->sm_count * per_sm, needb = (n + CTD_WARPS_PER_BLOCK - 1) / CTD_WARPS_PER_BLOCK;
+    const int grid = (int)(needb < want ? needb : want);
+    ctd_status s = ctd_ensure_opts(e, (size_t)grid * CTD_WARPS_PER_BLOCK);
+    if (s != CTD_OK) return s;
+    a.tree_list = d_list; a.first_root = 0; a.n_roots = n; a.counter = e->d_counter; a.opts_scratch = e->d_opts_scratch;
+    p.n_pending = e->d_n_pending;
+    CTD_CUDA(e, cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream));
+    CTD_CUDA(e, cudaMemsetAsync(e->d_n_pending, 0, 2 * sizeof(uint32_t), e->stream));
+    if (preset) CTD_CUDA(e, ctd_mccfr_pred_preset_launch(p, grid, e->stream));
+    else CTD_CUDA(e, ctd_mccfr_pred_generic_launch(p, grid, e->stream));
+    e->launches++;
+    CTD_CUDA(e, cudaGetLastError());
+    if (waves_out) *waves_out = 1;
+    return CTD_OK;
+  }
   // Two groups of trees take turns: each group's waves (walk kernel -> batched leaf evaluation -> walk kernel ...) run on
   // their own stream, so the tail of one group's wave -- a few trees with expensive expansions -- overlaps with the other
   // group's kernel instead of idling the GPU.  Trees are independent, results do not depend on the grouping.
@@ -1550,7 +1569,7 @@ static ctd_status ctd_value_forward(ctd_engine* e, uint32_t n, const uint8_t* pe
   if (st == nullptr) st = e->stream;
   const float* feat = e->d_feat + (size_t)row0 * CTD_FEATURES_PAD;
   float* pred = e->d_pred + (size_t)row0 * 8;
-  if (e->value_backend == 0) {
+  if (e->value_backend != 1) {   // fp32 batch kernel (also what ctd_value_eval uses in fused mode)
     ctd_k_value_mlp<<<(n + CTD_MLP_ROWS - 1) / CTD_MLP_ROWS, 256, CTD_MLP_SMEM, st>>>(feat, pending, n, e->model, pred, weight);
     e->launches++;
     CTD_CUDA(e, cudaGetLastError());
@@ -1569,7 +1588,7 @@ static ctd_status ctd_value_forward(ctd_engine* e, uint32_t n, const uint8_t* pe
 }
 
 ctd_status ctd_set_value_backend(ctd_engine* e, int backend) {
-  if (!e || (backend != 0 && backend != 1)) return CTD_EARG;
+  if (!e || backend < 0 || backend > 2) return CTD_EARG;
   e->value_backend = backend;
   return CTD_OK;
 }

@@ -120,6 +120,13 @@ struct CtdArena {
   unsigned long long cap;    // units
 };
 
+#define CTD_TREE_SCRATCH 416
+#define CTD_ACT_FLOATS 1024
+// ValueOnlyNN(418, 512) in eval mode with BatchNorm folded into fc1 / fc2, weights transposed to [in][out] (ctd_set_value_model)
+struct CtdValueNet {
+  const float *w1t, *b1, *w2t, *b2, *w3t, *b3, *w4t, *b4;  // w1t [448][512], w2t [512][256], w3t [256][128], w4t [128][6]
+  float weight;                                            // model_reward_weights
+};
 // a tree plus the on-chip working set of the warp that grows it
 struct CtdTree {
   CtdTreeHdr* hdr;
@@ -130,8 +137,11 @@ struct CtdTree {
   CtdWork* w;       // working game (shared memory on the device)
   CtdKnow* kn;      // working knowledge of the viewer
   uint64_t* opts;   // CTD_MCCFR_OPT_CAP descriptors
-  uint8_t* scratch; // >= 384 bytes, 16-byte aligned: [0,256) determinisation scratch, [256,336) Game.used_cards staged on chip
+  uint8_t* scratch; // CTD_TREE_SCRATCH bytes, 16-byte aligned: [0,256) determinisation scratch, [256,336) Game.used_cards staged on chip,
+                    // [336,416) occurrence index of every card of used_cards among the cards of its type
   ctd_state* stage; // 16-byte aligned staging record (shared memory on the device)
+  const struct CtdValueNet* vnet;  // deep MCCFR, fused mode: the warp evaluates its own leaves (null: the walk hands leaves to the caller)
+  float* act;       // fused mode: CTD_ACT_FLOATS floats of shared memory for the features and the activations
 };
 
 // address spaces of a tree's parts on the device: working set in shared memory, the tree block in HBM
@@ -199,6 +209,14 @@ __device__ __forceinline__ void ctd_copy_g2s(void* sdst, const void* gsrc) {
 #endif
 
 CTD_HD inline double ctd_uniform(CtdWork& w) { return (double)ctd_u32(w) / 4294967296.0; }
+
+// IEEE fp64 division and exp are ~40 / ~100 instructions inline at every use; the search's arithmetic is a few dozen of them per
+// iteration, its instruction footprint is what it pays for (profiles/README.md): one out-of-line copy of each
+#ifndef CTD_MATH_ATTR
+#define CTD_MATH_ATTR CTD_NI
+#endif
+CTD_HD CTD_MATH_ATTR inline double ctd_ddiv(double a, double b) { return a / b; }
+CTD_HD CTD_MATH_ATTR inline double ctd_dexp(double x) { return exp(x); }
 
 // ------------------------------------------------------------------------------------------ tree memory
 CTD_HD inline int ctd_clz32(uint32_t x) {
@@ -284,13 +302,29 @@ CTD_HD CTD_NI inline void ctd_sample_private(CtdWork& w, CtdKnow& k, const uint8
   CTD_LOOP for (int h = 0; h < k.n_hk; ++h)
     if (k.hk[h].flags & CTD_HK_USED)
       CTD_LOOP for (int i = 0; i < k.hk[h].n; ++i) ++cnt[ctd_ctype(k.pool[k.hk[h].off + i])];
+  // first occurrence per removal: the k-th card of a type (deal order) goes exactly when k < pending removals of that type.
+  // used_cards[80 + i] holds that k (ctd_tree_stage_used: used_cards is constant over a tree), so every card decides by itself
   int nu = 0;
+  const uint8_t* occ = used_cards + 80;
+#if defined(__CUDA_ARCH__)
+  if (__activemask() == 0xFFFFFFFFu) {   // converged warp (search kernels): 32 cards at a time, ballot + prefix count compaction
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    CTD_LOOP for (int base = 0; base < 96; base += 32) {
+      const int i = base + lane;
+      const int c = i < 76 ? used_cards[i] : 0xFF;   // 0xFF pads the 66-card deal of Game(preset=False)
+      const bool keep = c != 0xFF && occ[i] >= cnt[ctd_ctype(c)];
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+      if (keep) unknown[nu + __popc(m & ((1u << lane) - 1u))] = (uint8_t)c;
+      nu += __popc(m);
+    }
+    __syncwarp();
+  } else
+#endif
   CTD_LOOP for (int i = 0; i < 76; ++i) {
     int c = used_cards[i];
     if (c == 0xFF) break;  // Game(preset=False) plays with 66 cards
-    int t = ctd_ctype(c);
-    if (cnt[t] != 0) --cnt[t];
-    else unknown[nu++] = (uint8_t)c;
+    if (occ[i] >= cnt[ctd_ctype(c)]) unknown[nu++] = (uint8_t)c;
   }
   // (3) sample_deck (:245-262): believed Lighthouse order first, then shuffled unknown cards
   int need = w.n_deck;
@@ -303,10 +337,22 @@ CTD_HD CTD_NI inline void ctd_sample_private(CtdWork& w, CtdKnow& k, const uint8
       need -= take;
       break;
     }
-  ctd_shuffle(w, nu, [unknown](int i) -> uint8_t& { return unknown[i]; });
+  ctd_shuffle_bytes(w, unknown, nu);
   int uh = 0;
-  CTD_LOOP for (int i = 0; i < need; ++i)
-    if (uh < nu) w.deck[w.n_deck++] = unknown[uh++];
+  {
+    const int take = need < nu ? need : nu;
+#if defined(__CUDA_ARCH__)
+    if (__activemask() == 0xFFFFFFFFu) {   // converged warp: a plain parallel copy
+      const int base = w.n_deck;
+      __syncwarp();
+      for (int i = threadIdx.x & 31; i < take; i += 32) w.deck[base + i] = unknown[i];
+      __syncwarp();
+    } else
+#endif
+    CTD_LOOP for (int i = 0; i < take; ++i) w.deck[w.n_deck + i] = unknown[i];
+    w.n_deck = (uint8_t)(w.n_deck + take);
+    uh = take;
+  }
   // (3b) sample_warrants_and_blackmails (:321-336): which of the flagged ranks carries the real one is re-rolled,
   // blackmails first
   CTD_LOOP for (int pass = 0; pass < 2; ++pass) {
@@ -316,7 +362,7 @@ CTD_HD CTD_NI inline void ctd_sample_private(CtdWork& w, CtdKnow& k, const uint8
     CTD_LOOP for (int r = 0; r < 8; ++r)
       if (w.rprops[r] & mask) keys[nk++] = (uint8_t)r;
     if (nk == 0) continue;
-    ctd_shuffle(w, nk, [keys](int i) -> uint8_t& { return keys[i]; });
+    ctd_shuffle_bytes(w, keys, nk);
     const int real = keys[0];
     CTD_LOOP for (int r = 0; r < 8; ++r)
       if (w.rprops[r] & mask) w.rprops[r] = (uint8_t)((w.rprops[r] & ~mask) | ((r == real ? 1 : 2) << sh));
@@ -375,7 +421,10 @@ CTD_HD CTD_NI inline void ctd_sample_private(CtdWork& w, CtdKnow& k, const uint8
 }
 
 // ------------------------------------------------------------------------------------------ node helpers
-CTD_HD inline void ctd_node_store(CtdTree& T, CtdNode& n) {
+#ifndef CTD_NODE_MOVE_ATTR
+#define CTD_NODE_MOVE_ATTR CTD_NI   /* one copy of the 2.3 KB record moves: the search kernels are bound by their instruction footprint */
+#endif
+CTD_HD CTD_NODE_MOVE_ATTR inline void ctd_node_store(CtdTree& T, CtdNode& n) {
   const CtdWork& w = *T.w;
   CTD_COPY_S2G(n.snap, &w, CTD_SNAP_BYTES);
   CTD_COPY_S2G(&n.know, T.kn, (int)sizeof(CtdKnow));
@@ -383,7 +432,7 @@ CTD_HD inline void ctd_node_store(CtdTree& T, CtdNode& n) {
   n.gstate = w.state;
   n.winner = w.winner;
 }
-CTD_HD inline void ctd_node_load(CtdTree& T, const CtdNode& n) {
+CTD_HD CTD_NODE_MOVE_ATTR inline void ctd_node_load(CtdTree& T, const CtdNode& n) {
   // chance state lives in the working record and must survive a load
   CtdWork& w = *T.w;
   CTD_COPY_G2S(&w, n.snap, CTD_SNAP_BYTES);   // the chance fields sit outside the snapshot and survive
@@ -401,12 +450,12 @@ CTD_HD CTD_NI inline void ctd_skip_false_choice(CtdTree& T) {
   int i = 0;
   for (;;) {
     if (w.gflags & 2) return;
-    CtdEmit e{T.opts, 1, 0, 0xFFFFFFFFu, 0};
+    CtdEmit e{nullptr, 0, 0, 0, 0};   // count, and keep the first option
     ctd_enumerate(w, e, T.kn);
     if (w.err) return;
     if (e.n != 1) return;
     ++i;
-    bool won = ctd_apply(w, T.opts[0], ks);
+    bool won = ctd_apply(w, e.got, ks);
     if (won || w.err || i > 100) return;
   }
 }
@@ -477,7 +526,17 @@ CTD_HD inline uint64_t ctd_carried_form(const CtdWork& w, uint64_t d) {
 
 // Game.used_cards is constant over a tree and read 76 bytes at a time by every determinisation: keep a copy next to the
 // working set (shared memory on the device) instead of walking the tree header in HBM.  Call once per (re)attached tree.
-CTD_HD inline void ctd_tree_stage_used(CtdTree& T) { ctd_copy16(T.scratch + 256, T.hdr->used_cards, 80); }
+CTD_HD inline void ctd_stage_used(uint8_t* u, const uint8_t* used_cards) {   // u: 160 bytes
+  CTD_LOOP for (int i = 0; i < 80; ++i) u[i] = i < 76 ? used_cards[i] : 0xFF;
+  // occurrence index of every card among the cards of its type, in deal order (what the determinisation's filter tests)
+  uint8_t seen[40];
+  CTD_LOOP for (int t = 0; t < 40; ++t) seen[t] = 0;
+  CTD_LOOP for (int i = 0; i < 80; ++i) {
+    const int c = u[i];
+    u[80 + i] = c == 0xFF ? 0 : seen[ctd_ctype(c)]++;
+  }
+}
+CTD_HD inline void ctd_tree_stage_used(CtdTree& T) { ctd_stage_used(T.scratch + 256, T.hdr->used_cards); }
 
 // "sample if it is not the same player's turn as in the parent" (:139-140, :157-158)
 CTD_HD inline void ctd_maybe_sample(CtdTree& T, const CtdNode& n) {
@@ -486,6 +545,51 @@ CTD_HD inline void ctd_maybe_sample(CtdTree& T, const CtdNode& n) {
     bool role_sample = root ? false : ctd_node(T, n.parent).gstate != 0;
     ctd_sample_private(*T.w, *T.kn, T.scratch + 256, role_sample, T.scratch);
   }
+}
+
+// One uniformly random legal option without a list buffer: count, draw, enumerate again and keep the k-th.  The Seer's and the
+// Scholar's enumerations are not pure (fresh shuffles, a shrinking list: game/agent_functions.py:332-361, :462-470), so the second
+// pass starts from the state the first one started from and regenerates the same list; what is left behind is exactly one
+// enumeration plus one draw, as in `options = game.get_options_from_state(); choice(options)` (run_utils.py:38-39).
+struct CtdEnumSave {
+  uint32_t draws, tape_pos;
+  uint8_t n_seven, seven[7];
+};
+CTD_HD inline CtdEnumSave ctd_enum_save(const CtdWork& w) {
+  CtdEnumSave s;
+  s.draws = w.draws; s.tape_pos = w.tape_pos; s.n_seven = w.n_seven;
+  CTD_LOOP for (int i = 0; i < 7; ++i) s.seven[i] = w.seven[i];
+  return s;
+}
+CTD_HD inline uint64_t ctd_enum_select(CtdWork& w, const CtdKnow* kn, const CtdEnumSave& s, uint32_t k) {
+  const uint32_t draws1 = w.draws, tape1 = w.tape_pos;
+  w.draws = s.draws; w.tape_pos = s.tape_pos; w.buf_blk = 0xFFFFFFFFu; w.n_seven = s.n_seven;
+  CTD_LOOP for (int i = 0; i < 7; ++i) w.seven[i] = s.seven[i];
+  CtdEmit e2{nullptr, 0, 0, k, 0};
+  ctd_enumerate(w, e2, kn);
+  w.draws = draws1; w.tape_pos = tape1; w.buf_blk = 0xFFFFFFFFu;
+  return e2.got;
+}
+// The legal options of the working game, materialised.  Lists of up to CTD_SMALL_OPTS descriptors (mean 4, p99 31 in preset
+// games) stay on chip in the warp's staging record, which the search does not use otherwise; longer ones are enumerated again
+// into the warp's HBM buffer (from the state the first pass started from: the Seer's give-back lists draw chance and can be long).
+// *list receives where the first min(n, capacity) descriptors are.
+#define CTD_SMALL_OPTS 32
+static_assert(CTD_SMALL_OPTS * sizeof(uint64_t) <= sizeof(ctd_state), "the small option buffer is the staging record");
+CTD_HD inline uint32_t ctd_list_options(CtdTree& T, const uint64_t** list) {
+  CtdWork& w = *T.w;
+  uint64_t* small = (uint64_t*)T.stage;
+  const CtdEnumSave sv = ctd_enum_save(w);
+  CtdEmit e{small, CTD_SMALL_OPTS, 0, 0xFFFFFFFFu, 0};
+  ctd_enumerate(w, e, T.kn);
+  *list = small;
+  if (e.n <= CTD_SMALL_OPTS) return e.n;
+  w.draws = sv.draws; w.tape_pos = sv.tape_pos; w.buf_blk = 0xFFFFFFFFu; w.n_seven = sv.n_seven;
+  CTD_LOOP for (int i = 0; i < 7; ++i) w.seven[i] = sv.seven[i];
+  CtdEmit e2{T.opts, CTD_MCCFR_OPT_CAP, 0, 0xFFFFFFFFu, 0};
+  ctd_enumerate(w, e2, T.kn);
+  *list = T.opts;
+  return e2.n;
 }
 
 // CFRNode.expand (:93-179)
@@ -504,10 +608,10 @@ CTD_HD CTD_NI inline void ctd_expand(CtdTree& T, int ni) {
       ctd_node_load(T, n);
       uint64_t d = 0;
       while (w.state != 1 && !w.err) {
-        CtdEmit e{T.opts, CTD_MCCFR_OPT_CAP, 0, 0xFFFFFFFFu, 0};
-        ctd_enumerate(w, e, T.kn);
-        if (e.n == 0) { w.err |= CTD_ERR_REF_RAISE; break; }
-        d = T.opts[ctd_randbelow(w, e.n)];
+        const uint64_t* list;
+        const uint32_t n_opts = ctd_list_options(T, &list);
+        if (n_opts == 0) { w.err |= CTD_ERR_REF_RAISE; break; }
+        d = list[ctd_randbelow(w, n_opts)];   // role-pick lists hold at most eight options
         ctd_apply(w, d, ks);
       }
       int ci = ctd_new_node(T, ni, n.depth + 1);
@@ -518,17 +622,16 @@ CTD_HD CTD_NI inline void ctd_expand(CtdTree& T, int ni) {
   } else if (n.player == viewer && n.n_children == 0) {
     // expand_for_original_player (:133-151): one child per legal option
     ctd_node_load(T, n);
-    CtdEmit e{T.opts, CTD_MCCFR_OPT_CAP, 0, 0xFFFFFFFFu, 0};
-    ctd_enumerate(w, e, T.kn);
-    if (e.n == 0) { T.hdr->status |= w.err ? CTD_TREE_REF_RAISE : CTD_TREE_EENGINE; return; }
+    const uint64_t* list;
+    const uint32_t K = ctd_list_options(T, &list);
+    if (K == 0) { T.hdr->status |= w.err ? CTD_TREE_REF_RAISE : CTD_TREE_EENGINE; return; }
     // the reference enumerates on the node's own game (:134): the Scholar's list shrinks there, and every child is a copy of that
     if (w.state == 9) CTD_COPY_S2G(n.snap, &w, CTD_SNAP_BYTES);
-    const uint32_t K = e.n;
     if (!ctd_reserve(T, n, K, 3 * K)) return;
     CtdChild* kids = ctd_kids(T, n);
     // the option list must survive the children's own enumerations: park it in the child table
     if (K <= CTD_MCCFR_OPT_CAP) {
-      CTD_LOOP for (uint32_t i = 0; i < K; ++i) kids[i] = CtdChild{T.opts[i], 0, 0};
+      CTD_LOOP for (uint32_t i = 0; i < K; ++i) kids[i] = CtdChild{list[i], 0, 0};
     } else {
       // a list longer than the option buffer (pure enumerations only: the Magician's discards, the Cardinal's exchanges): enumerate
       // once more straight into the node's still unused doubles, move it over, zero the doubles again
@@ -554,13 +657,13 @@ CTD_HD CTD_NI inline void ctd_expand(CtdTree& T, int ni) {
     CtdChild* kids = ctd_kids(T, n);
     ctd_node_load(T, n);
     ctd_maybe_sample(T, n);
-    CtdEmit e{T.opts, CTD_MCCFR_OPT_CAP, 0, 0xFFFFFFFFu, 0};
-    ctd_enumerate(w, e, T.kn);
-    if (e.n == 0) { T.hdr->status |= w.err ? CTD_TREE_REF_RAISE : CTD_TREE_EENGINE; return; }
-    uint32_t pick = ctd_randbelow(w, e.n);
+    const uint64_t* list;
+    const uint32_t n_opts = ctd_list_options(T, &list);
+    if (n_opts == 0) { T.hdr->status |= w.err ? CTD_TREE_REF_RAISE : CTD_TREE_EENGINE; return; }
+    uint32_t pick = ctd_randbelow(w, n_opts);
     uint64_t d;
-    if (pick < CTD_MCCFR_OPT_CAP) d = T.opts[pick];
-    else { CtdEmit e2{T.opts, 0, 0, pick, 0}; ctd_enumerate(w, e2, T.kn); d = e2.got; }
+    if (pick < CTD_MCCFR_OPT_CAP) d = list[pick];
+    else { CtdEmit e2{nullptr, 0, 0, pick, 0}; ctd_enumerate(w, e2, T.kn); d = e2.got; }   // beyond the buffer: pure enumerations only
     d = ctd_carried_form(w, d);
     ctd_apply(w, d, ks);
     bool seen = false;
@@ -595,22 +698,22 @@ CTD_HD CTD_NI inline void ctd_update_strategy(CtdTree& T, int ni) {
   const double log13 = 0.26236426446749106;  // np.log(1.3)
   if (!(n.flags & CTD_NF_ROLE_PICK)) {
     double tot = 0.0;
-    CTD_LOOP for (int a = 0; a < K; ++a) { S[a] = exp(-R[a] * log13); tot += S[a]; }
-    if (tot > 0.0) { CTD_LOOP for (int a = 0; a < K; ++a) S[a] = S[a] / tot; }
-    else { CTD_LOOP for (int a = 0; a < K; ++a) S[a] = 1.0 / K; }
+    CTD_LOOP for (int a = 0; a < K; ++a) { S[a] = ctd_dexp(-R[a] * log13); tot += S[a]; }
+    if (tot > 0.0) { CTD_LOOP for (int a = 0; a < K; ++a) S[a] = ctd_ddiv(S[a], tot); }
+    else { CTD_LOOP for (int a = 0; a < K; ++a) S[a] = ctd_ddiv(1.0, (double)K); }
     double cs = 0.0;
     CTD_LOOP for (int a = 0; a < K; ++a) { C[a] += S[a]; cs += C[a]; }
-    CTD_LOOP for (int a = 0; a < K; ++a) C[a] = C[a] / cs;
+    CTD_LOOP for (int a = 0; a < K; ++a) C[a] = ctd_ddiv(C[a], cs);
   } else {
     // normalised over the PLAYER axis (axis=0), then C renormalised over all 60 entries
     CTD_LOOP for (int a = 0; a < 10; ++a) {
       double tot = 0.0;
-      CTD_LOOP for (int p = 0; p < 6; ++p) { S[p * 10 + a] = exp(-R[p * 10 + a] * log13); tot += S[p * 10 + a]; }
-      CTD_LOOP for (int p = 0; p < 6; ++p) S[p * 10 + a] = tot > 1e-8 ? S[p * 10 + a] / tot : 1.0 / 6.0;
+      CTD_LOOP for (int p = 0; p < 6; ++p) { S[p * 10 + a] = ctd_dexp(-R[p * 10 + a] * log13); tot += S[p * 10 + a]; }
+      CTD_LOOP for (int p = 0; p < 6; ++p) S[p * 10 + a] = tot > 1e-8 ? ctd_ddiv(S[p * 10 + a], tot) : 1.0 / 6.0;
     }
     double cs = 0.0;
     CTD_LOOP for (int i = 0; i < 60; ++i) { C[i] += S[i]; cs += C[i]; }
-    CTD_LOOP for (int i = 0; i < 60; ++i) C[i] = C[i] / cs;
+    CTD_LOOP for (int i = 0; i < 60; ++i) C[i] = ctd_ddiv(C[i], cs);
   }
 }
 
@@ -625,16 +728,26 @@ CTD_HD CTD_NI inline int ctd_action_choice(CtdTree& T, int ni) {
   if (!(n.flags & CTD_NF_ROLE_PICK)) {
     double cs = 0.0;
     CTD_LOOP for (int a = 0; a < K; ++a) cs += C[a];
-    // cdf[a] = running sum of C[a] / cs; the draw is compared with cdf[a] / cdf[K-1].  No buffer: the running sum is formed
-    // twice with the same operations in the same order (K is unbounded: the Cardinal expands thousands of children)
+    // cdf[a] = running sum of C[a] / cs; the draw is compared with cdf[a] / cdf[K-1]
+    double* cdf = K <= CTD_SMALL_OPTS ? (double*)T.stage : (K <= CTD_MCCFR_OPT_CAP ? (double*)T.opts : nullptr);
+    if (cdf != nullptr) {
+      double run = 0.0;
+      CTD_LOOP for (int a = 0; a < K; ++a) { run += ctd_ddiv(C[a], cs); cdf[a] = run; }
+      const double last = cdf[K - 1];
+      const double u = ctd_uniform(*T.w);
+      int i = 0;
+      while (i < K - 1 && ctd_ddiv(cdf[i], last) <= u) ++i;
+      return (int)kids[i].node;
+    }
+    // no buffer can hold it (the Cardinal expands thousands of children): the running sum is formed twice, same operations, same order
     double last = 0.0;
-    CTD_LOOP for (int a = 0; a < K; ++a) last += C[a] / cs;
+    CTD_LOOP for (int a = 0; a < K; ++a) last += ctd_ddiv(C[a], cs);
     const double u = ctd_uniform(*T.w);
     double run = 0.0;
     int i = 0;
     CTD_LOOP for (; i < K - 1; ++i) {
-      run += C[i] / cs;
-      if (!(run / last <= u)) break;
+      run += ctd_ddiv(C[i], cs);
+      if (!(ctd_ddiv(run, last) <= u)) break;
     }
     return (int)kids[i].node;
   }
@@ -645,15 +758,15 @@ CTD_HD CTD_NI inline int ctd_action_choice(CtdTree& T, int ni) {
   CTD_LOOP for (int a = 0; a < 10; ++a) {
     double v = 0.0;
     CTD_LOOP for (int i = 0; i < 6; ++i) v += C[n.order[i] * 10 + a] * (double)(6 - i);
-    avg[a] = v / 15.0;
+    avg[a] = ctd_ddiv(v, 15.0);
   }
   CTD_LOOP for (int a = 0; a < 10; ++a) s += avg[a];
   double run = 0.0;
-  CTD_LOOP for (int a = 0; a < 10; ++a) { run += (s == 0.0 ? 1.0 / 10 : avg[a] / s); cdf[a] = run; }
+  CTD_LOOP for (int a = 0; a < 10; ++a) { run += (s == 0.0 ? 1.0 / 10 : ctd_ddiv(avg[a], s)); cdf[a] = run; }
   const double last = cdf[K - 1];
   const double u = ctd_uniform(*T.w);
   int i = 0;
-  while (i < K - 1 && cdf[i] / last <= u) ++i;
+  while (i < K - 1 && ctd_ddiv(cdf[i], last) <= u) ++i;
   return (int)kids[i].node;
 }
 
@@ -668,7 +781,7 @@ CTD_HD CTD_NI inline void ctd_backpropagate(CtdTree& T, int ni, const double rew
     if (training || vs == 0.0 || !model) CTD_LOOP for (int i = 0; i < 6; ++i) n.V[i] += reward[i];
     vs = 0.0;
     CTD_LOOP for (int i = 0; i < 6; ++i) vs += n.V[i];
-    CTD_LOOP for (int i = 0; i < 6; ++i) n.P[i] = n.V[i] / vs;
+    CTD_LOOP for (int i = 0; i < 6; ++i) n.P[i] = ctd_ddiv(n.V[i], vs);
     ++n.visits;
     const int K = (int)n.n_children;
     if (K == 0) continue;
@@ -759,13 +872,13 @@ CTD_HD CTD_NI inline uint64_t ctd_live_choice(CtdTree& T) {
     double cs = 0.0;
     CTD_LOOP for (int a = 0; a < K; ++a) cs += C[a];
     double last = 0.0;
-    CTD_LOOP for (int a = 0; a < K; ++a) last += C[a] / cs;
+    CTD_LOOP for (int a = 0; a < K; ++a) last += ctd_ddiv(C[a], cs);
     const double u = ctd_uniform(w);
     double run = 0.0;
     int i = 0;
     CTD_LOOP for (; i < K - 1; ++i) {
-      run += C[i] / cs;
-      if (!(run / last <= u)) break;
+      run += ctd_ddiv(C[i], cs);
+      if (!(ctd_ddiv(run, last) <= u)) break;
     }
     return ctd_kids(T, n)[i].desc;
   }
@@ -778,13 +891,13 @@ CTD_HD CTD_NI inline uint64_t ctd_live_choice(CtdTree& T) {
     if ((w.rtc_mask >> r) & 1) { ranks[m] = r; sub[m] = S[r]; tot += S[r]; ++m; }
   if (m == 0) return 0;
   double last = 0.0;
-  CTD_LOOP for (int j = 0; j < m; ++j) last += sub[j] / tot;
+  CTD_LOOP for (int j = 0; j < m; ++j) last += ctd_ddiv(sub[j], tot);
   const double u = ctd_uniform(w);
   double run = 0.0;
   int i = 0;
   CTD_LOOP for (; i < m - 1; ++i) {
-    run += sub[i] / tot;
-    if (!(run / last <= u)) break;
+    run += ctd_ddiv(sub[i], tot);
+    if (!(ctd_ddiv(run, last) <= u)) break;
   }
   return ctd_opt(CTD_K_ROLE_PICK, w.player) | ctd_f_rank(ranks[i]);
 }
@@ -829,6 +942,91 @@ CTD_HD CTD_NI inline void ctd_encode_game(const CtdWork& w, const CtdKnow& k, in
     if (rp & CTD_RP_BLACKMAIL) f[378 + r * 5 + 4] = 1.f;
   }
 }
+
+#if defined(__CUDA_ARCH__)
+// ---- the value model evaluated by the warp that needs the value (fused deep MCCFR) ----
+// CFRNode.model_inference (algorithms/deep_mccfr.py:364-374): ValueOnlyNN forward in eval mode, square_and_normalize
+// (train_utils.py:143-145), times model_reward_weights.  One leaf at a time is a matrix-VECTOR product: there is no tile for a
+// tensor core to work on, and batching leaves across trees is what forces the search into waves (every tree waits for the
+// slowest walker of its wave).  Here the 32 lanes share the output columns of each layer, the inputs are broadcast from shared
+// memory, and both sources of sparsity are used: a feature row has ~70 non-zeros of 418 (one-hot blocks, small counts), and
+// about half of the ReLU outputs are zero.  fp32 FMAs in ascending input order: the same arithmetic, term for term, as the fp32
+// batch kernel (ctd_k_value_mlp), since skipped terms are exact zeros.  All 32 lanes must be converged.
+// act: [0,448) features in; scratch and activations (layout in the body).  Weights stream from L2 (1.5 MB, resident).
+template <int NOUT4>   // float4 column groups per lane: layer width = 128 * NOUT4
+__device__ __forceinline__ void ctd_vnet_layer(const float* __restrict__ wt, const float* __restrict__ bias, const float* in, int n_in,
+                                               uint16_t* list, float* out, int lane) {
+  // compact the indices of the non-zero inputs (ballot + prefix count)
+  int nnz = 0;
+  for (int base = 0; base < n_in; base += 32) {
+    const int k = base + lane;
+    const bool nz = k < n_in && in[k] != 0.f;
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, nz);
+    if (nz) list[nnz + __popc(m & ((1u << lane) - 1u))] = (uint16_t)k;
+    nnz += __popc(m);
+  }
+  __syncwarp();
+  float4 acc[NOUT4];
+#pragma unroll
+  for (int j = 0; j < NOUT4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int width = 128 * NOUT4;
+  const float4* w4 = reinterpret_cast<const float4*>(wt) + lane;
+  // two inputs per trip: their weight rows are independent loads
+  int i = 0;
+  for (; i + 1 < nnz; i += 2) {
+    const int k0 = list[i], k1 = list[i + 1];
+    const float x0 = in[k0], x1 = in[k1];
+    float4 a[NOUT4], b[NOUT4];
+#pragma unroll
+    for (int j = 0; j < NOUT4; ++j) { a[j] = __ldg(w4 + (k0 * width) / 4 + 32 * j); b[j] = __ldg(w4 + (k1 * width) / 4 + 32 * j); }
+#pragma unroll
+    for (int j = 0; j < NOUT4; ++j) {
+      acc[j].x = fmaf(a[j].x, x0, acc[j].x); acc[j].y = fmaf(a[j].y, x0, acc[j].y); acc[j].z = fmaf(a[j].z, x0, acc[j].z); acc[j].w = fmaf(a[j].w, x0, acc[j].w);
+      acc[j].x = fmaf(b[j].x, x1, acc[j].x); acc[j].y = fmaf(b[j].y, x1, acc[j].y); acc[j].z = fmaf(b[j].z, x1, acc[j].z); acc[j].w = fmaf(b[j].w, x1, acc[j].w);
+    }
+  }
+  if (i < nnz) {
+    const int k0 = list[i];
+    const float x0 = in[k0];
+#pragma unroll
+    for (int j = 0; j < NOUT4; ++j) {
+      const float4 a = __ldg(w4 + (k0 * width) / 4 + 32 * j);
+      acc[j].x = fmaf(a.x, x0, acc[j].x); acc[j].y = fmaf(a.y, x0, acc[j].y); acc[j].z = fmaf(a.z, x0, acc[j].z); acc[j].w = fmaf(a.w, x0, acc[j].w);
+    }
+  }
+  __syncwarp();   // every lane is done with `in` and `list` (the output may overlap them)
+#pragma unroll
+  for (int j = 0; j < NOUT4; ++j) {
+    const float4 c = __ldg(reinterpret_cast<const float4*>(bias) + lane + 32 * j);
+    float4 r;
+    r.x = fmaxf(acc[j].x + c.x, 0.f); r.y = fmaxf(acc[j].y + c.y, 0.f); r.z = fmaxf(acc[j].z + c.z, 0.f); r.w = fmaxf(acc[j].w + c.w, 0.f);
+    reinterpret_cast<float4*>(out)[lane + 32 * j] = r;
+  }
+  __syncwarp();
+}
+static __device__ __noinline__ void ctd_value_inline(const CtdValueNet& m, float* act, float pred[6]) {
+  const int lane = threadIdx.x & 31;
+  // act (floats): layer 1 reads x [0,448), index list at [448,660), writes h1 [512,1024); layer 2 reads h1, list at [256,512),
+  // writes h2 [0,256); layer 3 reads h2, list at [256,384), writes h3 [384,512)
+  ctd_vnet_layer<4>(m.w1t, m.b1, act, CTD_FEATURES, reinterpret_cast<uint16_t*>(act + 448), act + 512, lane);
+  ctd_vnet_layer<2>(m.w2t, m.b2, act + 512, 512, reinterpret_cast<uint16_t*>(act + 256), act, lane);
+  ctd_vnet_layer<1>(m.w3t, m.b3, act, 256, reinterpret_cast<uint16_t*>(act + 256), act + 384, lane);
+  // fc4: six outputs, each a sequential fp32 sum over the 128 inputs (lanes 0..5), then weight * y^2 / sum(y^2)
+  float y = 0.f;
+  if (lane < 6) {
+    const float* h3 = act + 384;
+    for (int k = 0; k < 128; ++k) y = fmaf(__ldg(m.w4t + k * 6 + lane), h3[k], y);
+    y += __ldg(m.b4 + lane);
+    y *= y;
+  }
+  float sq[6], s = 0.f;
+#pragma unroll
+  for (int o = 0; o < 6; ++o) { sq[o] = __shfl_sync(0xFFFFFFFFu, y, o); s += sq[o]; }
+#pragma unroll
+  for (int o = 0; o < 6; ++o) pred[o] = m.weight * (sq[o] / s);
+  __syncwarp();
+}
+#endif
 
 // CFRNode.cfr_pred (algorithms/deep_mccfr.py:207-229) as a resumable walk.  When the walk reaches a node deeper than
 // max_depth whose value is not cached it writes the node's features to `feat` (CTD_FEATURES_PAD floats), expands
@@ -875,6 +1073,22 @@ CTD_HD CTD_NI inline int ctd_cfr_pred_advance(CtdTree& T, uint32_t iters, uint32
     if (n.depth > max_depth && !(n.flags & CTD_NF_TERMINAL)) {
       if (!(n.flags & CTD_NF_HAS_PRED)) {
         ctd_node_load(T, n);
+#if defined(__CUDA_ARCH__)
+        if (T.vnet != nullptr) {   // fused mode: this warp evaluates the leaf itself and walks on -- no wave, no waiting
+          ctd_encode_game(*T.w, *T.kn, n.gstate == 0 ? 5 : n.player, T.act);
+          ctd_expand(T, node);
+          float pr[6];
+          ctd_value_inline(*T.vnet, T.act, pr);
+          double reward[6];
+          CTD_LOOP for (int i = 0; i < 6; ++i) { n.pred[i] = pr[i]; reward[i] = (double)pr[i]; }
+          n.flags |= CTD_NF_HAS_PRED;
+          ctd_backpropagate(T, node, reward);
+          ctd_update_strategy(T, node);
+          node = 0;
+          ++h.iterations;
+          continue;
+        }
+#endif
         ctd_encode_game(*T.w, *T.kn, n.gstate == 0 ? 5 : n.player, feat);
         ctd_expand(T, node);
         h.cur_node = (uint32_t)node;
@@ -920,29 +1134,6 @@ CTD_HD CTD_NI inline int ctd_cfr_pred_advance(CtdTree& T, uint32_t iters, uint32
 //                                algorithms/deep_mccfr.py:19-20), so the searching player may be the previous seat: the
 //                                root carries the knowledge of that seat and ctd_tree_init does the skipping
 // Leaves the root in `w`, the six observers' knowledge in kn6[0..6); returns the searching seat.
-// One uniformly random legal option without a list buffer: count, draw, enumerate again and keep the k-th.  The Seer's and the
-// Scholar's enumerations are not pure (fresh shuffles, a shrinking list: game/agent_functions.py:332-361, :462-470), so the second
-// pass starts from the state the first one started from and regenerates the same list; what is left behind is exactly one
-// enumeration plus one draw, as in `options = game.get_options_from_state(); choice(options)` (run_utils.py:38-39).
-struct CtdEnumSave {
-  uint32_t draws, tape_pos;
-  uint8_t n_seven, seven[7];
-};
-CTD_HD inline CtdEnumSave ctd_enum_save(const CtdWork& w) {
-  CtdEnumSave s;
-  s.draws = w.draws; s.tape_pos = w.tape_pos; s.n_seven = w.n_seven;
-  CTD_LOOP for (int i = 0; i < 7; ++i) s.seven[i] = w.seven[i];
-  return s;
-}
-CTD_HD inline uint64_t ctd_enum_select(CtdWork& w, const CtdKnow* kn, const CtdEnumSave& s, uint32_t k) {
-  const uint32_t draws1 = w.draws, tape1 = w.tape_pos;
-  w.draws = s.draws; w.tape_pos = s.tape_pos; w.buf_blk = 0xFFFFFFFFu; w.n_seven = s.n_seven;
-  CTD_LOOP for (int i = 0; i < 7; ++i) w.seven[i] = s.seven[i];
-  CtdEmit e2{nullptr, 0, 0, k, 0};
-  ctd_enumerate(w, e2, kn);
-  w.draws = draws1; w.tape_pos = tape1; w.buf_blk = 0xFFFFFFFFu;
-  return e2.got;
-}
 CTD_HD inline uint64_t ctd_choose_uniform(CtdWork& w, const CtdKnow* kn) {
   const CtdEnumSave sv = ctd_enum_save(w);
   CtdEmit e{nullptr, 0, 0, 0xFFFFFFFFu, 0};

@@ -57,7 +57,7 @@ static __device__ void ctd_write_result(CtdTree& T, ctd_mccfr_result* r) {
 __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) CTD_MCCFR_KERNEL_NAME(CtdMccfrArgs a) {
   __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
   __shared__ CtdKnow knows[CTD_WARPS_PER_BLOCK];
-  __shared__ __align__(16) uint8_t scratch[CTD_WARPS_PER_BLOCK][384];
+  __shared__ __align__(16) uint8_t scratch[CTD_WARPS_PER_BLOCK][CTD_TREE_SCRATCH];
   __shared__ __align__(16) ctd_state tstage[CTD_WARPS_PER_BLOCK];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   uint64_t* opts = a.opts_scratch + ((size_t)blockIdx.x * CTD_WARPS_PER_BLOCK + wib) * CTD_MCCFR_OPT_CAP;
@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) CTD_MCCFR_KER
     if (CTD_MCCFR_ALL_LANES || lane == 0) {
       CtdTree T;
       T.w = &works[wib]; T.kn = &knows[wib]; T.opts = opts; T.scratch = scratch[wib]; T.stage = &tstage[wib];
+      T.vnet = nullptr; T.act = nullptr;
       CtdTreeHdr* hdr = &a.hdrs[t];
       CtdWork& w = *T.w;
       for (int i = 0; i < 80; ++i) hdr->used_cards[i] = i < 76 ? a.used_cards[t * 76 + i] : 0;
@@ -111,6 +112,8 @@ struct CtdPredArgs {
   uint8_t* pending;   // [n_roots]
   uint32_t* n_pending;   // [0] trees waiting for a leaf value, [1] trees that yielded mid-walk
   uint32_t budget;       // iterations a tree may walk in one wave
+  int fused;             // 1: every warp evaluates its own leaves with `net` (one launch, no waves)
+  CtdValueNet net;
 };
 
 #ifndef CTD_NO_PRED_KERNEL
@@ -118,8 +121,9 @@ struct CtdPredArgs {
 __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) CTD_MCCFR_PRED_KERNEL_NAME(CtdPredArgs p) {
   __shared__ CtdWork works[CTD_WARPS_PER_BLOCK];
   __shared__ CtdKnow knows[CTD_WARPS_PER_BLOCK];
-  __shared__ __align__(16) uint8_t scratch[CTD_WARPS_PER_BLOCK][384];
+  __shared__ __align__(16) uint8_t scratch[CTD_WARPS_PER_BLOCK][CTD_TREE_SCRATCH];
   __shared__ __align__(16) ctd_state tstage[CTD_WARPS_PER_BLOCK];
+  extern __shared__ __align__(16) float acts[];   // fused mode: CTD_ACT_FLOATS floats per warp (dynamic: the block then holds more than 48 KB)
   const CtdMccfrArgs& a = p.m;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   uint64_t* opts = a.opts_scratch + ((size_t)blockIdx.x * CTD_WARPS_PER_BLOCK + wib) * CTD_MCCFR_OPT_CAP;
@@ -134,6 +138,7 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) CTD_MCCFR_PRE
       T.w = &works[wib]; T.kn = &knows[wib]; T.opts = opts; T.scratch = scratch[wib]; T.stage = &tstage[wib];
       CtdTreeHdr* hdr = &a.hdrs[t];
       T.hdr = hdr;
+      T.vnet = p.fused ? &p.net : nullptr; T.act = p.fused ? acts + wib * CTD_ACT_FLOATS : nullptr;
       CtdWork& w = *T.w;
       if (p.first) {
         for (int i = 0; i < 80; ++i) hdr->used_cards[i] = i < 76 ? a.used_cards[t * 76 + i] : 0;
@@ -170,4 +175,5 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) CTD_MCCFR_PRE
     __syncwarp();
   }
 }
+#define CTD_PRED_FUSED_SMEM (CTD_WARPS_PER_BLOCK * CTD_ACT_FLOATS * sizeof(float))
 #endif  // CTD_NO_PRED_KERNEL

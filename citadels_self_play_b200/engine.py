@@ -195,8 +195,9 @@ class Engine:
         self._check(self._lib.ctd_set_value_model(self._h, *[a.ctypes.data for a in arrs]), "ctd_set_value_model")
 
     def set_value_backend(self, backend):
-        """'fp32' (CUDA cores) or 'tcgen05' (tensor cores, 3xTF32 split precision)."""
-        b = {"fp32": 0, "tcgen05": 1}[backend]
+        """'fp32' (CUDA cores, batched), 'tcgen05' (tensor cores, 3xTF32 split precision, batched) or 'fused' (deep MCCFR in one
+        launch: every warp evaluates its own leaves in fp32; value_eval then uses the fp32 batch kernel)."""
+        b = {"fp32": 0, "tcgen05": 1, "fused": 2}[backend]
         self._check(self._lib.ctd_set_value_backend(self._h, b), "ctd_set_value_backend")
 
     def value_eval(self, features, weight=5.0):

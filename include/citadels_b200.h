@@ -271,7 +271,10 @@ ctd_status ctd_mccfr_root_children(ctd_engine* e, uint32_t tree, uint32_t first,
  * the reference's state_dict, run_utils.py:11-18). */
 ctd_status ctd_set_value_model(ctd_engine* e, const float* w1t, const float* b1, const float* w2t, const float* b2,
                                const float* w3t, const float* b3, const float* w4t, const float* b4);
-/* which kernels evaluate the dense layers: 0 = fp32 CUDA cores, 1 = tcgen05 tensor cores with 3xTF32 split precision */
+/* how leaf values are computed.  Batched over all waiting leaves (ctd_value_eval, and ctd_mccfr_pred in waves): 0 = fp32 CUDA
+ * cores, 1 = tcgen05 tensor cores with 3xTF32 split precision.  2 = fused (ctd_mccfr_pred only; ctd_value_eval then uses the
+ * fp32 batch kernel): every warp evaluates the leaves its own tree meets, fp32, inside ONE launch of the search kernel -- no
+ * waves, nothing waits.  The values equal backend 0 term for term. */
 ctd_status ctd_set_value_backend(ctd_engine* e, int backend);
 /* CFRNode.model_inference (algorithms/deep_mccfr.py:364-374) for n feature rows of 448 floats (418 used):
  * out6[i] = weight * square_and_normalize(model(features[i]))  (train_utils.py:143-145) */

@@ -4,9 +4,10 @@
 
 TEST / BENCH INFRASTRUCTURE, like everything under oracle/.  The reference is pure Python, so "compiling it from its own
 sources" is `py_compile`: every module of the hot path (game/*.py, algorithms/{deep_mccfr,models,train_utils,train}.py,
-run_utils.py) is compiled straight from /root/reference into a sourceless .pyc under oracle/_ref/ (git-ignored, NOT
-gpurun-ignored: it travels to the GPU box like the built .so files; no reference source is copied into the repo).  The GPU box
-has the same interpreter (the image is the same), so the .pyc files import there.  bench.py's `--impl reference` arm and its
+run_utils.py) is compiled straight from /root/reference into a code-object file under oracle/_ref/ (git-ignored, NOT
+gpurun-ignored: it travels to the GPU box like the built .so files; no reference source is copied into the repo).  The files
+are ordinary .pyc images under the suffix ".pyc.bin" (the snapshot that goes to the GPU box skips *.pyc like any cache file);
+oracle/ref_loop.py imports them with a twenty-line loader.  The GPU box has the same interpreter (the image is the same).  bench.py's `--impl reference` arm and its
 `cpu_baseline` legs time THIS code (kind "reference"); tests/test_ref_build.py checks it against the oracle's restatement.
 Only tests/, __graft_entry__ and bench.py's CPU legs may import it (oracle/ref_loop.py is the one entry point)."""
 import os
@@ -26,7 +27,7 @@ def available():
 
 
 def built():
-    return all(os.path.isfile(os.path.join(OUT, m + "c")) for m in MODULES)
+    return all(os.path.isfile(os.path.join(OUT, m + "c.bin")) for m in MODULES)
 
 
 def build(force=False):
@@ -34,7 +35,7 @@ def build(force=False):
     if not available():
         return built()
     for m in MODULES:
-        src, dst = os.path.join(REFERENCE, m), os.path.join(OUT, m + "c")
+        src, dst = os.path.join(REFERENCE, m), os.path.join(OUT, m + "c.bin")
         if force or not os.path.isfile(dst) or os.path.getmtime(dst) < os.path.getmtime(src):
             os.makedirs(os.path.dirname(dst), exist_ok=True)
             py_compile.compile(src, cfile=dst, dfile=m, doraise=True, optimize=0)

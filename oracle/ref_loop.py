@@ -14,12 +14,44 @@ import sys
 import time
 import types
 
+import importlib.abc
+import importlib.util
+import marshal
+
 _REF = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 _loaded = {}
 
 
 def available():
-    return os.path.isfile(os.path.join(_REF, "run_utils.pyc"))
+    return os.path.isfile(os.path.join(_REF, "run_utils.pyc.bin"))
+
+
+class _RefFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    """Imports run_utils, game.* and algorithms.* from oracle/_ref/**/*.pyc.bin (py_compile output of the reference's modules)."""
+
+    def find_spec(self, name, path=None, target=None):
+        parts = name.split(".")
+        if parts[0] not in ("run_utils", "game", "algorithms"):
+            return None
+        base = os.path.join(_REF, *parts)
+        if os.path.isdir(base):
+            return importlib.util.spec_from_loader(name, self, is_package=True)
+        if os.path.isfile(base + ".pyc.bin"):
+            return importlib.util.spec_from_loader(name, self)
+        return None
+
+    def create_module(self, spec):
+        return None
+
+    def exec_module(self, module):
+        base = os.path.join(_REF, *module.__name__.split("."))
+        if os.path.isdir(base):
+            module.__path__ = [base]
+            return
+        with open(base + ".pyc.bin", "rb") as f:
+            code = marshal.loads(f.read()[16:])      # 16-byte .pyc header: magic, flags, mtime, size
+        module.__file__ = base + ".pyc.bin"
+        exec(code, module.__dict__)
 
 
 def load():
@@ -32,8 +64,8 @@ def load():
             sys.modules[m] = types.ModuleType(m)
     sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
     sys.setrecursionlimit(5000)                                    # as train_from_scratch.py:17 (recursive backpropagate)
-    if _REF not in sys.path:
-        sys.path.insert(0, _REF)
+    if not any(isinstance(f, _RefFinder) for f in sys.meta_path):
+        sys.meta_path.insert(0, _RefFinder())
     import run_utils
     from algorithms.deep_mccfr import CFRNode
     from algorithms.models import ValueOnlyNN

@@ -93,7 +93,7 @@ struct HsTree {
 };
 static CtdKnow hs_kn;
 static uint64_t hs_opts[CTD_MCCFR_OPT_CAP];
-static uint8_t hs_scratch[384] __attribute__((aligned(16)));
+static uint8_t hs_scratch[CTD_TREE_SCRATCH] __attribute__((aligned(16)));
 static ctd_state hs_stage __attribute__((aligned(16)));
 
 static void hs_tree_begin(HsTree& H, const ctd_state* root, const CtdKnow* know, const uint8_t* used_cards, uint64_t seed, uint64_t gid,
@@ -103,7 +103,7 @@ static void hs_tree_begin(HsTree& H, const ctd_state* root, const CtdKnow* know,
   memset(&H.hdr, 0, sizeof(H.hdr));
   H.used = 1;
   CtdTree& T = H.T;
-  T.w = &w; T.kn = &hs_kn; T.opts = hs_opts; T.scratch = hs_scratch; T.stage = &hs_stage;
+  T.w = &w; T.kn = &hs_kn; T.opts = hs_opts; T.scratch = hs_scratch; T.stage = &hs_stage; T.vnet = nullptr; T.act = nullptr;
   T.hdr = &H.hdr;
   memcpy(H.hdr.used_cards, used_cards, 76);
   ctd_tree_stage_used(T);

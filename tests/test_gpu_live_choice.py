@@ -64,7 +64,7 @@ def test_facade_run_mccfr_and_arena_return_the_reference_decision(engine):
     for r in picks:
         g = F.Game.__new__(F.Game)
         g._engine, g.seed, g.gid, g._fresh, g._searches = engine, seed, int(z["gids"][r]), False, 0
-        g._rec = np.frombuffer(z["roots"][r].tobytes(), dtype=STATE_DTYPE)[0].copy()
+        g._rec = np.array(np.frombuffer(z["roots"][r].tobytes(), dtype=STATE_DTYPE)[0])
         viewer = int(g._rec["player"])
         g._know = np.zeros(6 * KNOW_BYTES, np.uint8)
         g._know[viewer * KNOW_BYTES:(viewer + 1) * KNOW_BYTES] = z["knows"][r]
@@ -87,5 +87,5 @@ def test_facade_run_mccfr_and_arena_return_the_reference_decision(engine):
         t = int(np.flatnonzero(load("live_choice_preset.npz")["terminal"])[0])
         zz = load("live_choice_preset.npz")
         g = games[0]
-        g._rec = np.frombuffer(zz["roots"][t].tobytes(), dtype=STATE_DTYPE)[0].copy()
+        g._rec = np.array(np.frombuffer(zz["roots"][t].tobytes(), dtype=STATE_DTYPE)[0])
         F.run_mccfr(g, max_iterations=10)

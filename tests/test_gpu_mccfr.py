@@ -214,8 +214,9 @@ def test_encoder_vs_oracle(engine):
         assert np.array_equal(feats[i], want), i
 
 
+@pytest.mark.parametrize("backend", ["tcgen05", "fused"])
 @pytest.mark.parametrize("name", ["deep_mccfr_preset.npz", "deep_mccfr_classic.npz", "deep_mccfr_random.npz"])
-def test_deep_trees_match_reference(engine, name):
+def test_deep_trees_match_reference(engine, name, backend):
     """Config 4: deep MCCFR, 200 iterations, value model at depth 10 -- every node against the real reference's
     cfr_pred trees (preset eight, classic eight, random 24-character rulesets).  Structure, options, game records and
     knowledge exact; regrets / strategies / values to 1e-5 of each array's scale (gate 3), the slack being fp32
@@ -223,10 +224,12 @@ def test_deep_trees_match_reference(engine, name):
     G = MccfrGolden(name)
     z = G.z
     engine.set_value_model(_model(0))
+    engine.set_value_backend(backend)
     engine.load_roots(z["roots"], z["knows"], z["used"], G.gids)
     out = engine.mccfr_pred(G.n, iterations=G.iterations, max_depth=int(z["max_depth"]), seed=G.seed, ruleset=G.ruleset,
                             trees=True)
-    assert out["waves"] >= 2
+    engine.set_value_backend("tcgen05")
+    assert out["waves"] >= 2 if backend != "fused" else out["waves"] == 1   # fused: one launch, every warp evaluates its own leaves
     for r in range(G.n):
         if z["terminal"][r]:
             assert out["results"][r]["status"] == 1
@@ -234,6 +237,22 @@ def test_deep_trees_match_reference(engine, name):
         assert out["results"][r]["status"] == 0
         assert_same_tree(G.nodes(r), tree_preorder(out["trees"][r]), ("deep", r), norm_rtol=1e-5)
 
+
+
+def test_fused_deep_mccfr_equals_the_batched_fp32_path(engine):
+    """Fused deep MCCFR (one launch, per-warp leaf evaluation) and the wave scheduler with the fp32 batch kernel run the same
+    fp32 arithmetic term for term: identical trees, bit for bit, on 256 fresh roots."""
+    n = 256
+    engine.set_value_model(_model(5, randomize_bn=True))
+    engine.make_roots(n, seed=1234, first_gid=40_000, back_lo=0, back_hi=60)
+    engine.set_value_backend("fp32")
+    a = engine.mccfr_pred(n, iterations=200, max_depth=10, seed=1234)
+    engine.set_value_backend("fused")
+    b = engine.mccfr_pred(n, iterations=200, max_depth=10, seed=1234)
+    engine.set_value_backend("tcgen05")
+    assert a["waves"] > 2 and b["waves"] == 1
+    for f in ("status", "n_nodes", "rng_draws", "n_children", "live_option", "node_value", "cumulative_regrets", "cumulative_strategy"):
+        assert np.array_equal(a["results"][f], b["results"][f]), f
 
 
 # ---------------------------------------------------------------- training targets (BASELINE configs[4])
