@@ -276,13 +276,19 @@ def bench_mccfr(args, rank, world, local, torch):
     eng.set_value_model(ValueOnlyNN(418, 512).eval())
     eng.mccfr_pred(R, iterations=IT, max_depth=10, seed=SEED)
     deep_it = deep_ms = deep_wall = 0
-    for _ in range(2):
+    for _ in range(2):     # the engine's default: fused (one launch, every warp evaluates its own leaves)
         t0 = time.perf_counter()
         o = eng.mccfr_pred(R, iterations=IT, max_depth=10, seed=SEED)
         deep_wall += time.perf_counter() - t0
         deep_it += int(o["results"]["iterations"].sum())
         deep_ms += o["kernel_ms"]
     out["deep_waves"] = int(o["waves"])
+    eng.set_value_backend("tcgen05")   # for comparison: waves, leaves batched on the tensor cores
+    eng.mccfr_pred(R, iterations=IT, max_depth=10, seed=SEED)
+    ow = eng.mccfr_pred(R, iterations=IT, max_depth=10, seed=SEED)
+    out["deep_waves_tc"] = int(ow["waves"])
+    tc_it, tc_ms = int(ow["results"]["iterations"].sum()), ow["kernel_ms"]
+    eng.set_value_backend("fused")
     split = [a + b for a, b in zip(split, status_split(o["results"]))]
     eng.close()
     # -- configs[4]: training-data generation, 2000 iterations, create_a_random_game(100) roots, nodes with >= 200 backprops
@@ -308,8 +314,8 @@ def bench_mccfr(args, rank, world, local, torch):
     cl_it, cl_ms = int(oc["results"]["iterations"].sum()), oc["kernel_ms"]
     split = [a + b for a, b in zip(split, status_split(oc["results"]))]
     eng.close()
-    ints = [pure_it, deep_it, gen_it, gen_targets, e2e_it, cl_it] + split
-    floats = [pure_ms, deep_ms, gen_ms, t5 * 1e3, pure_wall * 1e3, deep_wall * 1e3, e2e_wall * 1e3, gen_wall * 1e3, cl_ms]
+    ints = [pure_it, deep_it, gen_it, gen_targets, e2e_it, cl_it] + split + [tc_it]
+    floats = [pure_ms, deep_ms, gen_ms, t5 * 1e3, pure_wall * 1e3, deep_wall * 1e3, e2e_wall * 1e3, gen_wall * 1e3, cl_ms, tc_ms]
     return ints, floats, out
 
 
@@ -507,6 +513,8 @@ def main():
                 "pure_it_per_s": mi[0] / (mf[0] / 1e3), "deep_it_per_s": mi[1] / (mf[1] / 1e3),
                 "pure_it_per_s_wall": mi[0] / (mf[4] / 1e3), "deep_it_per_s_wall": mi[1] / (mf[5] / 1e3),
                 "deep_vs_pure": (mi[1] / mf[1]) / (mi[0] / mf[0]), "deep_waves": ex["deep_waves"],
+                "deep_mode": "fused: one launch, every warp evaluates the leaves of its own tree (fp32)",
+                "deep_it_per_s_waves_tcgen05": mi[10] / (mf[9] / 1e3), "deep_waves_tcgen05": ex["deep_waves_tc"],
                 "deep_max_depth": 10, "deep_model": "ValueOnlyNN(418,512), torch.manual_seed(0) init",
                 "e2e": {"value": mi[4] / (mf[6] / 1e3), "unit": "iterations/s", "h2d_bytes_per_step": ex["e2e_h2d_bytes"] * world,
                         "d2h_bytes_per_step": ex["e2e_d2h_bytes"] * world,

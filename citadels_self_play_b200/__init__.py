@@ -7,7 +7,8 @@ from .facade import (Game, Agent, option, Card, CFRNode, create_game, create_a_c
                      create_a_random_game, run_mccfr)
 
 from . import arena  # noqa: F401,E402  (compare_to_random.py semantics: play_games / play_games_batched)
-from . import datagen  # noqa: F401,E402  (train_from_scratch.get_mccfr_targets / generate_test_data.setup_game)
+from . import datagen  # noqa: F401,E402
+from . import parallel  # noqa: F401,E402  (multi-GPU: gathered data generation, labelled root-parallel mode)  (train_from_scratch.get_mccfr_targets / generate_test_data.setup_game)
 
 __all__ = ["arena", "datagen", "Engine", "EngineError", "RULESET_PRESET", "RULESET_CLASSIC", "DEFAULT_SEED", "Game", "Agent", "option", "Card",
            "CFRNode", "create_game", "create_a_close_to_finished_game", "create_a_random_game", "run_mccfr"]

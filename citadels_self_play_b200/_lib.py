@@ -57,6 +57,8 @@ SIGNATURES = {
                             ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_u32)]),
     "ctd_mccfr_targets": (_i, [c_void, _u32, _u64, _u32, _i, ctypes.c_double, ctypes.POINTER(_u32), ctypes.POINTER(_u32),
                                c_void, c_void, c_void, c_void]),
+    "ctd_mccfr_continue": (_i, [c_void, _u32, _u64, _u32, _i, c_void, ctypes.POINTER(ctypes.c_float)]),
+    "ctd_mccfr_root_set": (_i, [c_void, _u32, _u32, c_void, c_void, c_void]),
     "ctd_mccfr": (_i, [c_void, _u32, _u64, _u32, _i, c_void, ctypes.POINTER(ctypes.c_float)]),
 }
 

@@ -586,7 +586,8 @@ struct ctd_engine {
   const float *tc_w1, *tc_w2, *tc_w3;
   float *d_h1, *d_h2, *d_h3;
   int* d_tc_err;
-  int value_backend;  // 0 = fp32 CUDA cores (ctd_k_value_mlp), 1 = tcgen05 split-TF32 (ctd_k_linear_tc)
+  int value_backend;  // batched evaluations: 0 = fp32 CUDA cores (ctd_k_value_mlp), 1 = tcgen05 split-TF32 (ctd_k_linear_tc)
+  int fused;          // deep MCCFR: 1 = one launch, every warp evaluates its own leaves (ctd_value_inline); 0 = waves + batched evaluation
   uint8_t* h_pinned;  // pinned host staging for result copies
   size_t pinned_bytes;
   uint8_t* d_one;  // single-game staging: state | know6 | used_cards | count | winner | opts
@@ -633,7 +634,8 @@ ctd_status ctd_create(int device, uint32_t capacity, ctd_engine** out) {
   memset(e, 0, sizeof(*e));
   e->device = device;
   e->capacity = capacity;
-  e->value_backend = 1;  // dense layers on the tensor cores by default
+  e->value_backend = 1;  // batched evaluations: dense layers on the tensor cores
+  e->fused = 1;          // deep MCCFR: fused (measured 1.27x the wave scheduler at 4096 roots)
   *out = e;
   CTD_CUDA(e, cudaSetDevice(device));
   CTD_CUDA(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
@@ -1087,6 +1089,7 @@ struct CtdSearch {
   bool deep;
   uint32_t max_depth;
   float weight;
+  bool resume;      // pure MCCFR only: continue the trees of the previous call for `iterations` more
 };
 static ctd_status ctd_value_forward(ctd_engine* e, uint32_t n, const uint8_t* pending, float weight, uint32_t row0, cudaStream_t st);
 static ctd_status ctd_pred_buffers(ctd_engine* e);
@@ -1106,7 +1109,7 @@ static ctd_status ctd_pure_pass(ctd_engine* e, const CtdSearch& sp, const uint32
   memset(&a, 0, sizeof(a));
   a.n_roots = n; a.tree_list = d_list; a.roots = e->d_slots; a.knows = e->d_knows; a.used_cards = e->d_used_cards; a.gids = e->d_gids;
   a.seed = sp.seed; a.iterations = sp.iterations; a.n0_log2 = ctd_n0_log2(sp.iterations); a.hdrs = e->d_hdrs; a.arena = ctd_arena_of(e, ai);
-  a.results = e->d_results; a.counter = e->d_counter; a.opts_scratch = e->d_opts_scratch;
+  a.results = e->d_results; a.counter = e->d_counter; a.opts_scratch = e->d_opts_scratch; a.resume = sp.resume ? 1 : 0;
   CTD_CUDA(e, cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream));
   if (preset) CTD_CUDA(e, ctd_mccfr_preset_launch(a, grid, e->stream));
   else CTD_CUDA(e, ctd_mccfr_generic_launch(a, grid, e->stream));
@@ -1132,10 +1135,10 @@ static ctd_status ctd_deep_pass(ctd_engine* e, const CtdSearch& sp, const uint32
   p.max_depth = sp.max_depth; p.feat = e->d_feat; p.pred = e->d_pred; p.pending = e->d_pending;
   int per_sm = 0;
   const bool preset = sp.ruleset == CTD_RULESET_PRESET;
-  if (preset) CTD_CUDA(e, ctd_mccfr_pred_preset_blocks_per_sm(&per_sm, e->value_backend == 2));
-  else CTD_CUDA(e, ctd_mccfr_pred_generic_blocks_per_sm(&per_sm, e->value_backend == 2));
+  if (preset) CTD_CUDA(e, ctd_mccfr_pred_preset_blocks_per_sm(&per_sm, e->fused));
+  else CTD_CUDA(e, ctd_mccfr_pred_generic_blocks_per_sm(&per_sm, e->fused));
   if (per_sm < 1) per_sm = 1;
-  if (e->value_backend == 2) {
+  if (e->fused) {
     // fused: one launch; every warp walks its tree to the end and evaluates the leaves it meets itself (ctd_value_inline)
     p.fused = 1; p.budget = 0xFFFFFFFFu; p.first = 1;
     p.net = CtdValueNet{e->model.w1t, e->model.b1, e->model.w2t, e->model.b2, e->model.w3t, e->model.b3, e->model.w4t, e->model.b4, sp.weight};
@@ -1226,7 +1229,7 @@ static ctd_status ctd_deep_pass(ctd_engine* e, const CtdSearch& sp, const uint32
     CTD_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_join, 0));
   }
   if (waves_out) *waves_out = g_waves[0] > g_waves[1] ? g_waves[0] : g_waves[1];
-  if (e->value_backend == 1) {   // a tcgen05 kernel that timed out on an mbarrier skips its stores: never hand such values to the trees silently
+  if (e->value_backend == 1 && !e->fused) {   // a tcgen05 kernel that timed out on an mbarrier skips its stores: never hand such values to the trees silently
     int terr = 0;
     CTD_CUDA(e, cudaMemcpyAsync(&terr, e->d_tc_err, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CTD_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -1247,6 +1250,17 @@ static ctd_status ctd_search(ctd_engine* e, const CtdSearch& sp, ctd_mccfr_resul
   ctd_status s = ctd_ensure_results(e, sp.n_roots);
   if (s != CTD_OK) return s;
   if (sp.deep) { s = ctd_pred_buffers(e); if (s != CTD_OK) return s; }
+  if (sp.resume) {   // the trees stay where they are (arena 0 keeps its bump pointer); trees that run out of arena now keep status 2
+    if (!e->d_hdrs || sp.n_roots > e->trees_n || sp.deep) return CTD_EARG;
+    CTD_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    s = ctd_pure_pass(e, sp, nullptr, sp.n_roots, 0);
+    if (s != CTD_OK) return s;
+    CTD_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    if (results) CTD_CUDA(e, cudaMemcpyAsync(results, e->d_results, (size_t)sp.n_roots * sizeof(ctd_mccfr_result), cudaMemcpyDeviceToHost, e->stream));
+    CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+    if (elapsed_ms) CTD_CUDA(e, cudaEventElapsedTime(elapsed_ms, e->ev0, e->ev1));
+    return CTD_OK;
+  }
   uint64_t budget = ctd_tree_budget(sp.iterations, sp.ruleset);
   size_t arena0 = (size_t)(budget * sp.n_roots + (64ull << 20));
   if (const char* env = getenv("CTD_ARENA0_BYTES")) {   // test hook: a squeezed first arena exercises the retry path
@@ -1300,8 +1314,56 @@ ctd_status ctd_mccfr(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32_t it
                      ctd_mccfr_result* results, float* elapsed_ms) {
   if (!e || n_roots > e->capacity || !e->d_knows || (ruleset < CTD_RULESET_PRESET || ruleset > CTD_RULESET_RANDOM)) return CTD_EARG;
   if (n_roots == 0) return CTD_OK;
-  CtdSearch sp{n_roots, seed, iterations, ruleset, false, 0, 0.f};
+  CtdSearch sp{n_roots, seed, iterations, ruleset, false, 0, 0.f, false};
   return ctd_search(e, sp, results, elapsed_ms, nullptr);
+}
+
+// ---- root-parallel mode (labelled: NOT the reference's algorithm) ----
+// more iterations on the trees the last ctd_mccfr call grew (same n_roots, seed, ruleset), from where their walks stood
+ctd_status ctd_mccfr_continue(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32_t more_iterations, int ruleset,
+                              ctd_mccfr_result* results, float* elapsed_ms) {
+  if (!e || !e->d_knows || (ruleset < CTD_RULESET_PRESET || ruleset > CTD_RULESET_RANDOM)) return CTD_EARG;
+  if (n_roots == 0) return CTD_OK;
+  CtdSearch sp{n_roots, seed, more_iterations, ruleset, false, 0, 0.f, true};
+  return ctd_search(e, sp, results, elapsed_ms, nullptr);
+}
+
+__global__ void ctd_k_root_set(CtdTreeHdr* hdrs, uint32_t n, uint32_t stride, const double* R, const double* C, const double* V) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  CtdTree T;
+  ctd_tree_attach(T, &hdrs[t], CtdArena{hdrs[t].arena, nullptr, 0});
+  if (T.hdr->n_nodes == 0 || (T.hdr->status & ~CTD_TREE_TERMINAL_ROOT)) return;
+  CtdNode& n0 = ctd_node(T, 0);
+  for (int i = 0; i < 6; ++i) n0.V[i] = V[(size_t)t * 6 + i];
+  double vs = 0.0;
+  for (int i = 0; i < 6; ++i) vs += n0.V[i];
+  if (vs != 0.0) for (int i = 0; i < 6; ++i) n0.P[i] = n0.V[i] / vs;
+  if (n0.n_children == 0) return;
+  const uint32_t na = (n0.flags & CTD_NF_ROLE_PICK) ? 60u : n0.n_children;
+  if (na > stride) return;
+  double *r = ctd_R(T, n0), *c = ctd_C(T, n0);
+  for (uint32_t i = 0; i < na; ++i) { r[i] = R[(size_t)t * stride + i]; c[i] = C[(size_t)t * stride + i]; }
+}
+// overwrite node_value, cumulative_regrets and cumulative_strategy of the roots of trees [0, n_roots) (rows of `stride` doubles;
+// trees whose arrays are longer than a row keep theirs)
+ctd_status ctd_mccfr_root_set(ctd_engine* e, uint32_t n_roots, uint32_t stride, const double* cumulative_regrets,
+                              const double* cumulative_strategy, const double* node_value) {
+  if (!e || !e->d_hdrs || n_roots > e->trees_n || !cumulative_regrets || !cumulative_strategy || !node_value || stride == 0) return CTD_EARG;
+  if (n_roots == 0) return CTD_OK;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  const size_t ab = (size_t)n_roots * stride * sizeof(double), vb = (size_t)n_roots * 6 * sizeof(double);
+  ctd_status s = ctd_scratch(e, 2 * ab + vb);
+  if (s != CTD_OK) return s;
+  double* d = (double*)e->d_scratch;
+  CTD_CUDA(e, cudaMemcpyAsync(d, cumulative_regrets, ab, cudaMemcpyHostToDevice, e->stream));
+  CTD_CUDA(e, cudaMemcpyAsync(d + (size_t)n_roots * stride, cumulative_strategy, ab, cudaMemcpyHostToDevice, e->stream));
+  CTD_CUDA(e, cudaMemcpyAsync(d + 2 * (size_t)n_roots * stride, node_value, vb, cudaMemcpyHostToDevice, e->stream));
+  ctd_k_root_set<<<(n_roots + 127) / 128, 128, 0, e->stream>>>(e->d_hdrs, n_roots, stride, d, d + (size_t)n_roots * stride, d + 2 * (size_t)n_roots * stride);
+  e->launches++;
+  CTD_CUDA(e, cudaGetLastError());
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  return CTD_OK;
 }
 
 // trees of the last search, roots [first, first + n), as compact blocks (ctd_tree_export in csrc/ctd_mccfr.cuh)
@@ -1569,7 +1631,7 @@ static ctd_status ctd_value_forward(ctd_engine* e, uint32_t n, const uint8_t* pe
   if (st == nullptr) st = e->stream;
   const float* feat = e->d_feat + (size_t)row0 * CTD_FEATURES_PAD;
   float* pred = e->d_pred + (size_t)row0 * 8;
-  if (e->value_backend != 1) {   // fp32 batch kernel (also what ctd_value_eval uses in fused mode)
+  if (e->value_backend == 0) {
     ctd_k_value_mlp<<<(n + CTD_MLP_ROWS - 1) / CTD_MLP_ROWS, 256, CTD_MLP_SMEM, st>>>(feat, pending, n, e->model, pred, weight);
     e->launches++;
     CTD_CUDA(e, cudaGetLastError());
@@ -1589,7 +1651,8 @@ static ctd_status ctd_value_forward(ctd_engine* e, uint32_t n, const uint8_t* pe
 
 ctd_status ctd_set_value_backend(ctd_engine* e, int backend) {
   if (!e || backend < 0 || backend > 2) return CTD_EARG;
-  e->value_backend = backend;
+  e->fused = backend == 2;
+  e->value_backend = backend == 0 ? 0 : 1;
   return CTD_OK;
 }
 
@@ -1665,7 +1728,7 @@ ctd_status ctd_mccfr_pred(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32
                           float reward_weight, ctd_mccfr_result* results, float* elapsed_ms, uint32_t* waves_out) {
   if (!e || n_roots > e->capacity || !e->d_knows || !e->d_model || (ruleset < CTD_RULESET_PRESET || ruleset > CTD_RULESET_RANDOM)) return CTD_EARG;
   if (n_roots == 0) return CTD_OK;
-  CtdSearch sp{n_roots, seed, iterations, ruleset, true, max_depth, reward_weight};
+  CtdSearch sp{n_roots, seed, iterations, ruleset, true, max_depth, reward_weight, false};
   return ctd_search(e, sp, results, elapsed_ms, waves_out);
 }
 

@@ -827,13 +827,19 @@ CTD_HD CTD_NI inline void ctd_tree_init(CtdTree& T, CtdTreeHdr* hdr, const CtdAr
   h.rng_draws = T.w->draws;
 }
 
-// run `iters` iterations of the pure-MCCFR loop
-CTD_HD CTD_NI inline void ctd_cfr_train(CtdTree& T, uint32_t iters) {
+// run `iters` iterations of the pure-MCCFR loop.  resume: the tree was grown by an earlier call (root-parallel mode runs the
+// loop in rounds: parallel.root_parallel_mccfr); the walk continues from the node it stood on, on the tree's own chance stream.
+CTD_HD CTD_NI inline void ctd_cfr_train(CtdTree& T, uint32_t iters, bool resume = false) {
   CTD_TREE_SPACES(T);
   CtdTreeHdr& h = *T.hdr;
   if ((h.status & CTD_TREE_TERMINAL_ROOT) || h.n_nodes == 0) return;
-  ctd_expand(T, 0);
   int node = 0;
+  if (!resume) {
+    ctd_expand(T, 0);
+  } else {
+    T.w->draws = h.rng_draws; T.w->buf_blk = 0xFFFFFFFFu;
+    node = (int)h.cur_node;
+  }
   for (uint32_t it = 0; it < iters && !(h.status & ~CTD_TREE_TERMINAL_ROOT); ++it) {
     ctd_update_strategy(T, node);
     node = ctd_action_choice(T, node);
@@ -849,6 +855,7 @@ CTD_HD CTD_NI inline void ctd_cfr_train(CtdTree& T, uint32_t iters) {
     ++h.iterations;
   }
   ctd_update_strategy(T, 0);
+  h.cur_node = (uint32_t)node;
   h.rng_draws = T.w->draws;
 }
 

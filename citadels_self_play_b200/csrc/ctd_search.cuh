@@ -26,6 +26,7 @@ struct CtdMccfrArgs {
   unsigned long long* counter;
   uint64_t* opts_scratch;  // [gridDim.x * CTD_WARPS_PER_BLOCK][CTD_MCCFR_OPT_CAP]
   uint32_t first_root;
+  int resume;                  // 1: continue the trees an earlier launch grew (root-parallel rounds)
 };
 
 static __device__ void ctd_write_result(CtdTree& T, ctd_mccfr_result* r) {
@@ -77,6 +78,17 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) CTD_MCCFR_KER
       T.vnet = nullptr; T.act = nullptr;
       CtdTreeHdr* hdr = &a.hdrs[t];
       CtdWork& w = *T.w;
+      T.hdr = hdr;
+      if (a.resume) {
+        ctd_chance_init(w, a.seed, a.gids[t], 0);
+        w.stream = 1;
+        w.err = 0;
+        T.kn->err = 0;   // the working set is rebuilt from the tree on the first node load
+        ctd_tree_stage_used(T);
+        ctd_tree_attach(T, hdr, a.arena);
+        ctd_cfr_train(T, a.iterations, true);
+        if (a.results) ctd_write_result(T, &a.results[t]);
+      } else {
       for (int i = 0; i < 80; ++i) hdr->used_cards[i] = i < 76 ? a.used_cards[t * 76 + i] : 0;
       ctd_copy16(T.stage, &a.roots[t], (int)sizeof(ctd_state));
       ctd_unpack(T.stage, w);
@@ -84,7 +96,6 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) CTD_MCCFR_KER
       w.stream = 1;
       w.err = 0;
       ctd_copy16(T.kn, &a.knows[t], (int)sizeof(CtdKnow));
-      T.hdr = hdr;
       ctd_tree_stage_used(T);
 #ifdef CTD_FIXED_PRESET
       if (w.ruleset != CTD_RULESET_PRESET) {   // the caller named the wrong ruleset for this root: refuse, do not run
@@ -96,6 +107,7 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) CTD_MCCFR_KER
       ctd_tree_init(T, hdr, a.arena, a.n0_log2, T.kn->viewer, a.gids[t], false, false);
       ctd_cfr_train(T, a.iterations);
       if (a.results) ctd_write_result(T, &a.results[t]);
+      }
       }
     }
     __syncwarp();

@@ -23,17 +23,23 @@ from .layout import encode_options
 
 def get_mccfr_targets(model=None, minimum_sufficient_nodes=5000, base_usefullness_treshold=200, pretrain=False,
                       max_iterations=2000, engine=None, roots_per_batch=1024, seed=DEFAULT_SEED, first_gid=0,
-                      ruleset=RULESET_PRESET, back=(1, 100), stats=None):
+                      ruleset=RULESET_PRESET, back=(1, 100), stats=None, group=None):
     """train_from_scratch.get_mccfr_targets (train_from_scratch.py:53-64) with simulate_game (:23-36) batched: every batch is
-    `roots_per_batch` roots of create_a_random_game(back[1]) searched in one launch.  Trees that did not complete (status other
+    `roots_per_batch` roots of create_a_random_game(back[1]) searched in one launch.  Under torch.distributed (one process per
+    GPU) every rank searches its own `roots_per_batch` roots of each batch -- global root ids are dealt round-robin by batch and
+    rank, nothing crosses GPUs during the search -- and the targets of all ranks are gathered after every batch
+    (parallel.gather_targets), so every rank returns the same list, as the reference's Pool returns it to the parent.  Trees that did not complete (status other
     than 0: terminal roots -- run_mccfr raises ValueError on them in the reference --, roots the reference itself raises on,
     engine limits) contribute no targets (ctd_mccfr_targets skips them) and are counted in `stats`."""
     own = engine is None
     eng = engine or Engine(capacity=roots_per_batch)
-    targets, batches, gid = [], 0, int(first_gid)
+    from . import parallel, sharding
+    rank, world = parallel._world(group)
+    targets, batches = [], 0
     n_terminal = n_refused = 0
     try:
         while len(targets) < minimum_sufficient_nodes:
+            gid = int(first_gid) + sharding.first_gid(batches, rank, world, roots_per_batch)
             eng.make_roots(roots_per_batch, seed=seed, first_gid=gid, ruleset=ruleset, back_lo=back[0], back_hi=back[1],
                            flavour=ROOTS_RANDOM_GAME)
             st = eng.mccfr(roots_per_batch, iterations=max_iterations, seed=seed, ruleset=ruleset)["results"]["status"]
@@ -42,15 +48,14 @@ def get_mccfr_targets(model=None, minimum_sufficient_nodes=5000, base_usefullnes
             t = eng.mccfr_targets(roots_per_batch, iterations=max_iterations, seed=seed, ruleset=ruleset,
                                   threshold=float(base_usefullness_treshold))
             assert not len(t["meta"]) or (st[t["meta"]["tree"]] == 0).all()
-            targets += Engine.targets_as_tuples(t)
-            gid += roots_per_batch
+            targets += Engine.targets_as_tuples(parallel.gather_targets(t, group))
             batches += 1
             if batches > 10000:
                 raise RuntimeError("get_mccfr_targets: no targets are being produced (threshold too high for max_iterations?)")
     finally:
         if stats is not None:
-            stats.update(batches=batches, roots=batches * roots_per_batch, targets=len(targets), terminal_roots=n_terminal,
-                         refused_roots=n_refused)
+            stats.update(batches=batches, roots=batches * roots_per_batch * world, targets=len(targets), ranks=world,
+                         terminal_roots_this_rank=n_terminal, refused_roots_this_rank=n_refused)
         if own:
             eng.close()
     return targets

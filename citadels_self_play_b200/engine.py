@@ -187,6 +187,23 @@ class Engine:
                     "ctd_mccfr")
         return dict(results=res, trees=self.export_trees(n_roots) if trees else None, kernel_ms=ms.value)
 
+    def mccfr_continue(self, n_roots, more_iterations, seed=DEFAULT_SEED, ruleset=RULESET_PRESET):
+        """Root-parallel mode only: `more_iterations` further iterations on the trees of the last mccfr() call."""
+        res = np.zeros(n_roots, dtype=MCCFR_RESULT_DTYPE)
+        ms = ctypes.c_float()
+        self._check(self._lib.ctd_mccfr_continue(self._h, n_roots, seed, more_iterations, ruleset, res.ctypes.data, ctypes.byref(ms)),
+                    "ctd_mccfr_continue")
+        return dict(results=res, kernel_ms=ms.value)
+
+    def root_set(self, regrets, strategy, values):
+        """Root-parallel mode only: overwrite the roots' cumulative_regrets / cumulative_strategy [n, stride] and node_value [n, 6]."""
+        r = np.ascontiguousarray(regrets, dtype=np.float64)
+        c = np.ascontiguousarray(strategy, dtype=np.float64)
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        assert r.shape == c.shape and v.shape == (len(r), 6)
+        self._check(self._lib.ctd_mccfr_root_set(self._h, len(r), r.shape[1], r.ctypes.data, c.ctypes.data, v.ctypes.data),
+                    "ctd_mccfr_root_set")
+
     def set_value_model(self, model):
         """model: a ValueOnlyNN(418, 512) in eval mode (reference state_dict layout)."""
         from .value_model import fold
@@ -195,8 +212,8 @@ class Engine:
         self._check(self._lib.ctd_set_value_model(self._h, *[a.ctypes.data for a in arrs]), "ctd_set_value_model")
 
     def set_value_backend(self, backend):
-        """'fp32' (CUDA cores, batched), 'tcgen05' (tensor cores, 3xTF32 split precision, batched) or 'fused' (deep MCCFR in one
-        launch: every warp evaluates its own leaves in fp32; value_eval then uses the fp32 batch kernel)."""
+        """'fp32' (CUDA cores, leaves batched in waves), 'tcgen05' (tensor cores, 3xTF32 split precision, waves) or 'fused' (the
+        default: deep MCCFR in one launch, every warp evaluates its own leaves in fp32; value_eval stays on the tensor cores)."""
         b = {"fp32": 0, "tcgen05": 1, "fused": 2}[backend]
         self._check(self._lib.ctd_set_value_backend(self._h, b), "ctd_set_value_backend")
 

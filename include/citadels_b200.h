@@ -265,16 +265,30 @@ ctd_status ctd_mccfr_export(ctd_engine* e, uint32_t first, uint32_t n, uint64_t*
 ctd_status ctd_mccfr_root_children(ctd_engine* e, uint32_t tree, uint32_t first, uint32_t count, ctd_option* options,
                                    double* cumulative_regrets, double* strategy, double* cumulative_strategy);
 
+/* ---- root-parallel mode: NOT the reference's algorithm (its trees are private, algorithms/deep_mccfr.py:27-29; results differ from
+ * the reference's by construction and are excluded from the parity gates).  BASELINE.json's configs[4] / north_star name it:
+ * several GPUs search the SAME roots with different chance streams and pool the root's regrets / strategy / values with an
+ * all-reduce every T iterations (host side: citadels_self_play_b200/parallel.py).  These two calls are what it needs. ---- */
+/* `more_iterations` further iterations on the trees the last ctd_mccfr call left on the device (same n_roots, seed, ruleset) */
+ctd_status ctd_mccfr_continue(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32_t more_iterations, int ruleset,
+                              ctd_mccfr_result* results, float* elapsed_ms);
+/* overwrite root.node_value [n_roots][6], root.cumulative_regrets and root.cumulative_strategy [n_roots][stride] (vector roots:
+ * the first n_children entries; role-pick roots: 60) of those trees; winning_probabilities follow node_value */
+ctd_status ctd_mccfr_root_set(ctd_engine* e, uint32_t n_roots, uint32_t stride, const double* cumulative_regrets,
+                              const double* cumulative_strategy, const double* node_value);
+
 /* ---- value model at depth-limited leaves (algorithms/models.py ValueOnlyNN(418, 512), eval mode) ----
  * Weights are passed BatchNorm-folded and transposed to [in][out]: w1t [448][512] (rows 418..447 zero), b1 [512],
  * w2t [512][256], b2 [256], w3t [256][128], b3 [128], w4t [128][6], b4 [6]  (value_model.fold() builds them from
  * the reference's state_dict, run_utils.py:11-18). */
 ctd_status ctd_set_value_model(ctd_engine* e, const float* w1t, const float* b1, const float* w2t, const float* b2,
                                const float* w3t, const float* b3, const float* w4t, const float* b4);
-/* how leaf values are computed.  Batched over all waiting leaves (ctd_value_eval, and ctd_mccfr_pred in waves): 0 = fp32 CUDA
- * cores, 1 = tcgen05 tensor cores with 3xTF32 split precision.  2 = fused (ctd_mccfr_pred only; ctd_value_eval then uses the
- * fp32 batch kernel): every warp evaluates the leaves its own tree meets, fp32, inside ONE launch of the search kernel -- no
- * waves, nothing waits.  The values equal backend 0 term for term. */
+/* how leaf values are computed.
+ *   0  batched, fp32 CUDA cores: ctd_mccfr_pred advances the trees in waves and evaluates all waiting leaves at once
+ *   1  batched, tcgen05 tensor cores with 3xTF32 split precision (same waves)
+ *   2  (default) fused: ctd_mccfr_pred is ONE launch; every warp evaluates the leaves its own tree meets, in fp32, and walks
+ *      on -- no waves, nothing waits (the values equal backend 0 term for term).  Batched evaluations (ctd_value_eval, the
+ *      data-generation paths) stay on the tensor cores. */
 ctd_status ctd_set_value_backend(ctd_engine* e, int backend);
 /* CFRNode.model_inference (algorithms/deep_mccfr.py:364-374) for n feature rows of 448 floats (418 used):
  * out6[i] = weight * square_and_normalize(model(features[i]))  (train_utils.py:143-145) */

@@ -53,3 +53,32 @@ def test_generate_test_data_matches_oracle_roots():
         if j >= 6:
             break
     assert j >= 3
+
+
+def test_root_parallel_mode_single_rank_is_the_plain_search_and_rounds_continue_trees():
+    """The labelled root-parallel mode (parallel.root_parallel_mccfr): with one rank and one round it IS Engine.mccfr; in rounds,
+    ctd_mccfr_continue resumes the trees where their walks stood (iterations add up, trees keep growing, nothing is refused)."""
+    from citadels_self_play_b200 import Engine, parallel
+    eng = Engine(capacity=64)
+    try:
+        eng.make_roots(64, seed=77, first_gid=3000, back_lo=0, back_hi=40)
+        plain = eng.mccfr(64, iterations=120, seed=77)["results"]
+        one = parallel.root_parallel_mccfr(eng, 64, iterations=120, sync_every=120, seed=77)
+        for f in ("status", "n_nodes", "rng_draws", "cumulative_regrets", "cumulative_strategy", "node_value", "live_option"):
+            assert np.array_equal(plain[f], one[f]), f
+        rounds = parallel.root_parallel_mccfr(eng, 64, iterations=120, sync_every=40, seed=77)
+        live = plain["status"] == 0
+        assert (rounds["status"] == plain["status"]).all()
+        assert (rounds["iterations"][live] == 120).all() and (rounds["n_nodes"][live] >= 10).all()
+        # root_set round trip: what is written is what the next result record reports
+        R = np.tile(np.arange(128, dtype=np.float64), (64, 1))
+        C = np.full((64, 128), 1.0 / 128)
+        V = np.tile(np.arange(6, dtype=np.float64) + 1, (64, 1))
+        eng.root_set(R, C, V)
+        after = eng.mccfr_continue(64, 0, seed=77)["results"]
+        vec = live & (after["role_pick"] == 0) & (after["n_children"] > 0)
+        i = int(np.flatnonzero(vec)[0])
+        k = int(after["n_children"][i])
+        assert np.allclose(after["node_value"][i], V[i]) and np.allclose(after["cumulative_regrets"][i, :k], R[i, :k])
+    finally:
+        eng.close()

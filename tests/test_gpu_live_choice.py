@@ -31,7 +31,7 @@ def test_live_option_matches_reference(engine, name):
     assert int(z["role_pick"].sum()) == int(res["role_pick"][~z["terminal"]].sum())
 
 
-@pytest.mark.parametrize("backend", ["tcgen05", "fp32"])
+@pytest.mark.parametrize("backend", ["fused", "tcgen05", "fp32"])
 def test_deep_live_option_matches_reference(engine, backend):
     """run_mccfr(game, model, 200): cfr_pred at depth 10 with ValueOnlyNN(418,512) under torch.manual_seed(0), then the decision."""
     import torch
@@ -43,7 +43,7 @@ def test_deep_live_option_matches_reference(engine, backend):
     engine.set_value_backend(backend)
     engine.load_roots(z["roots"], z["knows"], z["used"], z["gids"])
     res = engine.mccfr_pred(n, iterations=int(z["iterations"]), max_depth=int(z["max_depth"]), seed=int(z["seed"]))["results"]
-    engine.set_value_backend("tcgen05")
+    engine.set_value_backend("fused")      # back to the default
     live = [r for r in range(n) if not z["terminal"][r]]
     # leaf values differ from torch's CPU GEMV in the last fp32 bits; a decision flips only if the uniform draw lands within
     # that distance of a CDF step, so every one of the 24 recorded decisions is expected to match

@@ -197,7 +197,7 @@ def test_value_kernel_vs_torch_fp32(engine, randomize_bn, backend):
     assert np.allclose(got.sum(1), 5.0, rtol=1e-5)
     x = np.random.RandomState(1).randn(300, 418).astype(np.float32)      # arbitrary (not integer) inputs, ragged M
     assert np.abs(engine.value_eval(x) - reference_value(m, x)).max() <= 1e-5 * 5.0
-    engine.set_value_backend("tcgen05")
+    engine.set_value_backend("fused")      # back to the default
 
 
 def test_encoder_vs_oracle(engine):
@@ -228,7 +228,7 @@ def test_deep_trees_match_reference(engine, name, backend):
     engine.load_roots(z["roots"], z["knows"], z["used"], G.gids)
     out = engine.mccfr_pred(G.n, iterations=G.iterations, max_depth=int(z["max_depth"]), seed=G.seed, ruleset=G.ruleset,
                             trees=True)
-    engine.set_value_backend("tcgen05")
+    engine.set_value_backend("fused")      # back to the default
     assert out["waves"] >= 2 if backend != "fused" else out["waves"] == 1   # fused: one launch, every warp evaluates its own leaves
     for r in range(G.n):
         if z["terminal"][r]:
@@ -249,7 +249,7 @@ def test_fused_deep_mccfr_equals_the_batched_fp32_path(engine):
     a = engine.mccfr_pred(n, iterations=200, max_depth=10, seed=1234)
     engine.set_value_backend("fused")
     b = engine.mccfr_pred(n, iterations=200, max_depth=10, seed=1234)
-    engine.set_value_backend("tcgen05")
+    engine.set_value_backend("fused")      # back to the default
     assert a["waves"] > 2 and b["waves"] == 1
     for f in ("status", "n_nodes", "rng_draws", "n_children", "live_option", "node_value", "cumulative_regrets", "cumulative_strategy"):
         assert np.array_equal(a["results"][f], b["results"][f]), f

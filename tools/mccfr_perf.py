@@ -24,8 +24,8 @@ if what in ("pure", "both"):
 if what in ("deep", "both"):
     torch.manual_seed(0)
     e.set_value_model(ValueOnlyNN(418, 512).eval())
-    e.set_value_backend(os.environ.get("CTD_BACKEND", "tcgen05"))
-    out["backend"] = os.environ.get("CTD_BACKEND", "tcgen05")
+    e.set_value_backend(os.environ.get("CTD_BACKEND", "fused"))
+    out["backend"] = os.environ.get("CTD_BACKEND", "fused")
     best = 0
     for i in range(reps):
         o = e.mccfr_pred(R, iterations=IT, max_depth=10, seed=0xC17ADE15, ruleset=RS)
