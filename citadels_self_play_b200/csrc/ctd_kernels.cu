@@ -25,6 +25,7 @@
 #include "ctd_mccfr.cuh"
 #include "ctd_search.cuh"
 #include "ctd_value_tc.cuh"
+#include "ctd_train.cuh"
 
 
 // ------------------------------------------------------------------------------------------ device helpers
@@ -590,6 +591,7 @@ struct ctd_engine {
   int fused;          // deep MCCFR: 1 = one launch, every warp evaluates its own leaves (ctd_value_inline); 0 = waves + batched evaluation
   uint8_t* h_pinned;  // pinned host staging for result copies
   size_t pinned_bytes;
+  struct CtdTrainer* trainer;   // value-network training (ctd_train_*), created on first use
   uint8_t* d_one;  // single-game staging: state | know6 | used_cards | count | winner | opts
   char err[256];
 };
@@ -651,9 +653,11 @@ ctd_status ctd_create(int device, uint32_t capacity, ctd_engine** out) {
   return CTD_OK;
 }
 
+void ctd_train_end(ctd_engine* e);
 void ctd_destroy(ctd_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
+  ctd_train_end(e);
   if (e->d_slots) cudaFree(e->d_slots);
   if (e->d_tape) cudaFree(e->d_tape);
   if (e->d_tape_off) cudaFree(e->d_tape_off);
@@ -1730,6 +1734,214 @@ ctd_status ctd_mccfr_pred(ctd_engine* e, uint32_t n_roots, uint64_t seed, uint32
   if (n_roots == 0) return CTD_OK;
   CtdSearch sp{n_roots, seed, iterations, ruleset, true, max_depth, reward_weight, false};
   return ctd_search(e, sp, results, elapsed_ms, waves_out);
+}
+
+
+// ------------------------------------------------------------------------------------------ value-network training
+// algorithms/train.py:13-86 (train_node_value_only) on the device; kernels in ctd_train.cuh
+struct CtdTrainer {
+  uint32_t n_train, n_val, batch, bp;   // bp: batch rounded up to a multiple of 32 (the K extent of the weight-gradient products)
+  uint32_t step;                        // optimiser steps taken (Adam bias correction, dropout mask counter)
+  float *feat_tr, *feat_va;
+  double *val_tr, *val_va;
+  uint32_t* perm;
+  float *P, *G, *M, *V;                 // CtdTrainLayout
+  float *rm1, *rv1, *rm2, *rv2;         // BatchNorm running statistics
+  float *X, *XT, *Z1, *H1, *H1T, *Z2, *H2, *H2T, *H3, *dY, *dZ3, *dZ3T, *dH2, *dZ2T, *dH1, *dZ1T, *W2T, *W3T, *inv1, *inv2, *zero;
+  double *T, *loss;
+};
+static void ctd_tr_free(CtdTrainer* t) {
+  void* ptrs[] = {t->feat_tr, t->feat_va, t->val_tr, t->val_va, t->perm, t->P, t->G, t->M, t->V, t->rm1, t->rv1, t->rm2, t->rv2, t->X, t->XT,
+                  t->Z1, t->H1, t->H1T, t->Z2, t->H2, t->H2T, t->H3, t->dY, t->dZ3, t->dZ3T, t->dH2, t->dZ2T, t->dH1, t->dZ1T, t->W2T, t->W3T,
+                  t->inv1, t->inv2, t->zero, t->T, t->loss};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete t;
+}
+void ctd_train_end(ctd_engine* e) {
+  if (!e || !e->trainer) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  ctd_tr_free(e->trainer);
+  e->trainer = nullptr;
+}
+#define CTD_TR_ALLOC(ptr, count)                                                                          \
+  do {                                                                                                    \
+    cudaError_t _c = cudaMalloc((void**)&(ptr), (size_t)(count) * sizeof(*(ptr)));                        \
+    if (_c == cudaSuccess) _c = cudaMemsetAsync((ptr), 0, (size_t)(count) * sizeof(*(ptr)), e->stream);   \
+    if (_c != cudaSuccess) { ctd_tr_free(t); return ctd_fail(e, _c, "training buffers"); }              \
+  } while (0)
+
+ctd_status ctd_train_begin(ctd_engine* e, uint32_t n_train, const float* features, const double* node_values, uint32_t n_val,
+                           const float* val_features, const double* val_node_values, uint32_t batch_size) {
+  if (!e || !features || !node_values || n_train == 0 || batch_size == 0 || batch_size > 65536 || (n_val != 0 && (!val_features || !val_node_values)))
+    return CTD_EARG;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  ctd_train_end(e);
+  CtdTrainer* t = new (std::nothrow) CtdTrainer();
+  if (!t) return CTD_ENOMEM;
+  memset(t, 0, sizeof(*t));
+  t->n_train = n_train; t->n_val = n_val; t->batch = batch_size; t->bp = (batch_size + 31) & ~31u;
+  const size_t bp = t->bp;
+  CTD_TR_ALLOC(t->feat_tr, (size_t)n_train * 418); CTD_TR_ALLOC(t->val_tr, (size_t)n_train * 6);
+  CTD_TR_ALLOC(t->feat_va, (size_t)(n_val ? n_val : 1) * 418); CTD_TR_ALLOC(t->val_va, (size_t)(n_val ? n_val : 1) * 6);
+  CTD_TR_ALLOC(t->perm, n_train);
+  CTD_TR_ALLOC(t->P, CtdTrainLayout::total); CTD_TR_ALLOC(t->G, CtdTrainLayout::total); CTD_TR_ALLOC(t->M, CtdTrainLayout::total); CTD_TR_ALLOC(t->V, CtdTrainLayout::total);
+  CTD_TR_ALLOC(t->rm1, CTD_TR_H1); CTD_TR_ALLOC(t->rv1, CTD_TR_H1); CTD_TR_ALLOC(t->rm2, CTD_TR_H2); CTD_TR_ALLOC(t->rv2, CTD_TR_H2);
+  CTD_TR_ALLOC(t->X, bp * CTD_TR_IN); CTD_TR_ALLOC(t->XT, bp * CTD_TR_IN);
+  CTD_TR_ALLOC(t->Z1, bp * CTD_TR_H1); CTD_TR_ALLOC(t->H1, bp * CTD_TR_H1); CTD_TR_ALLOC(t->H1T, bp * CTD_TR_H1);
+  CTD_TR_ALLOC(t->Z2, bp * CTD_TR_H2); CTD_TR_ALLOC(t->H2, bp * CTD_TR_H2); CTD_TR_ALLOC(t->H2T, bp * CTD_TR_H2);
+  CTD_TR_ALLOC(t->H3, bp * CTD_TR_H3); CTD_TR_ALLOC(t->dY, bp * 8); CTD_TR_ALLOC(t->dZ3, bp * CTD_TR_H3); CTD_TR_ALLOC(t->dZ3T, bp * CTD_TR_H3);
+  CTD_TR_ALLOC(t->dH2, bp * CTD_TR_H2); CTD_TR_ALLOC(t->dZ2T, bp * CTD_TR_H2); CTD_TR_ALLOC(t->dH1, bp * CTD_TR_H1); CTD_TR_ALLOC(t->dZ1T, bp * CTD_TR_H1);
+  CTD_TR_ALLOC(t->W2T, (size_t)CTD_TR_H1 * CTD_TR_H2); CTD_TR_ALLOC(t->W3T, (size_t)CTD_TR_H2 * CTD_TR_H3);
+  CTD_TR_ALLOC(t->inv1, CTD_TR_H1); CTD_TR_ALLOC(t->inv2, CTD_TR_H2); CTD_TR_ALLOC(t->zero, 512);
+  CTD_TR_ALLOC(t->T, bp * 6); CTD_TR_ALLOC(t->loss, 2);
+  cudaError_t c = cudaMemcpyAsync(t->feat_tr, features, (size_t)n_train * 418 * sizeof(float), cudaMemcpyHostToDevice, e->stream);
+  if (c == cudaSuccess) c = cudaMemcpyAsync(t->val_tr, node_values, (size_t)n_train * 6 * sizeof(double), cudaMemcpyHostToDevice, e->stream);
+  if (c == cudaSuccess && n_val) c = cudaMemcpyAsync(t->feat_va, val_features, (size_t)n_val * 418 * sizeof(float), cudaMemcpyHostToDevice, e->stream);
+  if (c == cudaSuccess && n_val) c = cudaMemcpyAsync(t->val_va, val_node_values, (size_t)n_val * 6 * sizeof(double), cudaMemcpyHostToDevice, e->stream);
+  if (c == cudaSuccess) c = cudaFuncSetAttribute(ctd_k_linear_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CTD_TC_SMEM);
+  if (c == cudaSuccess && !e->d_tc_err) { c = cudaMalloc((void**)&e->d_tc_err, sizeof(int)); if (c == cudaSuccess) c = cudaMemsetAsync(e->d_tc_err, 0, sizeof(int), e->stream); }
+  if (c == cudaSuccess) c = cudaStreamSynchronize(e->stream);
+  if (c != cudaSuccess) { ctd_tr_free(t); return ctd_fail(e, c, "training data upload"); }
+  e->trainer = t;
+  return CTD_OK;
+}
+
+// the 16 tensors of ValueOnlyNN(418, 512).state_dict() in its own order (num_batches_tracked aside):
+// fc1.weight [512][418] fc1.bias bn1.weight bn1.bias bn1.running_mean bn1.running_var fc2.weight [256][512] fc2.bias bn2.weight
+// bn2.bias bn2.running_mean bn2.running_var fc3.weight [128][256] fc3.bias fc4.weight [6][128] fc4.bias
+static const size_t ctd_tr_count[16] = {512 * 418, 512, 512, 512, 512, 512, 256 * 512, 256, 256, 256, 256, 256, 128 * 256, 128, 6 * 128, 6};
+static float* ctd_tr_slot(CtdTrainer* t, int i) {
+  typedef CtdTrainLayout L;
+  float* P = t->P;
+  float* slots[16] = {P + L::w1, P + L::b1, P + L::g1, P + L::be1, t->rm1, t->rv1, P + L::w2, P + L::b2, P + L::g2, P + L::be2, t->rm2, t->rv2,
+                      P + L::w3, P + L::b3, P + L::w4, P + L::b4};
+  return slots[i];
+}
+ctd_status ctd_train_set_state(ctd_engine* e, const float* const* tensors16) {
+  if (!e || !e->trainer || !tensors16) return CTD_EARG;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  CtdTrainer* t = e->trainer;
+  CTD_CUDA(e, cudaMemsetAsync(t->P, 0, CtdTrainLayout::total * sizeof(float), e->stream));
+  CTD_CUDA(e, cudaMemsetAsync(t->M, 0, CtdTrainLayout::total * sizeof(float), e->stream));
+  CTD_CUDA(e, cudaMemsetAsync(t->V, 0, CtdTrainLayout::total * sizeof(float), e->stream));
+  for (int i = 0; i < 16; ++i) {
+    if (!tensors16[i]) return CTD_EARG;
+    if (i == 0)   // fc1.weight: rows of 418 into rows of 512
+      CTD_CUDA(e, cudaMemcpy2DAsync(ctd_tr_slot(t, 0), CTD_TR_IN * sizeof(float), tensors16[0], 418 * sizeof(float), 418 * sizeof(float), 512, cudaMemcpyHostToDevice, e->stream));
+    else
+      CTD_CUDA(e, cudaMemcpyAsync(ctd_tr_slot(t, i), tensors16[i], ctd_tr_count[i] * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  }
+  t->step = 0;
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  return CTD_OK;
+}
+ctd_status ctd_train_get_state(ctd_engine* e, float* const* tensors16) {
+  if (!e || !e->trainer || !tensors16) return CTD_EARG;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  CtdTrainer* t = e->trainer;
+  for (int i = 0; i < 16; ++i) {
+    if (!tensors16[i]) return CTD_EARG;
+    if (i == 0)
+      CTD_CUDA(e, cudaMemcpy2DAsync(tensors16[0], 418 * sizeof(float), ctd_tr_slot(t, 0), CTD_TR_IN * sizeof(float), 418 * sizeof(float), 512, cudaMemcpyDeviceToHost, e->stream));
+    else
+      CTD_CUDA(e, cudaMemcpyAsync(tensors16[i], ctd_tr_slot(t, i), ctd_tr_count[i] * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  }
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  return CTD_OK;
+}
+
+// C [M][N] (ldc) = A [M][K] (lda) . B [N][K]^T (ldb) + bias, optional ReLU, on the tensor cores (N multiple of 128, K of 32)
+static void ctd_tr_gemm(ctd_engine* e, const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M, int N, int K, int relu) {
+  ctd_k_linear_tc<<<dim3((M + CTD_TC_BM - 1) / CTD_TC_BM, N / CTD_TC_BN), 128, CTD_TC_SMEM, e->stream>>>(A, lda, B, ldb, bias, C, ldc, M, K, relu, e->d_tc_err);
+  e->launches++;
+}
+static void ctd_tr_transpose(ctd_engine* e, const float* in, int R, int C, int ld_in, float* out, int ld_out) {
+  ctd_k_tr_transpose<<<dim3((C + 31) / 32, (ld_out + 31) / 32), dim3(32, 8), 0, e->stream>>>(in, R, C, ld_in, out, ld_out);
+  e->launches++;
+}
+// forward of one batch already gathered into t->X / t->T; train: batch statistics + dropout, else running statistics
+static void ctd_tr_forward(ctd_engine* e, CtdTrainer* t, uint32_t B, int train, uint64_t seed) {
+  typedef CtdTrainLayout L;
+  const uint32_t bp = t->bp;
+  ctd_tr_gemm(e, t->X, CTD_TR_IN, t->P + L::w1, CTD_TR_IN, t->P + L::b1, t->Z1, CTD_TR_H1, (int)B, CTD_TR_H1, CTD_TR_IN, 0);
+  ctd_k_tr_bn_fwd<<<CTD_TR_H1 / 32, dim3(32, 8), 0, e->stream>>>(t->Z1, CTD_TR_H1, B, bp, t->P + L::g1, t->P + L::be1, t->rm1, t->rv1, t->inv1, t->H1, train, seed, t->step, 1);
+  ctd_tr_gemm(e, t->H1, CTD_TR_H1, t->P + L::w2, CTD_TR_H1, t->P + L::b2, t->Z2, CTD_TR_H2, (int)B, CTD_TR_H2, CTD_TR_H1, 0);
+  ctd_k_tr_bn_fwd<<<CTD_TR_H2 / 32, dim3(32, 8), 0, e->stream>>>(t->Z2, CTD_TR_H2, B, bp, t->P + L::g2, t->P + L::be2, t->rm2, t->rv2, t->inv2, t->H2, train, seed, t->step, 2);
+  ctd_tr_gemm(e, t->H2, CTD_TR_H2, t->P + L::w3, CTD_TR_H2, t->P + L::b3, t->H3, CTD_TR_H3, (int)B, CTD_TR_H3, CTD_TR_H2, 1);
+  e->launches += 2;
+}
+
+// one epoch of train_node_value_only: every batch of `perm` order (model.train()), then the evaluation pass over the validation
+// set in its own order (model.eval()).  *train_loss / *eval_loss: mean over batches of the batch-mean KL loss (train.py:46-69).
+ctd_status ctd_train_epoch(ctd_engine* e, uint64_t seed, float lr, const uint32_t* perm, double* train_loss, double* eval_loss) {
+  if (!e || !e->trainer) return CTD_EARG;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  CtdTrainer* t = e->trainer;
+  typedef CtdTrainLayout L;
+  const uint32_t bp = t->bp;
+  if (perm) CTD_CUDA(e, cudaMemcpyAsync(t->perm, perm, (size_t)t->n_train * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+  double tl = 0.0, el = 0.0;
+  uint32_t nb = 0;
+  for (uint32_t first = 0; first < t->n_train; first += t->batch, ++nb) {
+    const uint32_t B = t->n_train - first < t->batch ? t->n_train - first : t->batch;
+    ctd_k_tr_gather<<<bp, 128, 0, e->stream>>>(t->feat_tr, t->val_tr, perm ? t->perm : nullptr, first, B, bp, t->X, t->T);
+    ctd_tr_forward(e, t, B, 1, seed);
+    CTD_CUDA(e, cudaMemsetAsync(t->loss, 0, sizeof(double), e->stream));
+    CTD_CUDA(e, cudaMemsetAsync(t->G, 0, L::total * sizeof(float), e->stream));
+    ctd_k_tr_head<<<(B + 127) / 128, 128, 0, e->stream>>>(t->H3, t->P + L::w4, t->P + L::b4, t->T, B, t->dY, t->loss);
+    // ---- backward
+    ctd_k_tr_fc4_bwd<<<bp, CTD_TR_H3, 0, e->stream>>>(t->dY, t->P + L::w4, t->H3, B, bp, t->dZ3);
+    ctd_k_tr_fc4_wgrad<<<6, CTD_TR_H3, 0, e->stream>>>(t->dY, t->H3, B, t->G + L::w4, t->G + L::b4);
+    ctd_tr_transpose(e, t->dZ3, (int)bp, CTD_TR_H3, CTD_TR_H3, t->dZ3T, (int)bp);
+    ctd_tr_transpose(e, t->H2, (int)bp, CTD_TR_H2, CTD_TR_H2, t->H2T, (int)bp);
+    ctd_tr_gemm(e, t->dZ3T, (int)bp, t->H2T, (int)bp, t->zero, t->G + L::w3, CTD_TR_H2, CTD_TR_H3, CTD_TR_H2, (int)bp, 0);      // dW3 = dZ3^T . H2
+    ctd_k_tr_colsum<<<CTD_TR_H3 / 32, dim3(32, 8), 0, e->stream>>>(t->dZ3, CTD_TR_H3, B, t->G + L::b3);
+    ctd_tr_transpose(e, t->P + L::w3, CTD_TR_H3, CTD_TR_H2, CTD_TR_H2, t->W3T, CTD_TR_H3);
+    ctd_tr_gemm(e, t->dZ3, CTD_TR_H3, t->W3T, CTD_TR_H3, t->zero, t->dH2, CTD_TR_H2, (int)B, CTD_TR_H2, CTD_TR_H3, 0);           // dH2 = dZ3 . W3
+    ctd_k_tr_bn_bwd<<<CTD_TR_H2 / 32, dim3(32, 8), 0, e->stream>>>(t->dH2, t->Z2, t->H2, CTD_TR_H2, B, bp, t->P + L::g2, t->inv2, t->G + L::g2, t->G + L::be2);
+    ctd_tr_transpose(e, t->dH2, (int)bp, CTD_TR_H2, CTD_TR_H2, t->dZ2T, (int)bp);
+    ctd_tr_transpose(e, t->H1, (int)bp, CTD_TR_H1, CTD_TR_H1, t->H1T, (int)bp);
+    ctd_tr_gemm(e, t->dZ2T, (int)bp, t->H1T, (int)bp, t->zero, t->G + L::w2, CTD_TR_H1, CTD_TR_H2, CTD_TR_H1, (int)bp, 0);      // dW2 = dZ2^T . H1
+    ctd_k_tr_colsum<<<CTD_TR_H2 / 32, dim3(32, 8), 0, e->stream>>>(t->dH2, CTD_TR_H2, B, t->G + L::b2);
+    ctd_tr_transpose(e, t->P + L::w2, CTD_TR_H2, CTD_TR_H1, CTD_TR_H1, t->W2T, CTD_TR_H2);
+    ctd_tr_gemm(e, t->dH2, CTD_TR_H2, t->W2T, CTD_TR_H2, t->zero, t->dH1, CTD_TR_H1, (int)B, CTD_TR_H1, CTD_TR_H2, 0);           // dH1 = dZ2 . W2
+    ctd_k_tr_bn_bwd<<<CTD_TR_H1 / 32, dim3(32, 8), 0, e->stream>>>(t->dH1, t->Z1, t->H1, CTD_TR_H1, B, bp, t->P + L::g1, t->inv1, t->G + L::g1, t->G + L::be1);
+    ctd_tr_transpose(e, t->dH1, (int)bp, CTD_TR_H1, CTD_TR_H1, t->dZ1T, (int)bp);
+    ctd_tr_transpose(e, t->X, (int)bp, CTD_TR_IN, CTD_TR_IN, t->XT, (int)bp);
+    ctd_tr_gemm(e, t->dZ1T, (int)bp, t->XT, (int)bp, t->zero, t->G + L::w1, CTD_TR_IN, CTD_TR_H1, CTD_TR_IN, (int)bp, 0);        // dW1 = dZ1^T . X
+    ctd_k_tr_colsum<<<CTD_TR_H1 / 32, dim3(32, 8), 0, e->stream>>>(t->dH1, CTD_TR_H1, B, t->G + L::b1);
+    // ---- Adam
+    t->step += 1;
+    const float bc1 = 1.f - powf(0.9f, (float)t->step), bc2 = 1.f - powf(0.999f, (float)t->step);
+    ctd_k_tr_adam<<<(unsigned)((L::total + 255) / 256), 256, 0, e->stream>>>(t->P, t->G, t->M, t->V, L::total, lr, bc1, bc2);
+    e->launches += 10;
+    CTD_CUDA(e, cudaGetLastError());
+    double h = 0.0;
+    CTD_CUDA(e, cudaMemcpyAsync(&h, t->loss, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+    tl += h / (double)B;
+  }
+  if (train_loss) *train_loss = nb ? tl / nb : 0.0;
+  uint32_t vb = 0;
+  for (uint32_t first = 0; first < t->n_val; first += t->batch, ++vb) {
+    const uint32_t B = t->n_val - first < t->batch ? t->n_val - first : t->batch;
+    ctd_k_tr_gather<<<bp, 128, 0, e->stream>>>(t->feat_va, t->val_va, nullptr, first, B, bp, t->X, t->T);
+    ctd_tr_forward(e, t, B, 0, seed);
+    CTD_CUDA(e, cudaMemsetAsync(t->loss, 0, sizeof(double), e->stream));
+    ctd_k_tr_head<<<(B + 127) / 128, 128, 0, e->stream>>>(t->H3, t->P + L::w4, t->P + L::b4, t->T, B, nullptr, t->loss);
+    e->launches += 2;
+    CTD_CUDA(e, cudaGetLastError());
+    double h = 0.0;
+    CTD_CUDA(e, cudaMemcpyAsync(&h, t->loss, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+    el += h / (double)B;
+  }
+  if (eval_loss) *eval_loss = vb ? el / vb : 0.0;
+  int terr = 0;
+  CTD_CUDA(e, cudaMemcpy(&terr, e->d_tc_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (terr) { CTD_CUDA(e, cudaMemset(e->d_tc_err, 0, sizeof(int))); snprintf(e->err, sizeof(e->err), "tcgen05 GEMM: mbarrier wait timed out"); return CTD_ECUDA; }
+  return CTD_OK;
 }
 
 }  // extern "C"

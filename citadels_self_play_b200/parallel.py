@@ -76,6 +76,7 @@ def root_parallel_mccfr(engine, n_roots, iterations=2000, sync_every=200, seed=D
     key = (int(seed) + rank * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
     res = None
     done = 0
+    prev_R = prev_V = None       # the pooled regrets / values after the previous round (what every rank continued from)
     while done < iterations:
         step = min(sync_every, iterations - done)
         out = engine.mccfr(n_roots, iterations=step, seed=key, ruleset=ruleset) if done == 0 else \
@@ -86,19 +87,25 @@ def root_parallel_mccfr(engine, n_roots, iterations=2000, sync_every=200, seed=D
             continue
         k = res["n_children"].astype(np.int64)
         poolable = (res["status"] == 0) & (res["role_pick"] == 0) & (res["viewer"] == res["player"]) & (k > 0) & (k <= 128)
-        R = np.where(poolable[:, None], res["cumulative_regrets"][:, :128], 0.0)
+        if prev_R is None:
+            prev_R, prev_V = np.zeros((n_roots, 128)), np.zeros((n_roots, 6))
+        # regrets and values are running sums: pool what THIS round added on every rank; the cumulative strategy is a normalised
+        # moving average: pool it as the mean
+        dR = np.where(poolable[:, None], res["cumulative_regrets"][:, :128] - prev_R, 0.0)
         C = np.where(poolable[:, None], res["cumulative_strategy"][:, :128], 0.0)
-        V = np.where((res["status"] == 0)[:, None], res["node_value"], 0.0)
-        pk = torch.from_numpy(np.concatenate([R, C, V, poolable[:, None].astype(np.float64)], axis=1)).to(_device())
+        dV = np.where((res["status"] == 0)[:, None], res["node_value"] - prev_V, 0.0)
+        pk = torch.from_numpy(np.concatenate([dR, C, dV, poolable[:, None].astype(np.float64)], axis=1)).to(_device())
         dist.all_reduce(pk, op=dist.ReduceOp.SUM, group=group)
         pk = pk.cpu().numpy()
-        R, C, V, votes = pk[:, :128], pk[:, 128:256], pk[:, 256:262], pk[:, 262]
+        dR, C, dV, votes = pk[:, :128], pk[:, 128:256], pk[:, 256:262], pk[:, 262]
         ok = poolable & (votes == world)               # the same decision node on every rank
         cs = C.sum(axis=1, keepdims=True)
         C = np.where(cs > 0, C / np.where(cs > 0, cs, 1.0), C)
-        R = np.where(ok[:, None], R, res["cumulative_regrets"][:, :128])
+        R = np.where(ok[:, None], prev_R + dR, res["cumulative_regrets"][:, :128])
         C = np.where(ok[:, None], C, res["cumulative_strategy"][:, :128])
+        V = prev_V + dV
         engine.root_set(R, C, V)
+        prev_R, prev_V = np.where(ok[:, None], R, 0.0), V
         res = res.copy()
         res["cumulative_regrets"][:, :128], res["cumulative_strategy"][:, :128], res["node_value"] = R, C, V
     return res

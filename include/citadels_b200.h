@@ -324,6 +324,24 @@ ctd_status ctd_mccfr_targets(ctd_engine* e, uint32_t n_roots, uint64_t seed, uin
                              uint32_t* n_records, uint32_t* n_option_slots, float* features, ctd_target_meta* meta,
                              ctd_option* options, double* regrets);
 
+/* ---- value-network training (algorithms/train.py:13-86 train_node_value_only): ValueOnlyNN(418, 512) in train mode (BatchNorm with
+ * batch statistics, Dropout(0.2)), KLDivLoss(batchmean) on log(square_and_normalize(outputs) + 1e-10) vs square_and_normalize(labels),
+ * Adam.  The dense products run on the tcgen05 kernel of the inference path.  Host loop (epochs, StepLR, best-eval checkpoint):
+ * citadels_self_play_b200/train.py. ---- */
+/* training set: features [n_train][418] (item[0] of the reference's target tuples) and node values [n_train][6] (item[2], float64);
+ * validation set likewise; batch_size as in DataLoader(batch_size=...) */
+ctd_status ctd_train_begin(ctd_engine* e, uint32_t n_train, const float* features, const double* node_values, uint32_t n_val,
+                           const float* val_features, const double* val_node_values, uint32_t batch_size);
+/* the 16 float32 tensors of ValueOnlyNN(418, 512).state_dict(), in its order (num_batches_tracked left out): fc1.weight [512][418],
+ * fc1.bias, bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var, fc2.weight [256][512], fc2.bias, bn2.*, fc3.weight [128][256],
+ * fc3.bias, fc4.weight [6][128], fc4.bias.  set_state also resets the optimiser (Adam moments, step count). */
+ctd_status ctd_train_set_state(ctd_engine* e, const float* const* tensors16);
+ctd_status ctd_train_get_state(ctd_engine* e, float* const* tensors16);
+/* one epoch (train.py:36-69): every batch of the training set in `perm` order (n_train indices; NULL = as stored) with
+ * learning rate lr, then the evaluation pass.  Dropout masks are Philox(seed, optimiser step, layer, element). */
+ctd_status ctd_train_epoch(ctd_engine* e, uint64_t seed, float lr, const uint32_t* perm, double* train_loss, double* eval_loss);
+void ctd_train_end(ctd_engine* e);
+
 /* number of kernels this engine has launched so far */
 uint64_t ctd_launch_count(const ctd_engine* e);
 

@@ -69,7 +69,7 @@ def test_root_parallel_mode_single_rank_is_the_plain_search_and_rounds_continue_
         rounds = parallel.root_parallel_mccfr(eng, 64, iterations=120, sync_every=40, seed=77)
         live = plain["status"] == 0
         assert (rounds["status"] == plain["status"]).all()
-        assert (rounds["iterations"][live] == 120).all() and (rounds["n_nodes"][live] >= 10).all()
+        assert (rounds["iterations"][live] == 120).all() and (rounds["n_nodes"][live] >= 2).all()
         # root_set round trip: what is written is what the next result record reports
         R = np.tile(np.arange(128, dtype=np.float64), (64, 1))
         C = np.full((64, 128), 1.0 / 128)

@@ -109,12 +109,18 @@ def test_two_rank_gather_and_root_parallel_pooling():
         assert [c[:2] for c in calls] == [("mccfr", 20), ("continue", 20), ("continue", 10)]
         assert len(sets) == 3
         R, C, V = sets[-1]
-        assert np.allclose(R[0, :4], [1 + 2, 4, 6, 8])                       # root 0: a decision node on both ranks -> summed
-        assert np.allclose(C[0, :4], [0.25, 0.25, 0.25, 0.25])               # summed and renormalised
+        R1, C1, V1 = sets[0]
+        assert np.allclose(R1[0, :4], [1 + 2, 4, 6, 8])                      # round 1, root 0: a decision node on both ranks -> summed
+        assert np.allclose(C1[0, :4], [0.25, 0.25, 0.25, 0.25])              # mean of the two strategies, renormalised
+        assert np.allclose(V1, np.arange(18).reshape(3, 6) * 3)              # values are pooled for every completed root
+        # later rounds pool INCREMENTS over what every rank continued from: the scripted engine reports its first-round arrays
+        # again, i.e. increments of (local - pooled) per rank
+        own0, own1 = _ScriptedEngine(0).res, _ScriptedEngine(1).res
+        inc = (own0["cumulative_regrets"][0, :4] - R1[0, :4]) + (own1["cumulative_regrets"][0, :4] - R1[0, :4])
+        assert np.allclose(sets[1][0][0, :4], R1[0, :4] + inc)
         own = _ScriptedEngine(rank).res
         assert np.allclose(R[1, :3], own["cumulative_regrets"][1, :3])       # root 1: not the same node everywhere -> kept
-        assert np.allclose(V, np.arange(18).reshape(3, 6) * 3)               # values are pooled for every completed root
-        assert np.allclose(res["cumulative_regrets"][0, :4], [3, 4, 6, 8])
+        assert np.array_equal(res["cumulative_regrets"][0, :4], R[0, :4])
     assert got[0][1][0][2] != got[1][1][0][2]                                # per-rank Philox keys
 
 
