@@ -60,6 +60,7 @@ SIGNATURES = {
     "ctd_train_begin": (_i, [c_void, _u32, c_void, c_void, _u32, c_void, c_void, _u32]),
     "ctd_train_set_state": (_i, [c_void, c_void]),
     "ctd_train_get_state": (_i, [c_void, c_void]),
+    "ctd_train_get_grads": (_i, [c_void, c_void]),
     "ctd_train_epoch": (_i, [c_void, _u64, ctypes.c_float, c_void, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "ctd_train_end": (None, [c_void]),
     "ctd_mccfr_continue": (_i, [c_void, _u32, _u64, _u32, _i, c_void, ctypes.POINTER(ctypes.c_float)]),

@@ -587,6 +587,10 @@ struct ctd_engine {
   const float *tc_w1, *tc_w2, *tc_w3;
   float *d_h1, *d_h2, *d_h3;
   int* d_tc_err;
+  // the weights pre-split into their three TF32 terms, [3][N][K] per layer, and their tensor maps (TMA loads of the B operand)
+  float* d_wsplit;
+  CUtensorMap tmap[3];
+  bool tmap_ok;
   int value_backend;  // batched evaluations: 0 = fp32 CUDA cores (ctd_k_value_mlp), 1 = tcgen05 split-TF32 (ctd_k_linear_tc)
   int fused;          // deep MCCFR: 1 = one launch, every warp evaluates its own leaves (ctd_value_inline); 0 = waves + batched evaluation
   uint8_t* h_pinned;  // pinned host staging for result copies
@@ -690,6 +694,7 @@ void ctd_destroy(ctd_engine* e) {
   if (e->d_h2) cudaFree(e->d_h2);
   if (e->d_h3) cudaFree(e->d_h3);
   if (e->d_tc_err) cudaFree(e->d_tc_err);
+  if (e->d_wsplit) cudaFree(e->d_wsplit);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
@@ -1620,6 +1625,7 @@ static ctd_status ctd_pred_buffers(ctd_engine* e) {
   CTD_CUDA(e, cudaMemsetAsync(e->d_pending, 0, (size_t)e->capacity, e->stream));
   CTD_CUDA(e, cudaFuncSetAttribute(ctd_k_value_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CTD_MLP_SMEM));
   CTD_CUDA(e, cudaFuncSetAttribute(ctd_k_linear_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CTD_TC_SMEM));
+  CTD_CUDA(e, cudaFuncSetAttribute(ctd_k_linear_tc_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CTD_TC_SMEM));
   CTD_CUDA(e, cudaMalloc((void**)&e->d_h1, (size_t)e->capacity * 512 * sizeof(float)));
   CTD_CUDA(e, cudaMalloc((void**)&e->d_h2, (size_t)e->capacity * 256 * sizeof(float)));
   CTD_CUDA(e, cudaMalloc((void**)&e->d_h3, (size_t)e->capacity * 128 * sizeof(float)));
@@ -1643,6 +1649,15 @@ static ctd_status ctd_value_forward(ctd_engine* e, uint32_t n, const uint8_t* pe
   }
   float *h1 = e->d_h1 + (size_t)row0 * 512, *h2 = e->d_h2 + (size_t)row0 * 256, *h3 = e->d_h3 + (size_t)row0 * 128;
   const int M = (int)n, gm = (M + CTD_TC_BM - 1) / CTD_TC_BM;
+  if (e->tmap_ok) {   // weight operand by TMA from the pre-split terms
+    ctd_k_linear_tc_tma<<<dim3(gm, 512 / CTD_TC_BN), 128, CTD_TC_SMEM, st>>>(feat, CTD_FEATURES_PAD, e->tmap[0], e->model.b1, h1, 512, M, CTD_FEATURES_PAD, 1, e->d_tc_err);
+    ctd_k_linear_tc_tma<<<dim3(gm, 256 / CTD_TC_BN), 128, CTD_TC_SMEM, st>>>(h1, 512, e->tmap[1], e->model.b2, h2, 256, M, 512, 1, e->d_tc_err);
+    ctd_k_linear_tc_tma<<<dim3(gm, 128 / CTD_TC_BN), 128, CTD_TC_SMEM, st>>>(h2, 256, e->tmap[2], e->model.b3, h3, 128, M, 256, 1, e->d_tc_err);
+    ctd_k_value_head<<<(n + 127) / 128, 128, 0, st>>>(h3, e->model.w4t, e->model.b4, pending, n, pred, weight);
+    e->launches += 4;
+    CTD_CUDA(e, cudaGetLastError());
+    return CTD_OK;
+  }
   ctd_k_linear_tc<<<dim3(gm, 512 / CTD_TC_BN), 128, CTD_TC_SMEM, st>>>(feat, CTD_FEATURES_PAD, e->tc_w1, CTD_FEATURES_PAD, e->model.b1, h1, 512,
                                                                        M, CTD_FEATURES_PAD, 1, e->d_tc_err);
   ctd_k_linear_tc<<<dim3(gm, 256 / CTD_TC_BN), 128, CTD_TC_SMEM, st>>>(h1, 512, e->tc_w2, 512, e->model.b2, h2, 256, M, 512, 1, e->d_tc_err);
@@ -1651,6 +1666,29 @@ static ctd_status ctd_value_forward(ctd_engine* e, uint32_t n, const uint8_t* pe
   e->launches += 4;
   CTD_CUDA(e, cudaGetLastError());
   return CTD_OK;
+}
+
+// 3-D tensor map (K, N, term) over a [3][N][K] fp32 tensor, box = 16 bytes of K x 128 rows x one term, no swizzle.  The encoder
+// lives in the driver (cuTensorMapEncodeTiled): fetched through the runtime, so the library does not link libcuda.
+typedef CUresult (*ctd_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static bool ctd_make_weight_map(CUtensorMap* map, float* base, int N, int K) {
+  static ctd_encode_tiled_fn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+      (void)cudaGetLastError();
+      return false;
+    }
+    encode = (ctd_encode_tiled_fn)fn;
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, 3};
+  const cuuint64_t strides[2] = {(cuuint64_t)K * 4, (cuuint64_t)N * K * 4};
+  const cuuint32_t box[3] = {4, 128, 1}, estr[3] = {1, 1, 1};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 ctd_status ctd_set_value_backend(ctd_engine* e, int backend) {
@@ -1690,6 +1728,19 @@ ctd_status ctd_set_value_model(ctd_engine* e, const float* w1t, const float* b1,
     delete[] h;
     if (c != cudaSuccess) return ctd_fail(e, c, "upload tc weights");
     e->tc_w1 = e->d_model_tc; e->tc_w2 = e->d_model_tc + t1; e->tc_w3 = e->d_model_tc + t1 + t2;
+    // split the static weights into their TF32 terms once and describe them to the TMA engine
+    if (!e->d_wsplit) CTD_CUDA(e, cudaMalloc((void**)&e->d_wsplit, 3 * (t1 + t2 + t3) * sizeof(float)));
+    float* sp[3] = {e->d_wsplit, e->d_wsplit + 3 * t1, e->d_wsplit + 3 * (t1 + t2)};
+    const size_t cnt[3] = {t1, t2, t3};
+    const float* src[3] = {e->tc_w1, e->tc_w2, e->tc_w3};
+    const int Ns[3] = {512, 256, 128}, Ks[3] = {CTD_FEATURES_PAD, 512, 256};
+    e->tmap_ok = getenv("CTD_TC_NO_TMA") == nullptr;
+    for (int l = 0; l < 3; ++l) {
+      ctd_k_split3<<<(unsigned)((cnt[l] + 255) / 256), 256, 0, e->stream>>>(src[l], sp[l], cnt[l]);
+      e->launches++;
+      e->tmap_ok = e->tmap_ok && ctd_make_weight_map(&e->tmap[l], sp[l], Ns[l], Ks[l]);
+    }
+    CTD_CUDA(e, cudaGetLastError());
   }
   CTD_CUDA(e, cudaStreamSynchronize(e->stream));
   return CTD_OK;
@@ -1846,6 +1897,25 @@ ctd_status ctd_train_get_state(ctd_engine* e, float* const* tensors16) {
       CTD_CUDA(e, cudaMemcpy2DAsync(tensors16[0], 418 * sizeof(float), ctd_tr_slot(t, 0), CTD_TR_IN * sizeof(float), 418 * sizeof(float), 512, cudaMemcpyDeviceToHost, e->stream));
     else
       CTD_CUDA(e, cudaMemcpyAsync(tensors16[i], ctd_tr_slot(t, i), ctd_tr_count[i] * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  }
+  CTD_CUDA(e, cudaStreamSynchronize(e->stream));
+  return CTD_OK;
+}
+
+// the gradients of the last optimiser step in the same 16-tensor layout (running statistics have none: zeros) -- test hook
+ctd_status ctd_train_get_grads(ctd_engine* e, float* const* tensors16) {
+  if (!e || !e->trainer || !tensors16) return CTD_EARG;
+  CTD_CUDA(e, cudaSetDevice(e->device));
+  CtdTrainer* t = e->trainer;
+  for (int i = 0; i < 16; ++i) {
+    if (!tensors16[i]) return CTD_EARG;
+    const bool stat = i == 4 || i == 5 || i == 10 || i == 11;
+    if (stat) { memset(tensors16[i], 0, ctd_tr_count[i] * sizeof(float)); continue; }
+    const float* src = t->G + (ctd_tr_slot(t, i) - t->P);
+    if (i == 0)
+      CTD_CUDA(e, cudaMemcpy2DAsync(tensors16[0], 418 * sizeof(float), src, CTD_TR_IN * sizeof(float), 418 * sizeof(float), 512, cudaMemcpyDeviceToHost, e->stream));
+    else
+      CTD_CUDA(e, cudaMemcpyAsync(tensors16[i], src, ctd_tr_count[i] * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
   }
   CTD_CUDA(e, cudaStreamSynchronize(e->stream));
   return CTD_OK;

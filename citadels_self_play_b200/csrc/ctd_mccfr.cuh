@@ -142,6 +142,7 @@ struct CtdTree {
   ctd_state* stage; // 16-byte aligned staging record (shared memory on the device)
   const struct CtdValueNet* vnet;  // deep MCCFR, fused mode: the warp evaluates its own leaves (null: the walk hands leaves to the caller)
   float* act;       // fused mode: CTD_ACT_FLOATS floats of shared memory for the features and the activations
+  bool walk_settled; // the last ctd_new_node left the game at a real choice or at its end (not cut by the forced-move limit)
 };
 
 // address spaces of a tree's parts on the device: working set in shared memory, the tree block in HBM
@@ -443,20 +444,21 @@ CTD_HD CTD_NODE_MOVE_ATTR inline void ctd_node_load(CtdTree& T, const CtdNode& n
 }
 
 // CFRNode.skip_false_choice (:37-49) on the working game
-CTD_HD CTD_NI inline void ctd_skip_false_choice(CtdTree& T) {
+CTD_HD CTD_NI inline bool ctd_skip_false_choice(CtdTree& T) {   // false: stopped by the 100-move limit with a forced move pending
   CTD_TREE_SPACES(T);
   CtdWork& w = *T.w;
   CtdKnowSet ks{T.kn, 1};
   int i = 0;
   for (;;) {
-    if (w.gflags & 2) return;
+    if (w.gflags & 2) return true;
     CtdEmit e{nullptr, 0, 0, 0, 0};   // count, and keep the first option
     ctd_enumerate(w, e, T.kn);
-    if (w.err) return;
-    if (e.n != 1) return;
+    if (w.err) return true;
+    if (e.n != 1) return true;
     ++i;
     bool won = ctd_apply(w, e.got, ks);
-    if (won || w.err || i > 100) return;
+    if (won || w.err) return true;
+    if (i > 100) return false;
   }
 }
 
@@ -478,7 +480,7 @@ CTD_HD CTD_NI inline int ctd_new_node(CtdTree& T, int parent, int depth) {
       h.chunk[c] = off;
     }
   }
-  ctd_skip_false_choice(T);
+  T.walk_settled = ctd_skip_false_choice(T);
   if ((T.w->err | T.kn->err) & CTD_ERR_OVERFLOW) h.status |= CTD_TREE_EENGINE;
   if ((T.w->err | T.kn->err) & ~CTD_ERR_OVERFLOW) h.status |= CTD_TREE_REF_RAISE;
   h.n_nodes = idx + 1;
@@ -641,12 +643,33 @@ CTD_HD CTD_NI inline void ctd_expand(CtdTree& T, int ni) {
       CTD_LOOP for (uint32_t i = 0; i < K; ++i) kids[i] = CtdChild{big[i], 0, 0};
       CTD_LOOP for (uint32_t i = 0; i < K; ++i) big[i] = 0;   // 0.0
     }
+    // Every discard_and_draw option of the Magician has the same effect (carry_out_magicking ignores the option's cards,
+    // game/option_functions.py:295-300) and a classic Magician's turn lists ~1600 of them.  When a child was built without
+    // determinisation and without a single chance draw, building the next one from the same parent is the same computation
+    // bit for bit: the working set already holds its result, only the node has to be stored.
+    const bool resampled = n.parent < 0 || n.player != ctd_node(T, n.parent).player;
+    bool prev_same_effect = false;
     CTD_LOOP for (uint32_t i = 0; i < K; ++i) {
-      ctd_node_load(T, n);
-      ctd_maybe_sample(T, n);
-      uint64_t d = ctd_carried_form(w, kids[i].desc);
-      ctd_apply(w, d, ks);
-      int ci = ctd_new_node(T, ni, n.depth + 1);
+      const uint64_t d0 = kids[i].desc;
+      uint64_t d;
+      if (prev_same_effect && CTD_OPT_KIND(d0) == CTD_K_DISCARD_AND_DRAW) {
+        d = d0;
+      } else {
+        ctd_node_load(T, n);
+        ctd_maybe_sample(T, n);
+        d = ctd_carried_form(w, d0);
+        const uint32_t draws0 = w.draws;
+        ctd_apply(w, d, ks);
+        prev_same_effect = false;
+        int ci = ctd_new_node(T, ni, n.depth + 1);
+        if (ci < 0) return;
+        kids[i] = CtdChild{d, (uint32_t)ci, 0};
+        ++n.n_children;
+        prev_same_effect = !resampled && CTD_OPT_KIND(d0) == CTD_K_DISCARD_AND_DRAW && w.draws == draws0 && !w.err && !T.kn->err &&
+                           w.state != 8 && w.state != 9 && T.walk_settled;
+        continue;
+      }
+      int ci = ctd_new_node(T, ni, n.depth + 1);   // re-checks the forced moves (none: the state stands where the twin's walk stopped)
       if (ci < 0) return;
       kids[i] = CtdChild{d, (uint32_t)ci, 0};
       ++n.n_children;

@@ -28,6 +28,7 @@
 // Weights total 1.5 MB and stay L2-resident; activations between layers round-trip through L2 (M x 512 floats).
 #pragma once
 #include <stdint.h>
+#include <cuda.h>   // CUtensorMap (the descriptor type only; the encoder is fetched from the driver at run time)
 
 #define CTD_TC_BM 128
 #define CTD_TC_BN 128
@@ -241,6 +242,142 @@ __global__ void __launch_bounds__(128) ctd_k_linear_tc(const float* __restrict__
         o.y = __uint_as_float(v[j + 1]) + bias[n0 + c0 + j + 1];
         o.z = __uint_as_float(v[j + 2]) + bias[n0 + c0 + j + 2];
         o.w = __uint_as_float(v[j + 3]) + bias[n0 + c0 + j + 3];
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        *reinterpret_cast<float4*>(y + j) = o;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)(128 * CTD_TC_ACCS)));
+}
+
+// ---- the same product with the WEIGHT operand brought in by the TMA engine -------------------------------------------------
+// The weights are static: ctd_set_value_model splits them into their three TF32 terms ONCE (ctd_k_split3, the same cvt.rna the
+// kernel above applies to every operand on every launch) and keeps them as a [3][N][K] fp32 tensor with a 3-D tensor map
+// (K, N, term).  A stage's B operand is then 24 bulk tensor copies of 128 rows x 16 bytes (one per term and 16-byte K chunk:
+// cp.async.bulk.tensor.3d, SASS UTMALDG) issued by one thread and landing on the stage's `full` mbarrier (expect_tx = 48 KB),
+// while all four warps stage the activation operand as before.  A box of 128 rows x 16 bytes lands as sixteen stacked 8-row core
+// matrices, so the B descriptors use SBO = 128 B (8-row groups) and LBO = 2048 B (K-adjacent chunks); A keeps 1024 / 128.
+__global__ void ctd_k_split3(const float* __restrict__ w, float* __restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a, b, c;
+  ctd_tc_split3(w[i], a, b, c);
+  out[i] = a; out[n + i] = b; out[2 * n + i] = c;
+}
+__device__ __forceinline__ void ctd_tma_load_3d(uint32_t smem_dst, const CUtensorMap* map, uint32_t mbar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_dst), "l"((uint64_t)map), "r"(mbar), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__global__ void __launch_bounds__(128) ctd_k_linear_tc_tma(const float* __restrict__ X, int ldx, const __grid_constant__ CUtensorMap wmap,
+                                                           const float* __restrict__ bias, float* __restrict__ Y, int ldy, int M, int K,
+                                                           int relu, int* err) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  __shared__ uint64_t bars[2];    // stage free again: the MMAs that read it have completed (tcgen05.commit)
+  __shared__ uint64_t full[2];    // stage's weight tiles have landed (TMA complete_tx)
+  __shared__ uint32_t tmem_base_slot;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int m0 = blockIdx.x * CTD_TC_BM, n0 = blockIdx.y * CTD_TC_BN;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ctd_smem_u32(&tmem_base_slot)), "r"((uint32_t)(128 * CTD_TC_ACCS)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    ctd_mbar_init(&bars[0], 1); ctd_mbar_init(&bars[1], 1);
+    ctd_mbar_init(&full[0], 1); ctd_mbar_init(&full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_base_slot;
+  const int stages = K / CTD_TC_BK;
+  bool ok = true;
+  for (int s = 0; s < stages; ++s) {
+    const int buf = s & 1;
+    uint8_t* st = smem + buf * CTD_TC_STAGE_BYTES;
+    if (s >= 2) ok = ctd_mbar_wait(&bars[buf], (uint32_t)(((s >> 1) - 1) & 1), err) && ok;  // MMAs of slice s-2 are done
+    const int k0 = s * CTD_TC_BK;
+    if (tid == 0) {   // the weight operand: 3 terms x 8 chunks of 128 rows x 16 bytes
+      const uint32_t fb = ctd_smem_u32(&full[buf]);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"((uint32_t)(CTD_TC_TERMS * CTD_TC_TILE_BYTES)) : "memory");
+      const uint32_t b0 = ctd_smem_u32(st) + CTD_TC_TERMS * CTD_TC_TILE_BYTES;
+#pragma unroll 1
+      for (int t = 0; t < CTD_TC_TERMS; ++t)
+#pragma unroll 1
+        for (int c = 0; c < CTD_TC_BK / 4; ++c)
+          ctd_tma_load_3d(b0 + t * CTD_TC_TILE_BYTES + c * 2048, &wmap, fb, k0 + 4 * c, n0, t);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {   // the activation operand: load, split, store in the UMMA layout
+      const int idx = tid + 128 * i, row = idx >> 3, chunk = idx & 7;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m0 + row < M) a = *reinterpret_cast<const float4*>(X + (size_t)(m0 + row) * ldx + k0 + 4 * chunk);
+      ctd_tc_stage_chunk(st, row, chunk, a);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      ok = ctd_mbar_wait(&full[buf], (uint32_t)((s >> 1) & 1), err) && ok;   // the weight tiles are in
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a0 = ctd_smem_u32(st), b0 = a0 + CTD_TC_TERMS * CTD_TC_TILE_BYTES;
+#pragma unroll
+      for (int kk = 0; kk < CTD_TC_BK / 8; ++kk) {
+        const uint32_t tmem_acc = tmem_d + (uint32_t)((kk % CTD_TC_ACCS) * 128);
+        uint32_t acc = CTD_TC_ACCS == 1 ? (uint32_t)((s | kk) != 0) : (uint32_t)(s != 0 || kk >= CTD_TC_ACCS);
+#pragma unroll
+        for (int sum = CTD_TC_TERMS - 1; sum >= 0; --sum)
+#pragma unroll
+          for (int i = 0; i <= sum; ++i) {
+            const int j = sum - i;
+            ctd_umma_tf32(tmem_acc, ctd_umma_desc(a0 + i * CTD_TC_TILE_BYTES + (uint32_t)kk * 256, 128, 1024),
+                          ctd_umma_desc(b0 + j * CTD_TC_TILE_BYTES + (uint32_t)kk * 4096, 2048, 128), acc);
+            acc = 1;
+          }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(ctd_smem_u32(&bars[buf])) : "memory");
+    }
+  }
+  {
+    const int last = stages - 1;
+    ok = ctd_mbar_wait(&bars[last & 1], (uint32_t)((last >> 1) & 1), err) && ok;
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const int row = m0 + tid;
+#pragma unroll 1
+  for (int c0 = 0; c0 < CTD_TC_BN; c0 += 32) {
+    uint32_t v[32];
+    float sum[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) sum[j] = 0.f;
+#pragma unroll 1
+    for (int ai = 0; ai < CTD_TC_ACCS; ++ai) {
+      const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ai * 128 + c0);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+            "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+            "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+            "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(v[j]);
+    }
+    if (ok && row < M) {
+      float* y = Y + (size_t)row * ldy + n0 + c0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 o;
+        o.x = sum[j + 0] + bias[n0 + c0 + j + 0];
+        o.y = sum[j + 1] + bias[n0 + c0 + j + 1];
+        o.z = sum[j + 2] + bias[n0 + c0 + j + 2];
+        o.w = sum[j + 3] + bias[n0 + c0 + j + 3];
         if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
         *reinterpret_cast<float4*>(y + j) = o;
       }

@@ -92,6 +92,14 @@ class Trainer:
         self.e._check(self.lib.ctd_train_get_state(self.h, self._ptrs(arrs)), "ctd_train_get_state")
         return dict(zip(STATE_KEYS, arrs))
 
+    def get_grads(self):
+        """Test hook: the gradients of the last optimiser step, keyed like the state_dict."""
+        shapes = [(512, 418), (512,), (512,), (512,), (512,), (512,), (256, 512), (256,), (256,), (256,), (256,), (256,), (128, 256), (128,),
+                  (6, 128), (6,)]
+        arrs = [np.zeros(s, dtype=np.float32) for s in shapes]
+        self.e._check(self.lib.ctd_train_get_grads(self.h, self._ptrs(arrs)), "ctd_train_get_grads")
+        return dict(zip(STATE_KEYS, arrs))
+
     def epoch(self, seed, lr, perm):
         tl, el = ctypes.c_double(), ctypes.c_double()
         p = None if perm is None else np.ascontiguousarray(perm, dtype=np.uint32)

@@ -337,6 +337,8 @@ ctd_status ctd_train_begin(ctd_engine* e, uint32_t n_train, const float* feature
  * fc3.bias, fc4.weight [6][128], fc4.bias.  set_state also resets the optimiser (Adam moments, step count). */
 ctd_status ctd_train_set_state(ctd_engine* e, const float* const* tensors16);
 ctd_status ctd_train_get_state(ctd_engine* e, float* const* tensors16);
+/* (test hook) the gradients of the last optimiser step, same layout; the running statistics have none (zeros) */
+ctd_status ctd_train_get_grads(ctd_engine* e, float* const* tensors16);
 /* one epoch (train.py:36-69): every batch of the training set in `perm` order (n_train indices; NULL = as stored) with
  * learning rate lr, then the evaluation pass.  Dropout masks are Philox(seed, optimiser step, layer, element). */
 ctd_status ctd_train_epoch(ctd_engine* e, uint64_t seed, float lr, const uint32_t* perm, double* train_loss, double* eval_loss);

@@ -9,7 +9,8 @@
    batch 2048, with two call sites routed the way random.shuffle is routed elsewhere in this harness: its DataLoader yields the
    batches in the order citadels_self_play_b200.train.epoch_permutation defines, and torch.nn.functional.dropout keeps the
    elements citadels_self_play_b200.train.dropout_mask defines.  Initial weights: torch.manual_seed(1234) default init.
-Recorded: per-epoch train / eval losses (captured from the arguments of the reference's plot_metrics), the best evaluation loss it
+Recorded: the loss and the gradients of the first optimiser step (norms, row sums, 512 probe entries of the big matrices; small
+tensors in full); per-epoch train / eval losses (captured from the arguments of the reference's plot_metrics), the best evaluation loss it
 returns, and of its best_model.pt the small tensors in full and, for the three big matrices, norms, row sums and 256 probe entries."""
 import ctypes
 import os
@@ -95,6 +96,25 @@ def run_reference(xtr, vtr, xva, vva):
     def capture(train_losses, eval_losses, learning_rates, epochs, folder):
         state["curves"] = (list(train_losses), list(eval_losses), list(learning_rates))
 
+    # the gradients and the loss of the very first optimiser step (equal weights on both sides: the cleanest comparison there is)
+    first = {}
+    _step = torch.optim.Adam.step
+
+    def step(self, *a, **kw):
+        if not first:
+            names = ["fc1.weight", "fc1.bias", "bn1.weight", "bn1.bias", "fc2.weight", "fc2.bias", "bn2.weight", "bn2.bias", "fc3.weight",
+                     "fc3.bias", "fc4.weight", "fc4.bias"]
+            params = [p for g in self.param_groups for p in g["params"]]
+            first.update({n: p.grad.detach().clone().numpy() for n, p in zip(names, params)})
+        return _step(self, *a, **kw)
+    torch.optim.Adam.step = step
+    _kl = RT.nn.KLDivLoss.forward
+
+    def kl(self, inp, tgt):
+        out = _kl(self, inp, tgt)
+        state.setdefault("first_loss", float(out))
+        return out
+    RT.nn.KLDivLoss.forward = kl
     RT.DataLoader = Loader
     RT.plot_metrics = capture
     torch.nn.functional.dropout = dropout
@@ -105,7 +125,9 @@ def run_reference(xtr, vtr, xva, vva):
         best = RT.train_node_value_only(train, val, epochs=EPOCHS, lr=LR, hidden_size=512, gamma=GAMMA, batch_size=BATCH, device="cpu",
                                         parent_folder=tmp)
         sd = torch.load(os.path.join(tmp, "best_model.pt"), map_location="cpu")
-    return best, state["curves"], {k: v.numpy() for k, v in sd.items()}
+    torch.optim.Adam.step = _step
+    RT.nn.KLDivLoss.forward = _kl
+    return best, state["curves"], {k: v.numpy() for k, v in sd.items()}, first, state["first_loss"]
 
 
 def main():
@@ -114,11 +136,21 @@ def main():
     xtr, vtr, gid = make_targets(5000, 700000)
     xva, vva, _ = make_targets(1000, gid)
     assert np.array_equal(xtr, np.round(xtr)) and np.abs(xtr).max() < 32768
-    best, (tl, el, lrs), sd = run_reference(xtr, vtr, xva, vva)
+    best, (tl, el, lrs), sd, grads, first_loss = run_reference(xtr, vtr, xva, vva)
     rng = np.random.RandomState(7)
     out = dict(train_x=xtr.astype(np.int16), train_v=vtr, val_x=xva.astype(np.int16), val_v=vva, seed=np.uint64(TRAIN_SEED),
                epochs=np.int32(EPOCHS), lr=np.float64(LR), gamma=np.float64(GAMMA), batch=np.int32(BATCH), init_seed=np.int32(1234),
                best_eval=np.float64(best), train_losses=np.asarray(tl), eval_losses=np.asarray(el), lrs=np.asarray(lrs))
+    out["first_loss"] = np.float64(first_loss)
+    for k, v in grads.items():          # gradients of the first step: norms, probes, small tensors in full
+        out["g_" + k + "_norm"] = np.float64(np.sqrt((v.astype(np.float64) ** 2).sum()))
+        if v.size > 1024:
+            probe = rng.randint(0, v.size, size=512)
+            out["g_" + k + "_probe_idx"] = probe
+            out["g_" + k + "_probe"] = v.reshape(-1)[probe]
+            out["g_" + k + "_rowsum"] = v.sum(1)
+        else:
+            out["g_" + k] = v
     for k, v in sd.items():
         if v.ndim == 2 and v.size > 1024:
             probe = rng.randint(0, v.size, size=256)
