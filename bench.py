@@ -305,8 +305,9 @@ def bench_mccfr(args, rank, world, local, torch):
     split = [a + b for a, b in zip(split, status_split(o5["results"]))]
     gen_it, gen_ms, gen_targets = int(o5["results"]["iterations"].sum()), o5["kernel_ms"], len(tg["meta"])
     eng.close()
-    # -- the classic eight (the characters north_star lists): pure MCCFR on R/4 roots
-    Rc = max(64, R // 4)
+    # -- the classic eight (the characters north_star lists): pure MCCFR on as many roots (a Magician's turn expands ~1600 children
+    # at once: a few such trees are the tail of a small batch)
+    Rc = R
     eng = Engine(capacity=Rc, device=local)
     eng.make_roots(Rc, seed=SEED, first_gid=sharding.first_gid(2, rank, world, Rc), ruleset=1, back_lo=0, back_hi=20)
     eng.mccfr(Rc, iterations=IT, seed=SEED, ruleset=1)
@@ -526,7 +527,7 @@ def main():
                 "datagen_2000it": {"roots_per_gpu": R5, "roots": "create_a_random_game(100)", "it_per_s": mi[2] / (mf[2] / 1e3),
                                    "it_per_s_wall": mi[2] / (mf[7] / 1e3), "targets": mi[3], "usefulness_threshold": 200,
                                    "targets_export_ms": mf[3]},
-                "classic": {"roots_per_gpu": R5, "pure_it_per_s": mi[5] / (mf[8] / 1e3)}}
+                "classic": {"roots_per_gpu": R, "pure_it_per_s": mi[5] / (mf[8] / 1e3)}}
             if not args.no_cpu_baseline:
                 cores = os.cpu_count() or 1
                 ci, cw_, kind = cpu_mccfr(6, cores)
