@@ -315,8 +315,18 @@ def bench_mccfr(args, rank, world, local, torch):
     cl_it, cl_ms = int(oc["results"]["iterations"].sum()), oc["kernel_ms"]
     split = [a + b for a, b in zip(split, status_split(oc["results"]))]
     eng.close()
-    ints = [pure_it, deep_it, gen_it, gen_targets, e2e_it, cl_it] + split + [tc_it]
-    floats = [pure_ms, deep_ms, gen_ms, t5 * 1e3, pure_wall * 1e3, deep_wall * 1e3, e2e_wall * 1e3, gen_wall * 1e3, cl_ms, tc_ms]
+    # -- four times the roots in one call (the shared tree arena holds them: ~1 MB per 200-iteration tree): what the kernel does
+    # when every warp slot stays busy to the end
+    Rb = 4 * R
+    eng = Engine(capacity=Rb, device=local)
+    eng.make_roots(Rb, seed=SEED, first_gid=sharding.first_gid(3, rank, world, Rb), back_lo=0, back_hi=20)
+    eng.mccfr(Rb, iterations=IT, seed=SEED)
+    ob = eng.mccfr(Rb, iterations=IT, seed=SEED)
+    big_it, big_ms = int(ob["results"]["iterations"].sum()), ob["kernel_ms"]
+    split = [a + b for a, b in zip(split, status_split(ob["results"]))]
+    eng.close()
+    ints = [pure_it, deep_it, gen_it, gen_targets, e2e_it, cl_it] + split + [tc_it, big_it]
+    floats = [pure_ms, deep_ms, gen_ms, t5 * 1e3, pure_wall * 1e3, deep_wall * 1e3, e2e_wall * 1e3, gen_wall * 1e3, cl_ms, tc_ms, big_ms]
     return ints, floats, out
 
 
@@ -512,6 +522,7 @@ def main():
                 "unit": "MCCFR iterations/s (one iteration = one node-step, algorithms/deep_mccfr.py:194-204)",
                 "roots_per_gpu": R, "iterations_per_root": 200, "root_step_back": "0..20",
                 "pure_it_per_s": mi[0] / (mf[0] / 1e3), "deep_it_per_s": mi[1] / (mf[1] / 1e3),
+                "pure_it_per_s_4x_roots": mi[11] / (mf[10] / 1e3), "roots_per_gpu_4x": 4 * R,
                 "pure_it_per_s_wall": mi[0] / (mf[4] / 1e3), "deep_it_per_s_wall": mi[1] / (mf[5] / 1e3),
                 "deep_vs_pure": (mi[1] / mf[1]) / (mi[0] / mf[0]), "deep_waves": ex["deep_waves"],
                 "deep_mode": "fused: one launch, every warp evaluates the leaves of its own tree (fp32)",

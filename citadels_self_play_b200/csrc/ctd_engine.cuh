@@ -1126,6 +1126,7 @@ CTD_HD CTD_NI inline void ctd_enumerate(CtdWork& w, E& e, const CtdKnow* kn = nu
       case 3:  // blackmail_response_options (:35-38)
         if (role == CTD_ROLE_BEWITCHED) { w.err |= CTD_ERR_REF_RAISE; return; }
         if (w.rprops[role] & CTD_RP_BLACKMAIL) {
+          CTD_NOT_PRESET(); CTD_NOT_CLASSIC();
           e.one(ctd_opt(CTD_K_BLACKMAIL_RESPONSE, p) | ctd_f_named(CTD_N_PAY));
           e.one(ctd_opt(CTD_K_BLACKMAIL_RESPONSE, p) | ctd_f_named(CTD_N_NOT_PAY));
         } else {
@@ -1136,10 +1137,12 @@ CTD_HD CTD_NI inline void ctd_enumerate(CtdWork& w, E& e, const CtdKnow* kn = nu
         e.one(ctd_opt(w.gold[p] > 0 ? CTD_K_GRAVEYARD : CTD_K_EMPTY, p));
         return;
       case 4:  // reveal_blackmail_as_blackmailer_options (:40-41)
+        CTD_NOT_PRESET(); CTD_NOT_CLASSIC();
         e.one(ctd_opt(CTD_K_REVEAL_BLACKMAIL, p) | ctd_f_target(w.next_player) | ctd_f_named(CTD_N_REVEAL));
         e.one(ctd_opt(CTD_K_REVEAL_BLACKMAIL, p) | ctd_f_target(w.next_player) | ctd_f_named(CTD_N_NOT_REVEAL));
         return;
       case 7:  // reveal_warrant_as_magistrate_options (:43-44)
+        CTD_NOT_PRESET(); CTD_NOT_CLASSIC();
         e.one(ctd_opt(CTD_K_REVEAL_WARRANT, p) | ctd_f_target(w.next_player) | ctd_f_named(CTD_N_REVEAL));
         e.one(ctd_opt(CTD_K_REVEAL_WARRANT, p) | ctd_f_target(w.next_player) | ctd_f_named(CTD_N_NOT_REVEAL));
         return;
@@ -1155,8 +1158,8 @@ CTD_HD CTD_NI inline void ctd_enumerate(CtdWork& w, E& e, const CtdKnow* kn = nu
         ctd_main_round_options(w, p, nm, e);
         return;
       }
-      if (st == 8) { ctd_seer_give_back_options(w, p, e); return; }
-      if (st == 9) { ctd_scholar_give_back_options(w, p, e); return; }
+      if (st == 8) { CTD_NOT_PRESET(); CTD_NOT_CLASSIC(); ctd_seer_give_back_options(w, p, e); return; }
+      if (st == 9) { CTD_NOT_PRESET(); CTD_NOT_CLASSIC(); ctd_scholar_give_back_options(w, p, e); return; }
       if (st == 10) {
         int q = w.wiz_target;
         if (q >= 6) { w.err |= CTD_ERR_REF_RAISE; return; }
@@ -1170,7 +1173,7 @@ CTD_HD CTD_NI inline void ctd_enumerate(CtdWork& w, E& e, const CtdKnow* kn = nu
     e.one(ctd_opt(CTD_K_FINISH, p) | ctd_f_next_witch(1) | ctd_f_crown(king));
     return;
   }
-  if (nm == CTD_EMPEROR && !(w.done & CTD_DM_CHARACTER)) { ctd_emperor_options(w, p, true, e); return; }
+  if (nm == CTD_EMPEROR && !(w.done & CTD_DM_CHARACTER)) { CTD_NOT_PRESET(); CTD_NOT_CLASSIC(); ctd_emperor_options(w, p, true, e); return; }
   e.one(ctd_opt(CTD_K_FINISH, p) | ctd_f_crown(king));
 }
 

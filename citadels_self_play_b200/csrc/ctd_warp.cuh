@@ -171,18 +171,22 @@ static __device__ CTD_CHOOSE_ATTR uint64_t ctd_warp_choose(CtdWork& w, int lane,
         }
         c_build = __popc(m0);
         if (!(done & CTD_DM_CHARACTER)) {  // 2. character
-          if (nm == CTD_SPY) c_char = 25;
-          else if (nm == CTD_ASSASSIN) c_char = 7;
-          else if (nm == CTD_THIEF) c_char = 6;
-          else if (nm == CTD_NAVIGATOR) c_char = 2;
-          else if (nm == CTD_KING || nm == CTD_BISHOP || nm == CTD_MERCHANT || nm == CTD_ARCHITECT) c_char = 1;
+          if (nm == CTD_SPY) { CTD_NOT_CLASSIC(); c_char = 25; }
+          else if (nm == CTD_ASSASSIN) { CTD_NOT_PRESET(); c_char = 7; }
+          else if (nm == CTD_THIEF) { CTD_NOT_PRESET(); c_char = 6; }
+          else if (nm == CTD_NAVIGATOR) { CTD_NOT_CLASSIC(); c_char = 2; }
+          else if (nm == CTD_KING) c_char = 1;
+          else if (nm == CTD_BISHOP || nm == CTD_MERCHANT || nm == CTD_ARCHITECT) { CTD_NOT_PRESET(); c_char = 1; }
           else if (nm == CTD_WIZARD) {
+            CTD_NOT_CLASSIC();
             m1 = __ballot_sync(CTD_ALL, lane < 6 && lane != p && w.n_hand[lane < 6 ? lane : 0] > 0);
             c_char = __popc(m1);
           } else if (nm == CTD_ABBOT) {
+            CTD_NOT_CLASSIC();
             m1 = __ballot_sync(CTD_ALL, lane < nh && ctd_csuit(hc) == CTD_SUIT_RELIGION);
             c_char = m1 ? __popc(m1) + 1 : 0;
           } else if (nm == CTD_MAGICIAN) {
+            CTD_NOT_PRESET();
             c_char = 5 + __reduce_add_sync(CTD_ALL, lane < nh ? ctd_magician_count(nh, lane + 1) : 0u);
           } else if (nm == CTD_WARLORD) {
             // lane = (seat, slot): seats 0..2 in m1, seats 3..5 in m2, ten building slots per seat (cities of >= 7 are immune)

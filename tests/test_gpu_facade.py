@@ -102,3 +102,28 @@ def test_cfrnode_through_facade_matches_oracle():
     assert chosen in [o for o, _ in node.children] or node.role_pick_node
     chosen2, root2 = F.run_mccfr(copy.deepcopy(snaps_f[k]), max_iterations=50)
     assert chosen2.name in [o.name for o in root2.game.get_options_from_state()]
+
+
+def test_sample_private_information_and_option_encoding_match_oracle():
+    """The two facade methods that only CFRNode calls in the reference: Game.sample_private_information (game/game.py:215-242,
+    device: ctd_game_sample) against the oracle's restatement on the same chance stream, and option.encode_option
+    (game/option.py:52-115) against the oracle's encoder."""
+    from oracle import mccfr_oracle as M
+    rng = random.Random(11)
+    for ruleset, gid in ((0, 301), (0, 302), (2, 303)):
+        fg, og = _pair(4321, gid, ruleset)
+        for _ in range(150):
+            ch = rng.choice(fg.get_options_from_state())
+            if ch.carry_out(fg):
+                break
+            og.apply(ch.desc)
+        else:
+            for o in fg.get_options_from_state()[:12]:
+                assert np.array_equal(o.encode_option().numpy()[0], np.asarray(M.encode_option(o.desc), dtype=np.float32))
+                assert o.encode_option().shape == (1, 131)
+            viewer = (fg.gamestate.player_id + 2) % 6
+            fg.sample_private_information(fg.players[viewer], role_sample=True)
+            og.sample_private_information(viewer, role_sample=True)
+            assert visible(fg.record()) == visible(og.pack()), (ruleset, gid)
+            assert fg._know[viewer * 592:(viewer + 1) * 592].tobytes() == og.pack_know(viewer)
+            assert len(fg.get_options_from_state()) >= 1
