@@ -23,6 +23,7 @@ SIGNATURES = {
     "ctd_create": (_i, [_i, _u32, ctypes.POINTER(c_void)]),
     "ctd_destroy": (None, [c_void]),
     "ctd_last_error": (ctypes.c_char_p, [c_void]),
+    "ctd_sizeof": (_u32, [_i]),
     "ctd_sync": (_i, [c_void]),
     "ctd_set_stream": (_i, [c_void, c_void]),
     "ctd_set_seed": (_i, [c_void, _u64]),

@@ -702,6 +702,21 @@ void ctd_destroy(ctd_engine* e) {
 }
 
 const char* ctd_last_error(const ctd_engine* e) { return e ? e->err : "null engine"; }
+// sizes of the records that cross the boundary (binding self-check): 0 ctd_state, 1 ctd_mccfr_result, 2 ctd_target_meta,
+// 3 knowledge block, 4 exported tree header, 5 exported node, 6 child entry, 7 ctd_playout_stats
+uint32_t ctd_sizeof(int what) {
+  switch (what) {
+    case 0: return (uint32_t)sizeof(ctd_state);
+    case 1: return (uint32_t)sizeof(ctd_mccfr_result);
+    case 2: return (uint32_t)sizeof(ctd_target_meta);
+    case 3: return (uint32_t)sizeof(CtdKnow);
+    case 4: return (uint32_t)sizeof(CtdTreeHdrOut);
+    case 5: return (uint32_t)sizeof(CtdNodeOut);
+    case 6: return (uint32_t)sizeof(CtdChild);
+    case 7: return (uint32_t)sizeof(ctd_playout_stats);
+    default: return 0;
+  }
+}
 uint64_t ctd_launch_count(const ctd_engine* e) { return e ? e->launches : 0; }
 
 ctd_status ctd_sync(ctd_engine* e) {

@@ -129,6 +129,9 @@ typedef struct ctd_playout_stats {
 ctd_status ctd_create(int device, uint32_t capacity, ctd_engine** out);
 void ctd_destroy(ctd_engine* e);
 const char* ctd_last_error(const ctd_engine* e);
+/* sizeof of the records that cross this boundary, for a binding to check its own layouts against: 0 ctd_state, 1 ctd_mccfr_result,
+ * 2 ctd_target_meta, 3 knowledge block, 4 exported tree header, 5 exported node, 6 exported child entry, 7 ctd_playout_stats */
+uint32_t ctd_sizeof(int what);
 ctd_status ctd_sync(ctd_engine* e);
 /* use an existing CUDA stream (cudaStream_t as void*); default is a stream the engine owns */
 ctd_status ctd_set_stream(ctd_engine* e, void* cuda_stream);

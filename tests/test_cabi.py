@@ -36,6 +36,18 @@ def test_state_layout_matches_header():
         assert (shape[0] if shape else 1) == (int(cnt) if cnt else 1), name
 
 
+def test_record_layouts_match_the_library():
+    """The numpy mirrors of every record that crosses the C ABI have the sizes the library was compiled with."""
+    import __graft_entry__
+    __graft_entry__.build()
+    from citadels_self_play_b200 import _lib, layout
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    lib.ctd_sizeof.restype = ctypes.c_uint32
+    want = [layout.STATE_DTYPE.itemsize, layout.MCCFR_RESULT_DTYPE.itemsize, layout.TARGET_META_DTYPE.itemsize, layout.KNOW_DTYPE.itemsize,
+            layout.TREE_HDR_DTYPE.itemsize, layout.NODE_DTYPE.itemsize, layout.CHILD_DTYPE.itemsize, ctypes.sizeof(_lib.PlayoutStats)]
+    assert [lib.ctd_sizeof(i) for i in range(8)] == want
+
+
 def test_engine_fails_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():
