@@ -463,7 +463,9 @@ CTD_HD CTD_NI inline bool ctd_skip_false_choice(CtdTree& T) {   // false: stoppe
 }
 
 // allocate a child node from the working game (CFRNode.__init__, :9-33); returns its index or -1
-CTD_HD CTD_NI inline int ctd_new_node(CtdTree& T, int parent, int depth) {
+// settled: the working game is known to stand at a real choice already (a twin of the node built just before), the forced-move
+// walk would change nothing and is skipped
+CTD_HD CTD_NI inline int ctd_new_node(CtdTree& T, int parent, int depth, bool settled = false) {
   CTD_TREE_SPACES(T);
   CtdTreeHdr& h = *T.hdr;
   const uint32_t idx = h.n_nodes;
@@ -480,7 +482,7 @@ CTD_HD CTD_NI inline int ctd_new_node(CtdTree& T, int parent, int depth) {
       h.chunk[c] = off;
     }
   }
-  T.walk_settled = ctd_skip_false_choice(T);
+  if (!settled) T.walk_settled = ctd_skip_false_choice(T);
   if ((T.w->err | T.kn->err) & CTD_ERR_OVERFLOW) h.status |= CTD_TREE_EENGINE;
   if ((T.w->err | T.kn->err) & ~CTD_ERR_OVERFLOW) h.status |= CTD_TREE_REF_RAISE;
   h.n_nodes = idx + 1;
@@ -669,7 +671,7 @@ CTD_HD CTD_NI inline void ctd_expand(CtdTree& T, int ni) {
                            w.state != 8 && w.state != 9 && T.walk_settled;
         continue;
       }
-      int ci = ctd_new_node(T, ni, n.depth + 1);   // re-checks the forced moves (none: the state stands where the twin's walk stopped)
+      int ci = ctd_new_node(T, ni, n.depth + 1, true);   // no forced moves: the state stands where the twin's walk stopped
       if (ci < 0) return;
       kids[i] = CtdChild{d, (uint32_t)ci, 0};
       ++n.n_children;
@@ -719,6 +721,54 @@ CTD_HD CTD_NI inline void ctd_update_strategy(CtdTree& T, int ni) {
   if (K == 0) return;  // empty arrays: numpy no-ops
   double *R = ctd_R(T, n), *S = ctd_S(T, n), *C = ctd_C(T, n);
   const double log13 = 0.26236426446749106;  // np.log(1.3)
+#if defined(__CUDA_ARCH__)
+  // Search kernels (whole warp converged on this code): the element-wise exp / divisions go one element per lane, every sum
+  // stays the sequential left-to-right sum of the scalar form -- same operations on the same operands, bit for bit.
+  if (__activemask() == 0xFFFFFFFFu) {
+    const int lane = (int)(threadIdx.x & 31);
+    if (!(n.flags & CTD_NF_ROLE_PICK)) {
+      for (int a = lane; a < K; a += 32) S[a] = ctd_dexp(-R[a] * log13);
+      __syncwarp();
+      double tot = 0.0;
+      CTD_LOOP for (int a = 0; a < K; ++a) tot += S[a];
+      __syncwarp();
+      const bool pos = tot > 0.0;
+      for (int a = lane; a < K; a += 32) {
+        const double sa = pos ? ctd_ddiv(S[a], tot) : ctd_ddiv(1.0, (double)K);
+        S[a] = sa;
+        C[a] += sa;
+      }
+      __syncwarp();
+      double cs = 0.0;
+      CTD_LOOP for (int a = 0; a < K; ++a) cs += C[a];
+      __syncwarp();
+      for (int a = lane; a < K; a += 32) C[a] = ctd_ddiv(C[a], cs);
+      __syncwarp();
+    } else {
+      for (int i = lane; i < 60; i += 32) S[i] = ctd_dexp(-R[i] * log13);
+      __syncwarp();
+      double tot = 0.0;   // lane a < 10: the sum of its column over the six players, in seat order
+      if (lane < 10) CTD_LOOP for (int p = 0; p < 6; ++p) tot += S[p * 10 + lane];
+      __syncwarp();
+      CTD_LOOP for (int base = 0; base < 64; base += 32) {
+        const int i = base + lane;
+        const double t = __shfl_sync(0xFFFFFFFFu, tot, i % 10);
+        if (i < 60) {
+          const double si = t > 1e-8 ? ctd_ddiv(S[i], t) : 1.0 / 6.0;
+          S[i] = si;
+          C[i] += si;
+        }
+      }
+      __syncwarp();
+      double cs = 0.0;
+      CTD_LOOP for (int i = 0; i < 60; ++i) cs += C[i];
+      __syncwarp();
+      for (int i = lane; i < 60; i += 32) C[i] = ctd_ddiv(C[i], cs);
+      __syncwarp();
+    }
+    return;
+  }
+#endif
   if (!(n.flags & CTD_NF_ROLE_PICK)) {
     double tot = 0.0;
     CTD_LOOP for (int a = 0; a < K; ++a) { S[a] = ctd_dexp(-R[a] * log13); tot += S[a]; }
@@ -753,6 +803,28 @@ CTD_HD CTD_NI inline int ctd_action_choice(CtdTree& T, int ni) {
     CTD_LOOP for (int a = 0; a < K; ++a) cs += C[a];
     // cdf[a] = running sum of C[a] / cs; the draw is compared with cdf[a] / cdf[K-1]
     double* cdf = K <= CTD_SMALL_OPTS ? (double*)T.stage : (K <= CTD_MCCFR_OPT_CAP ? (double*)T.opts : nullptr);
+#if defined(__CUDA_ARCH__)
+    if (cdf != nullptr && __activemask() == 0xFFFFFFFFu) {   // search kernels: divisions one per lane, sums and the draw as below
+      const int lane = (int)(threadIdx.x & 31);
+      __syncwarp();
+      for (int a = lane; a < K; a += 32) cdf[a] = ctd_ddiv(C[a], cs);
+      __syncwarp();
+      double run = 0.0;
+      CTD_LOOP for (int a = 0; a < K; ++a) { run += cdf[a]; cdf[a] = run; }
+      __syncwarp();
+      const double last = cdf[K - 1];
+      const double u = ctd_uniform(*T.w);
+      int i = K - 1;
+      CTD_LOOP for (int base = 0; base < K - 1; base += 32) {
+        const int a = base + lane;
+        const bool stop = a < K - 1 && !(ctd_ddiv(cdf[a], last) <= u);
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, stop);
+        if (m) { i = base + __ffs(m) - 1; break; }
+      }
+      __syncwarp();
+      return (int)kids[i].node;
+    }
+#endif
     if (cdf != nullptr) {
       double run = 0.0;
       CTD_LOOP for (int a = 0; a < K; ++a) { run += ctd_ddiv(C[a], cs); cdf[a] = run; }
@@ -804,6 +876,41 @@ CTD_HD CTD_NI inline void ctd_backpropagate(CtdTree& T, int ni, const double rew
     if (training || vs == 0.0 || !model) CTD_LOOP for (int i = 0; i < 6; ++i) n.V[i] += reward[i];
     vs = 0.0;
     CTD_LOOP for (int i = 0; i < 6; ++i) vs += n.V[i];
+#if defined(__CUDA_ARCH__)
+    if (__activemask() == 0xFFFFFFFFu) {   // search kernels: one seat / one child per lane; max is exact in any order
+      const int lane = (int)(threadIdx.x & 31);
+      __syncwarp();
+      if (lane < 6) n.P[lane] = ctd_ddiv(n.V[lane], vs);
+      __syncwarp();
+      ++n.visits;
+      const int K = (int)n.n_children;
+      if (K == 0) continue;
+      double* R = ctd_R(T, n);
+      const CtdChild* kids = ctd_kids(T, n);
+      if (!(n.flags & CTD_NF_ROLE_PICK)) {
+        const int pl = n.player;
+        double m = -1e300;
+        CTD_LOOP for (int base = 0; base < K; base += 32) {
+          const int a = base + lane;
+          double v = a < K ? ctd_node(T, kids[a].node).P[pl] : -1e300;
+          if (!(v > -1e300)) v = -1e300;   // `v > m ? v : m` never takes a NaN
+          CTD_LOOP for (int o = 16; o > 0; o >>= 1) {
+            const double y = __shfl_xor_sync(0xFFFFFFFFu, v, o);
+            v = y > v ? y : v;
+          }
+          m = v > m ? v : m;
+        }
+        for (int a = lane; a < K; a += 32) R[a] += m - ctd_node(T, kids[a].node).P[pl];
+      } else if (lane < 10) {
+        const double* cp = ctd_node(T, kids[lane].node).P;
+        double m = cp[0];
+        CTD_LOOP for (int p = 1; p < 6; ++p) m = cp[p] > m ? cp[p] : m;
+        CTD_LOOP for (int p = 0; p < 6; ++p) R[p * 10 + lane] += m - cp[p];
+      }
+      __syncwarp();
+      continue;
+    }
+#endif
     CTD_LOOP for (int i = 0; i < 6; ++i) n.P[i] = ctd_ddiv(n.V[i], vs);
     ++n.visits;
     const int K = (int)n.n_children;
