@@ -151,6 +151,19 @@ struct CtdTree {
   CTD_ASSUME_GLOBAL((T).hdr); CTD_ASSUME_GLOBAL((T).nodes0); CTD_ASSUME_GLOBAL((T).abase);                    \
   CTD_ASSUME_GLOBAL((T).opts)
 
+// Device code runs either on one lane (export / target walks, ctd_kernels.cu) or with the whole warp converged on the same scalar
+// code (the search kernels).  In the search units the second is a fact of the build (CTD_SEARCH_UNIT), elsewhere it is tested.
+#if defined(__CUDA_ARCH__)
+#ifdef CTD_SEARCH_UNIT
+#pragma nv_diag_suppress 128   /* the one-lane fallbacks behind `if (CTD_CONVERGED()) { ...; return; }` are unreachable here, on purpose */
+#define CTD_CONVERGED() true
+#define CTD_ACTIVE_MASK() 0xFFFFFFFFu
+#else
+#define CTD_CONVERGED() (__activemask() == 0xFFFFFFFFu)
+#define CTD_ACTIVE_MASK() __activemask()
+#endif
+#endif
+
 // 16-byte vector copy (both pointers 16-byte aligned, bytes a multiple of 16): the tree lives in HBM and its records
 // move as a handful of independent 128-bit transactions instead of hundreds of dependent byte accesses
 CTD_HD inline void ctd_copy16(void* dst, const void* src, int bytes) {
@@ -173,7 +186,7 @@ CTD_HD inline void ctd_copy16(void* dst, const void* src, int bytes) {
 template <int BYTES>
 __device__ __forceinline__ void ctd_copy_s2g(void* gdst, const void* ssrc) {
   static_assert(BYTES % 16 == 0, "vector copy");
-  const unsigned m = __activemask();
+  const unsigned m = CTD_ACTIVE_MASK();
   const int nl = __popc(m), rank = __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
   char* g = (char*)gdst;
@@ -189,7 +202,7 @@ __device__ __forceinline__ void ctd_copy_s2g(void* gdst, const void* ssrc) {
 template <int BYTES>
 __device__ __forceinline__ void ctd_copy_g2s(void* sdst, const void* gsrc) {
   static_assert(BYTES % 16 == 0, "vector copy");
-  const unsigned m = __activemask();
+  const unsigned m = CTD_ACTIVE_MASK();
   const int nl = __popc(m), rank = __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(sdst);
   const char* g = (const char*)gsrc;
@@ -240,7 +253,7 @@ CTD_HD inline CtdChild* ctd_kids(const CtdTree& T, const CtdNode& n) { return (C
 CTD_HD inline uint32_t ctd_arena_alloc(CtdTree& T, uint32_t units) {
   unsigned long long off;
 #if defined(__CUDA_ARCH__)
-  const unsigned m = __activemask();
+  const unsigned m = CTD_ACTIVE_MASK();
   const int leader = __ffs(m) - 1;
   off = 0;
   if ((int)(threadIdx.x & 31) == leader) off = atomicAdd(T.ar.used, (unsigned long long)units);
@@ -264,7 +277,7 @@ CTD_HD CTD_NI inline uint32_t ctd_tree_alloc(CtdTree& T, size_t bytes) {
     left = CTD_SLAB_UNITS;
   }
 #if defined(__CUDA_ARCH__)
-  __syncwarp(__activemask());   // every lane has read the old slab state before any lane writes the new one
+  __syncwarp(CTD_ACTIVE_MASK());   // every lane has read the old slab state before any lane writes the new one
 #endif
   h.slab_off = off + units;
   h.slab_left = left - units;
@@ -308,7 +321,7 @@ CTD_HD CTD_NI inline void ctd_sample_private(CtdWork& w, CtdKnow& k, const uint8
   int nu = 0;
   const uint8_t* occ = used_cards + 80;
 #if defined(__CUDA_ARCH__)
-  if (__activemask() == 0xFFFFFFFFu) {   // converged warp (search kernels): 32 cards at a time, ballot + prefix count compaction
+  if (CTD_CONVERGED()) {   // converged warp (search kernels): 32 cards at a time, ballot + prefix count compaction
     const int lane = threadIdx.x & 31;
     __syncwarp();
     CTD_LOOP for (int base = 0; base < 96; base += 32) {
@@ -343,7 +356,7 @@ CTD_HD CTD_NI inline void ctd_sample_private(CtdWork& w, CtdKnow& k, const uint8
   {
     const int take = need < nu ? need : nu;
 #if defined(__CUDA_ARCH__)
-    if (__activemask() == 0xFFFFFFFFu) {   // converged warp: a plain parallel copy
+    if (CTD_CONVERGED()) {   // converged warp: a plain parallel copy
       const int base = w.n_deck;
       __syncwarp();
       for (int i = threadIdx.x & 31; i < take; i += 32) w.deck[base + i] = unknown[i];
@@ -477,7 +490,7 @@ CTD_HD CTD_NI inline int ctd_new_node(CtdTree& T, int parent, int depth, bool se
       const uint32_t off = ctd_arena_alloc(T, (uint32_t)((bytes + CTD_ARENA_UNIT - 1) / CTD_ARENA_UNIT));
       if (off == 0) { h.status |= CTD_TREE_EPOOL; return -1; }
 #if defined(__CUDA_ARCH__)
-      __syncwarp(__activemask());
+      __syncwarp(CTD_ACTIVE_MASK());
 #endif
       h.chunk[c] = off;
     }
@@ -507,7 +520,7 @@ CTD_HD inline bool ctd_reserve(CtdTree& T, CtdNode& n, uint32_t kids, uint32_t d
   h.arr_used += doubles;
   double* a = (double*)(ctd_kids(T, n) + kids);
 #if defined(__CUDA_ARCH__)
-  if (__activemask() == 0xFFFFFFFFu) {   // converged warp: the lanes split the zero-fill
+  if (CTD_CONVERGED()) {   // converged warp: the lanes split the zero-fill
     for (uint32_t i = threadIdx.x & 31u; i < doubles; i += 32u) a[i] = 0.0;
     __syncwarp();
     return true;
@@ -724,48 +737,36 @@ CTD_HD CTD_NI inline void ctd_update_strategy(CtdTree& T, int ni) {
 #if defined(__CUDA_ARCH__)
   // Search kernels (whole warp converged on this code): the element-wise exp / divisions go one element per lane, every sum
   // stays the sequential left-to-right sum of the scalar form -- same operations on the same operands, bit for bit.
-  if (__activemask() == 0xFFFFFFFFu) {
+  if (CTD_CONVERGED()) {
     const int lane = (int)(threadIdx.x & 31);
-    if (!(n.flags & CTD_NF_ROLE_PICK)) {
-      for (int a = lane; a < K; a += 32) S[a] = ctd_dexp(-R[a] * log13);
-      __syncwarp();
-      double tot = 0.0;
+    const bool rp = n.flags & CTD_NF_ROLE_PICK;
+    const int E = rp ? 60 : K;   // entries of R / S / C
+    for (int i = lane; i < E; i += 32) S[i] = ctd_dexp(-R[i] * log13);
+    __syncwarp();
+    // what an entry is divided by: the sum over the children (vector nodes), over the six players of its column (role-pick nodes)
+    double tot = 0.0;
+    if (!rp) {
       CTD_LOOP for (int a = 0; a < K; ++a) tot += S[a];
-      __syncwarp();
-      const bool pos = tot > 0.0;
-      for (int a = lane; a < K; a += 32) {
-        const double sa = pos ? ctd_ddiv(S[a], tot) : ctd_ddiv(1.0, (double)K);
-        S[a] = sa;
-        C[a] += sa;
-      }
-      __syncwarp();
-      double cs = 0.0;
-      CTD_LOOP for (int a = 0; a < K; ++a) cs += C[a];
-      __syncwarp();
-      for (int a = lane; a < K; a += 32) C[a] = ctd_ddiv(C[a], cs);
-      __syncwarp();
-    } else {
-      for (int i = lane; i < 60; i += 32) S[i] = ctd_dexp(-R[i] * log13);
-      __syncwarp();
-      double tot = 0.0;   // lane a < 10: the sum of its column over the six players, in seat order
-      if (lane < 10) CTD_LOOP for (int p = 0; p < 6; ++p) tot += S[p * 10 + lane];
-      __syncwarp();
-      CTD_LOOP for (int base = 0; base < 64; base += 32) {
-        const int i = base + lane;
-        const double t = __shfl_sync(0xFFFFFFFFu, tot, i % 10);
-        if (i < 60) {
-          const double si = t > 1e-8 ? ctd_ddiv(S[i], t) : 1.0 / 6.0;
-          S[i] = si;
-          C[i] += si;
-        }
-      }
-      __syncwarp();
-      double cs = 0.0;
-      CTD_LOOP for (int i = 0; i < 60; ++i) cs += C[i];
-      __syncwarp();
-      for (int i = lane; i < 60; i += 32) C[i] = ctd_ddiv(C[i], cs);
-      __syncwarp();
+    } else if (lane < 10) {
+      CTD_LOOP for (int p = 0; p < 6; ++p) tot += S[p * 10 + lane];
     }
+    __syncwarp();
+    CTD_LOOP for (int base = 0; base < E; base += 32) {
+      const int i = base + lane;
+      const double t = rp ? __shfl_sync(0xFFFFFFFFu, tot, i % 10) : tot;
+      if (i < E) {
+        const bool pos = rp ? t > 1e-8 : t > 0.0;   // otherwise uniform: 1/6 over the players, 1/K over the children
+        const double si = ctd_ddiv(pos ? S[i] : 1.0, pos ? t : (rp ? 6.0 : (double)K));
+        S[i] = si;
+        C[i] += si;
+      }
+    }
+    __syncwarp();
+    double cs = 0.0;
+    CTD_LOOP for (int i = 0; i < E; ++i) cs += C[i];
+    __syncwarp();
+    for (int i = lane; i < E; i += 32) C[i] = ctd_ddiv(C[i], cs);
+    __syncwarp();
     return;
   }
 #endif
@@ -804,7 +805,7 @@ CTD_HD CTD_NI inline int ctd_action_choice(CtdTree& T, int ni) {
     // cdf[a] = running sum of C[a] / cs; the draw is compared with cdf[a] / cdf[K-1]
     double* cdf = K <= CTD_SMALL_OPTS ? (double*)T.stage : (K <= CTD_MCCFR_OPT_CAP ? (double*)T.opts : nullptr);
 #if defined(__CUDA_ARCH__)
-    if (cdf != nullptr && __activemask() == 0xFFFFFFFFu) {   // search kernels: divisions one per lane, sums and the draw as below
+    if (cdf != nullptr && CTD_CONVERGED()) {   // search kernels: divisions one per lane, sums and the draw as below
       const int lane = (int)(threadIdx.x & 31);
       __syncwarp();
       for (int a = lane; a < K; a += 32) cdf[a] = ctd_ddiv(C[a], cs);
@@ -877,7 +878,7 @@ CTD_HD CTD_NI inline void ctd_backpropagate(CtdTree& T, int ni, const double rew
     vs = 0.0;
     CTD_LOOP for (int i = 0; i < 6; ++i) vs += n.V[i];
 #if defined(__CUDA_ARCH__)
-    if (__activemask() == 0xFFFFFFFFu) {   // search kernels: one seat / one child per lane; max is exact in any order
+    if (CTD_CONVERGED()) {   // search kernels: one seat / one child per lane; max is exact in any order
       const int lane = (int)(threadIdx.x & 31);
       __syncwarp();
       if (lane < 6) n.P[lane] = ctd_ddiv(n.V[lane], vs);
@@ -1049,7 +1050,7 @@ CTD_HD CTD_NI inline uint64_t ctd_live_choice(CtdTree& T) {
 CTD_HD CTD_NI inline void ctd_encode_game(const CtdWork& w, const CtdKnow& k, int player, float* f) {
   CTD_ASSUME_SHARED(&w);   // (k is a global record in ctd_k_encode)
 #if defined(__CUDA_ARCH__)
-  if (__activemask() == 0xFFFFFFFFu) {   // converged warp (search kernels): the lanes split the zero-fill
+  if (CTD_CONVERGED()) {   // converged warp (search kernels): the lanes split the zero-fill
     for (int i = threadIdx.x & 31; i < CTD_FEATURES_PAD; i += 32) f[i] = 0.f;
     __syncwarp();
   } else

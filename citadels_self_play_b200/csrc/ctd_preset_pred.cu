@@ -5,6 +5,7 @@
 #include <stddef.h>
 
 #define CTD_DEVICE_ONLY 1
+#define CTD_SEARCH_UNIT 1   /* every device function of this unit runs with the whole warp converged on the same scalar code (ctd_search.cuh) */
 // measured (round 2 A/B, 4096 roots): node moves, fp64 division / exp and the byte shuffle inlined at their uses are 10 % faster
 // than one out-of-line copy of each -- calls cost the search more (callee-saved registers through local memory on 32 lanes) than
 // the extra 30 KB of image

@@ -1,4 +1,5 @@
-"""Developer tool: latency of single MCCFR trees (one root per launch) vs the batch -- is the batch bound by its slowest tree?"""
+"""Developer tool: latency of single MCCFR trees (one root per launch) vs the batch -- is the batch bound by its slowest tree?
+   python tools/tree_latency.py [roots] [sampled trees] [ruleset] [first_gid]"""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -6,11 +7,13 @@ from citadels_self_play_b200 import Engine
 
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 192
+RS = int(sys.argv[3]) if len(sys.argv) > 3 else 0          # ruleset
+G0 = int(sys.argv[4]) if len(sys.argv) > 4 else 0          # first game id
 e = Engine(capacity=R)
-e.make_roots(R, seed=0xC17ADE15, first_gid=0, back_lo=0, back_hi=20)
+e.make_roots(R, seed=0xC17ADE15, first_gid=G0, ruleset=RS, back_lo=0, back_hi=20)
 roots, knows, used, gids = e.store_roots(R)
-o = e.mccfr(R, iterations=200, seed=0xC17ADE15)
-o = e.mccfr(R, iterations=200, seed=0xC17ADE15)
+o = e.mccfr(R, iterations=200, seed=0xC17ADE15, ruleset=RS)
+o = e.mccfr(R, iterations=200, seed=0xC17ADE15, ruleset=RS)
 batch_ms = o["kernel_ms"]
 nodes = o["results"]["n_nodes"].astype(np.int64)
 order = np.argsort(-nodes)
@@ -19,8 +22,8 @@ e1 = Engine(capacity=8)
 lat = []
 for i in pick:
     e1.load_roots(roots[i:i + 1], knows[i:i + 1], used[i:i + 1], gids[i:i + 1])
-    e1.mccfr(1, iterations=200, seed=0xC17ADE15)
-    t = e1.mccfr(1, iterations=200, seed=0xC17ADE15)["kernel_ms"]
+    e1.mccfr(1, iterations=200, seed=0xC17ADE15, ruleset=RS)
+    t = e1.mccfr(1, iterations=200, seed=0xC17ADE15, ruleset=RS)["kernel_ms"]
     lat.append(t)
 lat = np.array(lat)
 print(json.dumps({"roots": R, "batch_ms": batch_ms, "sum_single_ms_sampled": float(lat.sum()),
