@@ -1042,13 +1042,16 @@ static uint32_t ctd_n0_log2(uint32_t iterations) {
   while (k < 20 && (1ull << k) < 2ull * iterations) ++k;
   return k;
 }
-// arena bytes budgeted per tree: chunk 0 plus half of it again for the trees that outgrow it, the node arrays, slab slack.
+// arena bytes budgeted per tree: chunk 0 plus one and a half times as much again for the trees that outgrow it (2000-iteration
+// trees from create_a_random_game roots: 1.9 nodes per iteration, 40 % of them take a second chunk; a budget of 1.5 chunks ran
+// the shared arena dry at the very end of such a batch and sent the slowest trees through a second search), the node arrays,
+// slab slack.
 // The classic Magician expands ~1600 children at once and the Cardinal of the random rulesets thousands, more than once per tree:
 // those rulesets get a larger share.  A budget is an average, not a limit: trees borrow from each other, and a tree that finds
 // the arena exhausted is searched again from a larger one (ctd_search below).
 static uint64_t ctd_tree_budget(uint32_t iterations, int ruleset) {
   const uint64_t n0 = 1ull << ctd_n0_log2(iterations);
-  uint64_t b = n0 * sizeof(CtdNode) * 3 / 2 + (uint64_t)iterations * 10 * 40 + 4 * CTD_SLAB_UNITS * CTD_ARENA_UNIT;
+  uint64_t b = n0 * sizeof(CtdNode) * 5 / 2 + (uint64_t)iterations * 30 * 40 + 4 * CTD_SLAB_UNITS * CTD_ARENA_UNIT;
   if (ruleset == CTD_RULESET_CLASSIC) b *= 4;
   if (ruleset == CTD_RULESET_RANDOM) b *= 8;
   return b;
@@ -1324,6 +1327,7 @@ static ctd_status ctd_search(ctd_engine* e, const CtdSearch& sp, ctd_mccfr_resul
     if (rs != CTD_OK) break;
     rs = sp.deep ? ctd_deep_pass(e, sp, e->d_list, nf, ai, nullptr) : ctd_pure_pass(e, sp, e->d_list, nf, ai);
     if (rs != CTD_OK) break;
+    if (cudaEventRecord(e->ev1, e->stream) != cudaSuccess) { rs = CTD_ECUDA; break; }   // the reported kernel time covers every pass
     CTD_CUDA(e, cudaStreamSynchronize(e->stream));   // `st` is reused as the upload source
   }
   delete[] st;
