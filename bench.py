@@ -299,6 +299,7 @@ def bench_mccfr(args, rank, world, local, torch):
     t0 = time.perf_counter()
     o5 = eng.mccfr(R5, iterations=2000, seed=SEED)
     gen_wall = time.perf_counter() - t0
+    eng.mccfr_targets(R5, iterations=2000, seed=SEED, threshold=200.0)   # warm-up: the first call loads the kernel and sizes buffers
     t5 = time.perf_counter()
     tg = eng.mccfr_targets(R5, iterations=2000, seed=SEED, threshold=200.0)
     t5 = time.perf_counter() - t5

@@ -252,6 +252,10 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_targets(CtdTargetArgs a) {
   uint32_t nrec = 0, nopt = 0, rp_draws = 0;
   // trees that stopped early (arena exhausted, engine limit, the reference raises) are not training data
   if (h.n_nodes != 0 && h.status == CTD_TREE_OK) {
+    // Where node_value counts backpropagations (cfr_train, and cfr_pred in training mode: every backprop adds a reward that sums
+    // to one to each node on its path) a child never has more than its parent, so nothing below a node under the threshold
+    // qualifies and the walk does not go there: a 2000-iteration tree has ~3800 nodes and a handful over 200 backprops.
+    const bool prune = h.training || !h.has_model;
     int cur = 0;
     for (;;) {
       const CtdNode& n = ctd_node(T, cur);
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_targets(CtdTargetArgs a) {
         nopt += K;
       }
       // pre-order successor: first child, else next sibling of the nearest ancestor that has one
-      if (K != 0) { cur = (int)ctd_kids(T, n)[0].node; continue; }
+      if (K != 0 && !(prune && vs < a.threshold)) { cur = (int)ctd_kids(T, n)[0].node; continue; }
       int c = cur;
       for (;;) {
         const int par = ctd_node(T, c).parent;

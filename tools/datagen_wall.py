@@ -17,4 +17,8 @@ for rep in range(3):
     out.append({"wall_ms": w * 1e3, "kernel_ms_first_pass": o["kernel_ms"], "launches": e.launches - l0,
                 "status2": int((o["results"]["status"] & 2 != 0).sum()), "nodes": int(o["results"]["n_nodes"].sum()),
                 "max_nodes": int(o["results"]["n_nodes"].max())})
+for rep in range(3):
+    t0 = time.perf_counter()
+    tg = e.mccfr_targets(R, iterations=IT, seed=0xC17ADE15, threshold=200.0)
+    out.append({"targets_export_ms": (time.perf_counter() - t0) * 1e3, "targets": len(tg["meta"])})
 print(json.dumps(out))
