@@ -586,6 +586,7 @@ struct ctd_engine {
   float* d_pred;
   uint8_t* d_pending;
   uint32_t* d_n_pending;
+  uint32_t* d_n_epool;   // [1] trees that found their arena exhausted in the passes since it was last cleared
   // tensor-core path of the value model: weights as [out][in], activations between layers, error flag
   float* d_model_tc;
   const float *tc_w1, *tc_w2, *tc_w3;
@@ -653,6 +654,7 @@ ctd_status ctd_create(int device, uint32_t capacity, ctd_engine** out) {
   CTD_CUDA(e, cudaMalloc((void**)&e->d_slots, (size_t)capacity * sizeof(ctd_state)));
   CTD_CUDA(e, cudaMemsetAsync(e->d_slots, 0, (size_t)capacity * sizeof(ctd_state), e->stream));
   CTD_CUDA(e, cudaMalloc((void**)&e->d_counter, sizeof(unsigned long long)));
+  CTD_CUDA(e, cudaMalloc((void**)&e->d_n_epool, sizeof(uint32_t)));
   CTD_CUDA(e, cudaMalloc((void**)&e->d_stats, sizeof(ctd_playout_stats)));
   CTD_CUDA(e, cudaEventCreate(&e->ev0));
   CTD_CUDA(e, cudaEventCreate(&e->ev1));
@@ -691,6 +693,7 @@ void ctd_destroy(ctd_engine* e) {
   if (e->d_pred) cudaFree(e->d_pred);
   if (e->d_pending) cudaFree(e->d_pending);
   if (e->d_n_pending) cudaFree(e->d_n_pending);
+  if (e->d_n_epool) cudaFree(e->d_n_epool);
   if (e->d_one) cudaFree(e->d_one);
   if (e->h_pinned) cudaFreeHost(e->h_pinned);
   if (e->d_model_tc) cudaFree(e->d_model_tc);
@@ -1141,6 +1144,7 @@ static ctd_status ctd_pure_pass(ctd_engine* e, const CtdSearch& sp, const uint32
   a.n_roots = n; a.tree_list = d_list; a.roots = e->d_slots; a.knows = e->d_knows; a.used_cards = e->d_used_cards; a.gids = e->d_gids;
   a.seed = sp.seed; a.iterations = sp.iterations; a.n0_log2 = ctd_n0_log2(sp.iterations); a.hdrs = e->d_hdrs; a.arena = ctd_arena_of(e, ai);
   a.results = e->d_results; a.counter = e->d_counter; a.opts_scratch = e->d_opts_scratch; a.resume = sp.resume ? 1 : 0;
+  a.n_epool = e->d_n_epool;
   CTD_CUDA(e, cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream));
   if (preset) CTD_CUDA(e, ctd_mccfr_preset_launch(a, grid, e->stream));
   else CTD_CUDA(e, ctd_mccfr_generic_launch(a, grid, e->stream));
@@ -1157,7 +1161,7 @@ static ctd_status ctd_deep_pass(ctd_engine* e, const CtdSearch& sp, const uint32
   CtdMccfrArgs& a = p.m;
   a.roots = e->d_slots; a.knows = e->d_knows; a.used_cards = e->d_used_cards; a.gids = e->d_gids;
   a.seed = sp.seed; a.iterations = sp.iterations; a.n0_log2 = ctd_n0_log2(sp.iterations); a.hdrs = e->d_hdrs; a.arena = ctd_arena_of(e, ai);
-  a.results = e->d_results;
+  a.results = e->d_results; a.n_epool = e->d_n_epool;
   {  // wave budget: trees that never reach the depth limit would otherwise walk all their iterations in the first wave
     const char* env = getenv("CTD_PRED_BUDGET");
     p.budget = env ? (uint32_t)strtoul(env, nullptr, 10) : 20u;   // measured best at 4096 roots x 200 iterations (8: 8.4e6, 20: 1.12e7, 64: 8.9e6, unbounded: 7.3e6 it/s)
@@ -1301,6 +1305,7 @@ static ctd_status ctd_search(ctd_engine* e, const CtdSearch& sp, ctd_mccfr_resul
   s = ctd_ensure_arena(e, 0, arena0);
   if (s != CTD_OK) return s;
   e->trees_n = sp.n_roots;
+  CTD_CUDA(e, cudaMemsetAsync(e->d_n_epool, 0, sizeof(uint32_t), e->stream));
   CTD_CUDA(e, cudaEventRecord(e->ev0, e->stream));
   s = sp.deep ? ctd_deep_pass(e, sp, nullptr, sp.n_roots, 0, waves_out) : ctd_pure_pass(e, sp, nullptr, sp.n_roots, 0);
   if (s != CTD_OK) return s;
@@ -1310,7 +1315,13 @@ static ctd_status ctd_search(ctd_engine* e, const CtdSearch& sp, ctd_mccfr_resul
   if (!st) return CTD_ENOMEM;
   ctd_status rs = CTD_OK;
   for (int ai = 1; ai < CTD_MAX_ARENAS; ++ai) {
-    cudaError_t c = cudaMemcpy2DAsync(st, sizeof(uint32_t), (const uint8_t*)e->d_hdrs + offsetof(CtdTreeHdr, status), sizeof(CtdTreeHdr),
+    uint32_t any = 0;   // one word first: the strided read-back of every header's status costs a DMA descriptor per tree
+    cudaError_t c = cudaMemcpyAsync(&any, e->d_n_epool, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream);
+    if (c == cudaSuccess) c = cudaStreamSynchronize(e->stream);
+    if (c != cudaSuccess) { rs = ctd_fail(e, c, "exhausted-tree count read-back"); break; }
+    if (any == 0) break;
+    c = cudaMemsetAsync(e->d_n_epool, 0, sizeof(uint32_t), e->stream);
+    if (c == cudaSuccess) c = cudaMemcpy2DAsync(st, sizeof(uint32_t), (const uint8_t*)e->d_hdrs + offsetof(CtdTreeHdr, status), sizeof(CtdTreeHdr),
                                       sizeof(uint32_t), sp.n_roots, cudaMemcpyDeviceToHost, e->stream);
     if (c == cudaSuccess) c = cudaStreamSynchronize(e->stream);
     if (c != cudaSuccess) { rs = ctd_fail(e, c, "tree status read-back"); break; }

@@ -27,6 +27,7 @@ struct CtdMccfrArgs {
   uint64_t* opts_scratch;  // [gridDim.x * CTD_WARPS_PER_BLOCK][CTD_MCCFR_OPT_CAP]
   uint32_t first_root;
   int resume;                  // 1: continue the trees an earlier launch grew (root-parallel rounds)
+  uint32_t* n_epool;           // [1] or null: bumped for every tree that ends with CTD_TREE_EPOOL (the host then looks for them)
 };
 
 static __device__ void ctd_write_result(CtdTree& T, ctd_mccfr_result* r) {
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) CTD_MCCFR_KER
       if (a.results) ctd_write_result(T, &a.results[t]);
       }
       }
+      if (lane == 0 && a.n_epool && (hdr->status & CTD_TREE_EPOOL)) atomicAdd(a.n_epool, 1u);
     }
     __syncwarp();
   }
@@ -183,6 +185,7 @@ __global__ void __launch_bounds__(CTD_BLOCK, CTD_MCCFR_MIN_BLOCKS) CTD_MCCFR_PRE
       if (r == CTD_PRED_WAIT && lane == 0) atomicAdd(p.n_pending, 1u);
       if (r == CTD_PRED_YIELD && lane == 0) atomicAdd(p.n_pending + 1, 1u);
       if (r == CTD_PRED_DONE && a.results) ctd_write_result(T, &a.results[t]);
+      if (r == CTD_PRED_DONE && lane == 0 && a.n_epool && (hdr->status & CTD_TREE_EPOOL)) atomicAdd(a.n_epool, 1u);   // (a finished tree is counted by every later wave too: the host only asks "any?")
     }
     __syncwarp();
   }

@@ -104,7 +104,10 @@ enum { CTD_PM_ROLE_PICK, CTD_PM_GOLD_OR_CARD, CTD_PM_SINGLE, CTD_PM_KEEP, CTD_PM
 #endif
 // `ring` (playout kernel): the warp's Philox ring, refilled at the top of the step, so the one draw of the cooperative
 // path is a broadcast read by every lane instead of lane-0 code followed by a shuffle.
-static __device__ CTD_CHOOSE_ATTR uint64_t ctd_warp_choose(CtdWork& w, int lane, uint64_t* buf, uint32_t* count_out = nullptr,
+#ifndef CTD_CHOOSE_LINKAGE
+#define CTD_CHOOSE_LINKAGE static
+#endif
+CTD_CHOOSE_LINKAGE __device__ CTD_CHOOSE_ATTR uint64_t ctd_warp_choose(CtdWork& w, int lane, uint64_t* buf, uint32_t* count_out = nullptr,
                                                  int want = -1, const uint32_t* ring = nullptr) {
   const int p = w.player, st = w.state;
   if ((w.gflags & 2) || p >= 6) return ctd_choose_scalar(w, lane, buf, count_out, want);
