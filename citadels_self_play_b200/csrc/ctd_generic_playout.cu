@@ -7,9 +7,6 @@
 #define CTD_DEVICE_ONLY 1
 #define CTD_SMALL_CAPS 1   /* real games only: small containers, small working record (ctd_engine.cuh) */
 #define CTD_PLAYOUT_KERNEL_NAME ctd_k_playout
-#ifdef CTD_LAYOUT_HOT
-#include "ctd_layout_hot.h"
-#endif
 #include "ctd_playout.cuh"
 
 cudaError_t ctd_playout_generic_launch(const CtdPlayoutArgs& a, int grid, cudaStream_t stream) {

@@ -11,8 +11,13 @@
 #define CTD_SMALL_CAPS 1   /* real games only: small containers, small working record (ctd_engine.cuh) */
 #define CTD_FIXED_PRESET 1
 #define CTD_PLAYOUT_KERNEL_NAME ctd_k_playout_preset
-#ifdef CTD_LAYOUT_HOT
-#include "ctd_layout_hot.h"
+// where ptxas puts the per-step functions (see the header): worth a few per cent on an instruction-cache-bound kernel
+#ifndef CTD_LAYOUT_HEADER
+#define CTD_LAYOUT_HEADER "ctd_layout_preset.h"
+#endif
+#ifndef CTD_NO_LAYOUT
+#define CTD_CHOOSE_LINKAGE inline   /* external name: takes part in the ordering */
+#include CTD_LAYOUT_HEADER
 #endif
 #include "ctd_playout.cuh"
 

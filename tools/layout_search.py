@@ -1,0 +1,97 @@
+"""Developer tool: search over the placement of the playout kernels' device functions.
+
+ptxas lays the device functions of a kernel out in the order of their mangled names, and the playout kernels are bound by the SM's
+instruction cache (profiles/README.md), so WHERE the per-step functions sit relative to each other is worth +-5 %.  This script
+writes renaming headers (the format of csrc/ctd_layout_preset.h: `#define ctd_x ctd_hNN_...`) for a set of orders, builds one library per order
+(only the playout units are recompiled) under citadels_self_play_b200/variants/, and prints the command that times them on the GPU box:
+
+    python tools/layout_search.py build N SEED        # N random orders (+ the current header as variant 0)
+    gpurun -- 'python tools/layout_search.py run'     # times every variants/layout_*.so, preset and classic
+    python tools/layout_search.py pick                # reads gpurun_out/layout_search.json, prints the best order per ruleset
+"""
+import os, sys, json, random, subprocess, glob
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "citadels_self_play_b200", "csrc")
+VAR = os.path.join(ROOT, "citadels_self_play_b200", "variants")
+HOT = ["philox", "has", "append", "draw", "take_like", "count_type", "count_suit", "player_from_rank", "setup_next_player",
+       "refresh_used_roles", "apply_finish", "apply_build", "move_crown", "check_game_ending", "setup_round", "shuffle_bytes",
+       "reshuffle_if_empty", "apply", "warp_choose"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--extended-lambda", "-Xcompiler", "-fPIC"]
+
+
+def header(order, length):
+    lines = ["#pragma once"]
+    for i, h in enumerate(order):
+        new = f"ctd_h{i:02d}_{h}"
+        new = (new + "_" * length)[:length] if length > len(f"ctd_h{i:02d}_") + 1 else new
+        lines.append(f"#define ctd_{h} {new}")
+    return "\n".join(lines) + "\n"
+
+
+def build(n, seed):
+    os.makedirs(VAR, exist_ok=True)
+    base = "/tmp/ctd_layout_base"
+    os.makedirs(base, exist_ok=True)
+    units = ["ctd_kernels.cu"] + sorted(f for f in os.listdir(CSRC) if f.startswith(("ctd_generic_", "ctd_preset_", "ctd_classic_")) and f.endswith(".cu"))
+    fixed = [u for u in units if u not in ("ctd_preset_playout.cu", "ctd_classic_playout.cu")]
+    procs = [subprocess.Popen([NVCC] + FLAGS + ["-c", "-o", os.path.join(base, u[:-3] + ".o"), u], cwd=CSRC) for u in fixed]
+    assert all(p.wait() == 0 for p in procs)
+    rng = random.Random(seed)
+    plans = []
+    parents = [json.load(open(f)) for f in sys.argv[4:]]   # optional: mutate these plans instead of drawing fresh orders
+    for k in range(n):
+        if parents:
+            par = parents[k % len(parents)]
+            order = par["order"][:]
+            for _ in range(rng.choice([1, 1, 2, 3])):   # move one function somewhere else
+                x = order.pop(rng.randrange(len(order)))
+                order.insert(rng.randrange(len(order) + 1), x)
+            plans.append({"name": f"layout_s{seed}_{k:02d}", "order": order, "length": par["length"], "parent": par["name"]})
+        else:
+            order = HOT[:]
+            rng.shuffle(order)
+            plans.append({"name": f"layout_s{seed}_{k:02d}", "order": order, "length": rng.choice([34, 34, 34, 10])})
+    for p in plans:
+        hp = os.path.join(base, p["name"] + ".h")
+        open(hp, "w").write(header(p["order"], p["length"]))
+        objs = []
+        procs = []
+        for u in ("ctd_preset_playout.cu", "ctd_classic_playout.cu"):
+            o = os.path.join(base, p["name"] + "_" + u[:-3] + ".o")
+            objs.append(o)
+            procs.append(subprocess.Popen([NVCC] + FLAGS + [f'-DCTD_LAYOUT_HEADER="{hp}"',
+                                                             "-c", "-o", o, u], cwd=CSRC, stderr=subprocess.DEVNULL))
+        assert all(q.wait() == 0 for q in procs)
+        subprocess.check_call([NVCC, "-shared", "-o", os.path.join(VAR, p["name"] + ".so")] + objs + [os.path.join(base, u[:-3] + ".o") for u in fixed])
+        json.dump(p, open(os.path.join(VAR, p["name"] + ".json"), "w"))
+        print("built", p["name"], p["length"], flush=True)
+
+
+def run():
+    out = []
+    libs = [None] + sorted(glob.glob(os.path.join(VAR, "layout_*.so")))
+    for lib in libs:
+        row = {"lib": os.path.basename(lib) if lib else "shipped"}
+        for rs, key in ((0, "preset"), (1, "classic")):
+            env = dict(os.environ)
+            if lib: env["CTD_LIB"] = lib
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "playout_perf.py"), "1048576", str(rs)], env=env, capture_output=True, text=True)
+            try: row[key] = json.loads(r.stdout.strip().splitlines()[-1])["steps_per_s"]
+            except Exception: row[key] = None
+        out.append(row)
+        print(json.dumps(row), flush=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "layout_search.json"), "w"))
+
+
+def pick():
+    rows = json.load(open(os.path.join(ROOT, "gpurun_out", "layout_search.json")))
+    for key in ("preset", "classic"):
+        rows2 = sorted([r for r in rows if r.get(key)], key=lambda r: -r[key])
+        print(key, [(r["lib"], round(r[key] / 1e9, 4)) for r in rows2[:5]], "shipped", [round(r[key] / 1e9, 4) for r in rows if r["lib"] == "shipped"])
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "build": build(int(sys.argv[2]), int(sys.argv[3]))
+    elif sys.argv[1] == "run": run()
+    else: pick()
