@@ -20,6 +20,9 @@
 #define CTD_NO_TRAIN_KERNEL 1
 #define CTD_MCCFR_KERNEL_NAME ctd_k_mccfr_unused
 #define CTD_MCCFR_PRED_KERNEL_NAME ctd_k_mccfr_pred
+#ifdef CTD_LAYOUT_HEADER   /* placement of the device functions by name order, see ctd_layout_preset.h / tools/layout_search.py */
+#include CTD_LAYOUT_HEADER
+#endif
 #include "ctd_search.cuh"
 
 cudaError_t ctd_mccfr_pred_generic_launch(const CtdPredArgs& p, int grid, cudaStream_t stream) {

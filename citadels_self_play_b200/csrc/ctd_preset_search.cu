@@ -23,6 +23,9 @@
 #define CTD_NO_PRED_KERNEL 1
 #define CTD_MCCFR_KERNEL_NAME ctd_k_mccfr_preset
 #define CTD_MCCFR_PRED_KERNEL_NAME ctd_k_mccfr_pred_preset_unused
+#ifdef CTD_LAYOUT_HEADER   /* placement of the device functions by name order, see ctd_layout_preset.h / tools/layout_search.py */
+#include CTD_LAYOUT_HEADER
+#endif
 #include "ctd_search.cuh"
 
 cudaError_t ctd_mccfr_preset_launch(const CtdMccfrArgs& a, int grid, cudaStream_t stream) {

@@ -5,17 +5,38 @@ instruction cache (profiles/README.md), so WHERE the per-step functions sit rela
 writes renaming headers (the format of csrc/ctd_layout_preset.h: `#define ctd_x ctd_hNN_...`) for a set of orders, builds one library per order
 (only the playout units are recompiled) under citadels_self_play_b200/variants/, and prints the command that times them on the GPU box:
 
-    python tools/layout_search.py build N SEED        # N random orders (+ the current header as variant 0)
-    gpurun -- 'python tools/layout_search.py run'     # times every variants/layout_*.so, preset and classic
-    python tools/layout_search.py pick                # reads gpurun_out/layout_search.json, prints the best order per ruleset
+    python tools/layout_search.py build N SEED [parent.json ...]   # N random orders, or N mutations of the given plans
+    gpurun -- 'python tools/layout_search.py run'                  # times every variants/layout_<target>_*.so next to the shipped library
+    python tools/layout_search.py pick                             # reads gpurun_out/layout_search_<target>.json, prints the best orders
+LAYOUT_TARGET=playout (default: the preset / classic playout units) or search (the preset cfr_train / cfr_pred units).
 """
 import os, sys, json, random, subprocess, glob
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "citadels_self_play_b200", "csrc")
 VAR = os.path.join(ROOT, "citadels_self_play_b200", "variants")
-HOT = ["philox", "has", "append", "draw", "take_like", "count_type", "count_suit", "player_from_rank", "setup_next_player",
-       "refresh_used_roles", "apply_finish", "apply_build", "move_crown", "check_game_ending", "setup_round", "shuffle_bytes",
-       "reshuffle_if_empty", "apply", "warp_choose"]
+TARGETS = {
+    "playout": {
+        "units": ("ctd_preset_playout.cu", "ctd_classic_playout.cu"),
+        "functions": ["philox", "has", "append", "draw", "take_like", "count_type", "count_suit", "player_from_rank", "setup_next_player",
+                      "refresh_used_roles", "apply_finish", "apply_build", "move_crown", "check_game_ending", "setup_round", "shuffle_bytes",
+                      "reshuffle_if_empty", "apply", "warp_choose"],
+        "lengths": [34, 34, 34, 10],
+        "bench": [(("playout_perf.py", "1048576", "0"), {"steps_per_s": "preset"}), (("playout_perf.py", "1048576", "1"), {"steps_per_s": "classic"})],
+    },
+    "search": {   # the preset search kernels: cfr_train (pure) and cfr_pred (deep, fused)
+        "units": ("ctd_preset_search.cu", "ctd_preset_pred.cu"),
+        "functions": ["append", "expand", "philox", "unpack", "new_node", "node_far", "cfr_train", "enumerate", "kn_add_hk", "take_like", "tree_init",
+                      "count_suit", "count_type", "move_crown", "tree_alloc", "apply_build", "encode_game", "live_choice", "setup_round",
+                      "apply_finish", "count_points", "kn_hk_remove", "action_choice", "backpropagate", "kn_setup_round", "sample_private",
+                      "update_strategy", "cfr_pred_advance", "player_from_rank", "character_options", "check_game_ending", "setup_next_player",
+                      "skip_false_choice", "main_round_options", "refresh_used_roles", "reshuffle_if_empty", "wizard_take_options", "has", "draw",
+                      "apply"],
+        "lengths": [34],
+        "bench": [(("mccfr_perf.py", "4096", "200", "both"), {"pure_it_per_s": "pure", "deep_it_per_s": "deep"})],
+    },
+}
+TARGET = os.environ.get("LAYOUT_TARGET", "playout")
+HOT = TARGETS[TARGET]["functions"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--extended-lambda", "-Xcompiler", "-fPIC"]
 
@@ -34,7 +55,7 @@ def build(n, seed):
     base = "/tmp/ctd_layout_base"
     os.makedirs(base, exist_ok=True)
     units = ["ctd_kernels.cu"] + sorted(f for f in os.listdir(CSRC) if f.startswith(("ctd_generic_", "ctd_preset_", "ctd_classic_")) and f.endswith(".cu"))
-    fixed = [u for u in units if u not in ("ctd_preset_playout.cu", "ctd_classic_playout.cu")]
+    fixed = [u for u in units if u not in TARGETS[TARGET]["units"]]
     procs = [subprocess.Popen([NVCC] + FLAGS + ["-c", "-o", os.path.join(base, u[:-3] + ".o"), u], cwd=CSRC) for u in fixed]
     assert all(p.wait() == 0 for p in procs)
     rng = random.Random(seed)
@@ -47,17 +68,17 @@ def build(n, seed):
             for _ in range(rng.choice([1, 1, 2, 3])):   # move one function somewhere else
                 x = order.pop(rng.randrange(len(order)))
                 order.insert(rng.randrange(len(order) + 1), x)
-            plans.append({"name": f"layout_s{seed}_{k:02d}", "order": order, "length": par["length"], "parent": par["name"]})
+            plans.append({"name": f"layout_{TARGET}_s{seed}_{k:02d}", "order": order, "length": par["length"], "parent": par["name"]})
         else:
             order = HOT[:]
             rng.shuffle(order)
-            plans.append({"name": f"layout_s{seed}_{k:02d}", "order": order, "length": rng.choice([34, 34, 34, 10])})
+            plans.append({"name": f"layout_{TARGET}_s{seed}_{k:02d}", "order": order, "length": rng.choice(TARGETS[TARGET]["lengths"])})
     for p in plans:
         hp = os.path.join(base, p["name"] + ".h")
         open(hp, "w").write(header(p["order"], p["length"]))
         objs = []
         procs = []
-        for u in ("ctd_preset_playout.cu", "ctd_classic_playout.cu"):
+        for u in TARGETS[TARGET]["units"]:
             o = os.path.join(base, p["name"] + "_" + u[:-3] + ".o")
             objs.append(o)
             procs.append(subprocess.Popen([NVCC] + FLAGS + [f'-DCTD_LAYOUT_HEADER="{hp}"',
@@ -70,25 +91,29 @@ def build(n, seed):
 
 def run():
     out = []
-    libs = [None] + sorted(glob.glob(os.path.join(VAR, "layout_*.so")))
+    libs = [None] + sorted(glob.glob(os.path.join(VAR, f"layout_{TARGET}_*.so")))
     for lib in libs:
         row = {"lib": os.path.basename(lib) if lib else "shipped"}
-        for rs, key in ((0, "preset"), (1, "classic")):
+        for cmd, keys in TARGETS[TARGET]["bench"]:
             env = dict(os.environ)
             if lib: env["CTD_LIB"] = lib
-            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "playout_perf.py"), "1048576", str(rs)], env=env, capture_output=True, text=True)
-            try: row[key] = json.loads(r.stdout.strip().splitlines()[-1])["steps_per_s"]
-            except Exception: row[key] = None
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", cmd[0])] + list(cmd[1:]), env=env, capture_output=True, text=True)
+            try:
+                d = json.loads(r.stdout.strip().splitlines()[-1])
+                for k, name in keys.items(): row[name] = d[k]
+            except Exception:
+                for name in keys.values(): row[name] = None
         out.append(row)
         print(json.dumps(row), flush=True)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "layout_search.json"), "w"))
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"layout_search_{TARGET}.json"), "w"))
 
 
 def pick():
-    rows = json.load(open(os.path.join(ROOT, "gpurun_out", "layout_search.json")))
-    for key in ("preset", "classic"):
+    rows = json.load(open(os.path.join(ROOT, "gpurun_out", f"layout_search_{TARGET}.json")))
+    keys = [name for _, ks in TARGETS[TARGET]["bench"] for name in ks.values()]
+    for key in keys:
         rows2 = sorted([r for r in rows if r.get(key)], key=lambda r: -r[key])
-        print(key, [(r["lib"], round(r[key] / 1e9, 4)) for r in rows2[:5]], "shipped", [round(r[key] / 1e9, 4) for r in rows if r["lib"] == "shipped"])
+        print(key, [(r["lib"], f"{r[key]:.4g}") for r in rows2[:5]], "shipped", [f"{r[key]:.4g}" for r in rows if r["lib"] == "shipped"])
 
 
 if __name__ == "__main__":
