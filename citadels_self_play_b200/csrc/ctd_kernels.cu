@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(CTD_BLOCK) ctd_k_choose_check(const ctd_state*
     return;
   }
   for (uint32_t k = 0; k < nref && k < cap; ++k) {
-    uint64_t d = ctd_warp_choose(w, lane, choose_buf[wib], &cnt, (int)k);
+    uint64_t d = ctd_warp_choose<true>(w, lane, choose_buf[wib], &cnt, (int)k);
     __syncwarp();
     if (cnt != nref) { bad += 1000000; break; }
     uint64_t want = ref[k];

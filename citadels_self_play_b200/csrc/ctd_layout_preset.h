@@ -1,20 +1,20 @@
 // ctd_layout_preset.h -- placement of the per-step device functions of ctd_k_playout_preset.
 // ptxas lays the device functions of a kernel out in the order of their mangled names.  The playout kernels are bound by the SM's
 // instruction cache (profiles/README.md), and which of their hot lines share cache sets is worth +-5 %: tools/layout_search.py
-// timed 40 orders of the 19 functions the loop runs every step (renamed here to equally long names with an order prefix, so that
+// timed 64 orders of the 19 functions the loop runs every step (renamed here to equally long names with an order prefix, so that
 // they sit in one block in exactly this order, apart from the once-per-game code); this is the best one found for this unit
-// (preset 1.076e9 -> 1.112e9 env steps/s).  Regenerate with the tool after changing the rules code.
+// (preset 1.076e9 with the functions where their own names put them -> 1.124e9 env steps/s).  Regenerate with the tool after changing the rules code.
 #pragma once
 #define ctd_count_type ctd_h00_co
 #define ctd_apply ctd_h01_ap
 #define ctd_draw ctd_h02_dr
-#define ctd_setup_round ctd_h03_se
-#define ctd_setup_next_player ctd_h04_se
-#define ctd_apply_finish ctd_h05_ap
-#define ctd_has ctd_h06_ha
-#define ctd_append ctd_h07_ap
-#define ctd_count_suit ctd_h08_co
-#define ctd_refresh_used_roles ctd_h09_re
+#define ctd_refresh_used_roles ctd_h03_re
+#define ctd_setup_round ctd_h04_se
+#define ctd_setup_next_player ctd_h05_se
+#define ctd_apply_finish ctd_h06_ap
+#define ctd_has ctd_h07_ha
+#define ctd_append ctd_h08_ap
+#define ctd_count_suit ctd_h09_co
 #define ctd_take_like ctd_h10_ta
 #define ctd_check_game_ending ctd_h11_ch
 #define ctd_player_from_rank ctd_h12_pl

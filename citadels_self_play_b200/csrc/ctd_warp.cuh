@@ -37,7 +37,12 @@ __device__ __forceinline__ void ctd_ring_refill(CtdWork& w, int lane) {
 }
 
 // scalar fallback: lane 0 materialises the list, draws k, picks
-static __device__ __noinline__ uint64_t ctd_choose_scalar(CtdWork& w, int lane, uint64_t* buf, uint32_t* count_out, int want) {
+// CHECK: the checker's form (ctd_k_choose_check: report the count, take a given k).  The playout kernels instantiate CHECK = false,
+// where count_out / want / ring are dead on entry and cost neither registers nor code.
+template <bool CHECK>
+static __device__ __noinline__ uint64_t ctd_choose_scalar(CtdWork& w, int lane, uint64_t* buf, uint32_t* count_out_, int want_) {
+  uint32_t* const count_out = CHECK ? count_out_ : nullptr;
+  const int want = CHECK ? want_ : -1;
   CTD_ASSUME_SHARED(&w);
   uint64_t d = 0;
   uint32_t n = 0;
@@ -107,26 +112,36 @@ enum { CTD_PM_ROLE_PICK, CTD_PM_GOLD_OR_CARD, CTD_PM_SINGLE, CTD_PM_KEEP, CTD_PM
 #ifndef CTD_CHOOSE_LINKAGE
 #define CTD_CHOOSE_LINKAGE static
 #endif
-CTD_CHOOSE_LINKAGE __device__ CTD_CHOOSE_ATTR uint64_t ctd_warp_choose(CtdWork& w, int lane, uint64_t* buf, uint32_t* count_out = nullptr,
-                                                 int want = -1, const uint32_t* ring = nullptr) {
+template <bool CHECK = false>
+CTD_CHOOSE_LINKAGE __device__ CTD_CHOOSE_ATTR uint64_t ctd_warp_choose(CtdWork& w, int lane, uint64_t* buf, uint32_t* count_out_ = nullptr,
+                                                 int want_ = -1, const uint32_t* ring_ = nullptr) {
+  uint32_t* const count_out = CHECK ? count_out_ : nullptr;
+  const int want = CHECK ? want_ : -1;
+#if CTD_PLAYOUT_RING
+  const uint32_t* const ring = ring_;
+#else
+  const uint32_t* const ring = nullptr;
+#endif
   const int p = w.player, st = w.state;
-  if ((w.gflags & 2) || p >= 6) return ctd_choose_scalar(w, lane, buf, count_out, want);
+  if ((w.gflags & 2) || p >= 6) return ctd_choose_scalar<CHECK>(w, lane, buf, count_out, want);
   const uint64_t me = (uint64_t)p << 6;
   int mode = -1;
   uint32_t total = 0, m0 = 0, m1 = 0, m2 = 0;   // mode-specific masks
   uint64_t single = 0;
   // main-round class counts
-  uint32_t c_build = 0, c_char = 0, c_beg = 0, c_wgold = 0, c_smithy = 0, c_lab = 0, c_ms = 0, c_ws = 0, c_mus = 0;
+  // (the seven small ones share one register: bit 0 beg, 1 war gold, 2 smithy, 3 magic school (x5), bits 8-15 lab, 16-23 weapon storage,
+  // 24-31 museum -- the function runs under a 32-register bound and spills what does not fit)
+  uint32_t c_build = 0, c_char = 0, cx = 0;
   int nm = 0, nh = 0;
   uint64_t own = 0;
   if (st == 0) {  // pick_role_options: one per role still on offer, rank ascending
     mode = CTD_PM_ROLE_PICK; m0 = w.rtc_mask; total = __popc(m0);
   } else {
     const int role = w.role[p];
-    if (role >= 8) return ctd_choose_scalar(w, lane, buf, count_out, want);  // None / Bewitched: error paths
+    if (role >= 8) return ctd_choose_scalar<CHECK>(w, lane, buf, count_out, want);  // None / Bewitched: error paths
     nm = role * 3 + w.variant[role];
     const int rp = w.rprops[role];
-    if (rp & CTD_RP_DEAD) return ctd_choose_scalar(w, lane, buf, count_out, want);
+    if (rp & CTD_RP_DEAD) return ctd_choose_scalar<CHECK>(w, lane, buf, count_out, want);
     if (st == 1) {
       mode = CTD_PM_GOLD_OR_CARD; total = w.n_deck > 1 ? 2 : 1;
     } else if (st == 3 && !(rp & CTD_RP_BLACKMAIL)) {
@@ -142,7 +157,7 @@ CTD_CHOOSE_LINKAGE __device__ CTD_CHOOSE_ATTR uint64_t ctd_warp_choose(CtdWork& 
       }
       if (st == 2) {  // which_card_to_keep_options
         const int n = w.n_jd[p];
-        if (n > 32) return ctd_choose_scalar(w, lane, buf, count_out, want);
+        if (n > 32) return ctd_choose_scalar<CHECK>(w, lane, buf, count_out, want);
         if ((own >> 20) & 1) {  // Library: every pair i < j, no de-duplication
           mode = CTD_PM_KEEP_LIBRARY; m0 = (uint32_t)n; total = (uint32_t)(n * (n - 1) / 2);
         } else {
@@ -162,7 +177,7 @@ CTD_CHOOSE_LINKAGE __device__ CTD_CHOOSE_ATTR uint64_t ctd_warp_choose(CtdWork& 
         const uint32_t tier_ab = (1u << CTD_SPY) | (1u << CTD_WIZARD) | (1u << CTD_KING) | (1u << CTD_ABBOT) | (1u << CTD_ALCHEMIST) |
                                  (1u << CTD_NAVIGATOR) | (1u << CTD_WARLORD) | (1u << CTD_ASSASSIN) | (1u << CTD_THIEF) |
                                  (1u << CTD_MAGICIAN) | (1u << CTD_BISHOP) | (1u << CTD_MERCHANT) | (1u << CTD_ARCHITECT);
-        if (nh > 32 || lighthouse || !((tier_ab >> nm) & 1)) return ctd_choose_scalar(w, lane, buf, count_out, want);
+        if (nh > 32 || lighthouse || !((tier_ab >> nm) & 1)) return ctd_choose_scalar<CHECK>(w, lane, buf, count_out, want);
         mode = CTD_PM_MAIN;
         const int gold = w.gold[p], done = w.done;
         const int hc = lane < nh ? w.hand[p][lane] : 0, ht = ctd_ctype(hc);
@@ -207,22 +222,26 @@ CTD_CHOOSE_LINKAGE __device__ CTD_CHOOSE_ATTR uint64_t ctd_warp_choose(CtdWork& 
             c_char = __popc(m1) + __popc(m2);
           }
         }
-        c_beg = (nm == CTD_ABBOT && !(done & CTD_DM_BEGGED)) ? 1 : 0;
-        c_wgold = (nm == CTD_WARLORD && !(done & CTD_DM_TAKE_GOLD)) ? 1 : 0;
-        c_smithy = (((own >> 21) & 1) && gold >= 2 && !(done & CTD_DM_SMITHY)) ? 1 : 0;
-        c_lab = (((own >> 22) & 1) && !(done & CTD_DM_LAB)) ? (uint32_t)nh : 0;
-        c_ms = (((own >> 25) & 1) && !(done & CTD_DM_MAGIC_SCHOOL)) ? 5 : 0;
-        if ((own >> 27) & 1)
-          c_ws = (uint32_t)(w.n_bld[0] + w.n_bld[1] + w.n_bld[2] + w.n_bld[3] + w.n_bld[4] + w.n_bld[5] - nb);
+        if (nm == CTD_ABBOT && !(done & CTD_DM_BEGGED)) cx |= 1u;
+        if (nm == CTD_WARLORD && !(done & CTD_DM_TAKE_GOLD)) cx |= 2u;
+        if (((own >> 21) & 1) && gold >= 2 && !(done & CTD_DM_SMITHY)) cx |= 4u;
+        if (((own >> 25) & 1) && !(done & CTD_DM_MAGIC_SCHOOL)) cx |= 8u;
+        if (((own >> 22) & 1) && !(done & CTD_DM_LAB)) cx |= (uint32_t)nh << 8;
+        if ((own >> 27) & 1) {
+          const uint32_t ws = (uint32_t)(w.n_bld[0] + w.n_bld[1] + w.n_bld[2] + w.n_bld[3] + w.n_bld[4] + w.n_bld[5] - nb);
+          if (ws > 255u) return ctd_choose_scalar<CHECK>(w, lane, buf, count_out, want);   // beyond the packed field (no real game gets near)
+          cx |= ws << 16;
+        }
         uint32_t m_mus = 0;
         if (((own >> 34) & 1) && !(done & CTD_DM_MUSEUM)) m_mus = __ballot_sync(CTD_ALL, hfirst);
-        c_mus = __popc(m_mus);
+        cx |= (uint32_t)__popc(m_mus) << 24;
         if (nm != CTD_WARLORD) m2 = m_mus;          // m2 is free unless the Warlord uses it ...
         else single = m_mus;                        // ... then the museum mask travels in `single`
-        total = c_build + c_char + c_beg + c_wgold + c_smithy + c_lab + c_ms + c_ws + c_mus + 1;
+        total = c_build + c_char + (cx & 1u) + ((cx >> 1) & 1u) + ((cx >> 2) & 1u) + ((cx >> 3) & 1u) * 5u + ((cx >> 8) & 255u) +
+                ((cx >> 16) & 255u) + (cx >> 24) + 1;
       }
     } else {
-      return ctd_choose_scalar(w, lane, buf, count_out, want);
+      return ctd_choose_scalar<CHECK>(w, lane, buf, count_out, want);
     }
   }
   if (count_out) *count_out = total;
@@ -299,6 +318,8 @@ CTD_CHOOSE_LINKAGE __device__ CTD_CHOOSE_ATTR uint64_t ctd_warp_choose(CtdWork& 
     }
   }
   k -= c_char;
+  const uint32_t c_beg = cx & 1u, c_wgold = (cx >> 1) & 1u, c_smithy = (cx >> 2) & 1u, c_ms = ((cx >> 3) & 1u) * 5u,
+                 c_lab = (cx >> 8) & 255u, c_ws = (cx >> 16) & 255u, c_mus = cx >> 24;
   if (k < c_beg) return CTD_K_ABBOT_BEG | me;
   k -= c_beg;
   if (k < c_wgold) return CTD_K_TAKE_GOLD_WAR | me;
