@@ -116,7 +116,24 @@ def pick():
         print(key, [(r["lib"], f"{r[key]:.4g}") for r in rows2[:5]], "shipped", [f"{r[key]:.4g}" for r in rows if r["lib"] == "shipped"])
 
 
+def best_to(prefix):
+    """write the plan of the best variant per benchmark key to <prefix><key>.json when it beats the shipped library of the same run"""
+    rows = json.load(open(os.path.join(ROOT, "gpurun_out", f"layout_search_{TARGET}.json")))
+    keys = [name for _, ks in TARGETS[TARGET]["bench"] for name in ks.values()]
+    ship = {k: [r[k] for r in rows if r["lib"] == "shipped"][0] for k in keys}
+    for key in keys:
+        cand = sorted([r for r in rows if r.get(key) and r["lib"] != "shipped"], key=lambda r: -r[key])
+        if cand and cand[0][key] > ship[key] * 1.002:
+            plan = json.load(open(os.path.join(VAR, cand[0]["lib"][:-3] + ".json")))
+            plan["measured"] = {key: cand[0][key], "shipped_same_run": ship[key]}
+            json.dump(plan, open(prefix + key + ".json", "w"))
+            print("new best", key, cand[0]["lib"], f"{cand[0][key]:.5g}", "shipped", f"{ship[key]:.5g}")
+        else:
+            print("no improvement", key, f"{ship[key]:.5g}")
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "build": build(int(sys.argv[2]), int(sys.argv[3]))
     elif sys.argv[1] == "run": run()
+    elif sys.argv[1] == "best": best_to(sys.argv[2])
     else: pick()
