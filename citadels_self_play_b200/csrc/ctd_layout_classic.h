@@ -1,7 +1,7 @@
 // ctd_layout_classic.h -- placement of the per-step device functions of ctd_k_playout_classic.
 // ptxas lays the device functions of a kernel out in the order of their mangled names.  The playout kernels are bound by the SM's
 // instruction cache (profiles/README.md), and which of their hot lines share cache sets is worth +-5 %: tools/layout_search.py
-// timed 130 orders (random, then hill-climbing on the best) of the 19 functions the loop runs every step (renamed here to equally long names with an order prefix, so that
+// timed 230 orders (random, then hill-climbing on the best) of the 19 functions the loop runs every step (renamed here to equally long names with an order prefix, so that
 // they sit in one block in exactly this order, apart from the once-per-game code); this is the best one found for this unit
 // (classic 1.006e9 with the functions where their own names put them -> 1.141e9 env steps/s).  Regenerate with the tool after changing the rules code.
 #pragma once
@@ -10,9 +10,9 @@
 #define ctd_has ctd_h02_has_______________________
 #define ctd_append ctd_h03_append____________________
 #define ctd_draw ctd_h04_draw______________________
-#define ctd_take_like ctd_h05_take_like_________________
-#define ctd_reshuffle_if_empty ctd_h06_reshuffle_if_empty________
-#define ctd_player_from_rank ctd_h07_player_from_rank__________
+#define ctd_reshuffle_if_empty ctd_h05_reshuffle_if_empty________
+#define ctd_player_from_rank ctd_h06_player_from_rank__________
+#define ctd_take_like ctd_h07_take_like_________________
 #define ctd_setup_next_player ctd_h08_setup_next_player_________
 #define ctd_refresh_used_roles ctd_h09_refresh_used_roles________
 #define ctd_apply_finish ctd_h10_apply_finish______________
