@@ -413,7 +413,11 @@ CTD_HD CTD_NI inline void ctd_kn_setup_round(CtdKnow& k) {
 CTD_HD CTD_NI inline void ctd_kn_add_hk(CtdKnow& k, int pid, const uint8_t* cards, int n, int ring_head, int ring_mask,
                                         bool wizard) {
   CTD_ASSUME_SHARED_K(&k);
-  if (k.n_hk >= CTD_KN_HK_MAX || k.pool_used + n > CTD_KN_POOL) { k.err |= CTD_ERR_OVERFLOW; return; }
+  if (k.n_hk >= CTD_KN_HK_MAX || k.pool_used + n > CTD_KN_POOL) {
+#ifdef CTD_HOST_DEBUG
+    fprintf(stderr, "knowledge overflow: %d entries, pool %d + %d\n", (int)k.n_hk, (int)k.pool_used, n);
+#endif
+    k.err |= CTD_ERR_OVERFLOW; return; }
   CtdHK& h = k.hk[k.n_hk++];
   h.pid = (int8_t)pid; h.conf = 5; h.flags = wizard ? CTD_HK_WIZARD : 0; h.n = (uint8_t)n; h.off = k.pool_used; h.pad = 0;
   CTD_LOOP for (int i = 0; i < n; ++i) k.pool[k.pool_used + i] = cards[(ring_head + i) & ring_mask];
@@ -481,7 +485,11 @@ CTD_HD CTD_NI inline void ctd_append(CtdWork& w, uint8_t* a, uint8_t& n, int cap
 }
 CTD_HD inline uint8_t& ctd_dk(CtdWork& w, int i) { return w.deck[(w.deck_head + i) & (CTD_DECK_CAP - 1)]; }
 CTD_HD inline void ctd_deck_push(CtdWork& w, int c) {
-  if (w.n_deck >= CTD_DECK_CAP - 1) { w.err |= CTD_ERR_OVERFLOW; return; }
+  if (w.n_deck >= CTD_DECK_CAP - 1) {
+#ifdef CTD_HOST_DEBUG
+    fprintf(stderr, "deck overflow\n");
+#endif
+    w.err |= CTD_ERR_OVERFLOW; return; }
   ctd_dk(w, w.n_deck) = (uint8_t)c;
   ++w.n_deck;
 }

@@ -641,6 +641,9 @@ CTD_HD CTD_NI inline void ctd_expand(CtdTree& T, int ni) {
     ctd_node_load(T, n);
     const uint64_t* list;
     const uint32_t K = ctd_list_options(T, &list);
+#ifdef CTD_HOST_DEBUG
+    if (K == 0) fprintf(stderr, "expand: no options for the searching player, state %d err %d\n", (int)w.state, (int)w.err);
+#endif
     if (K == 0) { T.hdr->status |= w.err ? CTD_TREE_REF_RAISE : CTD_TREE_EENGINE; return; }
     // the reference enumerates on the node's own game (:134): the Scholar's list shrinks there, and every child is a copy of that
     if (w.state == 9) CTD_COPY_S2G(n.snap, &w, CTD_SNAP_BYTES);
@@ -697,6 +700,9 @@ CTD_HD CTD_NI inline void ctd_expand(CtdTree& T, int ni) {
     ctd_maybe_sample(T, n);
     const uint64_t* list;
     const uint32_t n_opts = ctd_list_options(T, &list);
+#ifdef CTD_HOST_DEBUG
+    if (n_opts == 0) fprintf(stderr, "expand: no options for an opponent, state %d err %d player %d role %d\n", (int)w.state, (int)w.err, (int)w.player, (int)w.role[w.player]);
+#endif
     if (n_opts == 0) { T.hdr->status |= w.err ? CTD_TREE_REF_RAISE : CTD_TREE_EENGINE; return; }
     uint32_t pick = ctd_randbelow(w, n_opts);
     uint64_t d;
