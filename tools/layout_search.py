@@ -19,7 +19,10 @@ TARGETS = {
         "units": ("ctd_preset_playout.cu", "ctd_classic_playout.cu"),
         "functions": ["philox", "has", "append", "draw", "take_like", "count_type", "count_suit", "player_from_rank", "setup_next_player",
                       "refresh_used_roles", "apply_finish", "apply_build", "move_crown", "check_game_ending", "setup_round", "shuffle_bytes",
-                      "reshuffle_if_empty", "apply", "warp_choose"],
+                      "reshuffle_if_empty", "apply", "warp_choose",
+                      # once-per-game and fallback code: part of the order too, so that the search can place it
+                      "unpack", "enumerate", "deal_preset", "count_points", "character_options", "main_round_options", "wizard_take_options",
+                      "pack"],
         "lengths": [34, 34, 34, 10],
         "bench": [(("playout_perf.py", "1048576", "0"), {"steps_per_s": "preset"}), (("playout_perf.py", "1048576", "1"), {"steps_per_s": "classic"})],
     },
