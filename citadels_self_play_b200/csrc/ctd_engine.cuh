@@ -349,18 +349,20 @@ CTD_HD CTD_SHUFFLE_ATTR inline void ctd_shuffle_bytes(CtdWork& w, uint8_t* a, in
 // What one observer ("viewer") believes: Agent.known_roles / Agent.known_hands (game/agent.py:25-26,
 // game/helper_classes.py:37-71), plus the looked-at hand of whoever used the Wizard this round
 // (the HandKnowledge the state-10 enumerator reads, game/agent_functions.py:311).  Playouts do not carry it.
-#define CTD_KN_HK_MAX 32 /* the Seer adds up to five one-card entries a round, each lives five rounds */
+#define CTD_KN_HK_MAX 64 /* the Seer adds up to five one-card entries a round, each lives five rounds; with a Wizard, a Spy and a
+                            Lighthouse at work as well, hypothetical games inside CFR trees were seen to pass 32 */
 #define CTD_KN_POOL 256
 #define CTD_KN_WIZ_CAP 48
 enum { CTD_HK_WIZARD = 1, CTD_HK_USED = 2 };
-struct CtdHK {
-  int8_t pid;      // -1 = the deck (Lighthouse)
-  uint8_t conf;    // 5..1, dropped at 0 (game/agent.py:100-109)
-  uint8_t flags;
-  uint8_t n;
-  uint16_t off;    // into pool
-  uint16_t pad;
+struct CtdHK {           // one HandKnowledge in four bytes (bit 0 upwards: pid 4, conf 3, flags 2, n 8, off 9)
+  int32_t pid : 4;       // -1 = the deck (Lighthouse)
+  uint32_t conf : 3;     // 5..1, dropped at 0 (game/agent.py:100-109)
+  uint32_t flags : 2;
+  uint32_t n : 8;
+  uint32_t off : 9;      // into pool
+  uint32_t pad : 6;
 };
+static_assert(sizeof(CtdHK) == 4, "CtdHK layout");
 struct alignas(16) CtdKnow {
   uint8_t viewer;
   uint8_t conf_mask;  // bit q: known_roles[*][q].confirmed (the same for every observer)
@@ -401,7 +403,7 @@ CTD_HD CTD_NI inline void ctd_kn_setup_round(CtdKnow& k) {
       k.hk[keep++] = h;
     }
   }
-  CTD_LOOP for (int i = keep; i < k.n_hk; ++i) { CtdHK z = {0, 0, 0, 0, 0, 0}; k.hk[i] = z; }
+  CTD_LOOP for (int i = keep; i < k.n_hk; ++i) { CtdHK z = {}; k.hk[i] = z; }
   CTD_LOOP for (int j = pos; j < k.pool_used; ++j) k.pool[j] = 0;  // unused bytes stay zero (records compare bytewise)
   k.n_hk = (uint8_t)keep;
   k.pool_used = pos;
@@ -419,7 +421,7 @@ CTD_HD CTD_NI inline void ctd_kn_add_hk(CtdKnow& k, int pid, const uint8_t* card
 #endif
     k.err |= CTD_ERR_OVERFLOW; return; }
   CtdHK& h = k.hk[k.n_hk++];
-  h.pid = (int8_t)pid; h.conf = 5; h.flags = wizard ? CTD_HK_WIZARD : 0; h.n = (uint8_t)n; h.off = k.pool_used; h.pad = 0;
+  h.pid = pid; h.conf = 5; h.flags = wizard ? CTD_HK_WIZARD : 0; h.n = (uint32_t)n; h.off = k.pool_used; h.pad = 0;
   CTD_LOOP for (int i = 0; i < n; ++i) k.pool[k.pool_used + i] = cards[(ring_head + i) & ring_mask];
   k.pool_used += (uint16_t)n;
 }

@@ -302,7 +302,7 @@ CTD_HD CTD_NI inline void ctd_sample_private(CtdWork& w, CtdKnow& k, const uint8
   CTD_LOOP for (int i = 0; i < k.n_hk; ++i) {
     double r = ctd_uniform(w);
     if ((double)(k.hk[i].conf - 1) * 0.2 > r) k.hk[i].flags |= CTD_HK_USED;
-    else k.hk[i].flags &= (uint8_t)~CTD_HK_USED;
+    else k.hk[i].flags &= (uint32_t)CTD_HK_WIZARD;   // clears CTD_HK_USED (flags is a two-bit field)
   }
   // (2) get_unknown_cards: used_cards minus everything visible, first occurrence per removal  (:183-213)
   uint8_t* unknown = scratch;       // <= 76

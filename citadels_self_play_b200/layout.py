@@ -60,11 +60,59 @@ def opt_fields(d):
 
 # ---- MCCFR tree export block (csrc/ctd_mccfr.cuh: CtdTreeHdrOut | CtdNodeOut[] | CtdChild[] | double[]) ----
 KNOW_BYTES = 592
-HK_DTYPE = np.dtype([("pid", np.int8), ("conf", np.uint8), ("flags", np.uint8), ("n", np.uint8), ("off", np.uint16),
-                     ("pad", np.uint16)])
+# one HandKnowledge entry is a 32-bit word (csrc/ctd_engine.cuh CtdHK): bits 0-3 pid (signed, -1 = the deck), 4-6 confidence,
+# 7-8 flags (1 wizard, 2 believed in this determinisation), 9-16 number of cards, 17-25 offset into the card pool
+KNOW_HK_MAX = 64
 KNOW_DTYPE = np.dtype([("viewer", np.uint8), ("conf_mask", np.uint8), ("n_hk", np.uint8), ("wiz_n", np.uint8),
-                       ("kr", np.uint16, 6), ("hk", HK_DTYPE, 32), ("wiz_cards", np.uint8, 48), ("pool", np.uint8, 256),
+                       ("kr", np.uint16, 6), ("hk", np.uint32, KNOW_HK_MAX), ("wiz_cards", np.uint8, 48), ("pool", np.uint8, 256),
                        ("pool_used", np.uint16), ("err", np.uint8), ("pad", np.uint8, 13)])
+
+
+def hk_pack(pid, conf, flags, n, off):
+    return (pid & 0xF) | (conf & 7) << 4 | (flags & 3) << 7 | (n & 0xFF) << 9 | (off & 0x1FF) << 17
+
+
+def hk_unpack(word):
+    word = int(word)
+    pid = word & 0xF
+    return dict(pid=pid - 16 if pid >= 8 else pid, conf=(word >> 4) & 7, flags=(word >> 7) & 3, n=(word >> 9) & 0xFF, off=(word >> 17) & 0x1FF)
+
+
+# Knowledge blocks written by a round-1 build (and the CFR fixtures under tests/golden/, which pin the reference's knowledge in that
+# form) hold at most 32 entries of 8 bytes (int8 pid, u8 conf, u8 flags, u8 n, u16 off, u16 pad) in the same 256 bytes.
+_HK_V1 = np.dtype([("pid", np.int8), ("conf", np.uint8), ("flags", np.uint8), ("n", np.uint8), ("off", np.uint16), ("pad", np.uint16)])
+
+
+def know_from_v1(blob):
+    """592-byte knowledge block(s) in the round-1 entry format -> the current one.  Accepts [592] or [n, 592] uint8."""
+    a = np.array(blob, dtype=np.uint8, copy=True)
+    flat = a.reshape(-1, KNOW_BYTES)
+    for row in flat:
+        old = row[16:272].copy().view(_HK_V1)
+        new = np.zeros(KNOW_HK_MAX, dtype=np.uint32)
+        for i in range(int(row[2])):
+            e = old[i]
+            new[i] = hk_pack(int(e["pid"]), int(e["conf"]), int(e["flags"]), int(e["n"]), int(e["off"]))
+        row[16:272] = new.view(np.uint8)
+    return a
+
+
+def know_to_v1(blob):
+    """The inverse (blocks with at most 32 entries): what the fixtures' knowledge checksums are taken over."""
+    a = np.array(blob, dtype=np.uint8, copy=True)
+    flat = a.reshape(-1, KNOW_BYTES)
+    for row in flat:
+        if int(row[2]) > 32:
+            raise ValueError("more than 32 hand-knowledge entries do not fit the round-1 format")
+        new = row[16:272].copy().view(np.uint32)
+        old = np.zeros(32, dtype=_HK_V1)
+        for i in range(int(row[2])):
+            f = hk_unpack(new[i])
+            old[i] = (f["pid"], f["conf"], f["flags"], f["n"], f["off"], 0)
+        row[16:272] = old.view(np.uint8)
+    return a
+
+
 assert KNOW_DTYPE.itemsize == KNOW_BYTES
 NODE_DTYPE = np.dtype([("parent", np.int32), ("depth", np.uint16), ("player", np.uint8), ("flags", np.uint8),
                        ("n_children", np.uint32), ("child_cap", np.uint32), ("child_off", np.uint32),

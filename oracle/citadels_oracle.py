@@ -1579,11 +1579,11 @@ class Game:
 
     def pack_know(self, viewer):
         """The engine's 592-byte knowledge block of one observer (csrc/ctd_engine.cuh `CtdKnow`)."""
-        b = bytearray(592)   # header 16 | hk[32] x 8 | wiz_cards[48] @272 | pool[256] @320 | pool_used @576
+        b = bytearray(592)   # header 16 | hk[64] x 4 | wiz_cards[48] @272 | pool[256] @320 | pool_used @576
         b[0] = viewer
         b[1] = sum(1 << q for q in range(6) if self.kr_conf[viewer][q])
         hks = self.kh[viewer]
-        assert len(hks) <= 32
+        assert len(hks) <= 64
         b[2] = len(hks)
         wiz = self.wiz_cards if self.wiz_target != 0xFF else []
         b[3] = len(wiz)
@@ -1591,8 +1591,8 @@ class Game:
             struct.pack_into("<H", b, 4 + 2 * q, self.kr_mask[viewer][q])
         pos = 0
         for i, h in enumerate(hks):
-            struct.pack_into("<bBBBHH", b, 16 + 8 * i, h.pid, h.conf, (1 if h.wizard else 0) | (2 if h.used else 0),
-                             len(h.cards), pos, 0)
+            flags = (1 if h.wizard else 0) | (2 if h.used else 0)   # CtdHK: pid 4 bits | conf 3 | flags 2 | n 8 | off 9
+            struct.pack_into("<I", b, 16 + 4 * i, (h.pid & 0xF) | (h.conf & 7) << 4 | flags << 7 | len(h.cards) << 9 | pos << 17)
             b[320 + pos:320 + pos + len(h.cards)] = bytes(h.cards)
             pos += len(h.cards)
         b[272:272 + len(wiz)] = bytes(wiz)
@@ -1611,7 +1611,9 @@ class Game:
                 self.kr_conf[o][q] = conf
         self.kh[v] = []
         for i in range(n_hk):
-            pid, conf, flags, n, off, _ = struct.unpack_from("<bBBBHH", blob, 16 + 8 * i)
+            word = struct.unpack_from("<I", blob, 16 + 4 * i)[0]
+            pid, conf, flags, n, off = word & 0xF, (word >> 4) & 7, (word >> 7) & 3, (word >> 9) & 0xFF, (word >> 17) & 0x1FF
+            pid = pid - 16 if pid >= 8 else pid
             h = HandKnowledge(pid, list(blob[320 + off:320 + off + n]), conf, bool(flags & 1))
             h.used = bool(flags & 2)
             self.kh[v].append(h)

@@ -295,7 +295,9 @@ def ref_knowledge(g):
 
 
 def ref_pack_know(g, viewer):
-    """Reference Agent.known_roles / known_hands of `viewer` -> the engine's 592-byte knowledge block."""
+    """Reference Agent.known_roles / known_hands of `viewer` -> a 592-byte knowledge block in the ROUND-1 entry format (32 entries of
+    8 bytes), the one the committed fixtures and their know_crc checksums were made with; tests convert with
+    citadels_self_play_b200.layout.know_from_v1 / know_to_v1 (the engine's own format holds 64 entries of 4 bytes)."""
     import struct
     pl = g.players[viewer]
     b = bytearray(592)   # header 16 | hk[32] x 8 | wiz_cards[48] @272 | pool[256] @320 | pool_used @576

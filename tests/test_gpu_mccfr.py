@@ -133,6 +133,22 @@ def test_roots_the_fixed_pool_refused_now_complete(engine):
                 assert_same_tree(oracle_preorder(node), tree_preorder(out["trees"][i]), ("big", gid0 + i))
 
 
+def test_roots_the_knowledge_block_refused_now_complete(engine):
+    """Two Game(preset=False) roots whose hypothetical games collect more than 32 hand-knowledge entries (status 4 while the
+    knowledge block held 32 of them), against the oracle."""
+    from oracle import mccfr_oracle as M
+    seed = 0xC17ADE15
+    for gid in (7003168, 7006460):
+        engine.make_roots(1, seed=seed, first_gid=gid, ruleset=2, back_lo=0, back_hi=20)
+        roots, knows, used, gids = engine.store_roots(1)
+        out = engine.mccfr(1, iterations=200, seed=seed, ruleset=2, trees=True)
+        assert out["results"][0]["status"] == 0
+        tv = out["trees"][0]
+        assert int(tv.nodes["know"]["n_hk"].max()) > 32
+        node = M.run_from_root(roots[0], knows[0], used[0], seed, int(gids[0]), 200)
+        assert_same_tree(oracle_preorder(node), tree_preorder(tv), ("busy seer", gid))
+
+
 def test_exhausted_arena_is_retried(engine, monkeypatch):
     """Tree memory: with the first arena squeezed to a sliver most trees find it exhausted; the engine searches them again from
     further arenas and the call returns the same trees as an unconstrained run."""

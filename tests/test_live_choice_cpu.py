@@ -28,8 +28,11 @@ def same_option(a, b):
 
 
 def load(name):
+    from citadels_self_play_b200.layout import know_from_v1
     with np.load(os.path.join(GOLDEN, name)) as f:
-        return {k: f[k] for k in f.files}
+        z = {k: f[k] for k in f.files}
+    z["knows"] = know_from_v1(z["knows"])   # the fixtures hold knowledge blocks in the round-1 entry format
+    return z
 
 
 @pytest.mark.parametrize("name", PURE)

@@ -86,6 +86,29 @@ def test_kernel_tree_memory_chunks_and_exhaustion(hostsim, monkeypatch):
     assert st & 2
 
 
+def test_kernel_knowledge_block_holds_a_busy_seer(hostsim):
+    """Two Game(preset=False) roots (seed 0xC17ADE15, gids 7003168 and 7006460, stepped back 0..20) whose hypothetical games collect
+    more than 32 hand-knowledge entries: refused with status 4 while the knowledge block held 32 entries, complete now and equal to
+    the oracle's trees node for node."""
+    from citadels_self_play_b200.layout import TreeView
+    u64, u32, vp, i32 = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int
+    hostsim.hs_make_root.argtypes = [u64, u64, i32, u32, u32, i32, vp, vp, vp, vp]
+    root, know, used, step = np.zeros(256, np.uint8), np.zeros(592, np.uint8), np.zeros(76, np.uint8), np.zeros(1, np.uint32)
+    SEED = 0xC17ADE15
+    nb = ctypes.c_uint64()
+    most = 0
+    for gid in (7003168, 7006460):
+        hostsim.hs_make_root(SEED, gid, 2, 0, 20, 0, root.ctypes.data, know.ctypes.data, used.ctypes.data, step.ctypes.data)
+        st = hostsim.hs_mccfr(root.ctypes.data, know.ctypes.data, used.ctypes.data, SEED, gid, 200, ARENA.ctypes.data, ARENA.nbytes,
+                              OUT.ctypes.data, OUT.nbytes, ctypes.byref(nb))
+        assert st == 0, (gid, st)
+        tv = TreeView(OUT[:nb.value].copy())
+        most = max(most, int(tv.nodes["know"]["n_hk"].max()))
+        node = M.run_from_root(root, know, used, SEED, gid, 200)
+        assert_same_tree(oracle_preorder(node), tree_preorder(tv), ("busy seer", gid))
+    assert most > 32
+
+
 # ---------------------------------------------------------------- deep MCCFR (config 4)
 def _model():
     import torch
