@@ -28,8 +28,9 @@ def test_v1_blocks_convert_both_ways(name):
     for b in range(len(k)):
         for i in range(int(k["n_hk"][b])):
             f = L.hk_unpack(k["hk"][b][i])
-            o = old[b, 16 + 8 * i:24 + 8 * i]
-            assert f["pid"] == int(np.int8(o[0])) and f["conf"] == o[1] and f["flags"] == o[2] and f["n"] == o[3] and f["off"] == o[4] + 256 * o[5]
+            o = [int(x) for x in old[b, 16 + 8 * i:24 + 8 * i]]
+            pid = o[0] - 256 if o[0] >= 128 else o[0]
+            assert (f["pid"], f["conf"], f["flags"], f["n"], f["off"]) == (pid, o[1], o[2], o[3], o[4] + 256 * o[5])
         assert not k["hk"][b][int(k["n_hk"][b]):].any()
 
 
