@@ -210,7 +210,7 @@ typedef struct ctd_mccfr_result {
                             raises inside its rules code for this root (an exception out of cfr_train).  Engine limits: bit 1 (2)
                             device memory exhausted even after the retries; bit 2 (4) a container outgrew its capacity
                             (csrc/ctd_engine.cuh: hands of 64, cities of 64, museums / just_drawn of 48, 64 hand-knowledge entries in the
-                            searching player's knowledge block; none seen in 84 000 scanned roots of the three rulesets) */
+                            searching player's knowledge block; none seen in 287 000 scanned roots of the three rulesets) */
   uint32_t n_nodes;
   uint32_t iterations;
   uint32_t rng_draws;
